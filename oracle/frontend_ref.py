@@ -1,0 +1,429 @@
+"""CPU oracle for the front end: a restatement of FeatureTracker (control flow
+only) on top of the REAL OpenCV 4.13 (`cv2`).  TEST INFRASTRUCTURE ONLY.
+
+Follows vins_estimator/src/feature_tracker/feature_tracker.{h,cpp} and
+camera_model/src/camera_models/PinholeCamera.cc of the reference:
+
+  readImage               feature_tracker.cpp:263-439
+  initGridsDetector       :33-94
+  inBorder                :96-103
+  gridDetect              :105-171
+  setMask                 :173-208
+  addPoints(KeyPoint&)    :220-233
+  rejectWithF             :441-473
+  updateID                :485-495 (+ loop estimator_nodelet.cpp:324-330)
+  undistortedPoints       :542-593
+  predictPtsInNextFrame   :595-608
+  liftProjective          PinholeCamera.cc:450-510
+  spaceToPlane            PinholeCamera.cc:520-543
+  distortion              PinholeCamera.cc:646-663
+
+All image arithmetic (pyramids, LK, FAST, RANSAC, circles) is executed by
+OpenCV itself through cv2 -- the same library the reference links -- so this
+oracle is the reference's arithmetic with only the glue restated.
+
+Deterministic-semantics decisions (documented in DESIGN.md):
+  * the reference races per-cell FAST (reading `mask`) against addPoints
+    (drawing circles into `mask`); the oracle defines the deterministic
+    semantics "every cell sees the mask snapshot taken right after setMask()"
+    (feature_tracker.cpp:397-409 with all futures finishing before the first
+    addPoints) -- what the reference computes whenever the worker threads win
+    the race.
+  * std::sort tie order: taken from the real libstdc++ std::sort through
+    oracle/stdsort.cpp.
+  * PUB_THIS_FRAME (a global in the reference) is an explicit argument.
+  * LK maxLevel: reference hard-codes 1 (IMU) / 3 (no IMU); `lk_max_level`
+    overrides it when the benchmark config asks for 3/4-level pyramids
+    (SURVEY.md section 8d).
+"""
+import ctypes
+import os
+import subprocess
+from dataclasses import dataclass, field
+
+import cv2
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SORT_SO = os.path.join(_HERE, "_build", "libstdsort.so")
+_sort_lib = None
+
+
+def build_stdsort():
+    os.makedirs(os.path.dirname(_SORT_SO), exist_ok=True)
+    src = os.path.join(_HERE, "stdsort.cpp")
+    if (not os.path.exists(_SORT_SO)) or os.path.getmtime(_SORT_SO) < os.path.getmtime(src):
+        subprocess.check_call(["g++", "-O2", "-shared", "-fPIC", "-o", _SORT_SO, src])
+    return _SORT_SO
+
+
+def stdsort_desc_perm(cnt):
+    """Permutation produced by the reference's std::sort (descending count)."""
+    global _sort_lib
+    if _sort_lib is None:
+        _sort_lib = ctypes.CDLL(build_stdsort())
+        _sort_lib.oracle_stdsort_desc_by_cnt.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
+    c = np.ascontiguousarray(cnt, dtype=np.int32)
+    out = np.zeros(len(c), np.int32)
+    if len(c):
+        _sort_lib.oracle_stdsort_desc_by_cnt(c.ctypes.data, len(c), out.ctypes.data)
+    return out
+
+
+def cv_round(v):
+    """cvRound: round half to even (SSE cvtss2si) -- what Point2f->Point does."""
+    return int(np.rint(v))
+
+
+@dataclass
+class FrontendConfig:
+    row: int = 480
+    col: int = 640
+    max_cnt: int = 150
+    min_dist: int = 25
+    f_threshold: float = 1.0
+    num_grid_rows: int = 7
+    num_grid_cols: int = 8
+    use_imu: int = 1
+    focal_length: float = 460.0     # parameters.h:11
+    fx: float = 600.0
+    fy: float = 600.0
+    cx: float = 320.0
+    cy: float = 240.0
+    k1: float = 0.1
+    k2: float = -0.2
+    p1: float = 1e-3
+    p2: float = 1e-3
+    lk_max_level: int = -1          # -1 => reference default (1 with IMU, 3 without)
+    use_ransac: int = 1             # 0 skips rejectWithF (kernel bring-up only)
+
+
+class PinholeCamera:
+    """PinholeCamera.cc:450-543,646-663 (the three functions on the path)."""
+
+    def __init__(self, cfg):
+        self.fx, self.fy, self.cx, self.cy = cfg.fx, cfg.fy, cfg.cx, cfg.cy
+        self.k1, self.k2, self.p1, self.p2 = cfg.k1, cfg.k2, cfg.p1, cfg.p2
+        self.inv_K11 = 1.0 / cfg.fx
+        self.inv_K13 = -cfg.cx / cfg.fx
+        self.inv_K22 = 1.0 / cfg.fy
+        self.inv_K23 = -cfg.cy / cfg.fy
+        self.no_distortion = (cfg.k1 == 0.0 and cfg.k2 == 0.0 and cfg.p1 == 0.0 and cfg.p2 == 0.0)
+
+    def distortion(self, x, y):
+        k1, k2, p1, p2 = self.k1, self.k2, self.p1, self.p2
+        mx2 = x * x
+        my2 = y * y
+        mxy = x * y
+        rho2 = mx2 + my2
+        rad = k1 * rho2 + k2 * rho2 * rho2
+        return (x * rad + 2.0 * p1 * mxy + p2 * (rho2 + 2.0 * mx2),
+                y * rad + 2.0 * p2 * mxy + p1 * (rho2 + 2.0 * my2))
+
+    def lift_projective(self, u, v):
+        mx_d = self.inv_K11 * u + self.inv_K13
+        my_d = self.inv_K22 * v + self.inv_K23
+        if self.no_distortion:
+            return mx_d, my_d, 1.0
+        dx, dy = self.distortion(mx_d, my_d)
+        mx_u = mx_d - dx
+        my_u = my_d - dy
+        for _ in range(1, 8):
+            dx, dy = self.distortion(mx_u, my_u)
+            mx_u = mx_d - dx
+            my_u = my_d - dy
+        return mx_u, my_u, 1.0
+
+    def space_to_plane(self, X, Y, Z):
+        x = X / Z
+        y = Y / Z
+        if not self.no_distortion:
+            dx, dy = self.distortion(x, y)
+            x = x + dx
+            y = y + dy
+        return self.fx * x + self.cx, self.fy * y + self.cy
+
+
+class FeatureTrackerRef:
+    def __init__(self, cfg: FrontendConfig):
+        self.cfg = cfg
+        self.cam = PinholeCamera(cfg)
+        self.fast = cv2.FastFeatureDetector_create()   # feature_tracker.cpp:29
+        self.n_id = 0
+        self.cur_img = None
+        self.forw_img = None
+        self.cur_pts = np.zeros((0, 2), np.float32)
+        self.forw_pts = np.zeros((0, 2), np.float32)
+        self.predict_pts = np.zeros((0, 2), np.float32)
+        self.unstable_pts = np.zeros((0, 2), np.float32)
+        self.cur_un_pts = np.zeros((0, 2), np.float32)
+        self.prev_un_pts = np.zeros((0, 2), np.float32)
+        self.pts_velocity = np.zeros((0, 2), np.float32)
+        self.ids = []
+        self.track_cnt = []
+        self.cur_un_pts_map = {}
+        self.prev_un_pts_map = {}
+        self.cur_time = 0.0
+        self.prev_time = 0.0
+        self.mask = None
+        self.last_status = None
+        self.last_ransac_status = None
+        self.last_new_keypoints = []
+        self.init_grids_detector()
+
+    # feature_tracker.cpp:33-94
+    def init_grids_detector(self):
+        c = self.cfg
+        ROW, COL = float(c.row), float(c.col)
+        R, C = c.num_grid_rows, c.num_grid_cols
+        gh = int(ROW / R)
+        gw = int(COL / C)
+        grh = int(ROW - (R - 1) * gh)
+        grw = int(COL - (C - 1) * gw)
+        self.grid_height, self.grid_width = gh, gw
+        rects = []
+        for i in range(R):
+            for j in range(C):
+                if j == 0:
+                    x, w = 0, gw + 3
+                elif j < C - 1:
+                    x, w = j * gw - 3, gw + 6
+                else:
+                    x, w = j * gw - 3, grw + 3
+                if i == 0:
+                    y, h = 0, gh + 3
+                elif i < R - 1:
+                    y, h = i * gh - 3, gh + 6
+                else:
+                    y, h = i * gh - 3, grh + 3
+                rects.append((x, y, w, h))
+        self.grids_rect = rects
+        self.grids_track_num = [0] * len(rects)
+        self.grids_texture_status = [True] * len(rects)
+        self.grids_threshold = int(c.max_cnt / len(rects))
+        assert self.grids_threshold > 0
+
+    # feature_tracker.cpp:96-103
+    def in_border(self, pt):
+        x = cv_round(pt[0])
+        y = cv_round(pt[1])
+        return 1 <= x < self.cfg.col - 1 and 1 <= y < self.cfg.row - 1
+
+    # feature_tracker.cpp:595-608
+    def predict_pts_in_next_frame(self, R):
+        out = np.zeros((len(self.cur_pts), 2), np.float32)
+        for i, p in enumerate(self.cur_pts):
+            x, y, z = self.cam.lift_projective(float(p[0]), float(p[1]))
+            P = R @ np.array([x, y, z], np.float64)
+            u, v = self.cam.space_to_plane(P[0], P[1], P[2])
+            out[i, 0] = u
+            out[i, 1] = v
+        self.predict_pts = out
+
+    # feature_tracker.cpp:105-171 (deterministic mask-snapshot semantics)
+    def grid_detect(self, grid_id, mask_snapshot):
+        x, y, w, h = self.grids_rect[grid_id]
+        kps = self.fast.detect(self.forw_img[y:y + h, x:x + w], mask_snapshot[y:y + h, x:x + w])
+        kps = [(k.pt[0], k.pt[1], k.response) for k in kps]
+        if not kps:
+            self.grids_texture_status[grid_id] = False
+            return []
+        num_to_add = self.grids_threshold - self.grids_track_num[grid_id] + 2
+        if len(kps) <= num_to_add:
+            return [(np.float32(px + x), np.float32(py + y), r) for (px, py, r) in kps]
+        slots = [None] * num_to_add
+        K = num_to_add
+        min_id = 0
+        for j, (px, py, r) in enumerate(kps):
+            if num_to_add > 0:
+                slots[j] = (np.float32(px + x), np.float32(py + y), r)
+                num_to_add -= 1
+                if r < slots[min_id][2]:
+                    min_id = j
+            elif r > slots[min_id][2]:
+                slots[min_id] = (np.float32(px + x), np.float32(py + y), r)
+                for k in range(K):
+                    if slots[k][2] < slots[min_id][2]:
+                        min_id = k
+        return slots
+
+    # feature_tracker.cpp:173-208
+    def set_mask(self):
+        c = self.cfg
+        self.mask = np.full((c.row, c.col), 255, np.uint8)
+        perm = stdsort_desc_perm(self.track_cnt)
+        pts, ids, cnt = [], [], []
+        for k in perm:
+            p = self.forw_pts[k]
+            px, py = cv_round(p[0]), cv_round(p[1])
+            if self.mask[py, px] == 255:
+                pts.append(p)
+                ids.append(self.ids[k])
+                cnt.append(self.track_cnt[k])
+                cv2.circle(self.mask, (px, py), c.min_dist, 0, -1)
+        self.forw_pts = np.array(pts, np.float32).reshape(-1, 2)
+        self.ids = ids
+        self.track_cnt = cnt
+        for p in self.unstable_pts:
+            cv2.circle(self.mask, (cv_round(p[0]), cv_round(p[1])), c.min_dist, 0, -1)
+
+    # feature_tracker.cpp:220-233
+    def add_points(self, kps):
+        c = self.cfg
+        add = []
+        for (px, py, r) in kps:
+            ix, iy = cv_round(px), cv_round(py)
+            if self.mask[iy, ix] == 255:
+                add.append((px, py))
+                self.ids.append(-1)
+                self.track_cnt.append(1)
+                cv2.circle(self.mask, (ix, iy), c.min_dist, 0, -1)
+        if add:
+            self.forw_pts = np.concatenate([self.forw_pts.reshape(-1, 2), np.array(add, np.float32)], 0)
+
+    def _reduce(self, status):
+        keep = np.asarray(status).astype(bool)
+        self.cur_pts = self.cur_pts[keep]
+        self.forw_pts = self.forw_pts[keep]
+        self.ids = [v for v, k in zip(self.ids, keep) if k]
+        self.cur_un_pts = self.cur_un_pts[keep]
+        self.track_cnt = [v for v, k in zip(self.track_cnt, keep) if k]
+
+    # feature_tracker.cpp:441-473
+    def reject_with_f(self):
+        c = self.cfg
+        self.last_ransac_status = None
+        if len(self.forw_pts) >= 8 and c.use_ransac:
+            n = len(self.cur_pts)
+            un_cur = np.zeros((n, 2), np.float32)
+            un_forw = np.zeros((n, 2), np.float32)
+            for i in range(n):
+                x, y, z = self.cam.lift_projective(float(self.cur_pts[i, 0]), float(self.cur_pts[i, 1]))
+                un_cur[i] = (c.focal_length * x / z + c.col / 2.0, c.focal_length * y / z + c.row / 2.0)
+                x, y, z = self.cam.lift_projective(float(self.forw_pts[i, 0]), float(self.forw_pts[i, 1]))
+                un_forw[i] = (c.focal_length * x / z + c.col / 2.0, c.focal_length * y / z + c.row / 2.0)
+            self.last_un_cur, self.last_un_forw = un_cur, un_forw
+            _, status = cv2.findFundamentalMat(un_cur, un_forw, cv2.FM_RANSAC, c.f_threshold, 0.99)
+            if status is None:
+                status = np.zeros((n, 1), np.uint8)   # C++: empty status => reduceVector drops all
+            status = status.ravel()
+            self.last_ransac_status = status.copy()
+            self._reduce(status)
+
+    # feature_tracker.cpp:542-593
+    def undistorted_points(self):
+        n = len(self.cur_pts)
+        self.cur_un_pts = np.zeros((n, 2), np.float32)
+        self.cur_un_pts_map = {}
+        for i in range(n):
+            x, y, z = self.cam.lift_projective(float(self.cur_pts[i, 0]), float(self.cur_pts[i, 1]))
+            v = (np.float32(x / z), np.float32(y / z))
+            self.cur_un_pts[i] = v
+            if self.ids[i] not in self.cur_un_pts_map:     # std::map::insert keeps the first
+                self.cur_un_pts_map[self.ids[i]] = v
+        vel = np.zeros((n, 2), np.float32)
+        if self.prev_un_pts_map:
+            dt = self.cur_time - self.prev_time
+            for i in range(n):
+                if self.ids[i] != -1 and self.ids[i] in self.prev_un_pts_map:
+                    pv = self.prev_un_pts_map[self.ids[i]]
+                    vel[i, 0] = np.float32(np.float64(np.float32(self.cur_un_pts[i, 0] - pv[0])) / dt)
+                    vel[i, 1] = np.float32(np.float64(np.float32(self.cur_un_pts[i, 1] - pv[1])) / dt)
+        self.pts_velocity = vel
+        self.prev_un_pts_map = dict(self.cur_un_pts_map)
+
+    # feature_tracker.cpp:485-495 + estimator_nodelet.cpp:324-330
+    def update_ids(self):
+        for i in range(len(self.ids)):
+            if self.ids[i] == -1:
+                self.ids[i] = self.n_id
+                self.n_id += 1
+
+    # feature_tracker.cpp:263-439
+    def read_image(self, img, cur_time, relative_R=None, pub_this_frame=True):
+        c = self.cfg
+        if relative_R is None:
+            relative_R = np.eye(3)
+        self.cur_time = cur_time
+        img = np.ascontiguousarray(img)
+        if self.forw_img is None:
+            self.cur_img = self.forw_img = img
+        else:
+            self.forw_img = img
+        self.forw_pts = np.zeros((0, 2), np.float32)
+        self.unstable_pts = np.zeros((0, 2), np.float32)
+        self.last_status = None
+        self.last_lk_pts = None
+        if len(self.cur_pts):
+            crit = (cv2.TERM_CRITERIA_COUNT + cv2.TERM_CRITERIA_EPS, 30, 0.01)
+            if c.use_imu:
+                self.predict_pts_in_next_frame(relative_R)
+                ml = 1 if c.lk_max_level < 0 else c.lk_max_level
+                fp, status, _ = cv2.calcOpticalFlowPyrLK(
+                    self.cur_img, self.forw_img, self.cur_pts, self.predict_pts.copy(),
+                    winSize=(21, 21), maxLevel=ml, criteria=crit, flags=cv2.OPTFLOW_USE_INITIAL_FLOW)
+            else:
+                ml = 3 if c.lk_max_level < 0 else c.lk_max_level
+                fp, status, _ = cv2.calcOpticalFlowPyrLK(
+                    self.cur_img, self.forw_img, self.cur_pts, None, winSize=(21, 21), maxLevel=ml)
+            self.forw_pts = fp.reshape(-1, 2).astype(np.float32)
+            status = status.ravel().copy()
+            self.last_lk_pts = self.forw_pts.copy()
+            self.last_lk_status = status.copy()
+            unstable = []
+            for i in range(len(self.forw_pts)):
+                ib = self.in_border(self.forw_pts[i])
+                if not status[i] and ib:
+                    unstable.append(self.forw_pts[i])
+                elif status[i] and not ib:
+                    status[i] = 0
+            self.unstable_pts = np.array(unstable, np.float32).reshape(-1, 2)
+            self.last_status = status.copy()
+            self._reduce(status)
+        self.track_cnt = [n + 1 for n in self.track_cnt]
+        self.last_new_keypoints = []
+        self.last_grids_id = []
+        if pub_this_frame:
+            self.reject_with_f()
+            self.set_mask()
+            n_max_cnt = c.max_cnt - len(self.forw_pts)
+            if n_max_cnt > 0:
+                R, C = c.num_grid_rows, c.num_grid_cols
+                self.grids_track_num = [0] * (R * C)
+                for p in self.forw_pts:
+                    col_id = int(p[0]) // self.grid_width
+                    row_id = int(p[1]) // self.grid_height
+                    if col_id == C:
+                        col_id -= 1
+                    if row_id == R:
+                        row_id -= 1
+                    self.grids_track_num[col_id + C * row_id] += 1
+                grids_id = []
+                for i in range(R * C):
+                    if self.grids_track_num[i] < self.grids_threshold and self.grids_texture_status[i]:
+                        grids_id.append(i)
+                    else:
+                        self.grids_texture_status[i] = True
+                self.last_grids_id = grids_id
+                snapshot = self.mask.copy()
+                per_cell = [self.grid_detect(g, snapshot) for g in grids_id]
+                for kps in per_cell:
+                    self.last_new_keypoints.append(kps)
+                    self.add_points(kps)
+        self.prev_un_pts = self.cur_un_pts
+        self.cur_img = self.forw_img
+        self.cur_pts = self.forw_pts
+        self.undistorted_points()
+        self.prev_time = self.cur_time
+        # nodelet: update all ids right after readImage (estimator_nodelet.cpp:324-330)
+        self.update_ids()
+
+    def feature_map(self):
+        """estimator_nodelet.cpp:336-363: {id: [x,y,1,u,v,vx,vy]} for track_cnt>1."""
+        out = {}
+        for j, fid in enumerate(self.ids):
+            if self.track_cnt[j] > 1:
+                out[fid] = np.array([self.cur_un_pts[j, 0], self.cur_un_pts[j, 1], 1.0,
+                                     self.cur_pts[j, 0], self.cur_pts[j, 1],
+                                     self.pts_velocity[j, 0], self.pts_velocity[j, 1]], np.float64)
+        return out
