@@ -1,0 +1,186 @@
+/*
+ * vrf.h -- C ABI of the B200-native VINS-RGBD-FAST hot path.
+ *
+ * The reference (jianhengLiu/VINS-RGBD-FAST) has no FFI seam inside its hot
+ * path: the seams are the C++ class surfaces `FeatureTracker`
+ * (vins_estimator/src/feature_tracker/feature_tracker.h:31-97) and `Estimator`
+ * (vins_estimator/src/estimator/estimator.h:35-202).  This header is the plain-C
+ * boundary placed directly underneath those classes: every entry point names
+ * the reference member function(s) it replaces.  Host shims that keep the
+ * reference's class/member names live in vins-rgbd-fast_b200/host/, and
+ * INTEGRATION.md shows the glue a maintainer adds to vins_estimator.
+ *
+ * Conventions
+ *   - plain pointers + sizes, no C++/torch types; all structs are POD.
+ *   - the caller owns every host buffer for the duration of a call; the
+ *     library owns all device memory and all per-sequence persistent state
+ *     (previous pyramid, tracks, ids, marginalization prior) inside the handle.
+ *   - return value: 0 = VRF_OK, <0 = hard error (bad argument, CUDA failure),
+ *     >0 = soft numerical status (reference: Ceres failures are ignored and
+ *     recovery happens in Estimator::failureDetection, estimator.cpp:1113-1159).
+ *   - one handle drives `n_seq` independent RGB-D+IMU sequences on one GPU
+ *     (the reference: one Estimator object per sequence); a sequence is not
+ *     re-entrant, distinct sequences are batched into the same kernel launches.
+ *   - there is NO CPU fallback: without a CUDA device vrf_create() fails.
+ */
+#ifndef VRF_H_
+#define VRF_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VRF_OK                 0
+#define VRF_ERR_ARG           (-1)
+#define VRF_ERR_CUDA          (-2)
+#define VRF_ERR_UNSUPPORTED   (-3)
+#define VRF_ERR_CAPACITY      (-4)
+#define VRF_ERR_NO_DEVICE     (-5)
+#define VRF_SOFT_NONFINITE      1   /* non-finite state after a solve */
+#define VRF_SOFT_NOT_SPD        2   /* reduced system not SPD even after regularisation */
+
+#define VRF_WINDOW_SIZE        10   /* parameters.h:12  WINDOW_SIZE */
+#define VRF_NUM_FRAMES         11   /* WINDOW_SIZE + 1 */
+#define VRF_MAX_FEATURES     1000   /* parameters.h:14  NUM_OF_F */
+#define VRF_TRACK_CAP        1024   /* per-sequence capacity of the track arrays */
+
+typedef struct vrf_handle vrf_handle;
+
+/* Image payload formats accepted by the tracker entry points. */
+#define VRF_FMT_GRAY8   0   /* what cv_bridge MONO8 hands to readImage (estimator_nodelet.cpp:292-307) */
+#define VRF_FMT_RGB8    1   /* raw sensor_msgs/Image rgb8 payload; gray = cv::cvtColor RGB2GRAY fixed point */
+
+/*
+ * Configuration: the reference's YAML -> extern globals (utility/parameters.h:17-77,
+ * parameters.cpp:81-243) plus the PINHOLE intrinsics read by
+ * FeatureTracker::readIntrinsicParameter (feature_tracker.cpp:497-501), restated
+ * as one POD struct.
+ */
+typedef struct VrfConfig {
+    /* front end */
+    int32_t row, col;                 /* ROW, COL */
+    int32_t max_cnt;                  /* MAX_CNT */
+    int32_t min_dist;                 /* MIN_DIST */
+    int32_t num_grid_rows, num_grid_cols;
+    int32_t use_imu;                  /* USE_IMU: IMU-predicted LK, maxLevel 1 (else maxLevel 3) */
+    int32_t equalize;                 /* EQUALIZE: must be 0 (CLAHE not on the benchmark path) */
+    int32_t fisheye;                  /* FISHEYE: must be 0 */
+    int32_t lk_max_level;             /* -1 = reference default; else explicit maxLevel (0..3) */
+    int32_t use_ransac;               /* 1 = rejectWithF enabled (reference behaviour) */
+    int32_t reserved0;
+    double  f_threshold;              /* F_THRESHOLD */
+    double  focal_length;             /* FOCAL_LENGTH = 460 (parameters.h:11) */
+    double  fx, fy, cx, cy;           /* projection_parameters */
+    double  k1, k2, p1, p2;           /* distortion_parameters */
+    /* back end */
+    int32_t num_iterations;           /* NUM_ITERATIONS (max_num_iterations) */
+    int32_t estimate_extrinsic;       /* ESTIMATE_EXTRINSIC (0: ex-pose constant) */
+    int32_t estimate_td;              /* ESTIMATE_TD: must be 0 this round (ProjectionTdFactor is SURVEY 8f-1) */
+    int32_t fix_depth;                /* FIX_DEPTH */
+    double  depth_max_dist;           /* DEPTH_MAX_DIST (upper bound 2/DEPTH_MAX_DIST for estimate_flag==2) */
+    double  g_norm;                   /* G = (0,0,g_norm) (parameters.cpp:13,158) */
+    double  acc_n, acc_w, gyr_n, gyr_w; /* IMU noise (IntegrationBase ctor, integration_base.h:24-31) */
+} VrfConfig;
+
+/* Fills `cfg` with the synthetic-benchmark defaults of SURVEY.md section 8(d). */
+void vrf_config_default(VrfConfig *cfg);
+
+/* Replaces: Estimator::setParameter + FeatureTracker ctor + initGridsDetector
+ * (estimator.cpp:15-41, feature_tracker.cpp:27-94) for `n_seq` independent sequences. */
+int  vrf_create(const VrfConfig *cfg, int n_seq, int device, vrf_handle **out);
+void vrf_destroy(vrf_handle *h);
+const char *vrf_strerror(int code);
+/* Last CUDA error string seen by this handle (diagnostics). */
+const char *vrf_last_cuda_error(const vrf_handle *h);
+/* Number of kernel launches issued by this handle so far (bench.py `gpu_launches`). */
+uint64_t vrf_launch_count(const vrf_handle *h);
+/* Replaces: Estimator::clearState() + setParameter() for one sequence
+ * (estimator_nodelet.cpp:255-258; failureDetection reboot estimator.cpp:345-353). */
+int  vrf_reset_sequence(vrf_handle *h, int seq);
+
+/* ------------------------------------------------------------------------- */
+/* Front end                                                                  */
+/* ------------------------------------------------------------------------- */
+
+/*
+ * Per-sequence result of one readImage call: the public members the nodelet
+ * reads after readImage + the updateID loop (estimator_nodelet.cpp:324-343):
+ * cur_pts, cur_un_pts, pts_velocity, ids, track_cnt; plus parity/debug members.
+ * All array pointers are caller-allocated with room for `capacity` features
+ * (use VRF_TRACK_CAP); optional ones may be NULL.
+ */
+typedef struct VrfTrackOut {
+    int32_t  capacity;         /* in */
+    int32_t  n;                /* out: cur_pts.size() */
+    float   *cur_pts;          /* out: 2*n (u,v)          FeatureTracker::cur_pts */
+    float   *cur_un_pts;       /* out: 2*n (x,y)          FeatureTracker::cur_un_pts */
+    float   *pts_velocity;     /* out: 2*n (vx,vy)        FeatureTracker::pts_velocity */
+    int32_t *ids;              /* out: n, after updateID  FeatureTracker::ids */
+    int32_t *track_cnt;        /* out: n                  FeatureTracker::track_cnt */
+    int32_t  n_id;             /* out: FeatureTracker::n_id after the updateID loop */
+    int32_t  n_predict;        /* out: number of LK inputs this frame (predict_pts.size()) */
+    float   *predict_pts;      /* out (optional): 2*n_predict  FeatureTracker::predict_pts */
+    float   *lk_pts;           /* out (optional): 2*n_predict  raw calcOpticalFlowPyrLK output */
+    uint8_t *lk_status;        /* out (optional): n_predict    raw LK status */
+    int32_t *grids_track_num;  /* out (optional): rows*cols    FeatureTracker::grids_track_num */
+    uint8_t *grids_texture_status; /* out (optional): rows*cols */
+    int32_t  n_unstable;       /* out: unstable_pts.size() */
+    int32_t  status;           /* out: per-sequence soft status */
+} VrfTrackOut;
+
+/*
+ * Replaces FeatureTracker::readImage(const cv::Mat&, double, const Matrix3d&)
+ * (feature_tracker.h:36-37, feature_tracker.cpp:263-439) followed by the nodelet's
+ * updateID loop (estimator_nodelet.cpp:324-330).
+ *   img            host pointer, `fmt` payload, `stride` bytes per row
+ *   cur_time       _cur_time
+ *   relative_R     row-major 3x3, cam(prev)->cam(cur) (Estimator::predictMotion,
+ *                  estimator.cpp:1790-1860); NULL = identity
+ *   pub_this_frame the reference's global PUB_THIS_FRAME (parameters.cpp:39),
+ *                  made an explicit argument
+ */
+int vrf_tracker_read_image(vrf_handle *h, int seq, const uint8_t *img, size_t stride, int fmt,
+                           double cur_time, const double *relative_R, int pub_this_frame,
+                           VrfTrackOut *out);
+
+/* Batched form: the same call for `n` distinct sequences in one set of kernel
+ * launches.  imgs[i] are host pointers (pinned memory recommended). */
+int vrf_tracker_read_image_batch(vrf_handle *h, int n, const int32_t *seqs,
+                                 const uint8_t *const *imgs, size_t stride, int fmt,
+                                 const double *cur_times, const double *relative_Rs /* n*9 or NULL */,
+                                 const int32_t *pub_flags, VrfTrackOut *outs);
+
+/* Device-resident form: `d_imgs` is a device pointer to n contiguous frames
+ * (frame i at d_imgs + i*frame_bytes, rows tightly packed) already in HBM.
+ * Enqueues the whole front end on the handle's stream and returns without
+ * synchronising; results are fetched with vrf_tracker_fetch_batch().
+ * If `d_depth` is non-NULL it points to n contiguous 16UC1 depth frames and the
+ * per-feature depth lookup of FeatureManager::addFeatureCheckParallax
+ * (feature_manager.cpp:71-80) is done on device (depth at (int)v,(int)u). */
+int vrf_tracker_enqueue_batch_dev(vrf_handle *h, int n, const int32_t *seqs,
+                                  const uint8_t *d_imgs, int fmt, const uint16_t *d_depth,
+                                  const double *cur_times, const double *relative_Rs,
+                                  const int32_t *pub_flags);
+int vrf_tracker_fetch_batch(vrf_handle *h, int n, const int32_t *seqs, VrfTrackOut *outs);
+/* Blocks until all work enqueued on the handle's stream has finished. */
+int vrf_synchronize(vrf_handle *h);
+/* The CUDA stream (cudaStream_t) the handle launches on, for event timing. */
+void *vrf_stream(vrf_handle *h);
+
+/* Test hooks for the tiny order-dependent host/device-shared routines. */
+/* libstdc++ std::sort restatement used by setMask (feature_tracker.cpp:186-188):
+ * writes the permutation that sorts `cnt` descending with the reference's tie order. */
+void vrf_debug_sort_desc(const int32_t *cnt, int32_t n, int32_t *perm_out);
+
+/* ------------------------------------------------------------------------- */
+/* Back end (declared in vrf_ba.h, included here for convenience)             */
+/* ------------------------------------------------------------------------- */
+#include "vrf_ba.h"
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VRF_H_ */

@@ -1,0 +1,135 @@
+"""GPU parity tests of the front end: the CUDA path called through the C ABI
+(vrf_tracker_read_image*) against the cv2-backed oracle (oracle/frontend_ref.py)
+on identical seeded synthetic frames.
+
+Bars (BASELINE.json north_star): feature IDs, track counts and grid-cell
+occupancy bit-exact; LK status identical; tracked (u,v) within 1e-3 px;
+undistorted points / velocities within float tolerance (1e-6 / 1e-4)."""
+import numpy as np
+import pytest
+
+from oracle.frontend_ref import FeatureTrackerRef, FrontendConfig
+from vrf_b200 import binding, synth
+
+pytestmark = pytest.mark.gpu
+
+PX_TOL = 1e-3       # px, north_star
+UN_TOL = 2e-6       # normalised-plane units (float32 rounding of a double computation)
+
+
+def run_pair(cfg_over, n_frames, seed, pub_every=3, cam=None, ransac=0, rgb=False):
+    cam = cam or synth.CamModel()
+    seq = synth.Sequence(seed, cam)
+    cfg = binding.default_config(row=cam.height, col=cam.width, fx=cam.fx, fy=cam.fy, cx=cam.cx, cy=cam.cy,
+                                 k1=cam.k1, k2=cam.k2, p1=cam.p1, p2=cam.p2, use_ransac=ransac, **cfg_over)
+    h = binding.Handle(cfg, 1, 0)
+    ref = FeatureTrackerRef(FrontendConfig(
+        row=cam.height, col=cam.width, max_cnt=cfg.max_cnt, min_dist=cfg.min_dist, use_imu=cfg.use_imu,
+        num_grid_rows=cfg.num_grid_rows, num_grid_cols=cfg.num_grid_cols, lk_max_level=cfg.lk_max_level,
+        fx=cam.fx, fy=cam.fy, cx=cam.cx, cy=cam.cy, k1=cam.k1, k2=cam.k2, p1=cam.p1, p2=cam.p2,
+        use_ransac=ransac, f_threshold=cfg.f_threshold))
+    for k in range(n_frames):
+        rgbf, gray, _ = seq.frame(k)
+        R = seq.relative_R(k)
+        pub = (k % pub_every == 0)
+        out = h.read_image(0, rgbf if rgb else gray, seq.time(k), R, pub=pub)
+        ref.read_image(gray, seq.time(k), R, pub_this_frame=pub)
+        yield k, out, ref
+    h.close()
+
+
+def check_frame(k, out, ref):
+    if ref.last_lk_pts is not None:
+        assert out.n_predict == len(ref.last_lk_pts), k
+        assert np.abs(out.predict_pts - ref.predict_pts).max() <= 1e-4, k
+        assert np.array_equal(out.lk_status, ref.last_lk_status), (k, np.nonzero(out.lk_status != ref.last_lk_status))
+        ok = ref.last_lk_status.astype(bool)
+        assert np.abs(out.lk_pts[ok] - ref.last_lk_pts[ok]).max() <= PX_TOL, k
+    assert out.n == len(ref.ids), (k, out.n, len(ref.ids))
+    assert np.array_equal(out.ids, np.asarray(ref.ids, np.int32)), k            # bit-exact feature IDs
+    assert np.array_equal(out.track_cnt, np.asarray(ref.track_cnt, np.int32)), k
+    assert out.n_id == ref.n_id, k
+    assert np.abs(out.cur_pts - ref.cur_pts).max() <= PX_TOL, k
+    assert np.abs(out.cur_un_pts - ref.cur_un_pts).max() <= UN_TOL, k
+    assert np.abs(out.pts_velocity - ref.pts_velocity).max() <= 1e-3, k
+    assert np.array_equal(out.grids_track_num, np.asarray(ref.grids_track_num, np.int32)), k   # occupancy
+    assert np.array_equal(out.grids_texture_status.astype(bool), np.asarray(ref.grids_texture_status)), k
+    assert out.n_unstable == len(ref.unstable_pts), k
+
+
+def test_sequence_parity_reference_default():
+    """640x480, 150 feats, IMU-predicted LK maxLevel 1 (reference default), publish every 3rd frame."""
+    n = 0
+    for k, out, ref in run_pair({}, 12, 1234):
+        check_frame(k, out, ref)
+        n += 1
+    assert n == 12
+
+
+def test_sequence_parity_three_level_pyramid():
+    """BASELINE config 2: 3-level pyramid (lk_max_level=2)."""
+    for k, out, ref in run_pair({"lk_max_level": 2}, 8, 77):
+        check_frame(k, out, ref)
+
+
+def test_sequence_parity_no_imu_four_levels():
+    """USE_IMU=0 branch: maxLevel 3, no initial flow (feature_tracker.cpp:309-310)."""
+    for k, out, ref in run_pair({"use_imu": 0}, 7, 5, pub_every=1):
+        check_frame(k, out, ref)
+
+
+def test_rgb_ingest_equals_gray_path():
+    """RGB8 payload: device-side cvtColor(RGB2GRAY) then the same pipeline."""
+    for k, out, ref in run_pair({}, 5, 31, rgb=True):
+        check_frame(k, out, ref)
+
+
+def test_1280x720_500_features():
+    """BASELINE config 4 geometry: 1280x720, 500 feats, 4 levels, min_dist 30."""
+    cam = synth.CamModel(fx=900.0, fy=900.0, cx=640.0, cy=360.0, width=1280, height=720)
+    for k, out, ref in run_pair({"max_cnt": 500, "min_dist": 30, "lk_max_level": 3}, 5, 11, cam=cam):
+        check_frame(k, out, ref)
+
+
+def test_batch_equals_single():
+    """Batched call over 3 independent sequences == three single-sequence calls."""
+    cam = synth.CamModel()
+    cfg = binding.default_config(use_ransac=0)
+    hb = binding.Handle(cfg, 3, 0)
+    hs = [binding.Handle(cfg, 1, 0) for _ in range(3)]
+    seqs = [synth.Sequence(100 + i, cam) for i in range(3)]
+    for k in range(5):
+        imgs = [s.frame(k)[1] for s in seqs]
+        Rs = [s.relative_R(k) for s in seqs]
+        ts = [s.time(k) for s in seqs]
+        pubs = [1 if (k + i) % 2 == 0 else 0 for i in range(3)]
+        outs = hb.read_image_batch([2, 0, 1], [imgs[2], imgs[0], imgs[1]], [ts[2], ts[0], ts[1]],
+                                   [Rs[2], Rs[0], Rs[1]], [pubs[2], pubs[0], pubs[1]])
+        for slot, i in enumerate([2, 0, 1]):
+            single = hs[i].read_image(0, imgs[i], ts[i], Rs[i], pub=pubs[i], debug=False)
+            assert outs[slot].n == single.n
+            assert np.array_equal(outs[slot].ids, single.ids)
+            assert np.array_equal(outs[slot].cur_pts, single.cur_pts)
+            assert np.array_equal(outs[slot].pts_velocity, single.pts_velocity)
+    hb.close()
+    for x in hs:
+        x.close()
+
+
+def test_textureless_and_reset():
+    """Flat frames: no corners -> texture flags drop, n == 0; then reset_sequence restarts ids at 0."""
+    cfg = binding.default_config(use_ransac=0)
+    h = binding.Handle(cfg, 1, 0)
+    flat = np.full((480, 640), 127, np.uint8)
+    out = h.read_image(0, flat, 1.0, None, pub=True)
+    assert out.n == 0 and not out.grids_texture_status.any()
+    seq = synth.Sequence(8)
+    out = h.read_image(0, seq.frame(0)[1], 1.1, None, pub=True)
+    # cells were flagged textureless => this publish frame only re-arms them (feature_tracker.cpp:383-392)
+    assert out.n == 0 and out.grids_texture_status.all()
+    out = h.read_image(0, seq.frame(1)[1], 1.2, None, pub=True)
+    assert out.n > 100
+    h.reset(0)
+    out = h.read_image(0, seq.frame(0)[1], 2.0, None, pub=True)
+    assert out.n > 100 and out.ids.min() == 0 and out.ids.max() == out.n - 1
+    h.close()

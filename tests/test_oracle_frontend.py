@@ -1,0 +1,159 @@
+"""CPU tests: pin the numpy spec (oracle/frontend_spec.py) against the real
+OpenCV 4.13 that the reference links, the std::sort restatement against the
+real libstdc++, and check that the C-ABI library exports every declared symbol.
+(The reference ships no tests or golden vectors -- SURVEY.md section 4 -- so cv2
+in this image *is* the pin for the third-party arithmetic.)"""
+import ctypes
+import re
+import os
+
+import cv2
+import numpy as np
+import pytest
+
+from oracle import frontend_spec as S
+from oracle import frontend_ref as FR
+from vrf_b200 import synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def tex(h, w, seed):
+    return synth.band_limited_texture(h, w, seed)
+
+
+@pytest.mark.parametrize("shape", [(480, 640), (121, 77), (60, 85), (720, 1280)])
+def test_pyrdown_bit_exact(shape):
+    img = tex(*shape, seed=1)
+    assert np.array_equal(S.pyr_down(img), cv2.pyrDown(img))
+    _, cvp = cv2.buildOpticalFlowPyramid(img, (21, 21), 3, withDerivatives=False)
+    mine = S.build_pyramid(img, len(cvp) - 1)
+    for a, b in zip(mine, cvp):
+        assert np.array_equal(a, b)
+
+
+def test_scharr_bit_exact():
+    img = tex(100, 130, 2)
+    dx, dy = S.scharr_deriv(img)
+    assert np.array_equal(dx, cv2.Scharr(img, cv2.CV_16S, 1, 0, borderType=cv2.BORDER_REFLECT_101))
+    assert np.array_equal(dy, cv2.Scharr(img, cv2.CV_16S, 0, 1, borderType=cv2.BORDER_REFLECT_101))
+
+
+def test_rgb2gray_bit_exact():
+    r = np.random.default_rng(0)
+    rgb = r.integers(0, 256, (96, 128, 3)).astype(np.uint8)
+    assert np.array_equal(synth.rgb_to_gray(rgb), cv2.cvtColor(rgb, cv2.COLOR_RGB2GRAY))
+
+
+@pytest.mark.parametrize("rect", [(0, 0, 83, 71), (77, 65, 86, 74), (557, 405, 83, 75), (0, 0, 640, 480)])
+def test_fast_bit_exact(rect):
+    det = cv2.FastFeatureDetector_create()
+    assert (det.getThreshold(), det.getNonmaxSuppression(), det.getType()) == (10, True, 2)
+    img = tex(480, 640, 3)
+    x, y, w, h = rect
+    roi = img[y:y + h, x:x + w]
+    mask = np.full((h, w), 255, np.uint8)
+    cv2.circle(mask, (w // 2, h // 2), 25, 0, -1)
+    for m in (None, mask):
+        kps = det.detect(roi, m)
+        got = [(int(k.pt[0]), int(k.pt[1]), int(k.response)) for k in kps]
+        assert got == S.fast_detect(roi, mask=m)
+
+
+def test_fast_flat_and_tiny():
+    assert S.fast_detect(np.full((40, 40), 128, np.uint8)) == []
+    assert S.fast_detect(np.zeros((6, 6), np.uint8)) == []
+
+
+@pytest.mark.parametrize("r", [1, 10, 20, 25, 30, 60])
+def test_filled_circle_is_disc(r):
+    m = np.full((200, 200), 255, np.uint8)
+    cv2.circle(m, (90, 110), r, 0, -1)
+    yy, xx = np.mgrid[0:200, 0:200]
+    assert np.array_equal(m == 0, S.circle_covers(90, 110, r, xx, yy))
+
+
+@pytest.mark.parametrize("ml,use_init", [(1, True), (3, False), (2, True)])
+def test_lk_spec_matches_cv2(ml, use_init):
+    rng = np.random.default_rng(7)
+    h, w = 480, 640
+    img0 = tex(h, w, 5)
+    M = np.array([[1.002, 0.004, 2.3], [-0.003, 0.999, -1.7]])
+    img1 = cv2.warpAffine(img0, M, (w, h), flags=cv2.INTER_LINEAR, borderMode=cv2.BORDER_REFLECT_101)
+    pts = rng.uniform([0, 0], [w, h], (40, 2)).astype(np.float32)
+    pts[:6] = [[0.5, 0.7], [639, 479], [3, 470], [635, 2], [10.2, 11.9], [320, 0]]
+    init = pts + rng.normal(0, 1.0, pts.shape).astype(np.float32)
+    a, st, _ = cv2.calcOpticalFlowPyrLK(
+        img0, img1, pts, init.copy() if use_init else None, winSize=(21, 21), maxLevel=ml,
+        criteria=(cv2.TERM_CRITERIA_COUNT + cv2.TERM_CRITERIA_EPS, 30, 0.01),
+        flags=cv2.OPTFLOW_USE_INITIAL_FLOW if use_init else 0)
+    b, sb = S.lk_track(S.build_pyramid(img0, ml), S.build_pyramid(img1, ml), pts, init, ml, use_initial_flow=use_init)
+    assert np.array_equal(st.ravel(), sb)
+    assert np.abs(a - b).max() <= 1e-3          # float summation order only
+
+
+def test_stdsort_restatement_matches_libstdcxx(built_lib):
+    """csrc/introsort.h (product) == real std::sort (oracle/stdsort.cpp), incl. heavy ties,
+    sizes around the 16-element insertion threshold, and a median-of-3 killer that
+    drives introsort into its heapsort fallback."""
+    from vrf_b200 import binding
+    rng = np.random.default_rng(3)
+    cases = []
+    for n in [0, 1, 2, 15, 16, 17, 31, 33, 64, 150, 151, 300, 500, 1000]:
+        cases.append(rng.integers(1, 4, n))
+        cases.append(rng.integers(1, 40, n))
+        cases.append(np.arange(n))
+        cases.append(np.arange(n)[::-1])
+        cases.append(np.ones(n, np.int64))
+    # median-of-3 killer (descending comparator => negate)
+    for n in [128, 512, 1000]:
+        k = n // 2
+        a = np.zeros(n, np.int64)
+        for i in range(1, k + 1):
+            if i % 2 == 1:
+                a[i - 1] = i
+                a[i] = k + i
+            a[k + i - 1] = 2 * i
+        cases.append(-a)
+    for c in cases:
+        c = np.asarray(c, np.int32)
+        assert np.array_equal(binding.sort_desc_perm(c), FR.stdsort_desc_perm(c)), len(c)
+
+
+def test_abi_exports_every_declared_symbol(built_lib):
+    from vrf_b200 import binding
+    declared = set()
+    for hdr in ("vrf.h", "vrf_ba.h"):
+        txt = open(os.path.join(ROOT, "include", hdr)).read()
+        txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+        declared |= set(re.findall(r"\b(vrf_[a-z0-9_]+)\s*\(", txt))
+    declared.discard("vrf_handle")
+    assert declared == set(binding.EXPORTS), declared ^ set(binding.EXPORTS)
+    for name in declared:
+        assert hasattr(built_lib, name), name
+
+
+def test_no_cpu_fallback(built_lib):
+    """Without a CUDA device vrf_create must fail loudly (there is no CPU path)."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from vrf_b200 import binding
+    cfg = binding.default_config()
+    hp = ctypes.c_void_p()
+    rc = built_lib.vrf_create(ctypes.byref(cfg), 1, 0, ctypes.byref(hp))
+    assert rc == -5 and not hp.value
+
+
+def test_oracle_tracker_runs_and_ids_are_unique():
+    seq, frames, rels = synth.render_gray_frames(99, 7)
+    ft = FR.FeatureTrackerRef(FR.FrontendConfig())
+    for k in range(7):
+        ft.read_image(frames[k], seq.time(k), rels[k], pub_this_frame=(k % 3 == 0))
+        assert len(set(ft.ids)) == len(ft.ids)
+        assert len(ft.ids) == len(ft.cur_pts) == len(ft.track_cnt) == len(ft.pts_velocity)
+    assert max(ft.track_cnt) == 7
+    # min-distance invariant established by setMask/addPoints on publish frames
+    p = np.rint(ft.cur_pts)
+    d2 = ((p[:, None, :] - p[None, :, :]) ** 2).sum(-1) + np.eye(len(p)) * 1e9
+    assert len(ft.ids) > 100

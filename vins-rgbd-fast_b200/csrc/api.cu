@@ -1,0 +1,367 @@
+// api.cu -- the extern "C" boundary (include/vrf.h): handle lifetime, per-sequence
+// host bookkeeping, and the front-end entry points.  Host code stays thin C++;
+// all arithmetic of the hot path runs in the kernels of frontend_kernels.cu /
+// ransac_kernels.cu / ba_kernels.cu.  There is no CPU fallback.
+#include <new>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "handle.h"
+#include "introsort.h"
+
+using namespace vrf;
+
+#define CK(call)                                                              \
+    do {                                                                      \
+        cudaError_t e__ = (call);                                             \
+        if (e__ != cudaSuccess) {                                             \
+            snprintf(h->errbuf, sizeof(h->errbuf), "%s:%d %s", __FILE__, __LINE__, cudaGetErrorString(e__)); \
+            return VRF_ERR_CUDA;                                              \
+        }                                                                     \
+    } while (0)
+
+template <class T>
+static cudaError_t dmalloc(T **p, size_t n)
+{
+    cudaError_t e = cudaMalloc((void **)p, n * sizeof(T));
+    if (e == cudaSuccess) e = cudaMemset(*p, 0, n * sizeof(T));
+    return e;
+}
+
+extern "C" void vrf_config_default(VrfConfig *c)
+{
+    memset(c, 0, sizeof(*c));
+    c->row = 480; c->col = 640;
+    c->max_cnt = 150; c->min_dist = 25;
+    c->num_grid_rows = 7; c->num_grid_cols = 8;
+    c->use_imu = 1; c->equalize = 0; c->fisheye = 0;
+    c->lk_max_level = -1; c->use_ransac = 1;
+    c->f_threshold = 1.0; c->focal_length = 460.0;
+    c->fx = 600.0; c->fy = 600.0; c->cx = 320.0; c->cy = 240.0;
+    c->k1 = 0.1; c->k2 = -0.2; c->p1 = 1e-3; c->p2 = 1e-3;
+    c->num_iterations = 8; c->estimate_extrinsic = 0; c->estimate_td = 0; c->fix_depth = 0;
+    c->depth_max_dist = 10.0; c->g_norm = 9.81;
+    c->acc_n = 0.1; c->acc_w = 0.001; c->gyr_n = 0.01; c->gyr_w = 0.0001;
+}
+
+extern "C" const char *vrf_strerror(int code)
+{
+    switch (code) {
+    case VRF_OK: return "ok";
+    case VRF_ERR_ARG: return "invalid argument";
+    case VRF_ERR_CUDA: return "CUDA error (see vrf_last_cuda_error)";
+    case VRF_ERR_UNSUPPORTED: return "configuration not supported by this build";
+    case VRF_ERR_CAPACITY: return "per-sequence feature capacity exceeded";
+    case VRF_ERR_NO_DEVICE: return "no CUDA device available (the library has no CPU fallback)";
+    case VRF_SOFT_NONFINITE: return "non-finite state after solve";
+    case VRF_SOFT_NOT_SPD: return "reduced system not SPD";
+    default: return "unknown vrf status";
+    }
+}
+
+extern "C" const char *vrf_last_cuda_error(const vrf_handle *h) { return h ? h->errbuf : ""; }
+extern "C" uint64_t vrf_launch_count(const vrf_handle *h) { return h ? h->launches : 0; }
+extern "C" void *vrf_stream(vrf_handle *h) { return h ? (void *)h->stream : nullptr; }
+
+extern "C" void vrf_debug_sort_desc(const int32_t *cnt, int32_t n, int32_t *perm_out)
+{
+    std::vector<SortItem> v(n > 0 ? n : 0);
+    for (int i = 0; i < n; ++i) { v[i].key = cnt[i]; v[i].val = i; }
+    std_sort_desc(v.data(), n);
+    for (int i = 0; i < n; ++i) perm_out[i] = v[i].val;
+}
+
+static int build_front_cfg(const VrfConfig &cfg, FrontCfg &fc)
+{
+    memset(&fc, 0, sizeof(fc));
+    if (cfg.row < 64 || cfg.col < 64 || (cfg.col & 15)) return VRF_ERR_ARG;   // uint4 row access
+    if (cfg.equalize || cfg.fisheye) return VRF_ERR_UNSUPPORTED;
+    if (cfg.max_cnt <= 0 || cfg.max_cnt > VRF_CAP / 2 || cfg.min_dist < 1) return VRF_ERR_ARG;
+    fc.rows = cfg.row; fc.cols = cfg.col;
+    int maxLevel = cfg.lk_max_level < 0 ? (cfg.use_imu ? 1 : 3) : cfg.lk_max_level;
+    if (maxLevel > VRF_MAX_LEVELS - 1) return VRF_ERR_ARG;
+    fc.levels = maxLevel + 1;
+    fc.max_cnt = cfg.max_cnt; fc.min_dist = cfg.min_dist;
+    fc.grows = cfg.num_grid_rows; fc.gcols = cfg.num_grid_cols;
+    fc.ncells = fc.grows * fc.gcols;
+    if (fc.grows < 1 || fc.gcols < 1 || fc.ncells > VRF_MAX_CELLS) return VRF_ERR_ARG;
+    // initGridsDetector (feature_tracker.cpp:33-94); ROW, COL are doubles in the reference
+    fc.gh = (int)((double)cfg.row / fc.grows);
+    fc.gw = (int)((double)cfg.col / fc.gcols);
+    fc.thr = (int)(cfg.max_cnt / fc.ncells);
+    if (fc.thr <= 0) return VRF_ERR_ARG;       // ROS_ASSERT_MSG(grids_threshold > 0) :89-93
+    if (fc.gh < 8 || fc.gw < 8) return VRF_ERR_ARG;
+    fc.kmax = fc.thr + 2;
+    fc.use_imu = cfg.use_imu; fc.use_ransac = cfg.use_ransac;
+    unsigned off = 0;
+    int w = cfg.col, hh = cfg.row;
+    for (int l = 0; l < fc.levels; ++l) {
+        fc.lw[l] = w; fc.lh[l] = hh; fc.lp[l] = (w + 15) & ~15;
+        fc.loff[l] = off;
+        off += (unsigned)fc.lp[l] * hh;
+        off = (off + 255u) & ~255u;
+        if (w <= 2 * VRF_LK_WIN + 2 || hh <= 2 * VRF_LK_WIN + 2) return VRF_ERR_ARG;  // single reflection only
+        w = (w + 1) / 2; hh = (hh + 1) / 2;
+    }
+    fc.pyr_bytes = off;
+    fc.fx = cfg.fx; fc.fy = cfg.fy; fc.cx = cfg.cx; fc.cy = cfg.cy;
+    fc.k1 = cfg.k1; fc.k2 = cfg.k2; fc.p1 = cfg.p1; fc.p2 = cfg.p2;
+    // PinholeCamera::setParameters (PinholeCamera.cc:292-295,306-310)
+    fc.ik11 = 1.0 / cfg.fx; fc.ik13 = -cfg.cx / cfg.fx;
+    fc.ik22 = 1.0 / cfg.fy; fc.ik23 = -cfg.cy / cfg.fy;
+    fc.nodist = (cfg.k1 == 0.0 && cfg.k2 == 0.0 && cfg.p1 == 0.0 && cfg.p2 == 0.0);
+    fc.focal = cfg.focal_length; fc.f_thr = cfg.f_threshold;
+    return VRF_OK;
+}
+
+extern "C" int vrf_create(const VrfConfig *cfg, int n_seq, int device, vrf_handle **out)
+{
+    if (!cfg || !out || n_seq < 1 || n_seq > VRF_MAX_BATCH) return VRF_ERR_ARG;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return VRF_ERR_NO_DEVICE;
+    if (device < 0 || device >= ndev) return VRF_ERR_ARG;
+    if (cfg->estimate_td) return VRF_ERR_UNSUPPORTED;
+    FrontCfg fc;
+    int rc = build_front_cfg(*cfg, fc);
+    if (rc != VRF_OK) return rc;
+    vrf_handle *h = new (std::nothrow) vrf_handle();
+    if (!h) return VRF_ERR_ARG;
+    h->cfg = *cfg; h->fc = fc; h->n_seq = n_seq; h->device = device;
+    h->errbuf[0] = 0; h->launches = 0;
+    auto fail = [&](int code) { vrf_destroy(h); return code; };
+    if (cudaSetDevice(device) != cudaSuccess) return fail(VRF_ERR_CUDA);
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return fail(VRF_ERR_CUDA);
+    h->sm_count = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) return fail(VRF_ERR_CUDA);
+    const size_t S = n_seq, SC = S * VRF_CAP, SG = S * VRF_MAX_CELLS;
+    FrontDev &d = h->fd;
+    cudaError_t e = cudaSuccess;
+#define A(ptr, n) if (e == cudaSuccess) e = dmalloc(&(ptr), (n))
+    A(d.pyr[0], S * fc.pyr_bytes); A(d.pyr[1], S * fc.pyr_bytes);
+    A(d.cur_pts, SC); A(d.prev_un, SC); A(d.ids, SC); A(d.cnt, SC); A(d.n_pts, S); A(d.n_id, S);
+    A(d.pred_pts, SC); A(d.lk_pts, SC); A(d.lk_status, SC); A(d.n_lk, S);
+    A(d.t_prev, SC); A(d.t_forw, SC); A(d.t_prevun, SC); A(d.t_ids, SC); A(d.t_cnt, SC); A(d.t_n, S); A(d.t_keep, SC);
+    A(d.unstable, SC); A(d.n_unstable, S); A(d.maskpts, 2 * SC); A(d.n_maskpts, S);
+    A(d.grid_cnt, SG); A(d.tex_status, SG); A(d.cell_k, SG);
+    A(d.cand, SG * fc.kmax * 3); A(d.ncand, SG);
+    A(d.o_pts, SC); A(d.o_un, SC); A(d.o_vel, SC); A(d.o_ids, SC); A(d.o_cnt, SC); A(d.out_hdr, S * 8);
+    A(d.work_prefix, VRF_MAX_BATCH + 1);
+    for (int k = 0; k < VRF_CALL_SLOTS; ++k) { A(h->d_calls_ring[k], S); }
+    h->frame_bytes_max = (size_t)cfg->row * cfg->col * 3;
+    A(h->d_stage, S * h->frame_bytes_max);
+#undef A
+    if (e != cudaSuccess) { snprintf(h->errbuf, sizeof(h->errbuf), "alloc: %s", cudaGetErrorString(e)); return fail(VRF_ERR_CUDA); }
+    if (cudaMemset(d.tex_status, 1, SG) != cudaSuccess) return fail(VRF_ERR_CUDA);   // grids_texture_status = true
+    for (int k = 0; k < VRF_CALL_SLOTS; ++k) {
+        if (cudaMallocHost((void **)&h->h_calls_ring[k], S * sizeof(SeqCall)) != cudaSuccess) return fail(VRF_ERR_CUDA);
+        if (cudaEventCreateWithFlags(&h->call_ev[k], cudaEventDisableTiming) != cudaSuccess) return fail(VRF_ERR_CUDA);
+    }
+    if (cudaMallocHost((void **)&h->h_hdr, S * 8 * sizeof(int)) != cudaSuccess) return fail(VRF_ERR_CUDA);
+    const size_t out_elems = SC;
+    if (cudaMallocHost((void **)&h->h_out, out_elems * (3 * sizeof(float2) + 2 * sizeof(int))) != cudaSuccess) return fail(VRF_ERR_CUDA);
+    h->cur_buf.assign(n_seq, 0);
+    h->has_img.assign(n_seq, 0);
+    h->prev_time.assign(n_seq, 0.0);
+    if (front_configure_kernels(fc) != 0) { snprintf(h->errbuf, sizeof(h->errbuf), "kernel attribute setup failed"); return fail(VRF_ERR_CUDA); }
+    rc = ba_create(h);
+    if (rc != VRF_OK) return fail(rc);
+    if (cudaDeviceSynchronize() != cudaSuccess) return fail(VRF_ERR_CUDA);
+    *out = h;
+    return VRF_OK;
+}
+
+extern "C" void vrf_destroy(vrf_handle *h)
+{
+    if (!h) return;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    ba_destroy(h);
+    FrontDev &d = h->fd;
+    void *ptrs[] = {d.pyr[0], d.pyr[1], d.cur_pts, d.prev_un, d.ids, d.cnt, d.n_pts, d.n_id, d.pred_pts, d.lk_pts,
+                    d.lk_status, d.n_lk, d.t_prev, d.t_forw, d.t_prevun, d.t_ids, d.t_cnt, d.t_n, d.t_keep,
+                    d.unstable, d.n_unstable, d.maskpts, d.n_maskpts, d.grid_cnt, d.tex_status, d.cell_k, d.cand,
+                    d.ncand, d.o_pts, d.o_un, d.o_vel, d.o_ids, d.o_cnt, d.out_hdr, d.work_prefix, h->d_stage};
+    for (void *p : ptrs) if (p) cudaFree(p);
+    for (int k = 0; k < VRF_CALL_SLOTS; ++k) {
+        if (h->d_calls_ring[k]) cudaFree(h->d_calls_ring[k]);
+        if (h->h_calls_ring[k]) cudaFreeHost(h->h_calls_ring[k]);
+        if (h->call_ev[k]) cudaEventDestroy(h->call_ev[k]);
+    }
+    if (h->h_hdr) cudaFreeHost(h->h_hdr);
+    if (h->h_out) cudaFreeHost(h->h_out);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+extern "C" int vrf_synchronize(vrf_handle *h)
+{
+    if (!h) return VRF_ERR_ARG;
+    CK(cudaStreamSynchronize(h->stream));
+    return VRF_OK;
+}
+
+extern "C" int vrf_reset_sequence(vrf_handle *h, int seq)
+{
+    if (!h || seq < 0 || seq >= h->n_seq) return VRF_ERR_ARG;
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->stream));
+    FrontDev &d = h->fd;
+    CK(cudaMemset(d.n_pts + seq, 0, sizeof(int)));
+    CK(cudaMemset(d.n_id + seq, 0, sizeof(int)));
+    CK(cudaMemset(d.grid_cnt + (size_t)seq * VRF_MAX_CELLS, 0, VRF_MAX_CELLS * sizeof(int)));
+    CK(cudaMemset(d.tex_status + (size_t)seq * VRF_MAX_CELLS, 1, VRF_MAX_CELLS));
+    h->cur_buf[seq] = 0; h->has_img[seq] = 0; h->prev_time[seq] = 0.0;
+    return ba_reset_sequence(h, seq);
+}
+
+// Fill the per-call descriptors, upload them and enqueue every front-end kernel.
+static int enqueue_front(vrf_handle *h, int n, const int32_t *seqs, const uint8_t *d_frames, size_t frame_bytes,
+                         int fmt, const double *times, const double *Rs, const int32_t *pubs)
+{
+    if (n < 1 || n > h->n_seq || !seqs || !times) return VRF_ERR_ARG;
+    if (fmt != VRF_FMT_GRAY8 && fmt != VRF_FMT_RGB8) return VRF_ERR_ARG;
+    std::vector<uint8_t> seen(h->n_seq, 0);
+    int any_pub = 0;
+    const unsigned slot = h->call_ctr++ % VRF_CALL_SLOTS;
+    CK(cudaEventSynchronize(h->call_ev[slot]));     // slot free again?
+    h->h_calls = h->h_calls_ring[slot];
+    h->d_calls = h->d_calls_ring[slot];
+    for (int i = 0; i < n; ++i) {
+        int s = seqs[i];
+        if (s < 0 || s >= h->n_seq || seen[s]) return VRF_ERR_ARG;
+        seen[s] = 1;
+        SeqCall &c = h->h_calls[i];
+        c.seq = s;
+        c.pub = pubs ? (pubs[i] != 0) : 1;
+        any_pub |= c.pub;
+        c.first = h->has_img[s] ? 0 : 1;
+        // cur_img lives in buffer cur_buf; forw_img goes to the other one
+        // (first frame: cur_img = forw_img = img, feature_tracker.cpp:279-287)
+        c.buf_prev = h->cur_buf[s];
+        c.buf_cur = c.first ? h->cur_buf[s] : 1 - h->cur_buf[s];
+        c.pad = 0;
+        c.dt = times[i] - h->prev_time[s];
+        for (int k = 0; k < 9; ++k) c.R[k] = Rs ? Rs[(size_t)i * 9 + k] : ((k % 4 == 0) ? 1.0 : 0.0);
+    }
+    CK(cudaMemcpyAsync(h->d_calls, h->h_calls, n * sizeof(SeqCall), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaEventRecord(h->call_ev[slot], h->stream));
+    front_launch(h->fc, h->d_calls, n, h->fd, d_frames, frame_bytes, fmt, any_pub, h->sm_count, h->stream, &h->launches);
+    if (h->fc.use_ransac && any_pub) ransac_launch(h->fc, h->d_calls, n, h->fd, h->stream, &h->launches);
+    front_launch_tail(h->fc, h->d_calls, n, h->fd, any_pub, h->stream, &h->launches);
+    CK(cudaGetLastError());
+    for (int i = 0; i < n; ++i) {
+        int s = seqs[i];
+        h->cur_buf[s] = h->h_calls[i].buf_cur;     // cur_img = forw_img
+        h->has_img[s] = 1;
+        h->prev_time[s] = times[i];
+    }
+    h->last_n = n;
+    return VRF_OK;
+}
+
+// Two-phase copy-out: headers first (n per item), then only the used prefix of
+// each output array with one strided copy per array.
+static int fetch_front(vrf_handle *h, int n, const int32_t *seqs, VrfTrackOut *outs)
+{
+    if (!outs || n < 1 || n > h->n_seq) return VRF_ERR_ARG;
+    FrontDev &d = h->fd;
+    CK(cudaMemcpyAsync(h->h_hdr, d.out_hdr, (size_t)n * 8 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    int maxn = 0;
+    for (int i = 0; i < n; ++i) maxn = h->h_hdr[i * 8] > maxn ? h->h_hdr[i * 8] : maxn;
+    if (maxn > VRF_CAP) maxn = VRF_CAP;
+    // host staging layout: 5 arrays of [n][maxn]
+    char *hp = (char *)h->h_out;
+    float2 *h_pts = (float2 *)hp; hp += (size_t)n * maxn * sizeof(float2);
+    float2 *h_un = (float2 *)hp; hp += (size_t)n * maxn * sizeof(float2);
+    float2 *h_vel = (float2 *)hp; hp += (size_t)n * maxn * sizeof(float2);
+    int *h_ids = (int *)hp; hp += (size_t)n * maxn * sizeof(int);
+    int *h_cnt = (int *)hp;
+    if (maxn > 0) {
+        CK(cudaMemcpy2DAsync(h_pts, maxn * sizeof(float2), d.o_pts, VRF_CAP * sizeof(float2), maxn * sizeof(float2), n, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaMemcpy2DAsync(h_un, maxn * sizeof(float2), d.o_un, VRF_CAP * sizeof(float2), maxn * sizeof(float2), n, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaMemcpy2DAsync(h_vel, maxn * sizeof(float2), d.o_vel, VRF_CAP * sizeof(float2), maxn * sizeof(float2), n, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaMemcpy2DAsync(h_ids, maxn * sizeof(int), d.o_ids, VRF_CAP * sizeof(int), maxn * sizeof(int), n, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaMemcpy2DAsync(h_cnt, maxn * sizeof(int), d.o_cnt, VRF_CAP * sizeof(int), maxn * sizeof(int), n, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+    }
+    int worst = VRF_OK;
+    for (int i = 0; i < n; ++i) {
+        VrfTrackOut &o = outs[i];
+        const int *hdr = h->h_hdr + i * 8;
+        const int s = seqs[i];
+        o.n = hdr[0]; o.n_id = hdr[1]; o.n_predict = hdr[2]; o.n_unstable = hdr[3]; o.status = hdr[4];
+        if (o.status != 0) worst = o.status;
+        int m = o.n < o.capacity ? o.n : o.capacity;
+        if (o.n > o.capacity) { o.status = VRF_ERR_CAPACITY; worst = VRF_ERR_CAPACITY; }
+        if (o.cur_pts) memcpy(o.cur_pts, h_pts + (size_t)i * maxn, m * sizeof(float2));
+        if (o.cur_un_pts) memcpy(o.cur_un_pts, h_un + (size_t)i * maxn, m * sizeof(float2));
+        if (o.pts_velocity) memcpy(o.pts_velocity, h_vel + (size_t)i * maxn, m * sizeof(float2));
+        if (o.ids) memcpy(o.ids, h_ids + (size_t)i * maxn, m * sizeof(int));
+        if (o.track_cnt) memcpy(o.track_cnt, h_cnt + (size_t)i * maxn, m * sizeof(int));
+        // optional parity/debug members (per-sequence copies; not on the fast path)
+        int np = o.n_predict < o.capacity ? o.n_predict : o.capacity;
+        if (o.predict_pts && np > 0) CK(cudaMemcpy(o.predict_pts, d.pred_pts + (size_t)s * VRF_CAP, np * sizeof(float2), cudaMemcpyDeviceToHost));
+        if (o.lk_pts && np > 0) CK(cudaMemcpy(o.lk_pts, d.lk_pts + (size_t)s * VRF_CAP, np * sizeof(float2), cudaMemcpyDeviceToHost));
+        if (o.lk_status && np > 0) CK(cudaMemcpy(o.lk_status, d.lk_status + (size_t)s * VRF_CAP, np, cudaMemcpyDeviceToHost));
+        if (o.grids_track_num) CK(cudaMemcpy(o.grids_track_num, d.grid_cnt + (size_t)s * VRF_MAX_CELLS, h->fc.ncells * sizeof(int), cudaMemcpyDeviceToHost));
+        if (o.grids_texture_status) CK(cudaMemcpy(o.grids_texture_status, d.tex_status + (size_t)s * VRF_MAX_CELLS, h->fc.ncells, cudaMemcpyDeviceToHost));
+    }
+    return worst;
+}
+
+extern "C" int vrf_tracker_read_image_batch(vrf_handle *h, int n, const int32_t *seqs, const uint8_t *const *imgs,
+                                            size_t stride, int fmt, const double *cur_times,
+                                            const double *relative_Rs, const int32_t *pub_flags, VrfTrackOut *outs)
+{
+    if (!h || !imgs || !outs) return VRF_ERR_ARG;
+    if (n < 1 || n > h->n_seq) return VRF_ERR_ARG;
+    CK(cudaSetDevice(h->device));
+    const int bpp = (fmt == VRF_FMT_RGB8) ? 3 : 1;
+    const size_t row_bytes = (size_t)h->cfg.col * bpp;
+    const size_t frame_bytes = row_bytes * h->cfg.row;
+    if (stride == 0) stride = row_bytes;
+    if (stride < row_bytes) return VRF_ERR_ARG;
+    for (int i = 0; i < n; ++i) {
+        if (!imgs[i]) return VRF_ERR_ARG;
+        if (stride == row_bytes)
+            CK(cudaMemcpyAsync(h->d_stage + (size_t)i * frame_bytes, imgs[i], frame_bytes, cudaMemcpyHostToDevice, h->stream));
+        else
+            CK(cudaMemcpy2DAsync(h->d_stage + (size_t)i * frame_bytes, row_bytes, imgs[i], stride, row_bytes, h->cfg.row, cudaMemcpyHostToDevice, h->stream));
+    }
+    int rc = enqueue_front(h, n, seqs, h->d_stage, frame_bytes, fmt, cur_times, relative_Rs, pub_flags);
+    if (rc != VRF_OK) return rc;
+    return fetch_front(h, n, seqs, outs);
+}
+
+extern "C" int vrf_tracker_read_image(vrf_handle *h, int seq, const uint8_t *img, size_t stride, int fmt,
+                                      double cur_time, const double *relative_R, int pub_this_frame, VrfTrackOut *out)
+{
+    int32_t s = seq, p = pub_this_frame;
+    const uint8_t *imgs[1] = {img};
+    return vrf_tracker_read_image_batch(h, 1, &s, imgs, stride, fmt, &cur_time, relative_R, &p, out);
+}
+
+extern "C" int vrf_tracker_enqueue_batch_dev(vrf_handle *h, int n, const int32_t *seqs, const uint8_t *d_imgs, int fmt,
+                                             const uint16_t *d_depth, const double *cur_times,
+                                             const double *relative_Rs, const int32_t *pub_flags)
+{
+    if (!h || !d_imgs) return VRF_ERR_ARG;
+    (void)d_depth;
+    CK(cudaSetDevice(h->device));
+    const int bpp = (fmt == VRF_FMT_RGB8) ? 3 : 1;
+    const size_t frame_bytes = (size_t)h->cfg.col * bpp * h->cfg.row;
+    if (((uintptr_t)d_imgs & 15) != 0) return VRF_ERR_ARG;
+    return enqueue_front(h, n, seqs, d_imgs, frame_bytes, fmt, cur_times, relative_Rs, pub_flags);
+}
+
+extern "C" int vrf_tracker_fetch_batch(vrf_handle *h, int n, const int32_t *seqs, VrfTrackOut *outs)
+{
+    if (!h || !seqs) return VRF_ERR_ARG;
+    CK(cudaSetDevice(h->device));
+    if (n != h->last_n) return VRF_ERR_ARG;
+    return fetch_front(h, n, seqs, outs);
+}

@@ -1,0 +1,922 @@
+// frontend_kernels.cu -- hand-written sm_100a kernels for the per-frame front end
+// (FeatureTracker::readImage, reference vins_estimator/src/feature_tracker/
+// feature_tracker.cpp:263-439).  Compiled with -fmad=false so that float/double
+// expressions round exactly like the reference's x86 (no-FMA) build.
+//
+// Kernel sequence for one batched readImage call (all sequences of the batch in
+// each launch; no host round trip in between):
+//   k_ingest        frame (GRAY8 | RGB8) -> pyramid level 0 of the "forw" buffer
+//                   (+ work-list prefix for k_lk)                 [HBM-bound]
+//   k_pyrdown xL    cv::pyrDown level l -> l+1                    [HBM/L2-bound]
+//   k_lk            predictPtsInNextFrame + cv::calcOpticalFlowPyrLK, one warp / feature
+//   k_post_a        status fix-up, inBorder, reduceVector x5, track_cnt++
+//   k_ransac        rejectWithF (cv::findFundamentalMat RANSAC)   (ransac_kernels.cu)
+//   k_post_b        reduceVector by inliers, setMask (std::sort + greedy circles),
+//                   grid occupancy + cell selection
+//   k_fast          gridDetect: FAST-9/16 + NMS + mask + top-K slots, one CTA / cell
+//   k_finish        addPoints, undistortedPoints (+velocity), updateID, outputs
+#include "common.cuh"
+#include "introsort.h"
+
+namespace vrf {
+
+// ---------------------------------------------------------------------------
+// k_ingest: copy / convert the input frame into pyramid level 0.
+// GRAY8: 16 px per thread (uint4 load/store).  RGB8: 16 px per thread =
+// 3 x uint4 coalesced loads, fixed-point cv::cvtColor RGB2GRAY
+// ((R*9798 + G*19235 + B*3735 + 16384) >> 15), one uint4 store.
+// Block (0,0) additionally builds the LK work-list prefix over the batch.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ unsigned gray4(unsigned r0, unsigned g0, unsigned b0)
+{
+    return (r0 * 9798u + g0 * 19235u + b0 * 3735u + 16384u) >> 15;
+}
+
+__global__ void __launch_bounds__(256)
+k_ingest(FrontCfg c, const SeqCall *calls, int ncalls, FrontDev d, const uint8_t *frames,
+         size_t frame_bytes, int fmt)
+{
+    const int ci = blockIdx.y;
+    if (blockIdx.x == 0 && ci == 0) {
+        // exclusive prefix of LK work items (n_pts of every sequence of the batch)
+        __shared__ int s_part[256];
+        int t = threadIdx.x;
+        int per = (ncalls + 255) / 256;
+        int b = t * per, e = min(ncalls, b + per);
+        int s = 0;
+        for (int i = b; i < e; ++i) s += calls[i].first ? 0 : d.n_pts[calls[i].seq];
+        s_part[t] = s;
+        __syncthreads();
+        if (t == 0) {
+            int acc = 0;
+            for (int i = 0; i < 256; ++i) { int v = s_part[i]; s_part[i] = acc; acc += v; }
+            d.work_prefix[ncalls] = acc;
+        }
+        __syncthreads();
+        int acc = s_part[t];
+        for (int i = b; i < e; ++i) {
+            d.work_prefix[i] = acc;
+            acc += calls[i].first ? 0 : d.n_pts[calls[i].seq];
+        }
+    }
+    const SeqCall call = calls[ci];
+    uint8_t *dst = d.pyr[call.buf_cur] + (size_t)call.seq * c.pyr_bytes;   // level 0 at offset 0
+    const uint8_t *src = frames + (size_t)ci * frame_bytes;
+    const int groups_per_row = c.cols >> 4;                 // cols % 16 == 0 enforced at create
+    const int total = groups_per_row * c.rows;
+    for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < total; g += gridDim.x * blockDim.x) {
+        int y = g / groups_per_row, xg = g - y * groups_per_row;
+        uint4 out;
+        if (fmt == VRF_FMT_GRAY8) {
+            out = __ldg(reinterpret_cast<const uint4 *>(src + (size_t)y * c.cols) + xg);
+        } else {
+            const uint4 *p = reinterpret_cast<const uint4 *>(src + (size_t)y * c.cols * 3) + xg * 3;
+            uint4 a = __ldg(p), b = __ldg(p + 1), cc = __ldg(p + 2);
+            unsigned w[12] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, cc.x, cc.y, cc.z, cc.w};
+            unsigned o[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                // 4 pixels = 12 bytes = words w[3q..3q+2]
+                unsigned w0 = w[3 * q], w1 = w[3 * q + 1], w2 = w[3 * q + 2];
+                unsigned p0 = gray4(w0 & 255u, (w0 >> 8) & 255u, (w0 >> 16) & 255u);
+                unsigned p1 = gray4(w0 >> 24, w1 & 255u, (w1 >> 8) & 255u);
+                unsigned p2 = gray4((w1 >> 16) & 255u, w1 >> 24, w2 & 255u);
+                unsigned p3 = gray4((w2 >> 8) & 255u, (w2 >> 16) & 255u, w2 >> 24);
+                o[q] = p0 | (p1 << 8) | (p2 << 16) | (p3 << 24);
+            }
+            out = make_uint4(o[0], o[1], o[2], o[3]);
+        }
+        reinterpret_cast<uint4 *>(dst + (size_t)y * c.lp[0])[xg] = out;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// k_pyrdown: cv::pyrDown (5x5 separable [1 4 6 4 1], (sum+128)>>8, REFLECT_101).
+// CTA tile = 64 x 16 outputs; horizontal pass of 35 input rows into shared
+// memory (u16), vertical pass from shared memory.
+// ---------------------------------------------------------------------------
+#define PD_TW 64
+#define PD_TH 16
+__global__ void __launch_bounds__(256)
+k_pyrdown(FrontCfg c, const SeqCall *calls, FrontDev d, int level)
+{
+    __shared__ unsigned short s_h[2 * PD_TH + 3][PD_TW];
+    const SeqCall call = calls[blockIdx.z];
+    const uint8_t *src = d.pyr[call.buf_cur] + (size_t)call.seq * c.pyr_bytes + c.loff[level];
+    uint8_t *dst = d.pyr[call.buf_cur] + (size_t)call.seq * c.pyr_bytes + c.loff[level + 1];
+    const int sw = c.lw[level], sh = c.lh[level], sp = c.lp[level];
+    const int dw = c.lw[level + 1], dh = c.lh[level + 1], dp = c.lp[level + 1];
+    const int ox = blockIdx.x * PD_TW, oy = blockIdx.y * PD_TH;
+    const int nrow = 2 * PD_TH + 3;
+    for (int i = threadIdx.x; i < nrow * PD_TW; i += 256) {
+        int r = i / PD_TW, x = i - r * PD_TW;
+        int sy = reflect101(2 * oy + r - 2, sh);
+        int dx = ox + x;
+        unsigned v = 0;
+        if (dx < dw) {
+            const uint8_t *row = src + (size_t)sy * sp;
+            int cx = 2 * dx;
+            int x0 = reflect101(cx - 2, sw), x1 = reflect101(cx - 1, sw), x3 = reflect101(cx + 1, sw),
+                x4 = reflect101(cx + 2, sw);
+            v = row[x0] + 4u * row[x1] + 6u * row[cx] + 4u * row[x3] + row[x4];
+        }
+        s_h[r][x] = (unsigned short)v;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < PD_TH * PD_TW; i += 256) {
+        int y = i / PD_TW, x = i - y * PD_TW;
+        int dy = oy + y, dx = ox + x;
+        if (dy < dh && dx < dw) {
+            unsigned v = s_h[2 * y][x] + 4u * s_h[2 * y + 1][x] + 6u * s_h[2 * y + 2][x] +
+                         4u * s_h[2 * y + 3][x] + s_h[2 * y + 4][x];
+            dst[(size_t)dy * dp + dx] = (uint8_t)((v + 128u) >> 8);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// k_lk: predictPtsInNextFrame (feature_tracker.cpp:595-608) + the per-point body of
+// cv::calcOpticalFlowPyrLK (LKTrackerInvoker; semantics pinned in
+// oracle/frontend_spec.py::lk_track).  One warp per feature, all pyramid levels.
+//   - 24x24 patch of the previous level staged in shared memory (REFLECT_101
+//     addressing = the padded pyramid of buildOpticalFlowPyramid),
+//   - Scharr derivatives computed on the fly (REFLECT_101 at the image border,
+//     0 outside the image = BORDER_CONSTANT of the derivative pyramid),
+//   - integer bilinear interpolation (14-bit weights) held in registers,
+//   - exact integer accumulation of the 2x2 normal equations / mismatch vector
+//     with redux.sync warp reductions, float32 update exactly as OpenCV.
+// ---------------------------------------------------------------------------
+#define LK_WPB 8
+#define LK_NPX 14   // ceil(441/32)
+
+__global__ void __launch_bounds__(LK_WPB * 32)
+k_lk(FrontCfg c, const SeqCall *calls, int ncalls, FrontDev d)
+{
+    __shared__ uint8_t s_I[LK_WPB][24 * 24];
+    __shared__ short2 s_D[LK_WPB][22 * 22];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int total = d.work_prefix[ncalls];
+    const int maxLevel = c.levels - 1;
+
+    for (int g = blockIdx.x * LK_WPB + wib; g < total; g += gridDim.x * LK_WPB) {
+        // locate the batch item: largest ci with prefix[ci] <= g
+        int lo = 0, hi = ncalls;
+        while (hi - lo > 1) {
+            int mid = (lo + hi) >> 1;
+            if (d.work_prefix[mid] <= g) lo = mid; else hi = mid;
+        }
+        const int ci = lo;
+        const int idx = g - d.work_prefix[ci];
+        const SeqCall call = calls[ci];
+        const size_t base = (size_t)call.seq * VRF_CAP + idx;
+        const uint8_t *pyrI = d.pyr[call.buf_prev] + (size_t)call.seq * c.pyr_bytes;
+        const uint8_t *pyrJ = d.pyr[call.buf_cur] + (size_t)call.seq * c.pyr_bytes;
+
+        const float2 prev = d.cur_pts[base];
+        float2 init = prev;
+        if (c.use_imu) {
+            double mx, my;
+            cam_lift(c, (double)prev.x, (double)prev.y, mx, my);
+            const double *R = call.R;
+            double X = R[0] * mx + R[1] * my + R[2];
+            double Y = R[3] * mx + R[4] * my + R[5];
+            double Z = R[6] * mx + R[7] * my + R[8];
+            double u, v;
+            cam_project(c, X, Y, Z, u, v);
+            init.x = (float)u; init.y = (float)v;
+        }
+        if (lane == 0) d.pred_pts[base] = init;
+
+        int st = 1;
+        float2 nextStored = init;
+        for (int level = maxLevel; level >= 0; --level) {
+            const int cols = c.lw[level], rows = c.lh[level], pitch = c.lp[level];
+            const uint8_t *I = pyrI + c.loff[level];
+            const uint8_t *J = pyrJ + c.loff[level];
+            const float scale = 1.0f / (float)(1 << level);
+            float2 prevPt = make_float2(prev.x * scale, prev.y * scale);
+            float2 nextPt;
+            if (level == maxLevel) {
+                if (c.use_imu) nextPt = make_float2(init.x * scale, init.y * scale);
+                else nextPt = prevPt;
+            } else
+                nextPt = make_float2(nextStored.x * 2.f, nextStored.y * 2.f);
+            nextStored = nextPt;
+            prevPt.x -= VRF_LK_HALF; prevPt.y -= VRF_LK_HALF;
+            const int ix = (int)floorf(prevPt.x), iy = (int)floorf(prevPt.y);
+            if (ix < -VRF_LK_WIN || ix >= cols || iy < -VRF_LK_WIN || iy >= rows) {
+                if (level == 0) st = 0;
+                continue;
+            }
+            float a = prevPt.x - (float)ix, b = prevPt.y - (float)iy;
+            int iw00 = __float2int_rn((1.f - a) * (1.f - b) * 16384.f);
+            int iw01 = __float2int_rn(a * (1.f - b) * 16384.f);
+            int iw10 = __float2int_rn((1.f - a) * b * 16384.f);
+            int iw11 = 16384 - iw00 - iw01 - iw10;
+
+            __syncwarp();
+            // stage 24x24 of I (origin ix-1, iy-1)
+            for (int t = lane; t < 576; t += 32) {
+                int sy = t / 24, sx = t - sy * 24;
+                int gx = reflect101(ix - 1 + sx, cols), gy = reflect101(iy - 1 + sy, rows);
+                s_I[wib][t] = __ldg(I + (size_t)gy * pitch + gx);
+            }
+            __syncwarp();
+            // Scharr at the 22x22 positions (ix+dx, iy+dy)
+            for (int t = lane; t < 484; t += 32) {
+                int dy_ = t / 22, dx_ = t - dy_ * 22;
+                int gx = ix + dx_, gy = iy + dy_;
+                short2 dv = make_short2(0, 0);
+                if (gx >= 0 && gx < cols && gy >= 0 && gy < rows) {
+                    const uint8_t *p = &s_I[wib][(dy_ + 1) * 24 + dx_ + 1];
+                    int p00 = p[-25], p01 = p[-24], p02 = p[-23];
+                    int p10 = p[-1], p12 = p[1];
+                    int p20 = p[23], p21 = p[24], p22 = p[25];
+                    int t0l = 3 * (p00 + p20) + 10 * p10;     // smoothing along y at x-1
+                    int t0r = 3 * (p02 + p22) + 10 * p12;     // at x+1
+                    int t1l = p20 - p00, t1c = p21 - p01, t1r = p22 - p02;
+                    dv.x = (short)(t0r - t0l);
+                    dv.y = (short)(3 * (t1l + t1r) + 10 * t1c);
+                }
+                s_D[wib][t] = dv;
+            }
+            __syncwarp();
+            int Iw[LK_NPX], Ixv[LK_NPX], Iyv[LK_NPX];
+            int a11 = 0, a12 = 0, a22 = 0;
+#pragma unroll
+            for (int k = 0; k < LK_NPX; ++k) {
+                int p = lane + 32 * k;
+                int iv = 0, ixv = 0, iyv = 0;
+                if (p < 441) {
+                    int wy = p / 21, wx = p - wy * 21;
+                    const uint8_t *q = &s_I[wib][(wy + 1) * 24 + wx + 1];
+                    iv = ((int)q[0] * iw00 + (int)q[1] * iw01 + (int)q[24] * iw10 + (int)q[25] * iw11 + (1 << 8)) >> 9;
+                    const short2 *dq = &s_D[wib][wy * 22 + wx];
+                    short2 d00 = dq[0], d01 = dq[1], d10 = dq[22], d11 = dq[23];
+                    ixv = (d00.x * iw00 + d01.x * iw01 + d10.x * iw10 + d11.x * iw11 + (1 << 13)) >> 14;
+                    iyv = (d00.y * iw00 + d01.y * iw01 + d10.y * iw10 + d11.y * iw11 + (1 << 13)) >> 14;
+                }
+                Iw[k] = iv; Ixv[k] = ixv; Iyv[k] = iyv;
+                a11 += ixv * ixv; a12 += ixv * iyv; a22 += iyv * iyv;
+            }
+            const float FLT_SCALE = 1.f / (float)(1 << 20);
+            float A11 = (float)warp_sum_i64(a11) * FLT_SCALE;
+            float A12 = (float)warp_sum_i64(a12) * FLT_SCALE;
+            float A22 = (float)warp_sum_i64(a22) * FLT_SCALE;
+            float D = A11 * A22 - A12 * A12;
+            float minEig = (A22 + A11 - sqrtf((A11 - A22) * (A11 - A22) + 4.f * A12 * A12)) / 882.f;
+            if (minEig < 1e-4f || D < 1.1920929e-07f) {
+                if (level == 0) st = 0;
+                continue;
+            }
+            D = 1.f / D;
+            nextPt.x -= VRF_LK_HALF; nextPt.y -= VRF_LK_HALF;
+            float2 prevDelta = make_float2(0.f, 0.f);
+            for (int j = 0; j < 30; ++j) {
+                const int jx = (int)floorf(nextPt.x), jy = (int)floorf(nextPt.y);
+                if (jx < -VRF_LK_WIN || jx >= cols || jy < -VRF_LK_WIN || jy >= rows) {
+                    if (level == 0) st = 0;
+                    break;
+                }
+                a = nextPt.x - (float)jx; b = nextPt.y - (float)jy;
+                const int w00 = __float2int_rn((1.f - a) * (1.f - b) * 16384.f);
+                const int w01 = __float2int_rn(a * (1.f - b) * 16384.f);
+                const int w10 = __float2int_rn((1.f - a) * b * 16384.f);
+                const int w11 = 16384 - w00 - w01 - w10;
+                int b1 = 0, b2 = 0;
+                const bool inside = (jx >= 0) && (jy >= 0) && (jx + 22 <= cols) && (jy + 22 <= rows);
+                if (inside) {
+                    const uint8_t *Jb = J + (size_t)jy * pitch + jx;
+#pragma unroll
+                    for (int k = 0; k < LK_NPX; ++k) {
+                        int p = lane + 32 * k;
+                        if (p < 441) {
+                            int wy = p / 21, wx = p - wy * 21;
+                            const uint8_t *q = Jb + wy * pitch + wx;
+                            int jv = ((int)__ldg(q) * w00 + (int)__ldg(q + 1) * w01 + (int)__ldg(q + pitch) * w10 +
+                                      (int)__ldg(q + pitch + 1) * w11 + (1 << 8)) >> 9;
+                            int diff = jv - Iw[k];
+                            b1 += diff * Ixv[k];
+                            b2 += diff * Iyv[k];
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int k = 0; k < LK_NPX; ++k) {
+                        int p = lane + 32 * k;
+                        if (p < 441) {
+                            int wy = p / 21, wx = p - wy * 21;
+                            int x0 = reflect101(jx + wx, cols), x1 = reflect101(jx + wx + 1, cols);
+                            int y0 = reflect101(jy + wy, rows), y1 = reflect101(jy + wy + 1, rows);
+                            const uint8_t *r0 = J + (size_t)y0 * pitch, *r1 = J + (size_t)y1 * pitch;
+                            int jv = ((int)__ldg(r0 + x0) * w00 + (int)__ldg(r0 + x1) * w01 + (int)__ldg(r1 + x0) * w10 +
+                                      (int)__ldg(r1 + x1) * w11 + (1 << 8)) >> 9;
+                            int diff = jv - Iw[k];
+                            b1 += diff * Ixv[k];
+                            b2 += diff * Iyv[k];
+                        }
+                    }
+                }
+                float fb1 = (float)warp_sum_i64(b1) * FLT_SCALE;
+                float fb2 = (float)warp_sum_i64(b2) * FLT_SCALE;
+                float2 delta = make_float2((A12 * fb2 - A22 * fb1) * D, (A12 * fb1 - A11 * fb2) * D);
+                nextPt.x += delta.x; nextPt.y += delta.y;
+                nextStored = make_float2(nextPt.x + VRF_LK_HALF, nextPt.y + VRF_LK_HALF);
+                if ((double)delta.x * (double)delta.x + (double)delta.y * (double)delta.y <= 0.01 * 0.01) break;
+                if (j > 0 && (double)fabsf(delta.x + prevDelta.x) < 0.01 && (double)fabsf(delta.y + prevDelta.y) < 0.01) {
+                    nextStored.x -= delta.x * 0.5f; nextStored.y -= delta.y * 0.5f;
+                    break;
+                }
+                prevDelta = delta;
+            }
+            if (st && level == 0) {
+                // `err` is requested by the reference => final bounds check (lkpyramid.cpp)
+                float qx = nextStored.x - VRF_LK_HALF, qy = nextStored.y - VRF_LK_HALF;
+                int kx = (int)floorf(qx), ky = (int)floorf(qy);
+                if (kx < -VRF_LK_WIN || kx >= cols || ky < -VRF_LK_WIN || ky >= rows) st = 0;
+            }
+        }
+        if (lane == 0) {
+            d.lk_pts[base] = nextStored;
+            d.lk_status[base] = (uint8_t)st;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Block-wide exclusive scan helper (blockDim.x == 256), returns total in *tot.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ int block_excl_scan_256(int v, int *s_warp, int *tot)
+{
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    int inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int n = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += n;
+    }
+    if (lane == 31) s_warp[w] = inc;
+    __syncthreads();
+    if (w == 0) {
+        int x = (lane < 8) ? s_warp[lane] : 0;
+        int xi = x;
+#pragma unroll
+        for (int o = 1; o < 8; o <<= 1) {
+            int n = __shfl_up_sync(0xffffffffu, xi, o);
+            if (lane >= o) xi += n;
+        }
+        if (lane < 8) s_warp[lane] = xi - x;
+        if (lane == 7) s_warp[8] = xi;
+    }
+    __syncthreads();
+    int res = inc - v + s_warp[w];
+    *tot = s_warp[8];
+    __syncthreads();
+    return res;
+}
+
+__device__ __forceinline__ bool in_border(const FrontCfg &c, float2 p)
+{
+    // FeatureTracker::inBorder (feature_tracker.cpp:96-103): cvRound = round half to even
+    int x = __float2int_rn(p.x), y = __float2int_rn(p.y);
+    return 1 <= x && x < c.cols - 1 && 1 <= y && y < c.rows - 1;
+}
+
+// ---------------------------------------------------------------------------
+// k_post_a: feature_tracker.cpp:313-349 -- status fix-up with inBorder,
+// unstable_pts, reduceVector of the five arrays (order preserving), track_cnt++.
+// One CTA (256 threads) per batch item; 4 consecutive elements per thread.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_post_a(FrontCfg c, const SeqCall *calls, FrontDev d)
+{
+    __shared__ int s_warp[9];
+    const SeqCall call = calls[blockIdx.x];
+    const int seq = call.seq;
+    const size_t base = (size_t)seq * VRF_CAP;
+    const int n = call.first ? 0 : d.n_pts[seq];
+    const int t4 = threadIdx.x * 4;
+    int keep[4], uns[4];
+    int nk = 0, nu = 0;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        int i = t4 + e;
+        keep[e] = 0; uns[e] = 0;
+        if (i < n) {
+            int st = d.lk_status[base + i];
+            float2 f = d.lk_pts[base + i];
+            bool ib = in_border(c, f);
+            if (!st && ib) uns[e] = 1;
+            else if (st && !ib) st = 0;
+            keep[e] = st;
+        }
+        nk += keep[e]; nu += uns[e];
+    }
+    int totk, totu;
+    int ok = block_excl_scan_256(nk, s_warp, &totk);
+    int ou = block_excl_scan_256(nu, s_warp, &totu);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        int i = t4 + e;
+        if (keep[e]) {
+            d.t_prev[base + ok] = d.cur_pts[base + i];
+            d.t_forw[base + ok] = d.lk_pts[base + i];
+            d.t_ids[base + ok] = d.ids[base + i];
+            d.t_cnt[base + ok] = d.cnt[base + i] + 1;      // for (auto &n : track_cnt) n++;
+            d.t_prevun[base + ok] = d.prev_un[base + i];
+            d.t_keep[base + ok] = 1;
+            ok++;
+        }
+        if (uns[e]) { d.unstable[base + ou] = d.lk_pts[base + i]; ou++; }
+    }
+    if (threadIdx.x == 0) {
+        d.t_n[seq] = totk;
+        d.n_unstable[seq] = totu;
+        d.n_lk[seq] = n;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// k_post_b: reduceVector by the RANSAC inlier mask (feature_tracker.cpp:463-468),
+// setMask (:173-208: std::sort by track_cnt desc, greedy accept against the
+// virtual circle mask, circles for unstable_pts), grid occupancy and cell
+// selection (:361-395).  One CTA per batch item.
+// The H x W mask image of the reference is *virtual* here: cv::circle(mask,p,r,0,-1)
+// zeroes exactly {q : |q-p|^2 <= r^2} (pinned in tests), so "mask.at(q)==255"
+// <=> no stored centre within r of q.  Centres are kept in d.maskpts.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_post_b(FrontCfg c, const SeqCall *calls, FrontDev d)
+{
+    extern __shared__ unsigned char smem_raw[];
+    float2 *s_forw = reinterpret_cast<float2 *>(smem_raw);                 // CAP
+    float2 *s_prev = s_forw + VRF_CAP;                                      // CAP
+    float2 *s_pun = s_prev + VRF_CAP;                                       // CAP
+    int *s_ids = reinterpret_cast<int *>(s_pun + VRF_CAP);                  // CAP
+    int *s_cnt = s_ids + VRF_CAP;                                           // CAP
+    SortItem *s_sort = reinterpret_cast<SortItem *>(s_cnt + VRF_CAP);       // CAP
+    int2 *s_acc = reinterpret_cast<int2 *>(s_sort + VRF_CAP);               // CAP accepted centres
+    int *s_order = reinterpret_cast<int *>(s_acc + VRF_CAP);                // CAP accepted source index
+    __shared__ int s_warp[9];
+    __shared__ int s_n, s_nacc;
+
+    const SeqCall call = calls[blockIdx.x];
+    const int seq = call.seq;
+    const size_t base = (size_t)seq * VRF_CAP;
+    const int n0 = d.t_n[seq];
+    // 1. compaction by RANSAC mask
+    {
+        const int t4 = threadIdx.x * 4;
+        int keep[4], nk = 0;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            int i = t4 + e;
+            keep[e] = (i < n0) ? (int)d.t_keep[base + i] : 0;
+            nk += keep[e];
+        }
+        int tot;
+        int o = block_excl_scan_256(nk, s_warp, &tot);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            int i = t4 + e;
+            if (keep[e]) {
+                s_forw[o] = d.t_forw[base + i];
+                s_prev[o] = d.t_prev[base + i];
+                s_pun[o] = d.t_prevun[base + i];
+                s_ids[o] = d.t_ids[base + i];
+                s_cnt[o] = d.t_cnt[base + i];
+                o++;
+            }
+        }
+        if (threadIdx.x == 0) s_n = tot;
+    }
+    __syncthreads();
+    int n = s_n;
+    const int nuns = d.n_unstable[seq];
+    if (call.pub) {
+        // 2. setMask: std::sort (libstdc++ introsort restatement, single thread)
+        for (int i = threadIdx.x; i < n; i += 256) { s_sort[i].key = s_cnt[i]; s_sort[i].val = i; }
+        __syncthreads();
+        if (threadIdx.x == 0) std_sort_desc(s_sort, n);
+        __syncthreads();
+        // greedy accept in sorted order (warp 0; lanes test the accepted list in parallel)
+        if (threadIdx.x < 32) {
+            const int lane = threadIdx.x;
+            const int r2 = c.min_dist * c.min_dist;
+            int nacc = 0;
+            for (int k = 0; k < n; ++k) {
+                int src = s_sort[k].val;
+                float2 p = s_forw[src];
+                int px = __float2int_rn(p.x), py = __float2int_rn(p.y);
+                bool hit = false;
+                for (int l = lane; l < nacc; l += 32) {
+                    int dx = s_acc[l].x - px, dy = s_acc[l].y - py;
+                    hit |= (dx * dx + dy * dy <= r2);
+                }
+                if (!__any_sync(0xffffffffu, hit)) {
+                    if (lane == 0) { s_acc[nacc] = make_int2(px, py); s_order[nacc] = src; }
+                    nacc++;
+                    __syncwarp();
+                }
+            }
+            if (lane == 0) s_nacc = nacc;
+        }
+        __syncthreads();
+        const int nacc = s_nacc;
+        // write back in accepted (sorted) order + the mask centres (accepted + unstable)
+        for (int i = threadIdx.x; i < nacc; i += 256) {
+            int src = s_order[i];
+            d.t_forw[base + i] = s_forw[src];
+            d.t_prev[base + i] = s_prev[src];
+            d.t_prevun[base + i] = s_pun[src];
+            d.t_ids[base + i] = s_ids[src];
+            d.t_cnt[base + i] = s_cnt[src];
+            d.maskpts[(size_t)seq * 2 * VRF_CAP + i] = s_acc[i];
+        }
+        for (int i = threadIdx.x; i < nuns; i += 256) {
+            float2 u = d.unstable[base + i];
+            d.maskpts[(size_t)seq * 2 * VRF_CAP + nacc + i] = make_int2(__float2int_rn(u.x), __float2int_rn(u.y));
+        }
+        n = nacc;
+        // 3. grid occupancy + cell selection (only when n_max_cnt > 0)
+        int *gcnt = d.grid_cnt + (size_t)seq * VRF_MAX_CELLS;
+        uint8_t *tex = d.tex_status + (size_t)seq * VRF_MAX_CELLS;
+        int *ck = d.cell_k + (size_t)seq * VRF_MAX_CELLS;
+        const bool detect = (c.max_cnt - n) > 0;
+        if (detect) {
+            for (int i = threadIdx.x; i < c.ncells; i += 256) gcnt[i] = 0;
+            __syncthreads();
+            for (int i = threadIdx.x; i < nacc; i += 256) {
+                float2 p = s_forw[s_order[i]];
+                int col = (int)p.x / c.gw, row = (int)p.y / c.gh;
+                if (col == c.gcols) --col;
+                if (row == c.grows) --row;
+                atomicAdd(&gcnt[col + c.gcols * row], 1);
+            }
+            __syncthreads();
+        }
+        for (int i = threadIdx.x; i < c.ncells; i += 256) {
+            int k = 0;
+            if (detect) {
+                if (gcnt[i] < c.thr && tex[i]) k = c.thr - gcnt[i] + 2;
+                else tex[i] = 1;
+            }
+            ck[i] = k;
+            d.ncand[(size_t)seq * VRF_MAX_CELLS + i] = 0;
+        }
+        if (threadIdx.x == 0) { d.t_n[seq] = n; d.n_maskpts[seq] = nacc + nuns; }
+    } else {
+        for (int i = threadIdx.x; i < n; i += 256) {
+            d.t_forw[base + i] = s_forw[i];
+            d.t_prev[base + i] = s_prev[i];
+            d.t_prevun[base + i] = s_pun[i];
+            d.t_ids[base + i] = s_ids[i];
+            d.t_cnt[base + i] = s_cnt[i];
+        }
+        for (int i = threadIdx.x; i < c.ncells; i += 256) d.cell_k[(size_t)seq * VRF_MAX_CELLS + i] = 0;
+        if (threadIdx.x == 0) { d.t_n[seq] = n; d.n_maskpts[seq] = 0; }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// k_fast: FeatureTracker::gridDetect (feature_tracker.cpp:105-171) for one grid
+// cell: cv::FastFeatureDetector (threshold 10, NMS, TYPE_9_16) on forw_img(rect)
+// with the snapshot mask, then the reference's top-K slot selection.
+// One CTA (256 threads) per (cell, batch item).  Dynamic shared memory:
+//   u8 img[h][w] | u8 score[h][w] | u32 kp[(w*h)/4+64] | int2 mpts[...]
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ bool has_run9(unsigned m)
+{
+    // 16-bit cyclic mask: any 9 contiguous set bits?
+    unsigned x = m | (m << 16);
+    x &= x >> 1;  // runs of 2
+    x &= x >> 2;  // 4
+    x &= x >> 4;  // 8
+    x &= (m | (m << 16)) >> 8;  // 9
+    return (x & 0xFFFFu) != 0;
+}
+
+__global__ void __launch_bounds__(256)
+k_fast(FrontCfg c, const SeqCall *calls, FrontDev d)
+{
+    extern __shared__ unsigned char smem_raw[];
+    __shared__ int s_warp[9];
+    __shared__ int s_nm, s_nkp;
+    const SeqCall call = calls[blockIdx.y];
+    const int seq = call.seq, cell = blockIdx.x;
+    if (!call.pub) return;
+    const int K = d.cell_k[(size_t)seq * VRF_MAX_CELLS + cell];
+    if (K == 0) return;
+    // rect (feature_tracker.cpp:44-86): +3 px overlap on interior edges
+    const int ci = cell / c.gcols, cj = cell - ci * c.gcols;
+    const int grw = c.cols - (c.gcols - 1) * c.gw, grh = c.rows - (c.grows - 1) * c.gh;
+    int rx, ry, rw, rh;
+    if (cj == 0) { rx = 0; rw = c.gw + 3; }
+    else if (cj < c.gcols - 1) { rx = cj * c.gw - 3; rw = c.gw + 6; }
+    else { rx = cj * c.gw - 3; rw = grw + 3; }
+    if (ci == 0) { ry = 0; rh = c.gh + 3; }
+    else if (ci < c.grows - 1) { ry = ci * c.gh - 3; rh = c.gh + 6; }
+    else { ry = ci * c.gh - 3; rh = grh + 3; }
+    const int npx = rw * rh;
+    uint8_t *s_img = smem_raw;
+    uint8_t *s_sc = s_img + ((npx + 15) & ~15);
+    unsigned *s_kp = reinterpret_cast<unsigned *>(s_sc + ((npx + 15) & ~15));
+    const int kp_cap = npx / 4 + 64;
+    int2 *s_m = reinterpret_cast<int2 *>(s_kp + kp_cap);
+
+    const uint8_t *img = d.pyr[call.buf_cur] + (size_t)seq * c.pyr_bytes;   // level 0
+    for (int i = threadIdx.x; i < npx; i += 256) {
+        int y = i / rw, x = i - y * rw;
+        s_img[i] = __ldg(img + (size_t)(ry + y) * c.lp[0] + rx + x);
+        s_sc[i] = 0;
+    }
+    if (threadIdx.x == 0) { s_nm = 0; s_nkp = 0; }
+    __syncthreads();
+    // mask centres whose circle can reach this rect
+    {
+        const int nm = d.n_maskpts[seq];
+        const int2 *mp = d.maskpts + (size_t)seq * 2 * VRF_CAP;
+        const int r = c.min_dist;
+        for (int i = threadIdx.x; i < nm; i += 256) {
+            int2 p = mp[i];
+            if (p.x + r >= rx && p.x - r < rx + rw && p.y + r >= ry && p.y - r < ry + rh) {
+                int o = atomicAdd(&s_nm, 1);
+                s_m[o] = p;
+            }
+        }
+    }
+    // scores on the rect interior
+    const int iw = rw - 6, ih = rh - 6;
+    const int off[16] = {3 * rw, 3 * rw + 1, 2 * rw + 2, rw + 3, 3, -rw + 3, -2 * rw + 2, -3 * rw + 1,
+                         -3 * rw, -3 * rw - 1, -2 * rw - 2, -rw - 3, -3, rw - 3, 2 * rw - 2, 3 * rw - 1};
+    for (int i = threadIdx.x; i < iw * ih; i += 256) {
+        int y = i / iw + 3, x = i - (y - 3) * iw + 3;
+        const uint8_t *p = s_img + y * rw + x;
+        int v = p[0];
+        int dd[16];
+        unsigned mb = 0, md = 0;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            dd[k] = v - (int)p[off[k]];
+            mb |= (dd[k] >= 11 ? 1u : 0u) << k;     // centre brighter than ring by > threshold
+            md |= (dd[k] <= -11 ? 1u : 0u) << k;
+        }
+        if (has_run9(mb) || has_run9(md)) {
+            // exact cornerScore: max over the 16 arcs of 9 of max(min d, -max d), minus 1
+            int best = -100000;
+#pragma unroll
+            for (int s = 0; s < 16; ++s) {
+                int mn = dd[s], mx = dd[s];
+#pragma unroll
+                for (int j = 1; j < 9; ++j) {
+                    int e = dd[(s + j) & 15];
+                    mn = min(mn, e); mx = max(mx, e);
+                }
+                best = max(best, max(mn, -mx));
+            }
+            int sc = best - 1;
+            s_sc[y * rw + x] = (uint8_t)(sc >= 10 ? sc : 0);
+        }
+    }
+    __syncthreads();
+    // NMS (strict maximum over the 8 neighbours) + mask, ordered (row-major) compaction
+    const int r2 = c.min_dist * c.min_dist;
+    const int nmask = s_nm;
+    const int nchunks = (iw * ih + 255) / 256;
+    int basecount = 0;
+    for (int ch = 0; ch < nchunks; ++ch) {
+        int i = ch * 256 + threadIdx.x;
+        int flag = 0, x = 0, y = 0, sc = 0;
+        if (i < iw * ih) {
+            y = i / iw + 3; x = i - (y - 3) * iw + 3;
+            const uint8_t *q = s_sc + y * rw + x;
+            sc = q[0];
+            if (sc > 0 && sc > q[-1] && sc > q[1] && sc > q[-rw - 1] && sc > q[-rw] && sc > q[-rw + 1] &&
+                sc > q[rw - 1] && sc > q[rw] && sc > q[rw + 1]) {
+                flag = 1;
+                int gx = rx + x, gy = ry + y;
+                for (int m = 0; m < nmask; ++m) {
+                    int dx = s_m[m].x - gx, dy = s_m[m].y - gy;
+                    if (dx * dx + dy * dy <= r2) { flag = 0; break; }
+                }
+            }
+        }
+        int tot;
+        int o = block_excl_scan_256(flag, s_warp, &tot);
+        if (flag && basecount + o < kp_cap) s_kp[basecount + o] = (unsigned)x | ((unsigned)y << 12) | ((unsigned)sc << 24);
+        basecount += tot;
+    }
+    __syncthreads();
+    // top-K slot selection (feature_tracker.cpp:119-167), sequential exactly as the reference
+    if (threadIdx.x == 0) {
+        const int nk = min(basecount, kp_cap);
+        float *cand = d.cand + ((size_t)seq * VRF_MAX_CELLS + cell) * c.kmax * 3;
+        int nout = 0;
+        if (nk == 0) {
+            d.tex_status[(size_t)seq * VRF_MAX_CELLS + cell] = 0;
+        } else if (nk <= K) {
+            for (int j = 0; j < nk; ++j) {
+                unsigned e = s_kp[j];
+                cand[3 * j] = (float)((int)(e & 0xFFF) + rx);
+                cand[3 * j + 1] = (float)((int)((e >> 12) & 0xFFF) + ry);
+                cand[3 * j + 2] = (float)(e >> 24);
+            }
+            nout = nk;
+        } else {
+            int minid = 0;
+            for (int j = 0; j < nk; ++j) {
+                unsigned e = s_kp[j];
+                float resp = (float)(e >> 24);
+                if (j < K) {
+                    cand[3 * j] = (float)((int)(e & 0xFFF) + rx);
+                    cand[3 * j + 1] = (float)((int)((e >> 12) & 0xFFF) + ry);
+                    cand[3 * j + 2] = resp;
+                    if (resp < cand[3 * minid + 2]) minid = j;
+                } else if (resp > cand[3 * minid + 2]) {
+                    cand[3 * minid] = (float)((int)(e & 0xFFF) + rx);
+                    cand[3 * minid + 1] = (float)((int)((e >> 12) & 0xFFF) + ry);
+                    cand[3 * minid + 2] = resp;
+                    for (int k = 0; k < K; ++k)
+                        if (cand[3 * k + 2] < cand[3 * minid + 2]) minid = k;
+                }
+            }
+            nout = K;
+        }
+        d.ncand[(size_t)seq * VRF_MAX_CELLS + cell] = nout;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// k_finish: addPoints(vector<KeyPoint>&) in cell order (feature_tracker.cpp:405-409,
+// :220-233), cur <- forw, undistortedPoints (:542-593) incl. velocity, the
+// nodelet's updateID loop (estimator_nodelet.cpp:324-330), outputs.
+// One CTA (256 threads) per batch item.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_finish(FrontCfg c, const SeqCall *calls, FrontDev d)
+{
+    __shared__ int2 s_acc[VRF_CAP];      // newly accepted centres
+    __shared__ float2 s_new[VRF_CAP];
+    __shared__ int s_warp[9];
+    __shared__ int s_nnew;
+    const SeqCall call = calls[blockIdx.x];
+    const int seq = call.seq;
+    const size_t base = (size_t)seq * VRF_CAP;
+    const int n = d.t_n[seq];
+    if (threadIdx.x == 0) s_nnew = 0;
+    __syncthreads();
+    if (call.pub && threadIdx.x < 32) {
+        const int lane = threadIdx.x;
+        const int r2 = c.min_dist * c.min_dist;
+        const int2 *mp = d.maskpts + (size_t)seq * 2 * VRF_CAP;
+        const int nm = d.n_maskpts[seq];
+        int nnew = 0;
+        for (int cell = 0; cell < c.ncells; ++cell) {
+            if (d.cell_k[(size_t)seq * VRF_MAX_CELLS + cell] == 0) continue;
+            const int nc = d.ncand[(size_t)seq * VRF_MAX_CELLS + cell];
+            const float *cand = d.cand + ((size_t)seq * VRF_MAX_CELLS + cell) * c.kmax * 3;
+            for (int j = 0; j < nc; ++j) {
+                float px = cand[3 * j], py = cand[3 * j + 1];
+                int ix = __float2int_rn(px), iy = __float2int_rn(py);
+                bool hit = false;
+                for (int l = lane; l < nm; l += 32) {
+                    int dx = mp[l].x - ix, dy = mp[l].y - iy;
+                    hit |= (dx * dx + dy * dy <= r2);
+                }
+                for (int l = lane; l < nnew; l += 32) {
+                    int dx = s_acc[l].x - ix, dy = s_acc[l].y - iy;
+                    hit |= (dx * dx + dy * dy <= r2);
+                }
+                if (!__any_sync(0xffffffffu, hit)) {
+                    if (lane == 0 && n + nnew < VRF_CAP) { s_acc[nnew] = make_int2(ix, iy); s_new[nnew] = make_float2(px, py); }
+                    if (n + nnew < VRF_CAP) nnew++;
+                    __syncwarp();
+                }
+            }
+        }
+        if (lane == 0) s_nnew = nnew;
+    }
+    __syncthreads();
+    const int nnew = s_nnew;
+    const int ntot = n + nnew;
+    // per point: final arrays, undistort, velocity, id assignment
+    int n_id0 = d.n_id[seq];
+    const int t4 = threadIdx.x * 4;
+    int isnew[4], cntn = 0;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        int i = t4 + e;
+        isnew[e] = (i < ntot) && ((i >= n) || d.t_ids[base + i] == -1);
+        cntn += isnew[e];
+    }
+    int totnew;
+    int o = block_excl_scan_256(cntn, s_warp, &totnew);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        int i = t4 + e;
+        if (i < ntot) {
+            float2 p; int id, cnt; float2 pun;
+            if (i < n) { p = d.t_forw[base + i]; id = d.t_ids[base + i]; cnt = d.t_cnt[base + i]; pun = d.t_prevun[base + i]; }
+            else { p = s_new[i - n]; id = -1; cnt = 1; pun = make_float2(0.f, 0.f); }
+            double mx, my;
+            cam_lift(c, (double)p.x, (double)p.y, mx, my);
+            float2 un = make_float2((float)mx, (float)my);   // b.x()/b.z(), z == 1
+            // velocity: only points that already carried an id when the previous
+            // undistortedPoints ran are found in prev_un_pts_map: cnt >= 3
+            float2 v = make_float2(0.f, 0.f);
+            if (!call.first && id != -1 && cnt >= 3) {
+                v.x = (float)((double)(un.x - pun.x) / call.dt);
+                v.y = (float)((double)(un.y - pun.y) / call.dt);
+            }
+            if (isnew[e]) { id = n_id0 + o; o++; }
+            d.cur_pts[base + i] = p;
+            d.ids[base + i] = id;
+            d.cnt[base + i] = cnt;
+            d.prev_un[base + i] = un;
+            const size_t ob = (size_t)blockIdx.x * VRF_CAP + i;
+            d.o_pts[ob] = p;
+            d.o_un[ob] = un;
+            d.o_vel[ob] = v;
+            d.o_ids[ob] = id;
+            d.o_cnt[ob] = cnt;
+        }
+    }
+    if (threadIdx.x == 0) {
+        d.n_pts[seq] = ntot;
+        d.n_id[seq] = n_id0 + totnew;
+        int *hdr = d.out_hdr + (size_t)blockIdx.x * 8;
+        hdr[0] = ntot;
+        hdr[1] = n_id0 + totnew;
+        hdr[2] = d.n_lk[seq];
+        hdr[3] = d.n_unstable[seq];
+        hdr[4] = (n + nnew >= VRF_CAP) ? VRF_ERR_CAPACITY : 0;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// launchers (called from api.cu)
+// ---------------------------------------------------------------------------
+size_t post_b_smem_bytes()
+{
+    return (size_t)VRF_CAP * (3 * sizeof(float2) + 2 * sizeof(int) + sizeof(SortItem) + sizeof(int2) + sizeof(int));
+}
+
+size_t fast_smem_bytes(const FrontCfg &c)
+{
+    int grw = c.cols - (c.gcols - 1) * c.gw, grh = c.rows - (c.grows - 1) * c.gh;
+    int rw = max(c.gw + 6, grw + 3), rh = max(c.gh + 6, grh + 3);
+    size_t npx = (size_t)rw * rh;
+    size_t a = (npx + 15) & ~(size_t)15;
+    return 2 * a + (npx / 4 + 64) * sizeof(unsigned) + (size_t)2 * VRF_CAP * sizeof(int2);
+}
+
+int front_configure_kernels(const FrontCfg &c)
+{
+    cudaError_t e = cudaFuncSetAttribute(k_post_b, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)post_b_smem_bytes());
+    if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(k_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast_smem_bytes(c));
+    return (int)e;
+}
+
+int front_launch(const FrontCfg &c, const SeqCall *d_calls, int ncalls, const FrontDev &d,
+                 const uint8_t *d_frames, size_t frame_bytes, int fmt, int any_pub, int sm_count,
+                 cudaStream_t st, uint64_t *launches)
+{
+    dim3 gi((c.rows * (c.cols >> 4) + 255) / 256, ncalls);
+    if (gi.x > 64) gi.x = 64;
+    k_ingest<<<gi, 256, 0, st>>>(c, d_calls, ncalls, d, d_frames, frame_bytes, fmt);
+    ++*launches;
+    for (int l = 0; l + 1 < c.levels; ++l) {
+        dim3 g((c.lw[l + 1] + PD_TW - 1) / PD_TW, (c.lh[l + 1] + PD_TH - 1) / PD_TH, ncalls);
+        k_pyrdown<<<g, 256, 0, st>>>(c, d_calls, d, l);
+        ++*launches;
+    }
+    {
+        long long maxwork = (long long)ncalls * VRF_CAP;
+        long long want = ((long long)ncalls * (c.max_cnt + 2 * c.ncells) + LK_WPB - 1) / LK_WPB;
+        long long cap = (long long)sm_count * 8;
+        int grid = (int)max(1LL, min(min(want, cap), maxwork));
+        k_lk<<<grid, LK_WPB * 32, 0, st>>>(c, d_calls, ncalls, d);
+        ++*launches;
+    }
+    k_post_a<<<ncalls, 256, 0, st>>>(c, d_calls, d);
+    ++*launches;
+    return 0;
+}
+
+int front_launch_tail(const FrontCfg &c, const SeqCall *d_calls, int ncalls, const FrontDev &d, int any_pub,
+                      cudaStream_t st, uint64_t *launches)
+{
+    k_post_b<<<ncalls, 256, post_b_smem_bytes(), st>>>(c, d_calls, d);
+    ++*launches;
+    if (any_pub) {
+        dim3 g(c.ncells, ncalls);
+        k_fast<<<g, 256, fast_smem_bytes(c), st>>>(c, d_calls, d);
+        ++*launches;
+    }
+    k_finish<<<ncalls, 256, 0, st>>>(c, d_calls, d);
+    ++*launches;
+    return 0;
+}
+
+}  // namespace vrf

@@ -1,0 +1,325 @@
+"""ctypes binding of the C ABI declared in include/vrf.h (harness only).
+
+Fails loudly if libvrf.so is missing: the product has no CPU fallback.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_PKG = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIB_PATH = os.path.join(_PKG, "libvrf.so")
+
+TRACK_CAP = 1024
+NUM_FRAMES = 11
+PRIOR_MAX_BLOCKS = 40
+PRIOR_MAX_DIM = 176
+
+FMT_GRAY8, FMT_RGB8 = 0, 1
+MARGIN_OLD, MARGIN_SECOND_NEW = 0, 1
+BLK_POSE, BLK_SPEEDBIAS, BLK_EXPOSE, BLK_TD = 0, 1, 2, 3
+
+
+class VrfConfig(C.Structure):
+    _fields_ = [
+        ("row", C.c_int32), ("col", C.c_int32), ("max_cnt", C.c_int32), ("min_dist", C.c_int32),
+        ("num_grid_rows", C.c_int32), ("num_grid_cols", C.c_int32), ("use_imu", C.c_int32),
+        ("equalize", C.c_int32), ("fisheye", C.c_int32), ("lk_max_level", C.c_int32),
+        ("use_ransac", C.c_int32), ("reserved0", C.c_int32),
+        ("f_threshold", C.c_double), ("focal_length", C.c_double),
+        ("fx", C.c_double), ("fy", C.c_double), ("cx", C.c_double), ("cy", C.c_double),
+        ("k1", C.c_double), ("k2", C.c_double), ("p1", C.c_double), ("p2", C.c_double),
+        ("num_iterations", C.c_int32), ("estimate_extrinsic", C.c_int32), ("estimate_td", C.c_int32),
+        ("fix_depth", C.c_int32), ("depth_max_dist", C.c_double), ("g_norm", C.c_double),
+        ("acc_n", C.c_double), ("acc_w", C.c_double), ("gyr_n", C.c_double), ("gyr_w", C.c_double),
+    ]
+
+
+class VrfTrackOut(C.Structure):
+    _fields_ = [
+        ("capacity", C.c_int32), ("n", C.c_int32),
+        ("cur_pts", C.c_void_p), ("cur_un_pts", C.c_void_p), ("pts_velocity", C.c_void_p),
+        ("ids", C.c_void_p), ("track_cnt", C.c_void_p),
+        ("n_id", C.c_int32), ("n_predict", C.c_int32),
+        ("predict_pts", C.c_void_p), ("lk_pts", C.c_void_p), ("lk_status", C.c_void_p),
+        ("grids_track_num", C.c_void_p), ("grids_texture_status", C.c_void_p),
+        ("n_unstable", C.c_int32), ("status", C.c_int32),
+    ]
+
+
+class VrfImuPreint(C.Structure):
+    _fields_ = [
+        ("sum_dt", C.c_double), ("delta_p", C.c_double * 3), ("delta_q", C.c_double * 4),
+        ("delta_v", C.c_double * 3), ("linearized_ba", C.c_double * 3), ("linearized_bg", C.c_double * 3),
+        ("jacobian", C.c_double * 225), ("covariance", C.c_double * 225),
+    ]
+
+
+class VrfPriorBlock(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("index", C.c_int32), ("size", C.c_int32), ("idx", C.c_int32),
+                ("x0", C.c_double * 9)]
+
+
+class VrfPrior(C.Structure):
+    _fields_ = [
+        ("n", C.c_int32), ("n_blocks", C.c_int32),
+        ("blocks", VrfPriorBlock * PRIOR_MAX_BLOCKS),
+        ("linearized_jacobians", C.c_double * (PRIOR_MAX_DIM * PRIOR_MAX_DIM)),
+        ("linearized_residuals", C.c_double * PRIOR_MAX_DIM),
+    ]
+
+
+class VrfBaProblem(C.Structure):
+    _fields_ = [
+        ("frame_count", C.c_int32), ("use_imu", C.c_int32), ("ex_constant", C.c_int32),
+        ("td_constant", C.c_int32), ("marginalization_flag", C.c_int32), ("max_iterations", C.c_int32),
+        ("para_Pose", (C.c_double * 7) * NUM_FRAMES), ("para_SpeedBias", (C.c_double * 9) * NUM_FRAMES),
+        ("para_Ex_Pose", C.c_double * 7), ("para_Td", C.c_double),
+        ("n_landmarks", C.c_int32), ("n_obs", C.c_int32),
+        ("para_Feature", C.c_void_p), ("lm_start_frame", C.c_void_p), ("lm_estimate_flag", C.c_void_p),
+        ("lm_obs_ptr", C.c_void_p), ("obs_pts", C.c_void_p),
+        ("imu", C.POINTER(VrfImuPreint)), ("prior", C.POINTER(VrfPrior)),
+    ]
+
+
+class VrfBaResult(C.Structure):
+    _fields_ = [
+        ("status", C.c_int32), ("iterations", C.c_int32), ("successful_steps", C.c_int32),
+        ("termination", C.c_int32), ("initial_cost", C.c_double), ("final_cost", C.c_double),
+        ("para_Pose", (C.c_double * 7) * NUM_FRAMES), ("para_SpeedBias", (C.c_double * 9) * NUM_FRAMES),
+        ("para_Ex_Pose", C.c_double * 7), ("para_Td", C.c_double), ("para_Feature", C.c_void_p),
+        ("Ps", (C.c_double * 3) * NUM_FRAMES), ("Rs", (C.c_double * 9) * NUM_FRAMES),
+        ("Vs", (C.c_double * 3) * NUM_FRAMES), ("Bas", (C.c_double * 3) * NUM_FRAMES),
+        ("Bgs", (C.c_double * 3) * NUM_FRAMES),
+        ("has_new_prior", C.c_int32), ("reserved", C.c_int32), ("new_prior", C.POINTER(VrfPrior)),
+    ]
+
+
+# every symbol include/vrf.h + include/vrf_ba.h declare
+EXPORTS = [
+    "vrf_config_default", "vrf_create", "vrf_destroy", "vrf_strerror", "vrf_last_cuda_error",
+    "vrf_launch_count", "vrf_reset_sequence", "vrf_tracker_read_image", "vrf_tracker_read_image_batch",
+    "vrf_tracker_enqueue_batch_dev", "vrf_tracker_fetch_batch", "vrf_synchronize", "vrf_stream",
+    "vrf_debug_sort_desc", "vrf_ba_solve", "vrf_ba_solve_batch", "vrf_ba_upload_batch",
+    "vrf_ba_enqueue_batch", "vrf_ba_download_batch", "vrf_debug_eval_projection", "vrf_debug_eval_imu",
+]
+
+_lib = None
+
+
+def load():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(f"{LIB_PATH} is missing: build it with `make -C vins-rgbd-fast_b200` "
+                           "(python -c 'import __graft_entry__ as g; g.build()'). There is no CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    lib.vrf_config_default.argtypes = [C.POINTER(VrfConfig)]
+    lib.vrf_config_default.restype = None
+    lib.vrf_create.argtypes = [C.POINTER(VrfConfig), C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+    lib.vrf_destroy.argtypes = [C.c_void_p]
+    lib.vrf_destroy.restype = None
+    lib.vrf_strerror.argtypes = [C.c_int]
+    lib.vrf_strerror.restype = C.c_char_p
+    lib.vrf_last_cuda_error.argtypes = [C.c_void_p]
+    lib.vrf_last_cuda_error.restype = C.c_char_p
+    lib.vrf_launch_count.argtypes = [C.c_void_p]
+    lib.vrf_launch_count.restype = C.c_uint64
+    lib.vrf_reset_sequence.argtypes = [C.c_void_p, C.c_int]
+    lib.vrf_tracker_read_image.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_int, C.c_double,
+                                           C.c_void_p, C.c_int, C.POINTER(VrfTrackOut)]
+    lib.vrf_tracker_read_image_batch.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int,
+                                                 C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(VrfTrackOut)]
+    lib.vrf_tracker_enqueue_batch_dev.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
+                                                  C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.vrf_tracker_fetch_batch.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.POINTER(VrfTrackOut)]
+    lib.vrf_synchronize.argtypes = [C.c_void_p]
+    lib.vrf_stream.argtypes = [C.c_void_p]
+    lib.vrf_stream.restype = C.c_void_p
+    lib.vrf_debug_sort_desc.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
+    lib.vrf_debug_sort_desc.restype = None
+    lib.vrf_ba_solve.argtypes = [C.c_void_p, C.c_int, C.POINTER(VrfBaProblem), C.POINTER(VrfBaResult)]
+    lib.vrf_ba_solve_batch.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.POINTER(VrfBaProblem), C.POINTER(VrfBaResult)]
+    lib.vrf_ba_upload_batch.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.POINTER(VrfBaProblem)]
+    lib.vrf_ba_enqueue_batch.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+    lib.vrf_ba_download_batch.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.POINTER(VrfBaResult)]
+    lib.vrf_debug_eval_projection.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 11
+    lib.vrf_debug_eval_imu.argtypes = [C.c_void_p, C.c_int, C.POINTER(VrfImuPreint)] + [C.c_void_p] * 9
+    _lib = lib
+    return lib
+
+
+def default_config(**over):
+    cfg = VrfConfig()
+    load().vrf_config_default(C.byref(cfg))
+    for k, v in over.items():
+        if not hasattr(cfg, k):
+            raise AttributeError(k)
+        setattr(cfg, k, v)
+    return cfg
+
+
+def check(rc, h=None, allow_soft=True):
+    if rc < 0 or (rc > 0 and not allow_soft):
+        lib = load()
+        msg = lib.vrf_strerror(rc).decode()
+        if h is not None:
+            msg += " | " + lib.vrf_last_cuda_error(h).decode()
+        raise RuntimeError(f"vrf error {rc}: {msg}")
+    return rc
+
+
+def sort_desc_perm(cnt):
+    c = np.ascontiguousarray(cnt, np.int32)
+    out = np.zeros(len(c), np.int32)
+    load().vrf_debug_sort_desc(c.ctypes.data, len(c), out.ctypes.data)
+    return out
+
+
+class TrackResult:
+    """numpy views of one VrfTrackOut."""
+
+    def __init__(self, ncells, debug=True):
+        cap = TRACK_CAP
+        self._cur = np.zeros((cap, 2), np.float32)
+        self._un = np.zeros((cap, 2), np.float32)
+        self._vel = np.zeros((cap, 2), np.float32)
+        self._ids = np.zeros(cap, np.int32)
+        self._cnt = np.zeros(cap, np.int32)
+        self._pred = np.zeros((cap, 2), np.float32)
+        self._lk = np.zeros((cap, 2), np.float32)
+        self._lkst = np.zeros(cap, np.uint8)
+        self._grid = np.zeros(ncells, np.int32)
+        self._tex = np.zeros(ncells, np.uint8)
+        self.debug = debug
+
+    def fill(self, o: VrfTrackOut):
+        o.capacity = TRACK_CAP
+        o.cur_pts = self._cur.ctypes.data
+        o.cur_un_pts = self._un.ctypes.data
+        o.pts_velocity = self._vel.ctypes.data
+        o.ids = self._ids.ctypes.data
+        o.track_cnt = self._cnt.ctypes.data
+        if self.debug:
+            o.predict_pts = self._pred.ctypes.data
+            o.lk_pts = self._lk.ctypes.data
+            o.lk_status = self._lkst.ctypes.data
+            o.grids_track_num = self._grid.ctypes.data
+            o.grids_texture_status = self._tex.ctypes.data
+        self._o = o
+
+    def finish(self):
+        o = self._o
+        n = min(o.n, TRACK_CAP)
+        self.n = o.n
+        self.cur_pts = self._cur[:n]
+        self.cur_un_pts = self._un[:n]
+        self.pts_velocity = self._vel[:n]
+        self.ids = self._ids[:n]
+        self.track_cnt = self._cnt[:n]
+        self.n_id = o.n_id
+        self.n_predict = o.n_predict
+        self.n_unstable = o.n_unstable
+        self.status = o.status
+        npd = min(o.n_predict, TRACK_CAP)
+        self.predict_pts = self._pred[:npd]
+        self.lk_pts = self._lk[:npd]
+        self.lk_status = self._lkst[:npd]
+        self.grids_track_num = self._grid
+        self.grids_texture_status = self._tex
+        return self
+
+
+class Handle:
+    """RAII wrapper of vrf_handle for `n_seq` sequences on one GPU."""
+
+    def __init__(self, cfg: VrfConfig, n_seq=1, device=0):
+        self.lib = load()
+        self.cfg = cfg
+        self.n_seq = n_seq
+        self.ncells = cfg.num_grid_rows * cfg.num_grid_cols
+        hp = C.c_void_p()
+        rc = self.lib.vrf_create(C.byref(cfg), n_seq, device, C.byref(hp))
+        if rc != 0:
+            raise RuntimeError(f"vrf_create failed: {rc} {self.lib.vrf_strerror(rc).decode()}")
+        self.h = hp
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.vrf_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def launches(self):
+        return int(self.lib.vrf_launch_count(self.h))
+
+    def stream(self):
+        return self.lib.vrf_stream(self.h)
+
+    def synchronize(self):
+        check(self.lib.vrf_synchronize(self.h), self.h)
+
+    def reset(self, seq):
+        check(self.lib.vrf_reset_sequence(self.h, seq), self.h)
+
+    def read_image(self, seq, img, t, R=None, pub=True, debug=True):
+        img = np.ascontiguousarray(img)
+        fmt = FMT_RGB8 if img.ndim == 3 else FMT_GRAY8
+        out = VrfTrackOut()
+        res = TrackResult(self.ncells, debug)
+        res.fill(out)
+        Rp = None
+        if R is not None:
+            Rm = np.ascontiguousarray(R, np.float64)
+            Rp = Rm.ctypes.data
+        rc = self.lib.vrf_tracker_read_image(self.h, seq, img.ctypes.data, 0, fmt, float(t), Rp, int(bool(pub)), C.byref(out))
+        check(rc, self.h)
+        return res.finish()
+
+    def read_image_batch(self, seqs, imgs, times, Rs=None, pubs=None, debug=False):
+        n = len(seqs)
+        imgs = [np.ascontiguousarray(im) for im in imgs]
+        fmt = FMT_RGB8 if imgs[0].ndim == 3 else FMT_GRAY8
+        seq_a = np.asarray(seqs, np.int32)
+        ptrs = (C.c_void_p * n)(*[im.ctypes.data for im in imgs])
+        t_a = np.asarray(times, np.float64)
+        R_a = None if Rs is None else np.ascontiguousarray(np.asarray(Rs, np.float64).reshape(n, 9))
+        p_a = None if pubs is None else np.asarray(pubs, np.int32)
+        outs = (VrfTrackOut * n)()
+        results = [TrackResult(self.ncells, debug) for _ in range(n)]
+        for r, o in zip(results, outs):
+            r.fill(o)
+        rc = self.lib.vrf_tracker_read_image_batch(
+            self.h, n, seq_a.ctypes.data, C.cast(ptrs, C.c_void_p), 0, fmt, t_a.ctypes.data,
+            None if R_a is None else R_a.ctypes.data, None if p_a is None else p_a.ctypes.data, outs)
+        check(rc, self.h)
+        return [r.finish() for r in results]
+
+    def enqueue_dev(self, seqs, d_ptr, fmt, times, Rs=None, pubs=None, d_depth=None):
+        n = len(seqs)
+        seq_a = np.asarray(seqs, np.int32)
+        t_a = np.asarray(times, np.float64)
+        R_a = None if Rs is None else np.ascontiguousarray(np.asarray(Rs, np.float64).reshape(n, 9))
+        p_a = None if pubs is None else np.asarray(pubs, np.int32)
+        rc = self.lib.vrf_tracker_enqueue_batch_dev(
+            self.h, n, seq_a.ctypes.data, d_ptr, fmt, d_depth, t_a.ctypes.data,
+            None if R_a is None else R_a.ctypes.data, None if p_a is None else p_a.ctypes.data)
+        check(rc, self.h)
+
+    def fetch(self, seqs, debug=False):
+        n = len(seqs)
+        seq_a = np.asarray(seqs, np.int32)
+        outs = (VrfTrackOut * n)()
+        results = [TrackResult(self.ncells, debug) for _ in range(n)]
+        for r, o in zip(results, outs):
+            r.fill(o)
+        rc = self.lib.vrf_tracker_fetch_batch(self.h, n, seq_a.ctypes.data, outs)
+        check(rc, self.h)
+        return [r.finish() for r in results]
