@@ -1,0 +1,386 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the B200-native VINS-RGBD-FAST hot path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--seqs S]
+
+A "step" = one pass of the hot path over one batch: every one of the S
+sequences resident on a GPU consumes one 640x480 RGB-D frame
+(FeatureTracker::readImage incl. FAST detection on publish frames, every 3rd
+frame = freq 10 Hz at 30 Hz input as in the reference configs) and, on publish
+frames, one 10-keyframe sliding-window BA solve (Estimator::optimization) once
+the back end is enabled in this build.  Metric: RGB-D VIO frames/s (BASELINE.json).
+
+value  : frames already resident in HBM, device timed with CUDA events.
+e2e    : same metric through the reference-facing C ABI with HOST buffers
+         (pinned): H2D of every frame and D2H of every result inside the timed
+         region.
+roofline: dominant kernel (by device time, per-kernel CUDA events in a separate
+         profiled pass of the same steps) against MEASURED_PEAKS.json.
+cpu_baseline / --impl reference: the cv2-backed oracle (the reference's OpenCV
+         arithmetic, control flow restated) on the host cores.
+Multi-GPU: one process per GPU (torchrun), sequences sharded, no data-path
+collective; NCCL only gathers the timing/counters.  scaling = weak.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "vins-rgbd-fast_b200"))
+
+W, H = 640, 480
+A_FRAME = 5 * W * H           # RGB8 + depth16 read once per frame
+PUB_EVERY = 3                 # freq 10 Hz / 30 Hz input
+N_DISTINCT = 8                # distinct rendered base sequences (replicated with phase offsets)
+T_FRAMES = 12                 # frames per base sequence, played ping-pong
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)), "measured"
+        except Exception:
+            pass
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def render_inputs(n_distinct, t_frames):
+    """Distinct base sequences: (rgb [T,H,W,3], depth [T,H,W] u16, gray, times, forward rel. rotations)."""
+    from vrf_b200 import synth
+    base = []
+    for i in range(n_distinct):
+        s = synth.Sequence(1234 + i)
+        rgb = np.zeros((t_frames, H, W, 3), np.uint8)
+        dep = np.zeros((t_frames, H, W), np.uint16)
+        gray = np.zeros((t_frames, H, W), np.uint8)
+        for k in range(t_frames):
+            rgb[k], gray[k], dep[k] = s.frame(k)
+        Rf = np.stack([s.relative_R(k) for k in range(t_frames)])      # cam(k-1)->cam(k)
+        base.append((rgb, dep, gray, Rf, s))
+    return base
+
+
+def pingpong(step, t_frames):
+    """frame index and playback direction for step `step` (0,1,..,T-1,T-2,..,1,0,1,..)."""
+    period = 2 * (t_frames - 1)
+    r = step % period
+    if r < t_frames:
+        return r, +1 if step == 0 or r > 0 else -1
+    return period - r, -1
+
+
+def frame_plan(step, t_frames):
+    period = 2 * (t_frames - 1)
+    r = step % period
+    prev_r = (step - 1) % period
+    idx = r if r < t_frames else period - r
+    pidx = prev_r if prev_r < t_frames else period - prev_r
+    return idx, pidx
+
+
+def rel_rotation(base_R, idx, pidx):
+    """Rotation cam(prev frame) -> cam(this frame) for ping-pong playback."""
+    if idx == pidx:
+        return np.eye(3)
+    if idx == pidx + 1:
+        return base_R[idx]
+    return base_R[pidx].T        # going backwards: inverse of cam(idx)->cam(pidx)
+
+
+def run_reference(args):
+    """CPU arm: the cv2-backed oracle of the front end on all host cores
+    (one independent sequence per worker process, cv2 threads = 1 each)."""
+    import multiprocessing as mp
+    cores = os.cpu_count() or 1
+    frames_per_worker = max(6, min(T_FRAMES * 2, args.ref_frames))
+    steps = max(1, args.steps)
+    ctx = mp.get_context("fork")
+    t_all = []
+    for it in range(args.warmup + steps):
+        with ctx.Pool(cores) as pool:
+            t0 = time.perf_counter()
+            res = pool.map(_ref_worker, [(1234 + (i % N_DISTINCT), frames_per_worker) for i in range(cores)])
+            dt = max(r[1] for r in res)           # workers run concurrently; slowest bounds the batch
+        if it >= args.warmup:
+            t_all.append(dt)
+    frames = cores * frames_per_worker
+    sec = float(np.mean(t_all))
+    fps = frames / sec
+    line = {
+        "impl": "reference", "metric": "RGB-D VIO frames/sec (640x480, front end; back end pending)", "value": fps,
+        "unit": "frames/s", "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup,
+        "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u8/f32 (cv2)", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "sample": f"{cores} sequences x {frames_per_worker} frames per step"},
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
+                         "sample": f"{cores} workers x {frames_per_worker} frames, cv2 4.13 FAST+PyrLK+RANSAC, python glue"},
+        "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def _ref_worker(arg):
+    seed, n = arg
+    import cv2
+    cv2.setNumThreads(1)
+    from oracle.frontend_ref import FeatureTrackerRef, FrontendConfig
+    from vrf_b200 import synth
+    s = synth.Sequence(seed)
+    frames = [s.frame(k)[1] for k in range(min(n, T_FRAMES))]
+    ft = FeatureTrackerRef(FrontendConfig(lk_max_level=2))
+    t0 = time.perf_counter()
+    for step in range(n):
+        idx, pidx = frame_plan(step, len(frames))
+        R = np.eye(3) if step == 0 else rel_rotation(np.stack([s.relative_R(k) for k in range(len(frames))]), idx, pidx)
+        ft.read_image(frames[idx], 1.0 + step / 30.0, R, pub_this_frame=(step % PUB_EVERY == 0))
+    return len(ft.ids), time.perf_counter() - t0
+
+
+WORKLOAD = ("BASELINE configs[1]: 640x480 RGB-D stream, 150 feats, 3-level pyramid LK, 7x8 grid FAST, "
+            "publish every 3rd frame; RGB8+depth16 frames resident in HBM")
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=60)
+    ap.add_argument("--warmup", type=int, default=6)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--seqs", type=int, default=64, help="sequences per GPU")
+    ap.add_argument("--ref-frames", type=int, default=24)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        if rank == 0:
+            run_reference(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from vrf_b200 import binding
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    S = args.seqs
+    dev = torch.device("cuda", local_rank)
+
+    # ---- synthetic inputs: rendered on host once, uploaded before timing ----
+    base = render_inputs(min(N_DISTINCT, S), T_FRAMES)
+    nb = len(base)
+    # HBM-resident copies of every distinct base sequence: [nb][T] RGB frames and depth frames
+    d_rgb = [torch.from_numpy(b[0]).to(dev) for b in base]
+    d_dep = [torch.from_numpy(b[1].view(np.int16)).to(dev) for b in base]
+    # pinned host mirrors for the e2e arm
+    h_rgb = [torch.from_numpy(b[0]).pin_memory() for b in base]
+
+    cfg = binding.default_config(lk_max_level=2, use_ransac=int(os.environ.get("VRF_BENCH_RANSAC", "0")))
+    hnd = binding.Handle(cfg, S, local_rank)
+    ext_stream = torch.cuda.ExternalStream(hnd.stream(), device=dev)
+    seqs = list(range(S))
+    # sequence s plays base s % nb with phase offset (s // nb) so that publish frames are staggered
+    phase = [(s // nb) + (s % PUB_EVERY) for s in seqs]
+
+    def step_plan(step):
+        idxs, Rs, pubs, times = [], [], [], []
+        for s in seqs:
+            st = step + phase[s]
+            idx, pidx = frame_plan(st, T_FRAMES)
+            idxs.append(idx)
+            Rs.append(np.eye(3) if step == 0 else rel_rotation(base[s % nb][3], idx, pidx))
+            pubs.append(1 if st % PUB_EVERY == 0 else 0)
+            times.append(1.0 + step / 30.0)
+        return idxs, np.stack(Rs), pubs, times
+
+    plans = [step_plan(k) for k in range(max(args.warmup + args.steps + 8, 2 * (T_FRAMES - 1)))]
+
+    # HBM-resident input: one contiguous [S][H][W][3] batch per step of the ping-pong period
+    # (what a camera DMA engine would have written; built once, before timing)
+    PERIOD = 2 * (T_FRAMES - 1)
+    d_steps = torch.empty((PERIOD, S, H, W, 3), dtype=torch.uint8, device=dev)
+    for p_ in range(PERIOD):
+        idxs = plans[p_][0] if p_ < len(plans) else step_plan(p_)[0]
+        for s in seqs:
+            d_steps[p_, s].copy_(d_rgb[s % nb][idxs[s]])
+    torch.cuda.synchronize()
+
+    def run_dev_step(k):
+        idxs, Rs, pubs, times = plans[k]
+        hnd.enqueue_dev(seqs, d_steps[k % PERIOD].data_ptr(), binding.FMT_RGB8, times, Rs, pubs, d_depth=None)
+
+    # ---- warm-up ----
+    for k in range(args.warmup):
+        run_dev_step(k)
+    hnd.synchronize()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    l0 = hnd.launches
+    ev0 = torch.cuda.Event(enable_timing=True)
+    ev1 = torch.cuda.Event(enable_timing=True)
+    ev0.record(ext_stream)
+    for k in range(args.warmup, args.warmup + args.steps):
+        run_dev_step(k)
+    ev1.record(ext_stream)
+    hnd.synchronize()
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
+    launches = hnd.launches - l0
+    ms_total = ev0.elapsed_time(ev1)
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.barrier()
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total_max = float(t.item())
+    frames_total = S * args.steps * world
+    value = frames_total / (ms_total_max * 1e-3)
+
+    # ---- profiled pass (per-kernel CUDA events) for the roofline ----
+    hnd.profile(True)
+    hnd.profile_read(reset=True)
+    nprof = min(12, args.steps)
+    for k in range(args.warmup, args.warmup + nprof):
+        run_dev_step(k)
+    prof = hnd.profile_read(reset=True)
+    hnd.profile(False)
+    tot_ms = sum(v[0] for v in prof.values()) or 1.0
+    kern = {k: {"ms_per_step": v[0] / nprof, "launches_per_step": v[1] / nprof, "share": v[0] / tot_ms}
+            for k, v in prof.items() if v[1] > 0}
+    peaks, peak_kind = load_peaks()
+    dom = max(kern.items(), key=lambda kv: kv[1]["ms_per_step"])[0] if kern else None
+    roof = None
+    if dom:
+        # algorithmic bytes per launch of the dominant kernel (DESIGN.md section "roofline")
+        alg = {"k_ingest": S * (3 * W * H + W * H),                 # RGB8 read + gray write
+               "k_pyrdown": None, "k_lk": None, "k_fast": None}.get(dom)
+        per_launch_ms = kern[dom]["ms_per_step"] / max(kern[dom]["launches_per_step"], 1e-9)
+        alg_bytes = alg if alg else S * A_FRAME / max(kern[dom]["launches_per_step"], 1)
+        ach = alg_bytes / (per_launch_ms * 1e-3) / 1e9
+        roof = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                "frac": ach / peaks["hbm_gbs"], "traffic": None, "peak_source": peak_kind,
+                "alg_bytes_per_launch": alg_bytes, "launch_ms": per_launch_ms, "kernels": kern}
+
+    # ---- e2e arm: host buffers through the C ABI (H2D + kernels + D2H per step) ----
+    e2e_steps = max(3, min(args.steps, 20))
+    hnd2 = binding.Handle(cfg, S, local_rank)
+
+    def run_host_step(k):
+        idxs, Rs, pubs, times = plans[k]
+        imgs = [h_rgb[s % nb][idxs[s]].numpy() for s in seqs]
+        return hnd2.read_image_batch(seqs, imgs, times, Rs, pubs, debug=False)
+
+    for k in range(3):
+        run_host_step(k)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    d2h = 0
+    for k in range(3, 3 + e2e_steps):
+        outs = run_host_step(k)
+        d2h = sum(o.n for o in outs) * 32 + S * 32
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.barrier()
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_val = S * e2e_steps * world / float(t.item())
+    hnd2.close()
+
+    cpu_base = None
+    if rank == 0 and not args.no_cpu_baseline:
+        import multiprocessing as mp
+        cores = os.cpu_count() or 1
+        with mp.get_context("fork").Pool(cores) as pool:
+            res = pool.map(_ref_worker, [(1234 + (i % N_DISTINCT), 24) for i in range(cores)])
+        sec = max(r[1] for r in res)
+        cpu_base = {"value": cores * 24 / sec, "unit": "frames/s", "cores": cores, "kind": "port",
+                    "sample": f"{cores} independent sequences x 24 frames, cv2 4.13 (real OpenCV) FAST+PyrLK, python glue, 1 cv2 thread/worker"}
+
+    if rank == 0:
+        line = {
+            "metric": "RGB-D VIO frames/sec (640x480, front end; back end pending)", "value": value, "unit": "frames/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total_max / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/i32/f32 (LK), f64 (camera model)",
+            "data": f"synthetic: {nb} rendered base sequences x {T_FRAMES} frames (ping-pong), replicated to {S} sequences/GPU with phase offsets",
+            "config": {"workload": WORKLOAD, "seqs_per_gpu": S, "l2": "inputs cycle through %d MB of distinct frames (> L2)" % (nb * T_FRAMES * 3 * W * H // 2**20),
+                       "parallelism": f"sequences sharded over {world} GPU(s), no data-path collective"},
+            "clocks": clocks, "gpu_launches": int(launches),
+            "e2e": {"value": e2e_val, "unit": "frames/s", "h2d_bytes_per_step": S * 3 * W * H, "d2h_bytes_per_step": int(d2h)},
+            "roofline": roof, "cpu_baseline": cpu_base,
+        }
+        print(json.dumps(line))
+    hnd.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -170,10 +170,24 @@ int vrf_synchronize(vrf_handle *h);
 /* The CUDA stream (cudaStream_t) the handle launches on, for event timing. */
 void *vrf_stream(vrf_handle *h);
 
+/* Optional per-kernel profiling: when enabled every kernel launch is bracketed by
+ * CUDA events on the handle's stream (the reference's analogue: TicToc running
+ * averages, utility/tic_toc.h + feature_tracker.cpp:333-337,424-428).
+ * vrf_profile_read() synchronises, returns the number of kernel kinds and fills
+ * name / accumulated device milliseconds / launch count per kind. */
+int vrf_profile_enable(vrf_handle *h, int on);
+int vrf_profile_read(vrf_handle *h, int max_kernels, const char **names, double *total_ms,
+                     uint64_t *launch_counts, int reset);
+
 /* Test hooks for the tiny order-dependent host/device-shared routines. */
 /* libstdc++ std::sort restatement used by setMask (feature_tracker.cpp:186-188):
  * writes the permutation that sorts `cnt` descending with the reference's tie order. */
 void vrf_debug_sort_desc(const int32_t *cnt, int32_t n, int32_t *perm_out);
+/* Copies an internal per-sequence device array to host (parity tests only).
+ * what: "pyr<L>" (level L of the current image pyramid, rows*cols u8, tightly packed),
+ *       "cand" (cells*kmax*3 float: x,y,response), "ncand" (cells int32),
+ *       "cell_k" (cells int32), "maskpts" (2*n int32) -- returns bytes written or <0. */
+long vrf_debug_read(vrf_handle *h, const char *what, int seq, void *dst, size_t dst_bytes);
 
 /* ------------------------------------------------------------------------- */
 /* Back end (declared in vrf_ba.h, included here for convenience)             */

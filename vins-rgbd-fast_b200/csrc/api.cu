@@ -248,9 +248,10 @@ static int enqueue_front(vrf_handle *h, int n, const int32_t *seqs, const uint8_
     }
     CK(cudaMemcpyAsync(h->d_calls, h->h_calls, n * sizeof(SeqCall), cudaMemcpyHostToDevice, h->stream));
     CK(cudaEventRecord(h->call_ev[slot], h->stream));
-    front_launch(h->fc, h->d_calls, n, h->fd, d_frames, frame_bytes, fmt, any_pub, h->sm_count, h->stream, &h->launches);
-    if (h->fc.use_ransac && any_pub) ransac_launch(h->fc, h->d_calls, n, h->fd, h->stream, &h->launches);
-    front_launch_tail(h->fc, h->d_calls, n, h->fd, any_pub, h->stream, &h->launches);
+    LaunchCtx lc{h->stream, &h->launches, &h->prof};
+    front_launch(h->fc, h->d_calls, n, h->fd, d_frames, frame_bytes, fmt, any_pub, h->sm_count, lc);
+    if (h->fc.use_ransac && any_pub) ransac_launch(h->fc, h->d_calls, n, h->fd, lc);
+    front_launch_tail(h->fc, h->d_calls, n, h->fd, any_pub, lc);
     CK(cudaGetLastError());
     for (int i = 0; i < n; ++i) {
         int s = seqs[i];
@@ -364,4 +365,66 @@ extern "C" int vrf_tracker_fetch_batch(vrf_handle *h, int n, const int32_t *seqs
     CK(cudaSetDevice(h->device));
     if (n != h->last_n) return VRF_ERR_ARG;
     return fetch_front(h, n, seqs, outs);
+}
+
+extern "C" long vrf_debug_read(vrf_handle *h, const char *what, int seq, void *dst, size_t dst_bytes)
+{
+    if (!h || !what || !dst || seq < 0 || seq >= h->n_seq) return VRF_ERR_ARG;
+    if (cudaSetDevice(h->device) != cudaSuccess) return VRF_ERR_CUDA;
+    if (cudaStreamSynchronize(h->stream) != cudaSuccess) return VRF_ERR_CUDA;
+    const FrontCfg &c = h->fc;
+    FrontDev &d = h->fd;
+    std::string w(what);
+    if (w.rfind("pyr", 0) == 0 && w.size() == 4) {
+        int l = w[3] - '0';
+        if (l < 0 || l >= c.levels) return VRF_ERR_ARG;
+        size_t need = (size_t)c.lw[l] * c.lh[l];
+        if (dst_bytes < need) return VRF_ERR_ARG;
+        const uint8_t *src = d.pyr[h->cur_buf[seq]] + (size_t)seq * c.pyr_bytes + c.loff[l];
+        if (cudaMemcpy2D(dst, c.lw[l], src, c.lp[l], c.lw[l], c.lh[l], cudaMemcpyDeviceToHost) != cudaSuccess) return VRF_ERR_CUDA;
+        return (long)need;
+    }
+    const void *src = nullptr;
+    size_t need = 0;
+    if (w == "cand") { src = d.cand + (size_t)seq * VRF_MAX_CELLS * c.kmax * 3; need = (size_t)c.ncells * c.kmax * 3 * sizeof(float); }
+    else if (w == "ncand") { src = d.ncand + (size_t)seq * VRF_MAX_CELLS; need = c.ncells * sizeof(int); }
+    else if (w == "cell_k") { src = d.cell_k + (size_t)seq * VRF_MAX_CELLS; need = c.ncells * sizeof(int); }
+    else if (w == "maskpts") {
+        int nm = 0;
+        if (cudaMemcpy(&nm, d.n_maskpts + seq, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return VRF_ERR_CUDA;
+        src = d.maskpts + (size_t)seq * 2 * VRF_CAP; need = (size_t)nm * sizeof(int2);
+    } else return VRF_ERR_ARG;
+    if (dst_bytes < need) return VRF_ERR_ARG;
+    if (need && cudaMemcpy(dst, src, need, cudaMemcpyDeviceToHost) != cudaSuccess) return VRF_ERR_CUDA;
+    return (long)need;
+}
+
+extern "C" int vrf_profile_enable(vrf_handle *h, int on)
+{
+    if (!h) return VRF_ERR_ARG;
+    h->prof.enabled = on != 0;
+    return VRF_OK;
+}
+
+extern "C" int vrf_profile_read(vrf_handle *h, int max_kernels, const char **names, double *total_ms,
+                                uint64_t *launch_counts, int reset)
+{
+    if (!h) return VRF_ERR_ARG;
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->stream));
+    Prof &p = h->prof;
+    for (auto &r : p.recs) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) { p.total_ms[r.id] += ms; p.count[r.id]++; }
+        p.pool.push_back(r.a); p.pool.push_back(r.b);
+    }
+    p.recs.clear();
+    int n = K_COUNT < max_kernels ? K_COUNT : max_kernels;
+    for (int i = 0; i < n; ++i) {
+        if (names) names[i] = kKernelNames[i];
+        if (total_ms) total_ms[i] = p.total_ms[i];
+        if (launch_counts) launch_counts[i] = p.count[i];
+    }
+    if (reset) for (int i = 0; i < K_COUNT; ++i) { p.total_ms[i] = 0; p.count[i] = 0; }
+    return n;
 }

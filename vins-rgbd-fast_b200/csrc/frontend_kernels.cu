@@ -16,6 +16,7 @@
 //   k_fast          gridDetect: FAST-9/16 + NMS + mask + top-K slots, one CTA / cell
 //   k_finish        addPoints, undistortedPoints (+velocity), updateID, outputs
 #include "common.cuh"
+#include "handle.h"
 #include "introsort.h"
 
 namespace vrf {
@@ -621,7 +622,7 @@ k_fast(FrontCfg c, const SeqCall *calls, FrontDev d)
     uint8_t *s_img = smem_raw;
     uint8_t *s_sc = s_img + ((npx + 15) & ~15);
     unsigned *s_kp = reinterpret_cast<unsigned *>(s_sc + ((npx + 15) & ~15));
-    const int kp_cap = npx / 4 + 64;
+    const int kp_cap = (npx / 4 + 64) & ~1;     // even: keeps s_m 8-byte aligned
     int2 *s_m = reinterpret_cast<int2 *>(s_kp + kp_cap);
 
     const uint8_t *img = d.pyr[call.buf_cur] + (size_t)seq * c.pyr_bytes;   // level 0
@@ -663,17 +664,26 @@ k_fast(FrontCfg c, const SeqCall *calls, FrontDev d)
         }
         if (has_run9(mb) || has_run9(md)) {
             // exact cornerScore: max over the 16 arcs of 9 of max(min d, -max d), minus 1
-            int best = -100000;
+            // NOTE (toolchain): ptxas 12.9 for sm_100a folds `max(max(mn, -mx), best)` into a
+            // VIMNMX3 and silently drops the negation (seen in SASS, confirmed on a B200:
+            // scores came out as max|d|-1).  The bright / dark arcs are therefore tracked in
+            // two separate chains and combined once at the end without an integer negate
+            // feeding a min/max: -max(d) == min(255 - d) - 255.
+            int best_b = -100000;      // max over arcs of min(d)
+            int best_e = -100000;      // max over arcs of min(255 - d)
 #pragma unroll
             for (int s = 0; s < 16; ++s) {
-                int mn = dd[s], mx = dd[s];
+                int mn = dd[s], me = 255 - dd[s];
 #pragma unroll
                 for (int j = 1; j < 9; ++j) {
                     int e = dd[(s + j) & 15];
-                    mn = min(mn, e); mx = max(mx, e);
+                    mn = min(mn, e); me = min(me, 255 - e);
                 }
-                best = max(best, max(mn, -mx));
+                best_b = max(best_b, mn);
+                best_e = max(best_e, me);
             }
+            int best_d = best_e - 255;
+            int best = best_b > best_d ? best_b : best_d;
             int sc = best - 1;
             s_sc[y * rw + x] = (uint8_t)(sc >= 10 ? sc : 0);
         }
@@ -879,43 +889,51 @@ int front_configure_kernels(const FrontCfg &c)
 }
 
 int front_launch(const FrontCfg &c, const SeqCall *d_calls, int ncalls, const FrontDev &d,
-                 const uint8_t *d_frames, size_t frame_bytes, int fmt, int any_pub, int sm_count,
-                 cudaStream_t st, uint64_t *launches)
+                 const uint8_t *d_frames, size_t frame_bytes, int fmt, int any_pub, int sm_count, LaunchCtx &lc)
 {
+    cudaStream_t st = lc.st;
     dim3 gi((c.rows * (c.cols >> 4) + 255) / 256, ncalls);
     if (gi.x > 64) gi.x = 64;
+    lc.begin(K_INGEST);
     k_ingest<<<gi, 256, 0, st>>>(c, d_calls, ncalls, d, d_frames, frame_bytes, fmt);
-    ++*launches;
+    lc.end();
     for (int l = 0; l + 1 < c.levels; ++l) {
         dim3 g((c.lw[l + 1] + PD_TW - 1) / PD_TW, (c.lh[l + 1] + PD_TH - 1) / PD_TH, ncalls);
+        lc.begin(K_PYRDOWN);
         k_pyrdown<<<g, 256, 0, st>>>(c, d_calls, d, l);
-        ++*launches;
+        lc.end();
     }
     {
         long long maxwork = (long long)ncalls * VRF_CAP;
         long long want = ((long long)ncalls * (c.max_cnt + 2 * c.ncells) + LK_WPB - 1) / LK_WPB;
         long long cap = (long long)sm_count * 8;
         int grid = (int)max(1LL, min(min(want, cap), maxwork));
+        lc.begin(K_LK);
         k_lk<<<grid, LK_WPB * 32, 0, st>>>(c, d_calls, ncalls, d);
-        ++*launches;
+        lc.end();
     }
+    lc.begin(K_POST_A);
     k_post_a<<<ncalls, 256, 0, st>>>(c, d_calls, d);
-    ++*launches;
+    lc.end();
     return 0;
 }
 
 int front_launch_tail(const FrontCfg &c, const SeqCall *d_calls, int ncalls, const FrontDev &d, int any_pub,
-                      cudaStream_t st, uint64_t *launches)
+                      LaunchCtx &lc)
 {
+    cudaStream_t st = lc.st;
+    lc.begin(K_POST_B);
     k_post_b<<<ncalls, 256, post_b_smem_bytes(), st>>>(c, d_calls, d);
-    ++*launches;
+    lc.end();
     if (any_pub) {
         dim3 g(c.ncells, ncalls);
+        lc.begin(K_FAST);
         k_fast<<<g, 256, fast_smem_bytes(c), st>>>(c, d_calls, d);
-        ++*launches;
+        lc.end();
     }
+    lc.begin(K_FINISH);
     k_finish<<<ncalls, 256, 0, st>>>(c, d_calls, d);
-    ++*launches;
+    lc.end();
     return 0;
 }
 

@@ -8,7 +8,51 @@
 
 namespace vrf {
 struct BaState;   // ba_host.cu
-}
+
+// Kernel ids for launch counting and optional per-kernel CUDA-event profiling.
+enum KernelId {
+    K_INGEST = 0, K_PYRDOWN, K_LK, K_POST_A, K_RANSAC, K_POST_B, K_FAST, K_FINISH,
+    K_BA_SOLVE, K_BA_MARG, K_COUNT
+};
+static const char *const kKernelNames[K_COUNT] = {
+    "k_ingest", "k_pyrdown", "k_lk", "k_post_a", "k_ransac", "k_post_b", "k_fast", "k_finish",
+    "k_ba_solve", "k_ba_marg"};
+
+struct Prof {
+    bool enabled = false;
+    struct Rec { int id; cudaEvent_t a, b; };
+    std::vector<Rec> recs;
+    std::vector<cudaEvent_t> pool;
+    double total_ms[K_COUNT] = {};
+    uint64_t count[K_COUNT] = {};
+};
+
+// Passed to every launcher: stream + launch counter + optional event bracketing.
+struct LaunchCtx {
+    cudaStream_t st;
+    uint64_t *launches;
+    Prof *prof;
+    cudaEvent_t pending_b = nullptr;
+    void begin(int id)
+    {
+        ++*launches;
+        if (prof && prof->enabled) {
+            cudaEvent_t a, b;
+            if (prof->pool.size() >= 2) {
+                a = prof->pool.back(); prof->pool.pop_back();
+                b = prof->pool.back(); prof->pool.pop_back();
+            } else { cudaEventCreate(&a); cudaEventCreate(&b); }
+            cudaEventRecord(a, st);
+            prof->recs.push_back({id, a, b});
+            pending_b = b;
+        }
+    }
+    void end()
+    {
+        if (pending_b) { cudaEventRecord(pending_b, st); pending_b = nullptr; }
+    }
+};
+}  // namespace vrf
 
 struct vrf_handle {
     VrfConfig cfg;
@@ -32,6 +76,7 @@ struct vrf_handle {
     int last_n = 0;
     char errbuf[256];
     uint64_t launches = 0;
+    vrf::Prof prof;
     vrf::BaState *ba = nullptr;
 };
 
@@ -39,12 +84,11 @@ namespace vrf {
 // frontend_kernels.cu
 int front_configure_kernels(const FrontCfg &c);
 int front_launch(const FrontCfg &c, const SeqCall *d_calls, int ncalls, const FrontDev &d, const uint8_t *d_frames,
-                 size_t frame_bytes, int fmt, int any_pub, int sm_count, cudaStream_t st, uint64_t *launches);
+                 size_t frame_bytes, int fmt, int any_pub, int sm_count, LaunchCtx &lc);
 int front_launch_tail(const FrontCfg &c, const SeqCall *d_calls, int ncalls, const FrontDev &d, int any_pub,
-                      cudaStream_t st, uint64_t *launches);
+                      LaunchCtx &lc);
 // ransac_kernels.cu
-int ransac_launch(const FrontCfg &c, const SeqCall *d_calls, int ncalls, const FrontDev &d, cudaStream_t st,
-                  uint64_t *launches);
+int ransac_launch(const FrontCfg &c, const SeqCall *d_calls, int ncalls, const FrontDev &d, LaunchCtx &lc);
 // ba_host.cu
 int ba_create(vrf_handle *h);
 void ba_destroy(vrf_handle *h);

@@ -2,5 +2,5 @@
 #include "common.cuh"
 #include "handle.h"
 namespace vrf {
-int ransac_launch(const FrontCfg &, const SeqCall *, int, const FrontDev &, cudaStream_t, uint64_t *) { return 0; }
+int ransac_launch(const FrontCfg &, const SeqCall *, int, const FrontDev &, LaunchCtx &) { return 0; }
 }

@@ -100,7 +100,7 @@ EXPORTS = [
     "vrf_config_default", "vrf_create", "vrf_destroy", "vrf_strerror", "vrf_last_cuda_error",
     "vrf_launch_count", "vrf_reset_sequence", "vrf_tracker_read_image", "vrf_tracker_read_image_batch",
     "vrf_tracker_enqueue_batch_dev", "vrf_tracker_fetch_batch", "vrf_synchronize", "vrf_stream",
-    "vrf_debug_sort_desc", "vrf_ba_solve", "vrf_ba_solve_batch", "vrf_ba_upload_batch",
+    "vrf_profile_enable", "vrf_profile_read", "vrf_debug_sort_desc", "vrf_debug_read", "vrf_ba_solve", "vrf_ba_solve_batch", "vrf_ba_upload_batch",
     "vrf_ba_enqueue_batch", "vrf_ba_download_batch", "vrf_debug_eval_projection", "vrf_debug_eval_imu",
 ]
 
@@ -139,6 +139,10 @@ def load():
     lib.vrf_stream.restype = C.c_void_p
     lib.vrf_debug_sort_desc.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
     lib.vrf_debug_sort_desc.restype = None
+    lib.vrf_profile_enable.argtypes = [C.c_void_p, C.c_int]
+    lib.vrf_profile_read.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+    lib.vrf_debug_read.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_void_p, C.c_size_t]
+    lib.vrf_debug_read.restype = C.c_long
     lib.vrf_ba_solve.argtypes = [C.c_void_p, C.c_int, C.POINTER(VrfBaProblem), C.POINTER(VrfBaResult)]
     lib.vrf_ba_solve_batch.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.POINTER(VrfBaProblem), C.POINTER(VrfBaResult)]
     lib.vrf_ba_upload_batch.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.POINTER(VrfBaProblem)]
@@ -265,6 +269,30 @@ class Handle:
 
     def synchronize(self):
         check(self.lib.vrf_synchronize(self.h), self.h)
+
+    def profile(self, on):
+        check(self.lib.vrf_profile_enable(self.h, int(on)), self.h)
+
+    def profile_read(self, reset=True):
+        names = (C.c_char_p * 16)()
+        ms = np.zeros(16, np.float64)
+        cnt = np.zeros(16, np.uint64)
+        n = self.lib.vrf_profile_read(self.h, 16, C.cast(names, C.c_void_p), ms.ctypes.data, cnt.ctypes.data, int(reset))
+        check(n, self.h)
+        return {names[i].decode(): (float(ms[i]), int(cnt[i])) for i in range(n)}
+
+    def debug_read(self, what, seq, dtype, count):
+        buf = np.zeros(count, dtype)
+        rc = self.lib.vrf_debug_read(self.h, what.encode(), seq, buf.ctypes.data, buf.nbytes)
+        if rc < 0:
+            raise RuntimeError(f"vrf_debug_read({what}) failed: {rc}")
+        return buf[: rc // buf.itemsize]
+
+    def pyramid_level(self, seq, level):
+        w, hh = self.cfg.col, self.cfg.row
+        for _ in range(level):
+            w, hh = (w + 1) // 2, (hh + 1) // 2
+        return self.debug_read(f"pyr{level}", seq, np.uint8, w * hh).reshape(hh, w)
 
     def reset(self, seq):
         check(self.lib.vrf_reset_sequence(self.h, seq), self.h)
