@@ -183,7 +183,7 @@ def _ref_worker(arg):
     from vrf_b200 import synth
     s = synth.Sequence(seed)
     frames = [s.frame(k)[1] for k in range(min(n, T_FRAMES))]
-    ft = FeatureTrackerRef(FrontendConfig(lk_max_level=2))
+    ft = FeatureTrackerRef(FrontendConfig(lk_max_level=2, use_ransac=int(os.environ.get("VRF_BENCH_RANSAC", "1"))))
     t0 = time.perf_counter()
     for step in range(n):
         idx, pidx = frame_plan(step, len(frames))
@@ -206,7 +206,8 @@ def main():
     ap.add_argument("--ref-frames", type=int, default=24)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
-    args.warmup = max(args.warmup, 3)
+    if args.impl != "reference":
+        args.warmup = max(args.warmup, 3)
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -216,6 +217,17 @@ def main():
         if rank == 0:
             run_reference(args)
         return
+
+    # CPU baseline first, in a child process, before this process creates a CUDA context
+    # (the oracle fans out over all host cores with multiprocessing)
+    cpu_base = None
+    if rank == 0 and not args.no_cpu_baseline:
+        try:
+            out = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "1",
+                                  "--warmup", "0", "--ref-frames", "24"], capture_output=True, text=True, timeout=600)
+            cpu_base = json.loads(out.stdout.strip().splitlines()[-1])["cpu_baseline"]
+        except Exception as e:           # reported, never silently replaced
+            cpu_base = {"value": None, "unit": "frames/s", "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {e}"}
 
     import torch
     import torch.distributed as dist
@@ -238,7 +250,7 @@ def main():
     # pinned host mirrors for the e2e arm
     h_rgb = [torch.from_numpy(b[0]).pin_memory() for b in base]
 
-    cfg = binding.default_config(lk_max_level=2, use_ransac=int(os.environ.get("VRF_BENCH_RANSAC", "0")))
+    cfg = binding.default_config(lk_max_level=2, use_ransac=int(os.environ.get("VRF_BENCH_RANSAC", "1")))
     hnd = binding.Handle(cfg, S, local_rank)
     ext_stream = torch.cuda.ExternalStream(hnd.stream(), device=dev)
     seqs = list(range(S))
@@ -353,16 +365,6 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_val = S * e2e_steps * world / float(t.item())
     hnd2.close()
-
-    cpu_base = None
-    if rank == 0 and not args.no_cpu_baseline:
-        import multiprocessing as mp
-        cores = os.cpu_count() or 1
-        with mp.get_context("fork").Pool(cores) as pool:
-            res = pool.map(_ref_worker, [(1234 + (i % N_DISTINCT), 24) for i in range(cores)])
-        sec = max(r[1] for r in res)
-        cpu_base = {"value": cores * 24 / sec, "unit": "frames/s", "cores": cores, "kind": "port",
-                    "sample": f"{cores} independent sequences x 24 frames, cv2 4.13 (real OpenCV) FAST+PyrLK, python glue, 1 cv2 thread/worker"}
 
     if rank == 0:
         line = {

@@ -104,9 +104,45 @@ def _pad_deriv(d, win):
     return np.pad(d, win, mode="constant")
 
 
+def _sum_a_opencv(P):
+    """float32 accumulation of the 21x21 integer products exactly as OpenCV's SSE path
+    (lkpyramid.cpp, CV_SIMD128): per row, pixels 0..15 go to 4 lane accumulators
+    (lane = x mod 4, float adds in x order), pixels 16..20 to a scalar accumulator;
+    result = scalar + ((l0 + l2) + (l1 + l3))  (v_reduce_sum).  Pinned empirically
+    against cv2 4.13: bit-exact tracks (tests/test_oracle_frontend.py)."""
+    f32 = np.float32
+    vq = np.zeros(4, np.float32)
+    sc = f32(0)
+    Pf = P.astype(np.float32)          # |products| < 2^24: exact
+    for y in range(P.shape[0]):
+        for x0 in (0, 4, 8, 12):
+            vq = (vq + Pf[y, x0:x0 + 4]).astype(np.float32)
+        for x in range(16, P.shape[1]):
+            sc = f32(sc + Pf[y, x])
+    return f32(sc + f32(f32(vq[0] + vq[2]) + f32(vq[1] + vq[3])))
+
+
+def _sum_b_opencv(P):
+    """float32 accumulation of diff*I{x,y} as OpenCV's SSE path: per row and per 8-pixel
+    group, v_dotprod forms the exact int32 pair sums p[k]+p[k+4] (k=0..3), converts them
+    to float and adds them to 4 accumulators; pixels 16..20 go to a scalar float
+    accumulator (each product converted to float first);
+    result = scalar + ((a0 + a2) + (a1 + a3))."""
+    f32 = np.float32
+    acc = np.zeros(4, np.float32)
+    sc = f32(0)
+    for y in range(P.shape[0]):
+        for x0 in (0, 8):
+            p = P[y, x0:x0 + 8]
+            acc = (acc + (p[0:4] + p[4:8]).astype(np.float32)).astype(np.float32)
+        for x in range(16, P.shape[1]):
+            sc = f32(sc + f32(int(P[y, x])))
+    return f32(sc + f32(f32(acc[0] + acc[2]) + f32(acc[1] + acc[3])))
+
+
 def lk_track(prev_pyr, next_pyr, prev_pts, next_pts_init, max_level,
              use_initial_flow=True, win=21, max_count=30, epsilon=0.01,
-             min_eig_threshold=1e-4):
+             min_eig_threshold=1e-4, accum="opencv"):
     """Restatement of cv::calcOpticalFlowPyrLK for 8UC1 images given prebuilt
     pyramids.  Returns (next_pts float32 Nx2, status uint8 N).
 
@@ -162,11 +198,17 @@ def lk_track(prev_pyr, next_pyr, prev_pts, next_pts_init, max_level,
             Iw = (interp(Ip, y0, x0, iw00, iw01, iw10, iw11) + (1 << (W_BITS - 5 - 1))) >> (W_BITS - 5)
             Ix = (interp(dxp, y0, x0, iw00, iw01, iw10, iw11) + (1 << (W_BITS - 1))) >> W_BITS
             Iy = (interp(dyp, y0, x0, iw00, iw01, iw10, iw11) + (1 << (W_BITS - 1))) >> W_BITS
-            # OpenCV accumulates in float32; the exact integer sum rounded once
-            # to float32 differs from it by ~1e-6 relative (summation order).
-            A11 = f32(f32(int((Ix * Ix).sum())) * FLT_SCALE)
-            A12 = f32(f32(int((Ix * Iy).sum())) * FLT_SCALE)
-            A22 = f32(f32(int((Iy * Iy).sum())) * FLT_SCALE)
+            # OpenCV accumulates in float32 in a fixed SIMD lane order; accum="opencv"
+            # reproduces that order bit-exactly, accum="exact" rounds the exact integer
+            # sum once (differs by ~1e-6 relative).
+            if accum == "opencv" and win == 21:
+                A11 = f32(_sum_a_opencv(Ix * Ix) * FLT_SCALE)
+                A12 = f32(_sum_a_opencv(Ix * Iy) * FLT_SCALE)
+                A22 = f32(_sum_a_opencv(Iy * Iy) * FLT_SCALE)
+            else:
+                A11 = f32(f32(int((Ix * Ix).sum())) * FLT_SCALE)
+                A12 = f32(f32(int((Ix * Iy).sum())) * FLT_SCALE)
+                A22 = f32(f32(int((Iy * Iy).sum())) * FLT_SCALE)
             D = f32(A11 * A22 - A12 * A12)
             minEig = f32((A22 + A11 - np.sqrt(f32((A11 - A22) * (A11 - A22) + f32(4.0) * A12 * A12))) / f32(2 * win * win))
             if minEig < f32(min_eig_threshold) or D < FLT_EPSILON:
@@ -189,8 +231,12 @@ def lk_track(prev_pyr, next_pyr, prev_pts, next_pts_init, max_level,
                 w11 = (1 << W_BITS) - w00 - w01 - w10
                 Jw = (interp(Jp, jy + win, jx + win, w00, w01, w10, w11) + (1 << (W_BITS - 5 - 1))) >> (W_BITS - 5)
                 diff = Jw - Iw
-                b1 = f32(f32(int((diff * Ix).sum())) * FLT_SCALE)
-                b2 = f32(f32(int((diff * Iy).sum())) * FLT_SCALE)
+                if accum == "opencv" and win == 21:
+                    b1 = f32(_sum_b_opencv(diff * Ix) * FLT_SCALE)
+                    b2 = f32(_sum_b_opencv(diff * Iy) * FLT_SCALE)
+                else:
+                    b1 = f32(f32(int((diff * Ix).sum())) * FLT_SCALE)
+                    b2 = f32(f32(int((diff * Iy).sum())) * FLT_SCALE)
                 delta = np.array([f32(f32(A12 * b2 - A22 * b1) * D), f32(f32(A12 * b1 - A11 * b2) * D)], np.float32)
                 nextPt = nextPt + delta
                 nextp[p] = nextPt + half

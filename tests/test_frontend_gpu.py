@@ -67,6 +67,27 @@ def test_sequence_parity_reference_default():
     assert n == 12
 
 
+def test_sequence_parity_with_ransac_long():
+    """Reference behaviour incl. rejectWithF (cv::findFundamentalMat RANSAC) on publish frames,
+    24 frames: IDs stay bit-exact over the whole run."""
+    n = 0
+    for k, out, ref in run_pair({}, 24, 4242, ransac=1):
+        check_frame(k, out, ref)
+        if ref.last_ransac_status is not None:
+            n += 1
+    assert n >= 6
+
+
+def test_lk_tracks_bit_exact():
+    """The LK kernel accumulates in OpenCV's SIMD lane order => raw tracks are bit-identical to
+    cv2.calcOpticalFlowPyrLK (no drift between the two pipelines)."""
+    for k, out, ref in run_pair({"lk_max_level": 2}, 10, 2024):
+        if ref.last_lk_pts is not None:
+            assert np.array_equal(out.lk_status, ref.last_lk_status), k
+            assert np.array_equal(out.lk_pts, ref.last_lk_pts), (k, np.abs(out.lk_pts - ref.last_lk_pts).max())
+        assert np.array_equal(out.cur_pts, ref.cur_pts), k
+
+
 def test_sequence_parity_three_level_pyramid():
     """BASELINE config 2: 3-level pyramid (lk_max_level=2)."""
     for k, out, ref in run_pair({"lk_max_level": 2}, 8, 77):

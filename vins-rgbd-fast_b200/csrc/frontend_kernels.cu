@@ -143,21 +143,48 @@ k_pyrdown(FrontCfg c, const SeqCall *calls, FrontDev d, int level)
 //     addressing = the padded pyramid of buildOpticalFlowPyramid),
 //   - Scharr derivatives computed on the fly (REFLECT_101 at the image border,
 //     0 outside the image = BORDER_CONSTANT of the derivative pyramid),
-//   - integer bilinear interpolation (14-bit weights) held in registers,
-//   - exact integer accumulation of the 2x2 normal equations / mismatch vector
-//     with redux.sync warp reductions, float32 update exactly as OpenCV.
+//   - integer bilinear interpolation (14-bit weights), all 32 lanes in parallel,
+//   - the 2x2 normal equations / mismatch vector are accumulated in float32 in
+//     *exactly OpenCV's SIMD lane order* (ordered add chains, one lane per chain),
+//     so tracks are bit-identical to cv2.calcOpticalFlowPyrLK -- no drift between
+//     the two pipelines over long sequences.
 // ---------------------------------------------------------------------------
 #define LK_WPB 8
 #define LK_NPX 14   // ceil(441/32)
+#define LK_R1_BYTES 896     // region 1: 24x24 u8 patch of I, later 441(+7) int16 "diff"
+#define LK_R2_BYTES 1936    // region 2: 22x22 short2 Scharr, later 441(+7) short2 (Ix,Iy) of the window
 
-__global__ void __launch_bounds__(LK_WPB * 32)
+// OpenCV's float accumulation order (lkpyramid.cpp SSE path; pinned bit-exactly against
+// cv2 4.13 in oracle/frontend_spec.py::_sum_a_opencv/_sum_b_opencv):
+//   per window row, pixels 0..15 feed 4 SIMD-lane accumulators, pixels 16..20 a scalar one;
+//   total = scalar + ((l0 + l2) + (l1 + l3)).
+// A-sums: lane j adds float(prod[x]) for x = j, j+4, j+8, j+12 (in that order) per row.
+// b-sums: lane k adds float(prod[x0+k] + prod[x0+k+4]) for x0 = 0, 8 per row (v_dotprod).
+// Each accumulator is an ordered chain of float adds => one warp lane per chain:
+//   lane = 5*q + r, q = which sum, r = 0..3 SIMD lane, r = 4 scalar tail.
+__device__ __forceinline__ float lk_combine(float acc, int q)
+{
+    float l0 = __shfl_sync(0xffffffffu, acc, 5 * q + 0);
+    float l1 = __shfl_sync(0xffffffffu, acc, 5 * q + 1);
+    float l2 = __shfl_sync(0xffffffffu, acc, 5 * q + 2);
+    float l3 = __shfl_sync(0xffffffffu, acc, 5 * q + 3);
+    float tl = __shfl_sync(0xffffffffu, acc, 5 * q + 4);
+    return tl + ((l0 + l2) + (l1 + l3));
+}
+
+__global__ void __launch_bounds__(LK_WPB * 32, 2)
 k_lk(FrontCfg c, const SeqCall *calls, int ncalls, FrontDev d)
 {
-    __shared__ uint8_t s_I[LK_WPB][24 * 24];
-    __shared__ short2 s_D[LK_WPB][22 * 22];
+    __shared__ __align__(16) unsigned char s_r1[LK_WPB][LK_R1_BYTES];
+    __shared__ __align__(16) unsigned char s_r2[LK_WPB][LK_R2_BYTES];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    uint8_t *s_I = s_r1[wib];
+    short *s_diff = reinterpret_cast<short *>(s_r1[wib]);
+    short2 *s_D = reinterpret_cast<short2 *>(s_r2[wib]);
+    const short *s_dI = reinterpret_cast<const short *>(s_r2[wib]);   // interleaved (Ix, Iy) per window pixel
     const int total = d.work_prefix[ncalls];
     const int maxLevel = c.levels - 1;
+    const int cq = lane / 5, cr = lane - 5 * cq;      // accumulation chain owned by this lane
 
     for (int g = blockIdx.x * LK_WPB + wib; g < total; g += gridDim.x * LK_WPB) {
         // locate the batch item: largest ci with prefix[ci] <= g
@@ -216,20 +243,20 @@ k_lk(FrontCfg c, const SeqCall *calls, int ncalls, FrontDev d)
             int iw11 = 16384 - iw00 - iw01 - iw10;
 
             __syncwarp();
-            // stage 24x24 of I (origin ix-1, iy-1)
+            // stage 24x24 of I (origin ix-1, iy-1), REFLECT_101 = the padded pyramid level
             for (int t = lane; t < 576; t += 32) {
                 int sy = t / 24, sx = t - sy * 24;
                 int gx = reflect101(ix - 1 + sx, cols), gy = reflect101(iy - 1 + sy, rows);
-                s_I[wib][t] = __ldg(I + (size_t)gy * pitch + gx);
+                s_I[t] = __ldg(I + (size_t)gy * pitch + gx);
             }
             __syncwarp();
-            // Scharr at the 22x22 positions (ix+dx, iy+dy)
+            // Scharr at the 22x22 positions (ix+dx, iy+dy); 0 outside the image (BORDER_CONSTANT)
             for (int t = lane; t < 484; t += 32) {
                 int dy_ = t / 22, dx_ = t - dy_ * 22;
                 int gx = ix + dx_, gy = iy + dy_;
                 short2 dv = make_short2(0, 0);
                 if (gx >= 0 && gx < cols && gy >= 0 && gy < rows) {
-                    const uint8_t *p = &s_I[wib][(dy_ + 1) * 24 + dx_ + 1];
+                    const uint8_t *p = &s_I[(dy_ + 1) * 24 + dx_ + 1];
                     int p00 = p[-25], p01 = p[-24], p02 = p[-23];
                     int p10 = p[-1], p12 = p[1];
                     int p20 = p[23], p21 = p[24], p22 = p[25];
@@ -239,31 +266,66 @@ k_lk(FrontCfg c, const SeqCall *calls, int ncalls, FrontDev d)
                     dv.x = (short)(t0r - t0l);
                     dv.y = (short)(3 * (t1l + t1r) + 10 * t1c);
                 }
-                s_D[wib][t] = dv;
+                s_D[t] = dv;
             }
             __syncwarp();
-            int Iw[LK_NPX], Ixv[LK_NPX], Iyv[LK_NPX];
-            int a11 = 0, a12 = 0, a22 = 0;
+            // integer bilinear interpolation of the window: I (5 fractional bits), Ix, Iy
+            int Iw[LK_NPX];
+            unsigned dpk[LK_NPX];                 // packed (Ix, Iy) as two int16
 #pragma unroll
             for (int k = 0; k < LK_NPX; ++k) {
                 int p = lane + 32 * k;
                 int iv = 0, ixv = 0, iyv = 0;
                 if (p < 441) {
                     int wy = p / 21, wx = p - wy * 21;
-                    const uint8_t *q = &s_I[wib][(wy + 1) * 24 + wx + 1];
+                    const uint8_t *q = &s_I[(wy + 1) * 24 + wx + 1];
                     iv = ((int)q[0] * iw00 + (int)q[1] * iw01 + (int)q[24] * iw10 + (int)q[25] * iw11 + (1 << 8)) >> 9;
-                    const short2 *dq = &s_D[wib][wy * 22 + wx];
+                    const short2 *dq = &s_D[wy * 22 + wx];
                     short2 d00 = dq[0], d01 = dq[1], d10 = dq[22], d11 = dq[23];
                     ixv = (d00.x * iw00 + d01.x * iw01 + d10.x * iw10 + d11.x * iw11 + (1 << 13)) >> 14;
                     iyv = (d00.y * iw00 + d01.y * iw01 + d10.y * iw10 + d11.y * iw11 + (1 << 13)) >> 14;
                 }
-                Iw[k] = iv; Ixv[k] = ixv; Iyv[k] = iyv;
-                a11 += ixv * ixv; a12 += ixv * iyv; a22 += iyv * iyv;
+                Iw[k] = iv;
+                dpk[k] = ((unsigned)ixv & 0xFFFFu) | ((unsigned)iyv << 16);
+            }
+            __syncwarp();
+            // regions are free now: region 2 <- (Ix,Iy) per window pixel
+#pragma unroll
+            for (int k = 0; k < LK_NPX; ++k) {
+                int p = lane + 32 * k;
+                if (p < 448) reinterpret_cast<unsigned *>(s_r2[wib])[p] = (p < 441) ? dpk[k] : 0u;
+            }
+            __syncwarp();
+            // A11, A12, A22: 15 ordered float chains (lanes 0..14)
+            float A11, A12, A22;
+            {
+                float acc = 0.f;
+                if (lane < 15) {
+                    const int sa = (cq == 2) ? 1 : 0, sb = (cq == 0) ? 0 : 1;   // (Ix,Ix) (Ix,Iy) (Iy,Iy)
+#pragma unroll 1
+                    for (int y = 0; y < VRF_LK_WIN; ++y) {
+                        const short *row = s_dI + 2 * (y * 21);
+                        if (cr < 4) {
+#pragma unroll
+                            for (int gq = 0; gq < 4; ++gq) {
+                                const short *e = row + 2 * (4 * gq + cr);
+                                acc += (float)((int)e[sa] * (int)e[sb]);
+                            }
+                        } else {
+#pragma unroll
+                            for (int x = 16; x < 21; ++x) {
+                                const short *e = row + 2 * x;
+                                acc += (float)((int)e[sa] * (int)e[sb]);
+                            }
+                        }
+                    }
+                }
+                A11 = lk_combine(acc, 0);
+                A12 = lk_combine(acc, 1);
+                A22 = lk_combine(acc, 2);
             }
             const float FLT_SCALE = 1.f / (float)(1 << 20);
-            float A11 = (float)warp_sum_i64(a11) * FLT_SCALE;
-            float A12 = (float)warp_sum_i64(a12) * FLT_SCALE;
-            float A22 = (float)warp_sum_i64(a22) * FLT_SCALE;
+            A11 *= FLT_SCALE; A12 *= FLT_SCALE; A22 *= FLT_SCALE;
             float D = A11 * A22 - A12 * A12;
             float minEig = (A22 + A11 - sqrtf((A11 - A22) * (A11 - A22) + 4.f * A12 * A12)) / 882.f;
             if (minEig < 1e-4f || D < 1.1920929e-07f) {
@@ -284,8 +346,8 @@ k_lk(FrontCfg c, const SeqCall *calls, int ncalls, FrontDev d)
                 const int w01 = __float2int_rn(a * (1.f - b) * 16384.f);
                 const int w10 = __float2int_rn((1.f - a) * b * 16384.f);
                 const int w11 = 16384 - w00 - w01 - w10;
-                int b1 = 0, b2 = 0;
                 const bool inside = (jx >= 0) && (jy >= 0) && (jx + 22 <= cols) && (jy + 22 <= rows);
+                __syncwarp();
                 if (inside) {
                     const uint8_t *Jb = J + (size_t)jy * pitch + jx;
 #pragma unroll
@@ -296,10 +358,9 @@ k_lk(FrontCfg c, const SeqCall *calls, int ncalls, FrontDev d)
                             const uint8_t *q = Jb + wy * pitch + wx;
                             int jv = ((int)__ldg(q) * w00 + (int)__ldg(q + 1) * w01 + (int)__ldg(q + pitch) * w10 +
                                       (int)__ldg(q + pitch + 1) * w11 + (1 << 8)) >> 9;
-                            int diff = jv - Iw[k];
-                            b1 += diff * Ixv[k];
-                            b2 += diff * Iyv[k];
-                        }
+                            s_diff[p] = (short)(jv - Iw[k]);
+                        } else if (p < 448)
+                            s_diff[p] = 0;
                     }
                 } else {
 #pragma unroll
@@ -312,14 +373,34 @@ k_lk(FrontCfg c, const SeqCall *calls, int ncalls, FrontDev d)
                             const uint8_t *r0 = J + (size_t)y0 * pitch, *r1 = J + (size_t)y1 * pitch;
                             int jv = ((int)__ldg(r0 + x0) * w00 + (int)__ldg(r0 + x1) * w01 + (int)__ldg(r1 + x0) * w10 +
                                       (int)__ldg(r1 + x1) * w11 + (1 << 8)) >> 9;
-                            int diff = jv - Iw[k];
-                            b1 += diff * Ixv[k];
-                            b2 += diff * Iyv[k];
+                            s_diff[p] = (short)(jv - Iw[k]);
+                        } else if (p < 448)
+                            s_diff[p] = 0;
+                    }
+                }
+                __syncwarp();
+                // b1, b2: 10 ordered float chains (lanes 0..9)
+                float acc = 0.f;
+                if (lane < 10) {
+#pragma unroll 1
+                    for (int y = 0; y < VRF_LK_WIN; ++y) {
+                        const short *df = s_diff + y * 21;
+                        const short *di = s_dI + 2 * (y * 21) + cq;       // + cq selects Ix (b1) / Iy (b2)
+                        if (cr < 4) {
+#pragma unroll
+                            for (int hq = 0; hq < 2; ++hq) {
+                                int x = 8 * hq + cr;
+                                int v = (int)df[x] * (int)di[2 * x] + (int)df[x + 4] * (int)di[2 * (x + 4)];   // v_dotprod
+                                acc += (float)v;
+                            }
+                        } else {
+#pragma unroll
+                            for (int x = 16; x < 21; ++x) acc += (float)((int)df[x] * (int)di[2 * x]);
                         }
                     }
                 }
-                float fb1 = (float)warp_sum_i64(b1) * FLT_SCALE;
-                float fb2 = (float)warp_sum_i64(b2) * FLT_SCALE;
+                float fb1 = lk_combine(acc, 0) * FLT_SCALE;
+                float fb2 = lk_combine(acc, 1) * FLT_SCALE;
                 float2 delta = make_float2((A12 * fb2 - A22 * fb1) * D, (A12 * fb1 - A11 * fb2) * D);
                 nextPt.x += delta.x; nextPt.y += delta.y;
                 nextStored = make_float2(nextPt.x + VRF_LK_HALF, nextPt.y + VRF_LK_HALF);
