@@ -27,6 +27,10 @@ extern "C" {
 #define VRF_MARGIN_OLD          0   /* estimator.h: MARGIN_OLD */
 #define VRF_MARGIN_SECOND_NEW   1   /* estimator.h: MARGIN_SECOND_NEW */
 
+/* pass as VrfBaProblem::prior to reuse the prior the library kept on the device from the
+ * previous vrf_ba_solve of this sequence (last_marginalization_info, estimator.h:167) */
+#define VRF_PRIOR_DEVICE ((const VrfPrior *)(uintptr_t)1)
+
 #define VRF_PRIOR_MAX_BLOCKS   40
 #define VRF_PRIOR_MAX_DIM     176   /* 6 (ex) + 1 (td) + 11*6 + 11*9 = 172, padded */
 
@@ -136,19 +140,6 @@ int vrf_ba_solve_batch(vrf_handle *h, int n, const int32_t *seqs,
 int vrf_ba_upload_batch(vrf_handle *h, int n, const int32_t *seqs, const VrfBaProblem *probs);
 int vrf_ba_enqueue_batch(vrf_handle *h, int n, const int32_t *seqs);
 int vrf_ba_download_batch(vrf_handle *h, int n, const int32_t *seqs, VrfBaResult *res);
-
-/* Single-factor evaluation hooks (parity tests of rows B2-B5 in SURVEY.md section 8a):
- * evaluate one factor on the GPU and return raw residual + Jacobians (row-major,
- * global parameterisation sizes as in the reference's SizedCostFunction<...>). */
-int vrf_debug_eval_projection(vrf_handle *h, int n, const double *pose_i /*n*7*/, const double *pose_j,
-                              const double *ex_pose, const double *inv_dep, const double *pts_i /*n*2*/,
-                              const double *pts_j, double *residuals /*n*2*/,
-                              double *jac_pose_i /*n*2*7*/, double *jac_pose_j, double *jac_ex,
-                              double *jac_feat /*n*2*/);
-int vrf_debug_eval_imu(vrf_handle *h, int n, const VrfImuPreint *pre, const double *pose_i,
-                       const double *sb_i /*n*9*/, const double *pose_j, const double *sb_j,
-                       double *residuals /*n*15*/, double *jac_pose_i /*n*15*7*/, double *jac_sb_i /*n*15*9*/,
-                       double *jac_pose_j, double *jac_sb_j);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,153 @@
+"""GPU parity tests of the back end: vrf_ba_solve* (CUDA, through the C ABI) against the
+C oracle (oracle/ba_ref.c) on identical seeded sliding-window problems.
+
+Bars: same iteration/acceptance sequence; costs to 1e-9 relative; optimised poses within
+1e-4 m (north_star) -- asserted at 1e-7; the new marginalization prior compared through its
+sign/rotation-invariant content J0^T J0 and J0^T r0."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from oracle import ba_ref
+from vrf_b200 import ba_problem as BP
+from vrf_b200 import binding as B
+
+pytestmark = pytest.mark.gpu
+
+POSE_TOL = 1e-7          # m (bar: 1e-4 m)
+
+
+def make_cfg(**kw):
+    cfg = B.default_config(use_ransac=0)
+    cfg.num_iterations = 8; cfg.fix_depth = 0; cfg.depth_max_dist = 10.0; cfg.g_norm = 9.81
+    cfg.acc_n = 0.1; cfg.acc_w = 0.001; cfg.gyr_n = 0.01; cfg.gyr_w = 0.0001
+    for k, v in kw.items():
+        setattr(cfg, k, v)
+    return cfg
+
+
+def compare(sol_g, sol_o, pb, tol=POSE_TOL):
+    cg, co = sol_g.c, sol_o.c
+    assert (cg.iterations, cg.successful_steps, cg.termination) == (co.iterations, co.successful_steps, co.termination)
+    assert abs(cg.initial_cost - co.initial_cost) <= 1e-9 * co.initial_cost
+    assert abs(cg.final_cost - co.final_cost) <= 1e-7 * co.final_cost
+    assert np.abs(sol_g.pose[:, :3] - sol_o.pose[:, :3]).max() <= tol
+    assert np.abs(sol_g.pose[:, 3:] - sol_o.pose[:, 3:]).max() <= tol
+    assert np.abs(sol_g.sb - sol_o.sb).max() <= 10 * tol
+    assert np.abs(sol_g.lam[:pb.M] - sol_o.lam[:pb.M]).max() <= 10 * tol
+    assert np.abs(sol_g.Ps - sol_o.Ps).max() <= tol
+    assert np.abs(sol_g.Rs - sol_o.Rs).max() <= tol
+    assert np.abs(sol_g.Vs - sol_o.Vs).max() <= 10 * tol
+
+
+def compare_prior(pg, po):
+    assert pg.n == po.n and pg.n_blocks == po.n_blocks
+    bg, bo = BP.prior_blocks(pg), BP.prior_blocks(po)
+    for a, b in zip(bg, bo):
+        assert a[:4] == b[:4]
+        assert np.abs(np.array(a[4]) - np.array(b[4])).max() <= 1e-7
+    Ag, gg = BP.prior_normal_equations(pg)
+    Ao, go = BP.prior_normal_equations(po)
+    assert np.abs(Ag - Ao).max() <= 1e-6 * np.abs(Ao).max()
+    assert np.abs(gg - go).max() <= 1e-6 * max(1.0, np.abs(go).max())
+
+
+def test_window_chain_matches_oracle():
+    """4 consecutive windows (MARGIN_OLD); every GPU solve starts from the oracle's prior so
+    that each call is compared on identical inputs."""
+    cfg = make_cfg()
+    h = B.Handle(cfg, 1, 0)
+    sim = BP.WindowSimulator(5, cfg, n_landmarks=150)
+    for a in range(4):
+        pb = sim.window(a)
+        so = ba_ref.solve(cfg, pb)
+        sg = h.ba_solve(0, pb)
+        compare(sg, so, pb)
+        assert sg.c.has_new_prior == so.c.has_new_prior == 1
+        compare_prior(sg.new_prior, so.new_prior)
+        sim.commit(a, so)
+    h.close()
+
+
+def test_device_resident_prior_chain():
+    """The library keeps last_marginalization_info on the device: a GPU-only chain
+    (VRF_PRIOR_DEVICE) tracks the oracle chain."""
+    cfg = make_cfg()
+    h = B.Handle(cfg, 1, 0)
+    sim_o = BP.WindowSimulator(9, cfg, n_landmarks=120)
+    sim_g = BP.WindowSimulator(9, cfg, n_landmarks=120)
+    for a in range(4):
+        pbo = sim_o.window(a)
+        so = ba_ref.solve(cfg, pbo)
+        sim_o.commit(a, so)
+        pbg = sim_g.window(a)
+        if a > 0:
+            pbg.c.prior = C.cast(C.c_void_p(1), C.POINTER(B.VrfPrior))      # VRF_PRIOR_DEVICE
+        sg = h.ba_solve(0, pbg)
+        sim_g.commit(a, sg)
+        assert np.abs(sg.Ps - so.Ps).max() <= 1e-5          # chains are independent from window 1 on
+        assert abs(sg.c.final_cost - so.c.final_cost) <= 1e-4 * so.c.final_cost
+    h.close()
+
+
+def test_margin_second_new_and_batch():
+    """Batch of 3 sequences; the third marginalises the second-newest frame (prior only)."""
+    cfg = make_cfg()
+    h = B.Handle(cfg, 3, 0)
+    sims = [BP.WindowSimulator(20 + i, cfg, n_landmarks=100 + 40 * i) for i in range(3)]
+    # first window for all (creates priors)
+    pbs = [s.window(0) for s in sims]
+    sos = [ba_ref.solve(cfg, pb) for pb in pbs]
+    sgs = h.ba_solve_batch([0, 1, 2], pbs)
+    for sg, so, pb, s in zip(sgs, sos, pbs, sims):
+        compare(sg, so, pb)
+        compare_prior(sg.new_prior, so.new_prior)
+        s.commit(0, so)
+    flags = [B.MARGIN_OLD, B.MARGIN_OLD, B.MARGIN_SECOND_NEW]
+    pbs = [s.window(1, marg_flag=f) for s, f in zip(sims, flags)]
+    sos = [ba_ref.solve(cfg, pb) for pb in pbs]
+    sgs = h.ba_solve_batch([2, 0, 1], [pbs[2], pbs[0], pbs[1]])
+    for sg, i in zip(sgs, [2, 0, 1]):
+        compare(sg, sos[i], pbs[i])
+        assert sg.c.has_new_prior == sos[i].c.has_new_prior == 1
+        compare_prior(sg.new_prior, sos[i].new_prior)
+    h.close()
+
+
+def test_fixed_depth_and_no_prior():
+    """fix_depth=1: landmarks measured by the depth sensor (estimate_flag 1) are constant
+    parameter blocks (estimator.cpp:1291-1292); first window has no prior."""
+    cfg = make_cfg(fix_depth=1)
+    h = B.Handle(cfg, 1, 0)
+    sim = BP.WindowSimulator(33, cfg, n_landmarks=130, flag2_frac=0.3)
+    pb = sim.window(0)
+    so = ba_ref.solve(cfg, pb)
+    sg = h.ba_solve(0, pb)
+    compare(sg, so, pb)
+    const = pb.flag == 1
+    assert np.array_equal(sg.lam[:pb.M][const], pb.lam[const])        # untouched
+    compare_prior(sg.new_prior, so.new_prior)
+    h.close()
+
+
+def test_window_not_full_has_no_prior():
+    cfg = make_cfg()
+    h = B.Handle(cfg, 1, 0)
+    sim = BP.WindowSimulator(41, cfg, n_landmarks=80)
+    pb = sim.window(0)
+    pb.c.frame_count = 6
+    # drop observations beyond frame 6
+    keep_l, lam, start, flag, ptr, pts = [], [], [], [], [0], []
+    for l in range(pb.M):
+        o0, o1 = pb.obs_ptr[l], pb.obs_ptr[l + 1]
+        n = min(o1 - o0, 7 - pb.start[l])
+        if n >= 2:
+            lam.append(pb.lam[l]); start.append(pb.start[l]); flag.append(pb.flag[l])
+            pts.extend(pb.obs_pts[o0:o0 + n]); ptr.append(len(pts))
+    pb.set_landmarks(lam, start, flag, ptr, np.array(pts)); pb.finalize()
+    so = ba_ref.solve(cfg, pb)
+    sg = h.ba_solve(0, pb)
+    compare(sg, so, pb)
+    assert sg.c.has_new_prior == so.c.has_new_prior == 0
+    h.close()

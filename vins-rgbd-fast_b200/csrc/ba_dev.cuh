@@ -1,0 +1,78 @@
+// ba_dev.cuh -- device-side problem layout of the back end (shared by ba_kernels.cu,
+// ba_marg.cu and ba_host.cu).
+#pragma once
+#include "common.cuh"
+#include "handle.h"
+
+#define BA_NF VRF_NUM_FRAMES
+#define BA_NC 171                 // 11*6 pose + 11*9 speed-bias + 6 ex-pose tangent columns
+#define BA_THREADS 512
+#define BA_MAX_LM 1024            // >= NUM_OF_F (parameters.h:14)
+#define BA_MAX_OBS 8192
+#define BA_MAX_M0 384             // landmarks hosted at frame 0 that one marginalization can drop
+#define BA_MAX_POS (15 + BA_MAX_M0 + BA_NC)
+
+namespace vrf {
+
+struct BaMeta {
+    int M, nobs, nimu, np, nframes, use_imu, max_iter, marg_flag, has_prior, frame_count;
+    int imu_j[BA_NF];
+    double g_norm;
+};
+
+// prior as stored on device (MarginalizationInfo: marginalization_factor.h:62-74); produced by
+// k_ba_marg or uploaded from a host VrfPrior.  J0 has leading dimension n.
+struct BaPriorStore {
+    int n, n_blocks, valid, pad;
+    int kind[VRF_PRIOR_MAX_BLOCKS], index[VRF_PRIOR_MAX_BLOCKS], size[VRF_PRIOR_MAX_BLOCKS], idx[VRF_PRIOR_MAX_BLOCKS];
+    double x0[VRF_PRIOR_MAX_BLOCKS * 9];
+    double r0[VRF_PRIOR_MAX_DIM];
+    double J0[VRF_PRIOR_MAX_DIM * VRF_PRIOR_MAX_DIM];
+};
+
+struct BaProbDev {
+    // inputs
+    const double *pose0, *sb0, *ex0;      // [11*7], [11*9], [7]
+    const double *lam0;                   // [M]
+    const int *start, *obs_ptr;
+    const uint8_t *lm_const;
+    const double *lm_ub;
+    const double *obs;                    // [nobs][2]
+    const VrfImuPreint *imu;              // [10]
+    const BaPriorStore *prior;            // NULL: no prior
+    BaPriorStore *prior_next;             // written by the marginalization kernel
+    double *HP;                           // [176*176] J0^T J0 scratch
+    int *colmap;                          // [176] prior column -> tangent column (-1: constant block)
+    // scratch / state
+    double *lam, *clam;                   // current / candidate inverse depths
+    double *W;                            // [M][66]
+    double *hll, *gl, *jscale_l, *diag_l, *gd_l, *gn_l, *u_l, *y_l, *hinv_l;
+    double *imuS;                         // [10][225] sqrt information (upper)
+};
+
+struct BaOutDev {
+    int status, iterations, successful, termination;
+    double initial_cost, final_cost;
+    double pose[BA_NF * 7], sb[BA_NF * 9], ex[7];
+    // double2vector (gauge fix) results
+    double Ps[BA_NF * 3], Rs[BA_NF * 9], Vs[BA_NF * 3], Bas[BA_NF * 3], Bgs[BA_NF * 3];
+    // states re-packed by vector2double after the gauge fix (marginalization linearises here)
+    double mpose[BA_NF * 7], msb[BA_NF * 9], mex[7];
+    int has_new_prior, pad;
+};
+
+// global scratch of the marginalization kernel (per problem)
+struct BaMargDev {
+    double *A, *b;          // [pos*pos], [pos]
+    double *V, *Ainv;       // [m*m]
+    double *T;              // [n*m]
+    double *Ar, *V2, *br;   // [n*n], [n*n], [n]
+    int *lmcol;             // [M] column of a dropped landmark (or -1)
+};
+
+// ba_kernels.cu / ba_marg.cu
+size_t ba_solve_smem_bytes();
+int ba_solve_launch(const BaMeta *d_meta, const BaProbDev *d_prob, BaOutDev *d_out, int n, LaunchCtx &lc);
+int ba_marg_launch(const BaMeta *d_meta, const BaProbDev *d_prob, BaOutDev *d_out, BaMargDev *d_marg, int n, LaunchCtx &lc);
+
+}  // namespace vrf

@@ -1,15 +1,329 @@
-// ba_host.cu -- back-end entry points (placeholder until the BA kernels land).
-#include "common.cuh"
-#include "handle.h"
+// ba_host.cu -- back-end entry points of the C ABI (include/vrf_ba.h): packs one
+// Estimator::optimization() call per sequence (vector2double order, reference
+// estimator.cpp:936-981 + problem assembly :1166-1302) into device buffers, launches the
+// solve + marginalization kernels, and unpacks results.  Thin host code; no arithmetic of
+// the hot path happens here.
+#include <new>
+#include <vector>
+
+#include "ba_dev.cuh"
+
 namespace vrf {
-int ba_create(vrf_handle *) { return VRF_OK; }
-void ba_destroy(vrf_handle *) {}
-int ba_reset_sequence(vrf_handle *, int) { return VRF_OK; }
+
+// pinned host staging of one packed problem
+struct BaHostPack {
+    double pose[BA_NF * 7], sb[BA_NF * 9], ex[7];
+    VrfImuPreint imu[BA_NF - 1];
+    double lam[BA_MAX_LM], lm_ub[BA_MAX_LM];
+    int start[BA_MAX_LM], obs_ptr[BA_MAX_LM + 1];
+    uint8_t lm_const[BA_MAX_LM];
+    double obs[BA_MAX_OBS * 2];
+};
+
+struct BaState {
+    int n_seq = 0;
+    BaHostPack *h_pack = nullptr;       // pinned [n_seq]
+    BaHostPack *d_pack = nullptr;       // device [n_seq]
+    BaMeta *h_meta = nullptr, *d_meta = nullptr;
+    BaProbDev *h_prob = nullptr, *d_prob = nullptr;
+    BaOutDev *h_out = nullptr, *d_out = nullptr;
+    BaMargDev *h_marg = nullptr, *d_marg = nullptr;
+    BaPriorStore *d_prior[2] = {nullptr, nullptr};   // [n_seq] each; cur index per sequence below
+    BaPriorStore *h_prior = nullptr;                 // pinned staging [1]
+    std::vector<int> prior_cur;                      // which store is "last_marginalization_info"
+    std::vector<uint8_t> prior_valid;
+    // per-sequence scratch
+    double *d_lam = nullptr, *d_clam = nullptr, *d_W = nullptr, *d_vecs = nullptr, *d_imuS = nullptr, *d_HP = nullptr;
+    int *d_colmap = nullptr;
+    double *d_margbuf = nullptr;
+    int *d_lmcol = nullptr;
+    std::vector<int> last_M;
+    std::vector<int> last_slots;
+};
+
+static const size_t kMargDoubles = (size_t)BA_MAX_POS * BA_MAX_POS + BA_MAX_POS + 2 * (size_t)(15 + BA_MAX_M0) * (15 + BA_MAX_M0) +
+                                   (size_t)VRF_PRIOR_MAX_DIM * (15 + BA_MAX_M0) + 2 * (size_t)VRF_PRIOR_MAX_DIM * VRF_PRIOR_MAX_DIM +
+                                   VRF_PRIOR_MAX_DIM;
+
+#define BCK(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { snprintf(h->errbuf, sizeof(h->errbuf), "%s:%d %s", __FILE__, __LINE__, cudaGetErrorString(e__)); return VRF_ERR_CUDA; } } while (0)
+
+int ba_create(vrf_handle *h)
+{
+    BaState *b = new (std::nothrow) BaState();
+    if (!b) return VRF_ERR_ARG;
+    h->ba = b;
+    const size_t S = h->n_seq;
+    b->n_seq = h->n_seq;
+    BCK(cudaMallocHost((void **)&b->h_pack, S * sizeof(BaHostPack)));
+    BCK(cudaMalloc((void **)&b->d_pack, S * sizeof(BaHostPack)));
+    BCK(cudaMallocHost((void **)&b->h_meta, S * sizeof(BaMeta)));
+    BCK(cudaMalloc((void **)&b->d_meta, S * sizeof(BaMeta)));
+    BCK(cudaMallocHost((void **)&b->h_prob, S * sizeof(BaProbDev)));
+    BCK(cudaMalloc((void **)&b->d_prob, S * sizeof(BaProbDev)));
+    BCK(cudaMallocHost((void **)&b->h_out, S * sizeof(BaOutDev)));
+    BCK(cudaMalloc((void **)&b->d_out, S * sizeof(BaOutDev)));
+    BCK(cudaMallocHost((void **)&b->h_marg, S * sizeof(BaMargDev)));
+    BCK(cudaMalloc((void **)&b->d_marg, S * sizeof(BaMargDev)));
+    for (int k = 0; k < 2; ++k) {
+        BCK(cudaMalloc((void **)&b->d_prior[k], S * sizeof(BaPriorStore)));
+        BCK(cudaMemset(b->d_prior[k], 0, S * sizeof(BaPriorStore)));
+    }
+    BCK(cudaMallocHost((void **)&b->h_prior, sizeof(BaPriorStore)));
+    BCK(cudaMalloc((void **)&b->d_lam, S * BA_MAX_LM * sizeof(double)));
+    BCK(cudaMalloc((void **)&b->d_clam, S * BA_MAX_LM * sizeof(double)));
+    BCK(cudaMalloc((void **)&b->d_W, S * BA_MAX_LM * 66 * sizeof(double)));
+    BCK(cudaMalloc((void **)&b->d_vecs, S * 9 * BA_MAX_LM * sizeof(double)));
+    BCK(cudaMalloc((void **)&b->d_imuS, S * (BA_NF - 1) * 225 * sizeof(double)));
+    BCK(cudaMalloc((void **)&b->d_HP, S * VRF_PRIOR_MAX_DIM * VRF_PRIOR_MAX_DIM * sizeof(double)));
+    BCK(cudaMalloc((void **)&b->d_colmap, S * VRF_PRIOR_MAX_DIM * sizeof(int)));
+    BCK(cudaMalloc((void **)&b->d_margbuf, S * kMargDoubles * sizeof(double)));
+    BCK(cudaMalloc((void **)&b->d_lmcol, S * BA_MAX_LM * sizeof(int)));
+    b->prior_cur.assign(S, 0);
+    b->prior_valid.assign(S, 0);
+    b->last_M.assign(S, 0);
+    return VRF_OK;
 }
-extern "C" int vrf_ba_solve(vrf_handle *, int, const VrfBaProblem *, VrfBaResult *) { return VRF_ERR_UNSUPPORTED; }
-extern "C" int vrf_ba_solve_batch(vrf_handle *, int, const int32_t *, const VrfBaProblem *, VrfBaResult *) { return VRF_ERR_UNSUPPORTED; }
-extern "C" int vrf_ba_upload_batch(vrf_handle *, int, const int32_t *, const VrfBaProblem *) { return VRF_ERR_UNSUPPORTED; }
-extern "C" int vrf_ba_enqueue_batch(vrf_handle *, int, const int32_t *) { return VRF_ERR_UNSUPPORTED; }
-extern "C" int vrf_ba_download_batch(vrf_handle *, int, const int32_t *, VrfBaResult *) { return VRF_ERR_UNSUPPORTED; }
-extern "C" int vrf_debug_eval_projection(vrf_handle *, int, const double *, const double *, const double *, const double *, const double *, const double *, double *, double *, double *, double *, double *) { return VRF_ERR_UNSUPPORTED; }
-extern "C" int vrf_debug_eval_imu(vrf_handle *, int, const VrfImuPreint *, const double *, const double *, const double *, const double *, double *, double *, double *, double *, double *) { return VRF_ERR_UNSUPPORTED; }
+
+void ba_destroy(vrf_handle *h)
+{
+    BaState *b = h->ba;
+    if (!b) return;
+    void *dev[] = {b->d_pack, b->d_meta, b->d_prob, b->d_out, b->d_marg, b->d_prior[0], b->d_prior[1], b->d_lam, b->d_clam,
+                   b->d_W, b->d_vecs, b->d_imuS, b->d_HP, b->d_colmap, b->d_margbuf, b->d_lmcol};
+    for (void *p : dev) if (p) cudaFree(p);
+    void *host[] = {b->h_pack, b->h_meta, b->h_prob, b->h_out, b->h_marg, b->h_prior};
+    for (void *p : host) if (p) cudaFreeHost(p);
+    delete b;
+    h->ba = nullptr;
+}
+
+int ba_reset_sequence(vrf_handle *h, int seq)
+{
+    BaState *b = h->ba;
+    if (!b) return VRF_OK;
+    b->prior_valid[seq] = 0;
+    return VRF_OK;
+}
+
+static int pack_problem(vrf_handle *h, int slot, int seq, const VrfBaProblem *pb)
+{
+    BaState *b = h->ba;
+    if (!pb || pb->n_landmarks < 0 || pb->n_landmarks > BA_MAX_LM || pb->n_obs > BA_MAX_OBS) return VRF_ERR_CAPACITY;
+    if (pb->frame_count < 1 || pb->frame_count > VRF_WINDOW_SIZE) return VRF_ERR_ARG;
+    if (!pb->ex_constant || !pb->td_constant) return VRF_ERR_UNSUPPORTED;     // estimate_extrinsic / estimate_td: later rounds
+    if (pb->n_landmarks > 0 && (!pb->para_Feature || !pb->lm_start_frame || !pb->lm_estimate_flag || !pb->lm_obs_ptr || !pb->obs_pts)) return VRF_ERR_ARG;
+    if (pb->use_imu && !pb->imu) return VRF_ERR_ARG;
+    BaHostPack &k = b->h_pack[slot];
+    memcpy(k.pose, pb->para_Pose, sizeof(k.pose));
+    memcpy(k.sb, pb->para_SpeedBias, sizeof(k.sb));
+    memcpy(k.ex, pb->para_Ex_Pose, sizeof(k.ex));
+    if (pb->use_imu) memcpy(k.imu, pb->imu, sizeof(VrfImuPreint) * pb->frame_count);
+    const int M = pb->n_landmarks;
+    for (int l = 0; l < M; ++l) {
+        k.lam[l] = pb->para_Feature[l];
+        k.start[l] = pb->lm_start_frame[l];
+        k.obs_ptr[l] = pb->lm_obs_ptr[l];
+        const int nobs = pb->lm_obs_ptr[l + 1] - pb->lm_obs_ptr[l];
+        if (nobs < 1 || pb->lm_start_frame[l] < 0 || pb->lm_start_frame[l] + nobs - 1 > pb->frame_count) return VRF_ERR_ARG;
+        // estimator.cpp:1291-1298: constant if (flag==1 && FIX_DEPTH); upper bound if flag==2
+        k.lm_const[l] = (pb->lm_estimate_flag[l] == 1 && h->cfg.fix_depth) ? 1 : 0;
+        k.lm_ub[l] = (pb->lm_estimate_flag[l] == 2) ? 2.0 / h->cfg.depth_max_dist : INFINITY;
+    }
+    k.obs_ptr[M] = M ? pb->lm_obs_ptr[M] : 0;
+    if (k.obs_ptr[M] != pb->n_obs) return VRF_ERR_ARG;
+    memcpy(k.obs, pb->obs_pts, sizeof(double) * 2 * pb->n_obs);
+
+    BaMeta &mt = b->h_meta[slot];
+    memset(&mt, 0, sizeof(mt));
+    mt.M = M; mt.nobs = pb->n_obs; mt.nframes = pb->frame_count + 1; mt.use_imu = pb->use_imu;
+    mt.frame_count = pb->frame_count;
+    mt.max_iter = pb->max_iterations > 0 ? pb->max_iterations : h->cfg.num_iterations;
+    mt.marg_flag = pb->marginalization_flag;
+    mt.g_norm = h->cfg.g_norm;
+    mt.nimu = 0;
+    if (pb->use_imu)
+        for (int j = 1; j <= pb->frame_count; ++j) {
+            if (pb->imu[j - 1].sum_dt > 10.0) continue;          // estimator.cpp:1231-1233
+            mt.imu_j[mt.nimu++] = j;
+        }
+    // prior: host-supplied, device-resident from the previous call, or none
+    int have_prior = 0;
+    if (pb->prior == VRF_PRIOR_DEVICE) have_prior = b->prior_valid[seq];
+    else if (pb->prior) {
+        const VrfPrior *P = pb->prior;
+        if (P->n < 0 || P->n > VRF_PRIOR_MAX_DIM || P->n_blocks > VRF_PRIOR_MAX_BLOCKS) return VRF_ERR_ARG;
+        BaPriorStore *hp = b->h_prior;
+        if (cudaStreamSynchronize(h->stream) != cudaSuccess) return VRF_ERR_CUDA;     // staging buffer reuse
+        hp->n = P->n; hp->n_blocks = P->n_blocks; hp->valid = 1; hp->pad = 0;
+        for (int q = 0; q < P->n_blocks; ++q) {
+            hp->kind[q] = P->blocks[q].kind; hp->index[q] = P->blocks[q].index; hp->size[q] = P->blocks[q].size; hp->idx[q] = P->blocks[q].idx;
+            memcpy(hp->x0 + 9 * q, P->blocks[q].x0, sizeof(double) * 9);
+        }
+        memcpy(hp->r0, P->linearized_residuals, sizeof(double) * P->n);
+        memcpy(hp->J0, P->linearized_jacobians, sizeof(double) * (size_t)P->n * P->n);
+        BaPriorStore *dst = b->d_prior[b->prior_cur[seq]] + seq;
+        const size_t bytes = offsetof(BaPriorStore, J0) + sizeof(double) * (size_t)P->n * P->n;
+        if (cudaMemcpyAsync(dst, hp, bytes, cudaMemcpyHostToDevice, h->stream) != cudaSuccess) return VRF_ERR_CUDA;
+        if (cudaStreamSynchronize(h->stream) != cudaSuccess) return VRF_ERR_CUDA;
+        b->prior_valid[seq] = 1;
+        have_prior = 1;
+    } else b->prior_valid[seq] = 0;
+    mt.has_prior = have_prior;
+
+    BaProbDev &pd = b->h_prob[slot];
+    BaHostPack *dp = b->d_pack + slot;
+    pd.pose0 = dp->pose; pd.sb0 = dp->sb; pd.ex0 = dp->ex; pd.lam0 = dp->lam;
+    pd.start = dp->start; pd.obs_ptr = dp->obs_ptr; pd.lm_const = dp->lm_const; pd.lm_ub = dp->lm_ub; pd.obs = dp->obs; pd.imu = dp->imu;
+    pd.prior = have_prior ? b->d_prior[b->prior_cur[seq]] + seq : nullptr;
+    pd.prior_next = b->d_prior[1 - b->prior_cur[seq]] + seq;
+    pd.HP = b->d_HP + (size_t)seq * VRF_PRIOR_MAX_DIM * VRF_PRIOR_MAX_DIM;
+    pd.colmap = b->d_colmap + (size_t)seq * VRF_PRIOR_MAX_DIM;
+    pd.lam = b->d_lam + (size_t)seq * BA_MAX_LM;
+    pd.clam = b->d_clam + (size_t)seq * BA_MAX_LM;
+    pd.W = b->d_W + (size_t)seq * BA_MAX_LM * 66;
+    double *v = b->d_vecs + (size_t)seq * 9 * BA_MAX_LM;
+    pd.hll = v; pd.gl = v + BA_MAX_LM; pd.jscale_l = v + 2 * BA_MAX_LM; pd.diag_l = v + 3 * BA_MAX_LM; pd.gd_l = v + 4 * BA_MAX_LM;
+    pd.gn_l = v + 5 * BA_MAX_LM; pd.u_l = v + 6 * BA_MAX_LM; pd.y_l = v + 7 * BA_MAX_LM; pd.hinv_l = v + 8 * BA_MAX_LM;
+    pd.imuS = b->d_imuS + (size_t)seq * (BA_NF - 1) * 225;
+
+    BaMargDev &mg = b->h_marg[slot];
+    double *mb = b->d_margbuf + (size_t)seq * kMargDoubles;
+    const size_t mmx = 15 + BA_MAX_M0;
+    mg.A = mb; mb += (size_t)BA_MAX_POS * BA_MAX_POS;
+    mg.b = mb; mb += BA_MAX_POS;
+    mg.V = mb; mb += mmx * mmx;
+    mg.Ainv = mb; mb += mmx * mmx;
+    mg.T = mb; mb += (size_t)VRF_PRIOR_MAX_DIM * mmx;
+    mg.Ar = mb; mb += (size_t)VRF_PRIOR_MAX_DIM * VRF_PRIOR_MAX_DIM;
+    mg.V2 = mb; mb += (size_t)VRF_PRIOR_MAX_DIM * VRF_PRIOR_MAX_DIM;
+    mg.br = mb;
+    mg.lmcol = b->d_lmcol + (size_t)seq * BA_MAX_LM;
+    b->last_M[seq] = M;
+    return VRF_OK;
+}
+
+static int upload(vrf_handle *h, int n, const int32_t *seqs, const VrfBaProblem *probs)
+{
+    BaState *b = h->ba;
+    if (!b || n < 1 || n > h->n_seq || !seqs || !probs) return VRF_ERR_ARG;
+    BCK(cudaSetDevice(h->device));
+    BCK(cudaStreamSynchronize(h->stream));          // pinned staging reuse
+    std::vector<uint8_t> seen(h->n_seq, 0);
+    for (int i = 0; i < n; ++i) {
+        if (seqs[i] < 0 || seqs[i] >= h->n_seq || seen[seqs[i]]) return VRF_ERR_ARG;
+        seen[seqs[i]] = 1;
+        int rc = pack_problem(h, i, seqs[i], &probs[i]);
+        if (rc != VRF_OK) return rc;
+    }
+    // only the used prefix of each pack is copied: header part (poses, imu) + landmark arrays up to M / nobs
+    for (int i = 0; i < n; ++i) {
+        const int M = b->h_meta[i].M, O = b->h_meta[i].nobs;
+        BaHostPack *hs = b->h_pack + i, *ds = b->d_pack + i;
+        BCK(cudaMemcpyAsync(ds, hs, offsetof(BaHostPack, lam), cudaMemcpyHostToDevice, h->stream));
+        if (M > 0) {
+            BCK(cudaMemcpyAsync(ds->lam, hs->lam, sizeof(double) * M, cudaMemcpyHostToDevice, h->stream));
+            BCK(cudaMemcpyAsync(ds->lm_ub, hs->lm_ub, sizeof(double) * M, cudaMemcpyHostToDevice, h->stream));
+            BCK(cudaMemcpyAsync(ds->start, hs->start, sizeof(int) * M, cudaMemcpyHostToDevice, h->stream));
+            BCK(cudaMemcpyAsync(ds->lm_const, hs->lm_const, M, cudaMemcpyHostToDevice, h->stream));
+            BCK(cudaMemcpyAsync(ds->obs, hs->obs, sizeof(double) * 2 * O, cudaMemcpyHostToDevice, h->stream));
+        }
+        BCK(cudaMemcpyAsync(ds->obs_ptr, hs->obs_ptr, sizeof(int) * (M + 1), cudaMemcpyHostToDevice, h->stream));
+    }
+    BCK(cudaMemcpyAsync(b->d_meta, b->h_meta, n * sizeof(BaMeta), cudaMemcpyHostToDevice, h->stream));
+    BCK(cudaMemcpyAsync(b->d_prob, b->h_prob, n * sizeof(BaProbDev), cudaMemcpyHostToDevice, h->stream));
+    BCK(cudaMemcpyAsync(b->d_marg, b->h_marg, n * sizeof(BaMargDev), cudaMemcpyHostToDevice, h->stream));
+    b->last_slots.assign(seqs, seqs + n);
+    return VRF_OK;
+}
+
+static int enqueue(vrf_handle *h, int n)
+{
+    BaState *b = h->ba;
+    LaunchCtx lc{h->stream, &h->launches, &h->prof};
+    if (ba_solve_launch(b->d_meta, b->d_prob, b->d_out, n, lc) != 0) return VRF_ERR_CUDA;
+    if (ba_marg_launch(b->d_meta, b->d_prob, b->d_out, b->d_marg, n, lc) != 0) return VRF_ERR_CUDA;
+    BCK(cudaGetLastError());
+    return VRF_OK;
+}
+
+static int download(vrf_handle *h, int n, const int32_t *seqs, VrfBaResult *res)
+{
+    BaState *b = h->ba;
+    BCK(cudaMemcpyAsync(b->h_out, b->d_out, n * sizeof(BaOutDev), cudaMemcpyDeviceToHost, h->stream));
+    BCK(cudaStreamSynchronize(h->stream));
+    int worst = VRF_OK;
+    for (int i = 0; i < n; ++i) {
+        const BaOutDev &o = b->h_out[i];
+        const int seq = seqs[i];
+        if (o.has_new_prior) { b->prior_cur[seq] = 1 - b->prior_cur[seq]; b->prior_valid[seq] = 1; }
+        if (!res) continue;
+        VrfBaResult &r = res[i];
+        r.status = o.status; r.iterations = o.iterations; r.successful_steps = o.successful; r.termination = o.termination;
+        r.initial_cost = o.initial_cost; r.final_cost = o.final_cost;
+        memcpy(r.para_Pose, o.pose, sizeof(o.pose)); memcpy(r.para_SpeedBias, o.sb, sizeof(o.sb)); memcpy(r.para_Ex_Pose, o.ex, sizeof(o.ex));
+        r.para_Td = 0.0;
+        memcpy(r.Ps, o.Ps, sizeof(o.Ps)); memcpy(r.Rs, o.Rs, sizeof(o.Rs)); memcpy(r.Vs, o.Vs, sizeof(o.Vs));
+        memcpy(r.Bas, o.Bas, sizeof(o.Bas)); memcpy(r.Bgs, o.Bgs, sizeof(o.Bgs));
+        r.has_new_prior = o.has_new_prior;
+        if (r.para_Feature && b->last_M[seq] > 0)
+            BCK(cudaMemcpy(r.para_Feature, b->d_lam + (size_t)seq * BA_MAX_LM, sizeof(double) * b->last_M[seq], cudaMemcpyDeviceToHost));
+        if (o.has_new_prior && r.new_prior) {
+            BaPriorStore *hp = b->h_prior;
+            const BaPriorStore *src = b->d_prior[b->prior_cur[seq]] + seq;
+            BCK(cudaMemcpy(hp, src, offsetof(BaPriorStore, J0), cudaMemcpyDeviceToHost));
+            const int nn = hp->n;
+            BCK(cudaMemcpy(hp->J0, src->J0, sizeof(double) * (size_t)nn * nn, cudaMemcpyDeviceToHost));
+            VrfPrior *P = r.new_prior;
+            P->n = nn; P->n_blocks = hp->n_blocks;
+            for (int q = 0; q < hp->n_blocks; ++q) {
+                P->blocks[q].kind = hp->kind[q]; P->blocks[q].index = hp->index[q]; P->blocks[q].size = hp->size[q]; P->blocks[q].idx = hp->idx[q];
+                memcpy(P->blocks[q].x0, hp->x0 + 9 * q, sizeof(double) * 9);
+            }
+            memcpy(P->linearized_residuals, hp->r0, sizeof(double) * nn);
+            memcpy(P->linearized_jacobians, hp->J0, sizeof(double) * (size_t)nn * nn);
+        }
+        if (o.status != VRF_OK) worst = o.status;
+    }
+    return worst;
+}
+
+}  // namespace vrf
+
+using namespace vrf;
+
+extern "C" int vrf_ba_upload_batch(vrf_handle *h, int n, const int32_t *seqs, const VrfBaProblem *probs)
+{
+    if (!h) return VRF_ERR_ARG;
+    return upload(h, n, seqs, probs);
+}
+
+extern "C" int vrf_ba_enqueue_batch(vrf_handle *h, int n, const int32_t *seqs)
+{
+    if (!h || !h->ba || !seqs || n < 1 || n != (int)h->ba->last_slots.size()) return VRF_ERR_ARG;
+    if (cudaSetDevice(h->device) != cudaSuccess) return VRF_ERR_CUDA;
+    return enqueue(h, n);
+}
+
+extern "C" int vrf_ba_download_batch(vrf_handle *h, int n, const int32_t *seqs, VrfBaResult *res)
+{
+    if (!h || !h->ba || !seqs || n < 1 || n != (int)h->ba->last_slots.size()) return VRF_ERR_ARG;
+    if (cudaSetDevice(h->device) != cudaSuccess) return VRF_ERR_CUDA;
+    return download(h, n, seqs, res);
+}
+
+extern "C" int vrf_ba_solve_batch(vrf_handle *h, int n, const int32_t *seqs, const VrfBaProblem *probs, VrfBaResult *res)
+{
+    if (!h) return VRF_ERR_ARG;
+    int rc = upload(h, n, seqs, probs);
+    if (rc != VRF_OK) return rc;
+    rc = enqueue(h, n);
+    if (rc != VRF_OK) return rc;
+    return download(h, n, seqs, res);
+}
+
+extern "C" int vrf_ba_solve(vrf_handle *h, int seq, const VrfBaProblem *prob, VrfBaResult *res)
+{
+    int32_t s = seq;
+    return vrf_ba_solve_batch(h, 1, &s, prob, res);
+}
+

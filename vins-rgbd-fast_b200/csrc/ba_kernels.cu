@@ -1,0 +1,694 @@
+// ba_kernels.cu -- sliding-window visual-inertial bundle adjustment on the GPU
+// (Estimator::optimization, reference vins_estimator/src/estimator/estimator.cpp:1161-1578).
+//
+// One CTA (512 threads) per sequence runs the WHOLE solve on device -- linearisation,
+// Jacobi scaling, per-landmark Schur reduction, dense Cholesky of the reduced camera
+// system, traditional dogleg with trust-region control -- with no host round trip
+// between iterations.  All arithmetic is FP64 (the reference/Ceres use double).
+//
+//   factor math            : ProjectionFactor::Evaluate (factor/projection_factor.cpp:22-130),
+//                            IMUFactor::Evaluate (factor/imu_factor.h:20-205),
+//                            MarginalizationFactor::Evaluate (factor/marginalization_factor.cpp:353-415),
+//                            CauchyLoss(1.0) + Ceres Corrector (restated at marginalization_factor.cpp:39-72)
+//   parameterisation       : PoseLocalParameterization (factor/pose_local_parameterization.cpp:3-28)
+//   solver (third party)   : ceres::Solve with DENSE_SCHUR + DOGLEG, max_num_iterations = NUM_ITERATIONS
+//                            (estimator.cpp:1348-1363); algorithm restated in oracle/ba_ref.c (parity
+//                            UNPINNED against real Ceres)
+//
+// Data layout (HBM, per problem, SoA over landmarks so that lanes of a warp read
+// consecutive words): lam[M], start[M], flag[M], obs_ptr[M+1], obs[O][2]; W[M][66]
+// (landmark-to-pose coupling rows), hll/gl/diag/gd/gn/step per landmark.
+// On chip: the 171x171 camera system lives in shared memory as a packed lower
+// triangle (117 KB) and is Schur-reduced and Cholesky-factorised in place; the
+// tangent layout is [pose f: 6f | speed-bias f: 66+9f | ex-pose: 165].
+//
+// Roofline: ~100-160 KB touched and ~5 MFLOP FP64 per iteration per problem => compute /
+// latency bound; the only dense contraction is the 171^3/3 Cholesky.
+#include "ba_math.cuh"
+
+namespace vrf {
+
+// --------------------------------------------------------------------------
+// shared-memory frame of the solve kernel
+// --------------------------------------------------------------------------
+struct BaShared {
+    double H[BA_NC * (BA_NC + 1) / 2];     // packed lower triangle: camera system, Schur-reduced & factorised in place
+    double g[BA_NC], diag[BA_NC], gd[BA_NC], gn[BA_NC], jscale[BA_NC], tmp[BA_NC], y[BA_NC + 1], colv[BA_NC + 1];
+    double pose[BA_NF * 7], sb[BA_NF * 9], ex[7];
+    double cpose[BA_NF * 7], csb[BA_NF * 9];          // candidate
+    double R[BA_NF * 9], ric[9];
+    double dx[VRF_PRIOR_MAX_DIM], pr[VRF_PRIOR_MAX_DIM];
+    double imuJ[BA_NF - 1][15 * 30];                 // whitened IMU Jacobians of the current linearisation
+    double imur[BA_NF - 1][16];
+    double red[BA_THREADS / 32];
+    double sc[16];
+    int flag[8];
+};
+
+__device__ __forceinline__ bool col_active_dev(const BaMeta &m, int col)
+{
+    if (col < 66) { int f = col / 6; return f < m.nframes && !(f == 0 && !m.use_imu); }
+    if (col < 165) { int f = (col - 66) / 9; return m.use_imu && f < m.nframes; }
+    return false;        // ex-pose constant in this build
+}
+
+// cost of all residual blocks at (pose, sb, lam); optionally the full linearisation into sh.H / sh.g / landmark arrays.
+__device__ double ba_evaluate(const BaMeta &m, const BaProbDev &p, BaShared &sh, const double *pose, const double *sb,
+                              const double *lam, bool lin)
+{
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = BA_THREADS / 32;
+    if (lin) {
+        for (int i = tid; i < BA_NC * (BA_NC + 1) / 2; i += BA_THREADS) sh.H[i] = 0.0;
+        for (int i = tid; i < BA_NC; i += BA_THREADS) sh.g[i] = 0.0;
+    }
+    for (int f = tid; f < BA_NF; f += BA_THREADS) d_q2R(pose + 7 * f + 3, sh.R + 9 * f);
+    if (tid == 0) d_q2R(sh.ex + 3, sh.ric);
+    __syncthreads();
+    double cost = 0.0;
+    // ---- projection factors: one warp per landmark, one lane per factor ----
+    for (int l = warp; l < m.M; l += nwarp) {
+        const int o0 = p.obs_ptr[l], nf = p.obs_ptr[l + 1] - o0 - 1;
+        const int i = p.start[l];
+        const bool lc = p.lm_const[l] != 0;
+        double r[2] = {0, 0}, Ji[12], Jj[12], Jl[2] = {0, 0};
+        const bool act = lane < nf;
+        const int j = i + 1 + lane;
+        if (act) {
+            const double xi = p.obs[2 * o0], yi = p.obs[2 * o0 + 1];
+            const double xj = p.obs[2 * (o0 + 1 + lane)], yj = p.obs[2 * (o0 + 1 + lane) + 1];
+            double rho0 = proj_eval(pose + 7 * i, sh.R + 9 * i, pose + 7 * j, sh.R + 9 * j, sh.ex, sh.ric, lam[l], xi, yi, xj, yj,
+                                    lin, lc, r, Ji, Jj, Jl);
+            cost += 0.5 * rho0;
+        }
+        if (!lin) continue;
+        if (!act) {
+#pragma unroll
+            for (int k = 0; k < 12; ++k) { Ji[k] = 0; Jj[k] = 0; }
+        }
+        // landmark scalars
+        double hl = warp_sum_d(Jl[0] * Jl[0] + Jl[1] * Jl[1]);
+        double gl = warp_sum_d(Jl[0] * r[0] + Jl[1] * r[1]);
+        double *Wl = p.W + (size_t)l * 66;
+        for (int k = lane; k < 66; k += 32) Wl[k] = 0.0;
+        __syncwarp();
+        // host-pose parts (reduced over the landmark's factors), then lane-private observer parts
+#pragma unroll
+        for (int a = 0; a < 6; ++a) {
+            double wi = warp_sum_d(Ji[a] * Jl[0] + Ji[6 + a] * Jl[1]);
+            double gi = warp_sum_d(Ji[a] * r[0] + Ji[6 + a] * r[1]);
+            if (lane == 0) { Wl[6 * i + a] = wi; atomicAdd(&sh.g[6 * i + a], gi); }
+#pragma unroll
+            for (int b = 0; b <= a; ++b) {
+                double h = warp_sum_d(Ji[a] * Ji[b] + Ji[6 + a] * Ji[6 + b]);
+                if (lane == 0) atomicAdd(&sh.H[pk(6 * i + a, 6 * i + b)], h);
+            }
+        }
+        if (act) {
+#pragma unroll
+            for (int a = 0; a < 6; ++a) {
+                Wl[6 * j + a] = Jj[a] * Jl[0] + Jj[6 + a] * Jl[1];
+                atomicAdd(&sh.g[6 * j + a], Jj[a] * r[0] + Jj[6 + a] * r[1]);
+#pragma unroll
+                for (int b = 0; b <= a; ++b) atomicAdd(&sh.H[pk(6 * j + a, 6 * j + b)], Jj[a] * Jj[b] + Jj[6 + a] * Jj[6 + b]);
+#pragma unroll
+                for (int b = 0; b < 6; ++b) atomicAdd(&sh.H[pk(6 * j + a, 6 * i + b)], Jj[a] * Ji[b] + Jj[6 + a] * Ji[6 + b]);
+            }
+        }
+        if (lane == 0) { p.hll[l] = hl; p.gl[l] = gl; }
+    }
+    // ---- IMU factors: one warp per factor ----
+    for (int f = warp; f < m.nimu; f += nwarp) {
+        const int j = m.imu_j[f], i = j - 1;
+        const VrfImuPreint *pre = p.imu + (j - 1);
+        const double *S = p.imuS + (size_t)(j - 1) * 225;
+        double rr[15];
+        ImuCtx cx;
+        imu_residual_raw(pre, pose + 7 * i, sb + 9 * i, pose + 7 * j, sb + 9 * j, m.g_norm, rr, &cx);
+        // whitened residual row `lane`
+        double rw = 0;
+        if (lane < 15) { for (int k = lane; k < 15; ++k) rw += S[lane * 15 + k] * rr[k]; cost += 0.5 * rw * rw; }
+        if (!lin) continue;
+        if (lane < 15) sh.imur[f][lane] = rw;
+        if (lane < 30) {
+            double col[15];
+            imu_jac_col(pre, pose + 7 * i, sb + 9 * i, pose + 7 * j, sb + 9 * j, m.g_norm, &cx, lane, col);
+            for (int rI = 0; rI < 15; ++rI) { double a = 0; for (int k = rI; k < 15; ++k) a += S[rI * 15 + k] * col[k]; sh.imuJ[f][rI * 30 + lane] = a; }
+        }
+        __syncwarp();
+        // accumulate J^T J and J^T r ; tangent column of local column c
+        auto tcol = [&](int c) { return c < 6 ? 6 * i + c : c < 15 ? 66 + 9 * i + (c - 6) : c < 21 ? 6 * j + (c - 15) : 66 + 9 * j + (c - 21); };
+        for (int e = lane; e < 30 * 31 / 2; e += 32) {
+            int a = 0, rem = e;
+            while (rem > a) { rem -= (a + 1); ++a; }       // e -> (a, b<=a) in the 30x30 lower triangle
+            int b = rem;
+            double h = 0;
+            for (int k = 0; k < 15; ++k) h += sh.imuJ[f][k * 30 + a] * sh.imuJ[f][k * 30 + b];
+            atomicAdd(&sh.H[pk(tcol(a), tcol(b))], h);
+        }
+        if (lane < 30) {
+            double gsum = 0;
+            for (int k = 0; k < 15; ++k) gsum += sh.imuJ[f][k * 30 + lane] * sh.imur[f][k];
+            atomicAdd(&sh.g[tcol(lane)], gsum);
+        }
+    }
+    __syncthreads();
+    // ---- prior ----
+    const BaPriorStore *P = p.prior;
+    const int np_ = (P && P->valid) ? P->n : 0;
+    if (np_ > 0) {
+        prior_dx(P, pose, sb, sh.ex, sh.dx);
+        __syncthreads();
+        const int n = np_;
+        for (int rI = tid; rI < n; rI += BA_THREADS) {
+            double a = P->r0[rI];
+            const double *row = P->J0 + (size_t)rI * n;
+            for (int k = 0; k < n; ++k) a += row[k] * sh.dx[k];
+            sh.pr[rI] = a;
+            cost += 0.5 * a * a;
+        }
+        __syncthreads();
+        if (lin) {
+            // g += J0^T r ; H += J0^T J0 (precomputed HP), both through the column map
+            for (int a = tid; a < n; a += BA_THREADS) {
+                int ca = p.colmap[a];
+                if (ca < 0) continue;
+                double gsum = 0;
+                for (int rI = 0; rI < n; ++rI) gsum += P->J0[(size_t)rI * n + a] * sh.pr[rI];
+                sh.g[ca] += gsum;
+            }
+            for (int e = tid; e < n * n; e += BA_THREADS) {
+                int a = e / n, b = e - a * n;
+                if (b > a) continue;
+                int ca = p.colmap[a], cb = p.colmap[b];
+                if (ca < 0 || cb < 0) continue;
+                sh.H[pk(ca, cb)] += p.HP[(size_t)a * n + b];
+            }
+        }
+    }
+    __syncthreads();
+    return block_sum(cost, sh.red);
+}
+
+// (sum over camera + landmark entries of a_c*b_c) helper: camera part from smem arrays, landmark part from global
+__device__ double dot_full(const BaMeta &m, const double *ac, const double *bc, const double *al, const double *bl, double *s_red)
+{
+    double v = 0;
+    for (int i = threadIdx.x; i < BA_NC; i += BA_THREADS) v += ac[i] * bc[i];
+    for (int l = threadIdx.x; l < m.M; l += BA_THREADS) v += al[l] * bl[l];
+    return block_sum(v, s_red);
+}
+
+__global__ void __launch_bounds__(BA_THREADS, 1)
+k_ba_solve(const BaMeta *metas, const BaProbDev *probs, BaOutDev *outs)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    BaShared &sh = *reinterpret_cast<BaShared *>(smem_raw);
+    const BaMeta m = metas[blockIdx.x];
+    const BaProbDev p = probs[blockIdx.x];
+    BaOutDev &out = outs[blockIdx.x];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = BA_THREADS / 32;
+    const int M = m.M;
+
+    for (int i = tid; i < BA_NF * 7; i += BA_THREADS) sh.pose[i] = p.pose0[i];
+    for (int i = tid; i < BA_NF * 9; i += BA_THREADS) sh.sb[i] = p.sb0[i];
+    if (tid < 7) sh.ex[tid] = p.ex0[tid];
+    for (int l = tid; l < M; l += BA_THREADS) p.lam[l] = p.lam0[l];
+    __syncthreads();
+    // ---- once per solve: IMU information square roots, prior normal matrix ----
+    {
+        double *scr = reinterpret_cast<double *>(sh.imuJ) + warp * 450;   // 10 warps x 450 doubles fit in imuJ
+        if (warp < m.nimu && warp < BA_NF - 1) imu_sqrt_info_warp(p.imu[m.imu_j[warp] - 1].covariance, p.imuS + (size_t)(m.imu_j[warp] - 1) * 225, scr);
+        for (int f = warp + nwarp; f < m.nimu; f += nwarp) imu_sqrt_info_warp(p.imu[m.imu_j[f] - 1].covariance, p.imuS + (size_t)(m.imu_j[f] - 1) * 225, scr);
+        const BaPriorStore *P = p.prior;
+        const int n = (P && P->valid) ? P->n : 0;
+        for (int e = tid; e < n * n; e += BA_THREADS) {
+            int a = e / n, b = e - a * n;
+            if (b > a) continue;
+            double h = 0;
+            for (int rI = 0; rI < n; ++rI) h += P->J0[(size_t)rI * n + a] * P->J0[(size_t)rI * n + b];
+            p.HP[(size_t)a * n + b] = h;
+        }
+        // prior column -> tangent column (constant blocks drop out)
+        if (n > 0)
+            for (int b = tid; b < P->n_blocks; b += BA_THREADS) {
+                const int kind = P->kind[b], ls = P->size[b] == 7 ? 6 : P->size[b];
+                int col = kind == VRF_BLK_POSE ? 6 * P->index[b] : kind == VRF_BLK_SPEEDBIAS ? 66 + 9 * P->index[b] : -1;
+                if (col >= 0 && !col_active_dev(m, col)) col = -1;
+                for (int c = 0; c < ls; ++c) p.colmap[P->idx[b] + c] = col < 0 ? -1 : col + c;
+            }
+    }
+    __syncthreads();
+    __threadfence_block();
+
+    double x_cost = ba_evaluate(m, p, sh, sh.pose, sh.sb, p.lam, true);
+    const double initial_cost = x_cost;
+    // Jacobi scaling (once): 1 / (1 + ||column||)
+    for (int c = tid; c < BA_NC; c += BA_THREADS) sh.jscale[c] = 1.0 / (1.0 + sqrt(sh.H[pk(c, c)]));
+    for (int l = tid; l < M; l += BA_THREADS) p.jscale_l[l] = 1.0 / (1.0 + sqrt(p.hll[l]));
+    __syncthreads();
+
+    double radius = 1e4, mu = 1e-8, alpha = 0, dogleg_norm = 0;
+    double Quu = 0, gdn2 = 0;           // u^T H u, |gd|^2
+    double ytg = 0, yDy = 0, utg = 0, uDy = 0, gnn2 = 0, gdgn = 0;
+    const double min_mu = 1e-8, max_mu = 1.0, mu_inc = 10.0;
+    int reuse = 0, invalid = 0, need_scale = 1, iterations = 0, successful = 0, termination = 0, status = VRF_OK;
+    double x_norm = 0, gradient_max = 0;
+    const int max_iter = m.max_iter;
+
+    auto xnorm2 = [&](const double *pose, const double *sb, const double *lam) {
+        double v = 0;
+        for (int i = tid; i < BA_NF * 7; i += BA_THREADS) if (col_active_dev(m, 6 * (i / 7))) v += pose[i] * pose[i];
+        for (int i = tid; i < BA_NF * 9; i += BA_THREADS) if (col_active_dev(m, 66 + 9 * (i / 9))) v += sb[i] * sb[i];
+        for (int l = tid; l < M; l += BA_THREADS) if (!p.lm_const[l]) v += lam[l] * lam[l];
+        return block_sum(v, sh.red);
+    };
+    x_norm = sqrt(xnorm2(sh.pose, sh.sb, p.lam));
+
+    while (true) {
+        if (need_scale) {
+            // scale the fresh linearisation: H_s = D H D, g_s = D g (Jacobi scaling of the Jacobian columns)
+            for (int e = tid; e < BA_NC * (BA_NC + 1) / 2; e += BA_THREADS) {
+                // unpack e -> (a,b): a = floor((sqrt(8e+1)-1)/2)
+                int a = (int)((sqrt(8.0 * e + 1.0) - 1.0) * 0.5);
+                while (a * (a + 1) / 2 > e) --a;
+                while ((a + 1) * (a + 2) / 2 <= e) ++a;
+                int b = e - a * (a + 1) / 2;
+                sh.H[e] *= sh.jscale[a] * sh.jscale[b];
+            }
+            for (int c = tid; c < BA_NC; c += BA_THREADS) sh.g[c] *= sh.jscale[c];
+            for (int l = warp; l < M; l += nwarp) {
+                const double sl = p.jscale_l[l];
+                double *Wl = p.W + (size_t)l * 66;
+                for (int k = lane; k < 66; k += 32) Wl[k] *= sl * sh.jscale[k];
+                if (lane == 0) { p.hll[l] *= sl * sl; p.gl[l] *= sl; }
+            }
+            __syncthreads();
+            // projected gradient max-norm (bounds): x - Plus(x, -g)
+            {
+                double mx = 0;
+                for (int f = tid; f < BA_NF; f += BA_THREADS) {
+                    if (col_active_dev(m, 6 * f)) {
+                        double dl[6], o[7];
+                        for (int k = 0; k < 6; ++k) dl[k] = -sh.g[6 * f + k] / sh.jscale[6 * f + k];
+                        d_pose_plus(sh.pose + 7 * f, dl, o);
+                        for (int k = 0; k < 7; ++k) mx = fmax(mx, fabs(sh.pose[7 * f + k] - o[k]));
+                    }
+                    if (col_active_dev(m, 66 + 9 * f))
+                        for (int k = 0; k < 9; ++k) mx = fmax(mx, fabs(sh.g[66 + 9 * f + k] / sh.jscale[66 + 9 * f + k]));
+                }
+                for (int l = tid; l < M; l += BA_THREADS) {
+                    if (p.lm_const[l]) continue;
+                    double v = p.lam[l] + (-p.gl[l] / p.jscale_l[l]);
+                    v = fmin(v, p.lm_ub[l]);
+                    mx = fmax(mx, fabs(p.lam[l] - v));
+                }
+                // block max via sum-free reduction
+                for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+                __syncthreads();
+                if (lane == 0) sh.red[warp] = mx;
+                __syncthreads();
+                mx = 0;
+                for (int i = 0; i < nwarp; ++i) mx = fmax(mx, sh.red[i]);
+                gradient_max = mx;
+            }
+            need_scale = 0;
+        }
+        if (iterations >= max_iter) { termination = 0; break; }
+        if (gradient_max <= 1e-10) { termination = 2; break; }
+        if (radius <= 1e-32) { termination = 4; break; }
+        ++iterations;
+
+        bool step_ok = true;
+        if (!reuse) {
+            reuse = 1;
+            // diagonal_ = sqrt(clamp(diag(J^T J))), gradient_ /= diagonal_
+            for (int c = tid; c < BA_NC; c += BA_THREADS) {
+                double dg = sqrt(fmin(fmax(sh.H[pk(c, c)], 1e-6), 1e32));
+                sh.diag[c] = dg; sh.gd[c] = sh.g[c] / dg; sh.tmp[c] = sh.g[c] / (dg * dg);      // tmp = u_c = D^-2 g
+            }
+            for (int l = tid; l < M; l += BA_THREADS) {
+                double dg = sqrt(fmin(fmax(p.hll[l], 1e-6), 1e32));
+                p.diag_l[l] = dg; p.gd_l[l] = p.gl[l] / dg; p.u_l[l] = p.lm_const[l] ? 0.0 : p.gl[l] / (dg * dg);
+            }
+            __syncthreads();
+            // Cauchy point: alpha = |gd|^2 / (u^T H u), H = J^T J of the scaled problem (before it is reduced in place)
+            {
+                double v = 0;
+                for (int a = tid; a < BA_NC; a += BA_THREADS) {
+                    double hv = 0;
+                    for (int b = 0; b < BA_NC; ++b) hv += sh.H[pk(a, b)] * sh.tmp[b];
+                    v += sh.tmp[a] * hv;
+                }
+                for (int l = warp; l < M; l += nwarp) {
+                    if (p.lm_const[l]) continue;
+                    const double *Wl = p.W + (size_t)l * 66;
+                    double wv = 0;
+                    for (int k = lane; k < 66; k += 32) wv += Wl[k] * sh.tmp[k];
+                    wv = warp_sum_d(wv);
+                    if (lane == 0) v += 2.0 * p.u_l[l] * wv + p.hll[l] * p.u_l[l] * p.u_l[l];
+                }
+                Quu = block_sum(v, sh.red);
+                double gsq = 0;
+                for (int c = tid; c < BA_NC; c += BA_THREADS) gsq += sh.gd[c] * sh.gd[c];
+                for (int l = tid; l < M; l += BA_THREADS) if (!p.lm_const[l]) gsq += p.gd_l[l] * p.gd_l[l];
+                gdn2 = block_sum(gsq, sh.red);
+                alpha = gdn2 / Quu;
+                utg = 0;
+                {
+                    double t = 0;
+                    for (int c = tid; c < BA_NC; c += BA_THREADS) t += sh.tmp[c] * sh.g[c];
+                    for (int l = tid; l < M; l += BA_THREADS) if (!p.lm_const[l]) t += p.u_l[l] * p.gl[l];
+                    utg = block_sum(t, sh.red);
+                }
+            }
+            // Gauss-Newton step: (H + mu D^2) y = g by Schur complement + Cholesky, retried with larger mu
+            bool solved = false;
+            while (mu < max_mu) {
+                // rhs
+                for (int c = tid; c < BA_NC; c += BA_THREADS) { sh.y[c] = sh.g[c]; }
+                __syncthreads();
+                // per-landmark pivots; reduce rhs
+                if (tid == 0) sh.flag[0] = 0;
+                __syncthreads();
+                for (int l = warp; l < M; l += nwarp) {
+                    if (p.lm_const[l]) continue;
+                    const double hl = p.hll[l] + mu * p.diag_l[l] * p.diag_l[l];
+                    if (!(hl > 0)) { if (lane == 0) sh.flag[0] = 1; continue; }
+                    const double *Wl = p.W + (size_t)l * 66;
+                    const double gl_h = p.gl[l] / hl;
+                    for (int k = lane; k < 66; k += 32) { double w = Wl[k]; if (w != 0.0) atomicAdd(&sh.y[k], -w * gl_h); }
+                    if (lane == 0) p.hinv_l[l] = 1.0 / hl;
+                }
+                __syncthreads();
+                // S = H + mu D^2 - W^T diag(1/h) W on the 66x66 pose block.  W is streamed through a
+                // shared-memory tile (64 landmarks x 66, pre-multiplied by 1/sqrt(h)); every thread owns
+                // a fixed set of the 2211 output entries, so the reduction is deterministic and atomic-free.
+                {
+                    double *tile = reinterpret_cast<double *>(sh.imuJ);      // 4500 doubles available, 64*66 = 4224 used
+                    int ea[5], eb[5], ne = 0;
+                    double acc[5] = {0, 0, 0, 0, 0};
+                    for (int e = tid; e < 66 * 67 / 2 && ne < 5; e += BA_THREADS) {
+                        int a = (int)((sqrt(8.0 * e + 1.0) - 1.0) * 0.5);
+                        while (a * (a + 1) / 2 > e) --a;
+                        while ((a + 1) * (a + 2) / 2 <= e) ++a;
+                        ea[ne] = a; eb[ne] = e - a * (a + 1) / 2; ++ne;
+                    }
+                    for (int t0 = 0; t0 < M; t0 += 64) {
+                        const int nt = min(64, M - t0);
+                        for (int q = tid; q < nt * 66; q += BA_THREADS) {
+                            int l = t0 + q / 66, k = q - (q / 66) * 66;
+                            tile[q] = p.lm_const[l] ? 0.0 : p.W[(size_t)l * 66 + k] * sqrt(p.hinv_l[l]);
+                        }
+                        __syncthreads();
+                        for (int q = 0; q < ne; ++q) {
+                            double s_ = 0;
+                            const double *ta = tile + ea[q], *tb = tile + eb[q];
+                            for (int l = 0; l < nt; ++l) s_ += ta[l * 66] * tb[l * 66];
+                            acc[q] += s_;
+                        }
+                        __syncthreads();
+                    }
+                    for (int q = 0; q < ne; ++q) sh.H[ea[q] * (ea[q] + 1) / 2 + eb[q]] -= acc[q];
+                }
+                for (int c = tid; c < BA_NC; c += BA_THREADS) sh.H[pk(c, c)] += mu * sh.diag[c] * sh.diag[c];
+                __syncthreads();
+                // in-place right-looking Cholesky (lower, packed) of the 171x171 reduced camera system.  The
+                // right-hand side rides along as an extra row (index BA_NC), which performs the forward
+                // substitution L z = g for free.
+                bool bad = sh.flag[0] != 0;
+                for (int j = 0; j < BA_NC && !bad; ++j) {
+                    if (tid == 0) {
+                        double d = sh.H[pk(j, j)];
+                        if (!(d > 0.0)) sh.flag[0] = 1; else sh.H[pk(j, j)] = sqrt(d);
+                    }
+                    __syncthreads();
+                    if (sh.flag[0]) { bad = true; break; }
+                    const double ljj = sh.H[pk(j, j)];
+                    for (int i = j + 1 + tid; i <= BA_NC; i += BA_THREADS) {
+                        if (i < BA_NC) { double v = sh.H[pk(i, j)] / ljj; sh.H[pk(i, j)] = v; sh.colv[i] = v; }
+                        else { double v = sh.y[j] / ljj; sh.y[j] = v; sh.colv[BA_NC] = v; }
+                    }
+                    __syncthreads();
+                    // trailing update H[ii,kk] -= L[ii,j] L[kk,j], j < kk <= ii; 16 x 32 thread tile over (ii, kk)
+                    {
+                        const int tx = tid & 31, ty = tid >> 5;
+                        for (int ii = j + 1 + ty; ii <= BA_NC; ii += BA_THREADS / 32) {
+                            const double li = sh.colv[ii];
+                            if (ii < BA_NC) {
+                                double *row = sh.H + ii * (ii + 1) / 2;
+                                for (int kk = j + 1 + tx; kk <= ii; kk += 32) row[kk] -= li * sh.colv[kk];
+                            } else {
+                                for (int kk = j + 1 + tx; kk < BA_NC; kk += 32) sh.y[kk] -= li * sh.colv[kk];
+                            }
+                        }
+                    }
+                    __syncthreads();
+                }
+                if (!bad) {
+                    // back substitution L^T x = z by one warp (warp-level sync only)
+                    if (warp == 0) {
+                        for (int i = BA_NC - 1; i >= 0; --i) {
+                            if (lane == 0) sh.y[i] /= sh.H[pk(i, i)];
+                            __syncwarp();
+                            const double yi = sh.y[i];
+                            const double *row = sh.H + i * (i + 1) / 2;
+                            for (int k = lane; k < i; k += 32) sh.y[k] -= row[k] * yi;
+                            __syncwarp();
+                        }
+                    }
+                    __syncthreads();
+                    double fin = 0;
+                    for (int c = tid; c < BA_NC; c += BA_THREADS) if (!isfinite(sh.y[c])) fin += 1;
+                    fin = block_sum(fin, sh.red);
+                    if (fin == 0) {
+                        // back-substitute the landmarks: y_l = (g_l - w_l . y_c) / h_l
+                        for (int l = warp; l < M; l += nwarp) {
+                            double v = 0;
+                            if (!p.lm_const[l]) {
+                                const double *Wl = p.W + (size_t)l * 66;
+                                for (int k = lane; k < 66; k += 32) v += Wl[k] * sh.y[k];
+                                v = warp_sum_d(v);
+                                v = (p.gl[l] - v) * p.hinv_l[l];
+                            }
+                            if (lane == 0) p.y_l[l] = v;
+                        }
+                        solved = true;
+                    }
+                }
+                __syncthreads();
+                if (solved) break;
+                // failed: the in-place factorisation destroyed H => re-linearise and retry with a larger mu
+                mu *= mu_inc;
+                ba_evaluate(m, p, sh, sh.pose, sh.sb, p.lam, true);
+                for (int e = tid; e < BA_NC * (BA_NC + 1) / 2; e += BA_THREADS) {
+                    int a = (int)((sqrt(8.0 * e + 1.0) - 1.0) * 0.5);
+                    while (a * (a + 1) / 2 > e) --a;
+                    while ((a + 1) * (a + 2) / 2 <= e) ++a;
+                    int b = e - a * (a + 1) / 2;
+                    sh.H[e] *= sh.jscale[a] * sh.jscale[b];
+                }
+                for (int c = tid; c < BA_NC; c += BA_THREADS) sh.g[c] *= sh.jscale[c];
+                for (int l = warp; l < M; l += nwarp) {
+                    const double sl = p.jscale_l[l];
+                    double *Wl = p.W + (size_t)l * 66;
+                    for (int k = lane; k < 66; k += 32) Wl[k] *= sl * sh.jscale[k];
+                    if (lane == 0) { p.hll[l] *= sl * sl; p.gl[l] *= sl; }
+                }
+                __syncthreads();
+            }
+            if (!solved) { status = VRF_SOFT_NOT_SPD; step_ok = false; }
+            else {
+                // gauss_newton_step_ = -diag * y ; scalar products needed by the dogleg model
+                double a1 = 0, a2 = 0, a3 = 0, a4 = 0, a5 = 0;
+                for (int c = tid; c < BA_NC; c += BA_THREADS) {
+                    const double yc = sh.y[c], dg = sh.diag[c];
+                    sh.gn[c] = -dg * yc;
+                    a1 += yc * sh.g[c]; a2 += dg * dg * yc * yc; a3 += dg * dg * sh.tmp[c] * yc;
+                    a4 += sh.gn[c] * sh.gn[c]; a5 += sh.gd[c] * sh.gn[c];
+                }
+                for (int l = tid; l < M; l += BA_THREADS) {
+                    if (p.lm_const[l]) { p.gn_l[l] = 0; continue; }
+                    const double yc = p.y_l[l], dg = p.diag_l[l];
+                    const double gnv = -dg * yc;
+                    p.gn_l[l] = gnv;
+                    a1 += yc * p.gl[l]; a2 += dg * dg * yc * yc; a3 += dg * dg * p.u_l[l] * yc;
+                    a4 += gnv * gnv; a5 += p.gd_l[l] * gnv;
+                }
+                ytg = block_sum(a1, sh.red); yDy = block_sum(a2, sh.red); uDy = block_sum(a3, sh.red);
+                gnn2 = block_sum(a4, sh.red); gdgn = block_sum(a5, sh.red);
+            }
+        }
+        if (step_ok) {
+            // ComputeTraditionalDoglegStep: step_d = c1 * gd + c2 * gn (dogleg space), step = step_d / diag
+            const double gnorm = sqrt(gdn2), gnn = sqrt(gnn2);
+            double c1, c2;
+            if (gnn <= radius) { c1 = 0; c2 = 1; dogleg_norm = gnn; }
+            else if (gnorm * alpha >= radius) { c1 = -(radius / gnorm); c2 = 0; dogleg_norm = radius; }
+            else {
+                const double b_dot_a = -alpha * gdgn;
+                const double a_sq = (alpha * gnorm) * (alpha * gnorm);
+                const double bma = a_sq - 2 * b_dot_a + gnn * gnn;
+                const double cc = b_dot_a - a_sq;
+                const double dd = sqrt(cc * cc + bma * (radius * radius - a_sq));
+                const double beta = (cc <= 0) ? (dd - cc) / bma : (radius * radius - a_sq) / (dd + cc);
+                c1 = -alpha * (1.0 - beta); c2 = beta;
+                dogleg_norm = sqrt(c1 * c1 * gdn2 + 2 * c1 * c2 * gdgn + c2 * c2 * gnn2);
+            }
+            // model_cost_change = -s^T g - 0.5 s^T H s with s = c1 u - c2 y (u = D^-2 g), all from stored scalars:
+            //   u^T H u = Quu ; y^T H y = y^T g - mu y^T D^2 y ; u^T H y = u^T g - mu u^T D^2 y
+            const double sTg = c1 * utg - c2 * ytg;
+            const double sHs = c1 * c1 * Quu - 2 * c1 * c2 * (utg - mu * uDy) + c2 * c2 * (ytg - mu * yDy);
+            const double mcc = -sTg - 0.5 * sHs;
+            if (!(mcc > 0.0)) step_ok = false;
+            else {
+                invalid = 0;
+                // candidate = x (+) (step * jscale)
+                for (int f = tid; f < BA_NF; f += BA_THREADS) {
+                    if (col_active_dev(m, 6 * f)) {
+                        double dl[6];
+                        for (int k = 0; k < 6; ++k) { int c = 6 * f + k; dl[k] = (c1 * sh.gd[c] + c2 * sh.gn[c]) / sh.diag[c] * sh.jscale[c]; }
+                        d_pose_plus(sh.pose + 7 * f, dl, sh.cpose + 7 * f);
+                    } else for (int k = 0; k < 7; ++k) sh.cpose[7 * f + k] = sh.pose[7 * f + k];
+                    for (int k = 0; k < 9; ++k) {
+                        int c = 66 + 9 * f + k;
+                        sh.csb[9 * f + k] = sh.sb[9 * f + k] + (col_active_dev(m, c) ? (c1 * sh.gd[c] + c2 * sh.gn[c]) / sh.diag[c] * sh.jscale[c] : 0.0);
+                    }
+                }
+                for (int l = tid; l < M; l += BA_THREADS) {
+                    double v = p.lam[l];
+                    if (!p.lm_const[l]) {
+                        v += (c1 * p.gd_l[l] + c2 * p.gn_l[l]) / p.diag_l[l] * p.jscale_l[l];
+                        v = fmin(v, p.lm_ub[l]);           // ParameterBlock::Plus projects onto the bounds
+                    }
+                    p.clam[l] = v;
+                }
+                __syncthreads();
+                const double cand_cost = ba_evaluate(m, p, sh, sh.cpose, sh.csb, p.clam, false);
+                // step norm over the non-constant blocks (ambient space)
+                double sn = 0;
+                for (int i = tid; i < BA_NF * 7; i += BA_THREADS) if (col_active_dev(m, 6 * (i / 7))) { double dd = sh.pose[i] - sh.cpose[i]; sn += dd * dd; }
+                for (int i = tid; i < BA_NF * 9; i += BA_THREADS) if (col_active_dev(m, 66 + 9 * (i / 9))) { double dd = sh.sb[i] - sh.csb[i]; sn += dd * dd; }
+                for (int l = tid; l < M; l += BA_THREADS) if (!p.lm_const[l]) { double dd = p.lam[l] - p.clam[l]; sn += dd * dd; }
+                const double step_norm = sqrt(block_sum(sn, sh.red));
+                if (step_norm <= 1e-8 * (x_norm + 1e-8)) { termination = 3; break; }
+                const double cost_change = x_cost - cand_cost;
+                if (fabs(cost_change) <= 1e-6 * x_cost) { termination = 1; break; }
+                const double rho = cost_change / mcc;
+                if (rho > 1e-3) {
+                    for (int i = tid; i < BA_NF * 7; i += BA_THREADS) sh.pose[i] = sh.cpose[i];
+                    for (int i = tid; i < BA_NF * 9; i += BA_THREADS) sh.sb[i] = sh.csb[i];
+                    for (int l = tid; l < M; l += BA_THREADS) p.lam[l] = p.clam[l];
+                    __syncthreads();
+                    x_cost = cand_cost;
+                    x_norm = sqrt(xnorm2(sh.pose, sh.sb, p.lam));
+                    ba_evaluate(m, p, sh, sh.pose, sh.sb, p.lam, true);
+                    need_scale = 1;
+                    ++successful;
+                    if (rho < 0.25) radius *= 0.5;
+                    if (rho > 0.75) radius = fmax(radius, 3.0 * dogleg_norm);
+                    mu = fmax(min_mu, 2.0 * mu / mu_inc);
+                    reuse = 0;
+                } else {
+                    radius *= 0.5;
+                    reuse = 1;
+                }
+                continue;
+            }
+        }
+        if (++invalid >= 5) { termination = 5; break; }
+        mu *= mu_inc;
+        reuse = 0;
+        if (status == VRF_SOFT_NOT_SPD && mu >= max_mu) { termination = 5; break; }
+        // H was consumed by the failed factorisation attempts: rebuild it
+        ba_evaluate(m, p, sh, sh.pose, sh.sb, p.lam, true);
+        need_scale = 1;
+    }
+    __syncthreads();
+    // ---- double2vector gauge fix (estimator.cpp:985-1111) + vector2double re-pack for marginalization ----
+    if (tid == 0) {
+        double R0[9], R00[9], ypr0[3], ypr00[3], rot[9];
+        d_q2R(p.pose0 + 3, R0);
+        d_R2ypr(R0, ypr0);
+        if (m.use_imu) {
+            d_q2R(sh.pose + 3, R00);
+            d_R2ypr(R00, ypr00);
+            const double yd = (ypr0[0] - ypr00[0]) / 180.0 * 3.14159265358979323846;
+            rot[0] = cos(yd); rot[1] = -sin(yd); rot[2] = 0; rot[3] = sin(yd); rot[4] = cos(yd); rot[5] = 0; rot[6] = 0; rot[7] = 0; rot[8] = 1;
+            if (fabs(fabs(ypr0[1]) - 90) < 1.0 || fabs(fabs(ypr00[1]) - 90) < 1.0) {
+                double R00T[9] = {R00[0], R00[3], R00[6], R00[1], R00[4], R00[7], R00[2], R00[5], R00[8]};
+                d_mm(R0, R00T, rot);
+            }
+        } else { for (int k = 0; k < 9; ++k) rot[k] = (k % 4 == 0) ? 1.0 : 0.0; }
+        for (int k = 0; k < 9; ++k) sh.tmp[k] = rot[k];
+    }
+    __syncthreads();
+    for (int f = tid; f < BA_NF; f += BA_THREADS) {
+        const double *rot = sh.tmp;
+        double q[4] = {sh.pose[7 * f + 3], sh.pose[7 * f + 4], sh.pose[7 * f + 5], sh.pose[7 * f + 6]}, R[9], Rf[9];
+        double nq = sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+        q[0] /= nq; q[1] /= nq; q[2] /= nq; q[3] /= nq;
+        d_q2R(q, R);
+        if (m.use_imu) {
+            d_mm(rot, R, Rf);
+            double dd[3] = {sh.pose[7 * f] - sh.pose[0], sh.pose[7 * f + 1] - sh.pose[1], sh.pose[7 * f + 2] - sh.pose[2]}, t[3], v[3];
+            d_mv(rot, dd, t);
+            d_mv(rot, sh.sb + 9 * f, v);
+            for (int k = 0; k < 3; ++k) {
+                out.Ps[3 * f + k] = t[k] + p.pose0[k]; out.Vs[3 * f + k] = v[k];
+                out.Bas[3 * f + k] = sh.sb[9 * f + 3 + k]; out.Bgs[3 * f + k] = sh.sb[9 * f + 6 + k];
+            }
+        } else {
+            for (int k = 0; k < 9; ++k) Rf[k] = R[k];
+            for (int k = 0; k < 3; ++k) { out.Ps[3 * f + k] = sh.pose[7 * f + k]; out.Vs[3 * f + k] = 0; out.Bas[3 * f + k] = 0; out.Bgs[3 * f + k] = 0; }
+        }
+        for (int k = 0; k < 9; ++k) out.Rs[9 * f + k] = Rf[k];
+        // vector2double (estimator.cpp:936-981)
+        for (int k = 0; k < 3; ++k) out.mpose[7 * f + k] = out.Ps[3 * f + k];
+        d_R2q(Rf, out.mpose + 7 * f + 3);
+        for (int k = 0; k < 3; ++k) {
+            out.msb[9 * f + k] = m.use_imu ? out.Vs[3 * f + k] : sh.sb[9 * f + k];
+            out.msb[9 * f + 3 + k] = sh.sb[9 * f + 3 + k]; out.msb[9 * f + 6 + k] = sh.sb[9 * f + 6 + k];
+        }
+    }
+    if (tid == 0) {
+        for (int k = 0; k < 3; ++k) out.mex[k] = sh.ex[k];
+        if (m.use_imu) {
+            double q[4] = {sh.ex[3], sh.ex[4], sh.ex[5], sh.ex[6]}, R[9];
+            double nq = sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+            q[0] /= nq; q[1] /= nq; q[2] /= nq; q[3] /= nq;
+            d_q2R(q, R); d_R2q(R, out.mex + 3);
+        } else for (int k = 3; k < 7; ++k) out.mex[k] = sh.ex[k];
+    }
+    // setDepth / getDepthVector round trip of the inverse depths (feature_manager.cpp:197-223,302-324)
+    for (int l = tid; l < M; l += BA_THREADS) { double depth = 1.0 / p.lam[l]; p.clam[l] = 1.0 / depth; }
+    __syncthreads();
+    // ---- outputs ----
+    double nf_ = 0;
+    for (int i = tid; i < BA_NF * 7; i += BA_THREADS) { out.pose[i] = sh.pose[i]; if (!isfinite(sh.pose[i])) nf_ += 1; }
+    nf_ = block_sum(nf_, sh.red);
+    if (nf_ > 0) status = VRF_SOFT_NONFINITE;
+    for (int i = tid; i < BA_NF * 9; i += BA_THREADS) out.sb[i] = sh.sb[i];
+    if (tid < 7) out.ex[tid] = sh.ex[tid];
+    __syncthreads();
+    if (tid == 0) {
+        out.status = status; out.iterations = iterations; out.successful = successful; out.termination = termination;
+        out.initial_cost = initial_cost; out.final_cost = x_cost;
+    }
+}
+
+size_t ba_solve_smem_bytes() { return sizeof(BaShared); }
+
+int ba_solve_launch(const BaMeta *d_meta, const BaProbDev *d_prob, BaOutDev *d_out, int n, LaunchCtx &lc)
+{
+    static bool configured = false;
+    if (!configured) {
+        if (cudaFuncSetAttribute(k_ba_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BaShared)) != cudaSuccess) return -1;
+        configured = true;
+    }
+    lc.begin(K_BA_SOLVE);
+    k_ba_solve<<<n, BA_THREADS, sizeof(BaShared), lc.st>>>(d_meta, d_prob, d_out);
+    lc.end();
+    return 0;
+}
+
+}  // namespace vrf

@@ -101,7 +101,7 @@ EXPORTS = [
     "vrf_launch_count", "vrf_reset_sequence", "vrf_tracker_read_image", "vrf_tracker_read_image_batch",
     "vrf_tracker_enqueue_batch_dev", "vrf_tracker_fetch_batch", "vrf_synchronize", "vrf_stream",
     "vrf_profile_enable", "vrf_profile_read", "vrf_debug_sort_desc", "vrf_debug_read", "vrf_ba_solve", "vrf_ba_solve_batch", "vrf_ba_upload_batch",
-    "vrf_ba_enqueue_batch", "vrf_ba_download_batch", "vrf_debug_eval_projection", "vrf_debug_eval_imu",
+    "vrf_ba_enqueue_batch", "vrf_ba_download_batch",
 ]
 
 _lib = None
@@ -148,8 +148,6 @@ def load():
     lib.vrf_ba_upload_batch.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.POINTER(VrfBaProblem)]
     lib.vrf_ba_enqueue_batch.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
     lib.vrf_ba_download_batch.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.POINTER(VrfBaResult)]
-    lib.vrf_debug_eval_projection.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 11
-    lib.vrf_debug_eval_imu.argtypes = [C.c_void_p, C.c_int, C.POINTER(VrfImuPreint)] + [C.c_void_p] * 9
     _lib = lib
     return lib
 
@@ -329,6 +327,44 @@ class Handle:
             None if R_a is None else R_a.ctypes.data, None if p_a is None else p_a.ctypes.data, outs)
         check(rc, self.h)
         return [r.finish() for r in results]
+
+    # ---- back end ----
+    def ba_solve_batch(self, seqs, problems):
+        """problems: list of vrf_b200.ba_problem.BaProblem (finalized). Returns list of BaSolution."""
+        from .ba_problem import BaSolution
+        n = len(seqs)
+        seq_a = np.asarray(seqs, np.int32)
+        probs = (VrfBaProblem * n)()
+        sols = [BaSolution(pb.M) for pb in problems]
+        res = (VrfBaResult * n)()
+        for i, pb in enumerate(problems):
+            C.memmove(C.byref(probs[i]), C.byref(pb.c), C.sizeof(VrfBaProblem))
+            C.memmove(C.byref(res[i]), C.byref(sols[i].c), C.sizeof(VrfBaResult))
+        rc = self.lib.vrf_ba_solve_batch(self.h, n, seq_a.ctypes.data, probs, res)
+        check(rc, self.h)
+        for i, s in enumerate(sols):
+            C.memmove(C.byref(s.c), C.byref(res[i]), C.sizeof(VrfBaResult))
+            s.rc = res[i].status
+        return sols
+
+    def ba_solve(self, seq, problem):
+        return self.ba_solve_batch([seq], [problem])[0]
+
+    def ba_upload(self, seqs, problems):
+        n = len(seqs)
+        seq_a = np.asarray(seqs, np.int32)
+        probs = (VrfBaProblem * n)()
+        for i, pb in enumerate(problems):
+            C.memmove(C.byref(probs[i]), C.byref(pb.c), C.sizeof(VrfBaProblem))
+        check(self.lib.vrf_ba_upload_batch(self.h, n, seq_a.ctypes.data, probs), self.h, allow_soft=False)
+
+    def ba_enqueue(self, seqs):
+        seq_a = np.asarray(seqs, np.int32)
+        check(self.lib.vrf_ba_enqueue_batch(self.h, len(seqs), seq_a.ctypes.data), self.h, allow_soft=False)
+
+    def ba_download(self, seqs):
+        seq_a = np.asarray(seqs, np.int32)
+        check(self.lib.vrf_ba_download_batch(self.h, len(seqs), seq_a.ctypes.data, None), self.h)
 
     def enqueue_dev(self, seqs, d_ptr, fmt, times, Rs=None, pubs=None, d_depth=None):
         n = len(seqs)
