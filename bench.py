@@ -66,7 +66,7 @@ class ClockSampler:
              "clocks_event_reasons.sw_power_cap")
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
         except Exception:
@@ -163,7 +163,7 @@ def run_reference(args):
     sec = float(np.mean(t_all))
     fps = frames / sec
     line = {
-        "impl": "reference", "metric": "RGB-D VIO frames/sec (640x480, front end; back end pending)", "value": fps,
+        "impl": "reference", "metric": "RGB-D VIO frames/sec (640x480, 10-KF BA)", "value": fps,
         "unit": "frames/s", "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup,
         "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u8/f32 (cv2)", "data": "synthetic",
@@ -184,16 +184,46 @@ def _ref_worker(arg):
     s = synth.Sequence(seed)
     frames = [s.frame(k)[1] for k in range(min(n, T_FRAMES))]
     ft = FeatureTrackerRef(FrontendConfig(lk_max_level=2, use_ransac=int(os.environ.get("VRF_BENCH_RANSAC", "1"))))
+    # back end: one pre-generated 10-KF window (with prior) per worker, re-solved on every publish frame
+    from oracle import ba_ref
+    from vrf_b200 import ba_problem as BP, binding as B
+    cfg = ba_config()
+    sim = BP.WindowSimulator(seed, cfg, n_landmarks=BA_LANDMARKS)
+    sol = ba_ref.solve(cfg, sim.window(0)); sim.commit(0, sol)
+    pb = sim.window(1)
+    Rf = np.stack([s.relative_R(k) for k in range(len(frames))])
     t0 = time.perf_counter()
     for step in range(n):
         idx, pidx = frame_plan(step, len(frames))
-        R = np.eye(3) if step == 0 else rel_rotation(np.stack([s.relative_R(k) for k in range(len(frames))]), idx, pidx)
-        ft.read_image(frames[idx], 1.0 + step / 30.0, R, pub_this_frame=(step % PUB_EVERY == 0))
+        R = np.eye(3) if step == 0 else rel_rotation(Rf, idx, pidx)
+        pub = (step % PUB_EVERY == 0)
+        ft.read_image(frames[idx], 1.0 + step / 30.0, R, pub_this_frame=pub)
+        if pub:
+            ba_ref.solve(cfg, pb)          # Estimator::optimization: solve + marginalization, 1 thread (Ceres num_threads = 1)
     return len(ft.ids), time.perf_counter() - t0
 
 
-WORKLOAD = ("BASELINE configs[1]: 640x480 RGB-D stream, 150 feats, 3-level pyramid LK, 7x8 grid FAST, "
-            "publish every 3rd frame; RGB8+depth16 frames resident in HBM")
+BA_LANDMARKS = 150
+
+
+def ba_config():
+    """VrfConfig without touching CUDA (the reference arm must not create a context)."""
+    from vrf_b200 import binding as B
+    cfg = B.VrfConfig()
+    cfg.row, cfg.col, cfg.max_cnt, cfg.min_dist = H, W, 150, 25
+    cfg.num_grid_rows, cfg.num_grid_cols, cfg.use_imu, cfg.lk_max_level = 7, 8, 1, 2
+    cfg.use_ransac = int(os.environ.get("VRF_BENCH_RANSAC", "1"))
+    cfg.f_threshold, cfg.focal_length = 1.0, 460.0
+    cfg.fx = cfg.fy = 600.0; cfg.cx, cfg.cy = 320.0, 240.0
+    cfg.k1, cfg.k2, cfg.p1, cfg.p2 = 0.1, -0.2, 1e-3, 1e-3
+    cfg.num_iterations, cfg.fix_depth, cfg.depth_max_dist, cfg.g_norm = 8, 0, 10.0, 9.81
+    cfg.acc_n, cfg.acc_w, cfg.gyr_n, cfg.gyr_w = 0.1, 0.001, 0.01, 0.0001
+    return cfg
+
+
+WORKLOAD = ("BASELINE configs[1]+[2]: 640x480 RGB-D streams, 150 feats, 3-level pyramid LK, 7x8 grid FAST + RANSAC, "
+            "publish every 3rd frame (freq 10 Hz @ 30 Hz); every publish frame runs one 10-keyframe sliding-window BA "
+            "(150 landmarks, ~1000 projection factors, 10 IMU factors, prior n=75, 8 dogleg iterations) + marginalization")
 
 
 def main():
@@ -205,6 +235,7 @@ def main():
     ap.add_argument("--seqs", type=int, default=64, help="sequences per GPU")
     ap.add_argument("--ref-frames", type=int, default=24)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--quick", action="store_true", help="profiling runs: skip the e2e arm and the CPU baseline")
     args = ap.parse_args()
     if args.impl != "reference":
         args.warmup = max(args.warmup, 3)
@@ -221,7 +252,7 @@ def main():
     # CPU baseline first, in a child process, before this process creates a CUDA context
     # (the oracle fans out over all host cores with multiprocessing)
     cpu_base = None
-    if rank == 0 and not args.no_cpu_baseline:
+    if rank == 0 and not args.no_cpu_baseline and not args.quick:
         try:
             out = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "1",
                                   "--warmup", "0", "--ref-frames", "24"], capture_output=True, text=True, timeout=600)
@@ -250,8 +281,28 @@ def main():
     # pinned host mirrors for the e2e arm
     h_rgb = [torch.from_numpy(b[0]).pin_memory() for b in base]
 
-    cfg = binding.default_config(lk_max_level=2, use_ransac=int(os.environ.get("VRF_BENCH_RANSAC", "1")))
+    cfg = ba_config()
     hnd = binding.Handle(cfg, S, local_rank)
+    # ---- back-end inputs: one 10-KF window per publishing sequence (S/3 per step), generated with the
+    # oracle's window simulator (prior from a first solved window), uploaded to HBM before timing ----
+    from oracle import ba_ref                      # input generation only (IMU pre-integration + first-window prior)
+    from vrf_b200 import ba_problem as BP
+    NBA = max(1, S // PUB_EVERY)
+    ba_probs = []
+    n_ba_distinct = min(NBA, 8)
+    for i in range(n_ba_distinct):
+        sim = BP.WindowSimulator(1234 + i, cfg, n_landmarks=BA_LANDMARKS)
+        sol0 = ba_ref.solve(cfg, sim.window(0)); sim.commit(0, sol0)
+        ba_probs.append(sim.window(1))
+    ba_batch = [ba_probs[i % n_ba_distinct] for i in range(NBA)]
+    ba_seqs = list(range(NBA))
+    ba_bytes = sum(56 * len(pb.obs_pts) + 8 * (75 * 75 + 75) + 10 * 3800 + 1500 for pb in ba_batch)
+    # the back end runs on its own handle/stream so that it overlaps the front end, as the
+    # reference's processThread overlaps its trackThread (estimator_nodelet.cpp:61-62)
+    hnd_ba = binding.Handle(cfg, NBA, local_rank)
+    ext_stream_ba = torch.cuda.ExternalStream(hnd_ba.stream(), device=dev)
+    hnd_ba.ba_upload(ba_seqs, ba_batch)
+    hnd_ba.synchronize()
     ext_stream = torch.cuda.ExternalStream(hnd.stream(), device=dev)
     seqs = list(range(S))
     # sequence s plays base s % nb with phase offset (s // nb) so that publish frames are staggered
@@ -283,28 +334,32 @@ def main():
     def run_dev_step(k):
         idxs, Rs, pubs, times = plans[k]
         hnd.enqueue_dev(seqs, d_steps[k % PERIOD].data_ptr(), binding.FMT_RGB8, times, Rs, pubs, d_depth=None)
+        hnd_ba.ba_enqueue(ba_seqs)           # S/3 windows: solve + gauge fix + marginalization
 
     # ---- warm-up ----
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for k in range(args.warmup):
         run_dev_step(k)
-    hnd.synchronize()
+    hnd.synchronize(); hnd_ba.synchronize()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    l0 = hnd.launches
+    l0 = hnd.launches + hnd_ba.launches
     ev0 = torch.cuda.Event(enable_timing=True)
     ev1 = torch.cuda.Event(enable_timing=True)
+    ev1b = torch.cuda.Event(enable_timing=True)
     ev0.record(ext_stream)
+    ext_stream_ba.wait_event(ev0)            # common start for both streams
     for k in range(args.warmup, args.warmup + args.steps):
         run_dev_step(k)
     ev1.record(ext_stream)
-    hnd.synchronize()
+    ev1b.record(ext_stream_ba)
+    hnd.synchronize(); hnd_ba.synchronize()
     torch.cuda.synchronize()
     clocks = sampler.stop()
-    launches = hnd.launches - l0
-    ms_total = ev0.elapsed_time(ev1)
+    launches = hnd.launches + hnd_ba.launches - l0
+    ms_total = max(ev0.elapsed_time(ev1), ev0.elapsed_time(ev1b))
     t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
     if world > 1:
         dist.barrier()
@@ -314,13 +369,15 @@ def main():
     value = frames_total / (ms_total_max * 1e-3)
 
     # ---- profiled pass (per-kernel CUDA events) for the roofline ----
-    hnd.profile(True)
-    hnd.profile_read(reset=True)
+    hnd.profile(True); hnd_ba.profile(True)
+    hnd.profile_read(reset=True); hnd_ba.profile_read(reset=True)
     nprof = min(12, args.steps)
     for k in range(args.warmup, args.warmup + nprof):
         run_dev_step(k)
     prof = hnd.profile_read(reset=True)
-    hnd.profile(False)
+    for kname, v in hnd_ba.profile_read(reset=True).items():
+        prof[kname] = (prof.get(kname, (0.0, 0))[0] + v[0], prof.get(kname, (0, 0))[1] + v[1])
+    hnd.profile(False); hnd_ba.profile(False)
     tot_ms = sum(v[0] for v in prof.values()) or 1.0
     kern = {k: {"ms_per_step": v[0] / nprof, "launches_per_step": v[1] / nprof, "share": v[0] / tot_ms}
             for k, v in prof.items() if v[1] > 0}
@@ -329,8 +386,10 @@ def main():
     roof = None
     if dom:
         # algorithmic bytes per launch of the dominant kernel (DESIGN.md section "roofline")
+        # algorithmic bytes per launch (DESIGN.md "Roofline"): image kernels = frame bytes they must move;
+        # k_ba_solve = the BA problem bytes of SURVEY 8(d); other kernels are charged the per-frame A_frame.
         alg = {"k_ingest": S * (3 * W * H + W * H),                 # RGB8 read + gray write
-               "k_pyrdown": None, "k_lk": None, "k_fast": None}.get(dom)
+               "k_ba_solve": ba_bytes, "k_ba_marg": ba_bytes}.get(dom)
         per_launch_ms = kern[dom]["ms_per_step"] / max(kern[dom]["launches_per_step"], 1e-9)
         alg_bytes = alg if alg else S * A_FRAME / max(kern[dom]["launches_per_step"], 1)
         ach = alg_bytes / (per_launch_ms * 1e-3) / 1e9
@@ -339,15 +398,17 @@ def main():
                 "alg_bytes_per_launch": alg_bytes, "launch_ms": per_launch_ms, "kernels": kern}
 
     # ---- e2e arm: host buffers through the C ABI (H2D + kernels + D2H per step) ----
-    e2e_steps = max(3, min(args.steps, 20))
+    e2e_steps = 0 if args.quick else max(3, min(args.steps, 20))
     hnd2 = binding.Handle(cfg, S, local_rank)
 
     def run_host_step(k):
         idxs, Rs, pubs, times = plans[k]
         imgs = [h_rgb[s % nb][idxs[s]].numpy() for s in seqs]
-        return hnd2.read_image_batch(seqs, imgs, times, Rs, pubs, debug=False)
+        outs_ = hnd2.read_image_batch(seqs, imgs, times, Rs, pubs, debug=False)
+        hnd2.ba_solve_batch(ba_seqs, ba_batch)      # host problems in, optimised states + prior out
+        return outs_
 
-    for k in range(3):
+    for k in range(3 if e2e_steps else 0):
         run_host_step(k)
     torch.cuda.synchronize()
     if world > 1:
@@ -356,30 +417,30 @@ def main():
     d2h = 0
     for k in range(3, 3 + e2e_steps):
         outs = run_host_step(k)
-        d2h = sum(o.n for o in outs) * 32 + S * 32
+        d2h = sum(o.n for o in outs) * 32 + S * 32 + NBA * (11 * (7 + 9 + 3 + 9 + 9) * 8 + 8 * BA_LANDMARKS + 76 * 77 * 8)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
     if world > 1:
         dist.barrier()
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_val = S * e2e_steps * world / float(t.item())
+    e2e_val = (S * e2e_steps * world / float(t.item())) if e2e_steps else None
     hnd2.close()
 
     if rank == 0:
         line = {
-            "metric": "RGB-D VIO frames/sec (640x480, front end; back end pending)", "value": value, "unit": "frames/s",
+            "metric": "RGB-D VIO frames/sec (640x480, 10-KF BA)", "value": value, "unit": "frames/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total_max / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/i32/f32 (LK), f64 (camera model)",
             "data": f"synthetic: {nb} rendered base sequences x {T_FRAMES} frames (ping-pong), replicated to {S} sequences/GPU with phase offsets",
-            "config": {"workload": WORKLOAD, "seqs_per_gpu": S, "l2": "inputs cycle through %d MB of distinct frames (> L2)" % (nb * T_FRAMES * 3 * W * H // 2**20),
+            "config": {"workload": WORKLOAD, "seqs_per_gpu": S, "ba_solves_per_step": NBA, "l2": "inputs cycle through %d MB of distinct frames (> L2)" % (nb * T_FRAMES * 3 * W * H // 2**20),
                        "parallelism": f"sequences sharded over {world} GPU(s), no data-path collective"},
             "clocks": clocks, "gpu_launches": int(launches),
-            "e2e": {"value": e2e_val, "unit": "frames/s", "h2d_bytes_per_step": S * 3 * W * H, "d2h_bytes_per_step": int(d2h)},
+            "e2e": {"value": e2e_val, "unit": "frames/s", "h2d_bytes_per_step": S * 3 * W * H + int(ba_bytes), "d2h_bytes_per_step": int(d2h)},
             "roofline": roof, "cpu_baseline": cpu_base,
         }
         print(json.dumps(line))
-    hnd.close()
+    hnd.close(); hnd_ba.close()
     if world > 1:
         dist.destroy_process_group()
 
