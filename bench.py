@@ -232,7 +232,7 @@ def main():
     ap.add_argument("--steps", type=int, default=60)
     ap.add_argument("--warmup", type=int, default=6)
     ap.add_argument("--impl", default="ours")
-    ap.add_argument("--seqs", type=int, default=64, help="sequences per GPU")
+    ap.add_argument("--seqs", type=int, default=444, help="sequences per GPU (444 => 148 concurrent BA windows = one CTA per SM)")
     ap.add_argument("--ref-frames", type=int, default=24)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--quick", action="store_true", help="profiling runs: skip the e2e arm and the CPU baseline")
@@ -378,6 +378,10 @@ def main():
     for kname, v in hnd_ba.profile_read(reset=True).items():
         prof[kname] = (prof.get(kname, (0.0, 0))[0] + v[0], prof.get(kname, (0, 0))[1] + v[1])
     hnd.profile(False); hnd_ba.profile(False)
+    try:
+        ba_phase = hnd_ba.debug_read("ba_prof", 0, np.int64, 8).tolist()
+    except Exception:
+        ba_phase = None
     tot_ms = sum(v[0] for v in prof.values()) or 1.0
     kern = {k: {"ms_per_step": v[0] / nprof, "launches_per_step": v[1] / nprof, "share": v[0] / tot_ms}
             for k, v in prof.items() if v[1] > 0}
@@ -395,7 +399,8 @@ def main():
         ach = alg_bytes / (per_launch_ms * 1e-3) / 1e9
         roof = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                 "frac": ach / peaks["hbm_gbs"], "traffic": None, "peak_source": peak_kind,
-                "alg_bytes_per_launch": alg_bytes, "launch_ms": per_launch_ms, "kernels": kern}
+                "alg_bytes_per_launch": alg_bytes, "launch_ms": per_launch_ms, "kernels": kern,
+                "ba_solve_phase_cycles": dict(zip(["linearise", "scale_grad", "cauchy", "schur", "cholesky", "solve_tail", "dogleg", "candidate"], ba_phase)) if ba_phase else None}
 
     # ---- e2e arm: host buffers through the C ABI (H2D + kernels + D2H per step) ----
     e2e_steps = 0 if args.quick else max(3, min(args.steps, 20))

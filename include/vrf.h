@@ -186,7 +186,8 @@ void vrf_debug_sort_desc(const int32_t *cnt, int32_t n, int32_t *perm_out);
 /* Copies an internal per-sequence device array to host (parity tests only).
  * what: "pyr<L>" (level L of the current image pyramid, rows*cols u8, tightly packed),
  *       "cand" (cells*kmax*3 float: x,y,response), "ncand" (cells int32),
- *       "cell_k" (cells int32), "maskpts" (2*n int32) -- returns bytes written or <0. */
+ *       "cell_k" (cells int32), "maskpts" (2*n int32), "ba_prof" (8 int64 SM clock counts per
+ *       phase of the last k_ba_solve in batch slot `seq`) -- returns bytes written or <0. */
 long vrf_debug_read(vrf_handle *h, const char *what, int seq, void *dst, size_t dst_bytes);
 
 /* ------------------------------------------------------------------------- */

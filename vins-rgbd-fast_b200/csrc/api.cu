@@ -384,6 +384,7 @@ extern "C" long vrf_debug_read(vrf_handle *h, const char *what, int seq, void *d
         if (cudaMemcpy2D(dst, c.lw[l], src, c.lp[l], c.lw[l], c.lh[l], cudaMemcpyDeviceToHost) != cudaSuccess) return VRF_ERR_CUDA;
         return (long)need;
     }
+    if (w == "ba_prof") return ba_debug_prof(h, seq, dst, dst_bytes);
     const void *src = nullptr;
     size_t need = 0;
     if (w == "cand") { src = d.cand + (size_t)seq * VRF_MAX_CELLS * c.kmax * 3; need = (size_t)c.ncells * c.kmax * 3 * sizeof(float); }

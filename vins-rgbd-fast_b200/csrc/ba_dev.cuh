@@ -59,6 +59,7 @@ struct BaOutDev {
     // states re-packed by vector2double after the gauge fix (marginalization linearises here)
     double mpose[BA_NF * 7], msb[BA_NF * 9], mex[7];
     int has_new_prior, pad;
+    long long prof[8];   // clock64 per phase: 0 linearise, 1 scale+grad, 2 cauchy, 3 schur, 4 cholesky, 5 solve tail, 6 dogleg, 7 candidate cost
 };
 
 // global scratch of the marginalization kernel (per problem)

@@ -287,6 +287,16 @@ static int download(vrf_handle *h, int n, const int32_t *seqs, VrfBaResult *res)
     return worst;
 }
 
+long ba_debug_prof(vrf_handle *h, int slot, void *dst, size_t bytes)
+{
+    BaState *b = h->ba;
+    if (!b || slot < 0 || slot >= h->n_seq || bytes < sizeof(long long) * 8) return VRF_ERR_ARG;
+    BaOutDev tmp;
+    if (cudaMemcpy(&tmp, b->d_out + slot, sizeof(BaOutDev), cudaMemcpyDeviceToHost) != cudaSuccess) return VRF_ERR_CUDA;
+    memcpy(dst, tmp.prof, sizeof(long long) * 8);
+    return (long)(sizeof(long long) * 8);
+}
+
 }  // namespace vrf
 
 using namespace vrf;

@@ -65,17 +65,20 @@ __device__ double ba_evaluate(const BaMeta &m, const BaProbDev &p, BaShared &sh,
     if (tid == 0) d_q2R(sh.ex + 3, sh.ric);
     __syncthreads();
     double cost = 0.0;
-    // ---- projection factors: one warp per landmark, one lane per factor ----
-    for (int l = warp; l < m.M; l += nwarp) {
-        const int o0 = p.obs_ptr[l], nf = p.obs_ptr[l + 1] - o0 - 1;
-        const int i = p.start[l];
-        const bool lc = p.lm_const[l] != 0;
+    // ---- projection factors: two landmarks per warp (16 lanes each), one lane per factor (track length <= 11) ----
+    const int half = lane >> 4, hl = lane & 15;
+    for (int lp = warp; 2 * lp < m.M; lp += nwarp) {
+        const int l = 2 * lp + half;
+        const bool lv = l < m.M;
+        const int o0 = lv ? p.obs_ptr[l] : 0, nf = lv ? p.obs_ptr[l + 1] - o0 - 1 : 0;
+        const int i = lv ? p.start[l] : 0;
+        const bool lc = lv ? (p.lm_const[l] != 0) : true;
         double r[2] = {0, 0}, Ji[12], Jj[12], Jl[2] = {0, 0};
-        const bool act = lane < nf;
-        const int j = i + 1 + lane;
+        const bool act = hl < nf;
+        const int j = i + 1 + hl;
         if (act) {
             const double xi = p.obs[2 * o0], yi = p.obs[2 * o0 + 1];
-            const double xj = p.obs[2 * (o0 + 1 + lane)], yj = p.obs[2 * (o0 + 1 + lane) + 1];
+            const double xj = p.obs[2 * (o0 + 1 + hl)], yj = p.obs[2 * (o0 + 1 + hl) + 1];
             double rho0 = proj_eval(pose + 7 * i, sh.R + 9 * i, pose + 7 * j, sh.R + 9 * j, sh.ex, sh.ric, lam[l], xi, yi, xj, yj,
                                     lin, lc, r, Ji, Jj, Jl);
             cost += 0.5 * rho0;
@@ -85,22 +88,22 @@ __device__ double ba_evaluate(const BaMeta &m, const BaProbDev &p, BaShared &sh,
 #pragma unroll
             for (int k = 0; k < 12; ++k) { Ji[k] = 0; Jj[k] = 0; }
         }
-        // landmark scalars
-        double hl = warp_sum_d(Jl[0] * Jl[0] + Jl[1] * Jl[1]);
-        double gl = warp_sum_d(Jl[0] * r[0] + Jl[1] * r[1]);
-        double *Wl = p.W + (size_t)l * 66;
-        for (int k = lane; k < 66; k += 32) Wl[k] = 0.0;
+        // landmark scalars (reductions stay inside the 16-lane half)
+        double hl_ = half_sum_d(Jl[0] * Jl[0] + Jl[1] * Jl[1]);
+        double gl = half_sum_d(Jl[0] * r[0] + Jl[1] * r[1]);
+        double *Wl = p.W + (size_t)(lv ? l : 0) * 66;
+        if (lv) for (int k = hl; k < 66; k += 16) Wl[k] = 0.0;
         __syncwarp();
         // host-pose parts (reduced over the landmark's factors), then lane-private observer parts
 #pragma unroll
         for (int a = 0; a < 6; ++a) {
-            double wi = warp_sum_d(Ji[a] * Jl[0] + Ji[6 + a] * Jl[1]);
-            double gi = warp_sum_d(Ji[a] * r[0] + Ji[6 + a] * r[1]);
-            if (lane == 0) { Wl[6 * i + a] = wi; atomicAdd(&sh.g[6 * i + a], gi); }
+            double wi = half_sum_d(Ji[a] * Jl[0] + Ji[6 + a] * Jl[1]);
+            double gi = half_sum_d(Ji[a] * r[0] + Ji[6 + a] * r[1]);
+            if (hl == 0 && lv) { Wl[6 * i + a] = wi; atomicAdd(&sh.g[6 * i + a], gi); }
 #pragma unroll
             for (int b = 0; b <= a; ++b) {
-                double h = warp_sum_d(Ji[a] * Ji[b] + Ji[6 + a] * Ji[6 + b]);
-                if (lane == 0) atomicAdd(&sh.H[pk(6 * i + a, 6 * i + b)], h);
+                double h = half_sum_d(Ji[a] * Ji[b] + Ji[6 + a] * Ji[6 + b]);
+                if (hl == 0 && lv) atomicAdd(&sh.H[pk(6 * i + a, 6 * i + b)], h);
             }
         }
         if (act) {
@@ -114,7 +117,7 @@ __device__ double ba_evaluate(const BaMeta &m, const BaProbDev &p, BaShared &sh,
                 for (int b = 0; b < 6; ++b) atomicAdd(&sh.H[pk(6 * j + a, 6 * i + b)], Jj[a] * Ji[b] + Jj[6 + a] * Ji[6 + b]);
             }
         }
-        if (lane == 0) { p.hll[l] = hl; p.gl[l] = gl; }
+        if (hl == 0 && lv) { p.hll[l] = hl_; p.gl[l] = gl; }
     }
     // ---- IMU factors: one warp per factor ----
     for (int f = warp; f < m.nimu; f += nwarp) {
@@ -240,7 +243,10 @@ k_ba_solve(const BaMeta *metas, const BaProbDev *probs, BaOutDev *outs)
     __syncthreads();
     __threadfence_block();
 
+    long long tprof[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tmark = clock64();
+#define TPROF(k) do { long long t_ = clock64(); tprof[k] += t_ - tmark; tmark = t_; } while (0)
     double x_cost = ba_evaluate(m, p, sh, sh.pose, sh.sb, p.lam, true);
+    TPROF(0);
     const double initial_cost = x_cost;
     // Jacobi scaling (once): 1 / (1 + ||column||)
     for (int c = tid; c < BA_NC; c += BA_THREADS) sh.jscale[c] = 1.0 / (1.0 + sqrt(sh.H[pk(c, c)]));
@@ -312,6 +318,7 @@ k_ba_solve(const BaMeta *metas, const BaProbDev *probs, BaOutDev *outs)
                 gradient_max = mx;
             }
             need_scale = 0;
+            TPROF(1);
         }
         if (iterations >= max_iter) { termination = 0; break; }
         if (gradient_max <= 1e-10) { termination = 2; break; }
@@ -361,6 +368,7 @@ k_ba_solve(const BaMeta *metas, const BaProbDev *probs, BaOutDev *outs)
                     utg = block_sum(t, sh.red);
                 }
             }
+            TPROF(2);
             // Gauss-Newton step: (H + mu D^2) y = g by Schur complement + Cholesky, retried with larger mu
             bool solved = false;
             while (mu < max_mu) {
@@ -412,38 +420,72 @@ k_ba_solve(const BaMeta *metas, const BaProbDev *probs, BaOutDev *outs)
                 }
                 for (int c = tid; c < BA_NC; c += BA_THREADS) sh.H[pk(c, c)] += mu * sh.diag[c] * sh.diag[c];
                 __syncthreads();
-                // in-place right-looking Cholesky (lower, packed) of the 171x171 reduced camera system.  The
-                // right-hand side rides along as an extra row (index BA_NC), which performs the forward
-                // substitution L z = g for free.
+                TPROF(3);
+                // in-place blocked Cholesky (lower, packed, panel width 8) of the 171x171 reduced camera system.
+                // The right-hand side rides along as an extra row (index BA_NC): forward substitution for free.
+                // Per panel: (1) warp 0 factors the 8x8 diagonal block, (2) one thread per row solves the
+                // panel's triangular system, (3) rank-8 update of the trailing matrix  => 3 barriers / panel.
                 bool bad = sh.flag[0] != 0;
-                for (int j = 0; j < BA_NC && !bad; ++j) {
+                for (int j0 = 0; j0 < BA_NC && !bad; j0 += 8) {
+                    const int nbp = min(8, BA_NC - j0);
                     if (tid == 0) {
-                        double d = sh.H[pk(j, j)];
-                        if (!(d > 0.0)) sh.flag[0] = 1; else sh.H[pk(j, j)] = sqrt(d);
+                        for (int jj = 0; jj < nbp; ++jj) {
+                            const int j = j0 + jj;
+                            double *rj = sh.H + j * (j + 1) / 2;
+                            double dsum = rj[j];
+                            for (int k = j0; k < j; ++k) dsum -= rj[k] * rj[k];
+                            if (!(dsum > 0.0)) { sh.flag[0] = 1; break; }
+                            const double ljj = sqrt(dsum);
+                            rj[j] = ljj;
+                            for (int i2 = j + 1; i2 < j0 + nbp; ++i2) {
+                                double *ri = sh.H + i2 * (i2 + 1) / 2;
+                                double t = ri[j];
+                                for (int k = j0; k < j; ++k) t -= ri[k] * rj[k];
+                                ri[j] = t / ljj;
+                            }
+                        }
                     }
                     __syncthreads();
                     if (sh.flag[0]) { bad = true; break; }
-                    const double ljj = sh.H[pk(j, j)];
-                    for (int i = j + 1 + tid; i <= BA_NC; i += BA_THREADS) {
-                        if (i < BA_NC) { double v = sh.H[pk(i, j)] / ljj; sh.H[pk(i, j)] = v; sh.colv[i] = v; }
-                        else { double v = sh.y[j] / ljj; sh.y[j] = v; sh.colv[BA_NC] = v; }
+                    // (2) rows below the panel (incl. the rhs row): x * Ld^T = a
+                    for (int i2 = j0 + nbp + tid; i2 <= BA_NC; i2 += BA_THREADS) {
+                        double *ri = (i2 < BA_NC) ? sh.H + i2 * (i2 + 1) / 2 : sh.y;
+                        double x[8];
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) {
+                            if (c < nbp) {
+                                const double *rc = sh.H + (j0 + c) * (j0 + c + 1) / 2;
+                                double t = ri[j0 + c];
+                                for (int k = 0; k < c; ++k) t -= x[k] * rc[j0 + k];
+                                x[c] = t / rc[j0 + c];
+                                ri[j0 + c] = x[c];
+                            }
+                        }
                     }
                     __syncthreads();
-                    // trailing update H[ii,kk] -= L[ii,j] L[kk,j], j < kk <= ii; 16 x 32 thread tile over (ii, kk)
+                    // (3) trailing update H[ii,kk] -= sum_c L[ii,j0+c] L[kk,j0+c]; 16 x 32 thread tile over (ii, kk)
                     {
                         const int tx = tid & 31, ty = tid >> 5;
-                        for (int ii = j + 1 + ty; ii <= BA_NC; ii += BA_THREADS / 32) {
-                            const double li = sh.colv[ii];
-                            if (ii < BA_NC) {
-                                double *row = sh.H + ii * (ii + 1) / 2;
-                                for (int kk = j + 1 + tx; kk <= ii; kk += 32) row[kk] -= li * sh.colv[kk];
-                            } else {
-                                for (int kk = j + 1 + tx; kk < BA_NC; kk += 32) sh.y[kk] -= li * sh.colv[kk];
+                        const int t0 = j0 + nbp;
+                        for (int ii = t0 + ty; ii <= BA_NC; ii += BA_THREADS / 32) {
+                            const double *li = (ii < BA_NC) ? sh.H + ii * (ii + 1) / 2 + j0 : sh.y + j0;
+                            double lv[8];
+#pragma unroll
+                            for (int c = 0; c < 8; ++c) lv[c] = (c < nbp) ? li[c] : 0.0;
+                            double *row = (ii < BA_NC) ? sh.H + ii * (ii + 1) / 2 : sh.y;
+                            const int kend = (ii < BA_NC) ? ii : BA_NC - 1;
+                            for (int kk = t0 + tx; kk <= kend; kk += 32) {
+                                const double *lk = sh.H + kk * (kk + 1) / 2 + j0;
+                                double acc = 0;
+#pragma unroll
+                                for (int c = 0; c < 8; ++c) if (c < nbp) acc += lv[c] * lk[c];
+                                row[kk] -= acc;
                             }
                         }
                     }
                     __syncthreads();
                 }
+                TPROF(4);
                 if (!bad) {
                     // back substitution L^T x = z by one warp (warp-level sync only)
                     if (warp == 0) {
@@ -496,6 +538,7 @@ k_ba_solve(const BaMeta *metas, const BaProbDev *probs, BaOutDev *outs)
                 }
                 __syncthreads();
             }
+            TPROF(5);
             if (!solved) { status = VRF_SOFT_NOT_SPD; step_ok = false; }
             else {
                 // gauss_newton_step_ = -diag * y ; scalar products needed by the dogleg model
@@ -563,7 +606,9 @@ k_ba_solve(const BaMeta *metas, const BaProbDev *probs, BaOutDev *outs)
                     p.clam[l] = v;
                 }
                 __syncthreads();
+                TPROF(6);
                 const double cand_cost = ba_evaluate(m, p, sh, sh.cpose, sh.csb, p.clam, false);
+                TPROF(7);
                 // step norm over the non-constant blocks (ambient space)
                 double sn = 0;
                 for (int i = tid; i < BA_NF * 7; i += BA_THREADS) if (col_active_dev(m, 6 * (i / 7))) { double dd = sh.pose[i] - sh.cpose[i]; sn += dd * dd; }
@@ -581,7 +626,9 @@ k_ba_solve(const BaMeta *metas, const BaProbDev *probs, BaOutDev *outs)
                     __syncthreads();
                     x_cost = cand_cost;
                     x_norm = sqrt(xnorm2(sh.pose, sh.sb, p.lam));
+                    TPROF(6);
                     ba_evaluate(m, p, sh, sh.pose, sh.sb, p.lam, true);
+                    TPROF(0);
                     need_scale = 1;
                     ++successful;
                     if (rho < 0.25) radius *= 0.5;
@@ -673,6 +720,7 @@ k_ba_solve(const BaMeta *metas, const BaProbDev *probs, BaOutDev *outs)
     if (tid == 0) {
         out.status = status; out.iterations = iterations; out.successful = successful; out.termination = termination;
         out.initial_cost = initial_cost; out.final_cost = x_cost;
+        for (int k = 0; k < 8; ++k) out.prof[k] = tprof[k];
     }
 }
 

@@ -99,6 +99,81 @@ __device__ void jacobi_eig(double *A, double *V, int n, MargShared &sh)
     __syncthreads();
 }
 
+// Same algorithm on matrices held in shared memory (n <= MARG_SMEM_N).  Row and column
+// rotations of a round are fused: the 2x2 block at rows {p1,q1} x cols {p2,q2} of J^T A J
+// only depends on the same 4 entries of A, so every (pair, pair) block is updated in place by
+// one thread and a round needs two barriers instead of three global-memory phases.
+#define MARG_SMEM_N 110
+__device__ void jacobi_eig_smem(double *A, double *V, int n, MargShared &sh)
+{
+    const int tid = threadIdx.x;
+    for (int e = tid; e < n * n; e += BA_THREADS) V[e] = (e / n == e % n) ? 1.0 : 0.0;
+    __syncthreads();
+    if (n < 2) return;
+    const int ne = (n + 1) & ~1;
+    const int npairs = ne / 2;
+    for (int sweep = 0; sweep < 40; ++sweep) {
+        double off = 0, dg = 0;
+        for (int e = tid; e < n * n; e += BA_THREADS) {
+            int i = e / n, j = e - i * n;
+            double v = A[e];
+            if (i == j) dg += v * v; else if (j > i) off += v * v;
+        }
+        off = block_sum(off, sh.red);
+        dg = block_sum(dg, sh.red);
+        if (off <= 1e-30 * dg || off == 0.0) break;
+        for (int r = 0; r < ne - 1; ++r) {
+            for (int k = tid; k < npairs; k += BA_THREADS) {
+                int p, q;
+                if (k == 0) { p = ne - 1; q = r; }
+                else { p = (r + k) % (ne - 1); q = (r - k + (ne - 1)) % (ne - 1); }
+                if (p > q) { int t = p; p = q; q = t; }
+                double c = 1.0, s_ = 0.0;
+                if (q < n) {
+                    double apq = A[p * n + q];
+                    if (apq != 0.0) {
+                        double app = A[p * n + p], aqq = A[q * n + q];
+                        double tau = (aqq - app) / (2.0 * apq);
+                        double t = (tau >= 0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
+                        c = 1.0 / sqrt(1.0 + t * t); s_ = t * c;
+                    }
+                } else { q = -1; }
+                sh.cs[2 * k] = c; sh.cs[2 * k + 1] = s_; sh.pq[2 * k] = p; sh.pq[2 * k + 1] = q;
+            }
+            __syncthreads();
+            const int nblk = npairs * npairs, nv = npairs * n;
+            for (int e = tid; e < nblk + nv; e += BA_THREADS) {
+                if (e < nblk) {
+                    const int k1 = e / npairs, k2 = e - k1 * npairs;
+                    const int p1 = sh.pq[2 * k1], q1 = sh.pq[2 * k1 + 1], p2 = sh.pq[2 * k2], q2 = sh.pq[2 * k2 + 1];
+                    const double c1 = sh.cs[2 * k1], s1 = sh.cs[2 * k1 + 1], c2 = sh.cs[2 * k2], s2 = sh.cs[2 * k2 + 1];
+                    if (s1 == 0.0 && s2 == 0.0) continue;
+                    const double a11 = A[p1 * n + p2];
+                    const double a12 = q2 >= 0 ? A[p1 * n + q2] : 0.0;
+                    const double a21 = q1 >= 0 ? A[q1 * n + p2] : 0.0;
+                    const double a22 = (q1 >= 0 && q2 >= 0) ? A[q1 * n + q2] : 0.0;
+                    const double t11 = c2 * a11 - s2 * a12, t12 = s2 * a11 + c2 * a12;
+                    const double t21 = c2 * a21 - s2 * a22, t22 = s2 * a21 + c2 * a22;
+                    A[p1 * n + p2] = c1 * t11 - s1 * t21;
+                    if (q2 >= 0) A[p1 * n + q2] = c1 * t12 - s1 * t22;
+                    if (q1 >= 0) A[q1 * n + p2] = s1 * t11 + c1 * t21;
+                    if (q1 >= 0 && q2 >= 0) A[q1 * n + q2] = s1 * t12 + c1 * t22;
+                } else {
+                    const int f = e - nblk;
+                    const int k = f / n, i = f - k * n;
+                    const int p_ = sh.pq[2 * k], q_ = sh.pq[2 * k + 1];
+                    const double c = sh.cs[2 * k], s_ = sh.cs[2 * k + 1];
+                    if (q_ < 0 || s_ == 0.0) continue;
+                    const double a = V[i * n + p_], b = V[i * n + q_];
+                    V[i * n + p_] = c * a - s_ * b; V[i * n + q_] = s_ * a + c * b;
+                }
+            }
+            __syncthreads();
+        }
+    }
+    __syncthreads();
+}
+
 __device__ __forceinline__ int find_block(const MargShared &sh, int kind, int index)
 {
     for (int i = 0; i < sh.nb; ++i) if (sh.kind[i] == kind && sh.index[i] == index) return i;
@@ -276,52 +351,161 @@ k_ba_marg(const BaMeta *metas, const BaProbDev *probs, BaOutDev *outs, const BaM
     }
     __syncthreads();
     __threadfence();
-    // ---- 3. A_mm pseudo-inverse through its eigen-decomposition ----
-    double *V = mg.V, *Ainv = mg.Ainv, *Amm = mg.Ainv;       // Amm lives in Ainv's buffer until the inverse is formed
-    double *Tm = mg.T;
-    // symmetrise into a separate m x m matrix (keep A intact for the Schur complement)
-    double *Ms = mg.Ar;      // temporary? no: Ar is n x n.  Use T's buffer if large enough, else V2 -- sized on host for m*m
-    (void)Ms;
-    for (int e = tid; e < mm * mm; e += BA_THREADS) { int i = e / mm, j = e - i * mm; Amm[e] = 0.5 * (A[(size_t)i * pos + j] + A[(size_t)j * pos + i]); }
-    __syncthreads();
-    jacobi_eig(Amm, V, mm, sh);
-    // Ainv = V diag(winv) V^T ; eigenvalues are on the diagonal of Amm: stash them first
-    double *wv = mg.br;      // br has room for n doubles only; use T's front (n*m >= m when n >= 1) for m eigenvalues
-    wv = Tm;
-    for (int k = tid; k < mm; k += BA_THREADS) { double w = Amm[(size_t)k * mm + k]; wv[k] = (w > 1e-8) ? 1.0 / w : 0.0; }
-    __syncthreads();
-    // scale V columns into Amm buffer is unsafe (aliasing): build Ainv row by row from V and wv into Ainv after copying wv to smem
-    for (int k = tid; k < mm && k < 2 * (BA_MAX_POS / 2 + 2); k += BA_THREADS) sh.cs[k] = wv[k];
-    __syncthreads();
-    for (int e = tid; e < mm * mm; e += BA_THREADS) {
-        int i = e / mm, j = e - i * mm;
-        double a = 0;
-        for (int k = 0; k < mm; ++k) a += V[(size_t)i * mm + k] * sh.cs[k] * V[(size_t)j * mm + k];
-        Ainv[e] = a;
-    }
-    __syncthreads();
-    // ---- 4. Schur complement ----
-    for (int e = tid; e < nn * mm; e += BA_THREADS) {
-        int i = e / mm, j = e - i * mm;
-        double a = 0;
-        for (int k = 0; k < mm; ++k) a += A[(size_t)(mm + i) * pos + k] * Ainv[(size_t)k * mm + j];
-        Tm[e] = a;
-    }
-    __syncthreads();
+    // ---- 3./4. Schur complement A' = Arr - Arm Amm^+ Amr, b' = br - Arm Amm^+ bm ----
+    // The reference forms Amm^+ = V diag(lambda > 1e-8 ? 1/lambda : 0) V^T (marginalization_factor.cpp:273-287).
+    // Amm is an arrow matrix [[P (pose0 | speed-bias0, <= 15), C], [C^T, D]] with D diagonal (one entry per
+    // dropped landmark; landmarks never couple to each other).  If Amm - 1e-8 I is positive definite, every
+    // eigenvalue exceeds the threshold, the pseudo-inverse IS the inverse, and the Schur complement is formed
+    // exactly by block elimination (landmarks, then the dense head).  Otherwise fall back to the explicit
+    // eigen-decomposition (parallel Jacobi), as the reference does.
+    double *big = reinterpret_cast<double *>(smem_raw + ((sizeof(MargShared) + 15) & ~(size_t)15));
     double *Ar = mg.Ar, *V2 = mg.V2, *br = mg.br;
-    for (int e = tid; e < nn * nn; e += BA_THREADS) {
-        int i = e / nn, j = e - i * nn;
-        double a = A[(size_t)(mm + i) * pos + mm + j];
-        for (int k = 0; k < mm; ++k) a -= Tm[(size_t)i * mm + k] * A[(size_t)k * pos + mm + j];
-        Ar[e] = a;
-    }
-    for (int i = tid; i < nn; i += BA_THREADS) {
-        double bb = bv[mm + i];
-        for (int k = 0; k < mm; ++k) bb -= Tm[(size_t)i * mm + k] * bv[k];
-        br[i] = bb;
-    }
+    double *Tm = mg.T, *V = mg.V, *Ainv = mg.Ainv;
+    const int nh = sh.first_kept > 0 ? (mm - 0) : 0;       // placeholder, head size computed below
+    (void)nh;
+    // head = dropped non-landmark columns [0, lm0), landmarks = [lm0, mm)
+    int lm0 = 0;
+    for (int i = 0; i < sh.first_kept; ++i) if (sh.present[i]) lm0 += sh.lsize[i];
+    const int nl0 = mm - lm0;
+    const double eps = 1e-8;
+    // PD test of Amm - eps I
+    if (tid == 0) sh.flag = 0;
     __syncthreads();
-    jacobi_eig(Ar, V2, nn, sh);
+    for (int l = tid; l < nl0; l += BA_THREADS) if (!(A[(size_t)(lm0 + l) * pos + lm0 + l] - eps > 0.0)) sh.flag = 1;
+    __syncthreads();
+    double *Hs = big;                    // head system (lm0 x lm0), then its inverse
+    if (!sh.flag && lm0 > 0) {
+        for (int e = tid; e < lm0 * lm0; e += BA_THREADS) {
+            int i = e / lm0, j = e - i * lm0;
+            double a = 0.5 * (A[(size_t)i * pos + j] + A[(size_t)j * pos + i]) - (i == j ? eps : 0.0);
+            for (int l = 0; l < nl0; ++l) a -= A[(size_t)i * pos + lm0 + l] * A[(size_t)j * pos + lm0 + l] / (A[(size_t)(lm0 + l) * pos + lm0 + l] - eps);
+            Hs[e] = a;
+        }
+        __syncthreads();
+        if (tid == 0) {        // tiny Cholesky (<= 15x15) as the PD test
+            for (int j = 0; j < lm0 && !sh.flag; ++j) {
+                double d = Hs[j * lm0 + j];
+                for (int k = 0; k < j; ++k) d -= Hs[j * lm0 + k] * Hs[j * lm0 + k];
+                if (!(d > 0.0)) { sh.flag = 1; break; }
+                d = sqrt(d); Hs[j * lm0 + j] = d;
+                for (int i = j + 1; i < lm0; ++i) { double t = Hs[i * lm0 + j]; for (int k = 0; k < j; ++k) t -= Hs[i * lm0 + k] * Hs[j * lm0 + k]; Hs[i * lm0 + j] = t / d; }
+            }
+        }
+        __syncthreads();
+    }
+    const bool fast = (sh.flag == 0);
+    if (fast) {
+        // (i) eliminate the landmarks from the [head | kept] system: X = head (lm0) + kept (nn) columns
+        const int nx = lm0 + nn;
+        double *Xs = mg.V;                       // nx*nx scratch in global (L2)
+        double *bx = mg.T;                       // nx
+        auto xcol = [&](int a) { return a < lm0 ? a : mm + (a - lm0); };
+        for (int e = tid; e < nx * nx; e += BA_THREADS) {
+            int i = e / nx, j = e - i * nx;
+            const int ci = xcol(i), cj = xcol(j);
+            double a = 0.5 * (A[(size_t)ci * pos + cj] + A[(size_t)cj * pos + ci]);
+            for (int l = 0; l < nl0; ++l) a -= A[(size_t)ci * pos + lm0 + l] * A[(size_t)cj * pos + lm0 + l] / A[(size_t)(lm0 + l) * pos + lm0 + l];
+            Xs[e] = a;
+        }
+        for (int i = tid; i < nx; i += BA_THREADS) {
+            const int ci = xcol(i);
+            double a = bv[ci];
+            for (int l = 0; l < nl0; ++l) a -= A[(size_t)ci * pos + lm0 + l] * bv[lm0 + l] / A[(size_t)(lm0 + l) * pos + lm0 + l];
+            bx[i] = a;
+        }
+        __syncthreads();
+        // (ii) invert the head block (Cholesky, one thread per column of the inverse) and eliminate it
+        if (lm0 > 0) {
+            if (tid == 0) {
+                for (int e = 0; e < lm0 * lm0; ++e) Hs[e] = Xs[(e / lm0) * nx + (e % lm0)];
+                for (int j = 0; j < lm0; ++j) {
+                    double d = Hs[j * lm0 + j];
+                    for (int k = 0; k < j; ++k) d -= Hs[j * lm0 + k] * Hs[j * lm0 + k];
+                    d = sqrt(d); Hs[j * lm0 + j] = d;
+                    for (int i = j + 1; i < lm0; ++i) { double t = Hs[i * lm0 + j]; for (int k = 0; k < j; ++k) t -= Hs[i * lm0 + k] * Hs[j * lm0 + k]; Hs[i * lm0 + j] = t / d; }
+                }
+            }
+            __syncthreads();
+            double *Hi = Hs + 256;               // inverse (lm0 x lm0)
+            if (tid < lm0) {
+                double x[16];
+                for (int i = 0; i < lm0; ++i) x[i] = (i == tid) ? 1.0 : 0.0;
+                for (int i = 0; i < lm0; ++i) { double t = x[i]; for (int k = 0; k < i; ++k) t -= Hs[i * lm0 + k] * x[k]; x[i] = t / Hs[i * lm0 + i]; }
+                for (int i = lm0 - 1; i >= 0; --i) { double t = x[i]; for (int k = i + 1; k < lm0; ++k) t -= Hs[k * lm0 + i] * x[k]; x[i] = t / Hs[i * lm0 + i]; }
+                for (int i = 0; i < lm0; ++i) Hi[i * lm0 + tid] = x[i];
+            }
+            __syncthreads();
+            // T15 = X_r,head * Hi  (nn x lm0) in smem after Hi
+            double *T15 = Hi + 256;
+            for (int e = tid; e < nn * lm0; e += BA_THREADS) {
+                int i = e / lm0, j = e - i * lm0;
+                double a = 0;
+                for (int k = 0; k < lm0; ++k) a += Xs[(size_t)(lm0 + i) * nx + k] * Hi[k * lm0 + j];
+                T15[e] = a;
+            }
+            __syncthreads();
+            for (int e = tid; e < nn * nn; e += BA_THREADS) {
+                int i = e / nn, j = e - i * nn;
+                double a = Xs[(size_t)(lm0 + i) * nx + lm0 + j];
+                for (int k = 0; k < lm0; ++k) a -= T15[i * lm0 + k] * Xs[(size_t)k * nx + lm0 + j];
+                Ar[e] = a;
+            }
+            for (int i = tid; i < nn; i += BA_THREADS) {
+                double a = bx[lm0 + i];
+                for (int k = 0; k < lm0; ++k) a -= T15[i * lm0 + k] * bx[k];
+                br[i] = a;
+            }
+        } else {
+            for (int e = tid; e < nn * nn; e += BA_THREADS) Ar[e] = Xs[e];
+            for (int i = tid; i < nn; i += BA_THREADS) br[i] = bx[i];
+        }
+        __syncthreads();
+    } else {
+        // explicit pseudo-inverse through the eigen-decomposition of Amm (global-memory Jacobi)
+        double *Amm = Ainv;
+        for (int e = tid; e < mm * mm; e += BA_THREADS) { int i = e / mm, j = e - i * mm; Amm[e] = 0.5 * (A[(size_t)i * pos + j] + A[(size_t)j * pos + i]); }
+        __syncthreads();
+        jacobi_eig(Amm, V, mm, sh);
+        for (int k = tid; k < mm; k += BA_THREADS) { double w = Amm[(size_t)k * mm + k]; sh.cs[k] = (w > eps) ? 1.0 / w : 0.0; }
+        __syncthreads();
+        for (int e = tid; e < mm * mm; e += BA_THREADS) {
+            int i = e / mm, j = e - i * mm;
+            double a = 0;
+            for (int k = 0; k < mm; ++k) a += V[(size_t)i * mm + k] * sh.cs[k] * V[(size_t)j * mm + k];
+            Ainv[e] = a;
+        }
+        __syncthreads();
+        for (int e = tid; e < nn * mm; e += BA_THREADS) {
+            int i = e / mm, j = e - i * mm;
+            double a = 0;
+            for (int k = 0; k < mm; ++k) a += A[(size_t)(mm + i) * pos + k] * Ainv[(size_t)k * mm + j];
+            Tm[e] = a;
+        }
+        __syncthreads();
+        for (int e = tid; e < nn * nn; e += BA_THREADS) {
+            int i = e / nn, j = e - i * nn;
+            double a = A[(size_t)(mm + i) * pos + mm + j];
+            for (int k = 0; k < mm; ++k) a -= Tm[(size_t)i * mm + k] * A[(size_t)k * pos + mm + j];
+            Ar[e] = a;
+        }
+        for (int i = tid; i < nn; i += BA_THREADS) {
+            double bb = bv[mm + i];
+            for (int k = 0; k < mm; ++k) bb -= Tm[(size_t)i * mm + k] * bv[k];
+            br[i] = bb;
+        }
+        __syncthreads();
+    }
+    // second decomposition: A' = V2 diag(S) V2^T (in shared memory when it fits)
+    if (nn <= MARG_SMEM_N) {
+        double *As = big, *Vs = big + nn * nn;
+        for (int e = tid; e < nn * nn; e += BA_THREADS) As[e] = Ar[e];
+        __syncthreads();
+        jacobi_eig_smem(As, Vs, nn, sh);
+        for (int e = tid; e < nn * nn; e += BA_THREADS) { V2[e] = Vs[e]; if (e / nn == e % nn) Ar[e] = As[e]; }
+        __syncthreads();
+    } else {
+        jacobi_eig(Ar, V2, nn, sh);
+    }
     // ---- 5. linearized_jacobians / residuals + kept blocks into the next prior store ----
     for (int k = tid; k < nn; k += BA_THREADS) {
         const double w = Ar[(size_t)k * nn + k];
@@ -348,17 +532,18 @@ k_ba_marg(const BaMeta *metas, const BaProbDev *probs, BaOutDev *outs, const BaM
     }
 }
 
-size_t ba_marg_smem_bytes() { return sizeof(MargShared); }
+static size_t marg_smem() { return ((sizeof(MargShared) + 15) & ~(size_t)15) + sizeof(double) * 2 * MARG_SMEM_N * MARG_SMEM_N; }
+size_t ba_marg_smem_bytes() { return marg_smem(); }
 
 int ba_marg_launch(const BaMeta *d_meta, const BaProbDev *d_prob, BaOutDev *d_out, BaMargDev *d_marg, int n, LaunchCtx &lc)
 {
     static bool configured = false;
     if (!configured) {
-        if (cudaFuncSetAttribute(k_ba_marg, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MargShared)) != cudaSuccess) return -1;
+        if (cudaFuncSetAttribute(k_ba_marg, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)marg_smem()) != cudaSuccess) return -1;
         configured = true;
     }
     lc.begin(K_BA_MARG);
-    k_ba_marg<<<n, BA_THREADS, sizeof(MargShared), lc.st>>>(d_meta, d_prob, d_out, d_marg);
+    k_ba_marg<<<n, BA_THREADS, marg_smem(), lc.st>>>(d_meta, d_prob, d_out, d_marg);
     lc.end();
     return 0;
 }

@@ -112,6 +112,13 @@ __device__ __forceinline__ double warp_sum_d(double v)
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
 }
+// sum over the 16-lane half of a warp the calling lane belongs to
+__device__ __forceinline__ double half_sum_d(double v)
+{
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
 // deterministic block sum (BA_THREADS threads), result broadcast to all threads
 static __device__ double block_sum(double v, double *s_red)
 {

@@ -93,4 +93,5 @@ int ransac_launch(const FrontCfg &c, const SeqCall *d_calls, int ncalls, const F
 int ba_create(vrf_handle *h);
 void ba_destroy(vrf_handle *h);
 int ba_reset_sequence(vrf_handle *h, int seq);
+long ba_debug_prof(vrf_handle *h, int slot, void *dst, size_t bytes);
 }  // namespace vrf
