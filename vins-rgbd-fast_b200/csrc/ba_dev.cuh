@@ -17,6 +17,7 @@ namespace vrf {
 struct BaMeta {
     int M, nobs, nimu, np, nframes, use_imu, max_iter, marg_flag, has_prior, frame_count;
     int imu_j[BA_NF];
+    int debug;            // VRF_BA_DEBUG env: bit0 = per-iteration trace (printf), bit1 = column Cholesky
     double g_norm;
 };
 

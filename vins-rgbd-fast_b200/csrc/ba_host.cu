@@ -3,6 +3,7 @@
 // estimator.cpp:936-981 + problem assembly :1166-1302) into device buffers, launches the
 // solve + marginalization kernels, and unpacks results.  Thin host code; no arithmetic of
 // the hot path happens here.
+#include <cstdlib>
 #include <new>
 #include <vector>
 
@@ -140,6 +141,7 @@ static int pack_problem(vrf_handle *h, int slot, int seq, const VrfBaProblem *pb
     mt.max_iter = pb->max_iterations > 0 ? pb->max_iterations : h->cfg.num_iterations;
     mt.marg_flag = pb->marginalization_flag;
     mt.g_norm = h->cfg.g_norm;
+    { const char *e = getenv("VRF_BA_DEBUG"); mt.debug = e ? atoi(e) : 0; }
     mt.nimu = 0;
     if (pb->use_imu)
         for (int j = 1; j <= pb->frame_count; ++j) {

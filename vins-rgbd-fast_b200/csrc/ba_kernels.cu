@@ -67,9 +67,10 @@ __device__ double ba_evaluate(const BaMeta &m, const BaProbDev &p, BaShared &sh,
     double cost = 0.0;
     // ---- projection factors: two landmarks per warp (16 lanes each), one lane per factor (track length <= 11) ----
     const int half = lane >> 4, hl = lane & 15;
-    for (int lp = warp; 2 * lp < m.M; lp += nwarp) {
-        const int l = 2 * lp + half;
-        const bool lv = l < m.M;
+    const bool single = (m.debug & 4) != 0;          // diagnostic: one landmark per warp
+    for (int lp = warp; (single ? lp : 2 * lp) < m.M; lp += nwarp) {
+        const int l = single ? lp : 2 * lp + half;
+        const bool lv = single ? (half == 0) : (l < m.M);
         const int o0 = lv ? p.obs_ptr[l] : 0, nf = lv ? p.obs_ptr[l + 1] - o0 - 1 : 0;
         const int i = lv ? p.start[l] : 0;
         const bool lc = lv ? (p.lm_const[l] != 0) : true;
@@ -418,6 +419,7 @@ k_ba_solve(const BaMeta *metas, const BaProbDev *probs, BaOutDev *outs)
                     }
                     for (int q = 0; q < ne; ++q) sh.H[ea[q] * (ea[q] + 1) / 2 + eb[q]] -= acc[q];
                 }
+                __syncthreads();      // the diagonal entries are touched again just below by other threads
                 for (int c = tid; c < BA_NC; c += BA_THREADS) sh.H[pk(c, c)] += mu * sh.diag[c] * sh.diag[c];
                 __syncthreads();
                 TPROF(3);
@@ -426,6 +428,26 @@ k_ba_solve(const BaMeta *metas, const BaProbDev *probs, BaOutDev *outs)
                 // Per panel: (1) warp 0 factors the 8x8 diagonal block, (2) one thread per row solves the
                 // panel's triangular system, (3) rank-8 update of the trailing matrix  => 3 barriers / panel.
                 bool bad = sh.flag[0] != 0;
+                if (m.debug & 2) {
+                    for (int j = 0; j < BA_NC && !bad; ++j) {
+                        if (tid == 0) { double d = sh.H[pk(j, j)]; if (!(d > 0.0)) sh.flag[0] = 1; else sh.H[pk(j, j)] = sqrt(d); }
+                        __syncthreads();
+                        if (sh.flag[0]) { bad = true; break; }
+                        const double ljj = sh.H[pk(j, j)];
+                        for (int i = j + 1 + tid; i <= BA_NC; i += BA_THREADS) {
+                            if (i < BA_NC) { double v = sh.H[pk(i, j)] / ljj; sh.H[pk(i, j)] = v; sh.colv[i] = v; }
+                            else { double v = sh.y[j] / ljj; sh.y[j] = v; sh.colv[BA_NC] = v; }
+                        }
+                        __syncthreads();
+                        const int tx = tid & 31, ty = tid >> 5;
+                        for (int ii = j + 1 + ty; ii <= BA_NC; ii += BA_THREADS / 32) {
+                            const double li = sh.colv[ii];
+                            if (ii < BA_NC) { double *row = sh.H + ii * (ii + 1) / 2; for (int kk = j + 1 + tx; kk <= ii; kk += 32) row[kk] -= li * sh.colv[kk]; }
+                            else for (int kk = j + 1 + tx; kk < BA_NC; kk += 32) sh.y[kk] -= li * sh.colv[kk];
+                        }
+                        __syncthreads();
+                    }
+                } else
                 for (int j0 = 0; j0 < BA_NC && !bad; j0 += 8) {
                     const int nbp = min(8, BA_NC - j0);
                     if (tid == 0) {
@@ -619,6 +641,9 @@ k_ba_solve(const BaMeta *metas, const BaProbDev *probs, BaOutDev *outs)
                 const double cost_change = x_cost - cand_cost;
                 if (fabs(cost_change) <= 1e-6 * x_cost) { termination = 1; break; }
                 const double rho = cost_change / mcc;
+                if ((m.debug & 1) && tid == 0 && blockIdx.x == 0)
+                    printf("gpu it %d cost %.6f cand %.6f mcc %.6g rho %.4f radius %.3g |step| %.3g mu %.1e gradmax %.3g c1 %.4g c2 %.4g\n",
+                           iterations, x_cost, cand_cost, mcc, rho, radius, dogleg_norm, mu, gradient_max, c1, c2);
                 if (rho > 1e-3) {
                     for (int i = tid; i < BA_NF * 7; i += BA_THREADS) sh.pose[i] = sh.cpose[i];
                     for (int i = tid; i < BA_NF * 9; i += BA_THREADS) sh.sb[i] = sh.csb[i];
