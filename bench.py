@@ -379,7 +379,12 @@ def main():
         prof[kname] = (prof.get(kname, (0.0, 0))[0] + v[0], prof.get(kname, (0, 0))[1] + v[1])
     hnd.profile(False); hnd_ba.profile(False)
     try:
-        ba_phase = hnd_ba.debug_read("ba_prof", 0, np.int64, 8).tolist()
+        ba_all = [hnd_ba.debug_read("ba_prof", i, np.int64, 20) for i in range(min(NBA, 8))]
+        ba_phase = ba_all[0][:8].tolist()
+        if args.quick:
+            for i, v in enumerate(ba_all):
+                print("ba slot", i, "solve phases", v[:8].tolist(), "sum", int(v[:8].sum()), "kernel", int(v[15]),
+                      "| marg phases", v[8:15].tolist(), "| it/succ/term/status", v[16:20].tolist(), file=sys.stderr)
     except Exception:
         ba_phase = None
     tot_ms = sum(v[0] for v in prof.values()) or 1.0

@@ -60,6 +60,7 @@ struct BaOutDev {
     // states re-packed by vector2double after the gauge fix (marginalization linearises here)
     double mpose[BA_NF * 7], msb[BA_NF * 9], mex[7];
     int has_new_prior, pad;
+    long long prof2[8];  // k_ba_marg: 0 table+zero, 1 prior, 2 imu+proj, 3 pd test, 4 schur (fast or eig), 5 jacobi, 6 output, 7 total kernel cycles of k_ba_solve
     long long prof[8];   // clock64 per phase: 0 linearise, 1 scale+grad, 2 cauchy, 3 schur, 4 cholesky, 5 solve tail, 6 dogleg, 7 candidate cost
 };
 

@@ -292,11 +292,15 @@ static int download(vrf_handle *h, int n, const int32_t *seqs, VrfBaResult *res)
 long ba_debug_prof(vrf_handle *h, int slot, void *dst, size_t bytes)
 {
     BaState *b = h->ba;
-    if (!b || slot < 0 || slot >= h->n_seq || bytes < sizeof(long long) * 8) return VRF_ERR_ARG;
+    if (!b || slot < 0 || slot >= h->n_seq || bytes < sizeof(long long) * 20) return VRF_ERR_ARG;
     BaOutDev tmp;
     if (cudaMemcpy(&tmp, b->d_out + slot, sizeof(BaOutDev), cudaMemcpyDeviceToHost) != cudaSuccess) return VRF_ERR_CUDA;
-    memcpy(dst, tmp.prof, sizeof(long long) * 8);
-    return (long)(sizeof(long long) * 8);
+    long long o[20];
+    memcpy(o, tmp.prof, sizeof(long long) * 8);
+    memcpy(o + 8, tmp.prof2, sizeof(long long) * 8);
+    o[16] = tmp.iterations; o[17] = tmp.successful; o[18] = tmp.termination; o[19] = tmp.status;
+    memcpy(dst, o, sizeof(o));
+    return (long)sizeof(o);
 }
 
 }  // namespace vrf

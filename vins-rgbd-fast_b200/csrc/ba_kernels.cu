@@ -53,7 +53,9 @@ __device__ __forceinline__ bool col_active_dev(const BaMeta &m, int col)
 }
 
 // cost of all residual blocks at (pose, sb, lam); optionally the full linearisation into sh.H / sh.g / landmark arrays.
-__device__ double ba_evaluate(const BaMeta &m, const BaProbDev &p, BaShared &sh, const double *pose, const double *sb,
+// __noinline__: the solve loop calls this from five sites; inlining produced a 51k-instruction kernel (800 KB of SASS)
+// that thrashed the instruction cache (one resident CTA per SM, 16 warps in different code regions).
+__device__ __noinline__ double ba_evaluate(const BaMeta &m, const BaProbDev &p, BaShared &sh, const double *pose, const double *sb,
                               const double *lam, bool lin)
 {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = BA_THREADS / 32;
@@ -193,6 +195,25 @@ __device__ double ba_evaluate(const BaMeta &m, const BaProbDev &p, BaShared &sh,
     return block_sum(cost, sh.red);
 }
 
+// scale a fresh linearisation: H_s = D H D, g_s = D g, W_s, hll_s, gl_s (Jacobi scaling of the Jacobian columns)
+__device__ __noinline__ void ba_scale(const BaMeta &m, const BaProbDev &p, BaShared &sh)
+{
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = BA_THREADS / 32;
+    for (int a = tid; a < BA_NC; a += BA_THREADS) {          // one packed row per thread
+        double *row = sh.H + a * (a + 1) / 2;
+        const double sa = sh.jscale[a];
+        for (int b = 0; b <= a; ++b) row[b] *= sa * sh.jscale[b];
+    }
+    for (int c = tid; c < BA_NC; c += BA_THREADS) sh.g[c] *= sh.jscale[c];
+    for (int l = warp; l < m.M; l += nwarp) {
+        const double sl = p.jscale_l[l];
+        double *Wl = p.W + (size_t)l * 66;
+        for (int k = lane; k < 66; k += 32) Wl[k] *= sl * sh.jscale[k];
+        if (lane == 0) { p.hll[l] *= sl * sl; p.gl[l] *= sl; }
+    }
+    __syncthreads();
+}
+
 // (sum over camera + landmark entries of a_c*b_c) helper: camera part from smem arrays, landmark part from global
 __device__ double dot_full(const BaMeta &m, const double *ac, const double *bc, const double *al, const double *bl, double *s_red)
 {
@@ -212,6 +233,7 @@ k_ba_solve(const BaMeta *metas, const BaProbDev *probs, BaOutDev *outs)
     BaOutDev &out = outs[blockIdx.x];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = BA_THREADS / 32;
     const int M = m.M;
+    const long long t_kernel00 = clock64();
 
     for (int i = tid; i < BA_NF * 7; i += BA_THREADS) sh.pose[i] = p.pose0[i];
     for (int i = tid; i < BA_NF * 9; i += BA_THREADS) sh.sb[i] = p.sb0[i];
@@ -244,6 +266,7 @@ k_ba_solve(const BaMeta *metas, const BaProbDev *probs, BaOutDev *outs)
     __syncthreads();
     __threadfence_block();
 
+    const long long t_kernel0 = t_kernel00;
     long long tprof[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tmark = clock64();
 #define TPROF(k) do { long long t_ = clock64(); tprof[k] += t_ - tmark; tmark = t_; } while (0)
     double x_cost = ba_evaluate(m, p, sh, sh.pose, sh.sb, p.lam, true);
@@ -273,23 +296,7 @@ k_ba_solve(const BaMeta *metas, const BaProbDev *probs, BaOutDev *outs)
 
     while (true) {
         if (need_scale) {
-            // scale the fresh linearisation: H_s = D H D, g_s = D g (Jacobi scaling of the Jacobian columns)
-            for (int e = tid; e < BA_NC * (BA_NC + 1) / 2; e += BA_THREADS) {
-                // unpack e -> (a,b): a = floor((sqrt(8e+1)-1)/2)
-                int a = (int)((sqrt(8.0 * e + 1.0) - 1.0) * 0.5);
-                while (a * (a + 1) / 2 > e) --a;
-                while ((a + 1) * (a + 2) / 2 <= e) ++a;
-                int b = e - a * (a + 1) / 2;
-                sh.H[e] *= sh.jscale[a] * sh.jscale[b];
-            }
-            for (int c = tid; c < BA_NC; c += BA_THREADS) sh.g[c] *= sh.jscale[c];
-            for (int l = warp; l < M; l += nwarp) {
-                const double sl = p.jscale_l[l];
-                double *Wl = p.W + (size_t)l * 66;
-                for (int k = lane; k < 66; k += 32) Wl[k] *= sl * sh.jscale[k];
-                if (lane == 0) { p.hll[l] *= sl * sl; p.gl[l] *= sl; }
-            }
-            __syncthreads();
+            ba_scale(m, p, sh);
             // projected gradient max-norm (bounds): x - Plus(x, -g)
             {
                 double mx = 0;
@@ -428,44 +435,38 @@ k_ba_solve(const BaMeta *metas, const BaProbDev *probs, BaOutDev *outs)
                 // Per panel: (1) warp 0 factors the 8x8 diagonal block, (2) one thread per row solves the
                 // panel's triangular system, (3) rank-8 update of the trailing matrix  => 3 barriers / panel.
                 bool bad = sh.flag[0] != 0;
-                if (m.debug & 2) {
-                    for (int j = 0; j < BA_NC && !bad; ++j) {
-                        if (tid == 0) { double d = sh.H[pk(j, j)]; if (!(d > 0.0)) sh.flag[0] = 1; else sh.H[pk(j, j)] = sqrt(d); }
-                        __syncthreads();
-                        if (sh.flag[0]) { bad = true; break; }
-                        const double ljj = sh.H[pk(j, j)];
-                        for (int i = j + 1 + tid; i <= BA_NC; i += BA_THREADS) {
-                            if (i < BA_NC) { double v = sh.H[pk(i, j)] / ljj; sh.H[pk(i, j)] = v; sh.colv[i] = v; }
-                            else { double v = sh.y[j] / ljj; sh.y[j] = v; sh.colv[BA_NC] = v; }
-                        }
-                        __syncthreads();
-                        const int tx = tid & 31, ty = tid >> 5;
-                        for (int ii = j + 1 + ty; ii <= BA_NC; ii += BA_THREADS / 32) {
-                            const double li = sh.colv[ii];
-                            if (ii < BA_NC) { double *row = sh.H + ii * (ii + 1) / 2; for (int kk = j + 1 + tx; kk <= ii; kk += 32) row[kk] -= li * sh.colv[kk]; }
-                            else for (int kk = j + 1 + tx; kk < BA_NC; kk += 32) sh.y[kk] -= li * sh.colv[kk];
-                        }
-                        __syncthreads();
-                    }
-                } else
                 for (int j0 = 0; j0 < BA_NC && !bad; j0 += 8) {
                     const int nbp = min(8, BA_NC - j0);
-                    if (tid == 0) {
-                        for (int jj = 0; jj < nbp; ++jj) {
-                            const int j = j0 + jj;
-                            double *rj = sh.H + j * (j + 1) / 2;
-                            double dsum = rj[j];
-                            for (int k = j0; k < j; ++k) dsum -= rj[k] * rj[k];
-                            if (!(dsum > 0.0)) { sh.flag[0] = 1; break; }
-                            const double ljj = sqrt(dsum);
-                            rj[j] = ljj;
-                            for (int i2 = j + 1; i2 < j0 + nbp; ++i2) {
-                                double *ri = sh.H + i2 * (i2 + 1) / 2;
-                                double t = ri[j];
-                                for (int k = j0; k < j; ++k) t -= ri[k] * rj[k];
-                                ri[j] = t / ljj;
+                    if (warp == 0) {
+                        // (1) the 8x8 diagonal block lives in registers of warp 0 (lane r = row r), factorised with shuffles
+                        const int rr = lane;
+                        double a8[8];
+                        const int rrow = j0 + min(rr, nbp - 1);
+                        const double *rp = sh.H + rrow * (rrow + 1) / 2 + j0;
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) a8[c] = (rr < nbp && c <= rr && c < nbp) ? rp[c] : 0.0;
+                        bool okp = true;
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            if (j < nbp) {
+                                const double dj = __shfl_sync(0xffffffffu, a8[j], j);
+                                if (!(dj > 0.0)) okp = false;
+                                const double ljj = sqrt(dj);
+                                const double lrj = (rr == j) ? ljj : a8[j] / ljj;
+                                if (rr >= j) a8[j] = lrj;
+#pragma unroll
+                                for (int c = j + 1; c < 8; ++c) {
+                                    const double lcj = __shfl_sync(0xffffffffu, a8[j], c);
+                                    if (c < nbp && rr >= c) a8[c] -= lrj * lcj;
+                                }
                             }
                         }
+                        if (rr < nbp) {
+                            double *wp = sh.H + (j0 + rr) * (j0 + rr + 1) / 2 + j0;
+#pragma unroll
+                            for (int c = 0; c < 8; ++c) if (c <= rr && c < nbp) wp[c] = a8[c];
+                        }
+                        if (!okp && lane == 0) sh.flag[0] = 1;
                     }
                     __syncthreads();
                     if (sh.flag[0]) { bad = true; break; }
@@ -544,21 +545,7 @@ k_ba_solve(const BaMeta *metas, const BaProbDev *probs, BaOutDev *outs)
                 // failed: the in-place factorisation destroyed H => re-linearise and retry with a larger mu
                 mu *= mu_inc;
                 ba_evaluate(m, p, sh, sh.pose, sh.sb, p.lam, true);
-                for (int e = tid; e < BA_NC * (BA_NC + 1) / 2; e += BA_THREADS) {
-                    int a = (int)((sqrt(8.0 * e + 1.0) - 1.0) * 0.5);
-                    while (a * (a + 1) / 2 > e) --a;
-                    while ((a + 1) * (a + 2) / 2 <= e) ++a;
-                    int b = e - a * (a + 1) / 2;
-                    sh.H[e] *= sh.jscale[a] * sh.jscale[b];
-                }
-                for (int c = tid; c < BA_NC; c += BA_THREADS) sh.g[c] *= sh.jscale[c];
-                for (int l = warp; l < M; l += nwarp) {
-                    const double sl = p.jscale_l[l];
-                    double *Wl = p.W + (size_t)l * 66;
-                    for (int k = lane; k < 66; k += 32) Wl[k] *= sl * sh.jscale[k];
-                    if (lane == 0) { p.hll[l] *= sl * sl; p.gl[l] *= sl; }
-                }
-                __syncthreads();
+                ba_scale(m, p, sh);
             }
             TPROF(5);
             if (!solved) { status = VRF_SOFT_NOT_SPD; step_ok = false; }
@@ -746,6 +733,7 @@ k_ba_solve(const BaMeta *metas, const BaProbDev *probs, BaOutDev *outs)
         out.status = status; out.iterations = iterations; out.successful = successful; out.termination = termination;
         out.initial_cost = initial_cost; out.final_cost = x_cost;
         for (int k = 0; k < 8; ++k) out.prof[k] = tprof[k];
+        out.prof2[7] = clock64() - t_kernel0;
     }
 }
 

@@ -32,7 +32,7 @@ struct MargShared {
 };
 
 // parallel-order cyclic Jacobi: A (n x n, row-major, global) -> eigenvalues on the diagonal, V eigenvectors (columns)
-__device__ void jacobi_eig(double *A, double *V, int n, MargShared &sh)
+__device__ __noinline__ void jacobi_eig(double *A, double *V, int n, MargShared &sh)
 {
     const int tid = threadIdx.x;
     for (int e = tid; e < n * n; e += BA_THREADS) V[e] = (e / n == e % n) ? 1.0 : 0.0;
@@ -104,7 +104,7 @@ __device__ void jacobi_eig(double *A, double *V, int n, MargShared &sh)
 // only depends on the same 4 entries of A, so every (pair, pair) block is updated in place by
 // one thread and a round needs two barriers instead of three global-memory phases.
 #define MARG_SMEM_N 110
-__device__ void jacobi_eig_smem(double *A, double *V, int n, MargShared &sh)
+__device__ __noinline__ void jacobi_eig_smem(double *A, double *V, int n, MargShared &sh)
 {
     const int tid = threadIdx.x;
     for (int e = tid; e < n * n; e += BA_THREADS) V[e] = (e / n == e % n) ? 1.0 : 0.0;
@@ -121,7 +121,7 @@ __device__ void jacobi_eig_smem(double *A, double *V, int n, MargShared &sh)
         }
         off = block_sum(off, sh.red);
         dg = block_sum(dg, sh.red);
-        if (off <= 1e-30 * dg || off == 0.0) break;
+        if (off <= 1e-26 * dg || off == 0.0) break;     // relative off-diagonal norm 1e-13
         for (int r = 0; r < ne - 1; ++r) {
             for (int k = tid; k < npairs; k += BA_THREADS) {
                 int p, q;
@@ -199,6 +199,8 @@ k_ba_marg(const BaMeta *metas, const BaProbDev *probs, BaOutDev *outs, const BaM
     const double *lam = p.clam;
     const int flag = m.marg_flag;
 
+    long long tp[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tmark = clock64();
+#define MPROF(k) do { long long t_ = clock64(); tp[k] += t_ - tmark; tmark = t_; } while (0)
     // ---- 1. block table (thread 0) ----
     if (tid == 0) {
         int go = (m.frame_count == VRF_WINDOW_SIZE);
@@ -267,6 +269,7 @@ k_ba_marg(const BaMeta *metas, const BaProbDev *probs, BaOutDev *outs, const BaM
     if (tid == 0) d_q2R(ex + 3, sh.ric);
     __syncthreads();
 
+    MPROF(0);
     // ---- 2a. prior factor ----
     if (P) {
         const int np = P->n;
@@ -300,6 +303,7 @@ k_ba_marg(const BaMeta *metas, const BaProbDev *probs, BaOutDev *outs, const BaM
         }
         __syncthreads();
     }
+    MPROF(1);
     // ---- 2b. IMU factor between frames 0 and 1 ----
     const bool use_imu01 = (flag == VRF_MARGIN_OLD) && m.use_imu && p.imu[0].sum_dt < 10.0;
     if (use_imu01 && warp == 0) {
@@ -351,6 +355,7 @@ k_ba_marg(const BaMeta *metas, const BaProbDev *probs, BaOutDev *outs, const BaM
     }
     __syncthreads();
     __threadfence();
+    MPROF(2);
     // ---- 3./4. Schur complement A' = Arr - Arm Amm^+ Amr, b' = br - Arm Amm^+ bm ----
     // The reference forms Amm^+ = V diag(lambda > 1e-8 ? 1/lambda : 0) V^T (marginalization_factor.cpp:273-287).
     // Amm is an arrow matrix [[P (pose0 | speed-bias0, <= 15), C], [C^T, D]] with D diagonal (one entry per
@@ -394,6 +399,7 @@ k_ba_marg(const BaMeta *metas, const BaProbDev *probs, BaOutDev *outs, const BaM
         __syncthreads();
     }
     const bool fast = (sh.flag == 0);
+    MPROF(3);
     if (fast) {
         // (i) eliminate the landmarks from the [head | kept] system: X = head (lm0) + kept (nn) columns
         const int nx = lm0 + nn;
@@ -495,6 +501,7 @@ k_ba_marg(const BaMeta *metas, const BaProbDev *probs, BaOutDev *outs, const BaM
         }
         __syncthreads();
     }
+    MPROF(4);
     // second decomposition: A' = V2 diag(S) V2^T (in shared memory when it fits)
     if (nn <= MARG_SMEM_N) {
         double *As = big, *Vs = big + nn * nn;
@@ -506,6 +513,7 @@ k_ba_marg(const BaMeta *metas, const BaProbDev *probs, BaOutDev *outs, const BaM
     } else {
         jacobi_eig(Ar, V2, nn, sh);
     }
+    MPROF(5);
     // ---- 5. linearized_jacobians / residuals + kept blocks into the next prior store ----
     for (int k = tid; k < nn; k += BA_THREADS) {
         const double w = Ar[(size_t)k * nn + k];
@@ -529,6 +537,9 @@ k_ba_marg(const BaMeta *metas, const BaProbDev *probs, BaOutDev *outs, const BaM
         }
         Q->n = nn; Q->n_blocks = nk; Q->valid = 1;
         out.has_new_prior = 1;
+        MPROF(6);
+        for (int k = 0; k < 7; ++k) out.prof2[k] = tp[k];
+        out.prof2[3] = fast ? tp[3] : -tp[3];          // negative => slow (explicit eigen) path was taken
     }
 }
 
