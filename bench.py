@@ -143,6 +143,23 @@ def rel_rotation(base_R, idx, pidx):
     return base_R[pidx].T        # going backwards: inverse of cam(idx)->cam(pidx)
 
 
+def shard_sequences(seqs_per_gpu, rank, world):
+    """Global ids of the sequences owned by `rank` (weak scaling: every rank owns `seqs_per_gpu`
+    independent sequences; sequence g lives on GPU g // seqs_per_gpu; frames never cross GPUs)."""
+    return list(range(rank * seqs_per_gpu, (rank + 1) * seqs_per_gpu))
+
+
+def aggregate_timing(ms_local, frames_local, dist_mod, device=None):
+    """max over ranks of the timed interval, sum over ranks of the processed frames."""
+    import torch
+    t = torch.tensor([ms_local], dtype=torch.float64, device=device)
+    f = torch.tensor([float(frames_local)], dtype=torch.float64, device=device)
+    if dist_mod is not None and dist_mod.is_initialized() and dist_mod.get_world_size() > 1:
+        dist_mod.all_reduce(t, op=dist_mod.ReduceOp.MAX)
+        dist_mod.all_reduce(f, op=dist_mod.ReduceOp.SUM)
+    return float(t.item()), int(round(f.item()))
+
+
 def run_reference(args):
     """CPU arm: the cv2-backed oracle of the front end on all host cores
     (one independent sequence per worker process, cv2 threads = 1 each)."""
@@ -304,7 +321,7 @@ def main():
     hnd_ba.ba_upload(ba_seqs, ba_batch)
     hnd_ba.synchronize()
     ext_stream = torch.cuda.ExternalStream(hnd.stream(), device=dev)
-    seqs = list(range(S))
+    seqs = list(range(S))          # local slots; global ids: shard_sequences(S, rank, world)
     # sequence s plays base s % nb with phase offset (s // nb) so that publish frames are staggered
     phase = [(s // nb) + (s % PUB_EVERY) for s in seqs]
 
@@ -360,12 +377,9 @@ def main():
     clocks = sampler.stop()
     launches = hnd.launches + hnd_ba.launches - l0
     ms_total = max(ev0.elapsed_time(ev1), ev0.elapsed_time(ev1b))
-    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
     if world > 1:
         dist.barrier()
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total_max = float(t.item())
-    frames_total = S * args.steps * world
+    ms_total_max, frames_total = aggregate_timing(ms_total, S * args.steps, dist if world > 1 else None, dev)
     value = frames_total / (ms_total_max * 1e-3)
 
     # ---- profiled pass (per-kernel CUDA events) for the roofline ----

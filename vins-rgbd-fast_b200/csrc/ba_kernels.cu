@@ -34,6 +34,7 @@ namespace vrf {
 struct BaShared {
     double H[BA_NC * (BA_NC + 1) / 2];     // packed lower triangle: camera system, Schur-reduced & factorised in place
     double g[BA_NC], diag[BA_NC], gd[BA_NC], gn[BA_NC], jscale[BA_NC], tmp[BA_NC], y[BA_NC + 1], colv[BA_NC + 1];
+    double Lp[8][BA_NC + 5];                 // current Cholesky panel, transposed: Lp[c][row] (bank-conflict-free trailing update)
     double pose[BA_NF * 7], sb[BA_NF * 9], ex[7];
     double cpose[BA_NF * 7], csb[BA_NF * 9];          // candidate
     double R[BA_NF * 9], ric[9];
@@ -470,19 +471,23 @@ k_ba_solve(const BaMeta *metas, const BaProbDev *probs, BaOutDev *outs)
                     }
                     __syncthreads();
                     if (sh.flag[0]) { bad = true; break; }
-                    // (2) rows below the panel (incl. the rhs row): x * Ld^T = a
+                    // (2) rows below the panel (incl. the rhs row): x * Ld^T = a ; the solved panel is also
+                    //     staged transposed in Lp so that step (3) reads it without bank conflicts
                     for (int i2 = j0 + nbp + tid; i2 <= BA_NC; i2 += BA_THREADS) {
                         double *ri = (i2 < BA_NC) ? sh.H + i2 * (i2 + 1) / 2 : sh.y;
                         double x[8];
 #pragma unroll
                         for (int c = 0; c < 8; ++c) {
+                            x[c] = 0.0;
                             if (c < nbp) {
                                 const double *rc = sh.H + (j0 + c) * (j0 + c + 1) / 2;
                                 double t = ri[j0 + c];
-                                for (int k = 0; k < c; ++k) t -= x[k] * rc[j0 + k];
+#pragma unroll
+                                for (int k = 0; k < 8; ++k) if (k < c) t -= x[k] * rc[j0 + k];
                                 x[c] = t / rc[j0 + c];
                                 ri[j0 + c] = x[c];
                             }
+                            sh.Lp[c][i2] = x[c];
                         }
                     }
                     __syncthreads();
@@ -491,17 +496,15 @@ k_ba_solve(const BaMeta *metas, const BaProbDev *probs, BaOutDev *outs)
                         const int tx = tid & 31, ty = tid >> 5;
                         const int t0 = j0 + nbp;
                         for (int ii = t0 + ty; ii <= BA_NC; ii += BA_THREADS / 32) {
-                            const double *li = (ii < BA_NC) ? sh.H + ii * (ii + 1) / 2 + j0 : sh.y + j0;
                             double lv[8];
 #pragma unroll
-                            for (int c = 0; c < 8; ++c) lv[c] = (c < nbp) ? li[c] : 0.0;
+                            for (int c = 0; c < 8; ++c) lv[c] = sh.Lp[c][ii];
                             double *row = (ii < BA_NC) ? sh.H + ii * (ii + 1) / 2 : sh.y;
                             const int kend = (ii < BA_NC) ? ii : BA_NC - 1;
                             for (int kk = t0 + tx; kk <= kend; kk += 32) {
-                                const double *lk = sh.H + kk * (kk + 1) / 2 + j0;
                                 double acc = 0;
 #pragma unroll
-                                for (int c = 0; c < 8; ++c) if (c < nbp) acc += lv[c] * lk[c];
+                                for (int c = 0; c < 8; ++c) acc += lv[c] * sh.Lp[c][kk];
                                 row[kk] -= acc;
                             }
                         }

@@ -112,12 +112,22 @@ __device__ __noinline__ void jacobi_eig_smem(double *A, double *V, int n, MargSh
     if (n < 2) return;
     const int ne = (n + 1) & ~1;
     const int npairs = ne / 2;
+    // per-thread work items of a round (fixed for the whole call): (pair, pair) blocks and (pair, row) eigenvector items
+    short itA[24], itB[24];
+    int nit = 0;
+    {
+        const int nblk = npairs * npairs, nv = npairs * n;
+        for (int e = tid; e < nblk + nv && nit < 24; e += BA_THREADS) {
+            if (e < nblk) { itA[nit] = (short)(e / npairs); itB[nit] = (short)(e % npairs); }
+            else { const int f = e - nblk; itA[nit] = (short)(-(f / n) - 1); itB[nit] = (short)(f % n); }
+            ++nit;
+        }
+    }
     for (int sweep = 0; sweep < 40; ++sweep) {
         double off = 0, dg = 0;
-        for (int e = tid; e < n * n; e += BA_THREADS) {
-            int i = e / n, j = e - i * n;
-            double v = A[e];
-            if (i == j) dg += v * v; else if (j > i) off += v * v;
+        for (int i = tid; i < n; i += BA_THREADS) {
+            const double *row = A + i * n;
+            for (int j = 0; j < n; ++j) { const double v = row[j]; if (i == j) dg += v * v; else if (j > i) off += v * v; }
         }
         off = block_sum(off, sh.red);
         dg = block_sum(dg, sh.red);
@@ -141,10 +151,10 @@ __device__ __noinline__ void jacobi_eig_smem(double *A, double *V, int n, MargSh
                 sh.cs[2 * k] = c; sh.cs[2 * k + 1] = s_; sh.pq[2 * k] = p; sh.pq[2 * k + 1] = q;
             }
             __syncthreads();
-            const int nblk = npairs * npairs, nv = npairs * n;
-            for (int e = tid; e < nblk + nv; e += BA_THREADS) {
-                if (e < nblk) {
-                    const int k1 = e / npairs, k2 = e - k1 * npairs;
+            for (int it = 0; it < nit; ++it) {
+                const int ka = itA[it], kb = itB[it];
+                if (ka >= 0) {          // 2x2 block (pair ka) x (pair kb)
+                    const int k1 = ka, k2 = kb;
                     const int p1 = sh.pq[2 * k1], q1 = sh.pq[2 * k1 + 1], p2 = sh.pq[2 * k2], q2 = sh.pq[2 * k2 + 1];
                     const double c1 = sh.cs[2 * k1], s1 = sh.cs[2 * k1 + 1], c2 = sh.cs[2 * k2], s2 = sh.cs[2 * k2 + 1];
                     if (s1 == 0.0 && s2 == 0.0) continue;
@@ -158,9 +168,8 @@ __device__ __noinline__ void jacobi_eig_smem(double *A, double *V, int n, MargSh
                     if (q2 >= 0) A[p1 * n + q2] = c1 * t12 - s1 * t22;
                     if (q1 >= 0) A[q1 * n + p2] = s1 * t11 + c1 * t21;
                     if (q1 >= 0 && q2 >= 0) A[q1 * n + q2] = s1 * t12 + c1 * t22;
-                } else {
-                    const int f = e - nblk;
-                    const int k = f / n, i = f - k * n;
+                } else {                // eigenvector row kb's... item: pair (-ka-1), row kb
+                    const int k = -ka - 1, i = kb;
                     const int p_ = sh.pq[2 * k], q_ = sh.pq[2 * k + 1];
                     const double c = sh.cs[2 * k], s_ = sh.cs[2 * k + 1];
                     if (q_ < 0 || s_ == 0.0) continue;
@@ -330,26 +339,74 @@ k_ba_marg(const BaMeta *metas, const BaProbDev *probs, BaOutDev *outs, const BaM
     }
     __syncthreads();
     // ---- 2c. projection factors hosted at frame 0 (all four parameter blocks, Cauchy corrector) ----
-    if (flag == VRF_MARGIN_OLD) {
+    // Accumulated on chip: the pose/ex-pose part in a packed 72x72 block in shared memory
+    // (local index: pose f -> 6f, ex-pose -> 66), the landmark rows (coupling w[72], h, g) in HBM.
+    double *big0 = reinterpret_cast<double *>(smem_raw + ((sizeof(MargShared) + 15) & ~(size_t)15));
+    double *H72 = big0;                     // 72*73/2 = 2628
+    double *g72 = big0 + 2628;              // 72
+    double *Wm = mg.Ainv;                   // [nl0][72] landmark coupling rows (Ainv is only used by the slow path, later)
+    double *hm = mg.V2;                     // [nl0] h, then [nl0] g   (V2 is only needed by the second decomposition)
+    int lm0c = 0;
+    for (int i = 0; i < sh.first_kept; ++i) if (sh.present[i]) lm0c += sh.lsize[i];
+    const int nl0c = mm - lm0c;
+    if (flag == VRF_MARGIN_OLD && nl0c > 0) {
+        for (int e = tid; e < 2628 + 72; e += BA_THREADS) big0[e] = 0.0;
+        for (int e = tid; e < nl0c * 72; e += BA_THREADS) Wm[e] = 0.0;
+        __syncthreads();
+        auto pk72 = [](int a_, int b_) { return a_ >= b_ ? a_ * (a_ + 1) / 2 + b_ : b_ * (b_ + 1) / 2 + a_; };
         for (int l = warp; l < M; l += nwarp) {
             const int cl = mg.lmcol[l];
             if (cl < 0) continue;
+            const int li = cl - lm0c;       // ordinal among the dropped landmarks
             const int o0 = p.obs_ptr[l], nf = p.obs_ptr[l + 1] - o0 - 1;
-            if (lane >= nf) continue;
+            const bool act = lane < nf;
             const int j = 1 + lane;
-            double r[2], Ji[12], Jj[12], Jl[2], Je[12];
-            proj_eval(pose, sh.R, pose + 7 * j, sh.R + 9 * j, ex, sh.ric, lam[l], p.obs[2 * o0], p.obs[2 * o0 + 1],
-                      p.obs[2 * (o0 + j)], p.obs[2 * (o0 + j) + 1], true, false, r, Ji, Jj, Jl, Je);
-            int cols[19]; double J0r[19], J1r[19];
+            double r[2] = {0, 0}, Ji[12], Jj[12], Jl[2] = {0, 0}, Je[12];
+            if (act)
+                proj_eval(pose, sh.R, pose + 7 * j, sh.R + 9 * j, ex, sh.ric, lam[l], p.obs[2 * o0], p.obs[2 * o0 + 1],
+                          p.obs[2 * (o0 + j)], p.obs[2 * (o0 + j) + 1], true, false, r, Ji, Jj, Jl, Je);
+            const double hsum = warp_sum_d(Jl[0] * Jl[0] + Jl[1] * Jl[1]);
+            const double gsum = warp_sum_d(Jl[0] * r[0] + Jl[1] * r[1]);
+            if (lane == 0) { hm[li] = hsum; hm[nl0c + li] = gsum; }
+            if (!act) continue;
+            double *wr = Wm + (size_t)li * 72;
+            // 18 local columns of this factor: pose0 (0..5), pose j (6j..), ex (66..)
+            int lc[18]; double J0r[18], J1r[18];
+#pragma unroll
             for (int c = 0; c < 6; ++c) {
-                cols[c] = sh.col_pose[0] + c; J0r[c] = Ji[c]; J1r[c] = Ji[6 + c];
-                cols[6 + c] = sh.col_pose[j] + c; J0r[6 + c] = Jj[c]; J1r[6 + c] = Jj[6 + c];
-                cols[12 + c] = sh.col_ex + c; J0r[12 + c] = Je[c]; J1r[12 + c] = Je[6 + c];
+                lc[c] = c; J0r[c] = Ji[c]; J1r[c] = Ji[6 + c];
+                lc[6 + c] = 6 * j + c; J0r[6 + c] = Jj[c]; J1r[6 + c] = Jj[6 + c];
+                lc[12 + c] = 66 + c; J0r[12 + c] = Je[c]; J1r[12 + c] = Je[6 + c];
             }
-            cols[18] = cl; J0r[18] = Jl[0]; J1r[18] = Jl[1];
-            for (int a = 0; a < 19; ++a) {
-                atomicAdd(&bv[cols[a]], J0r[a] * r[0] + J1r[a] * r[1]);
-                for (int c = 0; c < 19; ++c) atomicAdd(&A[(size_t)cols[a] * pos + cols[c]], J0r[a] * J0r[c] + J1r[a] * J1r[c]);
+#pragma unroll
+            for (int a_ = 0; a_ < 18; ++a_) {
+                atomicAdd(&g72[lc[a_]], J0r[a_] * r[0] + J1r[a_] * r[1]);
+                const double wv = J0r[a_] * Jl[0] + J1r[a_] * Jl[1];
+                if (a_ >= 6 && a_ < 12) wr[lc[a_]] = wv; else atomicAdd(&wr[lc[a_]], wv);
+#pragma unroll
+                for (int c = 0; c <= a_; ++c) atomicAdd(&H72[pk72(lc[a_], lc[c])], J0r[a_] * J0r[c] + J1r[a_] * J1r[c]);
+            }
+        }
+        __syncthreads();
+        __threadfence();
+        // scatter into A / b
+        auto acol72 = [&](int q) { return q < 66 ? (sh.col_pose[q / 6] < 0 ? -1 : sh.col_pose[q / 6] + q % 6) : (sh.col_ex < 0 ? -1 : sh.col_ex + (q - 66)); };
+        for (int e = tid; e < 72 * 72; e += BA_THREADS) {
+            const int a_ = e / 72, c = e - a_ * 72;
+            const int ca = acol72(a_), cc = acol72(c);
+            if (ca < 0 || cc < 0) continue;
+            const double v = H72[pk72(a_, c)];
+            if (v != 0.0) A[(size_t)ca * pos + cc] += v;
+        }
+        for (int q = tid; q < 72; q += BA_THREADS) { const int ca = acol72(q); if (ca >= 0) bv[ca] += g72[q]; }
+        for (int e = tid; e < nl0c * 73; e += BA_THREADS) {
+            const int li = e / 73, q = e - li * 73;
+            const int cl = lm0c + li;
+            if (q == 72) { A[(size_t)cl * pos + cl] = hm[li]; bv[cl] = hm[nl0c + li]; }
+            else {
+                const int ca = acol72(q);
+                const double v = Wm[(size_t)li * 72 + q];
+                if (ca >= 0 && v != 0.0) { A[(size_t)cl * pos + ca] = v; A[(size_t)ca * pos + cl] = v; }
             }
         }
     }
@@ -406,18 +463,56 @@ k_ba_marg(const BaMeta *metas, const BaProbDev *probs, BaOutDev *outs, const BaM
         double *Xs = mg.V;                       // nx*nx scratch in global (L2)
         double *bx = mg.T;                       // nx
         auto xcol = [&](int a) { return a < lm0 ? a : mm + (a - lm0); };
+        // landmark elimination Xs = A_XX - sum_l w_l w_l^T / h_l with the coupling rows streamed through a
+        // shared-memory tile (64 landmarks x 72, pre-scaled by 1/sqrt(h)); the head inverse scratch (Hs) is
+        // rebuilt afterwards, so the tile may use the whole dynamic buffer behind it.
+        double *tile = big + 4096;
+        short *xm = reinterpret_cast<short *>(big + 4096 + 64 * 72);     // X index -> local 72-index (or -1)
+        for (int a_ = tid; a_ < nx; a_ += BA_THREADS) {
+            const int ca = xcol(a_);
+            int q = -1;
+            for (int f = 0; f < BA_NF; ++f) if (sh.col_pose[f] >= 0 && ca >= sh.col_pose[f] && ca < sh.col_pose[f] + 6) q = 6 * f + (ca - sh.col_pose[f]);
+            if (sh.col_ex >= 0 && ca >= sh.col_ex && ca < sh.col_ex + 6) q = 66 + (ca - sh.col_ex);
+            xm[a_] = (short)q;
+        }
         for (int e = tid; e < nx * nx; e += BA_THREADS) {
             int i = e / nx, j = e - i * nx;
             const int ci = xcol(i), cj = xcol(j);
-            double a = 0.5 * (A[(size_t)ci * pos + cj] + A[(size_t)cj * pos + ci]);
-            for (int l = 0; l < nl0; ++l) a -= A[(size_t)ci * pos + lm0 + l] * A[(size_t)cj * pos + lm0 + l] / A[(size_t)(lm0 + l) * pos + lm0 + l];
-            Xs[e] = a;
+            Xs[e] = 0.5 * (A[(size_t)ci * pos + cj] + A[(size_t)cj * pos + ci]);
         }
-        for (int i = tid; i < nx; i += BA_THREADS) {
-            const int ci = xcol(i);
-            double a = bv[ci];
-            for (int l = 0; l < nl0; ++l) a -= A[(size_t)ci * pos + lm0 + l] * bv[lm0 + l] / A[(size_t)(lm0 + l) * pos + lm0 + l];
-            bx[i] = a;
+        for (int i = tid; i < nx; i += BA_THREADS) bx[i] = bv[xcol(i)];
+        __syncthreads();
+        if (nl0 > 0) {
+            double accs[72];      // up to ceil(nx*nx/512) entries per thread (nx <= 186 -> 68)
+            int nacc = 0;
+            for (int e = tid; e < nx * nx; e += BA_THREADS) if (nacc < 72) accs[nacc++] = 0.0;
+            double bacc = 0.0;
+            for (int t0 = 0; t0 < nl0; t0 += 64) {
+                const int nt = min(64, nl0 - t0);
+                for (int q = tid; q < nt * 72; q += BA_THREADS) {
+                    const int li = t0 + q / 72;
+                    tile[q] = Wm[(size_t)li * 72 + (q % 72)] / sqrt(hm[li]);
+                }
+                __syncthreads();
+                int k = 0;
+                for (int e = tid; e < nx * nx && k < 72; e += BA_THREADS, ++k) {
+                    const int i = e / nx, j = e - i * nx;
+                    const int qi = xm[i], qj = xm[j];
+                    if (qi < 0 || qj < 0) continue;
+                    double s_ = 0;
+                    for (int l = 0; l < nt; ++l) s_ += tile[l * 72 + qi] * tile[l * 72 + qj];
+                    accs[k] += s_;
+                }
+                if (tid < nx && xm[tid] >= 0) {
+                    double s_ = 0;
+                    for (int l = 0; l < nt; ++l) s_ += tile[l * 72 + xm[tid]] * hm[nl0 + t0 + l] / sqrt(hm[t0 + l]);
+                    bacc += s_;
+                }
+                __syncthreads();
+            }
+            int k = 0;
+            for (int e = tid; e < nx * nx && k < 72; e += BA_THREADS, ++k) Xs[e] -= accs[k];
+            if (tid < nx) bx[tid] -= bacc;
         }
         __syncthreads();
         // (ii) invert the head block (Cholesky, one thread per column of the inverse) and eliminate it
