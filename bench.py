@@ -421,16 +421,46 @@ def main():
                 "alg_bytes_per_launch": alg_bytes, "launch_ms": per_launch_ms, "kernels": kern,
                 "ba_solve_phase_cycles": dict(zip(["linearise", "scale_grad", "cauchy", "schur", "cholesky", "solve_tail", "dogleg", "candidate"], ba_phase)) if ba_phase else None}
 
+    if roof is not None:
+        img = {}
+        if "k_ingest" in kern:
+            t_ms = kern["k_ingest"]["ms_per_step"]
+            b_ = S * (3 * W * H + W * H)
+            img["k_ingest"] = {"alg_bytes": b_, "ms": t_ms, "achieved_gbs": b_ / (t_ms * 1e-3) / 1e9, "frac": b_ / (t_ms * 1e-3) / 1e9 / peaks["hbm_gbs"]}
+        if "k_pyrdown" in kern:
+            t_ms = kern["k_pyrdown"]["ms_per_step"]
+            b_ = S * (W * H + W * H // 4 + W * H // 4 + W * H // 16)      # level 0 -> 1 -> 2: read + write
+            img["k_pyrdown"] = {"alg_bytes": b_, "ms": t_ms, "achieved_gbs": b_ / (t_ms * 1e-3) / 1e9, "frac": b_ / (t_ms * 1e-3) / 1e9 / peaks["hbm_gbs"]}
+        roof["image_scan_kernels"] = img
+        try:    # DRAM traffic of the dominant kernel from the committed ncu capture (profiles/), per launch
+            tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+            if roof["kernel"] in tj:
+                roof["traffic"] = tj[roof["kernel"]]["dram_bytes_per_launch"]
+                roof["traffic_note"] = tj[roof["kernel"]].get("note")
+        except Exception:
+            pass
+
     # ---- e2e arm: host buffers through the C ABI (H2D + kernels + D2H per step) ----
     e2e_steps = 0 if args.quick else max(3, min(args.steps, 20))
     hnd2 = binding.Handle(cfg, S, local_rank)
 
+    # everything the harness allocates is created once; the timed loop only moves data and calls the C ABI
+    seq_np = np.asarray(seqs, np.int32)
+    ba_seq_np = np.asarray(ba_seqs, np.int32)
+    tr_outs, tr_res = hnd2.make_track_batch(S)
+    ba_probs_c, ba_res_c, ba_sols = hnd2.make_ba_batch(ba_batch)
+    import ctypes as C_
+    host_ptr = [[h_rgb[b_][f_].data_ptr() for f_ in range(T_FRAMES)] for b_ in range(nb)]
+    ptr_arr = (C_.c_void_p * S)()
+
     def run_host_step(k):
         idxs, Rs, pubs, times = plans[k]
-        imgs = [h_rgb[s % nb][idxs[s]].numpy() for s in seqs]
-        outs_ = hnd2.read_image_batch(seqs, imgs, times, Rs, pubs, debug=False)
-        hnd2.ba_solve_batch(ba_seqs, ba_batch)      # host problems in, optimised states + prior out
-        return outs_
+        for s_ in seqs:
+            ptr_arr[s_] = host_ptr[s_ % nb][idxs[s_]]
+        hnd2.read_image_batch_into(seq_np, ptr_arr, binding.FMT_RGB8, np.asarray(times, np.float64),
+                                   np.ascontiguousarray(Rs.reshape(S, 9)), np.asarray(pubs, np.int32), tr_outs)
+        hnd2.ba_solve_batch_into(ba_seq_np, ba_probs_c, ba_res_c)      # host problems in, optimised states + prior out
+        return tr_outs
 
     for k in range(3 if e2e_steps else 0):
         run_host_step(k)
@@ -441,7 +471,7 @@ def main():
     d2h = 0
     for k in range(3, 3 + e2e_steps):
         outs = run_host_step(k)
-        d2h = sum(o.n for o in outs) * 32 + S * 32 + NBA * (11 * (7 + 9 + 3 + 9 + 9) * 8 + 8 * BA_LANDMARKS + 76 * 77 * 8)
+        d2h = sum(outs[i_].n for i_ in range(S)) * 32 + S * 32 + NBA * (11 * (7 + 9 + 3 + 9 + 9) * 8 + 8 * BA_LANDMARKS + 76 * 77 * 8)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)

@@ -452,9 +452,12 @@ k_ba_solve(const BaMeta *metas, const BaProbDev *probs, BaOutDev *outs)
                             if (j < nbp) {
                                 const double dj = __shfl_sync(0xffffffffu, a8[j], j);
                                 if (!(dj > 0.0)) okp = false;
-                                const double ljj = sqrt(dj);
-                                const double lrj = (rr == j) ? ljj : a8[j] / ljj;
+                                // FP64 sqrt/div have ~500-cycle latencies on this part: one rsqrt per pivot instead
+                                const double rinv = rsqrt(dj);
+                                const double ljj = dj * rinv;
+                                const double lrj = (rr == j) ? ljj : a8[j] * rinv;
                                 if (rr >= j) a8[j] = lrj;
+                                if (lane == 0) sh.colv[j] = rinv;            // 1 / L[j0+j, j0+j]
 #pragma unroll
                                 for (int c = j + 1; c < 8; ++c) {
                                     const double lcj = __shfl_sync(0xffffffffu, a8[j], c);
@@ -484,7 +487,7 @@ k_ba_solve(const BaMeta *metas, const BaProbDev *probs, BaOutDev *outs)
                                 double t = ri[j0 + c];
 #pragma unroll
                                 for (int k = 0; k < 8; ++k) if (k < c) t -= x[k] * rc[j0 + k];
-                                x[c] = t / rc[j0 + c];
+                                x[c] = t * sh.colv[c];
                                 ri[j0 + c] = x[c];
                             }
                             sh.Lp[c][i2] = x[c];

@@ -142,10 +142,12 @@ __device__ __noinline__ void jacobi_eig_smem(double *A, double *V, int n, MargSh
                 if (q < n) {
                     double apq = A[p * n + q];
                     if (apq != 0.0) {
+                        // FP64 div/sqrt latencies dominate this (sequential) phase: 2 divisions + 2 rsqrt
                         double app = A[p * n + p], aqq = A[q * n + q];
                         double tau = (aqq - app) / (2.0 * apq);
-                        double t = (tau >= 0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
-                        c = 1.0 / sqrt(1.0 + t * t); s_ = t * c;
+                        double w1 = 1.0 + tau * tau;
+                        double t = (tau >= 0 ? 1.0 : -1.0) / (fabs(tau) + w1 * rsqrt(w1));
+                        c = rsqrt(1.0 + t * t); s_ = t * c;
                     }
                 } else { q = -1; }
                 sh.cs[2 * k] = c; sh.cs[2 * k + 1] = s_; sh.pq[2 * k] = p; sh.pq[2 * k + 1] = q;

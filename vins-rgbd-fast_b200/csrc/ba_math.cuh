@@ -146,7 +146,8 @@ __device__ __forceinline__ double proj_eval(const double *Pi, const double *Ri, 
                                             double *Jj, double *Jl, double *Jex = nullptr)
 {
     const double sqrt_info = 460.0 / 1.5;
-    double pci[3] = {xi / lam, yi / lam, 1.0 / lam};
+    const double ilam = 1.0 / lam;
+    double pci[3] = {xi * ilam, yi * ilam, ilam};
     double t[3], pii[3], pw[3], d[3], pij[3], e[3], pcj[3];
     d_mv(ric, pci, t);
     pii[0] = t[0] + tic[0]; pii[1] = t[1] + tic[1]; pii[2] = t[2] + tic[2];
@@ -157,15 +158,16 @@ __device__ __forceinline__ double proj_eval(const double *Pi, const double *Ri, 
     e[0] = pij[0] - tic[0]; e[1] = pij[1] - tic[1]; e[2] = pij[2] - tic[2];
     d_mtv(ric, e, pcj);
     const double dep = pcj[2];
-    r[0] = sqrt_info * (pcj[0] / dep - xj);
-    r[1] = sqrt_info * (pcj[1] / dep - yj);
+    const double idep = 1.0 / dep;
+    r[0] = sqrt_info * (pcj[0] * idep - xj);
+    r[1] = sqrt_info * (pcj[1] * idep - yj);
     const double s = r[0] * r[0] + r[1] * r[1];
     // CauchyLoss(1): rho' = 1/(1+s), rho'' < 0 => Corrector scales residual and Jacobian by sqrt(rho')
     const double sum = 1.0 + s, inv = 1.0 / sum;
     const double rho0 = log(sum);
     const double sr = sqrt(inv > 2.2250738585072014e-308 ? inv : 2.2250738585072014e-308);
     if (want_jac) {
-        double red[6] = {sqrt_info / dep, 0, -sqrt_info * pcj[0] / (dep * dep), 0, sqrt_info / dep, -sqrt_info * pcj[1] / (dep * dep)};
+        double red[6] = {sqrt_info * idep, 0, -sqrt_info * pcj[0] * idep * idep, 0, sqrt_info * idep, -sqrt_info * pcj[1] * idep * idep};
         double A[9], B[9], C[9], S[9], Mx[9];
         // A = ric^T Rj^T
         double RjT[9] = {Rj[0], Rj[3], Rj[6], Rj[1], Rj[4], Rj[7], Rj[2], Rj[5], Rj[8]};
@@ -192,7 +194,7 @@ __device__ __forceinline__ double proj_eval(const double *Pi, const double *Ri, 
             double tr[9], v[3], pts_i[3] = {xi, yi, 1.0};
             d_mm(B, ric, tr);
             d_mv(tr, pts_i, v);
-            const double k = -1.0 / (lam * lam);
+            const double k = -ilam * ilam;
             Jl[0] = sr * (red[0] * v[0] + red[1] * v[1] + red[2] * v[2]) * k;
             Jl[1] = sr * (red[3] * v[0] + red[4] * v[1] + red[5] * v[2]) * k;
         } else { Jl[0] = 0; Jl[1] = 0; }

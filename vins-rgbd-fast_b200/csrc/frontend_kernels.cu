@@ -151,7 +151,7 @@ k_pyrdown(FrontCfg c, const SeqCall *calls, FrontDev d, int level)
 // ---------------------------------------------------------------------------
 #define LK_WPB 8
 #define LK_NPX 14   // ceil(441/32)
-#define LK_R1_BYTES 896     // region 1: 24x24 u8 patch of I, later 441(+7) int16 "diff"
+#define LK_R1_BYTES 3584    // region 1: 24x24 u8 patch of I, later 441(+7) int2 products (diff*Ix, diff*Iy)
 #define LK_R2_BYTES 1936    // region 2: 22x22 short2 Scharr, later 441(+7) short2 (Ix,Iy) of the window
 
 // OpenCV's float accumulation order (lkpyramid.cpp SSE path; pinned bit-exactly against
@@ -179,7 +179,9 @@ k_lk(FrontCfg c, const SeqCall *calls, int ncalls, FrontDev d)
     __shared__ __align__(16) unsigned char s_r2[LK_WPB][LK_R2_BYTES];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     uint8_t *s_I = s_r1[wib];
-    short *s_diff = reinterpret_cast<short *>(s_r1[wib]);
+    int2 *s_prod = reinterpret_cast<int2 *>(s_r1[wib]);
+    const int *s_prodi = reinterpret_cast<const int *>(s_r1[wib]);
+    const unsigned *s_dIw = reinterpret_cast<const unsigned *>(s_r2[wib]);   // packed (Ix | Iy<<16) per window pixel
     short2 *s_D = reinterpret_cast<short2 *>(s_r2[wib]);
     const short *s_dI = reinterpret_cast<const short *>(s_r2[wib]);   // interleaved (Ix, Iy) per window pixel
     const int total = d.work_prefix[ncalls];
@@ -358,9 +360,11 @@ k_lk(FrontCfg c, const SeqCall *calls, int ncalls, FrontDev d)
                             const uint8_t *q = Jb + wy * pitch + wx;
                             int jv = ((int)__ldg(q) * w00 + (int)__ldg(q + 1) * w01 + (int)__ldg(q + pitch) * w10 +
                                       (int)__ldg(q + pitch + 1) * w11 + (1 << 8)) >> 9;
-                            s_diff[p] = (short)(jv - Iw[k]);
+                            const int diff = jv - Iw[k];
+                            const unsigned dw = s_dIw[p];
+                            s_prod[p] = make_int2(diff * (int)(short)(dw & 0xFFFFu), diff * ((int)dw >> 16));
                         } else if (p < 448)
-                            s_diff[p] = 0;
+                            s_prod[p] = make_int2(0, 0);
                     }
                 } else {
 #pragma unroll
@@ -373,9 +377,11 @@ k_lk(FrontCfg c, const SeqCall *calls, int ncalls, FrontDev d)
                             const uint8_t *r0 = J + (size_t)y0 * pitch, *r1 = J + (size_t)y1 * pitch;
                             int jv = ((int)__ldg(r0 + x0) * w00 + (int)__ldg(r0 + x1) * w01 + (int)__ldg(r1 + x0) * w10 +
                                       (int)__ldg(r1 + x1) * w11 + (1 << 8)) >> 9;
-                            s_diff[p] = (short)(jv - Iw[k]);
+                            const int diff = jv - Iw[k];
+                            const unsigned dw = s_dIw[p];
+                            s_prod[p] = make_int2(diff * (int)(short)(dw & 0xFFFFu), diff * ((int)dw >> 16));
                         } else if (p < 448)
-                            s_diff[p] = 0;
+                            s_prod[p] = make_int2(0, 0);
                     }
                 }
                 __syncwarp();
@@ -384,18 +390,16 @@ k_lk(FrontCfg c, const SeqCall *calls, int ncalls, FrontDev d)
                 if (lane < 10) {
 #pragma unroll 1
                     for (int y = 0; y < VRF_LK_WIN; ++y) {
-                        const short *df = s_diff + y * 21;
-                        const short *di = s_dI + 2 * (y * 21) + cq;       // + cq selects Ix (b1) / Iy (b2)
+                        const int *pr = s_prodi + 2 * (y * 21) + cq;          // + cq selects diff*Ix (b1) / diff*Iy (b2)
                         if (cr < 4) {
 #pragma unroll
                             for (int hq = 0; hq < 2; ++hq) {
-                                int x = 8 * hq + cr;
-                                int v = (int)df[x] * (int)di[2 * x] + (int)df[x + 4] * (int)di[2 * (x + 4)];   // v_dotprod
-                                acc += (float)v;
+                                const int x = 8 * hq + cr;
+                                acc += (float)(pr[2 * x] + pr[2 * (x + 4)]);        // v_dotprod pair sum, exact in int32
                             }
                         } else {
 #pragma unroll
-                            for (int x = 16; x < 21; ++x) acc += (float)((int)df[x] * (int)di[2 * x]);
+                            for (int x = 16; x < 21; ++x) acc += (float)pr[2 * x];
                         }
                     }
                 }

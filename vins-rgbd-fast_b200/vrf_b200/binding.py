@@ -366,6 +366,34 @@ class Handle:
         seq_a = np.asarray(seqs, np.int32)
         check(self.lib.vrf_ba_download_batch(self.h, len(seqs), seq_a.ctypes.data, None), self.h)
 
+    # ---- preallocated batch calls (no per-call python allocations; used by bench.py's e2e arm) ----
+    def make_track_batch(self, n, debug=False):
+        outs = (VrfTrackOut * n)()
+        results = [TrackResult(self.ncells, debug) for _ in range(n)]
+        for r, o in zip(results, outs):
+            r.fill(o)
+        return outs, results
+
+    def read_image_batch_into(self, seq_a, ptrs, fmt, t_a, R_a, p_a, outs):
+        """seq_a/t_a/R_a/p_a: contiguous numpy arrays, ptrs: (c_void_p * n) of host frame pointers."""
+        rc = self.lib.vrf_tracker_read_image_batch(self.h, len(seq_a), seq_a.ctypes.data, C.cast(ptrs, C.c_void_p), 0, fmt,
+                                                   t_a.ctypes.data, R_a.ctypes.data, p_a.ctypes.data, outs)
+        return check(rc, self.h)
+
+    def make_ba_batch(self, problems):
+        from .ba_problem import BaSolution
+        n = len(problems)
+        probs = (VrfBaProblem * n)()
+        res = (VrfBaResult * n)()
+        sols = [BaSolution(pb.M) for pb in problems]
+        for i, pb in enumerate(problems):
+            C.memmove(C.byref(probs[i]), C.byref(pb.c), C.sizeof(VrfBaProblem))
+            C.memmove(C.byref(res[i]), C.byref(sols[i].c), C.sizeof(VrfBaResult))
+        return probs, res, sols
+
+    def ba_solve_batch_into(self, seq_a, probs, res):
+        return check(self.lib.vrf_ba_solve_batch(self.h, len(seq_a), seq_a.ctypes.data, probs, res), self.h)
+
     def enqueue_dev(self, seqs, d_ptr, fmt, times, Rs=None, pubs=None, d_depth=None):
         n = len(seqs)
         seq_a = np.asarray(seqs, np.int32)
