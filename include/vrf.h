@@ -157,9 +157,9 @@ int vrf_tracker_read_image_batch(vrf_handle *h, int n, const int32_t *seqs,
  * (frame i at d_imgs + i*frame_bytes, rows tightly packed) already in HBM.
  * Enqueues the whole front end on the handle's stream and returns without
  * synchronising; results are fetched with vrf_tracker_fetch_batch().
- * If `d_depth` is non-NULL it points to n contiguous 16UC1 depth frames and the
- * per-feature depth lookup of FeatureManager::addFeatureCheckParallax
- * (feature_manager.cpp:71-80) is done on device (depth at (int)v,(int)u). */
+ * `d_depth` is reserved for the device-side depth lookup of
+ * FeatureManager::addFeatureCheckParallax (feature_manager.cpp:71-80) and must be NULL
+ * in this version (VRF_ERR_UNSUPPORTED otherwise). */
 int vrf_tracker_enqueue_batch_dev(vrf_handle *h, int n, const int32_t *seqs,
                                   const uint8_t *d_imgs, int fmt, const uint16_t *d_depth,
                                   const double *cur_times, const double *relative_Rs,

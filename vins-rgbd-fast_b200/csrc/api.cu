@@ -351,7 +351,7 @@ extern "C" int vrf_tracker_enqueue_batch_dev(vrf_handle *h, int n, const int32_t
                                              const double *relative_Rs, const int32_t *pub_flags)
 {
     if (!h || !d_imgs) return VRF_ERR_ARG;
-    (void)d_depth;
+    if (d_depth) return VRF_ERR_UNSUPPORTED;          // reserved
     CK(cudaSetDevice(h->device));
     const int bpp = (fmt == VRF_FMT_RGB8) ? 3 : 1;
     const size_t frame_bytes = (size_t)h->cfg.col * bpp * h->cfg.row;

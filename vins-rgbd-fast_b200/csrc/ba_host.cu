@@ -3,6 +3,7 @@
 // estimator.cpp:936-981 + problem assembly :1166-1302) into device buffers, launches the
 // solve + marginalization kernels, and unpacks results.  Thin host code; no arithmetic of
 // the hot path happens here.
+#include <algorithm>
 #include <cstdlib>
 #include <new>
 #include <vector>
@@ -31,6 +32,7 @@ struct BaState {
     BaMargDev *h_marg = nullptr, *d_marg = nullptr;
     BaPriorStore *d_prior[2] = {nullptr, nullptr};   // [n_seq] each; cur index per sequence below
     BaPriorStore *h_prior = nullptr;                 // pinned staging [1]
+    double *h_lam = nullptr;                         // pinned staging [n_seq][BA_MAX_LM]
     std::vector<int> prior_cur;                      // which store is "last_marginalization_info"
     std::vector<uint8_t> prior_valid;
     // per-sequence scratch
@@ -69,7 +71,8 @@ int ba_create(vrf_handle *h)
         BCK(cudaMalloc((void **)&b->d_prior[k], S * sizeof(BaPriorStore)));
         BCK(cudaMemset(b->d_prior[k], 0, S * sizeof(BaPriorStore)));
     }
-    BCK(cudaMallocHost((void **)&b->h_prior, sizeof(BaPriorStore)));
+    BCK(cudaMallocHost((void **)&b->h_prior, (S + 1) * sizeof(BaPriorStore)));     // [0]: download staging, [1 + slot]: upload staging
+    BCK(cudaMallocHost((void **)&b->h_lam, S * BA_MAX_LM * sizeof(double)));
     BCK(cudaMalloc((void **)&b->d_lam, S * BA_MAX_LM * sizeof(double)));
     BCK(cudaMalloc((void **)&b->d_clam, S * BA_MAX_LM * sizeof(double)));
     BCK(cudaMalloc((void **)&b->d_W, S * BA_MAX_LM * 66 * sizeof(double)));
@@ -92,7 +95,7 @@ void ba_destroy(vrf_handle *h)
     void *dev[] = {b->d_pack, b->d_meta, b->d_prob, b->d_out, b->d_marg, b->d_prior[0], b->d_prior[1], b->d_lam, b->d_clam,
                    b->d_W, b->d_vecs, b->d_imuS, b->d_HP, b->d_colmap, b->d_margbuf, b->d_lmcol};
     for (void *p : dev) if (p) cudaFree(p);
-    void *host[] = {b->h_pack, b->h_meta, b->h_prob, b->h_out, b->h_marg, b->h_prior};
+    void *host[] = {b->h_pack, b->h_meta, b->h_prob, b->h_out, b->h_marg, b->h_prior, b->h_lam};
     for (void *p : host) if (p) cudaFreeHost(p);
     delete b;
     h->ba = nullptr;
@@ -154,8 +157,7 @@ static int pack_problem(vrf_handle *h, int slot, int seq, const VrfBaProblem *pb
     else if (pb->prior) {
         const VrfPrior *P = pb->prior;
         if (P->n < 0 || P->n > VRF_PRIOR_MAX_DIM || P->n_blocks > VRF_PRIOR_MAX_BLOCKS) return VRF_ERR_ARG;
-        BaPriorStore *hp = b->h_prior;
-        if (cudaStreamSynchronize(h->stream) != cudaSuccess) return VRF_ERR_CUDA;     // staging buffer reuse
+        BaPriorStore *hp = b->h_prior + 1 + slot;      // per-slot pinned staging (upload() synchronised the stream before packing)
         hp->n = P->n; hp->n_blocks = P->n_blocks; hp->valid = 1; hp->pad = 0;
         for (int q = 0; q < P->n_blocks; ++q) {
             hp->kind[q] = P->blocks[q].kind; hp->index[q] = P->blocks[q].index; hp->size[q] = P->blocks[q].size; hp->idx[q] = P->blocks[q].idx;
@@ -166,7 +168,6 @@ static int pack_problem(vrf_handle *h, int slot, int seq, const VrfBaProblem *pb
         BaPriorStore *dst = b->d_prior[b->prior_cur[seq]] + seq;
         const size_t bytes = offsetof(BaPriorStore, J0) + sizeof(double) * (size_t)P->n * P->n;
         if (cudaMemcpyAsync(dst, hp, bytes, cudaMemcpyHostToDevice, h->stream) != cudaSuccess) return VRF_ERR_CUDA;
-        if (cudaStreamSynchronize(h->stream) != cudaSuccess) return VRF_ERR_CUDA;
         b->prior_valid[seq] = 1;
         have_prior = 1;
     } else b->prior_valid[seq] = 0;
@@ -217,20 +218,8 @@ static int upload(vrf_handle *h, int n, const int32_t *seqs, const VrfBaProblem 
         int rc = pack_problem(h, i, seqs[i], &probs[i]);
         if (rc != VRF_OK) return rc;
     }
-    // only the used prefix of each pack is copied: header part (poses, imu) + landmark arrays up to M / nobs
-    for (int i = 0; i < n; ++i) {
-        const int M = b->h_meta[i].M, O = b->h_meta[i].nobs;
-        BaHostPack *hs = b->h_pack + i, *ds = b->d_pack + i;
-        BCK(cudaMemcpyAsync(ds, hs, offsetof(BaHostPack, lam), cudaMemcpyHostToDevice, h->stream));
-        if (M > 0) {
-            BCK(cudaMemcpyAsync(ds->lam, hs->lam, sizeof(double) * M, cudaMemcpyHostToDevice, h->stream));
-            BCK(cudaMemcpyAsync(ds->lm_ub, hs->lm_ub, sizeof(double) * M, cudaMemcpyHostToDevice, h->stream));
-            BCK(cudaMemcpyAsync(ds->start, hs->start, sizeof(int) * M, cudaMemcpyHostToDevice, h->stream));
-            BCK(cudaMemcpyAsync(ds->lm_const, hs->lm_const, M, cudaMemcpyHostToDevice, h->stream));
-            BCK(cudaMemcpyAsync(ds->obs, hs->obs, sizeof(double) * 2 * O, cudaMemcpyHostToDevice, h->stream));
-        }
-        BCK(cudaMemcpyAsync(ds->obs_ptr, hs->obs_ptr, sizeof(int) * (M + 1), cudaMemcpyHostToDevice, h->stream));
-    }
+    // one contiguous copy of the n packed problems (pinned staging -> HBM); far cheaper than per-array copies
+    BCK(cudaMemcpyAsync(b->d_pack, b->h_pack, (size_t)n * sizeof(BaHostPack), cudaMemcpyHostToDevice, h->stream));
     BCK(cudaMemcpyAsync(b->d_meta, b->h_meta, n * sizeof(BaMeta), cudaMemcpyHostToDevice, h->stream));
     BCK(cudaMemcpyAsync(b->d_prob, b->h_prob, n * sizeof(BaProbDev), cudaMemcpyHostToDevice, h->stream));
     BCK(cudaMemcpyAsync(b->d_marg, b->h_marg, n * sizeof(BaMargDev), cudaMemcpyHostToDevice, h->stream));
@@ -252,6 +241,13 @@ static int download(vrf_handle *h, int n, const int32_t *seqs, VrfBaResult *res)
 {
     BaState *b = h->ba;
     BCK(cudaMemcpyAsync(b->h_out, b->d_out, n * sizeof(BaOutDev), cudaMemcpyDeviceToHost, h->stream));
+    // inverse depths of all sequences of the batch in one strided copy (only the used prefix of each row)
+    int maxM = 0, lo = h->n_seq, hi = -1;
+    for (int i = 0; i < n; ++i) { maxM = std::max(maxM, b->last_M[seqs[i]]); lo = std::min(lo, (int)seqs[i]); hi = std::max(hi, (int)seqs[i]); }
+    const bool want_lam = res != nullptr && maxM > 0;
+    if (want_lam)
+        BCK(cudaMemcpy2DAsync(b->h_lam, maxM * sizeof(double), b->d_lam + (size_t)lo * BA_MAX_LM, BA_MAX_LM * sizeof(double),
+                              maxM * sizeof(double), hi - lo + 1, cudaMemcpyDeviceToHost, h->stream));
     BCK(cudaStreamSynchronize(h->stream));
     int worst = VRF_OK;
     for (int i = 0; i < n; ++i) {
@@ -268,7 +264,7 @@ static int download(vrf_handle *h, int n, const int32_t *seqs, VrfBaResult *res)
         memcpy(r.Bas, o.Bas, sizeof(o.Bas)); memcpy(r.Bgs, o.Bgs, sizeof(o.Bgs));
         r.has_new_prior = o.has_new_prior;
         if (r.para_Feature && b->last_M[seq] > 0)
-            BCK(cudaMemcpy(r.para_Feature, b->d_lam + (size_t)seq * BA_MAX_LM, sizeof(double) * b->last_M[seq], cudaMemcpyDeviceToHost));
+            memcpy(r.para_Feature, b->h_lam + (size_t)(seq - lo) * maxM, sizeof(double) * b->last_M[seq]);
         if (o.has_new_prior && r.new_prior) {
             BaPriorStore *hp = b->h_prior;
             const BaPriorStore *src = b->d_prior[b->prior_cur[seq]] + seq;
