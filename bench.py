@@ -467,25 +467,35 @@ def main():
     # ---- e2e arm: host buffers through the C ABI (H2D + kernels + D2H per step) ----
     e2e_steps = 0 if args.quick else max(3, min(args.steps, 20))
     hnd2 = binding.Handle(cfg, S, local_rank)
+    hnd2_ba = binding.Handle(cfg, NBA, local_rank)     # processThread's handle (estimator_nodelet.cpp:61-62)
 
     # everything the harness allocates is created once; the timed loop only moves data and calls the C ABI
     seq_np = np.asarray(seqs, np.int32)
     ba_seq_np = np.asarray(ba_seqs, np.int32)
     tr_outs, tr_res = hnd2.make_track_batch(S)
-    ba_probs_c, ba_res_c, ba_sols = hnd2.make_ba_batch(ba_batch)
+    ba_probs_c, ba_res_c, ba_sols = hnd2_ba.make_ba_batch(ba_batch)
     for r_ in ba_res_c:
         r_.new_prior = None          # the new prior stays in HBM (last_marginalization_info lives in the handle)
     import ctypes as C_
     host_ptr = [[h_rgb[b_][f_].data_ptr() for f_ in range(T_FRAMES)] for b_ in range(nb)]
     ptr_arr = (C_.c_void_p * S)()
 
+    import threading
+
+    def run_host_ba():
+        hnd2_ba.ba_solve_batch_into(ba_seq_np, ba_probs_c, ba_res_c)   # host problems in, optimised states out
+
     def run_host_step(k):
+        # two host threads like the reference's trackThread / processThread: the back end's host-buffer call
+        # runs on its own handle while the front end's frames cross PCIe (ctypes releases the GIL)
         idxs, Rs, pubs, times = plans[k]
+        th = threading.Thread(target=run_host_ba)
+        th.start()
         for s_ in seqs:
             ptr_arr[s_] = host_ptr[s_ % nb][idxs[s_]]
         hnd2.read_image_batch_into(seq_np, ptr_arr, binding.FMT_RGB8, np.asarray(times, np.float64),
                                    np.ascontiguousarray(Rs.reshape(S, 9)), np.asarray(pubs, np.int32), tr_outs)
-        hnd2.ba_solve_batch_into(ba_seq_np, ba_probs_c, ba_res_c)      # host problems in, optimised states + prior out
+        th.join()
         return tr_outs
 
     for k in range(3 if e2e_steps else 0):
@@ -505,7 +515,7 @@ def main():
         dist.barrier()
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_val = (S * e2e_steps * world / float(t.item())) if e2e_steps else None
-    hnd2.close()
+    hnd2.close(); hnd2_ba.close()
 
     if rank == 0:
         line = {

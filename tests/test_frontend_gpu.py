@@ -138,6 +138,40 @@ def test_batch_equals_single():
         x.close()
 
 
+def test_chunked_host_batch_equals_single():
+    """A host-frame batch large enough to be cut into copy/compute chunks (100 sequences -> 2 chunks,
+    api.cu vrf_tracker_read_image_batch) returns, per batch position, what single-sequence handles return."""
+    cam = synth.CamModel()
+    cfg = binding.default_config(use_ransac=1)
+    n = 100
+    hb = binding.Handle(cfg, n, 0)
+    base = [synth.Sequence(300 + i, cam) for i in range(4)]
+    probe = [0, 49, 50, 51, 99]                     # both sides of the chunk boundary
+    hs = {i: binding.Handle(cfg, 1, 0) for i in probe}
+    order = list(range(n))[::-1]                    # batch position != sequence slot
+    for k in range(5):
+        fr = [b.frame(k)[1] for b in base]
+        Rs = [b.relative_R(k) for b in base]
+        pubs = [1 if (k + i) % 3 == 0 else 0 for i in range(n)]
+        outs = hb.read_image_batch(order, [fr[i % 4] for i in order], [1.0 + k / 30.0] * n,
+                                   [Rs[i % 4] for i in order], [pubs[i] for i in order])
+        for pos, i in enumerate(order):
+            if i not in hs:
+                continue
+            single = hs[i].read_image(0, fr[i % 4], 1.0 + k / 30.0, Rs[i % 4], pub=pubs[i], debug=False)
+            assert outs[pos].n == single.n, (k, i, outs[pos].n, single.n)
+            if k >= 3:
+                assert single.n > 50          # every probe has published at least once by then
+            assert np.array_equal(outs[pos].ids, single.ids)
+            assert np.array_equal(outs[pos].cur_pts, single.cur_pts)
+            assert np.array_equal(outs[pos].cur_un_pts, single.cur_un_pts)
+            assert np.array_equal(outs[pos].pts_velocity, single.pts_velocity)
+            assert np.array_equal(outs[pos].track_cnt, single.track_cnt)
+    hb.close()
+    for x in hs.values():
+        x.close()
+
+
 def test_textureless_and_reset():
     """Flat frames: no corners -> texture flags drop, n == 0; then reset_sequence restarts ids at 0."""
     cfg = binding.default_config(use_ransac=0)

@@ -136,6 +136,9 @@ extern "C" int vrf_create(const VrfConfig *cfg, int n_seq, int device, vrf_handl
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return fail(VRF_ERR_CUDA);
     h->sm_count = prop.multiProcessorCount;
     if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) return fail(VRF_ERR_CUDA);
+    if (cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking) != cudaSuccess) return fail(VRF_ERR_CUDA);
+    for (int k = 0; k < VRF_COPY_CHUNKS; ++k)
+        if (cudaEventCreateWithFlags(&h->copy_ev[k], cudaEventDisableTiming) != cudaSuccess) return fail(VRF_ERR_CUDA);
     const size_t S = n_seq, SC = S * VRF_CAP, SG = S * VRF_MAX_CELLS;
     FrontDev &d = h->fd;
     cudaError_t e = cudaSuccess;
@@ -177,6 +180,7 @@ extern "C" void vrf_destroy(vrf_handle *h)
 {
     if (!h) return;
     cudaSetDevice(h->device);
+    if (h->copy_stream) cudaStreamSynchronize(h->copy_stream);
     if (h->stream) cudaStreamSynchronize(h->stream);
     ba_destroy(h);
     FrontDev &d = h->fd;
@@ -192,6 +196,8 @@ extern "C" void vrf_destroy(vrf_handle *h)
     }
     if (h->h_hdr) cudaFreeHost(h->h_hdr);
     if (h->h_out) cudaFreeHost(h->h_out);
+    for (int k = 0; k < VRF_COPY_CHUNKS; ++k) if (h->copy_ev[k]) cudaEventDestroy(h->copy_ev[k]);
+    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
 }
@@ -218,10 +224,12 @@ extern "C" int vrf_reset_sequence(vrf_handle *h, int seq)
 }
 
 // Fill the per-call descriptors, upload them and enqueue every front-end kernel.
+// `out_base`: batch position of item 0 (a host-frame batch is enqueued in chunks; outputs are indexed by
+// batch position so that one fetch collects the whole batch).
 static int enqueue_front(vrf_handle *h, int n, const int32_t *seqs, const uint8_t *d_frames, size_t frame_bytes,
-                         int fmt, const double *times, const double *Rs, const int32_t *pubs)
+                         int fmt, const double *times, const double *Rs, const int32_t *pubs, int out_base = 0)
 {
-    if (n < 1 || n > h->n_seq || !seqs || !times) return VRF_ERR_ARG;
+    if (n < 1 || out_base < 0 || out_base + n > h->n_seq || !seqs || !times) return VRF_ERR_ARG;
     if (fmt != VRF_FMT_GRAY8 && fmt != VRF_FMT_RGB8) return VRF_ERR_ARG;
     std::vector<uint8_t> seen(h->n_seq, 0);
     int any_pub = 0;
@@ -249,9 +257,12 @@ static int enqueue_front(vrf_handle *h, int n, const int32_t *seqs, const uint8_
     CK(cudaMemcpyAsync(h->d_calls, h->h_calls, n * sizeof(SeqCall), cudaMemcpyHostToDevice, h->stream));
     CK(cudaEventRecord(h->call_ev[slot], h->stream));
     LaunchCtx lc{h->stream, &h->launches, &h->prof};
-    front_launch(h->fc, h->d_calls, n, h->fd, d_frames, frame_bytes, fmt, any_pub, h->sm_count, lc);
-    if (h->fc.use_ransac && any_pub) ransac_launch(h->fc, h->d_calls, n, h->fd, lc);
-    front_launch_tail(h->fc, h->d_calls, n, h->fd, any_pub, lc);
+    FrontDev fd = h->fd;
+    fd.o_pts += (size_t)out_base * VRF_CAP; fd.o_un += (size_t)out_base * VRF_CAP; fd.o_vel += (size_t)out_base * VRF_CAP;
+    fd.o_ids += (size_t)out_base * VRF_CAP; fd.o_cnt += (size_t)out_base * VRF_CAP; fd.out_hdr += (size_t)out_base * 8;
+    front_launch(h->fc, h->d_calls, n, fd, d_frames, frame_bytes, fmt, any_pub, h->sm_count, lc);
+    if (h->fc.use_ransac && any_pub) ransac_launch(h->fc, h->d_calls, n, fd, lc);
+    front_launch_tail(h->fc, h->d_calls, n, fd, any_pub, lc);
     CK(cudaGetLastError());
     for (int i = 0; i < n; ++i) {
         int s = seqs[i];
@@ -259,7 +270,7 @@ static int enqueue_front(vrf_handle *h, int n, const int32_t *seqs, const uint8_
         h->has_img[s] = 1;
         h->prev_time[s] = times[i];
     }
-    h->last_n = n;
+    h->last_n = out_base + n;
     return VRF_OK;
 }
 
@@ -326,15 +337,31 @@ extern "C" int vrf_tracker_read_image_batch(vrf_handle *h, int n, const int32_t 
     const size_t frame_bytes = row_bytes * h->cfg.row;
     if (stride == 0) stride = row_bytes;
     if (stride < row_bytes) return VRF_ERR_ARG;
-    for (int i = 0; i < n; ++i) {
-        if (!imgs[i]) return VRF_ERR_ARG;
-        if (stride == row_bytes)
-            CK(cudaMemcpyAsync(h->d_stage + (size_t)i * frame_bytes, imgs[i], frame_bytes, cudaMemcpyHostToDevice, h->stream));
-        else
-            CK(cudaMemcpy2DAsync(h->d_stage + (size_t)i * frame_bytes, row_bytes, imgs[i], stride, row_bytes, h->cfg.row, cudaMemcpyHostToDevice, h->stream));
+    {   // duplicates across the whole batch (each chunk re-checks its own part)
+        std::vector<uint8_t> seen(h->n_seq, 0);
+        for (int i = 0; i < n; ++i) {
+            if (!imgs[i] || seqs[i] < 0 || seqs[i] >= h->n_seq || seen[seqs[i]]) return VRF_ERR_ARG;
+            seen[seqs[i]] = 1;
+        }
     }
-    int rc = enqueue_front(h, n, seqs, h->d_stage, frame_bytes, fmt, cur_times, relative_Rs, pub_flags);
-    if (rc != VRF_OK) return rc;
+    // The batch is cut into chunks: chunk c+1's frames cross PCIe on the copy stream while chunk c's
+    // kernels run, so a call costs about max(H2D, kernels) instead of their sum.
+    int nchunk = n / 48;
+    nchunk = nchunk < 1 ? 1 : (nchunk > VRF_COPY_CHUNKS ? VRF_COPY_CHUNKS : nchunk);
+    for (int c = 0; c < nchunk; ++c) {
+        const int i0 = (int)((long long)n * c / nchunk), i1 = (int)((long long)n * (c + 1) / nchunk);
+        for (int i = i0; i < i1; ++i) {
+            if (stride == row_bytes)
+                CK(cudaMemcpyAsync(h->d_stage + (size_t)i * frame_bytes, imgs[i], frame_bytes, cudaMemcpyHostToDevice, h->copy_stream));
+            else
+                CK(cudaMemcpy2DAsync(h->d_stage + (size_t)i * frame_bytes, row_bytes, imgs[i], stride, row_bytes, h->cfg.row, cudaMemcpyHostToDevice, h->copy_stream));
+        }
+        CK(cudaEventRecord(h->copy_ev[c], h->copy_stream));
+        CK(cudaStreamWaitEvent(h->stream, h->copy_ev[c], 0));
+        int rc = enqueue_front(h, i1 - i0, seqs + i0, h->d_stage + (size_t)i0 * frame_bytes, frame_bytes, fmt, cur_times + i0,
+                               relative_Rs ? relative_Rs + (size_t)i0 * 9 : nullptr, pub_flags ? pub_flags + i0 : nullptr, i0);
+        if (rc != VRF_OK) { cudaStreamSynchronize(h->copy_stream); cudaStreamSynchronize(h->stream); return rc; }
+    }
     return fetch_front(h, n, seqs, outs);
 }
 

@@ -21,6 +21,7 @@ namespace vrf {
 struct MargShared {
     int kind[64], index[64], lsize[64], gsize[64], idx[64], present[64], drop[64];
     int nb, m, n, pos, first_kept, go;
+    int chunk[BA_MAX_LM / 32], maxobs, lm0;
     int col_pose[BA_NF], col_sb[BA_NF], col_ex;
     double red[BA_THREADS / 32];
     double cs[2 * (BA_MAX_POS / 2 + 2)];
@@ -99,84 +100,103 @@ __device__ __noinline__ void jacobi_eig(double *A, double *V, int n, MargShared 
     __syncthreads();
 }
 
-// Same algorithm on matrices held in shared memory (n <= MARG_SMEM_N).  Row and column
-// rotations of a round are fused: the 2x2 block at rows {p1,q1} x cols {p2,q2} of J^T A J
-// only depends on the same 4 entries of A, so every (pair, pair) block is updated in place by
-// one thread and a round needs two barriers instead of three global-memory phases.
+// Same algorithm on matrices held in shared memory (n <= MARG_SMEM_N), restructured for the SM:
+//  * matrices are padded to an even dimension ne with a zero row/column (its rotations are identities,
+//    so no "bye" branches) and an odd leading dimension ld (column-strided accesses hit distinct banks);
+//  * row and column rotations of a round are fused: the 2x2 block at rows {p1,q1} x cols {p2,q2} of
+//    J^T A J only depends on the same 4 entries of A; A stays exactly symmetric, so only the blocks of
+//    the upper (pair x pair) triangle are computed and mirrored -- half the FP64 work;
+//  * the rotation needs no division: with d = aqq - app, e = 2 apq, h = hypot(d, e), g = |d| + h:
+//    c = g / hypot(g, e), s = sign(d e) |e| / hypot(g, e)  (two rsqrt; FP64 div is ~10x an FMA here);
+//  * every thread keeps its work items for the whole call: <= 4 A blocks in registers and one
+//    (pair, row-group) column pair of V.
 #define MARG_SMEM_N 110
+#define MARG_SMEM_LD(n) ((((n) + 1) & ~1) | 1)
 __device__ __noinline__ void jacobi_eig_smem(double *A, double *V, int n, MargShared &sh)
 {
     const int tid = threadIdx.x;
-    for (int e = tid; e < n * n; e += BA_THREADS) V[e] = (e / n == e % n) ? 1.0 : 0.0;
+    const int ne = (n + 1) & ~1, ld = MARG_SMEM_LD(n);
+    const int npairs = ne / 2;
+    for (int e = tid; e < ne * ld; e += BA_THREADS) V[e] = (e / ld == e % ld) ? 1.0 : 0.0;
     __syncthreads();
     if (n < 2) return;
-    const int ne = (n + 1) & ~1;
-    const int npairs = ne / 2;
-    // per-thread work items of a round (fixed for the whole call): (pair, pair) blocks and (pair, row) eigenvector items
-    short itA[24], itB[24];
-    int nit = 0;
-    {
-        const int nblk = npairs * npairs, nv = npairs * n;
-        for (int e = tid; e < nblk + nv && nit < 24; e += BA_THREADS) {
-            if (e < nblk) { itA[nit] = (short)(e / npairs); itB[nit] = (short)(e % npairs); }
-            else { const int f = e - nblk; itA[nit] = (short)(-(f / n) - 1); itB[nit] = (short)(f % n); }
-            ++nit;
+    // A-block items: upper triangle of the (pair x pair) grid, dealt from the top thread down so that the
+    // threads without a V item (tid >= ng * npairs) take blocks first
+    const int ntri = npairs * (npairs + 1) / 2;
+    int bk1[4], bk2[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        int e = (BA_THREADS - 1 - tid) + u * BA_THREADS;
+        bk1[u] = -1; bk2[u] = 0;
+        if (e < ntri) {
+            int k1 = 0, rowlen = npairs;
+            while (e >= rowlen) { e -= rowlen; --rowlen; ++k1; }
+            bk1[u] = k1; bk2[u] = k1 + e;
         }
     }
+    const int ng = BA_THREADS / npairs;
+    const int vk = tid % npairs, vg = tid / npairs;
     for (int sweep = 0; sweep < 40; ++sweep) {
         double off = 0, dg = 0;
         for (int i = tid; i < n; i += BA_THREADS) {
-            const double *row = A + i * n;
-            for (int j = 0; j < n; ++j) { const double v = row[j]; if (i == j) dg += v * v; else if (j > i) off += v * v; }
+            const double *row = A + i * ld;
+            for (int j = i + 1; j < n; ++j) { const double v = row[j]; off += v * v; }
+            dg += row[i] * row[i];
         }
         off = block_sum(off, sh.red);
         dg = block_sum(dg, sh.red);
         if (off <= 1e-26 * dg || off == 0.0) break;     // relative off-diagonal norm 1e-13
         for (int r = 0; r < ne - 1; ++r) {
-            for (int k = tid; k < npairs; k += BA_THREADS) {
+            if (tid < npairs) {
+                const int k = tid;
                 int p, q;
                 if (k == 0) { p = ne - 1; q = r; }
                 else { p = (r + k) % (ne - 1); q = (r - k + (ne - 1)) % (ne - 1); }
                 if (p > q) { int t = p; p = q; q = t; }
                 double c = 1.0, s_ = 0.0;
-                if (q < n) {
-                    double apq = A[p * n + q];
-                    if (apq != 0.0) {
-                        // FP64 div/sqrt latencies dominate this (sequential) phase: 2 divisions + 2 rsqrt
-                        double app = A[p * n + p], aqq = A[q * n + q];
-                        double tau = (aqq - app) / (2.0 * apq);
-                        double w1 = 1.0 + tau * tau;
-                        double t = (tau >= 0 ? 1.0 : -1.0) / (fabs(tau) + w1 * rsqrt(w1));
-                        c = rsqrt(1.0 + t * t); s_ = t * c;
-                    }
-                } else { q = -1; }
+                const double apq = A[p * ld + q];
+                if (apq != 0.0) {
+                    const double d = A[q * ld + q] - A[p * ld + p], e2 = 2.0 * apq;
+                    const double w = d * d + e2 * e2;
+                    const double h = w * rsqrt(w);
+                    const double g = fabs(d) + h;
+                    const double rr = rsqrt(g * g + e2 * e2);
+                    const bool neg = (d != 0.0) && ((d < 0.0) != (e2 < 0.0));
+                    c = g * rr;
+                    s_ = (neg ? -fabs(e2) : fabs(e2)) * rr;
+                }
                 sh.cs[2 * k] = c; sh.cs[2 * k + 1] = s_; sh.pq[2 * k] = p; sh.pq[2 * k + 1] = q;
             }
             __syncthreads();
-            for (int it = 0; it < nit; ++it) {
-                const int ka = itA[it], kb = itB[it];
-                if (ka >= 0) {          // 2x2 block (pair ka) x (pair kb)
-                    const int k1 = ka, k2 = kb;
-                    const int p1 = sh.pq[2 * k1], q1 = sh.pq[2 * k1 + 1], p2 = sh.pq[2 * k2], q2 = sh.pq[2 * k2 + 1];
-                    const double c1 = sh.cs[2 * k1], s1 = sh.cs[2 * k1 + 1], c2 = sh.cs[2 * k2], s2 = sh.cs[2 * k2 + 1];
-                    if (s1 == 0.0 && s2 == 0.0) continue;
-                    const double a11 = A[p1 * n + p2];
-                    const double a12 = q2 >= 0 ? A[p1 * n + q2] : 0.0;
-                    const double a21 = q1 >= 0 ? A[q1 * n + p2] : 0.0;
-                    const double a22 = (q1 >= 0 && q2 >= 0) ? A[q1 * n + q2] : 0.0;
-                    const double t11 = c2 * a11 - s2 * a12, t12 = s2 * a11 + c2 * a12;
-                    const double t21 = c2 * a21 - s2 * a22, t22 = s2 * a21 + c2 * a22;
-                    A[p1 * n + p2] = c1 * t11 - s1 * t21;
-                    if (q2 >= 0) A[p1 * n + q2] = c1 * t12 - s1 * t22;
-                    if (q1 >= 0) A[q1 * n + p2] = s1 * t11 + c1 * t21;
-                    if (q1 >= 0 && q2 >= 0) A[q1 * n + q2] = s1 * t12 + c1 * t22;
-                } else {                // eigenvector row kb's... item: pair (-ka-1), row kb
-                    const int k = -ka - 1, i = kb;
-                    const int p_ = sh.pq[2 * k], q_ = sh.pq[2 * k + 1];
-                    const double c = sh.cs[2 * k], s_ = sh.cs[2 * k + 1];
-                    if (q_ < 0 || s_ == 0.0) continue;
-                    const double a = V[i * n + p_], b = V[i * n + q_];
-                    V[i * n + p_] = c * a - s_ * b; V[i * n + q_] = s_ * a + c * b;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int k1 = bk1[u], k2 = bk2[u];
+                if (k1 < 0) continue;
+                const double c1 = sh.cs[2 * k1], s1 = sh.cs[2 * k1 + 1], c2 = sh.cs[2 * k2], s2 = sh.cs[2 * k2 + 1];
+                if (s1 == 0.0 && s2 == 0.0) continue;
+                const int p1 = sh.pq[2 * k1], q1 = sh.pq[2 * k1 + 1], p2 = sh.pq[2 * k2], q2 = sh.pq[2 * k2 + 1];
+                const double a11 = A[p1 * ld + p2], a12 = A[p1 * ld + q2], a21 = A[q1 * ld + p2], a22 = A[q1 * ld + q2];
+                const double t11 = c2 * a11 - s2 * a12, t12 = s2 * a11 + c2 * a12;
+                const double t21 = c2 * a21 - s2 * a22, t22 = s2 * a21 + c2 * a22;
+                const double o11 = c1 * t11 - s1 * t21, o12 = c1 * t12 - s1 * t22;
+                const double o21 = s1 * t11 + c1 * t21, o22 = s1 * t12 + c1 * t22;
+                if (k1 == k2) {
+                    // diagonal block: the rotation annihilates a_pq; store the symmetric result
+                    A[p1 * ld + p1] = o11; A[q1 * ld + q1] = o22;
+                    A[p1 * ld + q1] = 0.0; A[q1 * ld + p1] = 0.0;
+                } else {
+                    A[p1 * ld + p2] = o11; A[p1 * ld + q2] = o12; A[q1 * ld + p2] = o21; A[q1 * ld + q2] = o22;
+                    A[p2 * ld + p1] = o11; A[q2 * ld + p1] = o12; A[p2 * ld + q1] = o21; A[q2 * ld + q1] = o22;
+                }
+            }
+            if (vg < ng) {
+                const double c = sh.cs[2 * vk], s_ = sh.cs[2 * vk + 1];
+                if (s_ != 0.0) {
+                    const int p_ = sh.pq[2 * vk], q_ = sh.pq[2 * vk + 1];
+                    for (int i = vg; i < ne; i += ng) {
+                        const double a = V[i * ld + p_], b = V[i * ld + q_];
+                        V[i * ld + p_] = c * a - s_ * b; V[i * ld + q_] = s_ * a + c * b;
+                    }
                 }
             }
             __syncthreads();
@@ -242,33 +262,68 @@ k_ba_marg(const BaMeta *metas, const BaProbDev *probs, BaOutDev *outs, const BaM
                 sh.present[find_block(sh, VRF_BLK_POSE, 0)] = 1; sh.present[find_block(sh, VRF_BLK_SPEEDBIAS, 0)] = 1;
                 sh.present[find_block(sh, VRF_BLK_POSE, 1)] = 1; sh.present[find_block(sh, VRF_BLK_SPEEDBIAS, 1)] = 1;
             }
+        }
+        sh.maxobs = 0;
+    }
+    __syncthreads();
+    // landmarks hosted at frame 0 with >= 2 observations are dropped (estimator.cpp:1419-1460): flag them in
+    // parallel; their column ordinal is a ballot prefix (landmark order = getDepthVector order)
+    bool ldrop[BA_MAX_LM / BA_THREADS];
+    int lrank[BA_MAX_LM / BA_THREADS];
+#pragma unroll
+    for (int u = 0; u < BA_MAX_LM / BA_THREADS; ++u) {
+        const int l = u * BA_THREADS + tid;
+        int nobs = 0;
+        bool dflag = false;
+        if (sh.go && flag == VRF_MARGIN_OLD && l < M) {
+            nobs = p.obs_ptr[l + 1] - p.obs_ptr[l];
+            dflag = (p.start[l] == 0 && nobs >= 2);
+        }
+        const unsigned ball = __ballot_sync(0xffffffffu, dflag);
+        if (lane == 0) sh.chunk[u * (BA_THREADS / 32) + warp] = __popc(ball);
+        if (dflag) atomicMax(&sh.maxobs, nobs);
+        ldrop[u] = dflag;
+        lrank[u] = __popc(ball & ((1u << lane) - 1u));
+    }
+    __syncthreads();
+    if (tid == 0 && sh.go) {
+        {
+            const int nb = sh.nb;
             int nl0 = 0;
-            if (flag == VRF_MARGIN_OLD)
-                for (int l = 0; l < M; ++l) {
-                    const int nobs = p.obs_ptr[l + 1] - p.obs_ptr[l];
-                    mg.lmcol[l] = -1;
-                    if (p.start[l] != 0 || nobs < 2) continue;
-                    mg.lmcol[l] = nl0++;          // provisional: ordinal among dropped landmarks
-                    sh.present[find_block(sh, VRF_BLK_POSE, 0)] = 1;
-                    sh.present[find_block(sh, VRF_BLK_EXPOSE, 0)] = 1;
-                    for (int k = 1; k < nobs; ++k) sh.present[find_block(sh, VRF_BLK_POSE, k)] = 1;
-                }
-            else for (int l = 0; l < M; ++l) mg.lmcol[l] = -1;
+            for (int c = 0; c < BA_MAX_LM / 32; ++c) nl0 += sh.chunk[c];
+            if (nl0 > 0) {
+                sh.present[find_block(sh, VRF_BLK_POSE, 0)] = 1;
+                sh.present[find_block(sh, VRF_BLK_EXPOSE, 0)] = 1;
+                for (int k = 1; k < sh.maxobs; ++k) sh.present[find_block(sh, VRF_BLK_POSE, k)] = 1;
+            }
             if (nl0 > BA_MAX_M0) { sh.go = 0; sh.flag = VRF_ERR_CAPACITY; }
             int pos = 0;
             for (int i = 0; i < sh.first_kept; ++i) if (sh.present[i]) { sh.idx[i] = pos; pos += sh.lsize[i]; }
             const int lm0 = pos;
+            sh.lm0 = lm0;
             pos += nl0;
             sh.m = pos;
             for (int i = sh.first_kept; i < nb; ++i) if (sh.present[i] && !sh.drop[i]) { sh.idx[i] = pos; pos += sh.lsize[i]; }
             sh.pos = pos; sh.n = pos - sh.m;
-            for (int l = 0; l < M; ++l) if (mg.lmcol[l] >= 0) mg.lmcol[l] += lm0;
             for (int f = 0; f < BA_NF; ++f) {
                 int i = find_block(sh, VRF_BLK_POSE, f); sh.col_pose[f] = (i >= 0 && sh.present[i]) ? sh.idx[i] : -1;
                 i = find_block(sh, VRF_BLK_SPEEDBIAS, f); sh.col_sb[f] = (i >= 0 && sh.present[i]) ? sh.idx[i] : -1;
             }
             { int i = find_block(sh, VRF_BLK_EXPOSE, 0); sh.col_ex = (i >= 0 && sh.present[i]) ? sh.idx[i] : -1; }
         }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int u = 0; u < BA_MAX_LM / BA_THREADS; ++u) {
+        const int l = u * BA_THREADS + tid;
+        if (l >= M) continue;
+        int col = -1;
+        if (ldrop[u]) {
+            int before = 0;
+            for (int c = 0; c < u * (BA_THREADS / 32) + warp; ++c) before += sh.chunk[c];
+            col = sh.lm0 + before + lrank[u];
+        }
+        mg.lmcol[l] = col;
     }
     __syncthreads();
     if (!sh.go) { if (tid == 0) { out.has_new_prior = 0; if (sh.flag) out.status = sh.flag; } return; }
@@ -601,11 +656,19 @@ k_ba_marg(const BaMeta *metas, const BaProbDev *probs, BaOutDev *outs, const BaM
     MPROF(4);
     // second decomposition: A' = V2 diag(S) V2^T (in shared memory when it fits)
     if (nn <= MARG_SMEM_N) {
-        double *As = big, *Vs = big + nn * nn;
-        for (int e = tid; e < nn * nn; e += BA_THREADS) As[e] = Ar[e];
+        const int ne2 = (nn + 1) & ~1, ld2 = MARG_SMEM_LD(nn);
+        double *As = big, *Vs = big + ne2 * ld2;
+        for (int e = tid; e < ne2 * ld2; e += BA_THREADS) {
+            const int i = e / ld2, j = e - i * ld2;
+            As[e] = (i < nn && j < nn) ? Ar[(size_t)i * nn + j] : 0.0;
+        }
         __syncthreads();
         jacobi_eig_smem(As, Vs, nn, sh);
-        for (int e = tid; e < nn * nn; e += BA_THREADS) { V2[e] = Vs[e]; if (e / nn == e % nn) Ar[e] = As[e]; }
+        for (int e = tid; e < nn * nn; e += BA_THREADS) {
+            const int i = e / nn, j = e - i * nn;
+            V2[e] = Vs[i * ld2 + j];
+            if (i == j) Ar[e] = As[i * ld2 + i];
+        }
         __syncthreads();
     } else {
         jacobi_eig(Ar, V2, nn, sh);
@@ -640,7 +703,7 @@ k_ba_marg(const BaMeta *metas, const BaProbDev *probs, BaOutDev *outs, const BaM
     }
 }
 
-static size_t marg_smem() { return ((sizeof(MargShared) + 15) & ~(size_t)15) + sizeof(double) * 2 * MARG_SMEM_N * MARG_SMEM_N; }
+static size_t marg_smem() { return ((sizeof(MargShared) + 15) & ~(size_t)15) + sizeof(double) * 2 * MARG_SMEM_N * MARG_SMEM_LD(MARG_SMEM_N); }
 size_t ba_marg_smem_bytes() { return marg_smem(); }
 
 int ba_marg_launch(const BaMeta *d_meta, const BaProbDev *d_prob, BaOutDev *d_out, BaMargDev *d_marg, int n, LaunchCtx &lc)

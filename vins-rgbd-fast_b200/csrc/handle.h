@@ -4,7 +4,8 @@
 
 #include "common.cuh"
 
-#define VRF_CALL_SLOTS 4
+#define VRF_CALL_SLOTS 8
+#define VRF_COPY_CHUNKS 8
 
 namespace vrf {
 struct BaState;   // ba_host.cu
@@ -59,6 +60,9 @@ struct vrf_handle {
     vrf::FrontCfg fc;
     int n_seq = 0, device = 0, sm_count = 0;
     cudaStream_t stream = nullptr;
+    // host-frame path: H2D copies run on their own stream, chunk by chunk, ahead of the kernels
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t copy_ev[VRF_COPY_CHUNKS] = {};
     vrf::FrontDev fd = {};
     // per-call descriptor ring (host pinned + device) so that enqueue calls can be pipelined
     vrf::SeqCall *h_calls_ring[VRF_CALL_SLOTS] = {};
