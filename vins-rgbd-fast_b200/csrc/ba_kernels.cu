@@ -53,6 +53,48 @@ __device__ __forceinline__ bool col_active_dev(const BaMeta &m, int col)
     return false;        // ex-pose constant in this build
 }
 
+#define BA_NPAIR (BA_NF * (BA_NF - 1) / 2)
+static_assert(BA_NPAIR * 54 <= (BA_NF - 1) * 15 * 30, "pair partials must fit in imuJ");
+
+__device__ __forceinline__ int pair_index(int i, int j) { return i * (2 * BA_NF - i - 1) / 2 + (j - i - 1); }
+
+// entry e of the 12x12 normal-equation block of one projection factor (host Jacobian Ji, observer Jacobian Jj,
+// 2x6 row-major each): 0..35 Jj^T Ji, 36..56 lower triangle of Jj^T Jj, 57..77 of Ji^T Ji, 78..83 Jj^T r, 84..89 Ji^T r.
+// Called with compile-time e (fully unrolled loops) so that the register arrays are indexed statically.
+__device__ __forceinline__ double pair_entry(int e, const double *Ji, const double *Jj, const double *r)
+{
+    if (e < 36) { const int a = e / 6, b = e % 6; return Jj[a] * Ji[b] + Jj[6 + a] * Ji[6 + b]; }
+    if (e < 78) {
+        const double *J = e < 57 ? Jj : Ji;
+        const int t = e < 57 ? e - 36 : e - 57;
+        int a = 0;
+        while ((a + 1) * (a + 2) / 2 <= t) ++a;
+        const int b = t - a * (a + 1) / 2;
+        return J[a] * J[b] + J[6 + a] * J[6 + b];
+    }
+    if (e < 84) { const int a = e - 78; return Jj[a] * r[0] + Jj[6 + a] * r[1]; }
+    if (e < 90) { const int a = e - 84; return Ji[a] * r[0] + Ji[6 + a] * r[1]; }
+    return 0.0;
+}
+
+// Sum 16 per-lane values over the 32 lanes with 16 shuffles: after the four scatter stages lane L holds the
+// total of value (L >> 1) over its 16-lane partner set, the last stage completes it (lanes 2m, 2m+1 agree).
+__device__ __forceinline__ double reduce_scatter16(double (&v)[16], int lane)
+{
+#pragma unroll
+    for (int st = 0; st < 4; ++st) {
+        const int n2 = 8 >> st, mask = 16 >> st;
+        const bool up = (lane & mask) != 0;
+#pragma unroll
+        for (int k = 0; k < n2; ++k) {
+            const double keep = up ? v[k + n2] : v[k];
+            const double send = up ? v[k] : v[k + n2];
+            v[k] = keep + __shfl_xor_sync(0xffffffffu, send, mask);
+        }
+    }
+    return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 1);
+}
+
 // cost of all residual blocks at (pose, sb, lam); optionally the full linearisation into sh.H / sh.g / landmark arrays.
 // __noinline__: the solve loop calls this from five sites; inlining produced a 51k-instruction kernel (800 KB of SASS)
 // that thrashed the instruction cache (one resident CTA per SM, 16 warps in different code regions).
@@ -63,66 +105,110 @@ __device__ __noinline__ double ba_evaluate(const BaMeta &m, const BaProbDev &p, 
     if (lin) {
         for (int i = tid; i < BA_NC * (BA_NC + 1) / 2; i += BA_THREADS) sh.H[i] = 0.0;
         for (int i = tid; i < BA_NC; i += BA_THREADS) sh.g[i] = 0.0;
+        for (int i = tid; i < BA_NPAIR * 54; i += BA_THREADS) (&sh.imuJ[0][0])[i] = 0.0;      // per-pair partials (see below)
+        for (int i = tid; i < m.M * 66; i += BA_THREADS) p.W[i] = 0.0;
+        for (int l = tid; l < m.M; l += BA_THREADS) { p.hll[l] = 0.0; p.gl[l] = 0.0; }
     }
     for (int f = tid; f < BA_NF; f += BA_THREADS) d_q2R(pose + 7 * f + 3, sh.R + 9 * f);
     if (tid == 0) d_q2R(sh.ex + 3, sh.ric);
+    const bool eprof = (m.debug & 16) != 0;
+    long long et[5] = {0, 0, 0, 0, 0}, ec = eprof ? clock64() : 0;
+#define EPROF(k) do { if (eprof) { long long t_ = clock64(); et[k] += t_ - ec; ec = t_; } } while (0)
     __syncthreads();
+    EPROF(0);
     double cost = 0.0;
-    // ---- projection factors: two landmarks per warp (16 lanes each), one lane per factor (track length <= 11) ----
-    const int half = lane >> 4, hl = lane & 15;
-    const bool single = (m.debug & 4) != 0;          // diagnostic: one landmark per warp
-    for (int lp = warp; (single ? lp : 2 * lp) < m.M; lp += nwarp) {
-        const int l = single ? lp : 2 * lp + half;
-        const bool lv = single ? (half == 0) : (l < m.M);
-        const int o0 = lv ? p.obs_ptr[l] : 0, nf = lv ? p.obs_ptr[l + 1] - o0 - 1 : 0;
-        const int i = lv ? p.start[l] : 0;
-        const bool lc = lv ? (p.lm_const[l] != 0) : true;
-        double r[2] = {0, 0}, Ji[12], Jj[12], Jl[2] = {0, 0};
-        const bool act = hl < nf;
-        const int j = i + 1 + hl;
-        if (act) {
-            const double xi = p.obs[2 * o0], yi = p.obs[2 * o0 + 1];
-            const double xj = p.obs[2 * (o0 + 1 + hl)], yj = p.obs[2 * (o0 + 1 + hl) + 1];
-            double rho0 = proj_eval(pose + 7 * i, sh.R + 9 * i, pose + 7 * j, sh.R + 9 * j, sh.ex, sh.ric, lam[l], xi, yi, xj, yj,
-                                    lin, lc, r, Ji, Jj, Jl);
-            cost += 0.5 * rho0;
+    if (!lin) {
+        // ---- projection factors, cost only: two landmarks per warp (16 lanes each), one lane per factor ----
+        const int half = lane >> 4, hl = lane & 15;
+        for (int lp = warp; 2 * lp < m.M; lp += nwarp) {
+            const int l = 2 * lp + half;
+            if (l >= m.M) continue;
+            const int o0 = p.obs_ptr[l], nf = p.obs_ptr[l + 1] - o0 - 1;
+            if (hl >= nf) continue;
+            const int i = p.start[l], j = i + 1 + hl;
+            double r[2], Ji[12], Jj[12], Jl[2];
+            cost += 0.5 * proj_eval(pose + 7 * i, sh.R + 9 * i, pose + 7 * j, sh.R + 9 * j, sh.ex, sh.ric, lam[l], p.obs[2 * o0],
+                                    p.obs[2 * o0 + 1], p.obs[2 * (o0 + 1 + hl)], p.obs[2 * (o0 + 1 + hl) + 1], false,
+                                    p.lm_const[l] != 0, r, Ji, Jj, Jl);
         }
-        if (!lin) continue;
-        if (!act) {
+    } else {
+        // ---- projection factors, linearisation: one warp per frame pair (host i, observer j), one lane per factor ----
+        // Every factor of the pair adds to the same 12x12 block of J^T J.  The 90 distinct sums (off-diagonal 6x6,
+        // two diagonal lower triangles, two gradient 6-vectors) are reduced over the warp's lanes with a
+        // reduce-scatter butterfly (one shuffle per value instead of five) and accumulated in registers over the
+        // pair's batches: no shared-memory atomics.  The off-diagonal block has a single owner and is stored
+        // directly; the diagonal parts go to per-pair partials that are summed per frame afterwards.
+        double *part = &sh.imuJ[0][0];              // [55][54]; imuJ is rewritten by the IMU phase below
+        const int nbatch = (m.M + 31) >> 5;
+        for (int pi = warp; pi < BA_NPAIR; pi += nwarp) {
+            int i = 0, rem = pi;
+            while (rem >= BA_NF - 1 - i) { rem -= BA_NF - 1 - i; ++i; }
+            const int j = i + 1 + rem;
+            double acc[6] = {0, 0, 0, 0, 0, 0};
+            bool any_pair = false;
+            for (int bt = 0; bt < nbatch; ++bt) {
+                const int l = 32 * bt + lane;
+                bool act = false;
+                int o0 = 0;
+                if (l < m.M && p.start[l] == i) {
+                    o0 = p.obs_ptr[l];
+                    act = (p.obs_ptr[l + 1] - o0 - 1) >= (j - i);
+                }
+                if (!__any_sync(0xffffffffu, act)) continue;
+                any_pair = true;
+                double r[2] = {0, 0}, Ji[12], Jj[12], Jl[2] = {0, 0};
 #pragma unroll
-            for (int k = 0; k < 12; ++k) { Ji[k] = 0; Jj[k] = 0; }
-        }
-        // landmark scalars (reductions stay inside the 16-lane half)
-        double hl_ = half_sum_d(Jl[0] * Jl[0] + Jl[1] * Jl[1]);
-        double gl = half_sum_d(Jl[0] * r[0] + Jl[1] * r[1]);
-        double *Wl = p.W + (size_t)(lv ? l : 0) * 66;
-        if (lv) for (int k = hl; k < 66; k += 16) Wl[k] = 0.0;
-        __syncwarp();
-        // host-pose parts (reduced over the landmark's factors), then lane-private observer parts
+                for (int k = 0; k < 12; ++k) { Ji[k] = 0; Jj[k] = 0; }
+                if (act) {
+                    const int oj = o0 + (j - i);
+                    const double rho0 = proj_eval(pose + 7 * i, sh.R + 9 * i, pose + 7 * j, sh.R + 9 * j, sh.ex, sh.ric, lam[l],
+                                                  p.obs[2 * o0], p.obs[2 * o0 + 1], p.obs[2 * oj], p.obs[2 * oj + 1], true,
+                                                  p.lm_const[l] != 0, r, Ji, Jj, Jl);
+                    cost += 0.5 * rho0;
+                    // landmark rows: the observer part has one contributor, the rest sums over the landmark's factors
+                    double *Wl = p.W + (size_t)l * 66;
 #pragma unroll
-        for (int a = 0; a < 6; ++a) {
-            double wi = half_sum_d(Ji[a] * Jl[0] + Ji[6 + a] * Jl[1]);
-            double gi = half_sum_d(Ji[a] * r[0] + Ji[6 + a] * r[1]);
-            if (hl == 0 && lv) { Wl[6 * i + a] = wi; atomicAdd(&sh.g[6 * i + a], gi); }
+                    for (int a = 0; a < 6; ++a) {
+                        Wl[6 * j + a] = Jj[a] * Jl[0] + Jj[6 + a] * Jl[1];
+                        atomicAdd(&Wl[6 * i + a], Ji[a] * Jl[0] + Ji[6 + a] * Jl[1]);
+                    }
+                    atomicAdd(&p.hll[l], Jl[0] * Jl[0] + Jl[1] * Jl[1]);
+                    atomicAdd(&p.gl[l], Jl[0] * r[0] + Jl[1] * r[1]);
+                }
 #pragma unroll
-            for (int b = 0; b <= a; ++b) {
-                double h = half_sum_d(Ji[a] * Ji[b] + Ji[6 + a] * Ji[6 + b]);
-                if (hl == 0 && lv) atomicAdd(&sh.H[pk(6 * i + a, 6 * i + b)], h);
+                for (int ps = 0; ps < 6; ++ps) {
+                    double v[16];
+#pragma unroll
+                    for (int t = 0; t < 16; ++t) v[t] = pair_entry(ps * 16 + t, Ji, Jj, r);
+                    acc[ps] += reduce_scatter16(v, lane);
+                }
+            }
+            if (any_pair && !(lane & 1)) {
+#pragma unroll
+                for (int ps = 0; ps < 6; ++ps) {
+                    const int e = ps * 16 + (lane >> 1);
+                    if (e < 36) sh.H[pk(6 * j + e / 6, 6 * i + e % 6)] = acc[ps];
+                    else if (e < 90) part[pi * 54 + (e - 36)] = acc[ps];
+                }
             }
         }
-        if (act) {
-#pragma unroll
-            for (int a = 0; a < 6; ++a) {
-                Wl[6 * j + a] = Jj[a] * Jl[0] + Jj[6 + a] * Jl[1];
-                atomicAdd(&sh.g[6 * j + a], Jj[a] * r[0] + Jj[6 + a] * r[1]);
-#pragma unroll
-                for (int b = 0; b <= a; ++b) atomicAdd(&sh.H[pk(6 * j + a, 6 * j + b)], Jj[a] * Jj[b] + Jj[6 + a] * Jj[6 + b]);
-#pragma unroll
-                for (int b = 0; b < 6; ++b) atomicAdd(&sh.H[pk(6 * j + a, 6 * i + b)], Jj[a] * Ji[b] + Jj[6 + a] * Ji[6 + b]);
-            }
+        __syncthreads();
+        // diagonal blocks and gradient of frame f: sum of the partials of every pair f takes part in
+        for (int t = tid; t < BA_NF * 27; t += BA_THREADS) {
+            const int f = t / 27, q = t - f * 27;
+            double sum = 0;
+            for (int i = 0; i < f; ++i) sum += part[pair_index(i, f) * 54 + (q < 21 ? q : 42 + (q - 21))];            // f observes
+            for (int j = f + 1; j < BA_NF; ++j) sum += part[pair_index(f, j) * 54 + (q < 21 ? 21 + q : 48 + (q - 21))];   // f hosts
+            if (q < 21) {
+                int a = 0;
+                while ((a + 1) * (a + 2) / 2 <= q) ++a;
+                sh.H[pk(6 * f + a, 6 * f + (q - a * (a + 1) / 2))] = sum;
+            } else
+                sh.g[6 * f + (q - 21)] = sum;
         }
-        if (hl == 0 && lv) { p.hll[l] = hl_; p.gl[l] = gl; }
+        __syncthreads();
     }
+    EPROF(1);
     // ---- IMU factors: one warp per factor ----
     for (int f = warp; f < m.nimu; f += nwarp) {
         const int j = m.imu_j[f], i = j - 1;
@@ -158,7 +244,9 @@ __device__ __noinline__ double ba_evaluate(const BaMeta &m, const BaProbDev &p, 
             atomicAdd(&sh.g[tcol(lane)], gsum);
         }
     }
+    EPROF(2);
     __syncthreads();
+    EPROF(3);
     // ---- prior ----
     const BaPriorStore *P = p.prior;
     const int np_ = (P && P->valid) ? P->n : 0;
@@ -193,6 +281,10 @@ __device__ __noinline__ double ba_evaluate(const BaMeta &m, const BaProbDev &p, 
         }
     }
     __syncthreads();
+    EPROF(4);
+    if (eprof && blockIdx.x == 0 && (tid == 0 || tid == 320 || tid == 500))
+        printf("evaluate lin=%d tid=%d zero=%lld proj=%lld imu=%lld wait=%lld prior=%lld\n", (int)lin, tid, et[0], et[1], et[2], et[3], et[4]);
+#undef EPROF
     return block_sum(cost, sh.red);
 }
 

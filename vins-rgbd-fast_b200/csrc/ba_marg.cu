@@ -21,11 +21,12 @@ namespace vrf {
 struct MargShared {
     int kind[64], index[64], lsize[64], gsize[64], idx[64], present[64], drop[64];
     int nb, m, n, pos, first_kept, go;
-    int chunk[BA_MAX_LM / 32], maxobs, lm0;
+    int chunk[BA_MAX_LM / 32], maxobs, lm0, jdbg;
     int col_pose[BA_NF], col_sb[BA_NF], col_ex;
     double red[BA_THREADS / 32];
-    double cs[2 * (BA_MAX_POS / 2 + 2)];
-    int pq[2 * (BA_MAX_POS / 2 + 2)];
+    __align__(16) double cs[2 * (BA_MAX_POS / 2 + 2)];
+    __align__(16) double cs_b[2 * (BA_MAX_POS / 2 + 2)];
+    __align__(8) int pq[2 * (BA_MAX_POS / 2 + 2)];
     double J[15 * 30], r[16];
     double dx[VRF_PRIOR_MAX_DIM], pr[VRF_PRIOR_MAX_DIM];
     double R[BA_NF * 9], ric[9];
@@ -100,28 +101,64 @@ __device__ __noinline__ void jacobi_eig(double *A, double *V, int n, MargShared 
     __syncthreads();
 }
 
-// Same algorithm on matrices held in shared memory (n <= MARG_SMEM_N), restructured for the SM:
+// Same algorithm on matrices held in shared memory (n <= MARG_SMEM_N).  The round loop is bound by
+// shared-memory bandwidth (every round reads and writes all of A and V), so the layout minimises bytes:
 //  * matrices are padded to an even dimension ne with a zero row/column (its rotations are identities,
-//    so no "bye" branches) and an odd leading dimension ld (column-strided accesses hit distinct banks);
-//  * row and column rotations of a round are fused: the 2x2 block at rows {p1,q1} x cols {p2,q2} of
-//    J^T A J only depends on the same 4 entries of A; A stays exactly symmetric, so only the blocks of
-//    the upper (pair x pair) triangle are computed and mirrored -- half the FP64 work;
+//    so no "bye" branches);
+//  * A is kept as its upper triangle only (entry (i,j) lives at [min][max], odd leading dimension).  Row and
+//    column rotations of a round are fused: the 2x2 block at rows {p1,q1} x cols {p2,q2} of J^T A J only
+//    depends on the same 4 entries, and by symmetry only the blocks of the upper (pair x pair) triangle
+//    exist: 4 loads + 4 stores per block, half the FP64 work of the two-sided update;
+//  * V is stored transposed (VT[col][row]) so that a rotation of columns (p,q) streams two contiguous
+//    rows of VT with 16-byte accesses, lanes along the row;
 //  * the rotation needs no division: with d = aqq - app, e = 2 apq, h = hypot(d, e), g = |d| + h:
 //    c = g / hypot(g, e), s = sign(d e) |e| / hypot(g, e)  (two rsqrt; FP64 div is ~10x an FMA here);
-//  * every thread keeps its work items for the whole call: <= 4 A blocks in registers and one
-//    (pair, row-group) column pair of V.
+//  * every thread keeps its work items for the whole call in registers.
 #define MARG_SMEM_N 110
-#define MARG_SMEM_LD(n) ((((n) + 1) & ~1) | 1)
-__device__ __noinline__ void jacobi_eig_smem(double *A, double *V, int n, MargShared &sh)
+#define MARG_NE(n) (((n) + 1) & ~1)
+#define MARG_LDA(n) (MARG_NE(n) | 1)
+#define MARG_A_ELEMS(n) (MARG_NE(n) * MARG_LDA(n))              /* even: VT stays 16-byte aligned */
+#define MARG_V_ELEMS(n) (MARG_NE(n) * MARG_NE(n))
+#define JAC_V_ITEMS 8      /* >= ceil(55 * 55 / 448), processed in groups of 4 */
+// round-robin tournament: pair k of round r (ne players, player ne-1 fixed), returned with p < q
+__device__ __forceinline__ int2 jac_pair(int r, int k, int ne)
+{
+    int p, q;
+    if (k == 0) { p = ne - 1; q = r; }
+    else {
+        p = r + k; if (p >= ne - 1) p -= ne - 1;
+        q = r - k; if (q < 0) q += ne - 1;
+    }
+    return p < q ? make_int2(p, q) : make_int2(q, p);
+}
+// rotation of pair k in round r from the current A: (c, s)
+__device__ __forceinline__ double2 jac_angle(const double *A, int ld, int2 pq)
+{
+    double c = 1.0, s_ = 0.0;
+    const double apq = A[pq.x * ld + pq.y];
+    if (apq != 0.0) {
+        const double d = A[pq.y * ld + pq.y] - A[pq.x * ld + pq.x], e2 = 2.0 * apq;
+        const double w = d * d + e2 * e2;
+        const double h = w * rsqrt(w);
+        const double g = fabs(d) + h;
+        const double rr = rsqrt(g * g + e2 * e2);
+        const bool neg = (d != 0.0) && ((d < 0.0) != (e2 < 0.0));
+        c = g * rr;
+        s_ = (neg ? -fabs(e2) : fabs(e2)) * rr;
+    }
+    return make_double2(c, s_);
+}
+
+#define JAC_ANGLE_THREADS 64       /* warps 0-1 compute the next round's angles while the others rotate V */
+__device__ __noinline__ void jacobi_eig_smem(double *A, double *VT, int n, MargShared &sh)
 {
     const int tid = threadIdx.x;
-    const int ne = (n + 1) & ~1, ld = MARG_SMEM_LD(n);
+    const int ne = MARG_NE(n), ld = MARG_LDA(n), ldv = ne;
     const int npairs = ne / 2;
-    for (int e = tid; e < ne * ld; e += BA_THREADS) V[e] = (e / ld == e % ld) ? 1.0 : 0.0;
+    for (int e = tid; e < ne * ldv; e += BA_THREADS) VT[e] = (e / ldv == e % ldv) ? 1.0 : 0.0;
     __syncthreads();
     if (n < 2) return;
-    // A-block items: upper triangle of the (pair x pair) grid, dealt from the top thread down so that the
-    // threads without a V item (tid >= ng * npairs) take blocks first
+    // A-block items: upper triangle of the (pair x pair) grid, dealt from the top thread down
     const int ntri = npairs * (npairs + 1) / 2;
     int bk1[4], bk2[4];
 #pragma unroll
@@ -134,8 +171,21 @@ __device__ __noinline__ void jacobi_eig_smem(double *A, double *V, int n, MargSh
             bk1[u] = k1; bk2[u] = k1 + e;
         }
     }
-    const int ng = BA_THREADS / npairs;
-    const int vk = tid % npairs, vg = tid / npairs;
+    // V items: (pair, row pair) on threads >= JAC_ANGLE_THREADS; consecutive lanes take consecutive row pairs
+    const int nvit = npairs * npairs;             // npairs rotations x (ne / 2) row pairs
+    const int nvthr = BA_THREADS - JAC_ANGLE_THREADS;
+    short vk[JAC_V_ITEMS], vi[JAC_V_ITEMS];
+#pragma unroll
+    for (int u = 0; u < JAC_V_ITEMS; ++u) {
+        const int e = (tid - JAC_ANGLE_THREADS) + u * nvthr;
+        const bool ok = tid >= JAC_ANGLE_THREADS && e < nvit;
+        vk[u] = (short)(ok ? e / npairs : -1);
+        vi[u] = (short)(ok ? e % npairs : 0);
+    }
+    double2 *csb[2] = {reinterpret_cast<double2 *>(sh.cs), reinterpret_cast<double2 *>(sh.cs_b)};
+    long long jt[4] = {0, 0, 0, 0}, jc = 0;
+    int nsweep = 0;
+#define JPROF(k) do { if (sh.jdbg) { long long t_ = clock64(); jt[k] += t_ - jc; jc = t_; } } while (0)
     for (int sweep = 0; sweep < 40; ++sweep) {
         double off = 0, dg = 0;
         for (int i = tid; i < n; i += BA_THREADS) {
@@ -146,63 +196,88 @@ __device__ __noinline__ void jacobi_eig_smem(double *A, double *V, int n, MargSh
         off = block_sum(off, sh.red);
         dg = block_sum(dg, sh.red);
         if (off <= 1e-26 * dg || off == 0.0) break;     // relative off-diagonal norm 1e-13
+        ++nsweep;
+        if (tid < npairs) csb[0][tid] = jac_angle(A, ld, jac_pair(0, tid, ne));
+        __syncthreads();
+        if (sh.jdbg) jc = clock64();
         for (int r = 0; r < ne - 1; ++r) {
-            if (tid < npairs) {
-                const int k = tid;
-                int p, q;
-                if (k == 0) { p = ne - 1; q = r; }
-                else { p = (r + k) % (ne - 1); q = (r - k + (ne - 1)) % (ne - 1); }
-                if (p > q) { int t = p; p = q; q = t; }
-                double c = 1.0, s_ = 0.0;
-                const double apq = A[p * ld + q];
-                if (apq != 0.0) {
-                    const double d = A[q * ld + q] - A[p * ld + p], e2 = 2.0 * apq;
-                    const double w = d * d + e2 * e2;
-                    const double h = w * rsqrt(w);
-                    const double g = fabs(d) + h;
-                    const double rr = rsqrt(g * g + e2 * e2);
-                    const bool neg = (d != 0.0) && ((d < 0.0) != (e2 < 0.0));
-                    c = g * rr;
-                    s_ = (neg ? -fabs(e2) : fabs(e2)) * rr;
-                }
-                sh.cs[2 * k] = c; sh.cs[2 * k + 1] = s_; sh.pq[2 * k] = p; sh.pq[2 * k + 1] = q;
-            }
-            __syncthreads();
+            const double2 *cs2 = csb[r & 1];
+            // ---- A <- J^T A J on the upper (pair x pair) triangle; loads of both blocks first ----
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int k1 = bk1[u], k2 = bk2[u];
-                if (k1 < 0) continue;
-                const double c1 = sh.cs[2 * k1], s1 = sh.cs[2 * k1 + 1], c2 = sh.cs[2 * k2], s2 = sh.cs[2 * k2 + 1];
-                if (s1 == 0.0 && s2 == 0.0) continue;
-                const int p1 = sh.pq[2 * k1], q1 = sh.pq[2 * k1 + 1], p2 = sh.pq[2 * k2], q2 = sh.pq[2 * k2 + 1];
-                const double a11 = A[p1 * ld + p2], a12 = A[p1 * ld + q2], a21 = A[q1 * ld + p2], a22 = A[q1 * ld + q2];
-                const double t11 = c2 * a11 - s2 * a12, t12 = s2 * a11 + c2 * a12;
-                const double t21 = c2 * a21 - s2 * a22, t22 = s2 * a21 + c2 * a22;
-                const double o11 = c1 * t11 - s1 * t21, o12 = c1 * t12 - s1 * t22;
-                const double o21 = s1 * t11 + c1 * t21, o22 = s1 * t12 + c1 * t22;
-                if (k1 == k2) {
-                    // diagonal block: the rotation annihilates a_pq; store the symmetric result
-                    A[p1 * ld + p1] = o11; A[q1 * ld + q1] = o22;
-                    A[p1 * ld + q1] = 0.0; A[q1 * ld + p1] = 0.0;
-                } else {
-                    A[p1 * ld + p2] = o11; A[p1 * ld + q2] = o12; A[q1 * ld + p2] = o21; A[q1 * ld + q2] = o22;
-                    A[p2 * ld + p1] = o11; A[q2 * ld + p1] = o12; A[p2 * ld + q1] = o21; A[q2 * ld + q1] = o22;
+            for (int u0 = 0; u0 < 4; u0 += 2) {
+                if (bk1[u0] < 0) break;
+                double a11[2], a12[2], a21[2], a22[2];
+                double2 r1[2], r2[2];
+                int e11[2], e12[2], e21[2], e22[2];
+                bool live[2];
+#pragma unroll
+                for (int uu = 0; uu < 2; ++uu) {
+                    const int k1 = bk1[u0 + uu], k2 = bk2[u0 + uu];
+                    live[uu] = k1 >= 0;
+                    const int kk1 = live[uu] ? k1 : 0, kk2 = live[uu] ? k2 : 0;
+                    r1[uu] = cs2[kk1]; r2[uu] = cs2[kk2];
+                    const int2 i1 = jac_pair(r, kk1, ne), i2 = jac_pair(r, kk2, ne);
+                    // diagonal block (k1 == k2): entries (p,p) (p,q) (p,q) (q,q)
+                    e11[uu] = min(i1.x, i2.x) * ld + max(i1.x, i2.x); e12[uu] = min(i1.x, i2.y) * ld + max(i1.x, i2.y);
+                    e21[uu] = min(i1.y, i2.x) * ld + max(i1.y, i2.x); e22[uu] = min(i1.y, i2.y) * ld + max(i1.y, i2.y);
+                    a11[uu] = A[e11[uu]]; a12[uu] = A[e12[uu]]; a21[uu] = A[e21[uu]]; a22[uu] = A[e22[uu]];
                 }
-            }
-            if (vg < ng) {
-                const double c = sh.cs[2 * vk], s_ = sh.cs[2 * vk + 1];
-                if (s_ != 0.0) {
-                    const int p_ = sh.pq[2 * vk], q_ = sh.pq[2 * vk + 1];
-                    for (int i = vg; i < ne; i += ng) {
-                        const double a = V[i * ld + p_], b = V[i * ld + q_];
-                        V[i * ld + p_] = c * a - s_ * b; V[i * ld + q_] = s_ * a + c * b;
+#pragma unroll
+                for (int uu = 0; uu < 2; ++uu) {
+                    const double c1 = r1[uu].x, s1 = r1[uu].y, c2 = r2[uu].x, s2 = r2[uu].y;
+                    if (!live[uu] || (s1 == 0.0 && s2 == 0.0)) continue;
+                    const double t11 = c2 * a11[uu] - s2 * a12[uu], t12 = s2 * a11[uu] + c2 * a12[uu];
+                    const double t21 = c2 * a21[uu] - s2 * a22[uu], t22 = s2 * a21[uu] + c2 * a22[uu];
+                    const double o11 = c1 * t11 - s1 * t21, o22 = s1 * t12 + c1 * t22;
+                    if (bk1[u0 + uu] == bk2[u0 + uu]) {
+                        // the rotation annihilates a_pq (e12 == e21 here)
+                        A[e11[uu]] = o11; A[e22[uu]] = o22; A[e12[uu]] = 0.0;
+                    } else {
+                        A[e11[uu]] = o11; A[e12[uu]] = c1 * t12 - s1 * t22;
+                        A[e21[uu]] = s1 * t11 + c1 * t21; A[e22[uu]] = o22;
                     }
                 }
             }
+            JPROF(0);
             __syncthreads();
+            JPROF(1);
+            if (tid < JAC_ANGLE_THREADS) {
+                // next round's rotation angles (double-buffered) ...
+                if (tid < npairs && r + 1 < ne - 1) csb[(r + 1) & 1][tid] = jac_angle(A, ld, jac_pair(r + 1, tid, ne));
+            } else {
+                // ... while the other warps apply this round's rotations to the eigenvectors
+#pragma unroll
+                for (int u0 = 0; u0 < JAC_V_ITEMS; u0 += 4) {
+                    if (vk[u0] < 0) break;
+                    double2 va[4], vb[4], rc[4];
+                    double2 *colp[4], *colq[4];
+#pragma unroll
+                    for (int uu = 0; uu < 4; ++uu) {
+                        const int k = vk[u0 + uu] < 0 ? 0 : vk[u0 + uu];
+                        rc[uu] = cs2[k];
+                        const int2 ip = jac_pair(r, k, ne);
+                        colp[uu] = reinterpret_cast<double2 *>(VT + ip.x * ldv) + vi[u0 + uu];
+                        colq[uu] = reinterpret_cast<double2 *>(VT + ip.y * ldv) + vi[u0 + uu];
+                        va[uu] = *colp[uu]; vb[uu] = *colq[uu];
+                    }
+#pragma unroll
+                    for (int uu = 0; uu < 4; ++uu) {
+                        if (vk[u0 + uu] < 0 || rc[uu].y == 0.0) continue;
+                        const double c = rc[uu].x, s_ = rc[uu].y;
+                        *colp[uu] = make_double2(c * va[uu].x - s_ * vb[uu].x, c * va[uu].y - s_ * vb[uu].y);
+                        *colq[uu] = make_double2(s_ * va[uu].x + c * vb[uu].x, s_ * va[uu].y + c * vb[uu].y);
+                    }
+                }
+            }
+            JPROF(2);
+            __syncthreads();
+            JPROF(3);
         }
     }
     __syncthreads();
+    if (sh.jdbg && blockIdx.x == 0 && (tid == 0 || tid == 300 || tid == 511))
+        printf("jacobi n=%d sweeps=%d tid=%d ablock=%lld wait1=%lld angle|V=%lld wait2=%lld\n", n, nsweep, tid, jt[0], jt[1], jt[2], jt[3]);
+#undef JPROF
 }
 
 __device__ __forceinline__ int find_block(const MargShared &sh, int kind, int index)
@@ -242,6 +317,7 @@ k_ba_marg(const BaMeta *metas, const BaProbDev *probs, BaOutDev *outs, const BaM
         }
         sh.go = go;
         sh.flag = 0;
+        sh.jdbg = (m.debug & 8) != 0;
         int nb = 0;
         auto add = [&](int kind, int index, int gs, int drop) {
             for (int i = 0; i < nb; ++i) if (sh.kind[i] == kind && sh.index[i] == index) return;
@@ -656,17 +732,17 @@ k_ba_marg(const BaMeta *metas, const BaProbDev *probs, BaOutDev *outs, const BaM
     MPROF(4);
     // second decomposition: A' = V2 diag(S) V2^T (in shared memory when it fits)
     if (nn <= MARG_SMEM_N) {
-        const int ne2 = (nn + 1) & ~1, ld2 = MARG_SMEM_LD(nn);
-        double *As = big, *Vs = big + ne2 * ld2;
+        const int ne2 = MARG_NE(nn), ld2 = MARG_LDA(nn);
+        double *As = big, *Vs = big + MARG_A_ELEMS(nn);
         for (int e = tid; e < ne2 * ld2; e += BA_THREADS) {
             const int i = e / ld2, j = e - i * ld2;
-            As[e] = (i < nn && j < nn) ? Ar[(size_t)i * nn + j] : 0.0;
+            As[e] = (i < nn && j < nn && j >= i) ? Ar[(size_t)i * nn + j] : 0.0;      // upper triangle
         }
         __syncthreads();
         jacobi_eig_smem(As, Vs, nn, sh);
         for (int e = tid; e < nn * nn; e += BA_THREADS) {
             const int i = e / nn, j = e - i * nn;
-            V2[e] = Vs[i * ld2 + j];
+            V2[e] = Vs[j * ne2 + i];                 // VT[col][row]
             if (i == j) Ar[e] = As[i * ld2 + i];
         }
         __syncthreads();
@@ -703,7 +779,7 @@ k_ba_marg(const BaMeta *metas, const BaProbDev *probs, BaOutDev *outs, const BaM
     }
 }
 
-static size_t marg_smem() { return ((sizeof(MargShared) + 15) & ~(size_t)15) + sizeof(double) * 2 * MARG_SMEM_N * MARG_SMEM_LD(MARG_SMEM_N); }
+static size_t marg_smem() { return ((sizeof(MargShared) + 15) & ~(size_t)15) + sizeof(double) * (MARG_A_ELEMS(MARG_SMEM_N) + MARG_V_ELEMS(MARG_SMEM_N)); }
 size_t ba_marg_smem_bytes() { return marg_smem(); }
 
 int ba_marg_launch(const BaMeta *d_meta, const BaProbDev *d_prob, BaOutDev *d_out, BaMargDev *d_marg, int n, LaunchCtx &lc)
