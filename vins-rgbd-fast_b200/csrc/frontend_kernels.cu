@@ -151,7 +151,7 @@ k_pyrdown(FrontCfg c, const SeqCall *calls, FrontDev d, int level)
 // ---------------------------------------------------------------------------
 #define LK_WPB 8
 #define LK_NPX 14   // ceil(441/32)
-#define LK_R1_BYTES 3584    // region 1: 24x24 u8 patch of I, later 441(+7) int2 products (diff*Ix, diff*Iy)
+#define LK_R1_BYTES 3584    // region 1: 24x24 u8 patch of I, later the float addend arrays of the b-sum chains (792 floats)
 #define LK_R2_BYTES 1936    // region 2: 22x22 short2 Scharr, later 441(+7) short2 (Ix,Iy) of the window
 
 // OpenCV's float accumulation order (lkpyramid.cpp SSE path; pinned bit-exactly against
@@ -172,6 +172,53 @@ __device__ __forceinline__ float lk_combine(float acc, int q)
     return tl + ((l0 + l2) + (l1 + l3));
 }
 
+// b-sum chains live on lanes 4q + r (SIMD accumulators) and 8 + q (scalar tail)
+__device__ __forceinline__ float lk_combine_b(float acc, int q)
+{
+    float l0 = __shfl_sync(0xffffffffu, acc, 4 * q + 0);
+    float l1 = __shfl_sync(0xffffffffu, acc, 4 * q + 1);
+    float l2 = __shfl_sync(0xffffffffu, acc, 4 * q + 2);
+    float l3 = __shfl_sync(0xffffffffu, acc, 4 * q + 3);
+    float tl = __shfl_sync(0xffffffffu, acc, 8 + q);
+    return tl + ((l0 + l2) + (l1 + l3));
+}
+
+// LK_UNITS: the 441 window pixels as 168 SIMD units (row y, half hq, SIMD lane r: pixels x = 8 hq + r and x + 4,
+// chain step s = 2 y + hq) followed by 105 tail units (row y, x = 16..20, chain step t = 5 y + x - 16).
+// Unit u = lane + 32 m; m = 0..4 are SIMD units on every lane, m = 5 is SIMD on lanes 0..7 and tail on the rest,
+// m = 6..8 are tail units.  Addend arrays (float, region 1): SIMD chain (q, r) at (4 q + r) * LK_FS_STRIDE + s,
+// tail chain q at LK_FT_BASE + q * LK_FT_STRIDE + t.
+#define LK_NUNIT 9
+#define LK_FS_STRIDE 72          // >= 44, = 8 mod 32: the four SIMD lanes of a step hit different banks
+#define LK_FT_BASE (8 * LK_FS_STRIDE)
+#define LK_FT_STRIDE 108
+__device__ __forceinline__ void lk_unit(int m, int lane, int &pa, int &pb, int &dst)
+{
+    const int u = lane + 32 * m;
+    if (m < 5 || (m == 5 && lane < 8)) {
+        const int sidx = u >> 2, r = u & 3;
+        pa = (sidx >> 1) * 21 + 8 * (sidx & 1) + r; pb = pa + 4;
+        dst = r * LK_FS_STRIDE + sidx;
+    } else {
+        const int t = u - 168;
+        if (t < 105) { const int y = t / 5; pa = y * 21 + 16 + (t - 5 * y); pb = -1; dst = LK_FT_BASE + t; }
+        else { pa = -1; pb = -1; dst = 0; }
+    }
+}
+
+// I (5 fractional bits), Ix, Iy of window pixel p by integer bilinear interpolation of the staged patch / Scharr tile
+__device__ __forceinline__ void lk_interp_I(const uint8_t *s_I, const short2 *s_D, int p, int iw00, int iw01, int iw10, int iw11,
+                                            int &iv, int &ixv, int &iyv)
+{
+    const int wy = p / 21, wx = p - wy * 21;
+    const uint8_t *q = &s_I[(wy + 1) * 24 + wx + 1];
+    iv = ((int)q[0] * iw00 + (int)q[1] * iw01 + (int)q[24] * iw10 + (int)q[25] * iw11 + (1 << 8)) >> 9;
+    const short2 *dq = &s_D[wy * 22 + wx];
+    const short2 d00 = dq[0], d01 = dq[1], d10 = dq[22], d11 = dq[23];
+    ixv = (d00.x * iw00 + d01.x * iw01 + d10.x * iw10 + d11.x * iw11 + (1 << 13)) >> 14;
+    iyv = (d00.y * iw00 + d01.y * iw01 + d10.y * iw10 + d11.y * iw11 + (1 << 13)) >> 14;
+}
+
 __global__ void __launch_bounds__(LK_WPB * 32, 2)
 k_lk(FrontCfg c, const SeqCall *calls, int ncalls, FrontDev d)
 {
@@ -179,8 +226,7 @@ k_lk(FrontCfg c, const SeqCall *calls, int ncalls, FrontDev d)
     __shared__ __align__(16) unsigned char s_r2[LK_WPB][LK_R2_BYTES];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     uint8_t *s_I = s_r1[wib];
-    int2 *s_prod = reinterpret_cast<int2 *>(s_r1[wib]);
-    const int *s_prodi = reinterpret_cast<const int *>(s_r1[wib]);
+    float *s_F = reinterpret_cast<float *>(s_r1[wib]);     // addend arrays of the b-sum chains (see LK_UNITS)
     const unsigned *s_dIw = reinterpret_cast<const unsigned *>(s_r2[wib]);   // packed (Ix | Iy<<16) per window pixel
     short2 *s_D = reinterpret_cast<short2 *>(s_r2[wib]);
     const short *s_dI = reinterpret_cast<const short *>(s_r2[wib]);   // interleaved (Ix, Iy) per window pixel
@@ -271,32 +317,44 @@ k_lk(FrontCfg c, const SeqCall *calls, int ncalls, FrontDev d)
                 s_D[t] = dv;
             }
             __syncwarp();
-            // integer bilinear interpolation of the window: I (5 fractional bits), Ix, Iy
-            int Iw[LK_NPX];
-            unsigned dpk[LK_NPX];                 // packed (Ix, Iy) as two int16
+            // integer bilinear interpolation of the window: I (5 fractional bits), Ix, Iy.
+            // Work is dealt in "units" that match OpenCV's accumulation (see LK_UNITS above): a SIMD unit is the
+            // pixel pair (x, x+4) whose products are summed in int32 before the float conversion, a tail unit
+            // is one pixel of columns 16..20.  Unit u = lane + 32 m.
+            unsigned IwU[LK_NUNIT];               // I of the unit's pixel(s): lo 16 bits pixel a, hi 16 bits pixel b
+            unsigned dpa[LK_NUNIT], dpb[LK_NUNIT];   // packed (Ix, Iy) as two int16
 #pragma unroll
-            for (int k = 0; k < LK_NPX; ++k) {
-                int p = lane + 32 * k;
-                int iv = 0, ixv = 0, iyv = 0;
-                if (p < 441) {
-                    int wy = p / 21, wx = p - wy * 21;
-                    const uint8_t *q = &s_I[(wy + 1) * 24 + wx + 1];
-                    iv = ((int)q[0] * iw00 + (int)q[1] * iw01 + (int)q[24] * iw10 + (int)q[25] * iw11 + (1 << 8)) >> 9;
-                    const short2 *dq = &s_D[wy * 22 + wx];
-                    short2 d00 = dq[0], d01 = dq[1], d10 = dq[22], d11 = dq[23];
-                    ixv = (d00.x * iw00 + d01.x * iw01 + d10.x * iw10 + d11.x * iw11 + (1 << 13)) >> 14;
-                    iyv = (d00.y * iw00 + d01.y * iw01 + d10.y * iw10 + d11.y * iw11 + (1 << 13)) >> 14;
+            for (int mm = 0; mm < LK_NUNIT; ++mm) {
+                int pa, pb, dst;
+                lk_unit(mm, lane, pa, pb, dst);
+                unsigned iw = 0, da_ = 0, db_ = 0;
+                if (pa >= 0) {
+                    int iv, ixv, iyv;
+                    lk_interp_I(s_I, s_D, pa, iw00, iw01, iw10, iw11, iv, ixv, iyv);
+                    iw = (unsigned)iv;
+                    da_ = ((unsigned)ixv & 0xFFFFu) | ((unsigned)iyv << 16);
+                    if (pb >= 0) {
+                        lk_interp_I(s_I, s_D, pb, iw00, iw01, iw10, iw11, iv, ixv, iyv);
+                        iw |= (unsigned)iv << 16;
+                        db_ = ((unsigned)ixv & 0xFFFFu) | ((unsigned)iyv << 16);
+                    }
                 }
-                Iw[k] = iv;
-                dpk[k] = ((unsigned)ixv & 0xFFFFu) | ((unsigned)iyv << 16);
+                IwU[mm] = iw; dpa[mm] = da_; dpb[mm] = db_;
             }
             __syncwarp();
-            // regions are free now: region 2 <- (Ix,Iy) per window pixel
+            // regions are free now: region 2 <- (Ix,Iy) per window pixel; region 1 <- zero padding of the addend arrays
 #pragma unroll
-            for (int k = 0; k < LK_NPX; ++k) {
-                int p = lane + 32 * k;
-                if (p < 448) reinterpret_cast<unsigned *>(s_r2[wib])[p] = (p < 441) ? dpk[k] : 0u;
+            for (int mm = 0; mm < LK_NUNIT; ++mm) {
+                int pa, pb, dst;
+                lk_unit(mm, lane, pa, pb, dst);
+                if (pa >= 0) {
+                    reinterpret_cast<unsigned *>(s_r2[wib])[pa] = dpa[mm];
+                    if (pb >= 0) reinterpret_cast<unsigned *>(s_r2[wib])[pb] = dpb[mm];
+                }
             }
+            if (lane < 7) reinterpret_cast<unsigned *>(s_r2[wib])[441 + lane] = 0u;
+            if (lane < 16) s_F[(lane >> 1) * LK_FS_STRIDE + 42 + (lane & 1)] = 0.f;            // SIMD chains: steps 42, 43
+            else if (lane < 22) s_F[LK_FT_BASE + ((lane - 16) / 3) * LK_FT_STRIDE + 105 + (lane - 16) % 3] = 0.f;   // tails: 105..107
             __syncwarp();
             // A11, A12, A22: 15 ordered float chains (lanes 0..14)
             float A11, A12, A22;
@@ -353,58 +411,68 @@ k_lk(FrontCfg c, const SeqCall *calls, int ncalls, FrontDev d)
                 if (inside) {
                     const uint8_t *Jb = J + (size_t)jy * pitch + jx;
 #pragma unroll
-                    for (int k = 0; k < LK_NPX; ++k) {
-                        int p = lane + 32 * k;
-                        if (p < 441) {
-                            int wy = p / 21, wx = p - wy * 21;
-                            const uint8_t *q = Jb + wy * pitch + wx;
-                            int jv = ((int)__ldg(q) * w00 + (int)__ldg(q + 1) * w01 + (int)__ldg(q + pitch) * w10 +
-                                      (int)__ldg(q + pitch + 1) * w11 + (1 << 8)) >> 9;
-                            const int diff = jv - Iw[k];
-                            const unsigned dw = s_dIw[p];
-                            s_prod[p] = make_int2(diff * (int)(short)(dw & 0xFFFFu), diff * ((int)dw >> 16));
-                        } else if (p < 448)
-                            s_prod[p] = make_int2(0, 0);
+                    for (int mm = 0; mm < LK_NUNIT; ++mm) {
+                        int pa, pb, dst;
+                        lk_unit(mm, lane, pa, pb, dst);
+                        if (pa < 0) continue;
+                        const int wy = pa / 21, wx = pa - wy * 21;
+                        const uint8_t *q = Jb + wy * pitch + wx;
+                        int jv = ((int)__ldg(q) * w00 + (int)__ldg(q + 1) * w01 + (int)__ldg(q + pitch) * w10 +
+                                  (int)__ldg(q + pitch + 1) * w11 + (1 << 8)) >> 9;
+                        int diff = jv - (int)(IwU[mm] & 0xFFFFu);
+                        unsigned dw = s_dIw[pa];
+                        int d1 = diff * (int)(short)(dw & 0xFFFFu), d2 = diff * ((int)dw >> 16);
+                        if (pb >= 0) {
+                            q += 4;
+                            jv = ((int)__ldg(q) * w00 + (int)__ldg(q + 1) * w01 + (int)__ldg(q + pitch) * w10 +
+                                  (int)__ldg(q + pitch + 1) * w11 + (1 << 8)) >> 9;
+                            diff = jv - (int)(IwU[mm] >> 16);
+                            dw = s_dIw[pb];
+                            d1 += diff * (int)(short)(dw & 0xFFFFu); d2 += diff * ((int)dw >> 16);     // v_dotprod pair sum, exact in int32
+                        }
+                        s_F[dst] = (float)d1;
+                        s_F[dst + (pb >= 0 ? 4 * LK_FS_STRIDE : LK_FT_STRIDE)] = (float)d2;
                     }
                 } else {
 #pragma unroll
-                    for (int k = 0; k < LK_NPX; ++k) {
-                        int p = lane + 32 * k;
-                        if (p < 441) {
-                            int wy = p / 21, wx = p - wy * 21;
-                            int x0 = reflect101(jx + wx, cols), x1 = reflect101(jx + wx + 1, cols);
-                            int y0 = reflect101(jy + wy, rows), y1 = reflect101(jy + wy + 1, rows);
+                    for (int mm = 0; mm < LK_NUNIT; ++mm) {
+                        int pa, pb, dst;
+                        lk_unit(mm, lane, pa, pb, dst);
+                        if (pa < 0) continue;
+                        int d1 = 0, d2 = 0;
+#pragma unroll
+                        for (int hh = 0; hh < 2; ++hh) {
+                            const int pp = hh ? pb : pa;
+                            if (pp < 0) continue;
+                            const int wy = pp / 21, wx = pp - wy * 21;
+                            const int x0 = reflect101(jx + wx, cols), x1 = reflect101(jx + wx + 1, cols);
+                            const int y0 = reflect101(jy + wy, rows), y1 = reflect101(jy + wy + 1, rows);
                             const uint8_t *r0 = J + (size_t)y0 * pitch, *r1 = J + (size_t)y1 * pitch;
-                            int jv = ((int)__ldg(r0 + x0) * w00 + (int)__ldg(r0 + x1) * w01 + (int)__ldg(r1 + x0) * w10 +
-                                      (int)__ldg(r1 + x1) * w11 + (1 << 8)) >> 9;
-                            const int diff = jv - Iw[k];
-                            const unsigned dw = s_dIw[p];
-                            s_prod[p] = make_int2(diff * (int)(short)(dw & 0xFFFFu), diff * ((int)dw >> 16));
-                        } else if (p < 448)
-                            s_prod[p] = make_int2(0, 0);
+                            const int jv = ((int)__ldg(r0 + x0) * w00 + (int)__ldg(r0 + x1) * w01 + (int)__ldg(r1 + x0) * w10 +
+                                            (int)__ldg(r1 + x1) * w11 + (1 << 8)) >> 9;
+                            const int diff = jv - (int)(hh ? (IwU[mm] >> 16) : (IwU[mm] & 0xFFFFu));
+                            const unsigned dw = s_dIw[pp];
+                            d1 += diff * (int)(short)(dw & 0xFFFFu); d2 += diff * ((int)dw >> 16);
+                        }
+                        s_F[dst] = (float)d1;
+                        s_F[dst + (pb >= 0 ? 4 * LK_FS_STRIDE : LK_FT_STRIDE)] = (float)d2;
                     }
                 }
                 __syncwarp();
-                // b1, b2: 10 ordered float chains (lanes 0..9)
+                // b1, b2: 10 ordered float chains (lanes 0..3 / 4..7: SIMD accumulators of b1 / b2, lanes 8, 9: scalar tails);
+                // every chain is a contiguous, zero-padded array (x + 0.0f is exact), read 4 addends at a time
                 float acc = 0.f;
                 if (lane < 10) {
-#pragma unroll 1
-                    for (int y = 0; y < VRF_LK_WIN; ++y) {
-                        const int *pr = s_prodi + 2 * (y * 21) + cq;          // + cq selects diff*Ix (b1) / diff*Iy (b2)
-                        if (cr < 4) {
-#pragma unroll
-                            for (int hq = 0; hq < 2; ++hq) {
-                                const int x = 8 * hq + cr;
-                                acc += (float)(pr[2 * x] + pr[2 * (x + 4)]);        // v_dotprod pair sum, exact in int32
-                            }
-                        } else {
-#pragma unroll
-                            for (int x = 16; x < 21; ++x) acc += (float)pr[2 * x];
-                        }
+                    const float4 *src = reinterpret_cast<const float4 *>(s_F + (lane < 8 ? lane * LK_FS_STRIDE : LK_FT_BASE + (lane - 8) * LK_FT_STRIDE));
+                    const int nq = lane < 8 ? 11 : 27;
+#pragma unroll 3
+                    for (int qd = 0; qd < nq; ++qd) {
+                        const float4 f4 = src[qd];
+                        acc += f4.x; acc += f4.y; acc += f4.z; acc += f4.w;
                     }
                 }
-                float fb1 = lk_combine(acc, 0) * FLT_SCALE;
-                float fb2 = lk_combine(acc, 1) * FLT_SCALE;
+                float fb1 = lk_combine_b(acc, 0) * FLT_SCALE;
+                float fb2 = lk_combine_b(acc, 1) * FLT_SCALE;
                 float2 delta = make_float2((A12 * fb2 - A22 * fb1) * D, (A12 * fb1 - A11 * fb2) * D);
                 nextPt.x += delta.x; nextPt.y += delta.y;
                 nextStored = make_float2(nextPt.x + VRF_LK_HALF, nextPt.y + VRF_LK_HALF);
