@@ -187,7 +187,7 @@ def run_reference(args):
         "dtype": "u8/f32 (cv2), f64 (BA)", "data": "synthetic",
         "config": {"workload": WORKLOAD, "sample": f"{cores} sequences x {frames_per_worker} frames per step"},
         "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
-                         "sample": f"{cores} workers x {frames_per_worker} frames/step: cv2 4.13 (real OpenCV) FAST+PyrLK+RANSAC with python glue, "
+                         "sample": f"{cores} workers x {frames_per_worker} frames/step: cv2 4.13 (real OpenCV) RGB2GRAY+FAST+PyrLK+RANSAC with python glue, depth lookup, "
                                    f"C restatement of the Ceres problem for the BA (1 thread per solve)"},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -207,7 +207,7 @@ def _ref_prepare(seed):
     from oracle import ba_ref
     from vrf_b200 import ba_problem as BP, synth
     s = synth.Sequence(seed)
-    frames = [s.frame(k)[1] for k in range(T_FRAMES)]
+    frames = [s.frame(k) for k in range(T_FRAMES)]          # (rgb, gray, depth16) as the two camera topics deliver them
     Rf = np.stack([s.relative_R(k) for k in range(T_FRAMES)])
     cfg = ba_config()
     sim = BP.WindowSimulator(seed, cfg, n_landmarks=BA_LANDMARKS)
@@ -217,8 +217,9 @@ def _ref_prepare(seed):
 
 
 def _ref_step(n):
+    import cv2
     from oracle import ba_ref
-    from oracle.frontend_ref import FeatureTrackerRef, FrontendConfig
+    from oracle.frontend_ref import FeatureTrackerRef, FrontendConfig, decode_depth, depth_lookup
     if "frames" not in _REF:
         _ref_prepare(1234 + os.getpid() % N_DISTINCT)
     frames, Rf, cfg, pb = _REF["frames"], _REF["Rf"], _REF["cfg"], _REF["pb"]
@@ -228,8 +229,11 @@ def _ref_step(n):
         idx, pidx = frame_plan(step, len(frames))
         R = np.eye(3) if step == 0 else rel_rotation(Rf, idx, pidx)
         pub = (step % PUB_EVERY == 0)
-        ft.read_image(frames[idx], 1.0 + step / 30.0, R, pub_this_frame=pub)
+        rgb, _, dep = frames[idx]
+        gray = cv2.cvtColor(rgb, cv2.COLOR_RGB2GRAY)        # cv_bridge::toCvCopy(MONO8), estimator_nodelet.cpp:292-307
+        ft.read_image(gray, 1.0 + step / 30.0, R, pub_this_frame=pub)
         if pub:
+            depth_lookup(decode_depth(dep, H, W), ft.cur_pts, cfg.depth_min_dist)   # :512-534, feature_manager.cpp:71-80
             ba_ref.solve(cfg, pb)          # Estimator::optimization: solve + marginalization, 1 thread (Ceres num_threads = 1)
     return len(ft.ids), time.perf_counter() - t0
 
@@ -249,11 +253,12 @@ def ba_config():
     cfg.k1, cfg.k2, cfg.p1, cfg.p2 = 0.1, -0.2, 1e-3, 1e-3
     cfg.num_iterations, cfg.fix_depth, cfg.depth_max_dist, cfg.g_norm = 8, 0, 10.0, 9.81
     cfg.acc_n, cfg.acc_w, cfg.gyr_n, cfg.gyr_w = 0.1, 0.001, 0.01, 0.0001
+    cfg.depth_min_dist = 0.3
     return cfg
 
 
-WORKLOAD = ("BASELINE configs[1]+[2]: 640x480 RGB-D streams, 150 feats, 3-level pyramid LK, 7x8 grid FAST + RANSAC, "
-            "publish every 3rd frame (freq 10 Hz @ 30 Hz); every publish frame runs one 10-keyframe sliding-window BA "
+WORKLOAD = ("BASELINE configs[1]+[2]: 640x480 RGB-D streams (RGB8 + 16UC1 depth), 150 feats, 3-level pyramid LK, 7x8 grid FAST + RANSAC, "
+            "publish every 3rd frame (freq 10 Hz @ 30 Hz) with per-feature depth lookup; every publish frame runs one 10-keyframe sliding-window BA "
             "(150 landmarks, ~1000 projection factors, 10 IMU factors, prior n=75, 8 dogleg iterations) + marginalization")
 
 
@@ -267,6 +272,7 @@ def main():
     ap.add_argument("--ref-frames", type=int, default=12, help="frames per worker per step of the reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--quick", action="store_true", help="profiling runs: skip the e2e arm and the CPU baseline")
+    ap.add_argument("--with-e2e", action="store_true", help="with --quick: still run the e2e arm")
     args = ap.parse_args()
     if args.impl != "reference":
         args.warmup = max(args.warmup, 3)
@@ -311,6 +317,7 @@ def main():
     d_dep = [torch.from_numpy(b[1].view(np.int16)).to(dev) for b in base]
     # pinned host mirrors for the e2e arm
     h_rgb = [torch.from_numpy(b[0]).pin_memory() for b in base]
+    h_dep = [torch.from_numpy(b[1].view(np.int16)).pin_memory() for b in base]
 
     cfg = ba_config()
     hnd = binding.Handle(cfg, S, local_rank)
@@ -356,15 +363,18 @@ def main():
     # (what a camera DMA engine would have written; built once, before timing)
     PERIOD = 2 * (T_FRAMES - 1)
     d_steps = torch.empty((PERIOD, S, H, W, 3), dtype=torch.uint8, device=dev)
+    d_steps_dep = torch.empty((PERIOD, S, H, W), dtype=torch.int16, device=dev)      # the paired 16UC1 depth frames
     for p_ in range(PERIOD):
         idxs = plans[p_][0] if p_ < len(plans) else step_plan(p_)[0]
         for s in seqs:
             d_steps[p_, s].copy_(d_rgb[s % nb][idxs[s]])
+            d_steps_dep[p_, s].copy_(d_dep[s % nb][idxs[s]])
     torch.cuda.synchronize()
 
     def run_dev_step(k):
         idxs, Rs, pubs, times = plans[k]
-        hnd.enqueue_dev(seqs, d_steps[k % PERIOD].data_ptr(), binding.FMT_RGB8, times, Rs, pubs, d_depth=None)
+        hnd.enqueue_dev(seqs, d_steps[k % PERIOD].data_ptr(), binding.FMT_RGB8, times, Rs, pubs,
+                        d_depth=d_steps_dep[k % PERIOD].data_ptr(), depth_fmt=binding.DEPTH_16UC1)
         hnd_ba.ba_enqueue(ba_seqs)           # S/3 windows: solve + gauge fix + marginalization
 
     # ---- warm-up ----
@@ -404,7 +414,8 @@ def main():
     hnd.profile(True); hnd.profile_read(reset=True)
     for k in range(args.warmup, args.warmup + nprof):
         idxs, Rs, pubs, times = plans[k]
-        hnd.enqueue_dev(seqs, d_steps[k % PERIOD].data_ptr(), binding.FMT_RGB8, times, Rs, pubs, d_depth=None)
+        hnd.enqueue_dev(seqs, d_steps[k % PERIOD].data_ptr(), binding.FMT_RGB8, times, Rs, pubs,
+                        d_depth=d_steps_dep[k % PERIOD].data_ptr(), depth_fmt=binding.DEPTH_16UC1)
     prof = hnd.profile_read(reset=True)
     hnd.profile(False)
     hnd_ba.profile(True); hnd_ba.profile_read(reset=True)
@@ -465,9 +476,12 @@ def main():
             pass
 
     # ---- e2e arm: host buffers through the C ABI (H2D + kernels + D2H per step) ----
-    e2e_steps = 0 if args.quick else max(3, min(args.steps, 20))
+    e2e_steps = 0 if (args.quick and not args.with_e2e) else max(3, min(args.steps, 20))
     hnd2 = binding.Handle(cfg, S, local_rank)
-    hnd2_ba = binding.Handle(cfg, NBA, local_rank)     # processThread's handle (estimator_nodelet.cpp:61-62)
+    # processThread's handle (estimator_nodelet.cpp:61-62).  Different sequences publish on different frames, so
+    # consecutive BA batches belong to different sequences: two groups of NBA sequences alternate.
+    hnd2_ba = binding.Handle(cfg, 2 * NBA, local_rank)
+    ba_grp = [np.arange(NBA, dtype=np.int32), np.arange(NBA, 2 * NBA, dtype=np.int32)]
 
     # everything the harness allocates is created once; the timed loop only moves data and calls the C ABI
     seq_np = np.asarray(seqs, np.int32)
@@ -478,38 +492,79 @@ def main():
         r_.new_prior = None          # the new prior stays in HBM (last_marginalization_info lives in the handle)
     import ctypes as C_
     host_ptr = [[h_rgb[b_][f_].data_ptr() for f_ in range(T_FRAMES)] for b_ in range(nb)]
+    host_dptr = [[h_dep[b_][f_].data_ptr() for f_ in range(T_FRAMES)] for b_ in range(nb)]
     ptr_arr = (C_.c_void_p * S)()
+    dptr_arr = (C_.c_void_p * S)()
+    t_host = {"front": 0.0, "ba": 0.0}
+    hnd2_out_w = min(binding.TRACK_CAP, 2 * cfg.max_cnt + (cfg.max_cnt // (cfg.num_grid_rows * cfg.num_grid_cols) + 2) * cfg.num_grid_rows * cfg.num_grid_cols)
 
     import threading
 
-    def run_host_ba():
-        hnd2_ba.ba_solve_batch_into(ba_seq_np, ba_probs_c, ba_res_c)   # host problems in, optimised states out
+    def run_host_ba(k, more):
+        # host problems in, optimised states out; two batches in flight (submit k+1, collect k)
+        t_ = time.perf_counter()
+        if more:
+            hnd2_ba.ba_submit_into(ba_grp[(k + 1) % 2], ba_probs_c)
+        hnd2_ba.ba_collect_into(ba_grp[k % 2], ba_res_c)
+        t_host["ba"] += time.perf_counter() - t_
 
-    def run_host_step(k):
-        # two host threads like the reference's trackThread / processThread: the back end's host-buffer call
-        # runs on its own handle while the front end's frames cross PCIe (ctypes releases the GIL)
-        idxs, Rs, pubs, times = plans[k]
-        th = threading.Thread(target=run_host_ba)
-        th.start()
+    R_flat = [np.ascontiguousarray(pl[1].reshape(S, 9)) for pl in plans]
+    pub_np = [np.asarray(pl[2], np.int32) for pl in plans]
+    time_np = [np.asarray(pl[3], np.float64) for pl in plans]
+
+    def submit_front(k):
+        idxs = plans[k][0]
         for s_ in seqs:
             ptr_arr[s_] = host_ptr[s_ % nb][idxs[s_]]
-        hnd2.read_image_batch_into(seq_np, ptr_arr, binding.FMT_RGB8, np.asarray(times, np.float64),
-                                   np.ascontiguousarray(Rs.reshape(S, 9)), np.asarray(pubs, np.int32), tr_outs)
-        th.join()
-        return tr_outs
+            dptr_arr[s_] = host_dptr[s_ % nb][idxs[s_]]
+        hnd2.submit_batch_into(seq_np, ptr_arr, binding.FMT_RGB8, time_np[k], R_flat[k], pub_np[k],
+                               dptrs=dptr_arr, dfmt=binding.DEPTH_16UC1)
 
-    for k in range(3 if e2e_steps else 0):
-        run_host_step(k)
+    part = os.environ.get("VRF_E2E_PART", "both")          # diagnosis only: "front" / "ba"
+
+    def run_host_steps(k0, k1):
+        """Steps k0..k1-1 through the host-buffer C ABI.  Two host threads like the reference's trackThread /
+        processThread: the back end's host-buffer call runs on its own handle (ctypes releases the GIL) while the
+        front end keeps two batches in flight (submit k+1, collect k) so that the next batch's frames cross PCIe
+        while this batch's kernels run.  Every frame's H2D and every result's D2H happens inside [k0, k1)."""
+        n_out = 0
+        if part != "ba":
+            submit_front(k0)
+        if part != "front":
+            hnd2_ba.ba_submit_into(ba_grp[k0 % 2], ba_probs_c)
+        for k in range(k0, k1):
+            th = threading.Thread(target=(lambda: run_host_ba(k, k + 1 < k1)) if part != "front" else (lambda: None))
+            th.start()
+            if part != "ba":
+                t_ = time.perf_counter()
+                if k + 1 < k1:
+                    submit_front(k + 1)
+                hnd2.collect_batch_into(seq_np, tr_outs)
+                t_host["front"] += time.perf_counter() - t_
+                n_out = sum(tr_outs[i_].n for i_ in range(S))
+            th.join()
+        return n_out
+
+    if e2e_steps:
+        run_host_steps(0, 3)
     torch.cuda.synchronize()
+    if os.environ.get("VRF_E2E_PROF"):
+        hnd2.profile(True); hnd2.profile_read(reset=True)
     if world > 1:
         dist.barrier()
     t0 = time.perf_counter()
     d2h = 0
-    for k in range(3, 3 + e2e_steps):
-        outs = run_host_step(k)
-        d2h = sum(outs[i_].n for i_ in range(S)) * 32 + S * 32 + NBA * (11 * (7 + 9 + 3 + 9 + 9) * 8 + 8 * BA_LANDMARKS)
+    if e2e_steps:
+        n_out = run_host_steps(3, 3 + e2e_steps)
+        d2h = S * hnd2_out_w * 35 + S * 32 + NBA * (11 * (7 + 9 + 3 + 9 + 9) * 8 + 8 * BA_LANDMARKS)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
+    if os.environ.get("VRF_E2E_PROF") and e2e_steps:
+        pr = hnd2.profile_read(reset=True)
+        print("e2e kernel ms/step:", {k_: round(v_[0] / e2e_steps, 3) for k_, v_ in pr.items() if v_[1]}, file=sys.stderr)
+    if e2e_steps and rank == 0:
+        print("e2e host-call seconds per step: front %.4f  ba %.4f  (step %.4f)" % (
+            t_host["front"] / (3 + e2e_steps), t_host["ba"] / (3 + e2e_steps), e2e_s / e2e_steps), file=sys.stderr)
     t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
     if world > 1:
         dist.barrier()
@@ -526,7 +581,7 @@ def main():
             "config": {"workload": WORKLOAD, "seqs_per_gpu": S, "ba_solves_per_step": NBA, "l2": "inputs cycle through %d MB of distinct frames (> L2)" % (nb * T_FRAMES * 3 * W * H // 2**20),
                        "parallelism": f"sequences sharded over {world} GPU(s), no data-path collective"},
             "clocks": clocks, "gpu_launches": int(launches),
-            "e2e": {"value": e2e_val, "unit": "frames/s", "h2d_bytes_per_step": S * 3 * W * H + NBA * (195600 + 8 * (75 * 75 + 75 + 40 * 13)), "d2h_bytes_per_step": int(d2h)},
+            "e2e": {"value": e2e_val, "unit": "frames/s", "h2d_bytes_per_step": S * 3 * W * H + (S // PUB_EVERY) * 2 * W * H + NBA * (195600 + 8 * (75 * 75 + 75 + 40 * 13)), "d2h_bytes_per_step": int(d2h)},
             "roofline": roof, "cpu_baseline": cpu_base,
         }
         print(json.dumps(line))

@@ -53,6 +53,12 @@ typedef struct vrf_handle vrf_handle;
 #define VRF_FMT_GRAY8   0   /* what cv_bridge MONO8 hands to readImage (estimator_nodelet.cpp:292-307) */
 #define VRF_FMT_RGB8    1   /* raw sensor_msgs/Image rgb8 payload; gray = cv::cvtColor RGB2GRAY fixed point */
 
+/* Depth payload formats (sensor_msgs/Image encodings handled at estimator_nodelet.cpp:512-533). */
+#define VRF_DEPTH_NONE   0  /* no depth message: the reference substitutes an all-zero image (:513-516) */
+#define VRF_DEPTH_16UC1  1  /* "16UC1" / "mono16": millimetres, used as is (:518-522) */
+#define VRF_DEPTH_32FC1  2  /* "32FC1": metres; the reference converts the whole frame with
+                               convertTo(CV_16UC1, 1000) (:523-527) -- here only the looked-up pixels are converted */
+
 /*
  * Configuration: the reference's YAML -> extern globals (utility/parameters.h:17-77,
  * parameters.cpp:81-243) plus the PINHOLE intrinsics read by
@@ -83,6 +89,8 @@ typedef struct VrfConfig {
     double  depth_max_dist;           /* DEPTH_MAX_DIST (upper bound 2/DEPTH_MAX_DIST for estimate_flag==2) */
     double  g_norm;                   /* G = (0,0,g_norm) (parameters.cpp:13,158) */
     double  acc_n, acc_w, gyr_n, gyr_w; /* IMU noise (IntegrationBase ctor, integration_base.h:24-31) */
+    double  depth_min_dist;           /* DEPTH_MIN_DIST: features with 0 < depth < this are dropped
+                                         (FeatureManager::addFeatureCheckParallax, feature_manager.cpp:76-80) */
 } VrfConfig;
 
 /* Fills `cfg` with the synthetic-benchmark defaults of SURVEY.md section 8(d). */
@@ -129,6 +137,12 @@ typedef struct VrfTrackOut {
     uint8_t *grids_texture_status; /* out (optional): rows*cols */
     int32_t  n_unstable;       /* out: unstable_pts.size() */
     int32_t  status;           /* out: per-sequence soft status */
+    /* depth of every feature at ((int)v, (int)u) of the depth frame handed in with this call, in millimetres
+     * (depth_img.at<unsigned short>, feature_manager.cpp:71-74; pt_depth_m = depth_mm / 1000.0), and whether
+     * addFeatureCheckParallax keeps the feature (0 = erased because 0 < depth < DEPTH_MIN_DIST, :76-80).
+     * Zero / one when the call carried no depth frame for this sequence. */
+    uint16_t *depth_mm;        /* out (optional): n */
+    uint8_t  *depth_keep;      /* out (optional): n */
 } VrfTrackOut;
 
 /*
@@ -153,15 +167,43 @@ int vrf_tracker_read_image_batch(vrf_handle *h, int n, const int32_t *seqs,
                                  const double *cur_times, const double *relative_Rs /* n*9 or NULL */,
                                  const int32_t *pub_flags, VrfTrackOut *outs);
 
+/* RGB-D form of the batched call: additionally takes the depth frame that the nodelet pairs with every
+ * image (estimator_nodelet.cpp:206-225,380-383) and performs, on the device, the depth decode of
+ * process() (:512-533) and the per-feature lookup + DEPTH_MIN_DIST test of
+ * FeatureManager::addFeatureCheckParallax (feature_manager.cpp:71-80); results in
+ * VrfTrackOut::depth_mm / depth_keep.  depths[i] may be NULL (no depth message).  Depth frames are only
+ * consumed on publish frames (the reference only forwards a frame to the back end when PUB_THIS_FRAME,
+ * estimator_nodelet.cpp:336-384), so only those cross PCIe.  `depth_stride` in bytes (0 = tightly packed). */
+int vrf_tracker_read_rgbd_batch(vrf_handle *h, int n, const int32_t *seqs,
+                                const uint8_t *const *imgs, size_t stride, int fmt,
+                                const void *const *depths, size_t depth_stride, int depth_fmt,
+                                const double *cur_times, const double *relative_Rs,
+                                const int32_t *pub_flags, VrfTrackOut *outs);
+
+/* Pipelined form of vrf_tracker_read_rgbd_batch for throughput over many sequences: submit() enqueues the H2D
+ * copies (pinned host memory recommended), every front-end kernel and the D2H copy of the results, and returns
+ * without waiting; collect() blocks until the OLDEST submitted batch has finished and fills `outs` (same n / seqs
+ * as its submit).  Up to two batches may be in flight (submit k+1, then collect k): the next batch's frames cross
+ * PCIe while the current batch's kernels run.  submit() returns VRF_ERR_CAPACITY when two batches are already
+ * pending.  The host frame buffers must stay valid until the batch has been collected.  The optional
+ * parity/debug members of VrfTrackOut (predict_pts, lk_*, grids_*) reflect the latest submitted batch.
+ * (Reference analogue: the img_buf / feature_buf queues between the ROS callbacks, trackThread and
+ * processThread, estimator_nodelet.cpp:125-146,192-225,380-384.) */
+int vrf_tracker_submit_rgbd_batch(vrf_handle *h, int n, const int32_t *seqs,
+                                  const uint8_t *const *imgs, size_t stride, int fmt,
+                                  const void *const *depths, size_t depth_stride, int depth_fmt,
+                                  const double *cur_times, const double *relative_Rs,
+                                  const int32_t *pub_flags);
+int vrf_tracker_collect_batch(vrf_handle *h, int n, const int32_t *seqs, VrfTrackOut *outs);
+
 /* Device-resident form: `d_imgs` is a device pointer to n contiguous frames
  * (frame i at d_imgs + i*frame_bytes, rows tightly packed) already in HBM.
  * Enqueues the whole front end on the handle's stream and returns without
  * synchronising; results are fetched with vrf_tracker_fetch_batch().
- * `d_depth` is reserved for the device-side depth lookup of
- * FeatureManager::addFeatureCheckParallax (feature_manager.cpp:71-80) and must be NULL
- * in this version (VRF_ERR_UNSUPPORTED otherwise). */
+ * `d_depth` (may be NULL): n contiguous depth frames of format `depth_fmt` (VRF_DEPTH_*), frame i paired
+ * with image i; read on publish frames only (see vrf_tracker_read_rgbd_batch). */
 int vrf_tracker_enqueue_batch_dev(vrf_handle *h, int n, const int32_t *seqs,
-                                  const uint8_t *d_imgs, int fmt, const uint16_t *d_depth,
+                                  const uint8_t *d_imgs, int fmt, const void *d_depth, int depth_fmt,
                                   const double *cur_times, const double *relative_Rs,
                                   const int32_t *pub_flags);
 int vrf_tracker_fetch_batch(vrf_handle *h, int n, const int32_t *seqs, VrfTrackOut *outs);

@@ -133,6 +133,17 @@ int vrf_ba_solve(vrf_handle *h, int seq, const VrfBaProblem *prob, VrfBaResult *
 int vrf_ba_solve_batch(vrf_handle *h, int n, const int32_t *seqs,
                        const VrfBaProblem *probs, VrfBaResult *res);
 
+/* Pipelined form of vrf_ba_solve_batch for throughput over many sequences: submit() packs the problems, enqueues
+ * their upload, the solve + marginalization kernels and the result copy, and returns without waiting; collect()
+ * blocks until the OLDEST submitted batch has finished and fills `res` (same n / seqs as its submit).  Up to two
+ * batches may be in flight; because a sequence's next window is built from the results of its previous one
+ * (slideWindow + the new prior), the sequences of batches in flight must be disjoint (VRF_ERR_ARG otherwise) --
+ * which is the natural order: different sequences publish on different frames.  VRF_ERR_CAPACITY when two batches
+ * are already pending.  (Reference analogue: feature_buf between trackThread and processThread,
+ * estimator_nodelet.cpp:380-384,462-479.) */
+int vrf_ba_submit_batch(vrf_handle *h, int n, const int32_t *seqs, const VrfBaProblem *probs);
+int vrf_ba_collect_batch(vrf_handle *h, int n, const int32_t *seqs, VrfBaResult *res);
+
 /* Device-resident split form used for steady-state throughput measurement:
  * upload() packs and copies the problems to HBM once, enqueue() runs
  * solve + gauge fix + marginalization on the handle's stream without

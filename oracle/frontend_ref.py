@@ -427,3 +427,50 @@ class FeatureTrackerRef:
                                      self.cur_pts[j, 0], self.cur_pts[j, 1],
                                      self.pts_velocity[j, 0], self.pts_velocity[j, 1]], np.float64)
         return out
+
+
+# ---------------------------------------------------------------------------
+# Depth ingest: the step right after the front end.
+# ---------------------------------------------------------------------------
+def decode_depth(depth_msg, rows, cols):
+    """estimator_nodelet.cpp:512-533: no message -> zeros; 16UC1/mono16 -> shared as is;
+    32FC1 -> depth_32fc1.convertTo(depth_img, CV_16UC1, 1000).
+
+    cv2's Python API has no Mat::convertTo binding.  OpenCV's 32F->16U cvtScale works in float32:
+    saturate_cast<ushort>(cvRound(src * 1000.f)) with round-half-even, x86 out-of-int-range / NaN -> INT_MIN -> 0.
+    The same float pipeline is reachable as cv2.addWeighted(src, 1000, src, 0, 0, dtype=CV_16U), used here so that
+    the arithmetic is still executed by the real OpenCV; tests/test_oracle_frontend.py pins the numpy formula
+    against it (incl. NaN / inf / negative / > 65.535 m values)."""
+    if depth_msg is None:
+        return np.zeros((rows, cols), np.uint16)
+    if depth_msg.dtype == np.uint16:
+        return depth_msg
+    if depth_msg.dtype == np.float32:
+        return cv2.addWeighted(depth_msg, 1000.0, depth_msg, 0.0, 0.0, dtype=cv2.CV_16U)
+    raise ValueError("Unknown depth encoding!")
+
+
+def decode_depth_numpy(depth_32f):
+    """Inspectable spec of the 32FC1 branch of decode_depth (what the kernel implements per looked-up pixel)."""
+    t = depth_32f.astype(np.float32) * np.float32(1000.0)
+    with np.errstate(invalid="ignore"):
+        r = np.where((t >= np.float32(-2147483648.0)) & (t < np.float32(2147483648.0)), np.rint(t), -2147483648.0)
+    return np.clip(r, 0, 65535).astype(np.uint16)
+
+
+def depth_lookup(depth_img, cur_pts, depth_min_dist):
+    """FeatureManager::addFeatureCheckParallax, feature_manager.cpp:71-80, for every feature (u, v) = cur_pts[j]
+    (the map entries 3 and 4, estimator_nodelet.cpp:344-352):
+        pt_depth_mm = depth_img.at<unsigned short>((int)v, (int)u);  pt_depth_m = pt_depth_mm / 1000.0
+        erase the feature iff 0 < pt_depth_m < DEPTH_MIN_DIST
+    Returns (depth_mm u16 [n], keep u8 [n])."""
+    n = len(cur_pts)
+    mm = np.zeros(n, np.uint16)
+    keep = np.ones(n, np.uint8)
+    for j in range(n):
+        u, v = float(cur_pts[j][0]), float(cur_pts[j][1])
+        mm[j] = depth_img[int(v), int(u)]
+        d_m = float(mm[j]) / 1000.0
+        if 0 < d_m < depth_min_dist:
+            keep[j] = 0
+    return mm, keep

@@ -151,3 +151,36 @@ def test_window_not_full_has_no_prior():
     compare(sg, so, pb)
     assert sg.c.has_new_prior == so.c.has_new_prior == 0
     h.close()
+
+
+def test_ba_pipelined_submit_collect_equals_synchronous():
+    """vrf_ba_submit_batch / vrf_ba_collect_batch with two batches in flight (disjoint sequences) return exactly
+    what the synchronous batched call returns; overlapping sequences and a third submit are refused."""
+    cfg = make_cfg()
+    sims = [BP.WindowSimulator(40 + i, cfg, n_landmarks=40) for i in range(4)]
+    pbs = []
+    for sim in sims:
+        s0 = ba_ref.solve(cfg, sim.window(0)); sim.commit(0, s0)
+        pbs.append(sim.window(1))
+    h_sync = B.Handle(cfg, 4, 0)
+    ref = h_sync.ba_solve_batch([0, 1, 2, 3], pbs)
+    h = B.Handle(cfg, 4, 0)
+    grp = [np.array([0, 1], np.int32), np.array([2, 3], np.int32)]
+    pa, ra, sa = h.make_ba_batch(pbs[:2])
+    pb_, rb, sb_ = h.make_ba_batch(pbs[2:])
+    h.ba_submit_into(grp[0], pa)
+    assert h.lib.vrf_ba_submit_batch(h.h, 2, grp[0].ctypes.data, pa) == -1        # same sequences still in flight
+    h.ba_submit_into(grp[1], pb_)
+    assert h.lib.vrf_ba_submit_batch(h.h, 2, grp[1].ctypes.data, pb_) == -4       # pipeline full
+    h.ba_collect_into(grp[0], ra)
+    h.ba_collect_into(grp[1], rb)
+    for i, (res, sols) in enumerate([(ra, sa), (rb, sb_)]):
+        for j in range(2):
+            C.memmove(C.byref(sols[j].c), C.byref(res[j]), C.sizeof(B.VrfBaResult))
+            g, r = sols[j], ref[2 * i + j]
+            assert (g.c.iterations, g.c.successful_steps) == (r.c.iterations, r.c.successful_steps)
+            # (double atomics in the linearisation: summation order, hence the last bits, vary from run to run)
+            assert abs(g.c.final_cost - r.c.final_cost) <= 1e-10 * r.c.final_cost
+            assert np.abs(g.Ps - r.Ps).max() <= 1e-9 and np.abs(g.pose - r.pose).max() <= 1e-9
+            assert np.abs(g.lam[:pbs[2 * i + j].M] - r.lam[:pbs[2 * i + j].M]).max() <= 1e-9
+    h.close(); h_sync.close()

@@ -189,3 +189,119 @@ def test_textureless_and_reset():
     out = h.read_image(0, seq.frame(0)[1], 2.0, None, pub=True)
     assert out.n > 100 and out.ids.min() == 0 and out.ids.max() == out.n - 1
     h.close()
+
+
+@pytest.mark.parametrize("fmt", ["16UC1", "32FC1"])
+def test_rgbd_depth_lookup_bit_exact(fmt):
+    """depth decode (estimator_nodelet.cpp:512-533) + per-feature lookup and DEPTH_MIN_DIST test
+    (feature_manager.cpp:71-80) on the device vs the oracle: depth_mm and the keep flags bit-exact, on publish
+    frames; zeros on non-publish frames (no depth frame is consumed there)."""
+    from oracle.frontend_ref import decode_depth, depth_lookup
+    cam = synth.CamModel()
+    seq = synth.Sequence(77, cam)
+    cfg = binding.default_config(use_ransac=1, depth_min_dist=2.2)      # scene depth 1.5..4 m: both branches taken
+    h = binding.Handle(cfg, 1, 0)
+    ref = FeatureTrackerRef(FrontendConfig(use_ransac=1))
+    culled = kept = 0
+    for k in range(7):
+        rgbf, gray, dep = seq.frame(k)
+        if fmt == "32FC1":
+            depm = dep.astype(np.float32) / np.float32(1000.0)
+            if k == 3:
+                depm[::7, ::5] = np.nan
+                depm[1::7, ::5] = 1e7
+        else:
+            depm = dep
+        R = seq.relative_R(k)
+        pub = (k % 3 == 0)
+        out = h.read_rgbd(0, rgbf, depm, seq.time(k), R, pub=pub)
+        ref.read_image(gray, seq.time(k), R, pub_this_frame=pub)
+        check_frame(k, out, ref)
+        if pub:
+            mm, keep = depth_lookup(decode_depth(depm, cam.height, cam.width), ref.cur_pts, cfg.depth_min_dist)
+            assert np.array_equal(out.depth_mm, mm), k
+            assert np.array_equal(out.depth_keep, keep), k
+            culled += int((keep == 0).sum()); kept += int(keep.sum())
+        else:
+            assert not out.depth_mm.any() and out.depth_keep.all(), k
+    assert culled > 0 and kept > 0
+    h.close()
+
+
+def test_rgbd_batch_dev_depth():
+    """Device-resident RGB-D batch (vrf_tracker_enqueue_batch_dev with a depth batch) == per-sequence host calls."""
+    import torch
+    from oracle.frontend_ref import depth_lookup
+    cam = synth.CamModel()
+    S = 3
+    seqs = [synth.Sequence(200 + s, cam) for s in range(S)]
+    cfg = binding.default_config(use_ransac=1, depth_min_dist=2.0)
+    h = binding.Handle(cfg, S, 0)
+    refs = [FeatureTrackerRef(FrontendConfig(use_ransac=1)) for _ in range(S)]
+    for k in range(4):
+        fr = [s.frame(k) for s in seqs]
+        rgb = torch.from_numpy(np.stack([f[0] for f in fr])).cuda()
+        dep = torch.from_numpy(np.stack([f[2] for f in fr]).view(np.int16)).cuda()
+        Rs = np.stack([s.relative_R(k) for s in seqs])
+        pubs = [1 if (k + s) % 2 == 0 else 0 for s in range(S)]
+        h.enqueue_dev(list(range(S)), rgb.data_ptr(), binding.FMT_RGB8, [seqs[0].time(k)] * S, Rs, pubs,
+                      d_depth=dep.data_ptr(), depth_fmt=binding.DEPTH_16UC1)
+        outs = h.fetch(list(range(S)))
+        for s in range(S):
+            refs[s].read_image(fr[s][1], seqs[0].time(k), Rs[s], pub_this_frame=bool(pubs[s]))
+            assert np.array_equal(outs[s].ids, np.asarray(refs[s].ids, np.int32)), (k, s)
+            if pubs[s]:
+                mm, keep = depth_lookup(fr[s][2], refs[s].cur_pts, cfg.depth_min_dist)
+                assert np.array_equal(outs[s].depth_mm, mm) and np.array_equal(outs[s].depth_keep, keep), (k, s)
+            else:
+                assert not outs[s].depth_mm.any(), (k, s)
+    h.close()
+
+
+def test_pipelined_submit_collect_equals_synchronous_calls():
+    """vrf_tracker_submit_rgbd_batch / vrf_tracker_collect_batch with two batches in flight return exactly what the
+    synchronous batched call returns (same ids, tracks, depths), and a third submit without a collect is refused."""
+    import ctypes as C
+    cam = synth.CamModel()
+    S, T = 3, 6
+    seqs = [synth.Sequence(300 + s, cam) for s in range(S)]
+    frames = [[sq.frame(k) for k in range(T)] for sq in seqs]
+    cfg = binding.default_config(use_ransac=1, depth_min_dist=2.0)
+    h_sync = binding.Handle(cfg, S, 0)
+    h_pipe = binding.Handle(cfg, S, 0)
+    seq_a = np.arange(S, dtype=np.int32)
+
+    def args(k):
+        ptrs = (C.c_void_p * S)(*[frames[s][k][0].ctypes.data for s in range(S)])
+        dptrs = (C.c_void_p * S)(*[frames[s][k][2].ctypes.data for s in range(S)])
+        t_a = np.full(S, seqs[0].time(k), np.float64)
+        R_a = np.ascontiguousarray(np.stack([seqs[s].relative_R(k) for s in range(S)]).reshape(S, 9))
+        p_a = np.asarray([1 if (k + s) % 3 == 0 else 0 for s in range(S)], np.int32)
+        return ptrs, dptrs, t_a, R_a, p_a
+
+    expect = []
+    for k in range(T):
+        ptrs, dptrs, t_a, R_a, p_a = args(k)
+        outs, res = h_sync.make_track_batch(S)
+        h_sync.read_image_batch_into(seq_a, ptrs, binding.FMT_RGB8, t_a, R_a, p_a, outs, dptrs=dptrs, dfmt=binding.DEPTH_16UC1)
+        expect.append([(r.finish().ids.copy(), r.cur_pts.copy(), r.cur_un_pts.copy(), r.pts_velocity.copy(),
+                        r.track_cnt.copy(), r.depth_mm.copy(), r.depth_keep.copy()) for r in res])
+    keep_alive = []
+    a0 = args(0); keep_alive.append(a0)
+    h_pipe.submit_batch_into(seq_a, a0[0], binding.FMT_RGB8, a0[2], a0[3], a0[4], dptrs=a0[1], dfmt=binding.DEPTH_16UC1)
+    for k in range(T):
+        if k + 1 < T:
+            a = args(k + 1); keep_alive.append(a)
+            h_pipe.submit_batch_into(seq_a, a[0], binding.FMT_RGB8, a[2], a[3], a[4], dptrs=a[1], dfmt=binding.DEPTH_16UC1)
+            if k == 0:      # two batches pending: a third submit must be refused, not queued
+                rc = h_pipe.lib.vrf_tracker_submit_rgbd_batch(h_pipe.h, S, seq_a.ctypes.data, C.cast(a[0], C.c_void_p), 0,
+                                                              binding.FMT_RGB8, None, 0, 0, a[2].ctypes.data, a[3].ctypes.data, a[4].ctypes.data)
+                assert rc == -4
+        outs, res = h_pipe.make_track_batch(S)
+        h_pipe.collect_batch_into(seq_a, outs)
+        for s in range(S):
+            r = res[s].finish()
+            e = expect[k][s]
+            for got, want in zip((r.ids, r.cur_pts, r.cur_un_pts, r.pts_velocity, r.track_cnt, r.depth_mm, r.depth_keep), e):
+                assert np.array_equal(got, want), (k, s)
+    h_sync.close(); h_pipe.close()

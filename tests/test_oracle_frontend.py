@@ -157,3 +157,28 @@ def test_oracle_tracker_runs_and_ids_are_unique():
     p = np.rint(ft.cur_pts)
     d2 = ((p[:, None, :] - p[None, :, :]) ** 2).sum(-1) + np.eye(len(p)) * 1e9
     assert len(ft.ids) > 100
+
+
+def test_depth_decode_32fc1_spec_matches_opencv_float_pipeline():
+    """estimator_nodelet.cpp:523-527 (convertTo(CV_16UC1, 1000)): the numpy spec the kernel follows equals OpenCV's
+    float32 scale + saturate_cast<ushort> pipeline, incl. NaN / inf / negative / out-of-range inputs."""
+    from oracle.frontend_ref import decode_depth, decode_depth_numpy
+    rng = np.random.default_rng(5)
+    d = (rng.random((480, 640)).astype(np.float32) * 12.0 - 1.0)
+    d[0, :8] = [np.nan, np.inf, -np.inf, 1e8, -5.0, 70.0, 3e6, 65.535]
+    d[1, :4] = [0.0005, 0.0015, 0.0025, 65.5355]           # half-way cases (round half to even)
+    assert np.array_equal(decode_depth(d, 480, 640), decode_depth_numpy(d))
+    assert decode_depth(None, 4, 6).shape == (4, 6) and not decode_depth(None, 4, 6).any()
+    u16 = rng.integers(0, 65535, (4, 6)).astype(np.uint16)
+    assert decode_depth(u16, 4, 6) is u16
+
+
+def test_depth_lookup_truncates_and_culls():
+    """feature_manager.cpp:71-80: (int) truncation of (v, u); 0 < d < DEPTH_MIN_DIST is erased, 0 (invalid) is kept."""
+    from oracle.frontend_ref import depth_lookup
+    dep = np.zeros((10, 12), np.uint16)
+    dep[3, 5] = 299; dep[3, 6] = 300; dep[4, 5] = 0; dep[4, 6] = 4000
+    pts = np.array([[5.99, 3.99], [6.0, 3.5], [5.5, 4.2], [6.9, 4.9]], np.float32)
+    mm, keep = depth_lookup(dep, pts, 0.3)
+    assert mm.tolist() == [299, 300, 0, 4000]
+    assert keep.tolist() == [0, 1, 1, 1]

@@ -2,6 +2,7 @@
 // host bookkeeping, and the front-end entry points.  Host code stays thin C++;
 // all arithmetic of the hot path runs in the kernels of frontend_kernels.cu /
 // ransac_kernels.cu / ba_kernels.cu.  There is no CPU fallback.
+#include <stdlib.h>
 #include <new>
 #include <string>
 #include <vector>
@@ -43,6 +44,7 @@ extern "C" void vrf_config_default(VrfConfig *c)
     c->num_iterations = 8; c->estimate_extrinsic = 0; c->estimate_td = 0; c->fix_depth = 0;
     c->depth_max_dist = 10.0; c->g_norm = 9.81;
     c->acc_n = 0.1; c->acc_w = 0.001; c->gyr_n = 0.01; c->gyr_w = 0.0001;
+    c->depth_min_dist = 0.3;      // config/realsense/vio.yaml: depth_min_dist
 }
 
 extern "C" const char *vrf_strerror(int code)
@@ -112,6 +114,7 @@ static int build_front_cfg(const VrfConfig &cfg, FrontCfg &fc)
     fc.ik22 = 1.0 / cfg.fy; fc.ik23 = -cfg.cy / cfg.fy;
     fc.nodist = (cfg.k1 == 0.0 && cfg.k2 == 0.0 && cfg.p1 == 0.0 && cfg.p2 == 0.0);
     fc.focal = cfg.focal_length; fc.f_thr = cfg.f_threshold;
+    fc.depth_min_dist = cfg.depth_min_dist;
     return VRF_OK;
 }
 
@@ -136,9 +139,14 @@ extern "C" int vrf_create(const VrfConfig *cfg, int n_seq, int device, vrf_handl
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return fail(VRF_ERR_CUDA);
     h->sm_count = prop.multiProcessorCount;
     if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) return fail(VRF_ERR_CUDA);
-    if (cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking) != cudaSuccess) return fail(VRF_ERR_CUDA);
-    for (int k = 0; k < VRF_COPY_CHUNKS; ++k)
-        if (cudaEventCreateWithFlags(&h->copy_ev[k], cudaEventDisableTiming) != cudaSuccess) return fail(VRF_ERR_CUDA);
+    for (int k = 0; k < VRF_COPY_STREAMS; ++k)
+        if (cudaStreamCreateWithFlags(&h->copy_stream[k], cudaStreamNonBlocking) != cudaSuccess) return fail(VRF_ERR_CUDA);
+    for (int p = 0; p < VRF_PIPE_DEPTH; ++p) {
+        for (int k = 0; k < VRF_COPY_CHUNKS; ++k)
+            for (int q = 0; q < VRF_COPY_STREAMS; ++q)
+                if (cudaEventCreateWithFlags(&h->copy_ev[p][k][q], cudaEventDisableTiming) != cudaSuccess) return fail(VRF_ERR_CUDA);
+        if (cudaEventCreateWithFlags(&h->pipe_done[p], cudaEventDisableTiming) != cudaSuccess) return fail(VRF_ERR_CUDA);
+    }
     const size_t S = n_seq, SC = S * VRF_CAP, SG = S * VRF_MAX_CELLS;
     FrontDev &d = h->fd;
     cudaError_t e = cudaSuccess;
@@ -150,11 +158,16 @@ extern "C" int vrf_create(const VrfConfig *cfg, int n_seq, int device, vrf_handl
     A(d.unstable, SC); A(d.n_unstable, S); A(d.maskpts, 2 * SC); A(d.n_maskpts, S);
     A(d.grid_cnt, SG); A(d.tex_status, SG); A(d.cell_k, SG);
     A(d.cand, SG * fc.kmax * 3); A(d.ncand, SG);
-    A(d.o_pts, SC); A(d.o_un, SC); A(d.o_vel, SC); A(d.o_ids, SC); A(d.o_cnt, SC); A(d.out_hdr, S * 8);
+    {   // result arrays [batch][out_pitch]: the publish logic adds at most kmax features per selected cell
+        int w = 2 * cfg->max_cnt + fc.kmax * fc.ncells;
+        h->out_w = d.out_pitch = w > VRF_CAP ? VRF_CAP : w;
+    }
+    const size_t SW = S * d.out_pitch;
+    A(d.o_pts, SW); A(d.o_un, SW); A(d.o_vel, SW); A(d.o_ids, SW); A(d.o_cnt, SW); A(d.out_hdr, S * 8);
+    A(d.o_depth, SW); A(d.o_dkeep, SW);
     A(d.work_prefix, VRF_MAX_BATCH + 1);
     for (int k = 0; k < VRF_CALL_SLOTS; ++k) { A(h->d_calls_ring[k], S); }
     h->frame_bytes_max = (size_t)cfg->row * cfg->col * 3;
-    A(h->d_stage, S * h->frame_bytes_max);
 #undef A
     if (e != cudaSuccess) { snprintf(h->errbuf, sizeof(h->errbuf), "alloc: %s", cudaGetErrorString(e)); return fail(VRF_ERR_CUDA); }
     if (cudaMemset(d.tex_status, 1, SG) != cudaSuccess) return fail(VRF_ERR_CUDA);   // grids_texture_status = true
@@ -163,8 +176,7 @@ extern "C" int vrf_create(const VrfConfig *cfg, int n_seq, int device, vrf_handl
         if (cudaEventCreateWithFlags(&h->call_ev[k], cudaEventDisableTiming) != cudaSuccess) return fail(VRF_ERR_CUDA);
     }
     if (cudaMallocHost((void **)&h->h_hdr, S * 8 * sizeof(int)) != cudaSuccess) return fail(VRF_ERR_CUDA);
-    const size_t out_elems = SC;
-    if (cudaMallocHost((void **)&h->h_out, out_elems * (3 * sizeof(float2) + 2 * sizeof(int))) != cudaSuccess) return fail(VRF_ERR_CUDA);
+    if (cudaMallocHost((void **)&h->h_out, SW * (3 * sizeof(float2) + 2 * sizeof(int) + sizeof(uint16_t) + sizeof(uint8_t))) != cudaSuccess) return fail(VRF_ERR_CUDA);
     h->cur_buf.assign(n_seq, 0);
     h->has_img.assign(n_seq, 0);
     h->prev_time.assign(n_seq, 0.0);
@@ -180,14 +192,16 @@ extern "C" void vrf_destroy(vrf_handle *h)
 {
     if (!h) return;
     cudaSetDevice(h->device);
-    if (h->copy_stream) cudaStreamSynchronize(h->copy_stream);
+    for (int k = 0; k < VRF_COPY_STREAMS; ++k) if (h->copy_stream[k]) cudaStreamSynchronize(h->copy_stream[k]);
     if (h->stream) cudaStreamSynchronize(h->stream);
     ba_destroy(h);
     FrontDev &d = h->fd;
     void *ptrs[] = {d.pyr[0], d.pyr[1], d.cur_pts, d.prev_un, d.ids, d.cnt, d.n_pts, d.n_id, d.pred_pts, d.lk_pts,
                     d.lk_status, d.n_lk, d.t_prev, d.t_forw, d.t_prevun, d.t_ids, d.t_cnt, d.t_n, d.t_keep,
                     d.unstable, d.n_unstable, d.maskpts, d.n_maskpts, d.grid_cnt, d.tex_status, d.cell_k, d.cand,
-                    d.ncand, d.o_pts, d.o_un, d.o_vel, d.o_ids, d.o_cnt, d.out_hdr, d.work_prefix, h->d_stage};
+                    d.ncand, d.o_pts, d.o_un, d.o_vel, d.o_ids, d.o_cnt, d.out_hdr, d.work_prefix,
+                    d.o_depth, d.o_dkeep, h->d_stage[0], h->d_stage[1], h->d_stage_depth[0], h->d_stage_depth[1]};
+    static_assert(VRF_PIPE_DEPTH == 2, "staging slots listed explicitly above");
     for (void *p : ptrs) if (p) cudaFree(p);
     for (int k = 0; k < VRF_CALL_SLOTS; ++k) {
         if (h->d_calls_ring[k]) cudaFree(h->d_calls_ring[k]);
@@ -196,8 +210,14 @@ extern "C" void vrf_destroy(vrf_handle *h)
     }
     if (h->h_hdr) cudaFreeHost(h->h_hdr);
     if (h->h_out) cudaFreeHost(h->h_out);
-    for (int k = 0; k < VRF_COPY_CHUNKS; ++k) if (h->copy_ev[k]) cudaEventDestroy(h->copy_ev[k]);
-    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+    for (int p = 0; p < VRF_PIPE_DEPTH; ++p) {
+        for (int k = 0; k < VRF_COPY_CHUNKS; ++k)
+            for (int q = 0; q < VRF_COPY_STREAMS; ++q) if (h->copy_ev[p][k][q]) cudaEventDestroy(h->copy_ev[p][k][q]);
+        if (h->pipe_done[p]) cudaEventDestroy(h->pipe_done[p]);
+        if (h->h_pipe_hdr[p]) cudaFreeHost(h->h_pipe_hdr[p]);
+        if (h->h_pipe_out[p]) cudaFreeHost(h->h_pipe_out[p]);
+    }
+    for (int k = 0; k < VRF_COPY_STREAMS; ++k) if (h->copy_stream[k]) cudaStreamDestroy(h->copy_stream[k]);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
 }
@@ -226,8 +246,12 @@ extern "C" int vrf_reset_sequence(vrf_handle *h, int seq)
 // Fill the per-call descriptors, upload them and enqueue every front-end kernel.
 // `out_base`: batch position of item 0 (a host-frame batch is enqueued in chunks; outputs are indexed by
 // batch position so that one fetch collects the whole batch).
+// Depth: `d_depth` = batch of depth planes (`depth_frame_bytes` each, format `depth_fmt`); `dslots` (may be NULL =
+// item i uses plane i) gives the plane index of every item, -1 = none.
 static int enqueue_front(vrf_handle *h, int n, const int32_t *seqs, const uint8_t *d_frames, size_t frame_bytes,
-                         int fmt, const double *times, const double *Rs, const int32_t *pubs, int out_base = 0)
+                         int fmt, const double *times, const double *Rs, const int32_t *pubs, int out_base = 0,
+                         const uint8_t *d_depth = nullptr, size_t depth_frame_bytes = 0, int depth_fmt = VRF_DEPTH_NONE,
+                         const int *dslots = nullptr)
 {
     if (n < 1 || out_base < 0 || out_base + n > h->n_seq || !seqs || !times) return VRF_ERR_ARG;
     if (fmt != VRF_FMT_GRAY8 && fmt != VRF_FMT_RGB8) return VRF_ERR_ARG;
@@ -250,7 +274,7 @@ static int enqueue_front(vrf_handle *h, int n, const int32_t *seqs, const uint8_
         // (first frame: cur_img = forw_img = img, feature_tracker.cpp:279-287)
         c.buf_prev = h->cur_buf[s];
         c.buf_cur = c.first ? h->cur_buf[s] : 1 - h->cur_buf[s];
-        c.pad = 0;
+        c.dslot = (d_depth && depth_fmt != VRF_DEPTH_NONE) ? (dslots ? dslots[i] : i) : -1;
         c.dt = times[i] - h->prev_time[s];
         for (int k = 0; k < 9; ++k) c.R[k] = Rs ? Rs[(size_t)i * 9 + k] : ((k % 4 == 0) ? 1.0 : 0.0);
     }
@@ -258,11 +282,12 @@ static int enqueue_front(vrf_handle *h, int n, const int32_t *seqs, const uint8_
     CK(cudaEventRecord(h->call_ev[slot], h->stream));
     LaunchCtx lc{h->stream, &h->launches, &h->prof};
     FrontDev fd = h->fd;
-    fd.o_pts += (size_t)out_base * VRF_CAP; fd.o_un += (size_t)out_base * VRF_CAP; fd.o_vel += (size_t)out_base * VRF_CAP;
-    fd.o_ids += (size_t)out_base * VRF_CAP; fd.o_cnt += (size_t)out_base * VRF_CAP; fd.out_hdr += (size_t)out_base * 8;
+    const size_t ob = (size_t)out_base * fd.out_pitch;
+    fd.o_pts += ob; fd.o_un += ob; fd.o_vel += ob; fd.o_ids += ob; fd.o_cnt += ob; fd.o_depth += ob; fd.o_dkeep += ob;
+    fd.out_hdr += (size_t)out_base * 8;
     front_launch(h->fc, h->d_calls, n, fd, d_frames, frame_bytes, fmt, any_pub, h->sm_count, lc);
     if (h->fc.use_ransac && any_pub) ransac_launch(h->fc, h->d_calls, n, fd, lc);
-    front_launch_tail(h->fc, h->d_calls, n, fd, any_pub, lc);
+    front_launch_tail(h->fc, h->d_calls, n, fd, any_pub, d_depth, depth_frame_bytes, depth_fmt, lc);
     CK(cudaGetLastError());
     for (int i = 0; i < n; ++i) {
         int s = seqs[i];
@@ -274,47 +299,53 @@ static int enqueue_front(vrf_handle *h, int n, const int32_t *seqs, const uint8_
     return VRF_OK;
 }
 
-// Two-phase copy-out: headers first (n per item), then only the used prefix of
-// each output array with one strided copy per array.
-static int fetch_front(vrf_handle *h, int n, const int32_t *seqs, VrfTrackOut *outs)
+// Result copy of a batch: headers + the [n][out_pitch] prefix of every output array, one contiguous transfer each,
+// stream-ordered behind the kernels.  Host layout: the seven arrays back to back.
+static int enqueue_result_copy(vrf_handle *h, int n, int *hdr_dst, void *out_dst)
 {
-    if (!outs || n < 1 || n > h->n_seq) return VRF_ERR_ARG;
     FrontDev &d = h->fd;
-    CK(cudaMemcpyAsync(h->h_hdr, d.out_hdr, (size_t)n * 8 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
-    int maxn = 0;
-    for (int i = 0; i < n; ++i) maxn = h->h_hdr[i * 8] > maxn ? h->h_hdr[i * 8] : maxn;
-    if (maxn > VRF_CAP) maxn = VRF_CAP;
-    // host staging layout: 5 arrays of [n][maxn]
-    char *hp = (char *)h->h_out;
-    float2 *h_pts = (float2 *)hp; hp += (size_t)n * maxn * sizeof(float2);
-    float2 *h_un = (float2 *)hp; hp += (size_t)n * maxn * sizeof(float2);
-    float2 *h_vel = (float2 *)hp; hp += (size_t)n * maxn * sizeof(float2);
-    int *h_ids = (int *)hp; hp += (size_t)n * maxn * sizeof(int);
-    int *h_cnt = (int *)hp;
-    if (maxn > 0) {
-        CK(cudaMemcpy2DAsync(h_pts, maxn * sizeof(float2), d.o_pts, VRF_CAP * sizeof(float2), maxn * sizeof(float2), n, cudaMemcpyDeviceToHost, h->stream));
-        CK(cudaMemcpy2DAsync(h_un, maxn * sizeof(float2), d.o_un, VRF_CAP * sizeof(float2), maxn * sizeof(float2), n, cudaMemcpyDeviceToHost, h->stream));
-        CK(cudaMemcpy2DAsync(h_vel, maxn * sizeof(float2), d.o_vel, VRF_CAP * sizeof(float2), maxn * sizeof(float2), n, cudaMemcpyDeviceToHost, h->stream));
-        CK(cudaMemcpy2DAsync(h_ids, maxn * sizeof(int), d.o_ids, VRF_CAP * sizeof(int), maxn * sizeof(int), n, cudaMemcpyDeviceToHost, h->stream));
-        CK(cudaMemcpy2DAsync(h_cnt, maxn * sizeof(int), d.o_cnt, VRF_CAP * sizeof(int), maxn * sizeof(int), n, cudaMemcpyDeviceToHost, h->stream));
-        CK(cudaStreamSynchronize(h->stream));
-    }
+    const size_t nw = (size_t)n * h->out_w;
+    char *hp = (char *)out_dst;
+    CK(cudaMemcpyAsync(hdr_dst, d.out_hdr, (size_t)n * 8 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+#define OUT1D(src, T) CK(cudaMemcpyAsync(hp, src, nw * sizeof(T), cudaMemcpyDeviceToHost, h->stream)); hp += nw * sizeof(T)
+    OUT1D(d.o_pts, float2); OUT1D(d.o_un, float2); OUT1D(d.o_vel, float2); OUT1D(d.o_ids, int); OUT1D(d.o_cnt, int);
+    OUT1D(d.o_depth, uint16_t); OUT1D(d.o_dkeep, uint8_t);
+#undef OUT1D
+    return VRF_OK;
+}
+
+static int unpack_results(vrf_handle *h, int n, const int32_t *seqs, VrfTrackOut *outs, const int *hdrs, const void *out_src)
+{
+    FrontDev &d = h->fd;
+    const int w = h->out_w;
+    const size_t nw = (size_t)n * w;
+    const char *hp = (const char *)out_src;
+    const float2 *h_pts = (const float2 *)hp; hp += nw * sizeof(float2);
+    const float2 *h_un = (const float2 *)hp; hp += nw * sizeof(float2);
+    const float2 *h_vel = (const float2 *)hp; hp += nw * sizeof(float2);
+    const int *h_ids = (const int *)hp; hp += nw * sizeof(int);
+    const int *h_cnt = (const int *)hp; hp += nw * sizeof(int);
+    const uint16_t *h_dep = (const uint16_t *)hp; hp += nw * sizeof(uint16_t);
+    const uint8_t *h_dkeep = (const uint8_t *)hp;
     int worst = VRF_OK;
     for (int i = 0; i < n; ++i) {
         VrfTrackOut &o = outs[i];
-        const int *hdr = h->h_hdr + i * 8;
+        const int *hdr = hdrs + i * 8;
         const int s = seqs[i];
         o.n = hdr[0]; o.n_id = hdr[1]; o.n_predict = hdr[2]; o.n_unstable = hdr[3]; o.status = hdr[4];
         if (o.status != 0) worst = o.status;
         int m = o.n < o.capacity ? o.n : o.capacity;
         if (o.n > o.capacity) { o.status = VRF_ERR_CAPACITY; worst = VRF_ERR_CAPACITY; }
-        if (o.cur_pts) memcpy(o.cur_pts, h_pts + (size_t)i * maxn, m * sizeof(float2));
-        if (o.cur_un_pts) memcpy(o.cur_un_pts, h_un + (size_t)i * maxn, m * sizeof(float2));
-        if (o.pts_velocity) memcpy(o.pts_velocity, h_vel + (size_t)i * maxn, m * sizeof(float2));
-        if (o.ids) memcpy(o.ids, h_ids + (size_t)i * maxn, m * sizeof(int));
-        if (o.track_cnt) memcpy(o.track_cnt, h_cnt + (size_t)i * maxn, m * sizeof(int));
-        // optional parity/debug members (per-sequence copies; not on the fast path)
+        if (m > w) m = w;
+        if (o.cur_pts) memcpy(o.cur_pts, h_pts + (size_t)i * w, m * sizeof(float2));
+        if (o.cur_un_pts) memcpy(o.cur_un_pts, h_un + (size_t)i * w, m * sizeof(float2));
+        if (o.pts_velocity) memcpy(o.pts_velocity, h_vel + (size_t)i * w, m * sizeof(float2));
+        if (o.ids) memcpy(o.ids, h_ids + (size_t)i * w, m * sizeof(int));
+        if (o.track_cnt) memcpy(o.track_cnt, h_cnt + (size_t)i * w, m * sizeof(int));
+        if (o.depth_mm) memcpy(o.depth_mm, h_dep + (size_t)i * w, m * sizeof(uint16_t));
+        if (o.depth_keep) memcpy(o.depth_keep, h_dkeep + (size_t)i * w, m);
+        // optional parity/debug members: read from the per-sequence state, i.e. only meaningful while no later
+        // batch has been submitted (per-sequence copies; not on the fast path)
         int np = o.n_predict < o.capacity ? o.n_predict : o.capacity;
         if (o.predict_pts && np > 0) CK(cudaMemcpy(o.predict_pts, d.pred_pts + (size_t)s * VRF_CAP, np * sizeof(float2), cudaMemcpyDeviceToHost));
         if (o.lk_pts && np > 0) CK(cudaMemcpy(o.lk_pts, d.lk_pts + (size_t)s * VRF_CAP, np * sizeof(float2), cudaMemcpyDeviceToHost));
@@ -325,12 +356,31 @@ static int fetch_front(vrf_handle *h, int n, const int32_t *seqs, VrfTrackOut *o
     return worst;
 }
 
-extern "C" int vrf_tracker_read_image_batch(vrf_handle *h, int n, const int32_t *seqs, const uint8_t *const *imgs,
-                                            size_t stride, int fmt, const double *cur_times,
-                                            const double *relative_Rs, const int32_t *pub_flags, VrfTrackOut *outs)
+static int fetch_front(vrf_handle *h, int n, const int32_t *seqs, VrfTrackOut *outs)
 {
-    if (!h || !imgs || !outs) return VRF_ERR_ARG;
+    if (!outs || n < 1 || n > h->n_seq) return VRF_ERR_ARG;
+    int rc = enqueue_result_copy(h, n, h->h_hdr, h->h_out);
+    if (rc != VRF_OK) return rc;
+    CK(cudaStreamSynchronize(h->stream));
+    return unpack_results(h, n, seqs, outs, h->h_hdr, h->h_out);
+}
+
+// Bytes per result entry of the fixed-width copy: cur_pts, cur_un_pts, pts_velocity (float2), ids, track_cnt (int),
+// depth_mm (u16), depth_keep (u8).
+static const size_t kOutEntryBytes = 3 * sizeof(float2) + 2 * sizeof(int) + sizeof(uint16_t) + sizeof(uint8_t);
+
+extern "C" int vrf_tracker_submit_rgbd_batch(vrf_handle *h, int n, const int32_t *seqs, const uint8_t *const *imgs,
+                                             size_t stride, int fmt, const void *const *depths, size_t depth_stride,
+                                             int depth_fmt, const double *cur_times, const double *relative_Rs,
+                                             const int32_t *pub_flags)
+{
+    if (!h || !imgs || !seqs || !cur_times) return VRF_ERR_ARG;
     if (n < 1 || n > h->n_seq) return VRF_ERR_ARG;
+    if (fmt != VRF_FMT_GRAY8 && fmt != VRF_FMT_RGB8) return VRF_ERR_ARG;
+    if (depth_fmt != VRF_DEPTH_NONE && depth_fmt != VRF_DEPTH_16UC1 && depth_fmt != VRF_DEPTH_32FC1) return VRF_ERR_ARG;
+    if (!depths) depth_fmt = VRF_DEPTH_NONE;
+    const int slot = (int)(h->pipe_submit % VRF_PIPE_DEPTH);
+    if (h->pipe_busy[slot]) return VRF_ERR_CAPACITY;          // VRF_PIPE_DEPTH batches already in flight: collect first
     CK(cudaSetDevice(h->device));
     const int bpp = (fmt == VRF_FMT_RGB8) ? 3 : 1;
     const size_t row_bytes = (size_t)h->cfg.col * bpp;
@@ -344,25 +394,109 @@ extern "C" int vrf_tracker_read_image_batch(vrf_handle *h, int n, const int32_t 
             seen[seqs[i]] = 1;
         }
     }
-    // The batch is cut into chunks: chunk c+1's frames cross PCIe on the copy stream while chunk c's
-    // kernels run, so a call costs about max(H2D, kernels) instead of their sum.
-    int nchunk = n / 48;
-    nchunk = nchunk < 1 ? 1 : (nchunk > VRF_COPY_CHUNKS ? VRF_COPY_CHUNKS : nchunk);
+    // ---- lazily allocated staging / result buffers of this pipeline slot ----
+    if (!h->d_stage[slot]) CK(cudaMalloc((void **)&h->d_stage[slot], (size_t)h->n_seq * h->frame_bytes_max));
+    if (!h->h_pipe_hdr[slot]) CK(cudaMallocHost((void **)&h->h_pipe_hdr[slot], (size_t)h->n_seq * 8 * sizeof(int)));
+    if (!h->h_pipe_out[slot]) CK(cudaMallocHost(&h->h_pipe_out[slot], (size_t)h->n_seq * h->out_w * kOutEntryBytes));
+    const size_t drow = (size_t)h->cfg.col * (depth_fmt == VRF_DEPTH_32FC1 ? 4 : 2);
+    const size_t dframe = drow * h->cfg.row;
+    if (depth_fmt != VRF_DEPTH_NONE) {
+        if (depth_stride == 0) depth_stride = drow;
+        if (depth_stride < drow) return VRF_ERR_ARG;
+        if (h->stage_depth_bytes[slot] < (size_t)h->n_seq * dframe) {       // sized for the widest format seen
+            CK(cudaStreamSynchronize(h->stream));
+            if (h->d_stage_depth[slot]) CK(cudaFree(h->d_stage_depth[slot]));
+            h->d_stage_depth[slot] = nullptr; h->stage_depth_bytes[slot] = 0;
+            CK(cudaMalloc((void **)&h->d_stage_depth[slot], (size_t)h->n_seq * dframe));
+            h->stage_depth_bytes[slot] = (size_t)h->n_seq * dframe;
+        }
+    }
+    uint8_t *stage = h->d_stage[slot], *stage_d = h->d_stage_depth[slot];
+    std::vector<int> dslots(n, -1);
+    // Overlap of PCIe and kernels.  With another batch in flight (submit k+1 before collect k) the next batch's
+    // frames already cross PCIe while this batch's kernels run, and the batch is enqueued in one piece (measured on
+    // B200: cutting it up only multiplies the latency-bound small kernels, 3.5 -> 6.1 ms per 444 frames).  A lone
+    // batch is cut into a few chunks so that chunk c+1's frames are copied while chunk c's kernels run.
+    const bool other_in_flight = h->pipe_busy[(slot + 1) % VRF_PIPE_DEPTH];
+    int nchunk = other_in_flight ? 1 : n / 96;
+    nchunk = nchunk < 1 ? 1 : (nchunk > 4 ? 4 : nchunk);
+    if (getenv("VRF_DEBUG_CHUNKS")) nchunk = atoi(getenv("VRF_DEBUG_CHUNKS"));
+    auto bail = [&](int rc) {
+        for (int q = 0; q < VRF_COPY_STREAMS; ++q) cudaStreamSynchronize(h->copy_stream[q]);
+        cudaStreamSynchronize(h->stream);
+        return rc;
+    };
+    static const int dbg_skip = getenv("VRF_DEBUG_SKIP") ? atoi(getenv("VRF_DEBUG_SKIP")) : 0;   // 1: no H2D, 2: no kernels
     for (int c = 0; c < nchunk; ++c) {
         const int i0 = (int)((long long)n * c / nchunk), i1 = (int)((long long)n * (c + 1) / nchunk);
         for (int i = i0; i < i1; ++i) {
+            if (dbg_skip == 1) break;
+            static const int dbg_ncs = getenv("VRF_DEBUG_COPY_STREAMS") ? atoi(getenv("VRF_DEBUG_COPY_STREAMS")) : VRF_COPY_STREAMS;
+            cudaStream_t cs = h->copy_stream[i % dbg_ncs];
             if (stride == row_bytes)
-                CK(cudaMemcpyAsync(h->d_stage + (size_t)i * frame_bytes, imgs[i], frame_bytes, cudaMemcpyHostToDevice, h->copy_stream));
+                CK(cudaMemcpyAsync(stage + (size_t)i * frame_bytes, imgs[i], frame_bytes, cudaMemcpyHostToDevice, cs));
             else
-                CK(cudaMemcpy2DAsync(h->d_stage + (size_t)i * frame_bytes, row_bytes, imgs[i], stride, row_bytes, h->cfg.row, cudaMemcpyHostToDevice, h->copy_stream));
+                CK(cudaMemcpy2DAsync(stage + (size_t)i * frame_bytes, row_bytes, imgs[i], stride, row_bytes, h->cfg.row, cudaMemcpyHostToDevice, cs));
+            // the depth plane is only consumed on publish frames: only those cross PCIe
+            if (depth_fmt != VRF_DEPTH_NONE && depths[i] && (!pub_flags || pub_flags[i])) {
+                dslots[i] = i;
+                if (depth_stride == drow)
+                    CK(cudaMemcpyAsync(stage_d + (size_t)i * dframe, depths[i], dframe, cudaMemcpyHostToDevice, cs));
+                else
+                    CK(cudaMemcpy2DAsync(stage_d + (size_t)i * dframe, drow, depths[i], depth_stride, drow, h->cfg.row, cudaMemcpyHostToDevice, cs));
+            }
         }
-        CK(cudaEventRecord(h->copy_ev[c], h->copy_stream));
-        CK(cudaStreamWaitEvent(h->stream, h->copy_ev[c], 0));
-        int rc = enqueue_front(h, i1 - i0, seqs + i0, h->d_stage + (size_t)i0 * frame_bytes, frame_bytes, fmt, cur_times + i0,
-                               relative_Rs ? relative_Rs + (size_t)i0 * 9 : nullptr, pub_flags ? pub_flags + i0 : nullptr, i0);
-        if (rc != VRF_OK) { cudaStreamSynchronize(h->copy_stream); cudaStreamSynchronize(h->stream); return rc; }
+        for (int q = 0; q < VRF_COPY_STREAMS; ++q) {
+            CK(cudaEventRecord(h->copy_ev[slot][c][q], h->copy_stream[q]));
+            CK(cudaStreamWaitEvent(h->stream, h->copy_ev[slot][c][q], 0));
+        }
+        if (dbg_skip == 2) continue;
+        int rc = enqueue_front(h, i1 - i0, seqs + i0, stage + (size_t)i0 * frame_bytes, frame_bytes, fmt, cur_times + i0,
+                               relative_Rs ? relative_Rs + (size_t)i0 * 9 : nullptr, pub_flags ? pub_flags + i0 : nullptr, i0,
+                               depth_fmt != VRF_DEPTH_NONE ? stage_d : nullptr, dframe, depth_fmt, dslots.data() + i0);
+        if (rc != VRF_OK) return bail(rc);
     }
-    return fetch_front(h, n, seqs, outs);
+    {   // ---- results, stream-ordered behind the kernels ----
+        int rc = enqueue_result_copy(h, n, h->h_pipe_hdr[slot], h->h_pipe_out[slot]);
+        if (rc != VRF_OK) return bail(rc);
+    }
+    CK(cudaEventRecord(h->pipe_done[slot], h->stream));
+    h->pipe_busy[slot] = true; h->pipe_n[slot] = n;
+    h->pipe_submit++;
+    return VRF_OK;
+}
+
+extern "C" int vrf_tracker_collect_batch(vrf_handle *h, int n, const int32_t *seqs, VrfTrackOut *outs)
+{
+    if (!h || !outs || !seqs) return VRF_ERR_ARG;
+    const int slot = (int)(h->pipe_collect % VRF_PIPE_DEPTH);
+    if (!h->pipe_busy[slot] || h->pipe_n[slot] != n) return VRF_ERR_ARG;
+    CK(cudaSetDevice(h->device));
+    CK(cudaEventSynchronize(h->pipe_done[slot]));
+    h->pipe_busy[slot] = false;
+    h->pipe_collect++;
+    return unpack_results(h, n, seqs, outs, h->h_pipe_hdr[slot], h->h_pipe_out[slot]);
+}
+
+extern "C" int vrf_tracker_read_rgbd_batch(vrf_handle *h, int n, const int32_t *seqs, const uint8_t *const *imgs,
+                                           size_t stride, int fmt, const void *const *depths, size_t depth_stride,
+                                           int depth_fmt, const double *cur_times, const double *relative_Rs,
+                                           const int32_t *pub_flags, VrfTrackOut *outs)
+{
+    if (!h || !outs) return VRF_ERR_ARG;
+    if (h->pipe_submit != h->pipe_collect) return VRF_ERR_ARG;      // pipelined batches pending: collect them first
+    int rc = vrf_tracker_submit_rgbd_batch(h, n, seqs, imgs, stride, fmt, depths, depth_stride, depth_fmt, cur_times,
+                                           relative_Rs, pub_flags);
+    if (rc != VRF_OK) return rc;
+    return vrf_tracker_collect_batch(h, n, seqs, outs);
+}
+
+extern "C" int vrf_tracker_read_image_batch(vrf_handle *h, int n, const int32_t *seqs, const uint8_t *const *imgs,
+                                            size_t stride, int fmt, const double *cur_times,
+                                            const double *relative_Rs, const int32_t *pub_flags, VrfTrackOut *outs)
+{
+    return vrf_tracker_read_rgbd_batch(h, n, seqs, imgs, stride, fmt, nullptr, 0, VRF_DEPTH_NONE, cur_times, relative_Rs,
+                                       pub_flags, outs);
 }
 
 extern "C" int vrf_tracker_read_image(vrf_handle *h, int seq, const uint8_t *img, size_t stride, int fmt,
@@ -374,16 +508,20 @@ extern "C" int vrf_tracker_read_image(vrf_handle *h, int seq, const uint8_t *img
 }
 
 extern "C" int vrf_tracker_enqueue_batch_dev(vrf_handle *h, int n, const int32_t *seqs, const uint8_t *d_imgs, int fmt,
-                                             const uint16_t *d_depth, const double *cur_times,
+                                             const void *d_depth, int depth_fmt, const double *cur_times,
                                              const double *relative_Rs, const int32_t *pub_flags)
 {
     if (!h || !d_imgs) return VRF_ERR_ARG;
-    if (d_depth) return VRF_ERR_UNSUPPORTED;          // reserved
+    if (!d_depth) depth_fmt = VRF_DEPTH_NONE;
+    if (depth_fmt != VRF_DEPTH_NONE && depth_fmt != VRF_DEPTH_16UC1 && depth_fmt != VRF_DEPTH_32FC1) return VRF_ERR_ARG;
+    if (depth_fmt != VRF_DEPTH_NONE && ((uintptr_t)d_depth & 3) != 0) return VRF_ERR_ARG;
     CK(cudaSetDevice(h->device));
     const int bpp = (fmt == VRF_FMT_RGB8) ? 3 : 1;
     const size_t frame_bytes = (size_t)h->cfg.col * bpp * h->cfg.row;
     if (((uintptr_t)d_imgs & 15) != 0) return VRF_ERR_ARG;
-    return enqueue_front(h, n, seqs, d_imgs, frame_bytes, fmt, cur_times, relative_Rs, pub_flags);
+    const size_t dframe = (size_t)h->cfg.col * h->cfg.row * (depth_fmt == VRF_DEPTH_32FC1 ? 4 : 2);
+    return enqueue_front(h, n, seqs, d_imgs, frame_bytes, fmt, cur_times, relative_Rs, pub_flags, 0,
+                         (const uint8_t *)d_depth, dframe, depth_fmt, nullptr);
 }
 
 extern "C" int vrf_tracker_fetch_batch(vrf_handle *h, int n, const int32_t *seqs, VrfTrackOut *outs)

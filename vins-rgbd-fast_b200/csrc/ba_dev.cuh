@@ -46,6 +46,7 @@ struct BaProbDev {
     int *colmap;                          // [176] prior column -> tangent column (-1: constant block)
     // scratch / state
     double *lam, *clam;                   // current / candidate inverse depths
+    double *lam_out;                      // optimised inverse depths of this batch item (result copy)
     double *W;                            // [M][66]
     double *hll, *gl, *jscale_l, *diag_l, *gd_l, *gn_l, *u_l, *y_l, *hinv_l;
     double *imuS;                         // [10][225] sqrt information (upper)

@@ -22,17 +22,29 @@ struct BaHostPack {
     double obs[BA_MAX_OBS * 2];
 };
 
-struct BaState {
-    int n_seq = 0;
-    BaHostPack *h_pack = nullptr;       // pinned [n_seq]
-    BaHostPack *d_pack = nullptr;       // device [n_seq]
+#define BA_PIPE 2      // batches in flight (vrf_ba_submit_batch / vrf_ba_collect_batch)
+
+// Everything a batch in flight owns: pinned staging, its device mirror, the result buffers.  Two slots so that
+// batch k+1 can be packed and uploaded while batch k runs.
+struct BaSlot {
+    BaHostPack *h_pack = nullptr, *d_pack = nullptr;       // [n_seq]
     BaMeta *h_meta = nullptr, *d_meta = nullptr;
     BaProbDev *h_prob = nullptr, *d_prob = nullptr;
     BaOutDev *h_out = nullptr, *d_out = nullptr;
     BaMargDev *h_marg = nullptr, *d_marg = nullptr;
+    BaPriorStore *h_prior = nullptr;                       // pinned upload staging [n_seq]
+    double *h_lam = nullptr, *d_lam_out = nullptr;         // optimised inverse depths by batch position [n_seq][BA_MAX_LM]
+    cudaEvent_t done = nullptr;
+    bool busy = false;
+    std::vector<int> seqs;                                 // sequences of the batch this slot holds
+};
+
+struct BaState {
+    int n_seq = 0;
+    BaSlot slot[BA_PIPE];
+    unsigned n_submit = 0, n_collect = 0;
     BaPriorStore *d_prior[2] = {nullptr, nullptr};   // [n_seq] each; cur index per sequence below
-    BaPriorStore *h_prior = nullptr;                 // pinned staging [1]
-    double *h_lam = nullptr;                         // pinned staging [n_seq][BA_MAX_LM]
+    BaPriorStore *h_prior_dl = nullptr;              // pinned download staging [1]
     std::vector<int> prior_cur;                      // which store is "last_marginalization_info"
     std::vector<uint8_t> prior_valid;
     // per-sequence scratch
@@ -50,6 +62,27 @@ static const size_t kMargDoubles = (size_t)BA_MAX_POS * BA_MAX_POS + BA_MAX_POS 
 
 #define BCK(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { snprintf(h->errbuf, sizeof(h->errbuf), "%s:%d %s", __FILE__, __LINE__, cudaGetErrorString(e__)); return VRF_ERR_CUDA; } } while (0)
 
+static int slot_alloc(vrf_handle *h, BaSlot &sl)
+{
+    if (sl.h_pack) return VRF_OK;
+    const size_t S = h->n_seq;
+    BCK(cudaMallocHost((void **)&sl.h_pack, S * sizeof(BaHostPack)));
+    BCK(cudaMalloc((void **)&sl.d_pack, S * sizeof(BaHostPack)));
+    BCK(cudaMallocHost((void **)&sl.h_meta, S * sizeof(BaMeta)));
+    BCK(cudaMalloc((void **)&sl.d_meta, S * sizeof(BaMeta)));
+    BCK(cudaMallocHost((void **)&sl.h_prob, S * sizeof(BaProbDev)));
+    BCK(cudaMalloc((void **)&sl.d_prob, S * sizeof(BaProbDev)));
+    BCK(cudaMallocHost((void **)&sl.h_out, S * sizeof(BaOutDev)));
+    BCK(cudaMalloc((void **)&sl.d_out, S * sizeof(BaOutDev)));
+    BCK(cudaMallocHost((void **)&sl.h_marg, S * sizeof(BaMargDev)));
+    BCK(cudaMalloc((void **)&sl.d_marg, S * sizeof(BaMargDev)));
+    BCK(cudaMallocHost((void **)&sl.h_prior, S * sizeof(BaPriorStore)));
+    BCK(cudaMallocHost((void **)&sl.h_lam, S * BA_MAX_LM * sizeof(double)));
+    BCK(cudaMalloc((void **)&sl.d_lam_out, S * BA_MAX_LM * sizeof(double)));
+    BCK(cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming));
+    return VRF_OK;
+}
+
 int ba_create(vrf_handle *h)
 {
     BaState *b = new (std::nothrow) BaState();
@@ -57,22 +90,12 @@ int ba_create(vrf_handle *h)
     h->ba = b;
     const size_t S = h->n_seq;
     b->n_seq = h->n_seq;
-    BCK(cudaMallocHost((void **)&b->h_pack, S * sizeof(BaHostPack)));
-    BCK(cudaMalloc((void **)&b->d_pack, S * sizeof(BaHostPack)));
-    BCK(cudaMallocHost((void **)&b->h_meta, S * sizeof(BaMeta)));
-    BCK(cudaMalloc((void **)&b->d_meta, S * sizeof(BaMeta)));
-    BCK(cudaMallocHost((void **)&b->h_prob, S * sizeof(BaProbDev)));
-    BCK(cudaMalloc((void **)&b->d_prob, S * sizeof(BaProbDev)));
-    BCK(cudaMallocHost((void **)&b->h_out, S * sizeof(BaOutDev)));
-    BCK(cudaMalloc((void **)&b->d_out, S * sizeof(BaOutDev)));
-    BCK(cudaMallocHost((void **)&b->h_marg, S * sizeof(BaMargDev)));
-    BCK(cudaMalloc((void **)&b->d_marg, S * sizeof(BaMargDev)));
+    if (int rc = slot_alloc(h, b->slot[0])) return rc;        // slot 1 is allocated by the first pipelined submit
     for (int k = 0; k < 2; ++k) {
         BCK(cudaMalloc((void **)&b->d_prior[k], S * sizeof(BaPriorStore)));
         BCK(cudaMemset(b->d_prior[k], 0, S * sizeof(BaPriorStore)));
     }
-    BCK(cudaMallocHost((void **)&b->h_prior, (S + 1) * sizeof(BaPriorStore)));     // [0]: download staging, [1 + slot]: upload staging
-    BCK(cudaMallocHost((void **)&b->h_lam, S * BA_MAX_LM * sizeof(double)));
+    BCK(cudaMallocHost((void **)&b->h_prior_dl, sizeof(BaPriorStore)));
     BCK(cudaMalloc((void **)&b->d_lam, S * BA_MAX_LM * sizeof(double)));
     BCK(cudaMalloc((void **)&b->d_clam, S * BA_MAX_LM * sizeof(double)));
     BCK(cudaMalloc((void **)&b->d_W, S * BA_MAX_LM * 66 * sizeof(double)));
@@ -92,11 +115,17 @@ void ba_destroy(vrf_handle *h)
 {
     BaState *b = h->ba;
     if (!b) return;
-    void *dev[] = {b->d_pack, b->d_meta, b->d_prob, b->d_out, b->d_marg, b->d_prior[0], b->d_prior[1], b->d_lam, b->d_clam,
+    void *dev[] = {b->d_prior[0], b->d_prior[1], b->d_lam, b->d_clam,
                    b->d_W, b->d_vecs, b->d_imuS, b->d_HP, b->d_colmap, b->d_margbuf, b->d_lmcol};
     for (void *p : dev) if (p) cudaFree(p);
-    void *host[] = {b->h_pack, b->h_meta, b->h_prob, b->h_out, b->h_marg, b->h_prior, b->h_lam};
-    for (void *p : host) if (p) cudaFreeHost(p);
+    if (b->h_prior_dl) cudaFreeHost(b->h_prior_dl);
+    for (BaSlot &sl : b->slot) {
+        void *sdev[] = {sl.d_pack, sl.d_meta, sl.d_prob, sl.d_out, sl.d_marg, sl.d_lam_out};
+        for (void *p : sdev) if (p) cudaFree(p);
+        void *host[] = {sl.h_pack, sl.h_meta, sl.h_prob, sl.h_out, sl.h_marg, sl.h_prior, sl.h_lam};
+        for (void *p : host) if (p) cudaFreeHost(p);
+        if (sl.done) cudaEventDestroy(sl.done);
+    }
     delete b;
     h->ba = nullptr;
 }
@@ -109,7 +138,7 @@ int ba_reset_sequence(vrf_handle *h, int seq)
     return VRF_OK;
 }
 
-static int pack_problem(vrf_handle *h, int slot, int seq, const VrfBaProblem *pb)
+static int pack_problem(vrf_handle *h, BaSlot &sl, int slot, int seq, const VrfBaProblem *pb)
 {
     BaState *b = h->ba;
     if (!pb || pb->n_landmarks < 0 || pb->n_landmarks > BA_MAX_LM || pb->n_obs > BA_MAX_OBS) return VRF_ERR_CAPACITY;
@@ -117,7 +146,7 @@ static int pack_problem(vrf_handle *h, int slot, int seq, const VrfBaProblem *pb
     if (!pb->ex_constant || !pb->td_constant) return VRF_ERR_UNSUPPORTED;     // estimate_extrinsic / estimate_td: later rounds
     if (pb->n_landmarks > 0 && (!pb->para_Feature || !pb->lm_start_frame || !pb->lm_estimate_flag || !pb->lm_obs_ptr || !pb->obs_pts)) return VRF_ERR_ARG;
     if (pb->use_imu && !pb->imu) return VRF_ERR_ARG;
-    BaHostPack &k = b->h_pack[slot];
+    BaHostPack &k = sl.h_pack[slot];
     memcpy(k.pose, pb->para_Pose, sizeof(k.pose));
     memcpy(k.sb, pb->para_SpeedBias, sizeof(k.sb));
     memcpy(k.ex, pb->para_Ex_Pose, sizeof(k.ex));
@@ -137,7 +166,7 @@ static int pack_problem(vrf_handle *h, int slot, int seq, const VrfBaProblem *pb
     if (k.obs_ptr[M] != pb->n_obs) return VRF_ERR_ARG;
     memcpy(k.obs, pb->obs_pts, sizeof(double) * 2 * pb->n_obs);
 
-    BaMeta &mt = b->h_meta[slot];
+    BaMeta &mt = sl.h_meta[slot];
     memset(&mt, 0, sizeof(mt));
     mt.M = M; mt.nobs = pb->n_obs; mt.nframes = pb->frame_count + 1; mt.use_imu = pb->use_imu;
     mt.frame_count = pb->frame_count;
@@ -157,7 +186,7 @@ static int pack_problem(vrf_handle *h, int slot, int seq, const VrfBaProblem *pb
     else if (pb->prior) {
         const VrfPrior *P = pb->prior;
         if (P->n < 0 || P->n > VRF_PRIOR_MAX_DIM || P->n_blocks > VRF_PRIOR_MAX_BLOCKS) return VRF_ERR_ARG;
-        BaPriorStore *hp = b->h_prior + 1 + slot;      // per-slot pinned staging (upload() synchronised the stream before packing)
+        BaPriorStore *hp = sl.h_prior + slot;          // per-problem pinned staging (the slot is idle while it is packed)
         hp->n = P->n; hp->n_blocks = P->n_blocks; hp->valid = 1; hp->pad = 0;
         for (int q = 0; q < P->n_blocks; ++q) {
             hp->kind[q] = P->blocks[q].kind; hp->index[q] = P->blocks[q].index; hp->size[q] = P->blocks[q].size; hp->idx[q] = P->blocks[q].idx;
@@ -173,8 +202,8 @@ static int pack_problem(vrf_handle *h, int slot, int seq, const VrfBaProblem *pb
     } else b->prior_valid[seq] = 0;
     mt.has_prior = have_prior;
 
-    BaProbDev &pd = b->h_prob[slot];
-    BaHostPack *dp = b->d_pack + slot;
+    BaProbDev &pd = sl.h_prob[slot];
+    BaHostPack *dp = sl.d_pack + slot;
     pd.pose0 = dp->pose; pd.sb0 = dp->sb; pd.ex0 = dp->ex; pd.lam0 = dp->lam;
     pd.start = dp->start; pd.obs_ptr = dp->obs_ptr; pd.lm_const = dp->lm_const; pd.lm_ub = dp->lm_ub; pd.obs = dp->obs; pd.imu = dp->imu;
     pd.prior = have_prior ? b->d_prior[b->prior_cur[seq]] + seq : nullptr;
@@ -182,6 +211,7 @@ static int pack_problem(vrf_handle *h, int slot, int seq, const VrfBaProblem *pb
     pd.HP = b->d_HP + (size_t)seq * VRF_PRIOR_MAX_DIM * VRF_PRIOR_MAX_DIM;
     pd.colmap = b->d_colmap + (size_t)seq * VRF_PRIOR_MAX_DIM;
     pd.lam = b->d_lam + (size_t)seq * BA_MAX_LM;
+    pd.lam_out = sl.d_lam_out + (size_t)slot * BA_MAX_LM;
     pd.clam = b->d_clam + (size_t)seq * BA_MAX_LM;
     pd.W = b->d_W + (size_t)seq * BA_MAX_LM * 66;
     double *v = b->d_vecs + (size_t)seq * 9 * BA_MAX_LM;
@@ -189,7 +219,7 @@ static int pack_problem(vrf_handle *h, int slot, int seq, const VrfBaProblem *pb
     pd.gn_l = v + 5 * BA_MAX_LM; pd.u_l = v + 6 * BA_MAX_LM; pd.y_l = v + 7 * BA_MAX_LM; pd.hinv_l = v + 8 * BA_MAX_LM;
     pd.imuS = b->d_imuS + (size_t)seq * (BA_NF - 1) * 225;
 
-    BaMargDev &mg = b->h_marg[slot];
+    BaMargDev &mg = sl.h_marg[slot];
     double *mb = b->d_margbuf + (size_t)seq * kMargDoubles;
     const size_t mmx = 15 + BA_MAX_M0;
     mg.A = mb; mb += (size_t)BA_MAX_POS * BA_MAX_POS;
@@ -205,53 +235,61 @@ static int pack_problem(vrf_handle *h, int slot, int seq, const VrfBaProblem *pb
     return VRF_OK;
 }
 
-static int upload(vrf_handle *h, int n, const int32_t *seqs, const VrfBaProblem *probs)
+// pack + upload one batch into pipeline slot `sl` (which must be idle)
+static int upload(vrf_handle *h, BaSlot &sl, int n, const int32_t *seqs, const VrfBaProblem *probs)
 {
     BaState *b = h->ba;
     if (!b || n < 1 || n > h->n_seq || !seqs || !probs) return VRF_ERR_ARG;
     BCK(cudaSetDevice(h->device));
-    BCK(cudaStreamSynchronize(h->stream));          // pinned staging reuse
+    if (int rc = slot_alloc(h, sl)) return rc;
     std::vector<uint8_t> seen(h->n_seq, 0);
     for (int i = 0; i < n; ++i) {
         if (seqs[i] < 0 || seqs[i] >= h->n_seq || seen[seqs[i]]) return VRF_ERR_ARG;
         seen[seqs[i]] = 1;
-        int rc = pack_problem(h, i, seqs[i], &probs[i]);
+    }
+    // a sequence's window k+1 is built from the results of window k: batches in flight must be disjoint
+    for (BaSlot &o : b->slot)
+        if (&o != &sl && o.busy)
+            for (int q : o.seqs) if (seen[q]) return VRF_ERR_ARG;
+    for (int i = 0; i < n; ++i) {
+        int rc = pack_problem(h, sl, i, seqs[i], &probs[i]);
         if (rc != VRF_OK) return rc;
     }
     // one contiguous copy of the n packed problems (pinned staging -> HBM); far cheaper than per-array copies
-    BCK(cudaMemcpyAsync(b->d_pack, b->h_pack, (size_t)n * sizeof(BaHostPack), cudaMemcpyHostToDevice, h->stream));
-    BCK(cudaMemcpyAsync(b->d_meta, b->h_meta, n * sizeof(BaMeta), cudaMemcpyHostToDevice, h->stream));
-    BCK(cudaMemcpyAsync(b->d_prob, b->h_prob, n * sizeof(BaProbDev), cudaMemcpyHostToDevice, h->stream));
-    BCK(cudaMemcpyAsync(b->d_marg, b->h_marg, n * sizeof(BaMargDev), cudaMemcpyHostToDevice, h->stream));
-    b->last_slots.assign(seqs, seqs + n);
+    BCK(cudaMemcpyAsync(sl.d_pack, sl.h_pack, (size_t)n * sizeof(BaHostPack), cudaMemcpyHostToDevice, h->stream));
+    BCK(cudaMemcpyAsync(sl.d_meta, sl.h_meta, n * sizeof(BaMeta), cudaMemcpyHostToDevice, h->stream));
+    BCK(cudaMemcpyAsync(sl.d_prob, sl.h_prob, n * sizeof(BaProbDev), cudaMemcpyHostToDevice, h->stream));
+    BCK(cudaMemcpyAsync(sl.d_marg, sl.h_marg, n * sizeof(BaMargDev), cudaMemcpyHostToDevice, h->stream));
+    sl.seqs.assign(seqs, seqs + n);
     return VRF_OK;
 }
 
-static int enqueue(vrf_handle *h, int n)
+static int enqueue(vrf_handle *h, BaSlot &sl, int n)
 {
-    BaState *b = h->ba;
     LaunchCtx lc{h->stream, &h->launches, &h->prof};
-    if (ba_solve_launch(b->d_meta, b->d_prob, b->d_out, n, lc) != 0) return VRF_ERR_CUDA;
-    if (ba_marg_launch(b->d_meta, b->d_prob, b->d_out, b->d_marg, n, lc) != 0) return VRF_ERR_CUDA;
+    if (ba_solve_launch(sl.d_meta, sl.d_prob, sl.d_out, n, lc) != 0) return VRF_ERR_CUDA;
+    if (ba_marg_launch(sl.d_meta, sl.d_prob, sl.d_out, sl.d_marg, n, lc) != 0) return VRF_ERR_CUDA;
     BCK(cudaGetLastError());
     return VRF_OK;
 }
 
-static int download(vrf_handle *h, int n, const int32_t *seqs, VrfBaResult *res)
+// result copy of a batch, stream-ordered behind its kernels; `done` marks its completion
+static int enqueue_download(vrf_handle *h, BaSlot &sl, int n, bool want_lam)
+{
+    BCK(cudaMemcpyAsync(sl.h_out, sl.d_out, n * sizeof(BaOutDev), cudaMemcpyDeviceToHost, h->stream));
+    if (want_lam)
+        BCK(cudaMemcpyAsync(sl.h_lam, sl.d_lam_out, (size_t)n * BA_MAX_LM * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    BCK(cudaEventRecord(sl.done, h->stream));
+    return VRF_OK;
+}
+
+static int finish_download(vrf_handle *h, BaSlot &sl, int n, const int32_t *seqs, VrfBaResult *res)
 {
     BaState *b = h->ba;
-    BCK(cudaMemcpyAsync(b->h_out, b->d_out, n * sizeof(BaOutDev), cudaMemcpyDeviceToHost, h->stream));
-    // inverse depths of all sequences of the batch in one strided copy (only the used prefix of each row)
-    int maxM = 0, lo = h->n_seq, hi = -1;
-    for (int i = 0; i < n; ++i) { maxM = std::max(maxM, b->last_M[seqs[i]]); lo = std::min(lo, (int)seqs[i]); hi = std::max(hi, (int)seqs[i]); }
-    const bool want_lam = res != nullptr && maxM > 0;
-    if (want_lam)
-        BCK(cudaMemcpy2DAsync(b->h_lam, maxM * sizeof(double), b->d_lam + (size_t)lo * BA_MAX_LM, BA_MAX_LM * sizeof(double),
-                              maxM * sizeof(double), hi - lo + 1, cudaMemcpyDeviceToHost, h->stream));
-    BCK(cudaStreamSynchronize(h->stream));
+    BCK(cudaEventSynchronize(sl.done));
     int worst = VRF_OK;
     for (int i = 0; i < n; ++i) {
-        const BaOutDev &o = b->h_out[i];
+        const BaOutDev &o = sl.h_out[i];
         const int seq = seqs[i];
         if (o.has_new_prior) { b->prior_cur[seq] = 1 - b->prior_cur[seq]; b->prior_valid[seq] = 1; }
         if (!res) continue;
@@ -264,9 +302,10 @@ static int download(vrf_handle *h, int n, const int32_t *seqs, VrfBaResult *res)
         memcpy(r.Bas, o.Bas, sizeof(o.Bas)); memcpy(r.Bgs, o.Bgs, sizeof(o.Bgs));
         r.has_new_prior = o.has_new_prior;
         if (r.para_Feature && b->last_M[seq] > 0)
-            memcpy(r.para_Feature, b->h_lam + (size_t)(seq - lo) * maxM, sizeof(double) * b->last_M[seq]);
+            memcpy(r.para_Feature, sl.h_lam + (size_t)i * BA_MAX_LM, sizeof(double) * b->last_M[seq]);
         if (o.has_new_prior && r.new_prior) {
-            BaPriorStore *hp = b->h_prior;
+            // (the store just produced is only read, never written, by the one later batch that may be in flight)
+            BaPriorStore *hp = b->h_prior_dl;
             const BaPriorStore *src = b->d_prior[b->prior_cur[seq]] + seq;
             BCK(cudaMemcpy(hp, src, offsetof(BaPriorStore, J0), cudaMemcpyDeviceToHost));
             const int nn = hp->n;
@@ -290,7 +329,7 @@ long ba_debug_prof(vrf_handle *h, int slot, void *dst, size_t bytes)
     BaState *b = h->ba;
     if (!b || slot < 0 || slot >= h->n_seq || bytes < sizeof(long long) * 20) return VRF_ERR_ARG;
     BaOutDev tmp;
-    if (cudaMemcpy(&tmp, b->d_out + slot, sizeof(BaOutDev), cudaMemcpyDeviceToHost) != cudaSuccess) return VRF_ERR_CUDA;
+    if (cudaMemcpy(&tmp, b->slot[0].d_out + slot, sizeof(BaOutDev), cudaMemcpyDeviceToHost) != cudaSuccess) return VRF_ERR_CUDA;
     long long o[20];
     memcpy(o, tmp.prof, sizeof(long long) * 8);
     memcpy(o + 8, tmp.prof2, sizeof(long long) * 8);
@@ -303,34 +342,70 @@ long ba_debug_prof(vrf_handle *h, int slot, void *dst, size_t bytes)
 
 using namespace vrf;
 
+static bool pipe_idle(const BaState *b) { return b->n_submit == b->n_collect; }
+
+// The split device-resident form works on pipeline slot 0 and requires an empty pipeline.
 extern "C" int vrf_ba_upload_batch(vrf_handle *h, int n, const int32_t *seqs, const VrfBaProblem *probs)
 {
-    if (!h) return VRF_ERR_ARG;
-    return upload(h, n, seqs, probs);
+    if (!h || !h->ba || !pipe_idle(h->ba)) return VRF_ERR_ARG;
+    if (cudaSetDevice(h->device) != cudaSuccess) return VRF_ERR_CUDA;
+    if (cudaStreamSynchronize(h->stream) != cudaSuccess) return VRF_ERR_CUDA;      // pinned staging reuse
+    return upload(h, h->ba->slot[0], n, seqs, probs);
 }
 
 extern "C" int vrf_ba_enqueue_batch(vrf_handle *h, int n, const int32_t *seqs)
 {
-    if (!h || !h->ba || !seqs || n < 1 || n != (int)h->ba->last_slots.size()) return VRF_ERR_ARG;
+    if (!h || !h->ba || !seqs || n < 1 || !pipe_idle(h->ba) || n != (int)h->ba->slot[0].seqs.size()) return VRF_ERR_ARG;
     if (cudaSetDevice(h->device) != cudaSuccess) return VRF_ERR_CUDA;
-    return enqueue(h, n);
+    return enqueue(h, h->ba->slot[0], n);
 }
 
 extern "C" int vrf_ba_download_batch(vrf_handle *h, int n, const int32_t *seqs, VrfBaResult *res)
 {
-    if (!h || !h->ba || !seqs || n < 1 || n != (int)h->ba->last_slots.size()) return VRF_ERR_ARG;
+    if (!h || !h->ba || !seqs || n < 1 || !pipe_idle(h->ba) || n != (int)h->ba->slot[0].seqs.size()) return VRF_ERR_ARG;
     if (cudaSetDevice(h->device) != cudaSuccess) return VRF_ERR_CUDA;
-    return download(h, n, seqs, res);
+    int rc = enqueue_download(h, h->ba->slot[0], n, res != nullptr);
+    if (rc != VRF_OK) return rc;
+    return finish_download(h, h->ba->slot[0], n, seqs, res);
+}
+
+extern "C" int vrf_ba_submit_batch(vrf_handle *h, int n, const int32_t *seqs, const VrfBaProblem *probs)
+{
+    if (!h || !h->ba) return VRF_ERR_ARG;
+    BaState *b = h->ba;
+    BaSlot &sl = b->slot[b->n_submit % BA_PIPE];
+    if (sl.busy) return VRF_ERR_CAPACITY;             // BA_PIPE batches already in flight: collect first
+    int rc = upload(h, sl, n, seqs, probs);
+    if (rc != VRF_OK) return rc;
+    rc = enqueue(h, sl, n);
+    if (rc != VRF_OK) return rc;
+    rc = enqueue_download(h, sl, n, true);
+    if (rc != VRF_OK) return rc;
+    sl.busy = true;
+    b->n_submit++;
+    return VRF_OK;
+}
+
+extern "C" int vrf_ba_collect_batch(vrf_handle *h, int n, const int32_t *seqs, VrfBaResult *res)
+{
+    if (!h || !h->ba || !seqs) return VRF_ERR_ARG;
+    BaState *b = h->ba;
+    BaSlot &sl = b->slot[b->n_collect % BA_PIPE];
+    if (!sl.busy || n != (int)sl.seqs.size()) return VRF_ERR_ARG;
+    for (int i = 0; i < n; ++i) if (seqs[i] != sl.seqs[i]) return VRF_ERR_ARG;
+    if (cudaSetDevice(h->device) != cudaSuccess) return VRF_ERR_CUDA;
+    int rc = finish_download(h, sl, n, seqs, res);
+    sl.busy = false;
+    b->n_collect++;
+    return rc;
 }
 
 extern "C" int vrf_ba_solve_batch(vrf_handle *h, int n, const int32_t *seqs, const VrfBaProblem *probs, VrfBaResult *res)
 {
-    if (!h) return VRF_ERR_ARG;
-    int rc = upload(h, n, seqs, probs);
+    if (!h || !h->ba || !pipe_idle(h->ba)) return VRF_ERR_ARG;
+    int rc = vrf_ba_submit_batch(h, n, seqs, probs);
     if (rc != VRF_OK) return rc;
-    rc = enqueue(h, n);
-    if (rc != VRF_OK) return rc;
-    return download(h, n, seqs, res);
+    return vrf_ba_collect_batch(h, n, seqs, res);
 }
 
 extern "C" int vrf_ba_solve(vrf_handle *h, int seq, const VrfBaProblem *prob, VrfBaResult *res)
@@ -338,4 +413,3 @@ extern "C" int vrf_ba_solve(vrf_handle *h, int seq, const VrfBaProblem *prob, Vr
     int32_t s = seq;
     return vrf_ba_solve_batch(h, 1, &s, prob, res);
 }
-

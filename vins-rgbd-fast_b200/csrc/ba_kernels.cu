@@ -817,7 +817,7 @@ k_ba_solve(const BaMeta *metas, const BaProbDev *probs, BaOutDev *outs)
         } else for (int k = 3; k < 7; ++k) out.mex[k] = sh.ex[k];
     }
     // setDepth / getDepthVector round trip of the inverse depths (feature_manager.cpp:197-223,302-324)
-    for (int l = tid; l < M; l += BA_THREADS) { double depth = 1.0 / p.lam[l]; p.clam[l] = 1.0 / depth; }
+    for (int l = tid; l < M; l += BA_THREADS) { double depth = 1.0 / p.lam[l]; p.clam[l] = 1.0 / depth; p.lam_out[l] = p.lam[l]; }
     __syncthreads();
     // ---- outputs ----
     double nf_ = 0;

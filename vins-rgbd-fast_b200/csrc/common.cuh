@@ -29,6 +29,7 @@ struct FrontCfg {
     double fx, fy, cx, cy, k1, k2, p1, p2;
     double ik11, ik13, ik22, ik23;
     double focal, f_thr;
+    double depth_min_dist;
     int nodist;
 };
 
@@ -38,7 +39,7 @@ struct SeqCall {
     int pub;
     int buf_prev, buf_cur;      // which pyramid buffer holds cur_img / receives forw_img
     int first;                  // 1: no previous image (forw_img.empty())
-    int pad;
+    int dslot;                  // index of this item's depth frame in the depth batch, -1 = no depth frame
     double dt;                  // cur_time - prev_time
     double R[9];                // relative_R row-major
 };
@@ -67,9 +68,13 @@ struct FrontDev {
     int *cell_k;                // [S][cells]   K for selected cells, 0 otherwise
     float *cand;                // [S][cells][kmax][3] (x, y, response)
     int *ncand;                 // [S][cells]
-    // outputs, indexed by batch position (not by sequence id)
+    // outputs, indexed by batch position (not by sequence id): [batch][out_pitch] each, so that the result copy of
+    // a batch is one contiguous transfer per array
+    int out_pitch;
     float2 *o_pts, *o_un, *o_vel;
     int *o_ids, *o_cnt;
+    uint16_t *o_depth;          // depth_img.at<ushort>((int)v, (int)u) in mm
+    uint8_t *o_dkeep;           // 0: erased by the DEPTH_MIN_DIST test of addFeatureCheckParallax
     int *out_hdr;               // [batch][8]: n, n_id, n_predict, n_unstable, status
     int *work_prefix;           // [MAX_BATCH+1] prefix of LK work items for the current call
 };

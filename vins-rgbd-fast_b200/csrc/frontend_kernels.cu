@@ -915,8 +915,20 @@ k_fast(FrontCfg c, const SeqCall *calls, FrontDev d)
 // nodelet's updateID loop (estimator_nodelet.cpp:324-330), outputs.
 // One CTA (256 threads) per batch item.
 // ---------------------------------------------------------------------------
+// Depth: the nodelet's depth decode (estimator_nodelet.cpp:512-533) and the lookup
+// depth_img.at<unsigned short>((int)v, (int)u) + DEPTH_MIN_DIST test of FeatureManager::addFeatureCheckParallax
+// (feature_manager.cpp:71-80) are fused here: the 32FC1 -> 16UC1 convertTo(…, 1000) is elementwise, so only the
+// looked-up pixels are converted (float multiply, round-half-even, x86 out-of-range -> INT_MIN, saturate).
+__device__ __forceinline__ unsigned depth_mm_at(const uint8_t *plane, int fmt, int cols, int x, int y)
+{
+    if (fmt == VRF_DEPTH_16UC1) return __ldg(reinterpret_cast<const unsigned short *>(plane) + (size_t)y * cols + x);
+    const float t = __ldg(reinterpret_cast<const float *>(plane) + (size_t)y * cols + x) * 1000.0f;
+    const int r = (t >= -2147483648.0f && t < 2147483648.0f) ? __float2int_rn(t) : (int)0x80000000;
+    return (unsigned)min(max(r, 0), 65535);
+}
+
 __global__ void __launch_bounds__(256)
-k_finish(FrontCfg c, const SeqCall *calls, FrontDev d)
+k_finish(FrontCfg c, const SeqCall *calls, FrontDev d, const uint8_t *depth, size_t depth_frame_bytes, int depth_fmt)
 {
     __shared__ int2 s_acc[VRF_CAP];      // newly accepted centres
     __shared__ float2 s_new[VRF_CAP];
@@ -926,6 +938,8 @@ k_finish(FrontCfg c, const SeqCall *calls, FrontDev d)
     const int seq = call.seq;
     const size_t base = (size_t)seq * VRF_CAP;
     const int n = d.t_n[seq];
+    const uint8_t *dplane = (depth && depth_fmt != VRF_DEPTH_NONE && call.dslot >= 0 && call.pub)
+                                ? depth + (size_t)call.dslot * depth_frame_bytes : nullptr;
     if (threadIdx.x == 0) s_nnew = 0;
     __syncthreads();
     if (call.pub && threadIdx.x < 32) {
@@ -996,12 +1010,18 @@ k_finish(FrontCfg c, const SeqCall *calls, FrontDev d)
             d.ids[base + i] = id;
             d.cnt[base + i] = cnt;
             d.prev_un[base + i] = un;
-            const size_t ob = (size_t)blockIdx.x * VRF_CAP + i;
+            if (i >= d.out_pitch) continue;        // reported through the status word below
+            const size_t ob = (size_t)blockIdx.x * d.out_pitch + i;
             d.o_pts[ob] = p;
             d.o_un[ob] = un;
             d.o_vel[ob] = v;
             d.o_ids[ob] = id;
             d.o_cnt[ob] = cnt;
+            unsigned mm = 0;
+            if (dplane) mm = depth_mm_at(dplane, depth_fmt, c.cols, min(max((int)p.x, 0), c.cols - 1), min(max((int)p.y, 0), c.rows - 1));
+            const double dm = (double)mm / 1000.0;
+            d.o_depth[ob] = (unsigned short)mm;
+            d.o_dkeep[ob] = (0.0 < dm && dm < c.depth_min_dist) ? 0 : 1;
         }
     }
     if (threadIdx.x == 0) {
@@ -1012,7 +1032,7 @@ k_finish(FrontCfg c, const SeqCall *calls, FrontDev d)
         hdr[1] = n_id0 + totnew;
         hdr[2] = d.n_lk[seq];
         hdr[3] = d.n_unstable[seq];
-        hdr[4] = (n + nnew >= VRF_CAP) ? VRF_ERR_CAPACITY : 0;
+        hdr[4] = (n + nnew >= VRF_CAP || ntot > d.out_pitch) ? VRF_ERR_CAPACITY : 0;
     }
 }
 
@@ -1072,7 +1092,7 @@ int front_launch(const FrontCfg &c, const SeqCall *d_calls, int ncalls, const Fr
 }
 
 int front_launch_tail(const FrontCfg &c, const SeqCall *d_calls, int ncalls, const FrontDev &d, int any_pub,
-                      LaunchCtx &lc)
+                      const uint8_t *d_depth, size_t depth_frame_bytes, int depth_fmt, LaunchCtx &lc)
 {
     cudaStream_t st = lc.st;
     lc.begin(K_POST_B);
@@ -1085,7 +1105,7 @@ int front_launch_tail(const FrontCfg &c, const SeqCall *d_calls, int ncalls, con
         lc.end();
     }
     lc.begin(K_FINISH);
-    k_finish<<<ncalls, 256, 0, st>>>(c, d_calls, d);
+    k_finish<<<ncalls, 256, 0, st>>>(c, d_calls, d, d_depth, depth_frame_bytes, depth_fmt);
     lc.end();
     return 0;
 }

@@ -4,8 +4,10 @@
 
 #include "common.cuh"
 
-#define VRF_CALL_SLOTS 8
+#define VRF_CALL_SLOTS 32
 #define VRF_COPY_CHUNKS 8
+#define VRF_PIPE_DEPTH 2        // host-frame batches in flight (submit / collect)
+#define VRF_COPY_STREAMS 2      // H2D copies alternate over two streams to keep the copy engines busy
 
 namespace vrf {
 struct BaState;   // ba_host.cu
@@ -61,8 +63,8 @@ struct vrf_handle {
     int n_seq = 0, device = 0, sm_count = 0;
     cudaStream_t stream = nullptr;
     // host-frame path: H2D copies run on their own stream, chunk by chunk, ahead of the kernels
-    cudaStream_t copy_stream = nullptr;
-    cudaEvent_t copy_ev[VRF_COPY_CHUNKS] = {};
+    cudaStream_t copy_stream[VRF_COPY_STREAMS] = {};
+    cudaEvent_t copy_ev[VRF_PIPE_DEPTH][VRF_COPY_CHUNKS][VRF_COPY_STREAMS] = {};
     vrf::FrontDev fd = {};
     // per-call descriptor ring (host pinned + device) so that enqueue calls can be pipelined
     vrf::SeqCall *h_calls_ring[VRF_CALL_SLOTS] = {};
@@ -70,8 +72,19 @@ struct vrf_handle {
     cudaEvent_t call_ev[VRF_CALL_SLOTS] = {};
     unsigned call_ctr = 0;
     vrf::SeqCall *h_calls = nullptr, *d_calls = nullptr;   // slot in use by the current call
-    uint8_t *d_stage = nullptr;
+    // host-frame path (all lazily allocated): per pipeline slot a staging area for the frames and the publish
+    // frames' depth planes, and pinned buffers that receive the fixed-width result copy of the batch
+    uint8_t *d_stage[VRF_PIPE_DEPTH] = {};
     size_t frame_bytes_max = 0;
+    uint8_t *d_stage_depth[VRF_PIPE_DEPTH] = {};
+    size_t stage_depth_bytes[VRF_PIPE_DEPTH] = {};
+    int *h_pipe_hdr[VRF_PIPE_DEPTH] = {};
+    void *h_pipe_out[VRF_PIPE_DEPTH] = {};
+    cudaEvent_t pipe_done[VRF_PIPE_DEPTH] = {};
+    int pipe_n[VRF_PIPE_DEPTH] = {};
+    bool pipe_busy[VRF_PIPE_DEPTH] = {};
+    unsigned pipe_submit = 0, pipe_collect = 0;
+    int out_w = 0;                          // entries per sequence in the fixed-width result copy
     int *h_hdr = nullptr;
     void *h_out = nullptr;
     std::vector<int> cur_buf;
@@ -90,7 +103,7 @@ int front_configure_kernels(const FrontCfg &c);
 int front_launch(const FrontCfg &c, const SeqCall *d_calls, int ncalls, const FrontDev &d, const uint8_t *d_frames,
                  size_t frame_bytes, int fmt, int any_pub, int sm_count, LaunchCtx &lc);
 int front_launch_tail(const FrontCfg &c, const SeqCall *d_calls, int ncalls, const FrontDev &d, int any_pub,
-                      LaunchCtx &lc);
+                      const uint8_t *d_depth, size_t depth_frame_bytes, int depth_fmt, LaunchCtx &lc);
 // ransac_kernels.cu
 int ransac_launch(const FrontCfg &c, const SeqCall *d_calls, int ncalls, const FrontDev &d, LaunchCtx &lc);
 // ba_host.cu

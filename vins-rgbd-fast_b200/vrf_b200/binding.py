@@ -16,6 +16,7 @@ PRIOR_MAX_BLOCKS = 40
 PRIOR_MAX_DIM = 176
 
 FMT_GRAY8, FMT_RGB8 = 0, 1
+DEPTH_NONE, DEPTH_16UC1, DEPTH_32FC1 = 0, 1, 2
 MARGIN_OLD, MARGIN_SECOND_NEW = 0, 1
 BLK_POSE, BLK_SPEEDBIAS, BLK_EXPOSE, BLK_TD = 0, 1, 2, 3
 
@@ -32,6 +33,7 @@ class VrfConfig(C.Structure):
         ("num_iterations", C.c_int32), ("estimate_extrinsic", C.c_int32), ("estimate_td", C.c_int32),
         ("fix_depth", C.c_int32), ("depth_max_dist", C.c_double), ("g_norm", C.c_double),
         ("acc_n", C.c_double), ("acc_w", C.c_double), ("gyr_n", C.c_double), ("gyr_w", C.c_double),
+        ("depth_min_dist", C.c_double),
     ]
 
 
@@ -44,6 +46,7 @@ class VrfTrackOut(C.Structure):
         ("predict_pts", C.c_void_p), ("lk_pts", C.c_void_p), ("lk_status", C.c_void_p),
         ("grids_track_num", C.c_void_p), ("grids_texture_status", C.c_void_p),
         ("n_unstable", C.c_int32), ("status", C.c_int32),
+        ("depth_mm", C.c_void_p), ("depth_keep", C.c_void_p),
     ]
 
 
@@ -99,9 +102,10 @@ class VrfBaResult(C.Structure):
 EXPORTS = [
     "vrf_config_default", "vrf_create", "vrf_destroy", "vrf_strerror", "vrf_last_cuda_error",
     "vrf_launch_count", "vrf_reset_sequence", "vrf_tracker_read_image", "vrf_tracker_read_image_batch",
+    "vrf_tracker_read_rgbd_batch", "vrf_tracker_submit_rgbd_batch", "vrf_tracker_collect_batch",
     "vrf_tracker_enqueue_batch_dev", "vrf_tracker_fetch_batch", "vrf_synchronize", "vrf_stream",
     "vrf_profile_enable", "vrf_profile_read", "vrf_debug_sort_desc", "vrf_debug_read", "vrf_ba_solve", "vrf_ba_solve_batch", "vrf_ba_upload_batch",
-    "vrf_ba_enqueue_batch", "vrf_ba_download_batch",
+    "vrf_ba_enqueue_batch", "vrf_ba_download_batch", "vrf_ba_submit_batch", "vrf_ba_collect_batch",
 ]
 
 _lib = None
@@ -131,7 +135,13 @@ def load():
                                            C.c_void_p, C.c_int, C.POINTER(VrfTrackOut)]
     lib.vrf_tracker_read_image_batch.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int,
                                                  C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(VrfTrackOut)]
-    lib.vrf_tracker_enqueue_batch_dev.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
+    lib.vrf_tracker_read_rgbd_batch.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int,
+                                                C.c_void_p, C.c_size_t, C.c_int,
+                                                C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(VrfTrackOut)]
+    lib.vrf_tracker_submit_rgbd_batch.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int,
+                                                  C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.vrf_tracker_collect_batch.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.POINTER(VrfTrackOut)]
+    lib.vrf_tracker_enqueue_batch_dev.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int,
                                                   C.c_void_p, C.c_void_p, C.c_void_p]
     lib.vrf_tracker_fetch_batch.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.POINTER(VrfTrackOut)]
     lib.vrf_synchronize.argtypes = [C.c_void_p]
@@ -145,6 +155,8 @@ def load():
     lib.vrf_debug_read.restype = C.c_long
     lib.vrf_ba_solve.argtypes = [C.c_void_p, C.c_int, C.POINTER(VrfBaProblem), C.POINTER(VrfBaResult)]
     lib.vrf_ba_solve_batch.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.POINTER(VrfBaProblem), C.POINTER(VrfBaResult)]
+    lib.vrf_ba_submit_batch.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.POINTER(VrfBaProblem)]
+    lib.vrf_ba_collect_batch.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.POINTER(VrfBaResult)]
     lib.vrf_ba_upload_batch.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.POINTER(VrfBaProblem)]
     lib.vrf_ba_enqueue_batch.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
     lib.vrf_ba_download_batch.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.POINTER(VrfBaResult)]
@@ -194,6 +206,8 @@ class TrackResult:
         self._lkst = np.zeros(cap, np.uint8)
         self._grid = np.zeros(ncells, np.int32)
         self._tex = np.zeros(ncells, np.uint8)
+        self._dmm = np.zeros(cap, np.uint16)
+        self._dkeep = np.zeros(cap, np.uint8)
         self.debug = debug
 
     def fill(self, o: VrfTrackOut):
@@ -203,6 +217,8 @@ class TrackResult:
         o.pts_velocity = self._vel.ctypes.data
         o.ids = self._ids.ctypes.data
         o.track_cnt = self._cnt.ctypes.data
+        o.depth_mm = self._dmm.ctypes.data
+        o.depth_keep = self._dkeep.ctypes.data
         if self.debug:
             o.predict_pts = self._pred.ctypes.data
             o.lk_pts = self._lk.ctypes.data
@@ -220,6 +236,8 @@ class TrackResult:
         self.pts_velocity = self._vel[:n]
         self.ids = self._ids[:n]
         self.track_cnt = self._cnt[:n]
+        self.depth_mm = self._dmm[:n]
+        self.depth_keep = self._dkeep[:n]
         self.n_id = o.n_id
         self.n_predict = o.n_predict
         self.n_unstable = o.n_unstable
@@ -309,10 +327,25 @@ class Handle:
         check(rc, self.h)
         return res.finish()
 
-    def read_image_batch(self, seqs, imgs, times, Rs=None, pubs=None, debug=False):
+    def read_rgbd(self, seq, img, depth, t, R=None, pub=True, debug=True):
+        """readImage + the depth decode / per-feature depth lookup of the back end's ingest (one sequence)."""
+        return self.read_image_batch([seq], [img], [t], None if R is None else [R], [int(bool(pub))], debug=debug,
+                                     depths=[depth])[0]
+
+    def read_image_batch(self, seqs, imgs, times, Rs=None, pubs=None, debug=False, depths=None):
         n = len(seqs)
         imgs = [np.ascontiguousarray(im) for im in imgs]
         fmt = FMT_RGB8 if imgs[0].ndim == 3 else FMT_GRAY8
+        dfmt, dptr = DEPTH_NONE, None
+        if depths is not None:
+            depths = [None if dm is None else np.ascontiguousarray(dm) for dm in depths]
+            kinds = {dm.dtype for dm in depths if dm is not None}
+            if kinds:
+                (kind,) = kinds
+                dfmt = DEPTH_32FC1 if kind == np.float32 else DEPTH_16UC1
+                assert kind in (np.dtype(np.float32), np.dtype(np.uint16))
+                dptrs = (C.c_void_p * n)(*[None if dm is None else dm.ctypes.data for dm in depths])
+                dptr = C.cast(dptrs, C.c_void_p)
         seq_a = np.asarray(seqs, np.int32)
         ptrs = (C.c_void_p * n)(*[im.ctypes.data for im in imgs])
         t_a = np.asarray(times, np.float64)
@@ -322,8 +355,8 @@ class Handle:
         results = [TrackResult(self.ncells, debug) for _ in range(n)]
         for r, o in zip(results, outs):
             r.fill(o)
-        rc = self.lib.vrf_tracker_read_image_batch(
-            self.h, n, seq_a.ctypes.data, C.cast(ptrs, C.c_void_p), 0, fmt, t_a.ctypes.data,
+        rc = self.lib.vrf_tracker_read_rgbd_batch(
+            self.h, n, seq_a.ctypes.data, C.cast(ptrs, C.c_void_p), 0, fmt, dptr, 0, dfmt, t_a.ctypes.data,
             None if R_a is None else R_a.ctypes.data, None if p_a is None else p_a.ctypes.data, outs)
         check(rc, self.h)
         return [r.finish() for r in results]
@@ -374,11 +407,22 @@ class Handle:
             r.fill(o)
         return outs, results
 
-    def read_image_batch_into(self, seq_a, ptrs, fmt, t_a, R_a, p_a, outs):
-        """seq_a/t_a/R_a/p_a: contiguous numpy arrays, ptrs: (c_void_p * n) of host frame pointers."""
-        rc = self.lib.vrf_tracker_read_image_batch(self.h, len(seq_a), seq_a.ctypes.data, C.cast(ptrs, C.c_void_p), 0, fmt,
-                                                   t_a.ctypes.data, R_a.ctypes.data, p_a.ctypes.data, outs)
+    def read_image_batch_into(self, seq_a, ptrs, fmt, t_a, R_a, p_a, outs, dptrs=None, dfmt=DEPTH_NONE):
+        """seq_a/t_a/R_a/p_a: contiguous numpy arrays, ptrs / dptrs: (c_void_p * n) of host frame / depth-frame pointers."""
+        rc = self.lib.vrf_tracker_read_rgbd_batch(self.h, len(seq_a), seq_a.ctypes.data, C.cast(ptrs, C.c_void_p), 0, fmt,
+                                                  None if dptrs is None else C.cast(dptrs, C.c_void_p), 0, dfmt,
+                                                  t_a.ctypes.data, R_a.ctypes.data, p_a.ctypes.data, outs)
         return check(rc, self.h)
+
+    def submit_batch_into(self, seq_a, ptrs, fmt, t_a, R_a, p_a, dptrs=None, dfmt=DEPTH_NONE):
+        """Pipelined host-frame call (vrf_tracker_submit_rgbd_batch); pair with collect_batch_into()."""
+        rc = self.lib.vrf_tracker_submit_rgbd_batch(self.h, len(seq_a), seq_a.ctypes.data, C.cast(ptrs, C.c_void_p), 0, fmt,
+                                                    None if dptrs is None else C.cast(dptrs, C.c_void_p), 0, dfmt,
+                                                    t_a.ctypes.data, R_a.ctypes.data, p_a.ctypes.data)
+        return check(rc, self.h, allow_soft=False)
+
+    def collect_batch_into(self, seq_a, outs):
+        return check(self.lib.vrf_tracker_collect_batch(self.h, len(seq_a), seq_a.ctypes.data, outs), self.h)
 
     def make_ba_batch(self, problems):
         from .ba_problem import BaSolution
@@ -394,14 +438,20 @@ class Handle:
     def ba_solve_batch_into(self, seq_a, probs, res):
         return check(self.lib.vrf_ba_solve_batch(self.h, len(seq_a), seq_a.ctypes.data, probs, res), self.h)
 
-    def enqueue_dev(self, seqs, d_ptr, fmt, times, Rs=None, pubs=None, d_depth=None):
+    def ba_submit_into(self, seq_a, probs):
+        return check(self.lib.vrf_ba_submit_batch(self.h, len(seq_a), seq_a.ctypes.data, probs), self.h, allow_soft=False)
+
+    def ba_collect_into(self, seq_a, res):
+        return check(self.lib.vrf_ba_collect_batch(self.h, len(seq_a), seq_a.ctypes.data, res), self.h)
+
+    def enqueue_dev(self, seqs, d_ptr, fmt, times, Rs=None, pubs=None, d_depth=None, depth_fmt=DEPTH_16UC1):
         n = len(seqs)
         seq_a = np.asarray(seqs, np.int32)
         t_a = np.asarray(times, np.float64)
         R_a = None if Rs is None else np.ascontiguousarray(np.asarray(Rs, np.float64).reshape(n, 9))
         p_a = None if pubs is None else np.asarray(pubs, np.int32)
         rc = self.lib.vrf_tracker_enqueue_batch_dev(
-            self.h, n, seq_a.ctypes.data, d_ptr, fmt, d_depth, t_a.ctypes.data,
+            self.h, n, seq_a.ctypes.data, d_ptr, fmt, d_depth, depth_fmt if d_depth else DEPTH_NONE, t_a.ctypes.data,
             None if R_a is None else R_a.ctypes.data, None if p_a is None else p_a.ctypes.data)
         check(rc, self.h)
 
