@@ -84,13 +84,15 @@ typedef struct VrfConfig {
     /* back end */
     int32_t num_iterations;           /* NUM_ITERATIONS (max_num_iterations) */
     int32_t estimate_extrinsic;       /* ESTIMATE_EXTRINSIC (0: ex-pose constant) */
-    int32_t estimate_td;              /* ESTIMATE_TD: must be 0 this round (ProjectionTdFactor is SURVEY 8f-1) */
+    int32_t estimate_td;              /* ESTIMATE_TD: 1 = ProjectionTdFactor instead of ProjectionFactor (estimator.cpp:1270-1285) */
     int32_t fix_depth;                /* FIX_DEPTH */
     double  depth_max_dist;           /* DEPTH_MAX_DIST (upper bound 2/DEPTH_MAX_DIST for estimate_flag==2) */
     double  g_norm;                   /* G = (0,0,g_norm) (parameters.cpp:13,158) */
     double  acc_n, acc_w, gyr_n, gyr_w; /* IMU noise (IntegrationBase ctor, integration_base.h:24-31) */
     double  depth_min_dist;           /* DEPTH_MIN_DIST: features with 0 < depth < this are dropped
                                          (FeatureManager::addFeatureCheckParallax, feature_manager.cpp:76-80) */
+    double  tr;                       /* TR: rolling-shutter read-out time per frame (rolling_shutter_tr, parameters.cpp);
+                                         0 for a global shutter.  Used by ProjectionTdFactor (TR / ROW * row) */
 } VrfConfig;
 
 /* Fills `cfg` with the synthetic-benchmark defaults of SURVEY.md section 8(d). */

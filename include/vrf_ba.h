@@ -78,8 +78,9 @@ typedef struct VrfPrior {
 typedef struct VrfBaProblem {
     int32_t frame_count;        /* Estimator::frame_count (== VRF_WINDOW_SIZE in steady state) */
     int32_t use_imu;            /* USE_IMU */
-    int32_t ex_constant;        /* 1: para_Ex_Pose constant (estimator.cpp:1191-1201) */
-    int32_t td_constant;        /* 1: para_Td constant (:1206-1211); must be 1 this round */
+    int32_t ex_constant;        /* 1: para_Ex_Pose constant (estimator.cpp:1191-1201: !(ESTIMATE_EXTRINSIC && frame_count ==
+                                   WINDOW_SIZE && |Vs[0]| > 0.2) && !openExEstimation) */
+    int32_t td_constant;        /* 1: para_Td constant (:1206-1211: !ESTIMATE_TD || |Vs[0]| < 0.2) */
     int32_t marginalization_flag;   /* VRF_MARGIN_OLD / VRF_MARGIN_SECOND_NEW */
     int32_t max_iterations;     /* NUM_ITERATIONS; 0 = use VrfConfig */
     /* states (vector2double order): [p(3), q(x,y,z,w)], [v, ba, bg] */
@@ -100,6 +101,11 @@ typedef struct VrfBaProblem {
     const VrfImuPreint *imu;
     /* prior from the previous call (NULL: none) */
     const VrfPrior *prior;
+    /* ProjectionTdFactor inputs, required iff VrfConfig::estimate_td (estimator.cpp:1270-1285,
+     * factor/projection_td_factor.cpp:34-150); indexed like obs_pts */
+    const double  *obs_velocity;    /* [n_obs][2] FeaturePerFrame::velocity.xy (z = 0, feature_manager.h:40-55) */
+    const double  *obs_cur_td;      /* [n_obs]    FeaturePerFrame::cur_td (td at the time the frame was processed) */
+    const double  *obs_row;         /* [n_obs]    FeaturePerFrame::uv.y() (pixel row, for the rolling-shutter term) */
 } VrfBaProblem;
 
 typedef struct VrfBaResult {

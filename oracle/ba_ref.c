@@ -40,10 +40,11 @@
 #include "../include/vrf.h"
 
 #define NF VRF_NUM_FRAMES
-#define NC 171                       /* 11*6 poses + 11*9 speed-bias + 6 ex-pose */
+#define NC 172                       /* 11*6 poses + 11*9 speed-bias + 6 ex-pose + 1 td */
 #define COL_POSE(f) (6 * (f))
 #define COL_SB(f) (66 + 9 * (f))
 #define COL_EX 165
+#define COL_TD 171
 
 /* ------------------------------------------------------------------ */
 /* quaternion / rotation helpers (Eigen semantics, storage x,y,z,w)    */
@@ -231,6 +232,48 @@ void oracle_projection_eval(const double *pose_i, const double *pose_j, const do
         for (int r = 0; r < 2; r++)
             Jf[r] = (red[r * 3] * v[0] + red[r * 3 + 1] * v[1] + red[r * 3 + 2] * v[2]) * -1.0 / (inv_dep * inv_dep);
     }
+}
+
+/* ------------------------------------------------------------------ */
+/* ProjectionTdFactor::Evaluate (projection_td_factor.cpp:34-150): the  */
+/* projection factor on the time-shifted points                         */
+/*   pts_td = pts - (td - td_obs + TR / ROW * row) * velocity  (:52-53) */
+/* plus the td column (:139-144).  vel = (vx, vy), z = 0.               */
+/* ------------------------------------------------------------------ */
+void oracle_projection_td_eval(const double *pose_i, const double *pose_j, const double *ex, double inv_dep, double td,
+                               const double *pts_i2, const double *pts_j2, const double *vel_i, const double *vel_j,
+                               double td_i, double td_j, double row_i, double row_j, double tr_over_row,
+                               double *res, double *Ji, double *Jj, double *Jex, double *Jf, double *Jtd)
+{
+    const double sqrt_info = 460.0 / 1.5;
+    const double si = td - td_i + tr_over_row * row_i, sj = td - td_j + tr_over_row * row_j;
+    double pi_td[2] = {pts_i2[0] - si * vel_i[0], pts_i2[1] - si * vel_i[1]};
+    double pj_td[2] = {pts_j2[0] - sj * vel_j[0], pts_j2[1] - sj * vel_j[1]};
+    oracle_projection_eval(pose_i, pose_j, ex, inv_dep, pi_td, pj_td, res, Ji, Jj, Jex, Jf);
+    if (!Jtd) return;
+    /* jacobian_td = reduce * ric^T Rj^T Ri ric * velocity_i / inv_dep * -1 + sqrt_info * velocity_j.head(2) */
+    const double *Pi = pose_i, *Qi = pose_i + 3, *Pj = pose_j, *Qj = pose_j + 3, *tic = ex, *qic = ex + 3;
+    double pc_i[3] = {pi_td[0] / inv_dep, pi_td[1] / inv_dep, 1.0 / inv_dep};
+    double t[3], p_imu_i[3], pw[3], p_imu_j[3], pc_j[3], qinv[4];
+    q_rot(qic, pc_i, t);
+    for (int k = 0; k < 3; k++) p_imu_i[k] = t[k] + tic[k];
+    q_rot(Qi, p_imu_i, t);
+    for (int k = 0; k < 3; k++) pw[k] = t[k] + Pi[k];
+    double d[3] = {pw[0] - Pj[0], pw[1] - Pj[1], pw[2] - Pj[2]};
+    q_inv(Qj, qinv); q_rot(qinv, d, p_imu_j);
+    double e[3] = {p_imu_j[0] - tic[0], p_imu_j[1] - tic[1], p_imu_j[2] - tic[2]};
+    q_inv(qic, qinv); q_rot(qinv, e, pc_j);
+    double dep_j = pc_j[2];
+    double red[6] = {sqrt_info * (1. / dep_j), 0, sqrt_info * (-pc_j[0] / (dep_j * dep_j)),
+                     0, sqrt_info * (1. / dep_j), sqrt_info * (-pc_j[1] / (dep_j * dep_j))};
+    double Ri[9], Rj[9], ric[9], RjT[9], ricT[9], A[9], C[9], tmp_r[9], v[3];
+    q_to_R(Qi, Ri); q_to_R(Qj, Rj); q_to_R(qic, ric);
+    m3_T(Rj, RjT); m3_T(ric, ricT);
+    m3_mul(ricT, RjT, A); m3_mul(A, Ri, C); m3_mul(C, ric, tmp_r);
+    double v3[3] = {vel_i[0], vel_i[1], 0.0};
+    m3_v(tmp_r, v3, v);
+    for (int r = 0; r < 2; r++)
+        Jtd[r] = (red[r * 3] * v[0] + red[r * 3 + 1] * v[1] + red[r * 3 + 2] * v[2]) / inv_dep * -1.0 + sqrt_info * vel_j[r];
 }
 
 /* ------------------------------------------------------------------ */
@@ -562,7 +605,9 @@ typedef struct {
     int nfac;
     int *f_lm, *f_i, *f_j;
     double *f_pi, *f_pj;      /* [nfac][2] */
-    double *f_r, *f_Ji, *f_Jj, *f_Jex, *f_Jl;   /* 2, 12, 12, 12, 2 per factor (local, corrected) */
+    double *f_vi, *f_vj;      /* [nfac][2] velocities (td factor) */
+    double *f_tdi, *f_tdj, *f_rowi, *f_rowj;    /* [nfac] cur_td and pixel row of both observations (td factor) */
+    double *f_r, *f_Ji, *f_Jj, *f_Jex, *f_Jl, *f_Jtd;   /* 2, 12, 12, 12, 2, 2 per factor (local, corrected) */
     /* imu */
     int imu_j[NF];            /* frame j of each used IMU factor */
     const VrfImuPreint *imu_pre[NF];
@@ -572,6 +617,8 @@ typedef struct {
     int pr_col[VRF_PRIOR_MAX_BLOCKS];   /* tangent column of each kept block (-1: landmark not allowed) */
     /* flags */
     int ex_active, pose0_const, use_imu, nframes;
+    int td_factor, td_active; /* ProjectionTdFactor in use (ESTIMATE_TD) / para_Td variable */
+    double tr_over_row;       /* TR / ROW */
     unsigned char *lm_const;
     double *lm_ub;            /* upper bound or +inf */
 } Lin;
@@ -645,19 +692,27 @@ static double evaluate(const VrfBaProblem *pb, const VrfConfig *cfg, Lin *L, con
     double cost = 0;
     for (int k = 0; k < L->nfac; k++) {
         int i = L->f_i[k], j = L->f_j[k], l = L->f_lm[k];
-        double r[2], Ji[14], Jj[14], Jex[14], Jf[2];
-        oracle_projection_eval(x->pose[i], x->pose[j], x->ex, x->lam[l], L->f_pi + 2 * k, L->f_pj + 2 * k, r,
-                               with_jac ? Ji : NULL, with_jac ? Jj : NULL, (with_jac && L->ex_active) ? Jex : NULL,
-                               (with_jac && !L->lm_const[l]) ? Jf : NULL);
+        double r[2], Ji[14], Jj[14], Jex[14], Jf[2], Jt[2] = {0, 0};
+        if (L->td_factor)
+            oracle_projection_td_eval(x->pose[i], x->pose[j], x->ex, x->lam[l], x->td, L->f_pi + 2 * k, L->f_pj + 2 * k,
+                                      L->f_vi + 2 * k, L->f_vj + 2 * k, L->f_tdi[k], L->f_tdj[k], L->f_rowi[k], L->f_rowj[k],
+                                      L->tr_over_row, r, with_jac ? Ji : NULL, with_jac ? Jj : NULL,
+                                      (with_jac && L->ex_active) ? Jex : NULL, (with_jac && !L->lm_const[l]) ? Jf : NULL,
+                                      (with_jac && L->td_active) ? Jt : NULL);
+        else
+            oracle_projection_eval(x->pose[i], x->pose[j], x->ex, x->lam[l], L->f_pi + 2 * k, L->f_pj + 2 * k, r,
+                                   with_jac ? Ji : NULL, with_jac ? Jj : NULL, (with_jac && L->ex_active) ? Jex : NULL,
+                                   (with_jac && !L->lm_const[l]) ? Jf : NULL);
         if (with_jac) {
             /* local parameterisation: first 6 columns of the 2x7 blocks */
             double li[12], lj[12], le[12], lf[2] = {0, 0};
             for (int rr = 0; rr < 2; rr++)
                 for (int c = 0; c < 6; c++) { li[rr * 6 + c] = Ji[rr * 7 + c]; lj[rr * 6 + c] = Jj[rr * 7 + c]; le[rr * 6 + c] = L->ex_active ? Jex[rr * 7 + c] : 0.0; }
             if (!L->lm_const[l]) { lf[0] = Jf[0]; lf[1] = Jf[1]; }
-            double *Jb[4] = {li, lj, le, lf};
-            int ncl[4] = {6, 6, 6, 1};
-            cost += 0.5 * cauchy_correct(r, Jb, ncl, 4);
+            double *Jb[5] = {li, lj, le, lf, Jt};
+            int ncl[5] = {6, 6, 6, 1, 1};
+            cost += 0.5 * cauchy_correct(r, Jb, ncl, 5);
+            L->f_Jtd[2 * k] = Jt[0]; L->f_Jtd[2 * k + 1] = Jt[1];
             memcpy(L->f_Ji + 12 * k, li, sizeof(li)); memcpy(L->f_Jj + 12 * k, lj, sizeof(lj));
             memcpy(L->f_Jex + 12 * k, le, sizeof(le)); L->f_Jl[2 * k] = lf[0]; L->f_Jl[2 * k + 1] = lf[1];
             L->f_r[2 * k] = r[0]; L->f_r[2 * k + 1] = r[1];
@@ -705,10 +760,11 @@ static void for_each_row(const VrfBaProblem *pb, const Lin *L, row_fn fn, void *
     for (int k = 0; k < L->nfac; k++) {
         int i = L->f_i[k], j = L->f_j[k], l = L->f_lm[k];
         for (int rr = 0; rr < 2; rr++) {
-            double vals[19]; int cols[19]; int n = 0;
+            double vals[20]; int cols[20]; int n = 0;
             for (int c = 0; c < 6; c++) { vals[n] = L->f_Ji[12 * k + rr * 6 + c]; cols[n++] = COL_POSE(i) + c; }
             for (int c = 0; c < 6; c++) { vals[n] = L->f_Jj[12 * k + rr * 6 + c]; cols[n++] = COL_POSE(j) + c; }
             if (L->ex_active) for (int c = 0; c < 6; c++) { vals[n] = L->f_Jex[12 * k + rr * 6 + c]; cols[n++] = COL_EX + c; }
+            if (L->td_active) { vals[n] = L->f_Jtd[2 * k + rr]; cols[n++] = COL_TD; }
             if (!L->lm_const[l]) { vals[n] = L->f_Jl[2 * k + rr]; cols[n++] = NC + l; }
             fn(ctx, vals, cols, n, L->f_r[2 * k + rr], rid++);
         }
@@ -748,6 +804,7 @@ static int col_active(const Lin *L, int col)
 {
     if (col < 66) { int f = col / 6; if (f >= L->nframes) return 0; if (f == 0 && L->pose0_const) return 0; return 1; }
     if (col < 165) { int f = (col - 66) / 9; return L->use_imu && f < L->nframes; }
+    if (col == COL_TD) return L->td_active;
     return L->ex_active;
 }
 
@@ -839,6 +896,7 @@ static void apply_delta(const Lin *L, const State *x, const double *delta, State
         if (col_active(L, COL_SB(f))) for (int k = 0; k < 9; k++) o->sb[f][k] = x->sb[f][k] + delta[COL_SB(f) + k];
     }
     if (L->ex_active) pose_plus(x->ex, delta + COL_EX, o->ex);
+    if (L->td_active) o->td = x->td + delta[COL_TD];
     for (int l = 0; l < L->M; l++) {
         double v = x->lam[l];
         if (!L->lm_const[l]) {
@@ -858,6 +916,7 @@ static double active_x_norm2_diff(const Lin *L, const State *a, const State *b)
         if (col_active(L, COL_SB(f))) for (int k = 0; k < 9; k++) { double d = a->sb[f][k] - (b ? b->sb[f][k] : 0); s += d * d; }
     }
     if (L->ex_active) for (int k = 0; k < 7; k++) { double d = a->ex[k] - (b ? b->ex[k] : 0); s += d * d; }
+    if (L->td_active) { double d = a->td - (b ? b->td : 0); s += d * d; }
     for (int l = 0; l < L->M; l++) if (!L->lm_const[l]) { double d = a->lam[l] - (b ? b->lam[l] : 0); s += d * d; }
     return s;
 }
@@ -924,6 +983,7 @@ static int solve(const VrfBaProblem *pb, const VrfConfig *cfg, Lin *L, State *x,
                     if (col_active(L, COL_SB(f))) for (int k = 0; k < 9; k++) mx = fmax(mx, fabs(x->sb[f][k] - cand.sb[f][k]));
                 }
                 if (L->ex_active) for (int k = 0; k < 7; k++) mx = fmax(mx, fabs(x->ex[k] - cand.ex[k]));
+                if (L->td_active) mx = fmax(mx, fabs(x->td - cand.td));
                 for (int l = 0; l < M; l++) if (!L->lm_const[l]) mx = fmax(mx, fabs(x->lam[l] - cand.lam[l]));
                 gradient_max_norm = mx;
             }
@@ -1201,6 +1261,7 @@ static int marginalize(const VrfBaProblem *pb, const VrfConfig *cfg, const State
     /* kept candidates in canonical order; presence decided by the factors below */
     int first_kept = nb;
     ADDB(VRF_BLK_EXPOSE, 0, 7, 0, x->ex);
+    ADDB(VRF_BLK_TD, 0, 1, 0, &x->td);
     for (int f = 0; f < NF; f++) ADDB(VRF_BLK_POSE, f, 7, 0, x->pose[f]);
     for (int f = 0; f < NF; f++) ADDB(VRF_BLK_SPEEDBIAS, f, 9, 0, x->sb[f]);
 #undef ADDB
@@ -1218,6 +1279,7 @@ static int marginalize(const VrfBaProblem *pb, const VrfConfig *cfg, const State
             B[mblock_find(B, nb, LM, l)].present = 1;
             B[mblock_find(B, nb, VRF_BLK_POSE, 0)].present = 1;
             B[mblock_find(B, nb, VRF_BLK_EXPOSE, 0)].present = 1;
+            if (cfg->estimate_td) B[mblock_find(B, nb, VRF_BLK_TD, 0)].present = 1;      /* estimator.cpp:1445-1458 */
             for (int k = 1; k < nobs; k++) B[mblock_find(B, nb, VRF_BLK_POSE, k)].present = 1;
         }
     }
@@ -1280,21 +1342,28 @@ static int marginalize(const VrfBaProblem *pb, const VrfConfig *cfg, const State
             int o0 = pb->lm_obs_ptr[l], nobs = pb->lm_obs_ptr[l + 1] - o0;
             if (pb->lm_start_frame[l] != 0 || nobs < 2) continue;
             for (int k = 1; k < nobs; k++) {
-                double r[2], Ji[14], Jj[14], Jex[14], Jf[2];
-                oracle_projection_eval(x->pose[0], x->pose[k], x->ex, x->lam[l], pb->obs_pts + 2 * o0, pb->obs_pts + 2 * (o0 + k), r, Ji, Jj, Jex, Jf);
+                double r[2], Ji[14], Jj[14], Jex[14], Jf[2], Jt[2] = {0, 0};
+                const int ntd = cfg->estimate_td ? 1 : 0;
+                if (ntd)
+                    oracle_projection_td_eval(x->pose[0], x->pose[k], x->ex, x->lam[l], x->td, pb->obs_pts + 2 * o0, pb->obs_pts + 2 * (o0 + k),
+                                              pb->obs_velocity + 2 * o0, pb->obs_velocity + 2 * (o0 + k), pb->obs_cur_td[o0], pb->obs_cur_td[o0 + k],
+                                              pb->obs_row[o0], pb->obs_row[o0 + k], cfg->tr / (double)cfg->row, r, Ji, Jj, Jex, Jf, Jt);
+                else
+                    oracle_projection_eval(x->pose[0], x->pose[k], x->ex, x->lam[l], pb->obs_pts + 2 * o0, pb->obs_pts + 2 * (o0 + k), r, Ji, Jj, Jex, Jf);
                 double li[12], lj[12], le[12], lf[2] = {Jf[0], Jf[1]};
                 for (int rr = 0; rr < 2; rr++) for (int c = 0; c < 6; c++) { li[rr * 6 + c] = Ji[rr * 7 + c]; lj[rr * 6 + c] = Jj[rr * 7 + c]; le[rr * 6 + c] = Jex[rr * 7 + c]; }
-                double *Jb[4] = {li, lj, le, lf}; int ncl[4] = {6, 6, 6, 1};
-                cauchy_correct(r, Jb, ncl, 4);
-                int cols[19]; double J[2][19];
+                double *Jb[5] = {li, lj, le, lf, Jt}; int ncl[5] = {6, 6, 6, 1, 1};
+                cauchy_correct(r, Jb, ncl, 4 + ntd);
+                int cols[20]; double J[2][20];
                 int ci = B[mblock_find(B, nb, VRF_BLK_POSE, 0)].idx, cj = B[mblock_find(B, nb, VRF_BLK_POSE, k)].idx;
                 int ce = B[mblock_find(B, nb, VRF_BLK_EXPOSE, 0)].idx, cl = B[mblock_find(B, nb, LM, l)].idx;
                 for (int c = 0; c < 6; c++) { cols[c] = ci + c; cols[6 + c] = cj + c; cols[12 + c] = ce + c; }
                 cols[18] = cl;
-                for (int rr = 0; rr < 2; rr++) { for (int c = 0; c < 6; c++) { J[rr][c] = li[rr * 6 + c]; J[rr][6 + c] = lj[rr * 6 + c]; J[rr][12 + c] = le[rr * 6 + c]; } J[rr][18] = lf[rr]; }
-                for (int a = 0; a < 19; a++) {
+                if (ntd) cols[19] = B[mblock_find(B, nb, VRF_BLK_TD, 0)].idx;
+                for (int rr = 0; rr < 2; rr++) { for (int c = 0; c < 6; c++) { J[rr][c] = li[rr * 6 + c]; J[rr][6 + c] = lj[rr * 6 + c]; J[rr][12 + c] = le[rr * 6 + c]; } J[rr][18] = lf[rr]; J[rr][19] = Jt[rr]; }
+                for (int a = 0; a < 19 + ntd; a++) {
                     bv[cols[a]] += J[0][a] * r[0] + J[1][a] * r[1];
-                    for (int c = 0; c < 19; c++) A[(size_t)cols[a] * pos + cols[c]] += J[0][a] * J[0][c] + J[1][a] * J[1][c];
+                    for (int c = 0; c < 19 + ntd; c++) A[(size_t)cols[a] * pos + cols[c]] += J[0][a] * J[0][c] + J[1][a] * J[1][c];
                 }
             }
         }
@@ -1339,7 +1408,7 @@ static int marginalize(const VrfBaProblem *pb, const VrfConfig *cfg, const State
         VrfPriorBlock *K = &out->blocks[nk++];
         K->kind = B[i].kind; K->size = B[i].gsize; K->idx = B[i].idx - m;
         memcpy(K->x0, B[i].x0, sizeof(double) * B[i].gsize);
-        if (B[i].kind == VRF_BLK_EXPOSE) K->index = 0;
+        if (B[i].kind == VRF_BLK_EXPOSE || B[i].kind == VRF_BLK_TD) K->index = 0;
         else if (flag == VRF_MARGIN_OLD) K->index = B[i].index - 1;
         else K->index = (B[i].index == VRF_WINDOW_SIZE) ? VRF_WINDOW_SIZE - 1 : B[i].index;
     }
@@ -1358,6 +1427,11 @@ int oracle_ba_solve(const VrfConfig *cfg, const VrfBaProblem *pb, VrfBaResult *r
     memset(&L, 0, sizeof(L));
     L.M = M; L.use_imu = pb->use_imu; L.nframes = pb->frame_count + 1;
     L.ex_active = !pb->ex_constant; L.pose0_const = !pb->use_imu;
+    /* ESTIMATE_TD selects ProjectionTdFactor (estimator.cpp:1270); para_Td is only added (and possibly fixed) as a
+       parameter block under USE_IMU (:1203-1212) -- without IMU Ceres adds it implicitly as a variable */
+    L.td_factor = cfg->estimate_td != 0;
+    L.td_active = L.td_factor && !(pb->use_imu && pb->td_constant);
+    L.tr_over_row = cfg->tr / (double)cfg->row;
     int nfac = 0;
     for (int l = 0; l < M; l++) { int no = pb->lm_obs_ptr[l + 1] - pb->lm_obs_ptr[l]; if (no >= 2) nfac += no - 1; }
     L.nfac = nfac;
@@ -1365,7 +1439,10 @@ int oracle_ba_solve(const VrfConfig *cfg, const VrfBaProblem *pb, VrfBaResult *r
     L.f_pi = (double *)malloc(sizeof(double) * 2 * (nfac + 1)); L.f_pj = (double *)malloc(sizeof(double) * 2 * (nfac + 1));
     L.f_r = (double *)malloc(sizeof(double) * 2 * (nfac + 1)); L.f_Ji = (double *)malloc(sizeof(double) * 12 * (nfac + 1));
     L.f_Jj = (double *)malloc(sizeof(double) * 12 * (nfac + 1)); L.f_Jex = (double *)malloc(sizeof(double) * 12 * (nfac + 1));
-    L.f_Jl = (double *)malloc(sizeof(double) * 2 * (nfac + 1));
+    L.f_Jl = (double *)malloc(sizeof(double) * 2 * (nfac + 1)); L.f_Jtd = (double *)calloc(2 * (nfac + 1), sizeof(double));
+    L.f_vi = (double *)calloc(2 * (nfac + 1), sizeof(double)); L.f_vj = (double *)calloc(2 * (nfac + 1), sizeof(double));
+    L.f_tdi = (double *)calloc(nfac + 1, sizeof(double)); L.f_tdj = (double *)calloc(nfac + 1, sizeof(double));
+    L.f_rowi = (double *)calloc(nfac + 1, sizeof(double)); L.f_rowj = (double *)calloc(nfac + 1, sizeof(double));
     L.lm_const = (unsigned char *)malloc(M + 1); L.lm_ub = (double *)malloc(sizeof(double) * (M + 1));
     int k = 0;
     for (int l = 0; l < M; l++) {
@@ -1376,6 +1453,12 @@ int oracle_ba_solve(const VrfConfig *cfg, const VrfBaProblem *pb, VrfBaResult *r
             L.f_lm[k] = l; L.f_i[k] = i; L.f_j[k] = i + t;
             L.f_pi[2 * k] = pb->obs_pts[2 * o0]; L.f_pi[2 * k + 1] = pb->obs_pts[2 * o0 + 1];
             L.f_pj[2 * k] = pb->obs_pts[2 * (o0 + t)]; L.f_pj[2 * k + 1] = pb->obs_pts[2 * (o0 + t) + 1];
+            if (L.td_factor) {
+                L.f_vi[2 * k] = pb->obs_velocity[2 * o0]; L.f_vi[2 * k + 1] = pb->obs_velocity[2 * o0 + 1];
+                L.f_vj[2 * k] = pb->obs_velocity[2 * (o0 + t)]; L.f_vj[2 * k + 1] = pb->obs_velocity[2 * (o0 + t) + 1];
+                L.f_tdi[k] = pb->obs_cur_td[o0]; L.f_tdj[k] = pb->obs_cur_td[o0 + t];
+                L.f_rowi[k] = pb->obs_row[o0]; L.f_rowj[k] = pb->obs_row[o0 + t];
+            }
         }
     }
     L.nimu = 0;
@@ -1389,7 +1472,8 @@ int oracle_ba_solve(const VrfConfig *cfg, const VrfBaProblem *pb, VrfBaResult *r
     if (pb->prior)
         for (int b = 0; b < pb->prior->n_blocks; b++) {
             const VrfPriorBlock *B = &pb->prior->blocks[b];
-            int col = B->kind == VRF_BLK_POSE ? COL_POSE(B->index) : B->kind == VRF_BLK_SPEEDBIAS ? COL_SB(B->index) : B->kind == VRF_BLK_EXPOSE ? COL_EX : -1;
+            int col = B->kind == VRF_BLK_POSE ? COL_POSE(B->index) : B->kind == VRF_BLK_SPEEDBIAS ? COL_SB(B->index)
+                      : B->kind == VRF_BLK_EXPOSE ? COL_EX : B->kind == VRF_BLK_TD ? COL_TD : -1;
             if (col >= 0 && !col_active(&L, col)) col = -1;
             L.pr_col[b] = col;
         }
@@ -1417,6 +1501,7 @@ int oracle_ba_solve(const VrfConfig *cfg, const VrfBaProblem *pb, VrfBaResult *r
     }
     free(x.lam); free(L.f_lm); free(L.f_i); free(L.f_j); free(L.f_pi); free(L.f_pj); free(L.f_r); free(L.f_Ji); free(L.f_Jj);
     free(L.f_Jex); free(L.f_Jl); free(L.lm_const); free(L.lm_ub); free(L.pr_r);
+    free(L.f_Jtd); free(L.f_vi); free(L.f_vj); free(L.f_tdi); free(L.f_tdj); free(L.f_rowi); free(L.f_rowj);
     return res->status;
 }
 

@@ -24,6 +24,8 @@ def lib():
         _lib.oracle_ba_solve.argtypes = [C.POINTER(B.VrfConfig), C.POINTER(B.VrfBaProblem), C.POINTER(B.VrfBaResult)]
         _lib.oracle_projection_eval.argtypes = [C.c_void_p] * 3 + [C.c_double] + [C.c_void_p] * 7
         _lib.oracle_projection_eval.restype = None
+        _lib.oracle_projection_td_eval.argtypes = [C.c_void_p] * 3 + [C.c_double] * 2 + [C.c_void_p] * 4 + [C.c_double] * 5 + [C.c_void_p] * 6
+        _lib.oracle_projection_td_eval.restype = None
         _lib.oracle_imu_eval.argtypes = [C.POINTER(B.VrfImuPreint)] + [C.c_void_p] * 4 + [C.c_double] + [C.c_void_p] * 5
         _lib.oracle_preint_init.argtypes = [C.POINTER(OraclePreint)] + [C.c_void_p] * 4 + [C.c_double] * 4
         _lib.oracle_preint_init.restype = None
@@ -46,6 +48,17 @@ def projection_eval(pose_i, pose_j, ex, inv_dep, pts_i, pts_j, jac=True):
     lib().oracle_projection_eval(_p(a[0]), _p(a[1]), _p(a[2]), float(inv_dep), _p(pi), _p(pj), _p(r),
                                  _p(Ji) if jac else None, _p(Jj) if jac else None, _p(Je) if jac else None, _p(Jf) if jac else None)
     return r, Ji, Jj, Je, Jf
+
+
+def projection_td_eval(pose_i, pose_j, ex, inv_dep, td, pts_i, pts_j, vel_i, vel_j, td_i, td_j, row_i, row_j, tr_over_row, jac=True):
+    r = np.zeros(2)
+    Ji = np.zeros((2, 7)); Jj = np.zeros((2, 7)); Je = np.zeros((2, 7)); Jf = np.zeros(2); Jt = np.zeros(2)
+    a = [np.ascontiguousarray(v, np.float64) for v in (pose_i, pose_j, ex, pts_i, pts_j, vel_i, vel_j)]
+    lib().oracle_projection_td_eval(_p(a[0]), _p(a[1]), _p(a[2]), float(inv_dep), float(td), _p(a[3]), _p(a[4]), _p(a[5]), _p(a[6]),
+                                    float(td_i), float(td_j), float(row_i), float(row_j), float(tr_over_row), _p(r),
+                                    _p(Ji) if jac else None, _p(Jj) if jac else None, _p(Je) if jac else None,
+                                    _p(Jf) if jac else None, _p(Jt) if jac else None)
+    return r, Ji, Jj, Je, Jf, Jt
 
 
 def imu_eval(pre, pose_i, sb_i, pose_j, sb_j, g_norm=9.81, jac=True):

@@ -39,6 +39,8 @@ def compare(sol_g, sol_o, pb, tol=POSE_TOL):
     assert np.abs(sol_g.Ps - sol_o.Ps).max() <= tol
     assert np.abs(sol_g.Rs - sol_o.Rs).max() <= tol
     assert np.abs(sol_g.Vs - sol_o.Vs).max() <= 10 * tol
+    assert np.abs(sol_g.ex - sol_o.ex).max() <= tol           # para_Ex_Pose (variable when ESTIMATE_EXTRINSIC)
+    assert abs(sol_g.td - sol_o.td) <= tol                    # para_Td (variable when ESTIMATE_TD)
 
 
 def compare_prior(pg, po):
@@ -184,3 +186,43 @@ def test_ba_pipelined_submit_collect_equals_synchronous():
             assert np.abs(g.Ps - r.Ps).max() <= 1e-9 and np.abs(g.pose - r.pose).max() <= 1e-9
             assert np.abs(g.lam[:pbs[2 * i + j].M] - r.lam[:pbs[2 * i + j].M]).max() <= 1e-9
     h.close(); h_sync.close()
+
+
+def test_extrinsic_estimation_matches_oracle():
+    """para_Ex_Pose variable (ESTIMATE_EXTRINSIC, estimator.cpp:1186-1201): the ex-pose columns of ProjectionFactor
+    (projection_factor.cpp:104-113) enter the camera system and the landmark Schur rows; chain of 3 windows incl. priors."""
+    cfg = make_cfg()
+    h = B.Handle(cfg, 1, 0)
+    sim = BP.WindowSimulator(31, cfg, n_landmarks=120, ex_constant=0, ex_perturb=0.02, tic=np.array([0.05, -0.03, 0.02]))
+    for a in range(3):
+        pb = sim.window(a)
+        so = ba_ref.solve(cfg, pb)
+        sg = h.ba_solve(0, pb)
+        compare(sg, so, pb)
+        assert np.abs(so.ex - pb.ex).max() > 1e-5                  # the extrinsic really moved
+        compare_prior(sg.new_prior, so.new_prior)
+        sim.commit(a, so)
+    h.close()
+
+
+@pytest.mark.parametrize("td_constant,ex_constant,tr", [(0, 1, 0.0), (0, 0, 0.02), (1, 1, 0.033)])
+def test_projection_td_factor_matches_oracle(td_constant, ex_constant, tr):
+    """ESTIMATE_TD: ProjectionTdFactor (projection_td_factor.cpp:34-150) with para_Td variable or
+    fixed, with and without the rolling-shutter row term, alone and together with a variable extrinsic; the new
+    prior keeps a td block (estimator.cpp:1445-1458)."""
+    cfg = make_cfg(estimate_td=1, tr=tr)
+    h = B.Handle(cfg, 1, 0)
+    sim = BP.WindowSimulator(33, cfg, n_landmarks=120, td_true=0.02, td_constant=td_constant, ex_constant=ex_constant,
+                             ex_perturb=0.0 if ex_constant else 0.02, tic=np.array([0.05, -0.03, 0.02]))
+    for a in range(3):
+        pb = sim.window(a)
+        so = ba_ref.solve(cfg, pb)
+        sg = h.ba_solve(0, pb)
+        compare(sg, so, pb)
+        if not td_constant:
+            assert abs(so.td - pb.td) > 1e-6                       # td really moved
+        compare_prior(sg.new_prior, so.new_prior)
+        kinds = [(k, s_) for (k, i, s_, ix, x0) in BP.prior_blocks(sg.new_prior)]
+        assert (B.BLK_TD, 1) in kinds
+        sim.commit(a, so)
+    h.close()

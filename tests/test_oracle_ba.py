@@ -266,3 +266,58 @@ def test_solver_agrees_with_scipy_at_convergence():
     assert cost_scipy * (1 - 1e-7) <= sol2.c.final_cost <= cost_scipy * (1 + 1e-12)
     assert np.abs(sol2.pose[:, :3] - pose_s[:, :3]).max() < 1e-5
     assert np.abs(sol2.lam[:M] - lam_s).max() < 1e-4
+
+
+def test_projection_td_jacobian_finite_difference():
+    """ProjectionTdFactor (projection_td_factor.cpp:34-150): the check the reference leaves unused
+    (ProjectionTdFactor::check, :152-267), incl. the td column and the rolling-shutter row term."""
+    rng = np.random.default_rng(3)
+    for _ in range(20):
+        pi = rand_pose(rng, 0.3); pj = pose_plus(pi, rng.normal(0, 0.05, 6))
+        ex = pose_plus(np.array([0.05, -0.02, 0.01, 0, 0, 0, 1.0]), rng.normal(0, 0.05, 6))
+        lam = rng.uniform(0.2, 0.8); td = rng.normal(0, 0.01)
+        pts_i = rng.uniform(-0.4, 0.4, 2); pts_j = pts_i + rng.normal(0, 0.02, 2)
+        vi, vj = rng.normal(0, 0.3, 2), rng.normal(0, 0.3, 2)
+        tdi, tdj = rng.normal(0, 0.01, 2); rows = rng.uniform(0, 480, 2); tor = 0.033 / 480
+        args = dict(td_i=tdi, td_j=tdj, row_i=rows[0], row_j=rows[1], tr_over_row=tor)
+        r, Ji, Jj, Je, Jf, Jt = ba_ref.projection_td_eval(pi, pj, ex, lam, td, pts_i, pts_j, vi, vj, **args)
+        # with zero velocity the factor reduces to ProjectionFactor
+        r0 = ba_ref.projection_td_eval(pi, pj, ex, lam, td, pts_i, pts_j, 0 * vi, 0 * vj, jac=False, **args)[0]
+        assert np.allclose(r0, ba_ref.projection_eval(pi, pj, ex, lam, pts_i, pts_j, jac=False)[0], atol=1e-12)
+        eps = 1e-6
+        for blk, J in ((0, Ji), (1, Jj), (2, Je)):
+            for c in range(6):
+                d = np.zeros(6); d[c] = eps
+                a3 = [pi, pj, ex]
+                a3[blk] = pose_plus(a3[blk], d)
+                r2 = ba_ref.projection_td_eval(a3[0], a3[1], a3[2], lam, td, pts_i, pts_j, vi, vj, jac=False, **args)[0]
+                assert np.allclose((r2 - r) / eps, J[:, c], rtol=2e-4, atol=2e-3)
+        r2 = ba_ref.projection_td_eval(pi, pj, ex, lam + eps, td, pts_i, pts_j, vi, vj, jac=False, **args)[0]
+        assert np.allclose((r2 - r) / eps, Jf, rtol=2e-4, atol=2e-3)
+        r2 = ba_ref.projection_td_eval(pi, pj, ex, lam, td + eps, pts_i, pts_j, vi, vj, jac=False, **args)[0]
+        assert np.allclose((r2 - r) / eps, Jt, rtol=2e-4, atol=2e-3)
+
+
+def test_td_and_extrinsic_estimation_recover_truth():
+    """estimate_td / estimate_extrinsic (estimator.cpp:1186-1212,1270-1285): with para_Td and para_Ex_Pose variable the
+    window chain tracks the simulated camera-IMU time offset (the estimate moves one-to-one with the true offset; the
+    simulator's IMU sampling leaves a constant bias, so two offsets are compared) and pulls the perturbed extrinsic
+    rotation towards the true one; the new prior carries a td block (kind 3, size 1) next to the ex block."""
+    est = {}
+    for td_true in (0.03, -0.03):
+        cfg = make_cfg()
+        cfg.estimate_td = 1; cfg.tr = 0.0; cfg.row = 480
+        sim = BP.WindowSimulator(9, cfg, n_landmarks=120, td_true=td_true, td_constant=0, ex_constant=0, ex_perturb=0.03,
+                                 tic=np.array([0.05, -0.03, 0.02]), pix_noise=0.1)
+        ang0 = np.linalg.norm(synth.so3_log(sim.ric.T @ sim.ex_est[1]))
+        for a in range(3):
+            pb = sim.window(a)
+            sol = ba_ref.solve(cfg, pb)
+            assert sol.rc == 0 and sol.c.final_cost < sol.c.initial_cost
+            sim.commit(a, sol)
+            kinds = [(k, s) for (k, i, s, ix, x0) in BP.prior_blocks(sol.new_prior)]
+            assert (B.BLK_EXPOSE, 7) in kinds and (B.BLK_TD, 1) in kinds
+        est[td_true] = sim.td_est
+        # (the extrinsic translation is barely observable under this gentle rotation; the rotation is)
+        assert np.linalg.norm(synth.so3_log(sim.ric.T @ sim.ex_est[1])) < 0.75 * ang0
+    assert abs((est[0.03] - est[-0.03]) - 0.06) < 0.2 * 0.06

@@ -45,6 +45,7 @@ extern "C" void vrf_config_default(VrfConfig *c)
     c->depth_max_dist = 10.0; c->g_norm = 9.81;
     c->acc_n = 0.1; c->acc_w = 0.001; c->gyr_n = 0.01; c->gyr_w = 0.0001;
     c->depth_min_dist = 0.3;      // config/realsense/vio.yaml: depth_min_dist
+    c->tr = 0.0;
 }
 
 extern "C" const char *vrf_strerror(int code)
@@ -125,7 +126,6 @@ extern "C" int vrf_create(const VrfConfig *cfg, int n_seq, int device, vrf_handl
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return VRF_ERR_NO_DEVICE;
     if (device < 0 || device >= ndev) return VRF_ERR_ARG;
-    if (cfg->estimate_td) return VRF_ERR_UNSUPPORTED;
     FrontCfg fc;
     int rc = build_front_cfg(*cfg, fc);
     if (rc != VRF_OK) return rc;

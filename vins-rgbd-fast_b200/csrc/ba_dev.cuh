@@ -5,7 +5,10 @@
 #include "handle.h"
 
 #define BA_NF VRF_NUM_FRAMES
-#define BA_NC 171                 // 11*6 pose + 11*9 speed-bias + 6 ex-pose tangent columns
+#define BA_NC 172                 // 11*6 pose + 11*9 speed-bias + 6 ex-pose + 1 td tangent columns
+#define BA_COL_EX 165
+#define BA_COL_TD 171
+#define BA_WS 73                  // landmark coupling row: 66 pose columns + 6 ex-pose + 1 td
 #define BA_THREADS 512
 #define BA_MAX_LM 1024            // >= NUM_OF_F (parameters.h:14)
 #define BA_MAX_OBS 8192
@@ -18,7 +21,12 @@ struct BaMeta {
     int M, nobs, nimu, np, nframes, use_imu, max_iter, marg_flag, has_prior, frame_count;
     int imu_j[BA_NF];
     int debug;            // VRF_BA_DEBUG env: bit0 = per-iteration trace (printf), bit1 = column Cholesky
+    int ex_active;        // para_Ex_Pose variable (estimator.cpp:1191-1201)
+    int td_factor;        // ESTIMATE_TD: ProjectionTdFactor instead of ProjectionFactor (:1270-1285)
+    int td_active;        // para_Td variable (:1203-1212)
+    int pad2;
     double g_norm;
+    double tr_over_row;   // TR / ROW (projection_td_factor.cpp:52-53)
 };
 
 // prior as stored on device (MarginalizationInfo: marginalization_factor.h:62-74); produced by
@@ -39,6 +47,8 @@ struct BaProbDev {
     const uint8_t *lm_const;
     const double *lm_ub;
     const double *obs;                    // [nobs][2]
+    const double *obs_vel, *obs_td, *obs_row;   // [nobs][2], [nobs], [nobs]: ProjectionTdFactor inputs (td_factor only)
+    const double *td0;                    // [1] para_Td
     const VrfImuPreint *imu;              // [10]
     const BaPriorStore *prior;            // NULL: no prior
     BaPriorStore *prior_next;             // written by the marginalization kernel
@@ -47,7 +57,7 @@ struct BaProbDev {
     // scratch / state
     double *lam, *clam;                   // current / candidate inverse depths
     double *lam_out;                      // optimised inverse depths of this batch item (result copy)
-    double *W;                            // [M][66]
+    double *W;                            // [M][BA_WS]
     double *hll, *gl, *jscale_l, *diag_l, *gd_l, *gn_l, *u_l, *y_l, *hinv_l;
     double *imuS;                         // [10][225] sqrt information (upper)
 };
@@ -60,6 +70,7 @@ struct BaOutDev {
     double Ps[BA_NF * 3], Rs[BA_NF * 9], Vs[BA_NF * 3], Bas[BA_NF * 3], Bgs[BA_NF * 3];
     // states re-packed by vector2double after the gauge fix (marginalization linearises here)
     double mpose[BA_NF * 7], msb[BA_NF * 9], mex[7];
+    double td, mtd;      // para_Td after the solve / as re-packed for marginalization
     int has_new_prior, pad;
     long long prof2[8];  // k_ba_marg: 0 table+zero, 1 prior, 2 imu+proj, 3 pd test, 4 schur (fast or eig), 5 jacobi, 6 output, 7 total kernel cycles of k_ba_solve
     long long prof[8];   // clock64 per phase: 0 linearise, 1 scale+grad, 2 cauchy, 3 schur, 4 cholesky, 5 solve tail, 6 dogleg, 7 candidate cost

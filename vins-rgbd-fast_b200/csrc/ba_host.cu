@@ -14,12 +14,16 @@ namespace vrf {
 
 // pinned host staging of one packed problem
 struct BaHostPack {
-    double pose[BA_NF * 7], sb[BA_NF * 9], ex[7];
+    double pose[BA_NF * 7], sb[BA_NF * 9], ex[7], td;
     VrfImuPreint imu[BA_NF - 1];
     double lam[BA_MAX_LM], lm_ub[BA_MAX_LM];
     int start[BA_MAX_LM], obs_ptr[BA_MAX_LM + 1];
     uint8_t lm_const[BA_MAX_LM];
     double obs[BA_MAX_OBS * 2];
+};
+// ProjectionTdFactor inputs (only staged / uploaded when VrfConfig::estimate_td)
+struct BaHostPackTd {
+    double vel[BA_MAX_OBS * 2], ctd[BA_MAX_OBS], row[BA_MAX_OBS];
 };
 
 #define BA_PIPE 2      // batches in flight (vrf_ba_submit_batch / vrf_ba_collect_batch)
@@ -28,6 +32,7 @@ struct BaHostPack {
 // batch k+1 can be packed and uploaded while batch k runs.
 struct BaSlot {
     BaHostPack *h_pack = nullptr, *d_pack = nullptr;       // [n_seq]
+    BaHostPackTd *h_packtd = nullptr, *d_packtd = nullptr; // [n_seq], estimate_td only
     BaMeta *h_meta = nullptr, *d_meta = nullptr;
     BaProbDev *h_prob = nullptr, *d_prob = nullptr;
     BaOutDev *h_out = nullptr, *d_out = nullptr;
@@ -68,6 +73,10 @@ static int slot_alloc(vrf_handle *h, BaSlot &sl)
     const size_t S = h->n_seq;
     BCK(cudaMallocHost((void **)&sl.h_pack, S * sizeof(BaHostPack)));
     BCK(cudaMalloc((void **)&sl.d_pack, S * sizeof(BaHostPack)));
+    if (h->cfg.estimate_td) {
+        BCK(cudaMallocHost((void **)&sl.h_packtd, S * sizeof(BaHostPackTd)));
+        BCK(cudaMalloc((void **)&sl.d_packtd, S * sizeof(BaHostPackTd)));
+    }
     BCK(cudaMallocHost((void **)&sl.h_meta, S * sizeof(BaMeta)));
     BCK(cudaMalloc((void **)&sl.d_meta, S * sizeof(BaMeta)));
     BCK(cudaMallocHost((void **)&sl.h_prob, S * sizeof(BaProbDev)));
@@ -98,7 +107,7 @@ int ba_create(vrf_handle *h)
     BCK(cudaMallocHost((void **)&b->h_prior_dl, sizeof(BaPriorStore)));
     BCK(cudaMalloc((void **)&b->d_lam, S * BA_MAX_LM * sizeof(double)));
     BCK(cudaMalloc((void **)&b->d_clam, S * BA_MAX_LM * sizeof(double)));
-    BCK(cudaMalloc((void **)&b->d_W, S * BA_MAX_LM * 66 * sizeof(double)));
+    BCK(cudaMalloc((void **)&b->d_W, S * BA_MAX_LM * BA_WS * sizeof(double)));
     BCK(cudaMalloc((void **)&b->d_vecs, S * 9 * BA_MAX_LM * sizeof(double)));
     BCK(cudaMalloc((void **)&b->d_imuS, S * (BA_NF - 1) * 225 * sizeof(double)));
     BCK(cudaMalloc((void **)&b->d_HP, S * VRF_PRIOR_MAX_DIM * VRF_PRIOR_MAX_DIM * sizeof(double)));
@@ -120,9 +129,9 @@ void ba_destroy(vrf_handle *h)
     for (void *p : dev) if (p) cudaFree(p);
     if (b->h_prior_dl) cudaFreeHost(b->h_prior_dl);
     for (BaSlot &sl : b->slot) {
-        void *sdev[] = {sl.d_pack, sl.d_meta, sl.d_prob, sl.d_out, sl.d_marg, sl.d_lam_out};
+        void *sdev[] = {sl.d_pack, sl.d_meta, sl.d_prob, sl.d_out, sl.d_marg, sl.d_lam_out, sl.d_packtd};
         for (void *p : sdev) if (p) cudaFree(p);
-        void *host[] = {sl.h_pack, sl.h_meta, sl.h_prob, sl.h_out, sl.h_marg, sl.h_prior, sl.h_lam};
+        void *host[] = {sl.h_pack, sl.h_meta, sl.h_prob, sl.h_out, sl.h_marg, sl.h_prior, sl.h_lam, sl.h_packtd};
         for (void *p : host) if (p) cudaFreeHost(p);
         if (sl.done) cudaEventDestroy(sl.done);
     }
@@ -143,13 +152,15 @@ static int pack_problem(vrf_handle *h, BaSlot &sl, int slot, int seq, const VrfB
     BaState *b = h->ba;
     if (!pb || pb->n_landmarks < 0 || pb->n_landmarks > BA_MAX_LM || pb->n_obs > BA_MAX_OBS) return VRF_ERR_CAPACITY;
     if (pb->frame_count < 1 || pb->frame_count > VRF_WINDOW_SIZE) return VRF_ERR_ARG;
-    if (!pb->ex_constant || !pb->td_constant) return VRF_ERR_UNSUPPORTED;     // estimate_extrinsic / estimate_td: later rounds
+    const int td_factor = h->cfg.estimate_td != 0;
+    if (td_factor && pb->n_landmarks > 0 && (!pb->obs_velocity || !pb->obs_cur_td || !pb->obs_row)) return VRF_ERR_ARG;
     if (pb->n_landmarks > 0 && (!pb->para_Feature || !pb->lm_start_frame || !pb->lm_estimate_flag || !pb->lm_obs_ptr || !pb->obs_pts)) return VRF_ERR_ARG;
     if (pb->use_imu && !pb->imu) return VRF_ERR_ARG;
     BaHostPack &k = sl.h_pack[slot];
     memcpy(k.pose, pb->para_Pose, sizeof(k.pose));
     memcpy(k.sb, pb->para_SpeedBias, sizeof(k.sb));
     memcpy(k.ex, pb->para_Ex_Pose, sizeof(k.ex));
+    k.td = pb->para_Td;
     if (pb->use_imu) memcpy(k.imu, pb->imu, sizeof(VrfImuPreint) * pb->frame_count);
     const int M = pb->n_landmarks;
     for (int l = 0; l < M; ++l) {
@@ -165,6 +176,12 @@ static int pack_problem(vrf_handle *h, BaSlot &sl, int slot, int seq, const VrfB
     k.obs_ptr[M] = M ? pb->lm_obs_ptr[M] : 0;
     if (k.obs_ptr[M] != pb->n_obs) return VRF_ERR_ARG;
     memcpy(k.obs, pb->obs_pts, sizeof(double) * 2 * pb->n_obs);
+    if (td_factor && pb->n_obs > 0) {
+        BaHostPackTd &kt = sl.h_packtd[slot];
+        memcpy(kt.vel, pb->obs_velocity, sizeof(double) * 2 * pb->n_obs);
+        memcpy(kt.ctd, pb->obs_cur_td, sizeof(double) * pb->n_obs);
+        memcpy(kt.row, pb->obs_row, sizeof(double) * pb->n_obs);
+    }
 
     BaMeta &mt = sl.h_meta[slot];
     memset(&mt, 0, sizeof(mt));
@@ -173,6 +190,12 @@ static int pack_problem(vrf_handle *h, BaSlot &sl, int slot, int seq, const VrfB
     mt.max_iter = pb->max_iterations > 0 ? pb->max_iterations : h->cfg.num_iterations;
     mt.marg_flag = pb->marginalization_flag;
     mt.g_norm = h->cfg.g_norm;
+    // estimator.cpp:1186-1212: ex-pose / td variable or constant; ESTIMATE_TD selects ProjectionTdFactor (:1270).
+    // para_Td is only added (and possibly fixed) under USE_IMU; without IMU Ceres adds it implicitly as a variable.
+    mt.ex_active = pb->ex_constant ? 0 : 1;
+    mt.td_factor = td_factor;
+    mt.td_active = (td_factor && !(pb->use_imu && pb->td_constant)) ? 1 : 0;
+    mt.tr_over_row = h->cfg.tr / (double)h->cfg.row;
     { const char *e = getenv("VRF_BA_DEBUG"); mt.debug = e ? atoi(e) : 0; }
     mt.nimu = 0;
     if (pb->use_imu)
@@ -204,7 +227,9 @@ static int pack_problem(vrf_handle *h, BaSlot &sl, int slot, int seq, const VrfB
 
     BaProbDev &pd = sl.h_prob[slot];
     BaHostPack *dp = sl.d_pack + slot;
-    pd.pose0 = dp->pose; pd.sb0 = dp->sb; pd.ex0 = dp->ex; pd.lam0 = dp->lam;
+    pd.pose0 = dp->pose; pd.sb0 = dp->sb; pd.ex0 = dp->ex; pd.lam0 = dp->lam; pd.td0 = &dp->td;
+    if (td_factor) { BaHostPackTd *dt = sl.d_packtd + slot; pd.obs_vel = dt->vel; pd.obs_td = dt->ctd; pd.obs_row = dt->row; }
+    else { pd.obs_vel = nullptr; pd.obs_td = nullptr; pd.obs_row = nullptr; }
     pd.start = dp->start; pd.obs_ptr = dp->obs_ptr; pd.lm_const = dp->lm_const; pd.lm_ub = dp->lm_ub; pd.obs = dp->obs; pd.imu = dp->imu;
     pd.prior = have_prior ? b->d_prior[b->prior_cur[seq]] + seq : nullptr;
     pd.prior_next = b->d_prior[1 - b->prior_cur[seq]] + seq;
@@ -213,7 +238,7 @@ static int pack_problem(vrf_handle *h, BaSlot &sl, int slot, int seq, const VrfB
     pd.lam = b->d_lam + (size_t)seq * BA_MAX_LM;
     pd.lam_out = sl.d_lam_out + (size_t)slot * BA_MAX_LM;
     pd.clam = b->d_clam + (size_t)seq * BA_MAX_LM;
-    pd.W = b->d_W + (size_t)seq * BA_MAX_LM * 66;
+    pd.W = b->d_W + (size_t)seq * BA_MAX_LM * BA_WS;
     double *v = b->d_vecs + (size_t)seq * 9 * BA_MAX_LM;
     pd.hll = v; pd.gl = v + BA_MAX_LM; pd.jscale_l = v + 2 * BA_MAX_LM; pd.diag_l = v + 3 * BA_MAX_LM; pd.gd_l = v + 4 * BA_MAX_LM;
     pd.gn_l = v + 5 * BA_MAX_LM; pd.u_l = v + 6 * BA_MAX_LM; pd.y_l = v + 7 * BA_MAX_LM; pd.hinv_l = v + 8 * BA_MAX_LM;
@@ -257,6 +282,8 @@ static int upload(vrf_handle *h, BaSlot &sl, int n, const int32_t *seqs, const V
     }
     // one contiguous copy of the n packed problems (pinned staging -> HBM); far cheaper than per-array copies
     BCK(cudaMemcpyAsync(sl.d_pack, sl.h_pack, (size_t)n * sizeof(BaHostPack), cudaMemcpyHostToDevice, h->stream));
+    if (h->cfg.estimate_td)
+        BCK(cudaMemcpyAsync(sl.d_packtd, sl.h_packtd, (size_t)n * sizeof(BaHostPackTd), cudaMemcpyHostToDevice, h->stream));
     BCK(cudaMemcpyAsync(sl.d_meta, sl.h_meta, n * sizeof(BaMeta), cudaMemcpyHostToDevice, h->stream));
     BCK(cudaMemcpyAsync(sl.d_prob, sl.h_prob, n * sizeof(BaProbDev), cudaMemcpyHostToDevice, h->stream));
     BCK(cudaMemcpyAsync(sl.d_marg, sl.h_marg, n * sizeof(BaMargDev), cudaMemcpyHostToDevice, h->stream));
@@ -297,7 +324,7 @@ static int finish_download(vrf_handle *h, BaSlot &sl, int n, const int32_t *seqs
         r.status = o.status; r.iterations = o.iterations; r.successful_steps = o.successful; r.termination = o.termination;
         r.initial_cost = o.initial_cost; r.final_cost = o.final_cost;
         memcpy(r.para_Pose, o.pose, sizeof(o.pose)); memcpy(r.para_SpeedBias, o.sb, sizeof(o.sb)); memcpy(r.para_Ex_Pose, o.ex, sizeof(o.ex));
-        r.para_Td = 0.0;
+        r.para_Td = o.td;
         memcpy(r.Ps, o.Ps, sizeof(o.Ps)); memcpy(r.Rs, o.Rs, sizeof(o.Rs)); memcpy(r.Vs, o.Vs, sizeof(o.Vs));
         memcpy(r.Bas, o.Bas, sizeof(o.Bas)); memcpy(r.Bgs, o.Bgs, sizeof(o.Bgs));
         r.has_new_prior = o.has_new_prior;

@@ -36,7 +36,8 @@ struct BaShared {
     double g[BA_NC], diag[BA_NC], gd[BA_NC], gn[BA_NC], jscale[BA_NC], tmp[BA_NC], y[BA_NC + 1], colv[BA_NC + 1];
     double Lp[8][BA_NC + 5];                 // current Cholesky panel, transposed: Lp[c][row] (bank-conflict-free trailing update)
     double pose[BA_NF * 7], sb[BA_NF * 9], ex[7];
-    double cpose[BA_NF * 7], csb[BA_NF * 9];          // candidate
+    double cpose[BA_NF * 7], csb[BA_NF * 9], cex[7];  // candidate
+    double tdv[2];                                    // para_Td: current, candidate
     double R[BA_NF * 9], ric[9];
     double dx[VRF_PRIOR_MAX_DIM], pr[VRF_PRIOR_MAX_DIM];
     double imuJ[BA_NF - 1][15 * 30];                 // whitened IMU Jacobians of the current linearisation
@@ -49,8 +50,52 @@ struct BaShared {
 __device__ __forceinline__ bool col_active_dev(const BaMeta &m, int col)
 {
     if (col < 66) { int f = col / 6; return f < m.nframes && !(f == 0 && !m.use_imu); }
-    if (col < 165) { int f = (col - 66) / 9; return m.use_imu && f < m.nframes; }
-    return false;        // ex-pose constant in this build
+    if (col < BA_COL_EX) { int f = (col - 66) / 9; return m.use_imu && f < m.nframes; }
+    return col == BA_COL_TD ? m.td_active != 0 : m.ex_active != 0;
+}
+
+// Contributions of one batch of projection factors of the pair (host i, observer j) to the rows of the "global"
+// block g = [ex-pose (6) | td (1)] (tangent columns 165..171), only when one of them is variable:
+// Jg^T Ji, Jg^T Jj, Jg^T r and the lower triangle of Jg^T Jg, each summed over the warp's lanes with the
+// reduce-scatter butterfly and added to the shared system.  Jg: 2 x 7 row-major.
+__device__ __forceinline__ double reduce_scatter16(double (&v)[16], int lane);
+__device__ __noinline__ void accumulate_g(double *H, double *g, int i, int j, int lane, const double *Ji, const double *Jj,
+                                          const double *Jg, const double *r)
+{
+#pragma unroll 1
+    for (int q = 0; q < 7; ++q) {
+        double v[16];
+        const double g0 = Jg[q], g1 = Jg[7 + q];
+#pragma unroll
+        for (int c = 0; c < 6; ++c) { v[c] = g0 * Ji[c] + g1 * Ji[6 + c]; v[6 + c] = g0 * Jj[c] + g1 * Jj[6 + c]; }
+        v[12] = g0 * r[0] + g1 * r[1]; v[13] = 0; v[14] = 0; v[15] = 0;
+        const double s_ = reduce_scatter16(v, lane);
+        if (!(lane & 1) && s_ != 0.0) {
+            const int e = lane >> 1;
+            if (e < 6) atomicAdd(&H[pk(BA_COL_EX + q, 6 * i + e)], s_);
+            else if (e < 12) atomicAdd(&H[pk(BA_COL_EX + q, 6 * j + e - 6)], s_);
+            else if (e == 12) atomicAdd(&g[BA_COL_EX + q], s_);
+        }
+    }
+#pragma unroll 1
+    for (int rd = 0; rd < 2; ++rd) {
+        double v[16];
+#pragma unroll
+        for (int t = 0; t < 16; ++t) {
+            const int e = rd * 16 + t;
+            int a = 0;
+            while ((a + 1) * (a + 2) / 2 <= e) ++a;
+            const int b = e - a * (a + 1) / 2;
+            v[t] = (e < 28) ? Jg[a] * Jg[b] + Jg[7 + a] * Jg[7 + b] : 0.0;
+        }
+        const double s_ = reduce_scatter16(v, lane);
+        const int e = rd * 16 + (lane >> 1);
+        if (!(lane & 1) && e < 28 && s_ != 0.0) {
+            int a = 0;
+            while ((a + 1) * (a + 2) / 2 <= e) ++a;
+            atomicAdd(&H[pk(BA_COL_EX + a, BA_COL_EX + e - a * (a + 1) / 2)], s_);
+        }
+    }
 }
 
 #define BA_NPAIR (BA_NF * (BA_NF - 1) / 2)
@@ -98,19 +143,22 @@ __device__ __forceinline__ double reduce_scatter16(double (&v)[16], int lane)
 // cost of all residual blocks at (pose, sb, lam); optionally the full linearisation into sh.H / sh.g / landmark arrays.
 // __noinline__: the solve loop calls this from five sites; inlining produced a 51k-instruction kernel (800 KB of SASS)
 // that thrashed the instruction cache (one resident CTA per SM, 16 warps in different code regions).
-__device__ __noinline__ double ba_evaluate(const BaMeta &m, const BaProbDev &p, BaShared &sh, const double *pose, const double *sb,
-                              const double *lam, bool lin)
+// GACT: ex-pose and/or td variable (two instantiations so that the common constant-extrinsic path keeps its registers).
+template <bool GACT>
+__device__ __noinline__ double ba_evaluate_t(const BaMeta &m, const BaProbDev &p, BaShared &sh, const double *pose, const double *sb,
+                                const double *ex, const double td, const double *lam, bool lin)
 {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = BA_THREADS / 32;
     if (lin) {
         for (int i = tid; i < BA_NC * (BA_NC + 1) / 2; i += BA_THREADS) sh.H[i] = 0.0;
         for (int i = tid; i < BA_NC; i += BA_THREADS) sh.g[i] = 0.0;
         for (int i = tid; i < BA_NPAIR * 54; i += BA_THREADS) (&sh.imuJ[0][0])[i] = 0.0;      // per-pair partials (see below)
-        for (int i = tid; i < m.M * 66; i += BA_THREADS) p.W[i] = 0.0;
+        for (int i = tid; i < m.M * BA_WS; i += BA_THREADS) p.W[i] = 0.0;
         for (int l = tid; l < m.M; l += BA_THREADS) { p.hll[l] = 0.0; p.gl[l] = 0.0; }
     }
     for (int f = tid; f < BA_NF; f += BA_THREADS) d_q2R(pose + 7 * f + 3, sh.R + 9 * f);
-    if (tid == 0) d_q2R(sh.ex + 3, sh.ric);
+    if (tid == 0) d_q2R(ex + 3, sh.ric);
+    constexpr bool gact = GACT;
     const bool eprof = (m.debug & 16) != 0;
     long long et[5] = {0, 0, 0, 0, 0}, ec = eprof ? clock64() : 0;
 #define EPROF(k) do { if (eprof) { long long t_ = clock64(); et[k] += t_ - ec; ec = t_; } } while (0)
@@ -126,9 +174,10 @@ __device__ __noinline__ double ba_evaluate(const BaMeta &m, const BaProbDev &p, 
             const int o0 = p.obs_ptr[l], nf = p.obs_ptr[l + 1] - o0 - 1;
             if (hl >= nf) continue;
             const int i = p.start[l], j = i + 1 + hl;
-            double r[2], Ji[12], Jj[12], Jl[2];
-            cost += 0.5 * proj_eval(pose + 7 * i, sh.R + 9 * i, pose + 7 * j, sh.R + 9 * j, sh.ex, sh.ric, lam[l], p.obs[2 * o0],
-                                    p.obs[2 * o0 + 1], p.obs[2 * (o0 + 1 + hl)], p.obs[2 * (o0 + 1 + hl) + 1], false,
+            double r[2], Ji[12], Jj[12], Jl[2], xi, yi, xj, yj;
+            obs_at(m, p, o0, td, xi, yi);
+            obs_at(m, p, o0 + 1 + hl, td, xj, yj);
+            cost += 0.5 * proj_eval(pose + 7 * i, sh.R + 9 * i, pose + 7 * j, sh.R + 9 * j, ex, sh.ric, lam[l], xi, yi, xj, yj, false,
                                     p.lm_const[l] != 0, r, Ji, Jj, Jl);
         }
     } else {
@@ -157,16 +206,35 @@ __device__ __noinline__ double ba_evaluate(const BaMeta &m, const BaProbDev &p, 
                 if (!__any_sync(0xffffffffu, act)) continue;
                 any_pair = true;
                 double r[2] = {0, 0}, Ji[12], Jj[12], Jl[2] = {0, 0};
+                double Jg[14];          // [ex-pose | td] block, only touched when one of them is variable
 #pragma unroll
                 for (int k = 0; k < 12; ++k) { Ji[k] = 0; Jj[k] = 0; }
+                if (gact) {
+#pragma unroll
+                    for (int k = 0; k < 14; ++k) Jg[k] = 0;
+                }
                 if (act) {
                     const int oj = o0 + (j - i);
-                    const double rho0 = proj_eval(pose + 7 * i, sh.R + 9 * i, pose + 7 * j, sh.R + 9 * j, sh.ex, sh.ric, lam[l],
-                                                  p.obs[2 * o0], p.obs[2 * o0 + 1], p.obs[2 * oj], p.obs[2 * oj + 1], true,
-                                                  p.lm_const[l] != 0, r, Ji, Jj, Jl);
+                    double xi, yi, xj, yj, rho0;
+                    obs_at(m, p, o0, td, xi, yi);
+                    obs_at(m, p, oj, td, xj, yj);
+                    double *Wl = p.W + (size_t)l * BA_WS;
+                    if (!gact)
+                        rho0 = proj_eval(pose + 7 * i, sh.R + 9 * i, pose + 7 * j, sh.R + 9 * j, ex, sh.ric, lam[l], xi, yi, xj, yj, true,
+                                         p.lm_const[l] != 0, r, Ji, Jj, Jl);
+                    else {
+                        double Je[12], Jt[2] = {0, 0};
+                        rho0 = proj_eval(pose + 7 * i, sh.R + 9 * i, pose + 7 * j, sh.R + 9 * j, ex, sh.ric, lam[l], xi, yi, xj, yj, true,
+                                         p.lm_const[l] != 0, r, Ji, Jj, Jl, Je, m.td_active ? p.obs_vel + 2 * o0 : nullptr,
+                                         m.td_active ? p.obs_vel + 2 * oj : nullptr, m.td_active ? Jt : nullptr);
+#pragma unroll
+                        for (int c = 0; c < 6; ++c) { Jg[c] = m.ex_active ? Je[c] : 0.0; Jg[7 + c] = m.ex_active ? Je[6 + c] : 0.0; }
+                        Jg[6] = Jt[0]; Jg[13] = Jt[1];
+#pragma unroll
+                        for (int q = 0; q < 7; ++q) atomicAdd(&Wl[66 + q], Jg[q] * Jl[0] + Jg[7 + q] * Jl[1]);
+                    }
                     cost += 0.5 * rho0;
                     // landmark rows: the observer part has one contributor, the rest sums over the landmark's factors
-                    double *Wl = p.W + (size_t)l * 66;
 #pragma unroll
                     for (int a = 0; a < 6; ++a) {
                         Wl[6 * j + a] = Jj[a] * Jl[0] + Jj[6 + a] * Jl[1];
@@ -175,6 +243,7 @@ __device__ __noinline__ double ba_evaluate(const BaMeta &m, const BaProbDev &p, 
                     atomicAdd(&p.hll[l], Jl[0] * Jl[0] + Jl[1] * Jl[1]);
                     atomicAdd(&p.gl[l], Jl[0] * r[0] + Jl[1] * r[1]);
                 }
+                if (gact) accumulate_g(sh.H, sh.g, i, j, lane, Ji, Jj, Jg, r);
 #pragma unroll
                 for (int ps = 0; ps < 6; ++ps) {
                     double v[16];
@@ -251,7 +320,7 @@ __device__ __noinline__ double ba_evaluate(const BaMeta &m, const BaProbDev &p, 
     const BaPriorStore *P = p.prior;
     const int np_ = (P && P->valid) ? P->n : 0;
     if (np_ > 0) {
-        prior_dx(P, pose, sb, sh.ex, sh.dx);
+        prior_dx(P, pose, sb, ex, td, sh.dx);
         __syncthreads();
         const int n = np_;
         for (int rI = tid; rI < n; rI += BA_THREADS) {
@@ -288,6 +357,13 @@ __device__ __noinline__ double ba_evaluate(const BaMeta &m, const BaProbDev &p, 
     return block_sum(cost, sh.red);
 }
 
+__device__ __forceinline__ double ba_evaluate(const BaMeta &m, const BaProbDev &p, BaShared &sh, const double *pose, const double *sb,
+                                              const double *ex, const double td, const double *lam, bool lin)
+{
+    return (m.ex_active || m.td_active) ? ba_evaluate_t<true>(m, p, sh, pose, sb, ex, td, lam, lin)
+                                        : ba_evaluate_t<false>(m, p, sh, pose, sb, ex, td, lam, lin);
+}
+
 // scale a fresh linearisation: H_s = D H D, g_s = D g, W_s, hll_s, gl_s (Jacobi scaling of the Jacobian columns)
 __device__ __noinline__ void ba_scale(const BaMeta &m, const BaProbDev &p, BaShared &sh)
 {
@@ -300,8 +376,8 @@ __device__ __noinline__ void ba_scale(const BaMeta &m, const BaProbDev &p, BaSha
     for (int c = tid; c < BA_NC; c += BA_THREADS) sh.g[c] *= sh.jscale[c];
     for (int l = warp; l < m.M; l += nwarp) {
         const double sl = p.jscale_l[l];
-        double *Wl = p.W + (size_t)l * 66;
-        for (int k = lane; k < 66; k += 32) Wl[k] *= sl * sh.jscale[k];
+        double *Wl = p.W + (size_t)l * BA_WS;
+        for (int k = lane; k < BA_WS; k += 32) Wl[k] *= sl * sh.jscale[wcol(k)];
         if (lane == 0) { p.hll[l] *= sl * sl; p.gl[l] *= sl; }
     }
     __syncthreads();
@@ -331,7 +407,9 @@ k_ba_solve(const BaMeta *metas, const BaProbDev *probs, BaOutDev *outs)
     for (int i = tid; i < BA_NF * 7; i += BA_THREADS) sh.pose[i] = p.pose0[i];
     for (int i = tid; i < BA_NF * 9; i += BA_THREADS) sh.sb[i] = p.sb0[i];
     if (tid < 7) sh.ex[tid] = p.ex0[tid];
+    if (tid == 0) { sh.tdv[0] = *p.td0; sh.tdv[1] = *p.td0; }
     for (int l = tid; l < M; l += BA_THREADS) p.lam[l] = p.lam0[l];
+    const int ws = (m.ex_active || m.td_active) ? BA_WS : 66;      // used width of the landmark coupling rows
     __syncthreads();
     // ---- once per solve: IMU information square roots, prior normal matrix ----
     {
@@ -351,7 +429,8 @@ k_ba_solve(const BaMeta *metas, const BaProbDev *probs, BaOutDev *outs)
         if (n > 0)
             for (int b = tid; b < P->n_blocks; b += BA_THREADS) {
                 const int kind = P->kind[b], ls = P->size[b] == 7 ? 6 : P->size[b];
-                int col = kind == VRF_BLK_POSE ? 6 * P->index[b] : kind == VRF_BLK_SPEEDBIAS ? 66 + 9 * P->index[b] : -1;
+                int col = kind == VRF_BLK_POSE ? 6 * P->index[b] : kind == VRF_BLK_SPEEDBIAS ? 66 + 9 * P->index[b]
+                          : kind == VRF_BLK_EXPOSE ? BA_COL_EX : kind == VRF_BLK_TD ? BA_COL_TD : -1;
                 if (col >= 0 && !col_active_dev(m, col)) col = -1;
                 for (int c = 0; c < ls; ++c) p.colmap[P->idx[b] + c] = col < 0 ? -1 : col + c;
             }
@@ -362,7 +441,7 @@ k_ba_solve(const BaMeta *metas, const BaProbDev *probs, BaOutDev *outs)
     const long long t_kernel0 = t_kernel00;
     long long tprof[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tmark = clock64();
 #define TPROF(k) do { long long t_ = clock64(); tprof[k] += t_ - tmark; tmark = t_; } while (0)
-    double x_cost = ba_evaluate(m, p, sh, sh.pose, sh.sb, p.lam, true);
+    double x_cost = ba_evaluate(m, p, sh, sh.pose, sh.sb, sh.ex, sh.tdv[0], p.lam, true);
     TPROF(0);
     const double initial_cost = x_cost;
     // Jacobi scaling (once): 1 / (1 + ||column||)
@@ -380,6 +459,8 @@ k_ba_solve(const BaMeta *metas, const BaProbDev *probs, BaOutDev *outs)
 
     auto xnorm2 = [&](const double *pose, const double *sb, const double *lam) {
         double v = 0;
+        if (m.ex_active && tid < 7) v += sh.ex[tid] * sh.ex[tid];
+        if (m.td_active && tid == 7) v += sh.tdv[0] * sh.tdv[0];
         for (int i = tid; i < BA_NF * 7; i += BA_THREADS) if (col_active_dev(m, 6 * (i / 7))) v += pose[i] * pose[i];
         for (int i = tid; i < BA_NF * 9; i += BA_THREADS) if (col_active_dev(m, 66 + 9 * (i / 9))) v += sb[i] * sb[i];
         for (int l = tid; l < M; l += BA_THREADS) if (!p.lm_const[l]) v += lam[l] * lam[l];
@@ -403,6 +484,13 @@ k_ba_solve(const BaMeta *metas, const BaProbDev *probs, BaOutDev *outs)
                     if (col_active_dev(m, 66 + 9 * f))
                         for (int k = 0; k < 9; ++k) mx = fmax(mx, fabs(sh.g[66 + 9 * f + k] / sh.jscale[66 + 9 * f + k]));
                 }
+                if (m.ex_active && tid == 32) {
+                    double dl[6], o[7];
+                    for (int k = 0; k < 6; ++k) dl[k] = -sh.g[BA_COL_EX + k] / sh.jscale[BA_COL_EX + k];
+                    d_pose_plus(sh.ex, dl, o);
+                    for (int k = 0; k < 7; ++k) mx = fmax(mx, fabs(sh.ex[k] - o[k]));
+                }
+                if (m.td_active && tid == 33) mx = fmax(mx, fabs(sh.g[BA_COL_TD] / sh.jscale[BA_COL_TD]));
                 for (int l = tid; l < M; l += BA_THREADS) {
                     if (p.lm_const[l]) continue;
                     double v = p.lam[l] + (-p.gl[l] / p.jscale_l[l]);
@@ -449,9 +537,9 @@ k_ba_solve(const BaMeta *metas, const BaProbDev *probs, BaOutDev *outs)
                 }
                 for (int l = warp; l < M; l += nwarp) {
                     if (p.lm_const[l]) continue;
-                    const double *Wl = p.W + (size_t)l * 66;
+                    const double *Wl = p.W + (size_t)l * BA_WS;
                     double wv = 0;
-                    for (int k = lane; k < 66; k += 32) wv += Wl[k] * sh.tmp[k];
+                    for (int k = lane; k < ws; k += 32) wv += Wl[k] * sh.tmp[wcol(k)];
                     wv = warp_sum_d(wv);
                     if (lane == 0) v += 2.0 * p.u_l[l] * wv + p.hll[l] * p.u_l[l] * p.u_l[l];
                 }
@@ -483,41 +571,43 @@ k_ba_solve(const BaMeta *metas, const BaProbDev *probs, BaOutDev *outs)
                     if (p.lm_const[l]) continue;
                     const double hl = p.hll[l] + mu * p.diag_l[l] * p.diag_l[l];
                     if (!(hl > 0)) { if (lane == 0) sh.flag[0] = 1; continue; }
-                    const double *Wl = p.W + (size_t)l * 66;
+                    const double *Wl = p.W + (size_t)l * BA_WS;
                     const double gl_h = p.gl[l] / hl;
-                    for (int k = lane; k < 66; k += 32) { double w = Wl[k]; if (w != 0.0) atomicAdd(&sh.y[k], -w * gl_h); }
+                    for (int k = lane; k < ws; k += 32) { double w = Wl[k]; if (w != 0.0) atomicAdd(&sh.y[wcol(k)], -w * gl_h); }
                     if (lane == 0) p.hinv_l[l] = 1.0 / hl;
                 }
                 __syncthreads();
-                // S = H + mu D^2 - W^T diag(1/h) W on the 66x66 pose block.  W is streamed through a
-                // shared-memory tile (64 landmarks x 66, pre-multiplied by 1/sqrt(h)); every thread owns
-                // a fixed set of the 2211 output entries, so the reduction is deterministic and atomic-free.
+                // S = H + mu D^2 - W^T diag(1/h) W on the pose block (66 columns; + ex-pose and td when variable: ws = 73).
+                // W is streamed through a shared-memory tile (up to 64 landmarks x ws, pre-multiplied by 1/sqrt(h));
+                // every thread owns a fixed set of the ws(ws+1)/2 output entries, so the reduction is deterministic
+                // and atomic-free.
                 {
-                    double *tile = reinterpret_cast<double *>(sh.imuJ);      // 4500 doubles available, 64*66 = 4224 used
-                    int ea[5], eb[5], ne = 0;
-                    double acc[5] = {0, 0, 0, 0, 0};
-                    for (int e = tid; e < 66 * 67 / 2 && ne < 5; e += BA_THREADS) {
+                    double *tile = reinterpret_cast<double *>(sh.imuJ);      // 4500 doubles available
+                    const int tl = ws == 66 ? 64 : 61;                        // 64*66 = 4224, 61*73 = 4453
+                    int ea[6], eb[6], ne = 0;
+                    double acc[6] = {0, 0, 0, 0, 0, 0};
+                    for (int e = tid; e < ws * (ws + 1) / 2 && ne < 6; e += BA_THREADS) {
                         int a = (int)((sqrt(8.0 * e + 1.0) - 1.0) * 0.5);
                         while (a * (a + 1) / 2 > e) --a;
                         while ((a + 1) * (a + 2) / 2 <= e) ++a;
                         ea[ne] = a; eb[ne] = e - a * (a + 1) / 2; ++ne;
                     }
-                    for (int t0 = 0; t0 < M; t0 += 64) {
-                        const int nt = min(64, M - t0);
-                        for (int q = tid; q < nt * 66; q += BA_THREADS) {
-                            int l = t0 + q / 66, k = q - (q / 66) * 66;
-                            tile[q] = p.lm_const[l] ? 0.0 : p.W[(size_t)l * 66 + k] * sqrt(p.hinv_l[l]);
+                    for (int t0 = 0; t0 < M; t0 += tl) {
+                        const int nt = min(tl, M - t0);
+                        for (int q = tid; q < nt * ws; q += BA_THREADS) {
+                            int l = t0 + q / ws, k = q - (q / ws) * ws;
+                            tile[q] = p.lm_const[l] ? 0.0 : p.W[(size_t)l * BA_WS + k] * sqrt(p.hinv_l[l]);
                         }
                         __syncthreads();
                         for (int q = 0; q < ne; ++q) {
                             double s_ = 0;
                             const double *ta = tile + ea[q], *tb = tile + eb[q];
-                            for (int l = 0; l < nt; ++l) s_ += ta[l * 66] * tb[l * 66];
+                            for (int l = 0; l < nt; ++l) s_ += ta[l * ws] * tb[l * ws];
                             acc[q] += s_;
                         }
                         __syncthreads();
                     }
-                    for (int q = 0; q < ne; ++q) sh.H[ea[q] * (ea[q] + 1) / 2 + eb[q]] -= acc[q];
+                    for (int q = 0; q < ne; ++q) sh.H[pk(wcol(ea[q]), wcol(eb[q]))] -= acc[q];
                 }
                 __syncthreads();      // the diagonal entries are touched again just below by other threads
                 for (int c = tid; c < BA_NC; c += BA_THREADS) sh.H[pk(c, c)] += mu * sh.diag[c] * sh.diag[c];
@@ -628,8 +718,8 @@ k_ba_solve(const BaMeta *metas, const BaProbDev *probs, BaOutDev *outs)
                         for (int l = warp; l < M; l += nwarp) {
                             double v = 0;
                             if (!p.lm_const[l]) {
-                                const double *Wl = p.W + (size_t)l * 66;
-                                for (int k = lane; k < 66; k += 32) v += Wl[k] * sh.y[k];
+                                const double *Wl = p.W + (size_t)l * BA_WS;
+                                for (int k = lane; k < ws; k += 32) v += Wl[k] * sh.y[wcol(k)];
                                 v = warp_sum_d(v);
                                 v = (p.gl[l] - v) * p.hinv_l[l];
                             }
@@ -642,7 +732,7 @@ k_ba_solve(const BaMeta *metas, const BaProbDev *probs, BaOutDev *outs)
                 if (solved) break;
                 // failed: the in-place factorisation destroyed H => re-linearise and retry with a larger mu
                 mu *= mu_inc;
-                ba_evaluate(m, p, sh, sh.pose, sh.sb, p.lam, true);
+                ba_evaluate(m, p, sh, sh.pose, sh.sb, sh.ex, sh.tdv[0], p.lam, true);
                 ba_scale(m, p, sh);
             }
             TPROF(5);
@@ -704,6 +794,15 @@ k_ba_solve(const BaMeta *metas, const BaProbDev *probs, BaOutDev *outs)
                         sh.csb[9 * f + k] = sh.sb[9 * f + k] + (col_active_dev(m, c) ? (c1 * sh.gd[c] + c2 * sh.gn[c]) / sh.diag[c] * sh.jscale[c] : 0.0);
                     }
                 }
+                if (tid == 64) {
+                    if (m.ex_active) {
+                        double dl[6];
+                        for (int k = 0; k < 6; ++k) { int c = BA_COL_EX + k; dl[k] = (c1 * sh.gd[c] + c2 * sh.gn[c]) / sh.diag[c] * sh.jscale[c]; }
+                        d_pose_plus(sh.ex, dl, sh.cex);
+                    } else for (int k = 0; k < 7; ++k) sh.cex[k] = sh.ex[k];
+                    const int c = BA_COL_TD;
+                    sh.tdv[1] = sh.tdv[0] + (m.td_active ? (c1 * sh.gd[c] + c2 * sh.gn[c]) / sh.diag[c] * sh.jscale[c] : 0.0);
+                }
                 for (int l = tid; l < M; l += BA_THREADS) {
                     double v = p.lam[l];
                     if (!p.lm_const[l]) {
@@ -714,13 +813,15 @@ k_ba_solve(const BaMeta *metas, const BaProbDev *probs, BaOutDev *outs)
                 }
                 __syncthreads();
                 TPROF(6);
-                const double cand_cost = ba_evaluate(m, p, sh, sh.cpose, sh.csb, p.clam, false);
+                const double cand_cost = ba_evaluate(m, p, sh, sh.cpose, sh.csb, sh.cex, sh.tdv[1], p.clam, false);
                 TPROF(7);
                 // step norm over the non-constant blocks (ambient space)
                 double sn = 0;
                 for (int i = tid; i < BA_NF * 7; i += BA_THREADS) if (col_active_dev(m, 6 * (i / 7))) { double dd = sh.pose[i] - sh.cpose[i]; sn += dd * dd; }
                 for (int i = tid; i < BA_NF * 9; i += BA_THREADS) if (col_active_dev(m, 66 + 9 * (i / 9))) { double dd = sh.sb[i] - sh.csb[i]; sn += dd * dd; }
                 for (int l = tid; l < M; l += BA_THREADS) if (!p.lm_const[l]) { double dd = p.lam[l] - p.clam[l]; sn += dd * dd; }
+                if (m.ex_active && tid < 7) { double dd = sh.ex[tid] - sh.cex[tid]; sn += dd * dd; }
+                if (m.td_active && tid == 7) { double dd = sh.tdv[0] - sh.tdv[1]; sn += dd * dd; }
                 const double step_norm = sqrt(block_sum(sn, sh.red));
                 if (step_norm <= 1e-8 * (x_norm + 1e-8)) { termination = 3; break; }
                 const double cost_change = x_cost - cand_cost;
@@ -733,11 +834,13 @@ k_ba_solve(const BaMeta *metas, const BaProbDev *probs, BaOutDev *outs)
                     for (int i = tid; i < BA_NF * 7; i += BA_THREADS) sh.pose[i] = sh.cpose[i];
                     for (int i = tid; i < BA_NF * 9; i += BA_THREADS) sh.sb[i] = sh.csb[i];
                     for (int l = tid; l < M; l += BA_THREADS) p.lam[l] = p.clam[l];
+                    if (tid < 7) sh.ex[tid] = sh.cex[tid];
+                    if (tid == 7) sh.tdv[0] = sh.tdv[1];
                     __syncthreads();
                     x_cost = cand_cost;
                     x_norm = sqrt(xnorm2(sh.pose, sh.sb, p.lam));
                     TPROF(6);
-                    ba_evaluate(m, p, sh, sh.pose, sh.sb, p.lam, true);
+                    ba_evaluate(m, p, sh, sh.pose, sh.sb, sh.ex, sh.tdv[0], p.lam, true);
                     TPROF(0);
                     need_scale = 1;
                     ++successful;
@@ -757,7 +860,7 @@ k_ba_solve(const BaMeta *metas, const BaProbDev *probs, BaOutDev *outs)
         reuse = 0;
         if (status == VRF_SOFT_NOT_SPD && mu >= max_mu) { termination = 5; break; }
         // H was consumed by the failed factorisation attempts: rebuild it
-        ba_evaluate(m, p, sh, sh.pose, sh.sb, p.lam, true);
+        ba_evaluate(m, p, sh, sh.pose, sh.sb, sh.ex, sh.tdv[0], p.lam, true);
         need_scale = 1;
     }
     __syncthreads();
@@ -826,6 +929,7 @@ k_ba_solve(const BaMeta *metas, const BaProbDev *probs, BaOutDev *outs)
     if (nf_ > 0) status = VRF_SOFT_NONFINITE;
     for (int i = tid; i < BA_NF * 9; i += BA_THREADS) out.sb[i] = sh.sb[i];
     if (tid < 7) out.ex[tid] = sh.ex[tid];
+    if (tid == 7) { out.td = sh.tdv[0]; out.mtd = sh.tdv[0]; }
     __syncthreads();
     if (tid == 0) {
         out.status = status; out.iterations = iterations; out.successful = successful; out.termination = termination;

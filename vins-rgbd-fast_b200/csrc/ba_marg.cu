@@ -22,7 +22,7 @@ struct MargShared {
     int kind[64], index[64], lsize[64], gsize[64], idx[64], present[64], drop[64];
     int nb, m, n, pos, first_kept, go;
     int chunk[BA_MAX_LM / 32], maxobs, lm0, jdbg;
-    int col_pose[BA_NF], col_sb[BA_NF], col_ex;
+    int col_pose[BA_NF], col_sb[BA_NF], col_ex, col_td;
     double red[BA_THREADS / 32];
     __align__(16) double cs[2 * (BA_MAX_POS / 2 + 2)];
     __align__(16) double cs_b[2 * (BA_MAX_POS / 2 + 2)];
@@ -287,6 +287,8 @@ __device__ __forceinline__ int find_block(const MargShared &sh, int kind, int in
 }
 
 #define MK_LM 100
+#define MG_L 73                         // local columns of the on-chip projection system: pose f -> 6f, ex-pose -> 66, td -> 72
+#define MG_LP (MG_L * (MG_L + 1) / 2)
 
 __global__ void __launch_bounds__(BA_THREADS, 1)
 k_ba_marg(const BaMeta *metas, const BaProbDev *probs, BaOutDev *outs, const BaMargDev *margs)
@@ -329,6 +331,7 @@ k_ba_marg(const BaMeta *metas, const BaProbDev *probs, BaOutDev *outs, const BaM
             else add(VRF_BLK_POSE, VRF_WINDOW_SIZE - 1, 7, 1);
             sh.first_kept = nb;
             add(VRF_BLK_EXPOSE, 0, 7, 0);
+            add(VRF_BLK_TD, 0, 1, 0);
             for (int f = 0; f < BA_NF; ++f) add(VRF_BLK_POSE, f, 7, 0);
             for (int f = 0; f < BA_NF; ++f) add(VRF_BLK_SPEEDBIAS, f, 9, 0);
             sh.nb = nb;
@@ -370,6 +373,7 @@ k_ba_marg(const BaMeta *metas, const BaProbDev *probs, BaOutDev *outs, const BaM
             if (nl0 > 0) {
                 sh.present[find_block(sh, VRF_BLK_POSE, 0)] = 1;
                 sh.present[find_block(sh, VRF_BLK_EXPOSE, 0)] = 1;
+                if (m.td_factor) sh.present[find_block(sh, VRF_BLK_TD, 0)] = 1;      // ProjectionTdFactor keeps para_Td (estimator.cpp:1445-1458)
                 for (int k = 1; k < sh.maxobs; ++k) sh.present[find_block(sh, VRF_BLK_POSE, k)] = 1;
             }
             if (nl0 > BA_MAX_M0) { sh.go = 0; sh.flag = VRF_ERR_CAPACITY; }
@@ -386,6 +390,7 @@ k_ba_marg(const BaMeta *metas, const BaProbDev *probs, BaOutDev *outs, const BaM
                 i = find_block(sh, VRF_BLK_SPEEDBIAS, f); sh.col_sb[f] = (i >= 0 && sh.present[i]) ? sh.idx[i] : -1;
             }
             { int i = find_block(sh, VRF_BLK_EXPOSE, 0); sh.col_ex = (i >= 0 && sh.present[i]) ? sh.idx[i] : -1; }
+            { int i = find_block(sh, VRF_BLK_TD, 0); sh.col_td = (i >= 0 && sh.present[i]) ? sh.idx[i] : -1; }
         }
     }
     __syncthreads();
@@ -416,7 +421,7 @@ k_ba_marg(const BaMeta *metas, const BaProbDev *probs, BaOutDev *outs, const BaM
     if (P) {
         const int np = P->n;
         // residual at the current (gauge-fixed) states
-        prior_dx(P, pose, sb, ex, sh.dx);
+        prior_dx(P, pose, sb, ex, out.mtd, sh.dx);
         __syncthreads();
         for (int rI = tid; rI < np; rI += BA_THREADS) {
             double a = P->r0[rI];
@@ -472,19 +477,19 @@ k_ba_marg(const BaMeta *metas, const BaProbDev *probs, BaOutDev *outs, const BaM
     }
     __syncthreads();
     // ---- 2c. projection factors hosted at frame 0 (all four parameter blocks, Cauchy corrector) ----
-    // Accumulated on chip: the pose/ex-pose part in a packed 72x72 block in shared memory
-    // (local index: pose f -> 6f, ex-pose -> 66), the landmark rows (coupling w[72], h, g) in HBM.
+    // Accumulated on chip: the pose / ex-pose / td part in a packed MG_L x MG_L block in shared memory
+    // (local index: pose f -> 6f, ex-pose -> 66, td -> 72), the landmark rows (coupling w[MG_L], h, g) in HBM.
     double *big0 = reinterpret_cast<double *>(smem_raw + ((sizeof(MargShared) + 15) & ~(size_t)15));
-    double *H72 = big0;                     // 72*73/2 = 2628
-    double *g72 = big0 + 2628;              // 72
-    double *Wm = mg.Ainv;                   // [nl0][72] landmark coupling rows (Ainv is only used by the slow path, later)
+    double *H72 = big0;                     // MG_LP
+    double *g72 = big0 + MG_LP;             // MG_L
+    double *Wm = mg.Ainv;                   // [nl0][MG_L] landmark coupling rows (Ainv is only used by the slow path, later)
     double *hm = mg.V2;                     // [nl0] h, then [nl0] g   (V2 is only needed by the second decomposition)
     int lm0c = 0;
     for (int i = 0; i < sh.first_kept; ++i) if (sh.present[i]) lm0c += sh.lsize[i];
     const int nl0c = mm - lm0c;
     if (flag == VRF_MARGIN_OLD && nl0c > 0) {
-        for (int e = tid; e < 2628 + 72; e += BA_THREADS) big0[e] = 0.0;
-        for (int e = tid; e < nl0c * 72; e += BA_THREADS) Wm[e] = 0.0;
+        for (int e = tid; e < MG_LP + MG_L; e += BA_THREADS) big0[e] = 0.0;
+        for (int e = tid; e < nl0c * MG_L; e += BA_THREADS) Wm[e] = 0.0;
         __syncthreads();
         auto pk72 = [](int a_, int b_) { return a_ >= b_ ? a_ * (a_ + 1) / 2 + b_ : b_ * (b_ + 1) / 2 + a_; };
         for (int l = warp; l < M; l += nwarp) {
@@ -494,17 +499,23 @@ k_ba_marg(const BaMeta *metas, const BaProbDev *probs, BaOutDev *outs, const BaM
             const int o0 = p.obs_ptr[l], nf = p.obs_ptr[l + 1] - o0 - 1;
             const bool act = lane < nf;
             const int j = 1 + lane;
-            double r[2] = {0, 0}, Ji[12], Jj[12], Jl[2] = {0, 0}, Je[12];
-            if (act)
-                proj_eval(pose, sh.R, pose + 7 * j, sh.R + 9 * j, ex, sh.ric, lam[l], p.obs[2 * o0], p.obs[2 * o0 + 1],
-                          p.obs[2 * (o0 + j)], p.obs[2 * (o0 + j) + 1], true, false, r, Ji, Jj, Jl, Je);
+            double r[2] = {0, 0}, Ji[12], Jj[12], Jl[2] = {0, 0}, Je[12], Jt[2] = {0, 0};
+            if (act) {
+                double xi, yi, xj, yj;
+                obs_at(m, p, o0, out.mtd, xi, yi);
+                obs_at(m, p, o0 + j, out.mtd, xj, yj);
+                proj_eval(pose, sh.R, pose + 7 * j, sh.R + 9 * j, ex, sh.ric, lam[l], xi, yi, xj, yj, true, false, r, Ji, Jj, Jl, Je,
+                          m.td_factor ? p.obs_vel + 2 * o0 : nullptr, m.td_factor ? p.obs_vel + 2 * (o0 + j) : nullptr,
+                          m.td_factor ? Jt : nullptr);
+            }
             const double hsum = warp_sum_d(Jl[0] * Jl[0] + Jl[1] * Jl[1]);
             const double gsum = warp_sum_d(Jl[0] * r[0] + Jl[1] * r[1]);
             if (lane == 0) { hm[li] = hsum; hm[nl0c + li] = gsum; }
             if (!act) continue;
-            double *wr = Wm + (size_t)li * 72;
-            // 18 local columns of this factor: pose0 (0..5), pose j (6j..), ex (66..)
-            int lc[18]; double J0r[18], J1r[18];
+            double *wr = Wm + (size_t)li * MG_L;
+            // 19 local columns of this factor: pose0 (0..5), pose j (6j..), ex (66..), td (72; zero unless ESTIMATE_TD)
+            int lc[19]; double J0r[19], J1r[19];
+            lc[18] = 72; J0r[18] = Jt[0]; J1r[18] = Jt[1];
 #pragma unroll
             for (int c = 0; c < 6; ++c) {
                 lc[c] = c; J0r[c] = Ji[c]; J1r[c] = Ji[6 + c];
@@ -512,7 +523,8 @@ k_ba_marg(const BaMeta *metas, const BaProbDev *probs, BaOutDev *outs, const BaM
                 lc[12 + c] = 66 + c; J0r[12 + c] = Je[c]; J1r[12 + c] = Je[6 + c];
             }
 #pragma unroll
-            for (int a_ = 0; a_ < 18; ++a_) {
+            for (int a_ = 0; a_ < 19; ++a_) {
+                if (a_ == 18 && !m.td_factor) break;
                 atomicAdd(&g72[lc[a_]], J0r[a_] * r[0] + J1r[a_] * r[1]);
                 const double wv = J0r[a_] * Jl[0] + J1r[a_] * Jl[1];
                 if (a_ >= 6 && a_ < 12) wr[lc[a_]] = wv; else atomicAdd(&wr[lc[a_]], wv);
@@ -523,22 +535,23 @@ k_ba_marg(const BaMeta *metas, const BaProbDev *probs, BaOutDev *outs, const BaM
         __syncthreads();
         __threadfence();
         // scatter into A / b
-        auto acol72 = [&](int q) { return q < 66 ? (sh.col_pose[q / 6] < 0 ? -1 : sh.col_pose[q / 6] + q % 6) : (sh.col_ex < 0 ? -1 : sh.col_ex + (q - 66)); };
-        for (int e = tid; e < 72 * 72; e += BA_THREADS) {
-            const int a_ = e / 72, c = e - a_ * 72;
+        auto acol72 = [&](int q) { return q < 66 ? (sh.col_pose[q / 6] < 0 ? -1 : sh.col_pose[q / 6] + q % 6)
+                                          : q < 72 ? (sh.col_ex < 0 ? -1 : sh.col_ex + (q - 66)) : sh.col_td; };
+        for (int e = tid; e < MG_L * MG_L; e += BA_THREADS) {
+            const int a_ = e / MG_L, c = e - a_ * MG_L;
             const int ca = acol72(a_), cc = acol72(c);
             if (ca < 0 || cc < 0) continue;
             const double v = H72[pk72(a_, c)];
             if (v != 0.0) A[(size_t)ca * pos + cc] += v;
         }
-        for (int q = tid; q < 72; q += BA_THREADS) { const int ca = acol72(q); if (ca >= 0) bv[ca] += g72[q]; }
-        for (int e = tid; e < nl0c * 73; e += BA_THREADS) {
-            const int li = e / 73, q = e - li * 73;
+        for (int q = tid; q < MG_L; q += BA_THREADS) { const int ca = acol72(q); if (ca >= 0) bv[ca] += g72[q]; }
+        for (int e = tid; e < nl0c * (MG_L + 1); e += BA_THREADS) {
+            const int li = e / (MG_L + 1), q = e - li * (MG_L + 1);
             const int cl = lm0c + li;
-            if (q == 72) { A[(size_t)cl * pos + cl] = hm[li]; bv[cl] = hm[nl0c + li]; }
+            if (q == MG_L) { A[(size_t)cl * pos + cl] = hm[li]; bv[cl] = hm[nl0c + li]; }
             else {
                 const int ca = acol72(q);
-                const double v = Wm[(size_t)li * 72 + q];
+                const double v = Wm[(size_t)li * MG_L + q];
                 if (ca >= 0 && v != 0.0) { A[(size_t)cl * pos + ca] = v; A[(size_t)ca * pos + cl] = v; }
             }
         }
@@ -597,15 +610,16 @@ k_ba_marg(const BaMeta *metas, const BaProbDev *probs, BaOutDev *outs, const BaM
         double *bx = mg.T;                       // nx
         auto xcol = [&](int a) { return a < lm0 ? a : mm + (a - lm0); };
         // landmark elimination Xs = A_XX - sum_l w_l w_l^T / h_l with the coupling rows streamed through a
-        // shared-memory tile (64 landmarks x 72, pre-scaled by 1/sqrt(h)); the head inverse scratch (Hs) is
+        // shared-memory tile (64 landmarks x MG_L, pre-scaled by 1/sqrt(h)); the head inverse scratch (Hs) is
         // rebuilt afterwards, so the tile may use the whole dynamic buffer behind it.
         double *tile = big + 4096;
-        short *xm = reinterpret_cast<short *>(big + 4096 + 64 * 72);     // X index -> local 72-index (or -1)
+        short *xm = reinterpret_cast<short *>(big + 4096 + 64 * MG_L);     // X index -> local index (or -1)
         for (int a_ = tid; a_ < nx; a_ += BA_THREADS) {
             const int ca = xcol(a_);
             int q = -1;
             for (int f = 0; f < BA_NF; ++f) if (sh.col_pose[f] >= 0 && ca >= sh.col_pose[f] && ca < sh.col_pose[f] + 6) q = 6 * f + (ca - sh.col_pose[f]);
             if (sh.col_ex >= 0 && ca >= sh.col_ex && ca < sh.col_ex + 6) q = 66 + (ca - sh.col_ex);
+            if (sh.col_td >= 0 && ca == sh.col_td) q = 72;
             xm[a_] = (short)q;
         }
         for (int e = tid; e < nx * nx; e += BA_THREADS) {
@@ -622,9 +636,9 @@ k_ba_marg(const BaMeta *metas, const BaProbDev *probs, BaOutDev *outs, const BaM
             double bacc = 0.0;
             for (int t0 = 0; t0 < nl0; t0 += 64) {
                 const int nt = min(64, nl0 - t0);
-                for (int q = tid; q < nt * 72; q += BA_THREADS) {
-                    const int li = t0 + q / 72;
-                    tile[q] = Wm[(size_t)li * 72 + (q % 72)] / sqrt(hm[li]);
+                for (int q = tid; q < nt * MG_L; q += BA_THREADS) {
+                    const int li = t0 + q / MG_L;
+                    tile[q] = Wm[(size_t)li * MG_L + (q % MG_L)] / sqrt(hm[li]);
                 }
                 __syncthreads();
                 int k = 0;
@@ -633,12 +647,12 @@ k_ba_marg(const BaMeta *metas, const BaProbDev *probs, BaOutDev *outs, const BaM
                     const int qi = xm[i], qj = xm[j];
                     if (qi < 0 || qj < 0) continue;
                     double s_ = 0;
-                    for (int l = 0; l < nt; ++l) s_ += tile[l * 72 + qi] * tile[l * 72 + qj];
+                    for (int l = 0; l < nt; ++l) s_ += tile[l * MG_L + qi] * tile[l * MG_L + qj];
                     accs[k] += s_;
                 }
                 if (tid < nx && xm[tid] >= 0) {
                     double s_ = 0;
-                    for (int l = 0; l < nt; ++l) s_ += tile[l * 72 + xm[tid]] * hm[nl0 + t0 + l] / sqrt(hm[t0 + l]);
+                    for (int l = 0; l < nt; ++l) s_ += tile[l * MG_L + xm[tid]] * hm[nl0 + t0 + l] / sqrt(hm[t0 + l]);
                     bacc += s_;
                 }
                 __syncthreads();
@@ -764,9 +778,10 @@ k_ba_marg(const BaMeta *metas, const BaProbDev *probs, BaOutDev *outs, const BaM
         for (int i = sh.first_kept; i < sh.nb; ++i) {
             if (!sh.present[i] || sh.drop[i]) continue;
             Q->kind[nk] = sh.kind[i]; Q->size[nk] = sh.gsize[i]; Q->idx[nk] = sh.idx[i] - mm;
-            const double *src = sh.kind[i] == VRF_BLK_POSE ? pose + 7 * sh.index[i] : sh.kind[i] == VRF_BLK_SPEEDBIAS ? sb + 9 * sh.index[i] : ex;
+            const double *src = sh.kind[i] == VRF_BLK_POSE ? pose + 7 * sh.index[i] : sh.kind[i] == VRF_BLK_SPEEDBIAS ? sb + 9 * sh.index[i]
+                                : sh.kind[i] == VRF_BLK_TD ? &out.mtd : ex;
             for (int c = 0; c < sh.gsize[i]; ++c) Q->x0[9 * nk + c] = src[c];
-            if (sh.kind[i] == VRF_BLK_EXPOSE) Q->index[nk] = 0;
+            if (sh.kind[i] == VRF_BLK_EXPOSE || sh.kind[i] == VRF_BLK_TD) Q->index[nk] = 0;
             else if (flag == VRF_MARGIN_OLD) Q->index[nk] = sh.index[i] - 1;
             else Q->index[nk] = (sh.index[i] == VRF_WINDOW_SIZE) ? VRF_WINDOW_SIZE - 1 : sh.index[i];
             ++nk;

@@ -133,6 +133,18 @@ static __device__ double block_sum(double v, double *s_red)
     return t;
 }
 __device__ __forceinline__ int pk(int a, int b) { return a >= b ? a * (a + 1) / 2 + b : b * (b + 1) / 2 + a; }
+// tangent column of entry k of a landmark coupling row (BA_WS entries: 66 pose columns, then ex-pose, then td)
+__device__ __forceinline__ int wcol(int k) { return k < 66 ? k : k + (BA_COL_EX - 66); }
+// observation o of a problem, time-shifted for ProjectionTdFactor:
+// pts_td = pts - (td - td_obs + TR / ROW * row) * velocity (projection_td_factor.cpp:52-53)
+__device__ __forceinline__ void obs_at(const BaMeta &m, const BaProbDev &p, int o, double td, double &x, double &y)
+{
+    x = p.obs[2 * o]; y = p.obs[2 * o + 1];
+    if (m.td_factor) {
+        const double s = td - p.obs_td[o] + m.tr_over_row * p.obs_row[o];
+        x -= s * p.obs_vel[2 * o]; y -= s * p.obs_vel[2 * o + 1];
+    }
+}
 
 // --------------------------------------------------------------------------
 // ProjectionFactor::Evaluate with precomputed rotations; CauchyLoss + Corrector applied.
@@ -143,8 +155,10 @@ struct FrameRot { double R[9]; };
 __device__ __forceinline__ double proj_eval(const double *Pi, const double *Ri, const double *Pj, const double *Rj,
                                             const double *tic, const double *ric, double lam, double xi, double yi,
                                             double xj, double yj, bool want_jac, bool lm_const, double *r, double *Ji,
-                                            double *Jj, double *Jl, double *Jex = nullptr)
-{
+                                            double *Jj, double *Jl, double *Jex = nullptr,
+                                            const double *vel_i = nullptr, const double *vel_j = nullptr, double *Jtd = nullptr)
+{   // ProjectionTdFactor (projection_td_factor.cpp:34-150): the caller passes the time-shifted points (:52-53);
+    // Jtd (:139-144) additionally needs both velocities.
     const double sqrt_info = 460.0 / 1.5;
     const double ilam = 1.0 / lam;
     double pci[3] = {xi * ilam, yi * ilam, ilam};
@@ -221,6 +235,14 @@ __device__ __forceinline__ double proj_eval(const double *Pi, const double *Ri, 
                     double e0 = -T1[c] + S1[c] + S2[c], e1 = -T1[3 + c] + S1[3 + c] + S2[3 + c], e2 = -T1[6 + c] + S1[6 + c] + S2[6 + c];
                     Jex[rr * 6 + 3 + c] = sr * (red[rr * 3] * e0 + red[rr * 3 + 1] * e1 + red[rr * 3 + 2] * e2);
                 }
+        }
+        if (Jtd) {
+            // reduce * ric^T Rj^T Ri ric * velocity_i / inv_dep_i * -1 + sqrt_info * velocity_j.head(2)
+            double tr[9], v[3], vel[3] = {vel_i[0], vel_i[1], 0.0};
+            d_mm(B, ric, tr);
+            d_mv(tr, vel, v);
+            Jtd[0] = sr * ((red[0] * v[0] + red[1] * v[1] + red[2] * v[2]) * ilam * -1.0 + sqrt_info * vel_j[0]);
+            Jtd[1] = sr * ((red[3] * v[0] + red[4] * v[1] + red[5] * v[2]) * ilam * -1.0 + sqrt_info * vel_j[1]);
         }
     }
     r[0] *= sr; r[1] *= sr;
@@ -408,14 +430,15 @@ static __device__ void imu_jac_col(const VrfImuPreint *pre, const double *pi, co
 // --------------------------------------------------------------------------
 // prior residual: dx then r = r0 + J0 dx (marginalization_factor.cpp:353-400)
 // --------------------------------------------------------------------------
-static __device__ void prior_dx(const BaPriorStore *P, const double *pose, const double *sb, const double *ex, double *dx)
+static __device__ void prior_dx(const BaPriorStore *P, const double *pose, const double *sb, const double *ex, double td, double *dx)
 {
     for (int b = threadIdx.x; b < P->n_blocks; b += blockDim.x) {
         const int kind = P->kind[b], index = P->index[b], size = P->size[b], idx = P->idx[b];
-        const double *cur = kind == VRF_BLK_POSE ? pose + 7 * index : kind == VRF_BLK_SPEEDBIAS ? sb + 9 * index : ex;
+        const double *cur = kind == VRF_BLK_POSE ? pose + 7 * index : kind == VRF_BLK_SPEEDBIAS ? sb + 9 * index
+                            : kind == VRF_BLK_TD ? &td : ex;
         const double *x0 = P->x0 + 9 * b;   // keep_block_data
         if (size != 7) {
-            for (int k = 0; k < size; ++k) dx[idx + k] = (kind == VRF_BLK_TD) ? 0.0 : cur[k] - x0[k];
+            for (int k = 0; k < size; ++k) dx[idx + k] = cur[k] - x0[k];
         } else {
             for (int k = 0; k < 3; ++k) dx[idx + k] = cur[k] - x0[k];
             double q0i[4], qe[4];

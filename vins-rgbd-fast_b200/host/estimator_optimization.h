@@ -12,28 +12,37 @@
 //   vrf_ba_solve                         replaces ceres::Solve + double2vector + marginalization
 //   scatter results                      :985-1111 (Rs, Ps, Vs, Bas, Bgs, depths via setDepth)
 #pragma once
+#include <cmath>
 #include <vector>
 
 #include "../../include/vrf.h"
 
 namespace vrf_host {
 
+// `use_imu`, `estimate_extrinsic`, `estimate_td` are the reference's globals USE_IMU / ESTIMATE_EXTRINSIC /
+// ESTIMATE_TD (utility/parameters.h); estimate_td must equal VrfConfig::estimate_td of the handle.
 template <class EstimatorT>
-int optimization(EstimatorT &e, vrf_handle *h, int seq, bool first_call_after_reset)
+int optimization(EstimatorT &e, vrf_handle *h, int seq, bool first_call_after_reset, int use_imu = 1,
+                 int estimate_extrinsic = 0, int estimate_td = 0)
 {
     e.vector2double();
     VrfBaProblem pb{};
     pb.frame_count = e.frame_count;
-    pb.use_imu = 1;
-    pb.ex_constant = 1;               // ESTIMATE_EXTRINSIC == 0 (estimator.cpp:1191-1201)
-    pb.td_constant = 1;               // ESTIMATE_TD == 0 this round
+    pb.use_imu = use_imu;
+    // estimator.cpp:1191-1201: the extrinsic becomes (and stays) variable once the window is full and the platform moves
+    if ((estimate_extrinsic && e.frame_count == VRF_WINDOW_SIZE && e.Vs[0].norm() > 0.2) || e.openExEstimation)
+        e.openExEstimation = true;
+    pb.ex_constant = e.openExEstimation ? 0 : 1;
+    // :1203-1212: td is fixed when it is not estimated or the platform is too slow
+    pb.td_constant = (!estimate_td || e.Vs[0].norm() < 0.2) ? 1 : 0;
+    pb.para_Td = e.para_Td[0][0];
     pb.marginalization_flag = (e.marginalization_flag == 0 /* MARGIN_OLD */) ? VRF_MARGIN_OLD : VRF_MARGIN_SECOND_NEW;
     for (int i = 0; i < VRF_NUM_FRAMES; ++i) {
         for (int k = 0; k < 7; ++k) pb.para_Pose[i][k] = e.para_Pose[i][k];
         for (int k = 0; k < 9; ++k) pb.para_SpeedBias[i][k] = e.para_SpeedBias[i][k];
     }
     for (int k = 0; k < 7; ++k) pb.para_Ex_Pose[k] = e.para_Ex_Pose[0][k];
-    std::vector<double> lam, obs;
+    std::vector<double> lam, obs, vel, ctd, row;     // vel / ctd / row: ProjectionTdFactor inputs (estimator.cpp:1270-1285)
     std::vector<int32_t> start, flag, ptr(1, 0);
     int feature_index = -1;
     for (auto &it : e.f_manager.feature) {
@@ -44,13 +53,17 @@ int optimization(EstimatorT &e, vrf_handle *h, int seq, bool first_call_after_re
         lam.push_back(e.para_Feature[feature_index][0]);
         start.push_back(it.start_frame);
         flag.push_back(it.estimate_flag);
-        for (auto &f : it.feature_per_frame) { obs.push_back(f.point.x()); obs.push_back(f.point.y()); }
+        for (auto &f : it.feature_per_frame) {
+            obs.push_back(f.point.x()); obs.push_back(f.point.y());
+            if (estimate_td) { vel.push_back(f.velocity.x()); vel.push_back(f.velocity.y()); ctd.push_back(f.cur_td); row.push_back(f.uv.y()); }
+        }
         ptr.push_back((int32_t)(obs.size() / 2));
     }
     pb.n_landmarks = (int32_t)lam.size();
     pb.n_obs = (int32_t)(obs.size() / 2);
     pb.para_Feature = lam.data(); pb.lm_start_frame = start.data(); pb.lm_estimate_flag = flag.data();
     pb.lm_obs_ptr = ptr.data(); pb.obs_pts = obs.data();
+    if (estimate_td) { pb.obs_velocity = vel.data(); pb.obs_cur_td = ctd.data(); pb.obs_row = row.data(); }
     std::vector<VrfImuPreint> imu(VRF_WINDOW_SIZE);
     for (int j = 1; j <= e.frame_count; ++j) {
         const auto &p = *e.pre_integrations[j];
@@ -75,6 +88,23 @@ int optimization(EstimatorT &e, vrf_handle *h, int seq, bool first_call_after_re
         }
     }
     for (size_t l = 0; l < lam_out.size(); ++l) e.para_Feature[l][0] = lam_out[l];
+    // double2vector: tic/ric <- para_Ex_Pose, td <- para_Td (estimator.cpp:1033-1060)
+    for (int k = 0; k < 7; ++k) e.para_Ex_Pose[0][k] = res.para_Ex_Pose[k];
+    e.para_Td[0][0] = res.para_Td;
+    if (use_imu) {
+        for (int k = 0; k < 3; ++k) e.tic[0](k) = res.para_Ex_Pose[k];
+        // ric = Quaterniond(w, x, y, z).normalized().toRotationMatrix()
+        double q[4] = {res.para_Ex_Pose[3], res.para_Ex_Pose[4], res.para_Ex_Pose[5], res.para_Ex_Pose[6]};
+        double nq = 0;
+        for (double v : q) nq += v * v;
+        nq = std::sqrt(nq);
+        const double x = q[0] / nq, y = q[1] / nq, z = q[2] / nq, w = q[3] / nq;
+        const double Rm[9] = {1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w),
+                              2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w),
+                              2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)};
+        for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) e.ric[0](r, c) = Rm[r * 3 + c];
+        e.td = res.para_Td;
+    }
     {   // f_manager.setDepth(dep) (feature_manager.cpp:197-223)
         auto dep = e.f_manager.getDepthVector();
         for (int i = 0; i < e.f_manager.getFeatureCount(); ++i) dep(i) = e.para_Feature[i][0];

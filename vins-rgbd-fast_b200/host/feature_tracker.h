@@ -37,14 +37,17 @@ public:
     {
         const size_t cap = VRF_TRACK_CAP;
         b_pts_.resize(2 * cap); b_un_.resize(2 * cap); b_vel_.resize(2 * cap); b_pred_.resize(2 * cap);
-        b_ids_.resize(cap); b_cnt_.resize(cap);
+        b_ids_.resize(cap); b_cnt_.resize(cap); b_dmm_.resize(cap); b_dkeep_.resize(cap);
         grids_track_num.assign(cfg.num_grid_rows * cfg.num_grid_cols, 0);
     }
 
     // feature_tracker.cpp:263-439 (+ the nodelet's updateID loop, estimator_nodelet.cpp:324-330).
     // PUB_THIS_FRAME is an explicit argument instead of the reference's unsynchronised global.
+    // `depth` (optional): the depth frame the nodelet pairs with this image (estimator_nodelet.cpp:206-225); its decode
+    // (:512-533) and the per-feature lookup + DEPTH_MIN_DIST test of FeatureManager::addFeatureCheckParallax
+    // (feature_manager.cpp:71-80) then run on the device: results in depth_mm / depth_keep.
     void readImage(const cv::Mat &_img, double _cur_time, const Eigen::Matrix3d &_relative_R = Eigen::Matrix3d::Identity(),
-                   bool pub_this_frame = true)
+                   bool pub_this_frame = true, const void *depth = nullptr, size_t depth_step = 0, int depth_fmt = VRF_DEPTH_NONE)
     {
         double R[9];
         for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) R[r * 3 + c] = _relative_R(r, c);
@@ -53,9 +56,14 @@ public:
         o.cur_pts = b_pts_.data(); o.cur_un_pts = b_un_.data(); o.pts_velocity = b_vel_.data();
         o.ids = b_ids_.data(); o.track_cnt = b_cnt_.data(); o.predict_pts = b_pred_.data();
         o.grids_track_num = grids_track_num.data();
+        o.depth_mm = b_dmm_.data(); o.depth_keep = b_dkeep_.data();
         const int fmt = _img.channels() == 3 ? VRF_FMT_RGB8 : VRF_FMT_GRAY8;
-        const int rc = vrf_tracker_read_image(h_, seq_, _img.data, _img.step, fmt, _cur_time, R, pub_this_frame ? 1 : 0, &o);
-        if (rc < 0) throw std::runtime_error(std::string("vrf_tracker_read_image: ") + vrf_strerror(rc));
+        const int32_t s = seq_, pub = pub_this_frame ? 1 : 0;
+        const uint8_t *imgs[1] = {_img.data};
+        const void *deps[1] = {depth};
+        const int rc = vrf_tracker_read_rgbd_batch(h_, 1, &s, imgs, _img.step, fmt, depth ? deps : nullptr, depth_step, depth_fmt,
+                                                   &_cur_time, R, &pub, &o);
+        if (rc < 0) throw std::runtime_error(std::string("vrf_tracker_read_rgbd_batch: ") + vrf_strerror(rc));
         cur_time = _cur_time;
         cur_pts.resize(o.n); cur_un_pts.resize(o.n); pts_velocity.resize(o.n); ids.resize(o.n); track_cnt.resize(o.n);
         for (int i = 0; i < o.n; ++i) {
@@ -64,6 +72,8 @@ public:
             pts_velocity[i] = cv::Point2f(b_vel_[2 * i], b_vel_[2 * i + 1]);
             ids[i] = b_ids_[i]; track_cnt[i] = b_cnt_[i];
         }
+        depth_mm.assign(b_dmm_.begin(), b_dmm_.begin() + o.n);
+        depth_keep.assign(b_dkeep_.begin(), b_dkeep_.begin() + o.n);
         predict_pts.resize(o.n_predict);
         for (int i = 0; i < o.n_predict; ++i) predict_pts[i] = cv::Point2f(b_pred_[2 * i], b_pred_[2 * i + 1]);
         n_id = o.n_id;
@@ -79,6 +89,8 @@ public:
     cv::Mat fisheye_mask, grids_detector_img;              // visualisation only; FISHEYE must be 0
     std::vector<cv::Point2f> cur_pts, predict_pts, cur_un_pts, pts_velocity;
     std::vector<int> ids, track_cnt, grids_track_num;
+    std::vector<uint16_t> depth_mm;                        // depth_img.at<ushort>((int)v, (int)u) per feature (publish frames)
+    std::vector<uint8_t> depth_keep;                       // 0: addFeatureCheckParallax erases it (0 < depth < DEPTH_MIN_DIST)
     double cur_time{};
     int n_id;
 
@@ -88,4 +100,6 @@ private:
     VrfConfig cfg_;
     std::vector<float> b_pts_, b_un_, b_vel_, b_pred_;
     std::vector<int32_t> b_ids_, b_cnt_;
+    std::vector<uint16_t> b_dmm_;
+    std::vector<uint8_t> b_dkeep_;
 };

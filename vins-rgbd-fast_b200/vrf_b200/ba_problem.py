@@ -26,6 +26,13 @@ class BaProblem:
         self.imu = (B.VrfImuPreint * B.NUM_FRAMES)()
         self.prior = None
         self.M = 0
+        self.td = 0.0
+        self.obs_vel = self.obs_cur_td = self.obs_row = None      # ProjectionTdFactor inputs (estimate_td)
+
+    def set_td_observations(self, vel, cur_td, row):
+        self.obs_vel = np.ascontiguousarray(vel, np.float64).reshape(-1, 2)
+        self.obs_cur_td = np.ascontiguousarray(cur_td, np.float64)
+        self.obs_row = np.ascontiguousarray(row, np.float64)
 
     def set_landmarks(self, lam, start, flag, obs_ptr, obs_pts):
         self.lam = np.ascontiguousarray(lam, np.float64)
@@ -44,7 +51,10 @@ class BaProblem:
                 c.para_SpeedBias[i][k] = self.sb[i, k]
         for k in range(7):
             c.para_Ex_Pose[k] = self.ex[k]
-        c.para_Td = 0.0
+        c.para_Td = float(self.td)
+        c.obs_velocity = None if self.obs_vel is None else self.obs_vel.ctypes.data
+        c.obs_cur_td = None if self.obs_cur_td is None else self.obs_cur_td.ctypes.data
+        c.obs_row = None if self.obs_row is None else self.obs_row.ctypes.data
         c.n_landmarks = self.M
         c.n_obs = len(self.obs_pts)
         c.para_Feature = self.lam.ctypes.data
@@ -74,6 +84,10 @@ class BaSolution:
     def pose(self): return self.arr("para_Pose", (B.NUM_FRAMES, 7))
     @property
     def sb(self): return self.arr("para_SpeedBias", (B.NUM_FRAMES, 9))
+    @property
+    def ex(self): return np.array(list(self.c.para_Ex_Pose))
+    @property
+    def td(self): return float(self.c.para_Td)
     @property
     def Ps(self): return self.arr("Ps", (B.NUM_FRAMES, 3))
     @property
@@ -120,7 +134,7 @@ class WindowSimulator:
     (what FeatureManager / processIMU would hand to optimization())."""
 
     def __init__(self, seed, cfg, n_landmarks=150, kf_dt=0.1, imu_rate=200.0, flag2_frac=0.1,
-                 pix_noise=0.5, ric=None, tic=None):
+                 pix_noise=0.5, ric=None, tic=None, td_true=0.0, ex_constant=1, td_constant=1, ex_perturb=0.0):
         self.cfg = cfg
         self.rng = np.random.default_rng(seed)
         self.traj = synth.Trajectory(seed, fps=1.0 / kf_dt, trans_per_frame=0.06, rot_deg_per_frame=1.5)
@@ -137,6 +151,15 @@ class WindowSimulator:
         self.est = {}           # absolute frame -> (P, R, V, Ba, Bg) current estimate
         self.prior = None
         self.seed = seed
+        # time offset camera <-> IMU: images are stamped td_true too early, i.e. the feature seen in the image
+        # stamped t(k) was really taken at t(k) + td_true (estimate_td); the estimate starts at 0
+        self.td_true = td_true
+        self.td_est = 0.0
+        self.ex_constant, self.td_constant = ex_constant, td_constant
+        self.ex_est = None
+        if ex_perturb > 0:
+            r = np.random.default_rng(seed + 991)
+            self.ex_est = (self.tic + r.normal(0, ex_perturb, 3), self.ric @ synth.so3_exp(r.normal(0, ex_perturb, 3)))
 
     def t(self, k):
         return 2.0 + k * self.kf_dt
@@ -145,8 +168,9 @@ class WindowSimulator:
         t = self.t(k)
         return self.traj.p_w(t), self.traj.R_wb(t), self.traj.v_w(t)
 
-    def _cam(self, k):
-        p, R, _ = self.true_state(k)
+    def _cam(self, k, dt=0.0):
+        t = self.t(k) + dt
+        p, R = self.traj.p_w(t), self.traj.R_wb(t)
         return p + R @ self.tic, R @ self.ric
 
     def _spawn(self, k):
@@ -165,12 +189,21 @@ class WindowSimulator:
         return out
 
     def _observe(self, lm, k):
-        pc, Rc = self._cam(k)
+        pc, Rc = self._cam(k, self.td_true)
         q = Rc.T @ (lm["P"] - pc)
         if q[2] < 0.3:
             return None
         r = np.random.default_rng((self.seed * 1000003 + lm["id"] * 7919 + k) % (2 ** 32))
         return q[:2] / q[2] + r.normal(0, self.pix_noise, 2)
+
+    def _velocity(self, lm, k, h=1e-3):
+        """normalised-plane velocity of the feature (what undistortedPoints differences between frames)"""
+        out = []
+        for dt in (-h, h):
+            pc, Rc = self._cam(k, self.td_true + dt)
+            q = Rc.T @ (lm["P"] - pc)
+            out.append(q[:2] / q[2])
+        return (out[1] - out[0]) / (2 * h)
 
     def _preint(self, k0, k1, ba, bg):
         """IMU between absolute frames k0 -> k1 (processIMU: first sample initialises acc_0/gyr_0)."""
@@ -207,12 +240,16 @@ class WindowSimulator:
             pb.pose[i, :3] = p
             pb.pose[i, 3:] = R_to_quat(R)
             pb.sb[i] = np.concatenate([v, ba, bg])
-        pb.ex[:3] = self.tic
-        pb.ex[3:] = R_to_quat(self.ric)
+        tic_e, ric_e = (self.tic, self.ric) if self.ex_est is None else self.ex_est
+        pb.ex[:3] = tic_e
+        pb.ex[3:] = R_to_quat(ric_e)
+        pb.c.ex_constant, pb.c.td_constant = self.ex_constant, self.td_constant
+        pb.td = self.td_est
         for j in range(1, B.NUM_FRAMES):
             _, _, _, ba, bg = self.est[a + j - 1]
             pb.imu[j - 1] = self._preint(a + j - 1, a + j, ba, bg)
         lam, start, flag, ptr, pts = [], [], [], [0], []
+        vel, ctd, row = [], [], []
         for lm in self.pool:
             f0, f1 = max(lm["first"], a), min(lm["last"], a + 10)
             if f1 - f0 + 1 < 2 or f0 - a >= 8:        # used_num >= 2 && start_frame < WINDOW_SIZE - 2
@@ -224,9 +261,16 @@ class WindowSimulator:
             depth = (Rc.T @ (lm["P"] - pc))[2] * (1.0 + lm["eps"])
             lam.append(1.0 / depth); start.append(f0 - a); flag.append(lm["flag"])
             pts.extend(obs); ptr.append(len(pts))
+            if self.cfg.estimate_td:
+                for k, o in zip(range(f0, f1 + 1), obs):
+                    vel.append(self._velocity(lm, k))
+                    ctd.append(0.0)                              # FeaturePerFrame::cur_td: td when the frame came in
+                    row.append(460.0 * o[1] + 0.5 * self.cfg.row)   # uv.y of the observation
             if len(lam) >= self.n_landmarks:
                 break
         pb.set_landmarks(lam, start, flag, ptr, np.array(pts))
+        if self.cfg.estimate_td:
+            pb.set_td_observations(vel, ctd, row)
         pb.prior = self.prior
         pb.c.marginalization_flag = marg_flag
         return pb.finalize()
@@ -237,6 +281,15 @@ class WindowSimulator:
         Ps, Rs, Vs, Bas, Bgs = sol.Ps, sol.Rs, sol.Vs, sol.Bas, sol.Bgs
         for i in range(B.NUM_FRAMES):
             self.est[a + i] = (Ps[i], Rs[i], Vs[i], Bas[i], Bgs[i])
+        if not self.td_constant:
+            self.td_est = sol.td
+        if not self.ex_constant:
+            q = sol.ex[3:] / np.linalg.norm(sol.ex[3:])
+            x, y, z, w = q
+            Rm = np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                           [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                           [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+            self.ex_est = (sol.ex[:3].copy(), Rm)
         if sol.c.has_new_prior:
             p = B.VrfPrior()
             C.memmove(C.byref(p), C.byref(sol.new_prior), C.sizeof(B.VrfPrior))

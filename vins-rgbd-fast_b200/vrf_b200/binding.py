@@ -33,7 +33,7 @@ class VrfConfig(C.Structure):
         ("num_iterations", C.c_int32), ("estimate_extrinsic", C.c_int32), ("estimate_td", C.c_int32),
         ("fix_depth", C.c_int32), ("depth_max_dist", C.c_double), ("g_norm", C.c_double),
         ("acc_n", C.c_double), ("acc_w", C.c_double), ("gyr_n", C.c_double), ("gyr_w", C.c_double),
-        ("depth_min_dist", C.c_double),
+        ("depth_min_dist", C.c_double), ("tr", C.c_double),
     ]
 
 
@@ -82,6 +82,7 @@ class VrfBaProblem(C.Structure):
         ("para_Feature", C.c_void_p), ("lm_start_frame", C.c_void_p), ("lm_estimate_flag", C.c_void_p),
         ("lm_obs_ptr", C.c_void_p), ("obs_pts", C.c_void_p),
         ("imu", C.POINTER(VrfImuPreint)), ("prior", C.POINTER(VrfPrior)),
+        ("obs_velocity", C.c_void_p), ("obs_cur_td", C.c_void_p), ("obs_row", C.c_void_p),
     ]
 
 
