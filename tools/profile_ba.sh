@@ -1,0 +1,8 @@
+#!/bin/bash
+# Run on the GPU box (gpurun): ncu --set full + source counters of the two back-end kernels and k_lk.
+mkdir -p gpurun_out
+CMD="python bench.py --steps 3 --warmup 3 --seqs 96 --quick"
+for k in ${KERNELS:-k_ba_marg k_ba_solve k_lk}; do
+  timeout 400 ncu --set full --clock-control none --import-source on -k regex:$k -s 2 -c 1 -f -o gpurun_out/prof_$k $CMD > gpurun_out/prof_$k.log 2>&1
+done
+ls -la gpurun_out

@@ -10,7 +10,7 @@
 #define VRF_CAP        VRF_TRACK_CAP   // per-sequence capacity of the track arrays
 #define VRF_MAX_CELLS  256
 #define VRF_MAX_LEVELS 4
-#define VRF_MAX_BATCH  1024            // sequences per batched call
+#define VRF_MAX_BATCH  4096            // sequences per batched call
 #define VRF_LK_WIN     21
 #define VRF_LK_HALF    10.0f
 
