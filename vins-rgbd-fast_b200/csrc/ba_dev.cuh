@@ -58,7 +58,7 @@ struct BaProbDev {
     double *lam, *clam;                   // current / candidate inverse depths
     double *lam_out;                      // optimised inverse depths of this batch item (result copy)
     double *W;                            // [M][BA_WS]
-    double *hll, *gl, *jscale_l, *diag_l, *gd_l, *gn_l, *u_l, *y_l, *hinv_l;
+    double *hll, *gl, *jscale_l, *diag_l, *gd_l, *gn_l, *u_l, *y_l, *hinv_l, *shinv_l;   // shinv_l = sqrt(hinv_l)
     double *imuS;                         // [10][225] sqrt information (upper)
 };
 

@@ -108,7 +108,7 @@ int ba_create(vrf_handle *h)
     BCK(cudaMalloc((void **)&b->d_lam, S * BA_MAX_LM * sizeof(double)));
     BCK(cudaMalloc((void **)&b->d_clam, S * BA_MAX_LM * sizeof(double)));
     BCK(cudaMalloc((void **)&b->d_W, S * BA_MAX_LM * BA_WS * sizeof(double)));
-    BCK(cudaMalloc((void **)&b->d_vecs, S * 9 * BA_MAX_LM * sizeof(double)));
+    BCK(cudaMalloc((void **)&b->d_vecs, S * 10 * BA_MAX_LM * sizeof(double)));
     BCK(cudaMalloc((void **)&b->d_imuS, S * (BA_NF - 1) * 225 * sizeof(double)));
     BCK(cudaMalloc((void **)&b->d_HP, S * VRF_PRIOR_MAX_DIM * VRF_PRIOR_MAX_DIM * sizeof(double)));
     BCK(cudaMalloc((void **)&b->d_colmap, S * VRF_PRIOR_MAX_DIM * sizeof(int)));
@@ -239,9 +239,10 @@ static int pack_problem(vrf_handle *h, BaSlot &sl, int slot, int seq, const VrfB
     pd.lam_out = sl.d_lam_out + (size_t)slot * BA_MAX_LM;
     pd.clam = b->d_clam + (size_t)seq * BA_MAX_LM;
     pd.W = b->d_W + (size_t)seq * BA_MAX_LM * BA_WS;
-    double *v = b->d_vecs + (size_t)seq * 9 * BA_MAX_LM;
+    double *v = b->d_vecs + (size_t)seq * 10 * BA_MAX_LM;
     pd.hll = v; pd.gl = v + BA_MAX_LM; pd.jscale_l = v + 2 * BA_MAX_LM; pd.diag_l = v + 3 * BA_MAX_LM; pd.gd_l = v + 4 * BA_MAX_LM;
     pd.gn_l = v + 5 * BA_MAX_LM; pd.u_l = v + 6 * BA_MAX_LM; pd.y_l = v + 7 * BA_MAX_LM; pd.hinv_l = v + 8 * BA_MAX_LM;
+    pd.shinv_l = v + 9 * BA_MAX_LM;
     pd.imuS = b->d_imuS + (size_t)seq * (BA_NF - 1) * 225;
 
     BaMargDev &mg = sl.h_marg[slot];

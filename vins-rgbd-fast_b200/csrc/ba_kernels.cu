@@ -40,12 +40,20 @@ struct BaShared {
     double tdv[2];                                    // para_Td: current, candidate
     double R[BA_NF * 9], ric[9];
     double dx[VRF_PRIOR_MAX_DIM], pr[VRF_PRIOR_MAX_DIM];
+    // prior block table / linearisation point / r0 / column map staged once per solve (L2 latency is ~800 cycles here)
+    double px0[VRF_PRIOR_MAX_BLOCKS * 9], pr0[VRF_PRIOR_MAX_DIM];
+    int pkind[VRF_PRIOR_MAX_BLOCKS], pindex[VRF_PRIOR_MAX_BLOCKS], psize[VRF_PRIOR_MAX_BLOCKS], pidx[VRF_PRIOR_MAX_BLOCKS];
+    int pcol[VRF_PRIOR_MAX_DIM], pnb;
     double imuJ[BA_NF - 1][15 * 30];                 // whitened IMU Jacobians of the current linearisation
     double imur[BA_NF - 1][16];
     double red[BA_THREADS / 32];
     double sc[16];
     int flag[8];
 };
+
+// Keep the frame inside the 196 KB shared-memory carve-out (1 KB is reserved per CTA): one step more (228 KB) leaves only
+// 28 KB of L1 for the landmark arrays / coupling rows in HBM and slowed every phase that touches them by 20-60 %.
+static_assert(sizeof(BaShared) <= 196 * 1024 - 1024, "BaShared must fit the 196 KB carve-out");
 
 __device__ __forceinline__ bool col_active_dev(const BaMeta &m, int col)
 {
@@ -58,7 +66,6 @@ __device__ __forceinline__ bool col_active_dev(const BaMeta &m, int col)
 // block g = [ex-pose (6) | td (1)] (tangent columns 165..171), only when one of them is variable:
 // Jg^T Ji, Jg^T Jj, Jg^T r and the lower triangle of Jg^T Jg, each summed over the warp's lanes with the
 // reduce-scatter butterfly and added to the shared system.  Jg: 2 x 7 row-major.
-__device__ __forceinline__ double reduce_scatter16(double (&v)[16], int lane);
 __device__ __noinline__ void accumulate_g(double *H, double *g, int i, int j, int lane, const double *Ji, const double *Jj,
                                           const double *Jg, const double *r)
 {
@@ -99,7 +106,6 @@ __device__ __noinline__ void accumulate_g(double *H, double *g, int i, int j, in
 }
 
 #define BA_NPAIR (BA_NF * (BA_NF - 1) / 2)
-static_assert(BA_NPAIR * 54 <= (BA_NF - 1) * 15 * 30, "pair partials must fit in imuJ");
 
 __device__ __forceinline__ int pair_index(int i, int j) { return i * (2 * BA_NF - i - 1) / 2 + (j - i - 1); }
 
@@ -122,22 +128,24 @@ __device__ __forceinline__ double pair_entry(int e, const double *Ji, const doub
     return 0.0;
 }
 
-// Sum 16 per-lane values over the 32 lanes with 16 shuffles: after the four scatter stages lane L holds the
-// total of value (L >> 1) over its 16-lane partner set, the last stage completes it (lanes 2m, 2m+1 agree).
-__device__ __forceinline__ double reduce_scatter16(double (&v)[16], int lane)
+// prior_dx (ba_math.cuh) on the block table staged in shared memory
+__device__ __forceinline__ void prior_dx_smem(BaShared &sh, const double *pose, const double *sb, const double *ex, double td)
 {
-#pragma unroll
-    for (int st = 0; st < 4; ++st) {
-        const int n2 = 8 >> st, mask = 16 >> st;
-        const bool up = (lane & mask) != 0;
-#pragma unroll
-        for (int k = 0; k < n2; ++k) {
-            const double keep = up ? v[k + n2] : v[k];
-            const double send = up ? v[k] : v[k + n2];
-            v[k] = keep + __shfl_xor_sync(0xffffffffu, send, mask);
+    for (int b = threadIdx.x; b < sh.pnb; b += BA_THREADS) {
+        const int kind = sh.pkind[b], index = sh.pindex[b], size = sh.psize[b], idx = sh.pidx[b];
+        const double *cur = kind == VRF_BLK_POSE ? pose + 7 * index : kind == VRF_BLK_SPEEDBIAS ? sb + 9 * index
+                            : kind == VRF_BLK_TD ? &td : ex;
+        const double *x0 = sh.px0 + 9 * b;   // keep_block_data
+        if (size != 7) {
+            for (int k = 0; k < size; ++k) sh.dx[idx + k] = cur[k] - x0[k];
+        } else {
+            for (int k = 0; k < 3; ++k) sh.dx[idx + k] = cur[k] - x0[k];
+            double q0i[4], qe[4];
+            d_qinv(x0 + 3, q0i); d_qmul(q0i, cur + 3, qe);
+            const double sg = (qe[3] >= 0) ? 1.0 : -1.0;
+            for (int k = 0; k < 3; ++k) sh.dx[idx + 3 + k] = sg * 2.0 * qe[k];
         }
     }
-    return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 1);
 }
 
 // cost of all residual blocks at (pose, sb, lam); optionally the full linearisation into sh.H / sh.g / landmark arrays.
@@ -152,12 +160,11 @@ __device__ __noinline__ double ba_evaluate_t(const BaMeta &m, const BaProbDev &p
     if (lin) {
         for (int i = tid; i < BA_NC * (BA_NC + 1) / 2; i += BA_THREADS) sh.H[i] = 0.0;
         for (int i = tid; i < BA_NC; i += BA_THREADS) sh.g[i] = 0.0;
-        for (int i = tid; i < BA_NPAIR * 54; i += BA_THREADS) (&sh.imuJ[0][0])[i] = 0.0;      // per-pair partials (see below)
         for (int i = tid; i < m.M * BA_WS; i += BA_THREADS) p.W[i] = 0.0;
         for (int l = tid; l < m.M; l += BA_THREADS) { p.hll[l] = 0.0; p.gl[l] = 0.0; }
     }
     for (int f = tid; f < BA_NF; f += BA_THREADS) d_q2R(pose + 7 * f + 3, sh.R + 9 * f);
-    if (tid == 0) d_q2R(ex + 3, sh.ric);
+    if (tid == 0) { d_q2R(ex + 3, sh.ric); sh.flag[2] = 0; }
     constexpr bool gact = GACT;
     const bool eprof = (m.debug & 16) != 0;
     long long et[5] = {0, 0, 0, 0, 0}, ec = eprof ? clock64() : 0;
@@ -165,31 +172,77 @@ __device__ __noinline__ double ba_evaluate_t(const BaMeta &m, const BaProbDev &p
     __syncthreads();
     EPROF(0);
     double cost = 0.0;
-    if (!lin) {
-        // ---- projection factors, cost only: two landmarks per warp (16 lanes each), one lane per factor ----
-        const int half = lane >> 4, hl = lane & 15;
-        for (int lp = warp; 2 * lp < m.M; lp += nwarp) {
-            const int l = 2 * lp + half;
-            if (l >= m.M) continue;
-            const int o0 = p.obs_ptr[l], nf = p.obs_ptr[l + 1] - o0 - 1;
-            if (hl >= nf) continue;
-            const int i = p.start[l], j = i + 1 + hl;
-            double r[2], Ji[12], Jj[12], Jl[2], xi, yi, xj, yj;
-            obs_at(m, p, o0, td, xi, yi);
-            obs_at(m, p, o0 + 1 + hl, td, xj, yj);
-            cost += 0.5 * proj_eval(pose + 7 * i, sh.R + 9 * i, pose + 7 * j, sh.R + 9 * j, ex, sh.ric, lam[l], xi, yi, xj, yj, false,
-                                    p.lm_const[l] != 0, r, Ji, Jj, Jl);
-        }
-    } else {
-        // ---- projection factors, linearisation: one warp per frame pair (host i, observer j), one lane per factor ----
-        // Every factor of the pair adds to the same 12x12 block of J^T J.  The 90 distinct sums (off-diagonal 6x6,
-        // two diagonal lower triangles, two gradient 6-vectors) are reduced over the warp's lanes with a
-        // reduce-scatter butterfly (one shuffle per value instead of five) and accumulated in registers over the
-        // pair's batches: no shared-memory atomics.  The off-diagonal block has a single owner and is stored
-        // directly; the diagonal parts go to per-pair partials that are summed per frame afterwards.
-        double *part = &sh.imuJ[0][0];              // [55][54]; imuJ is rewritten by the IMU phase below
-        const int nbatch = (m.M + 31) >> 5;
-        for (int pi = warp; pi < BA_NPAIR; pi += nwarp) {
+    // ---- residual blocks as a dynamic task queue over the 16 warps: the IMU factors first (the longest tasks), then the
+    // projection factors (linearisation: one task per frame pair; cost only: one task per two landmarks).  The IMU and
+    // projection tasks touch disjoint accumulators except the pose blocks of adjacent frames, which use atomics. ----
+    const int nbatch = (m.M + 31) >> 5;
+    const int nproj = lin ? BA_NPAIR : (m.M + 1) >> 1;
+    const int ntask = m.nimu + nproj;
+    for (;;) {
+        int task = 0;
+        if (lane == 0) task = atomicAdd(&sh.flag[2], 1);
+        task = __shfl_sync(0xffffffffu, task, 0);
+        if (task >= ntask) break;
+        if (task < m.nimu) {
+            // ---- IMU factor: one warp per factor ----
+            const int f = task;
+            const int j = m.imu_j[f], i = j - 1;
+            const VrfImuPreint *pre = p.imu + (j - 1);
+            const double *S = p.imuS + (size_t)(j - 1) * 225;
+            double rr[15];
+            ImuCtx cx;
+            imu_residual_raw(pre, pose + 7 * i, sb + 9 * i, pose + 7 * j, sb + 9 * j, m.g_norm, rr, &cx);
+            // whitened residual row `lane`
+            double rw = 0;
+            if (lane < 15) { for (int k = lane; k < 15; ++k) rw += S[lane * 15 + k] * rr[k]; cost += 0.5 * rw * rw; }
+            if (!lin) continue;
+            if (lane < 15) sh.imur[f][lane] = rw;
+            if (lane < 30) {
+                double col[15];
+                imu_jac_col(pre, pose + 7 * i, sb + 9 * i, pose + 7 * j, sb + 9 * j, m.g_norm, &cx, lane, col);
+                for (int rI = 0; rI < 15; ++rI) { double a = 0; for (int k = rI; k < 15; ++k) a += S[rI * 15 + k] * col[k]; sh.imuJ[f][rI * 30 + lane] = a; }
+            }
+            __syncwarp();
+            // accumulate J^T J and J^T r ; tangent column of local column c
+            auto tcol = [&](int c) { return c < 6 ? 6 * i + c : c < 15 ? 66 + 9 * i + (c - 6) : c < 21 ? 6 * j + (c - 15) : 66 + 9 * j + (c - 21); };
+            for (int a = 0; a < 30; ++a) {
+                // row a of the 30x30 lower triangle: lanes over b <= a
+                if (lane <= a) {
+                    double h = 0;
+#pragma unroll
+                    for (int k = 0; k < 15; ++k) h += sh.imuJ[f][k * 30 + a] * sh.imuJ[f][k * 30 + lane];
+                    atomicAdd(&sh.H[pk(tcol(a), tcol(lane))], h);
+                }
+            }
+            if (lane < 30) {
+                double gsum = 0;
+                for (int k = 0; k < 15; ++k) gsum += sh.imuJ[f][k * 30 + lane] * sh.imur[f][k];
+                atomicAdd(&sh.g[tcol(lane)], gsum);
+            }
+        } else if (!lin) {
+            // ---- projection factors, cost only: two landmarks per warp (16 lanes each), one lane per factor ----
+            const int half = lane >> 4, hl = lane & 15;
+            const int l = 2 * (task - m.nimu) + half;
+            if (l < m.M) {
+                const int o0 = p.obs_ptr[l], nf = p.obs_ptr[l + 1] - o0 - 1;
+                if (hl < nf) {
+                    const int i = p.start[l], j = i + 1 + hl;
+                    double r[2], Ji[12], Jj[12], Jl[2], xi, yi, xj, yj;
+                    obs_at(m, p, o0, td, xi, yi);
+                    obs_at(m, p, o0 + 1 + hl, td, xj, yj);
+                    cost += 0.5 * proj_eval(pose + 7 * i, sh.R + 9 * i, pose + 7 * j, sh.R + 9 * j, ex, sh.ric, lam[l], xi, yi, xj, yj, false,
+                                            p.lm_const[l] != 0, r, Ji, Jj, Jl);
+                }
+            }
+        } else {
+            // ---- projection factors, linearisation: one warp per frame pair (host i, observer j), one lane per factor ----
+            // Every factor of the pair adds to the same 12x12 block of J^T J.  The 90 distinct sums (off-diagonal 6x6,
+            // two diagonal lower triangles, two gradient 6-vectors) are reduced over the warp's lanes with a
+            // reduce-scatter butterfly (one shuffle per value instead of five) and accumulated in registers over the
+            // pair's batches: no shared-memory atomics.  The off-diagonal block has a single projection owner (adjacent
+            // frames also receive the IMU factor's block, hence the atomic there); the diagonal parts go to per-pair
+            // partials that are summed per frame afterwards.
+            const int pi = task - m.nimu;
             int i = 0, rem = pi;
             while (rem >= BA_NF - 1 - i) { rem -= BA_NF - 1 - i; ++i; }
             const int j = i + 1 + rem;
@@ -253,106 +306,105 @@ __device__ __noinline__ double ba_evaluate_t(const BaMeta &m, const BaProbDev &p
                 }
             }
             if (any_pair && !(lane & 1)) {
+                // off-diagonal 6x6 block: this pair is its only projection owner (adjacent frames also receive the IMU
+                // factor's block, hence the atomic there); diagonal blocks / gradients are shared with the other pairs of
+                // frames i and j and with the IMU factors: atomics (2970 per linearisation, spread over the 16 warps)
+                const bool adjacent = (j == i + 1);
 #pragma unroll
                 for (int ps = 0; ps < 6; ++ps) {
                     const int e = ps * 16 + (lane >> 1);
-                    if (e < 36) sh.H[pk(6 * j + e / 6, 6 * i + e % 6)] = acc[ps];
-                    else if (e < 90) part[pi * 54 + (e - 36)] = acc[ps];
+                    if (e < 36) {
+                        double *dst = &sh.H[pk(6 * j + e / 6, 6 * i + e % 6)];
+                        if (adjacent) atomicAdd(dst, acc[ps]); else *dst = acc[ps];
+                    } else if (e < 78) {
+                        const int f = e < 57 ? j : i, t = e < 57 ? e - 36 : e - 57;
+                        int a = 0;
+                        while ((a + 1) * (a + 2) / 2 <= t) ++a;
+                        atomicAdd(&sh.H[pk(6 * f + a, 6 * f + (t - a * (a + 1) / 2))], acc[ps]);
+                    } else if (e < 90) {
+                        const int f = e < 84 ? j : i, a = e < 84 ? e - 78 : e - 84;
+                        atomicAdd(&sh.g[6 * f + a], acc[ps]);
+                    }
                 }
             }
         }
-        __syncthreads();
-        // diagonal blocks and gradient of frame f: sum of the partials of every pair f takes part in
-        for (int t = tid; t < BA_NF * 27; t += BA_THREADS) {
-            const int f = t / 27, q = t - f * 27;
-            double sum = 0;
-            for (int i = 0; i < f; ++i) sum += part[pair_index(i, f) * 54 + (q < 21 ? q : 42 + (q - 21))];            // f observes
-            for (int j = f + 1; j < BA_NF; ++j) sum += part[pair_index(f, j) * 54 + (q < 21 ? 21 + q : 48 + (q - 21))];   // f hosts
-            if (q < 21) {
-                int a = 0;
-                while ((a + 1) * (a + 2) / 2 <= q) ++a;
-                sh.H[pk(6 * f + a, 6 * f + (q - a * (a + 1) / 2))] = sum;
-            } else
-                sh.g[6 * f + (q - 21)] = sum;
-        }
-        __syncthreads();
     }
     EPROF(1);
-    // ---- IMU factors: one warp per factor ----
-    for (int f = warp; f < m.nimu; f += nwarp) {
-        const int j = m.imu_j[f], i = j - 1;
-        const VrfImuPreint *pre = p.imu + (j - 1);
-        const double *S = p.imuS + (size_t)(j - 1) * 225;
-        double rr[15];
-        ImuCtx cx;
-        imu_residual_raw(pre, pose + 7 * i, sb + 9 * i, pose + 7 * j, sb + 9 * j, m.g_norm, rr, &cx);
-        // whitened residual row `lane`
-        double rw = 0;
-        if (lane < 15) { for (int k = lane; k < 15; ++k) rw += S[lane * 15 + k] * rr[k]; cost += 0.5 * rw * rw; }
-        if (!lin) continue;
-        if (lane < 15) sh.imur[f][lane] = rw;
-        if (lane < 30) {
-            double col[15];
-            imu_jac_col(pre, pose + 7 * i, sb + 9 * i, pose + 7 * j, sb + 9 * j, m.g_norm, &cx, lane, col);
-            for (int rI = 0; rI < 15; ++rI) { double a = 0; for (int k = rI; k < 15; ++k) a += S[rI * 15 + k] * col[k]; sh.imuJ[f][rI * 30 + lane] = a; }
-        }
-        __syncwarp();
-        // accumulate J^T J and J^T r ; tangent column of local column c
-        auto tcol = [&](int c) { return c < 6 ? 6 * i + c : c < 15 ? 66 + 9 * i + (c - 6) : c < 21 ? 6 * j + (c - 15) : 66 + 9 * j + (c - 21); };
-        for (int e = lane; e < 30 * 31 / 2; e += 32) {
-            int a = 0, rem = e;
-            while (rem > a) { rem -= (a + 1); ++a; }       // e -> (a, b<=a) in the 30x30 lower triangle
-            int b = rem;
-            double h = 0;
-            for (int k = 0; k < 15; ++k) h += sh.imuJ[f][k * 30 + a] * sh.imuJ[f][k * 30 + b];
-            atomicAdd(&sh.H[pk(tcol(a), tcol(b))], h);
-        }
-        if (lane < 30) {
-            double gsum = 0;
-            for (int k = 0; k < 15; ++k) gsum += sh.imuJ[f][k * 30 + lane] * sh.imur[f][k];
-            atomicAdd(&sh.g[tcol(lane)], gsum);
-        }
-    }
-    EPROF(2);
     __syncthreads();
     EPROF(3);
+    EPROF(2);
     // ---- prior ----
     const BaPriorStore *P = p.prior;
     const int np_ = (P && P->valid) ? P->n : 0;
     if (np_ > 0) {
-        prior_dx(P, pose, sb, ex, td, sh.dx);
-        __syncthreads();
         const int n = np_;
-        for (int rI = tid; rI < n; rI += BA_THREADS) {
-            double a = P->r0[rI];
-            const double *row = P->J0 + (size_t)rI * n;
-            for (int k = 0; k < n; ++k) a += row[k] * sh.dx[k];
-            sh.pr[rI] = a;
-            cost += 0.5 * a * a;
+        // r = r0 + J0 dx: one warp per row, lanes along the row (coalesced).  For the usual sizes (n <= 96) a warp's
+        // row fragments are requested before dx exists, so that the L2 latency overlaps prior_dx.
+        const bool small = n <= 96;
+        double jv[6][3];
+        if (small) {
+#pragma unroll
+            for (int q = 0; q < 6; ++q)
+#pragma unroll
+                for (int kk = 0; kk < 3; ++kk) {
+                    const int rI = warp + nwarp * q, k = lane + 32 * kk;
+                    jv[q][kk] = (rI < n && k < n) ? __ldg(&P->J0[(size_t)rI * n + k]) : 0.0;
+                }
+        }
+        prior_dx_smem(sh, pose, sb, ex, td);
+        __syncthreads();
+        if (small) {
+            double dxv[3], a[6];
+#pragma unroll
+            for (int kk = 0; kk < 3; ++kk) dxv[kk] = (lane + 32 * kk < n) ? sh.dx[lane + 32 * kk] : 0.0;
+#pragma unroll
+            for (int q = 0; q < 6; ++q) a[q] = jv[q][0] * dxv[0] + jv[q][1] * dxv[1] + jv[q][2] * dxv[2];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+                for (int q = 0; q < 6; ++q) a[q] += __shfl_xor_sync(0xffffffffu, a[q], o);
+#pragma unroll
+            for (int q = 0; q < 6; ++q) {
+                const int rI = warp + nwarp * q;
+                if (lane == 0 && rI < n) { const double v = a[q] + sh.pr0[rI]; sh.pr[rI] = v; cost += 0.5 * v * v; }
+            }
+        } else {
+            for (int rI = warp; rI < n; rI += nwarp) {
+                const double *row = P->J0 + (size_t)rI * n;
+                double a = 0;
+                for (int k = lane; k < n; k += 32) a += row[k] * sh.dx[k];
+                a = warp_sum_d(a);
+                if (lane == 0) { a += sh.pr0[rI]; sh.pr[rI] = a; cost += 0.5 * a * a; }
+            }
         }
         __syncthreads();
         if (lin) {
-            // g += J0^T r ; H += J0^T J0 (precomputed HP), both through the column map
-            for (int a = tid; a < n; a += BA_THREADS) {
-                int ca = p.colmap[a];
-                if (ca < 0) continue;
-                double gsum = 0;
-                for (int rI = 0; rI < n; ++rI) gsum += P->J0[(size_t)rI * n + a] * sh.pr[rI];
-                sh.g[ca] += gsum;
+            // g += J0^T r (column sums split over thread groups) ; H += J0^T J0 (precomputed HP), both through the column map
+            const int npad = (n + 31) & ~31, ngrp = BA_THREADS / npad;
+            const int a = tid % npad, grp = tid / npad;
+            if (grp < ngrp && a < n) {
+                const int ca = sh.pcol[a];
+                if (ca >= 0) {
+                    double gsum = 0;
+#pragma unroll 5
+                    for (int rI = grp; rI < n; rI += ngrp) gsum += __ldg(&P->J0[(size_t)rI * n + a]) * sh.pr[rI];
+                    atomicAdd(&sh.g[ca], gsum);
+                }
             }
+#pragma unroll 4
             for (int e = tid; e < n * n; e += BA_THREADS) {
-                int a = e / n, b = e - a * n;
-                if (b > a) continue;
-                int ca = p.colmap[a], cb = p.colmap[b];
+                int a2 = e / n, b = e - a2 * n;
+                if (b > a2) continue;
+                int ca = sh.pcol[a2], cb = sh.pcol[b];
                 if (ca < 0 || cb < 0) continue;
-                sh.H[pk(ca, cb)] += p.HP[(size_t)a * n + b];
+                sh.H[pk(ca, cb)] += p.HP[(size_t)a2 * n + b];
             }
         }
     }
     __syncthreads();
     EPROF(4);
     if (eprof && blockIdx.x == 0 && (tid == 0 || tid == 320 || tid == 500))
-        printf("evaluate lin=%d tid=%d zero=%lld proj=%lld imu=%lld wait=%lld prior=%lld\n", (int)lin, tid, et[0], et[1], et[2], et[3], et[4]);
+        printf("evaluate lin=%d tid=%d zero=%lld tasks=%lld diag=%lld wait=%lld prior=%lld\n", (int)lin, tid, et[0], et[1], et[2], et[3], et[4]);
 #undef EPROF
     return block_sum(cost, sh.red);
 }
@@ -364,22 +416,76 @@ __device__ __forceinline__ double ba_evaluate(const BaMeta &m, const BaProbDev &
                                         : ba_evaluate_t<false>(m, p, sh, pose, sb, ex, td, lam, lin);
 }
 
+// 8x8 diagonal block (rows/cols j0 .. j0+nbp-1) of the blocked Cholesky, factorised by ONE warp in registers (lane r = row r,
+// shuffles for the pivot column).  `update`: first subtract the rank-8 contribution of the panel staged in sh.Lp (look-ahead).
+// Writes the factor back to sh.H, the reciprocal pivots to sh.colv[0..7], and raises sh.flag[0] on a non-positive pivot.
+__device__ __noinline__ void chol_diag8(BaShared &sh, int j0, int nbp, int lane, bool update)
+{
+    const int rr = lane;
+    double a8[8];
+    const int rrow = j0 + min(rr, nbp - 1);
+    const double *rp = sh.H + rrow * (rrow + 1) / 2 + j0;
+    double lr[8];
+    if (update) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) lr[c] = sh.Lp[c][rrow];
+    }
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        double v = (rr < nbp && c <= rr && c < nbp) ? rp[c] : 0.0;
+        if (update && rr < nbp && c <= rr && c < nbp) {
+            double acc = 0;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) acc += lr[k] * sh.Lp[k][j0 + c];
+            v -= acc;
+        }
+        a8[c] = v;
+    }
+    bool okp = true;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        if (j < nbp) {
+            const double dj = __shfl_sync(0xffffffffu, a8[j], j);
+            if (!(dj > 0.0)) okp = false;
+            // FP64 sqrt/div have ~500-cycle latencies on this part: one rsqrt per pivot instead
+            const double rinv = rsqrt(dj);
+            const double ljj = dj * rinv;
+            const double lrj = (rr == j) ? ljj : a8[j] * rinv;
+            if (rr >= j) a8[j] = lrj;
+            if (lane == 0) sh.colv[j] = rinv;            // 1 / L[j0+j, j0+j]
+#pragma unroll
+            for (int c = j + 1; c < 8; ++c) {
+                const double lcj = __shfl_sync(0xffffffffu, a8[j], c);
+                if (c < nbp && rr >= c) a8[c] -= lrj * lcj;
+            }
+        }
+    }
+    if (rr < nbp) {
+        double *wp = sh.H + (j0 + rr) * (j0 + rr + 1) / 2 + j0;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) if (c <= rr && c < nbp) wp[c] = a8[c];
+    }
+    if (!okp && lane == 0) sh.flag[0] = 1;
+}
+
 // scale a fresh linearisation: H_s = D H D, g_s = D g, W_s, hll_s, gl_s (Jacobi scaling of the Jacobian columns)
 __device__ __noinline__ void ba_scale(const BaMeta &m, const BaProbDev &p, BaShared &sh)
 {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = BA_THREADS / 32;
-    for (int a = tid; a < BA_NC; a += BA_THREADS) {          // one packed row per thread
+    for (int a = warp; a < BA_NC; a += nwarp) {              // one packed row per warp, lanes along the row
         double *row = sh.H + a * (a + 1) / 2;
         const double sa = sh.jscale[a];
-        for (int b = 0; b <= a; ++b) row[b] *= sa * sh.jscale[b];
+        for (int b = lane; b <= a; b += 32) row[b] *= sa * sh.jscale[b];
     }
     for (int c = tid; c < BA_NC; c += BA_THREADS) sh.g[c] *= sh.jscale[c];
-    for (int l = warp; l < m.M; l += nwarp) {
-        const double sl = p.jscale_l[l];
-        double *Wl = p.W + (size_t)l * BA_WS;
-        for (int k = lane; k < BA_WS; k += 32) Wl[k] *= sl * sh.jscale[wcol(k)];
-        if (lane == 0) { p.hll[l] *= sl * sl; p.gl[l] *= sl; }
+    // coupling rows in HBM/L2: flat element loop so that every thread keeps several independent accesses in flight
+    const int nW = m.M * BA_WS;
+#pragma unroll 4
+    for (int e = tid; e < nW; e += BA_THREADS) {
+        const int l = e / BA_WS, k = e - l * BA_WS;
+        p.W[e] *= p.jscale_l[l] * sh.jscale[wcol(k)];
     }
+    for (int l = tid; l < m.M; l += BA_THREADS) { const double sl = p.jscale_l[l]; p.hll[l] *= sl * sl; p.gl[l] *= sl; }
     __syncthreads();
 }
 
@@ -425,15 +531,20 @@ k_ba_solve(const BaMeta *metas, const BaProbDev *probs, BaOutDev *outs)
             for (int rI = 0; rI < n; ++rI) h += P->J0[(size_t)rI * n + a] * P->J0[(size_t)rI * n + b];
             p.HP[(size_t)a * n + b] = h;
         }
-        // prior column -> tangent column (constant blocks drop out)
-        if (n > 0)
+        // prior column -> tangent column (constant blocks drop out); block table, x0 and r0 staged in shared memory
+        if (tid == 0) sh.pnb = n > 0 ? P->n_blocks : 0;
+        if (n > 0) {
             for (int b = tid; b < P->n_blocks; b += BA_THREADS) {
                 const int kind = P->kind[b], ls = P->size[b] == 7 ? 6 : P->size[b];
                 int col = kind == VRF_BLK_POSE ? 6 * P->index[b] : kind == VRF_BLK_SPEEDBIAS ? 66 + 9 * P->index[b]
                           : kind == VRF_BLK_EXPOSE ? BA_COL_EX : kind == VRF_BLK_TD ? BA_COL_TD : -1;
                 if (col >= 0 && !col_active_dev(m, col)) col = -1;
-                for (int c = 0; c < ls; ++c) p.colmap[P->idx[b] + c] = col < 0 ? -1 : col + c;
+                for (int c = 0; c < ls; ++c) { p.colmap[P->idx[b] + c] = col < 0 ? -1 : col + c; sh.pcol[P->idx[b] + c] = col < 0 ? -1 : col + c; }
+                sh.pkind[b] = kind; sh.pindex[b] = P->index[b]; sh.psize[b] = P->size[b]; sh.pidx[b] = P->idx[b];
             }
+            for (int i = tid; i < P->n_blocks * 9; i += BA_THREADS) sh.px0[i] = P->x0[i];
+            for (int i = tid; i < n; i += BA_THREADS) sh.pr0[i] = P->r0[i];
+        }
     }
     __syncthreads();
     __threadfence_block();
@@ -574,88 +685,76 @@ k_ba_solve(const BaMeta *metas, const BaProbDev *probs, BaOutDev *outs)
                     const double *Wl = p.W + (size_t)l * BA_WS;
                     const double gl_h = p.gl[l] / hl;
                     for (int k = lane; k < ws; k += 32) { double w = Wl[k]; if (w != 0.0) atomicAdd(&sh.y[wcol(k)], -w * gl_h); }
-                    if (lane == 0) p.hinv_l[l] = 1.0 / hl;
+                    if (lane == 0) { const double hi_ = 1.0 / hl; p.hinv_l[l] = hi_; p.shinv_l[l] = sqrt(hi_); }
                 }
                 __syncthreads();
                 // S = H + mu D^2 - W^T diag(1/h) W on the pose block (66 columns; + ex-pose and td when variable: ws = 73).
-                // W is streamed through a shared-memory tile (up to 64 landmarks x ws, pre-multiplied by 1/sqrt(h));
-                // every thread owns a fixed set of the ws(ws+1)/2 output entries, so the reduction is deterministic
-                // and atomic-free.
+                // W is streamed through a shared-memory tile (landmarks x ws, pre-multiplied by 1/sqrt(h), rows padded to a
+                // multiple of 3).  A thread owns one 3x3 block of the lower block-triangle and, when the thread count allows,
+                // one of two interleaved landmark subsets: 6 shared-memory loads per 9 FMAs instead of 18 (the phase is
+                // bound by shared-memory bandwidth).
                 {
                     double *tile = reinterpret_cast<double *>(sh.imuJ);      // 4500 doubles available
-                    const int tl = ws == 66 ? 64 : 61;                        // 64*66 = 4224, 61*73 = 4453
-                    int ea[6], eb[6], ne = 0;
-                    double acc[6] = {0, 0, 0, 0, 0, 0};
-                    for (int e = tid; e < ws * (ws + 1) / 2 && ne < 6; e += BA_THREADS) {
-                        int a = (int)((sqrt(8.0 * e + 1.0) - 1.0) * 0.5);
-                        while (a * (a + 1) / 2 > e) --a;
-                        while ((a + 1) * (a + 2) / 2 <= e) ++a;
-                        ea[ne] = a; eb[ne] = e - a * (a + 1) / 2; ++ne;
-                    }
+                    const int nb3 = (ws + 2) / 3, wsp = 3 * nb3;              // 22 blocks / stride 66, or 25 / 75
+                    const int tl = 4500 / wsp;                                // 68 or 60 landmarks per tile
+                    const int nblk = nb3 * (nb3 + 1) / 2;                     // 253 or 325
+                    const int ngrp = (2 * nblk <= BA_THREADS) ? 2 : 1;
+                    const bool actv = tid < ngrp * nblk;
+                    const int grp = tid / nblk, blk = tid - grp * nblk;
+                    int bi = 0;
+                    while ((bi + 1) * (bi + 2) / 2 <= blk) ++bi;
+                    const int bj = blk - bi * (bi + 1) / 2;
+                    double acc[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
                     for (int t0 = 0; t0 < M; t0 += tl) {
                         const int nt = min(tl, M - t0);
-                        for (int q = tid; q < nt * ws; q += BA_THREADS) {
-                            int l = t0 + q / ws, k = q - (q / ws) * ws;
-                            tile[q] = p.lm_const[l] ? 0.0 : p.W[(size_t)l * BA_WS + k] * sqrt(p.hinv_l[l]);
+                        for (int lr = warp; lr < nt; lr += nwarp) {
+                            const int l = t0 + lr;
+                            const double sc_ = p.lm_const[l] ? 0.0 : p.shinv_l[l];
+                            const double *Wl = p.W + (size_t)l * BA_WS;
+                            for (int k = lane; k < wsp; k += 32) tile[lr * wsp + k] = k < ws ? Wl[k] * sc_ : 0.0;
                         }
                         __syncthreads();
-                        for (int q = 0; q < ne; ++q) {
-                            double s_ = 0;
-                            const double *ta = tile + ea[q], *tb = tile + eb[q];
-                            for (int l = 0; l < nt; ++l) s_ += ta[l * ws] * tb[l * ws];
-                            acc[q] += s_;
+                        if (actv) {
+                            const double *ta = tile + 3 * bi, *tb = tile + 3 * bj;
+#pragma unroll 2
+                            for (int l = grp; l < nt; l += ngrp) {
+                                const double a0 = ta[l * wsp], a1 = ta[l * wsp + 1], a2 = ta[l * wsp + 2];
+                                const double b0 = tb[l * wsp], b1 = tb[l * wsp + 1], b2 = tb[l * wsp + 2];
+                                acc[0][0] += a0 * b0; acc[0][1] += a0 * b1; acc[0][2] += a0 * b2;
+                                acc[1][0] += a1 * b0; acc[1][1] += a1 * b1; acc[1][2] += a1 * b2;
+                                acc[2][0] += a2 * b0; acc[2][1] += a2 * b1; acc[2][2] += a2 * b2;
+                            }
                         }
                         __syncthreads();
                     }
-                    for (int q = 0; q < ne; ++q) sh.H[pk(wcol(ea[q]), wcol(eb[q]))] -= acc[q];
+                    if (actv) {
+#pragma unroll
+                        for (int i = 0; i < 3; ++i)
+#pragma unroll
+                            for (int j = 0; j < 3; ++j) {
+                                const int r = 3 * bi + i, c = 3 * bj + j;
+                                if (r < ws && c <= r && acc[i][j] != 0.0) atomicAdd(&sh.H[pk(wcol(r), wcol(c))], -acc[i][j]);
+                            }
+                    }
                 }
                 __syncthreads();      // the diagonal entries are touched again just below by other threads
                 for (int c = tid; c < BA_NC; c += BA_THREADS) sh.H[pk(c, c)] += mu * sh.diag[c] * sh.diag[c];
                 __syncthreads();
                 TPROF(3);
-                // in-place blocked Cholesky (lower, packed, panel width 8) of the 171x171 reduced camera system.
+                // in-place blocked Cholesky (lower, packed, panel width 8) of the 172x172 reduced camera system.
                 // The right-hand side rides along as an extra row (index BA_NC): forward substitution for free.
-                // Per panel: (1) warp 0 factors the 8x8 diagonal block, (2) one thread per row solves the
-                // panel's triangular system, (3) rank-8 update of the trailing matrix  => 3 barriers / panel.
+                // Per panel: (2) one thread per row solves the panel's triangular system, (3) rank-8 update of the
+                // trailing matrix by warps 1..15 (4 rows x 1 column register tiles) WHILE warp 0 updates and factorises
+                // the next panel's 8x8 diagonal block (look-ahead: the serial pivot chain is off the critical path)
+                // => 2 barriers / panel.
                 bool bad = sh.flag[0] != 0;
+                if (!bad) {
+                    if (warp == 0) chol_diag8(sh, 0, min(8, BA_NC), lane, false);
+                    __syncthreads();
+                    bad = sh.flag[0] != 0;
+                }
                 for (int j0 = 0; j0 < BA_NC && !bad; j0 += 8) {
                     const int nbp = min(8, BA_NC - j0);
-                    if (warp == 0) {
-                        // (1) the 8x8 diagonal block lives in registers of warp 0 (lane r = row r), factorised with shuffles
-                        const int rr = lane;
-                        double a8[8];
-                        const int rrow = j0 + min(rr, nbp - 1);
-                        const double *rp = sh.H + rrow * (rrow + 1) / 2 + j0;
-#pragma unroll
-                        for (int c = 0; c < 8; ++c) a8[c] = (rr < nbp && c <= rr && c < nbp) ? rp[c] : 0.0;
-                        bool okp = true;
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            if (j < nbp) {
-                                const double dj = __shfl_sync(0xffffffffu, a8[j], j);
-                                if (!(dj > 0.0)) okp = false;
-                                // FP64 sqrt/div have ~500-cycle latencies on this part: one rsqrt per pivot instead
-                                const double rinv = rsqrt(dj);
-                                const double ljj = dj * rinv;
-                                const double lrj = (rr == j) ? ljj : a8[j] * rinv;
-                                if (rr >= j) a8[j] = lrj;
-                                if (lane == 0) sh.colv[j] = rinv;            // 1 / L[j0+j, j0+j]
-#pragma unroll
-                                for (int c = j + 1; c < 8; ++c) {
-                                    const double lcj = __shfl_sync(0xffffffffu, a8[j], c);
-                                    if (c < nbp && rr >= c) a8[c] -= lrj * lcj;
-                                }
-                            }
-                        }
-                        if (rr < nbp) {
-                            double *wp = sh.H + (j0 + rr) * (j0 + rr + 1) / 2 + j0;
-#pragma unroll
-                            for (int c = 0; c < 8; ++c) if (c <= rr && c < nbp) wp[c] = a8[c];
-                        }
-                        if (!okp && lane == 0) sh.flag[0] = 1;
-                    }
-                    __syncthreads();
-                    if (sh.flag[0]) { bad = true; break; }
                     // (2) rows below the panel (incl. the rhs row): x * Ld^T = a ; the solved panel is also
                     //     staged transposed in Lp so that step (3) reads it without bank conflicts
                     for (int i2 = j0 + nbp + tid; i2 <= BA_NC; i2 += BA_THREADS) {
@@ -676,38 +775,89 @@ k_ba_solve(const BaMeta *metas, const BaProbDev *probs, BaOutDev *outs)
                         }
                     }
                     __syncthreads();
-                    // (3) trailing update H[ii,kk] -= sum_c L[ii,j0+c] L[kk,j0+c]; 16 x 32 thread tile over (ii, kk)
-                    {
-                        const int tx = tid & 31, ty = tid >> 5;
-                        const int t0 = j0 + nbp;
-                        for (int ii = t0 + ty; ii <= BA_NC; ii += BA_THREADS / 32) {
-                            double lv[8];
+                    // (3) trailing update H[ii,kk] -= sum_c L[ii,j0+c] L[kk,j0+c]
+                    const int t0 = j0 + nbp;
+                    const int nb2 = min(8, BA_NC - t0);            // width of the next panel (<= 0: none)
+                    if (warp == 0) {
+                        if (nb2 > 0) chol_diag8(sh, t0, nb2, lane, true);
+                    } else {
+                        const int w1 = warp - 1, nw1 = BA_THREADS / 32 - 1;
+                        for (int ib = t0 + max(nb2, 0) + w1; ib <= BA_NC; ib += 4 * nw1) {
+                            double lv[4][8];
+                            double *rowp[4];
+                            int kend[4];
 #pragma unroll
-                            for (int c = 0; c < 8; ++c) lv[c] = sh.Lp[c][ii];
-                            double *row = (ii < BA_NC) ? sh.H + ii * (ii + 1) / 2 : sh.y;
-                            const int kend = (ii < BA_NC) ? ii : BA_NC - 1;
-                            for (int kk = t0 + tx; kk <= kend; kk += 32) {
-                                double acc = 0;
+                            for (int r = 0; r < 4; ++r) {
+                                const int ii = ib + r * nw1;
+                                const bool ok = ii <= BA_NC;
+                                rowp[r] = (ii < BA_NC) ? sh.H + ii * (ii + 1) / 2 : sh.y;
+                                kend[r] = ok ? min(ii, BA_NC - 1) : -1;
 #pragma unroll
-                                for (int c = 0; c < 8; ++c) acc += lv[c] * sh.Lp[c][kk];
-                                row[kk] -= acc;
+                                for (int c = 0; c < 8; ++c) lv[r][c] = ok ? sh.Lp[c][ii] : 0.0;
+                            }
+                            const int kmax = max(max(kend[0], kend[1]), max(kend[2], kend[3]));
+                            for (int kk = t0 + lane; kk <= kmax; kk += 32) {
+                                double lp[8];
+#pragma unroll
+                                for (int c = 0; c < 8; ++c) lp[c] = sh.Lp[c][kk];
+#pragma unroll
+                                for (int r = 0; r < 4; ++r) {
+                                    if (kk <= kend[r]) {
+                                        double acc = 0;
+#pragma unroll
+                                        for (int c = 0; c < 8; ++c) acc += lv[r][c] * lp[c];
+                                        rowp[r][kk] -= acc;
+                                    }
+                                }
                             }
                         }
                     }
                     __syncthreads();
+                    if (sh.flag[0]) { bad = true; break; }
                 }
                 TPROF(4);
                 if (!bad) {
-                    // back substitution L^T x = z by one warp (warp-level sync only)
+                    // back substitution L^T x = z by one warp with the solution vector in registers (lane holds entries
+                    // lane, lane + 32, ...): per step one multiply by the stored reciprocal pivot, one broadcast and one
+                    // FMA per register; the rows of L are prefetched one step ahead.
+                    for (int c = tid; c < BA_NC; c += BA_THREADS) sh.colv[c] = 1.0 / sh.H[pk(c, c)];
+                    __syncthreads();
                     if (warp == 0) {
-                        for (int i = BA_NC - 1; i >= 0; --i) {
-                            if (lane == 0) sh.y[i] /= sh.H[pk(i, i)];
-                            __syncwarp();
-                            const double yi = sh.y[i];
-                            const double *row = sh.H + i * (i + 1) / 2;
-                            for (int k = lane; k < i; k += 32) sh.y[k] -= row[k] * yi;
-                            __syncwarp();
+                        constexpr int NS = (BA_NC + 31) / 32;
+                        double yv[NS], cur[NS], nxt[NS];
+#pragma unroll
+                        for (int q = 0; q < NS; ++q) { const int k = lane + 32 * q; yv[q] = k < BA_NC ? sh.y[k] : 0.0; }
+                        {
+                            const double *row = sh.H + (BA_NC - 1) * BA_NC / 2;
+#pragma unroll
+                            for (int q = 0; q < NS; ++q) { const int k = lane + 32 * q; cur[q] = k < BA_NC - 1 ? row[k] : 0.0; }
                         }
+                        double rcur = sh.colv[BA_NC - 1];
+#pragma unroll
+                        for (int mq = NS - 1; mq >= 0; --mq) {
+                            const int ihi = min(32 * mq + 31, BA_NC - 1);
+                            for (int i = ihi; i >= 32 * mq; --i) {
+                                // prefetch row i-1 (entries k < i-1)
+                                if (i > 0) {
+                                    const double *row = sh.H + (i - 1) * i / 2;
+#pragma unroll
+                                    for (int q = 0; q <= mq; ++q) { const int k = lane + 32 * q; nxt[q] = k < i - 1 ? row[k] : 0.0; }
+                                }
+                                const double rnx = sh.colv[i > 0 ? i - 1 : 0];
+                                const double xi = __shfl_sync(0xffffffffu, yv[mq] * rcur, i & 31);
+                                if (lane == (i & 31)) yv[mq] = xi;
+#pragma unroll
+                                for (int q = 0; q <= mq; ++q) {
+                                    const int k = lane + 32 * q;
+                                    if (k < i) yv[q] -= cur[q] * xi;
+                                }
+#pragma unroll
+                                for (int q = 0; q <= mq; ++q) cur[q] = nxt[q];
+                                rcur = rnx;
+                            }
+                        }
+#pragma unroll
+                        for (int q = 0; q < NS; ++q) { const int k = lane + 32 * q; if (k < BA_NC) sh.y[k] = yv[q]; }
                     }
                     __syncthreads();
                     double fin = 0;

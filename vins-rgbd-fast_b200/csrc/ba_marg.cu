@@ -114,12 +114,12 @@ __device__ __noinline__ void jacobi_eig(double *A, double *V, int n, MargShared 
 //  * the rotation needs no division: with d = aqq - app, e = 2 apq, h = hypot(d, e), g = |d| + h:
 //    c = g / hypot(g, e), s = sign(d e) |e| / hypot(g, e)  (two rsqrt; FP64 div is ~10x an FMA here);
 //  * every thread keeps its work items for the whole call in registers.
-#define MARG_SMEM_N 110
+#define MARG_SMEM_N 92
 #define MARG_NE(n) (((n) + 1) & ~1)
 #define MARG_LDA(n) (MARG_NE(n) | 1)
 #define MARG_A_ELEMS(n) (MARG_NE(n) * MARG_LDA(n))              /* even: VT stays 16-byte aligned */
 #define MARG_V_ELEMS(n) (MARG_NE(n) * MARG_NE(n))
-#define JAC_V_ITEMS 8      /* >= ceil(55 * 55 / 448), processed in groups of 4 */
+#define JAC_V_ITEMS 8      /* >= ceil(46 * 46 / 448), processed in groups of 4 */
 // round-robin tournament: pair k of round r (ne players, player ne-1 fixed), returned with p < q
 __device__ __forceinline__ int2 jac_pair(int r, int k, int ne)
 {
@@ -150,6 +150,8 @@ __device__ __forceinline__ double2 jac_angle(const double *A, int ld, int2 pq)
 }
 
 #define JAC_ANGLE_THREADS 64       /* warps 0-1 compute the next round's angles while the others rotate V */
+// (A table of the round-robin pairs in shared memory was tried and measured 7 % SLOWER: a round is bound by the
+// latency of its dependent shared-memory accesses, not by instruction issue, and the lookup lengthens that chain.)
 __device__ __noinline__ void jacobi_eig_smem(double *A, double *VT, int n, MargShared &sh)
 {
     const int tid = threadIdx.x;
@@ -158,6 +160,7 @@ __device__ __noinline__ void jacobi_eig_smem(double *A, double *VT, int n, MargS
     for (int e = tid; e < ne * ldv; e += BA_THREADS) VT[e] = (e / ldv == e % ldv) ? 1.0 : 0.0;
     __syncthreads();
     if (n < 2) return;
+    auto pair_at = [&](int r, int k) { return jac_pair(r, k, ne); };
     // A-block items: upper triangle of the (pair x pair) grid, dealt from the top thread down
     const int ntri = npairs * (npairs + 1) / 2;
     int bk1[4], bk2[4];
@@ -197,7 +200,7 @@ __device__ __noinline__ void jacobi_eig_smem(double *A, double *VT, int n, MargS
         dg = block_sum(dg, sh.red);
         if (off <= 1e-26 * dg || off == 0.0) break;     // relative off-diagonal norm 1e-13
         ++nsweep;
-        if (tid < npairs) csb[0][tid] = jac_angle(A, ld, jac_pair(0, tid, ne));
+        if (tid < npairs) csb[0][tid] = jac_angle(A, ld, pair_at(0, tid));
         __syncthreads();
         if (sh.jdbg) jc = clock64();
         for (int r = 0; r < ne - 1; ++r) {
@@ -216,7 +219,7 @@ __device__ __noinline__ void jacobi_eig_smem(double *A, double *VT, int n, MargS
                     live[uu] = k1 >= 0;
                     const int kk1 = live[uu] ? k1 : 0, kk2 = live[uu] ? k2 : 0;
                     r1[uu] = cs2[kk1]; r2[uu] = cs2[kk2];
-                    const int2 i1 = jac_pair(r, kk1, ne), i2 = jac_pair(r, kk2, ne);
+                    const int2 i1 = pair_at(r, kk1), i2 = pair_at(r, kk2);
                     // diagonal block (k1 == k2): entries (p,p) (p,q) (p,q) (q,q)
                     e11[uu] = min(i1.x, i2.x) * ld + max(i1.x, i2.x); e12[uu] = min(i1.x, i2.y) * ld + max(i1.x, i2.y);
                     e21[uu] = min(i1.y, i2.x) * ld + max(i1.y, i2.x); e22[uu] = min(i1.y, i2.y) * ld + max(i1.y, i2.y);
@@ -243,7 +246,7 @@ __device__ __noinline__ void jacobi_eig_smem(double *A, double *VT, int n, MargS
             JPROF(1);
             if (tid < JAC_ANGLE_THREADS) {
                 // next round's rotation angles (double-buffered) ...
-                if (tid < npairs && r + 1 < ne - 1) csb[(r + 1) & 1][tid] = jac_angle(A, ld, jac_pair(r + 1, tid, ne));
+                if (tid < npairs && r + 1 < ne - 1) csb[(r + 1) & 1][tid] = jac_angle(A, ld, pair_at(r + 1, tid));
             } else {
                 // ... while the other warps apply this round's rotations to the eigenvectors
 #pragma unroll
@@ -255,7 +258,7 @@ __device__ __noinline__ void jacobi_eig_smem(double *A, double *VT, int n, MargS
                     for (int uu = 0; uu < 4; ++uu) {
                         const int k = vk[u0 + uu] < 0 ? 0 : vk[u0 + uu];
                         rc[uu] = cs2[k];
-                        const int2 ip = jac_pair(r, k, ne);
+                        const int2 ip = pair_at(r, k);
                         colp[uu] = reinterpret_cast<double2 *>(VT + ip.x * ldv) + vi[u0 + uu];
                         colq[uu] = reinterpret_cast<double2 *>(VT + ip.y * ldv) + vi[u0 + uu];
                         va[uu] = *colp[uu]; vb[uu] = *colq[uu];
@@ -423,11 +426,12 @@ k_ba_marg(const BaMeta *metas, const BaProbDev *probs, BaOutDev *outs, const BaM
         // residual at the current (gauge-fixed) states
         prior_dx(P, pose, sb, ex, out.mtd, sh.dx);
         __syncthreads();
-        for (int rI = tid; rI < np; rI += BA_THREADS) {
-            double a = P->r0[rI];
+        for (int rI = warp; rI < np; rI += nwarp) {       // one warp per row, lanes along the row (coalesced)
             const double *row = P->J0 + (size_t)rI * np;
-            for (int k = 0; k < np; ++k) a += row[k] * sh.dx[k];
-            sh.pr[rI] = a;
+            double a = 0;
+            for (int k = lane; k < np; k += 32) a += row[k] * sh.dx[k];
+            a = warp_sum_d(a);
+            if (lane == 0) sh.pr[rI] = a + P->r0[rI];
         }
         // prior column -> A column (reuse p.colmap scratch)
         for (int b = tid; b < P->n_blocks; b += BA_THREADS) {
@@ -436,10 +440,14 @@ k_ba_marg(const BaMeta *metas, const BaProbDev *probs, BaOutDev *outs, const BaM
             for (int c = 0; c < ls; ++c) p.colmap[P->idx[b] + c] = (i >= 0) ? sh.idx[i] + c : -1;
         }
         __syncthreads();
-        for (int a = tid; a < np; a += BA_THREADS) {
-            double gsum = 0;
-            for (int rI = 0; rI < np; ++rI) gsum += P->J0[(size_t)rI * np + a] * sh.pr[rI];
-            if (p.colmap[a] >= 0) bv[p.colmap[a]] += gsum;
+        {
+            const int npad = (np + 31) & ~31, ngrp = BA_THREADS / npad;
+            const int a = tid % npad, grp = tid / npad;
+            if (grp < ngrp && a < np && p.colmap[a] >= 0) {
+                double gsum = 0;
+                for (int rI = grp; rI < np; rI += ngrp) gsum += P->J0[(size_t)rI * np + a] * sh.pr[rI];
+                atomicAdd(&bv[p.colmap[a]], gsum);
+            }
         }
         for (int e = tid; e < np * np; e += BA_THREADS) {
             int a = e / np, c = e - a * np;
@@ -500,6 +508,8 @@ k_ba_marg(const BaMeta *metas, const BaProbDev *probs, BaOutDev *outs, const BaM
             const bool act = lane < nf;
             const int j = 1 + lane;
             double r[2] = {0, 0}, Ji[12], Jj[12], Jl[2] = {0, 0}, Je[12], Jt[2] = {0, 0};
+#pragma unroll
+            for (int k = 0; k < 12; ++k) { Ji[k] = 0; Jj[k] = 0; Je[k] = 0; }
             if (act) {
                 double xi, yi, xj, yj;
                 obs_at(m, p, o0, out.mtd, xi, yi);
@@ -511,25 +521,59 @@ k_ba_marg(const BaMeta *metas, const BaProbDev *probs, BaOutDev *outs, const BaM
             const double hsum = warp_sum_d(Jl[0] * Jl[0] + Jl[1] * Jl[1]);
             const double gsum = warp_sum_d(Jl[0] * r[0] + Jl[1] * r[1]);
             if (lane == 0) { hm[li] = hsum; hm[nl0c + li] = gsum; }
-            if (!act) continue;
             double *wr = Wm + (size_t)li * MG_L;
-            // 19 local columns of this factor: pose0 (0..5), pose j (6j..), ex (66..), td (72; zero unless ESTIMATE_TD)
-            int lc[19]; double J0r[19], J1r[19];
-            lc[18] = 72; J0r[18] = Jt[0]; J1r[18] = Jt[1];
+            // (a) the 13 columns every factor of this landmark shares -- pose0 (Ji), ex-pose (Je), td (Jt): their 91
+            // normal-matrix entries, 13 gradient entries and 13 landmark-coupling entries are summed over the lanes
+            // with the reduce-scatter butterfly; one lane per value then adds the warp total (no intra-warp contention).
+            {
+                double s0[13], s1[13];
 #pragma unroll
-            for (int c = 0; c < 6; ++c) {
-                lc[c] = c; J0r[c] = Ji[c]; J1r[c] = Ji[6 + c];
-                lc[6 + c] = 6 * j + c; J0r[6 + c] = Jj[c]; J1r[6 + c] = Jj[6 + c];
-                lc[12 + c] = 66 + c; J0r[12 + c] = Je[c]; J1r[12 + c] = Je[6 + c];
+                for (int c = 0; c < 6; ++c) { s0[c] = Ji[c]; s1[c] = Ji[6 + c]; s0[6 + c] = Je[c]; s1[6 + c] = Je[6 + c]; }
+                s0[12] = Jt[0]; s1[12] = Jt[1];
+                auto scol = [](int a_) { return a_ < 6 ? a_ : a_ < 12 ? 66 + (a_ - 6) : 72; };
+#pragma unroll
+                for (int rd = 0; rd < 8; ++rd) {
+                    double v[16];
+#pragma unroll
+                    for (int t = 0; t < 16; ++t) {
+                        const int e = rd * 16 + t;
+                        if (e < 91) {
+                            int a_ = 0;
+                            while ((a_ + 1) * (a_ + 2) / 2 <= e) ++a_;
+                            const int b_ = e - a_ * (a_ + 1) / 2;
+                            v[t] = s0[a_] * s0[b_] + s1[a_] * s1[b_];
+                        } else if (e < 104) v[t] = s0[e - 91] * r[0] + s1[e - 91] * r[1];
+                        else if (e < 117) v[t] = s0[e - 104] * Jl[0] + s1[e - 104] * Jl[1];
+                        else v[t] = 0.0;
+                    }
+                    const double tot = reduce_scatter16(v, lane);
+                    const int e = rd * 16 + (lane >> 1);
+                    if (!(lane & 1) && e < 117 && tot != 0.0) {
+                        if (e < 91) {
+                            int a_ = 0;
+                            while ((a_ + 1) * (a_ + 2) / 2 <= e) ++a_;
+                            atomicAdd(&H72[pk72(scol(a_), scol(e - a_ * (a_ + 1) / 2))], tot);
+                        } else if (e < 104) atomicAdd(&g72[scol(e - 91)], tot);
+                        else wr[scol(e - 104)] = tot;                 // this warp owns the landmark's row
+                    }
+                }
             }
+            if (!act) continue;
+            // (b) the observer's own pose block (columns 6j..6j+5): lane-private within the warp
 #pragma unroll
-            for (int a_ = 0; a_ < 19; ++a_) {
-                if (a_ == 18 && !m.td_factor) break;
-                atomicAdd(&g72[lc[a_]], J0r[a_] * r[0] + J1r[a_] * r[1]);
-                const double wv = J0r[a_] * Jl[0] + J1r[a_] * Jl[1];
-                if (a_ >= 6 && a_ < 12) wr[lc[a_]] = wv; else atomicAdd(&wr[lc[a_]], wv);
+            for (int a_ = 0; a_ < 6; ++a_) {
+                const double j0a = Jj[a_], j1a = Jj[6 + a_];
+                const int ca = 6 * j + a_;
+                atomicAdd(&g72[ca], j0a * r[0] + j1a * r[1]);
+                wr[ca] = j0a * Jl[0] + j1a * Jl[1];
 #pragma unroll
-                for (int c = 0; c <= a_; ++c) atomicAdd(&H72[pk72(lc[a_], lc[c])], J0r[a_] * J0r[c] + J1r[a_] * J1r[c]);
+                for (int c = 0; c <= a_; ++c) atomicAdd(&H72[pk72(ca, 6 * j + c)], j0a * Jj[c] + j1a * Jj[6 + c]);
+#pragma unroll
+                for (int c = 0; c < 6; ++c) {
+                    atomicAdd(&H72[pk72(ca, c)], j0a * Ji[c] + j1a * Ji[6 + c]);
+                    atomicAdd(&H72[pk72(66 + c, ca)], j0a * Je[c] + j1a * Je[6 + c]);
+                }
+                if (m.td_factor) atomicAdd(&H72[pk72(72, ca)], j0a * Jt[0] + j1a * Jt[1]);
             }
         }
         __syncthreads();
@@ -794,6 +838,9 @@ k_ba_marg(const BaMeta *metas, const BaProbDev *probs, BaOutDev *outs, const BaM
     }
 }
 
+// 164 KB carve-out (minus the 1 KB reserve): leaves 92 KB of L1 for the global scratch of the elimination phases
+static_assert(((sizeof(MargShared) + 15) & ~(size_t)15) + sizeof(double) * (MARG_A_ELEMS(MARG_SMEM_N) + MARG_V_ELEMS(MARG_SMEM_N)) <= 164 * 1024 - 1024,
+              "marginalization frame must fit the 164 KB carve-out");
 static size_t marg_smem() { return ((sizeof(MargShared) + 15) & ~(size_t)15) + sizeof(double) * (MARG_A_ELEMS(MARG_SMEM_N) + MARG_V_ELEMS(MARG_SMEM_N)); }
 size_t ba_marg_smem_bytes() { return marg_smem(); }
 

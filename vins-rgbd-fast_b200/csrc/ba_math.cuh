@@ -119,6 +119,24 @@ __device__ __forceinline__ double half_sum_d(double v)
     for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
 }
+// Sum 16 per-lane values over the 32 lanes with 16 shuffles: after the four scatter stages lane L holds the
+// total of value (L >> 1) over its 16-lane partner set, the last stage completes it (lanes 2m, 2m+1 agree).
+__device__ __forceinline__ double reduce_scatter16(double (&v)[16], int lane)
+{
+#pragma unroll
+    for (int st = 0; st < 4; ++st) {
+        const int n2 = 8 >> st, mask = 16 >> st;
+        const bool up = (lane & mask) != 0;
+#pragma unroll
+        for (int k = 0; k < n2; ++k) {
+            const double keep = up ? v[k + n2] : v[k];
+            const double send = up ? v[k] : v[k + n2];
+            v[k] = keep + __shfl_xor_sync(0xffffffffu, send, mask);
+        }
+    }
+    return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 1);
+}
+
 // deterministic block sum (BA_THREADS threads), result broadcast to all threads
 static __device__ double block_sum(double v, double *s_red)
 {

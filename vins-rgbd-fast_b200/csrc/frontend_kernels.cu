@@ -93,15 +93,20 @@ k_ingest(FrontCfg c, const SeqCall *calls, int ncalls, FrontDev d, const uint8_t
 
 // ---------------------------------------------------------------------------
 // k_pyrdown: cv::pyrDown (5x5 separable [1 4 6 4 1], (sum+128)>>8, REFLECT_101).
-// CTA tile = 64 x 16 outputs; horizontal pass of 35 input rows into shared
-// memory (u16), vertical pass from shared memory.
+// CTA tile = 64 x 32 outputs.  A thread owns 8 adjacent outputs of a row: the
+// horizontal pass reads their 20 source bytes as one 16-byte word plus two
+// 2-byte halos (rows are 16-byte aligned), forms the five taps as packed
+// u16 pairs with byte permutes (row sums <= 16*255 fit 16 bits) and parks
+// 8 sums = 16 bytes in shared memory; the vertical pass combines five such
+// rows, again on packed pairs (<= 256*255 still fits), and stores 8 bytes.
 // ---------------------------------------------------------------------------
 #define PD_TW 64
-#define PD_TH 16
+#define PD_TH 32
+#define PD_SEG (PD_TW / 8)
 __global__ void __launch_bounds__(256)
 k_pyrdown(FrontCfg c, const SeqCall *calls, FrontDev d, int level)
 {
-    __shared__ unsigned short s_h[2 * PD_TH + 3][PD_TW];
+    __shared__ uint4 s_h[2 * PD_TH + 3][PD_SEG];
     const SeqCall call = calls[blockIdx.z];
     const uint8_t *src = d.pyr[call.buf_cur] + (size_t)call.seq * c.pyr_bytes + c.loff[level];
     uint8_t *dst = d.pyr[call.buf_cur] + (size_t)call.seq * c.pyr_bytes + c.loff[level + 1];
@@ -109,28 +114,69 @@ k_pyrdown(FrontCfg c, const SeqCall *calls, FrontDev d, int level)
     const int dw = c.lw[level + 1], dh = c.lh[level + 1], dp = c.lp[level + 1];
     const int ox = blockIdx.x * PD_TW, oy = blockIdx.y * PD_TH;
     const int nrow = 2 * PD_TH + 3;
-    for (int i = threadIdx.x; i < nrow * PD_TW; i += 256) {
-        int r = i / PD_TW, x = i - r * PD_TW;
-        int sy = reflect101(2 * oy + r - 2, sh);
-        int dx = ox + x;
-        unsigned v = 0;
-        if (dx < dw) {
+    for (int it = threadIdx.x; it < nrow * PD_SEG; it += 256) {
+        const int r = it / PD_SEG, sg = it - r * PD_SEG;
+        const int dx0 = ox + 8 * sg;
+        uint4 out = make_uint4(0, 0, 0, 0);
+        if (dx0 < dw) {
+            const int sy = reflect101(2 * oy + r - 2, sh);
             const uint8_t *row = src + (size_t)sy * sp;
-            int cx = 2 * dx;
-            int x0 = reflect101(cx - 2, sw), x1 = reflect101(cx - 1, sw), x3 = reflect101(cx + 1, sw),
-                x4 = reflect101(cx + 2, sw);
-            v = row[x0] + 4u * row[x1] + 6u * row[cx] + 4u * row[x3] + row[x4];
+            const int x0 = 2 * dx0;                       // source column of the first output's centre tap
+            uint4 w;
+            unsigned lft, rgt;                            // bytes (x0-2, x0-1) and (x0+16, x0+17)
+            if (x0 >= 2 && x0 + 18 <= sw) {
+                w = *reinterpret_cast<const uint4 *>(row + x0);
+                lft = *reinterpret_cast<const unsigned short *>(row + x0 - 2);
+                rgt = *reinterpret_cast<const unsigned short *>(row + x0 + 16);
+            } else {
+                unsigned bb[20];
+#pragma unroll
+                for (int k = 0; k < 20; ++k) bb[k] = row[reflect101(x0 - 2 + k, sw)];
+                lft = bb[0] | (bb[1] << 8);
+                w.x = bb[2] | (bb[3] << 8) | (bb[4] << 16) | (bb[5] << 24);
+                w.y = bb[6] | (bb[7] << 8) | (bb[8] << 16) | (bb[9] << 24);
+                w.z = bb[10] | (bb[11] << 8) | (bb[12] << 16) | (bb[13] << 24);
+                w.w = bb[14] | (bb[15] << 8) | (bb[16] << 16) | (bb[17] << 24);
+                rgt = bb[18] | (bb[19] << 8);
+            }
+            // even / odd source bytes as u16 pairs: EP[j] = (b[4j], b[4j+2]), OP[j] = (b[4j+1], b[4j+3])
+            const unsigned wv[4] = {w.x, w.y, w.z, w.w};
+            unsigned EP[6], OP[5];
+            EP[0] = (lft & 0xFFu) << 16;                  // (-, b[-2])
+            OP[0] = (lft >> 8) << 16;                     // (-, b[-1])
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { EP[j + 1] = __byte_perm(wv[j], 0u, 0x4240); OP[j + 1] = __byte_perm(wv[j], 0u, 0x4341); }
+            EP[5] = rgt & 0xFFu;                          // (b[16], -)
+            unsigned o[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const unsigned eprev = __byte_perm(EP[j], EP[j + 1], 0x5432), enext = __byte_perm(EP[j + 1], EP[j + 2], 0x5432);
+                const unsigned oprev = __byte_perm(OP[j], OP[j + 1], 0x5432);
+                o[j] = eprev + enext + 6u * EP[j + 1] + 4u * (oprev + OP[j + 1]);
+            }
+            out = make_uint4(o[0], o[1], o[2], o[3]);
         }
-        s_h[r][x] = (unsigned short)v;
+        s_h[r][sg] = out;
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < PD_TH * PD_TW; i += 256) {
-        int y = i / PD_TW, x = i - y * PD_TW;
-        int dy = oy + y, dx = ox + x;
-        if (dy < dh && dx < dw) {
-            unsigned v = s_h[2 * y][x] + 4u * s_h[2 * y + 1][x] + 6u * s_h[2 * y + 2][x] +
-                         4u * s_h[2 * y + 3][x] + s_h[2 * y + 4][x];
-            dst[(size_t)dy * dp + dx] = (uint8_t)((v + 128u) >> 8);
+    {
+        const int y = threadIdx.x / PD_SEG, sg = threadIdx.x - y * PD_SEG;
+        const int dy = oy + y, dx0 = ox + 8 * sg;
+        if (dy < dh && dx0 < dw) {
+            const uint4 a0 = s_h[2 * y][sg], a1 = s_h[2 * y + 1][sg], a2 = s_h[2 * y + 2][sg], a3 = s_h[2 * y + 3][sg], a4 = s_h[2 * y + 4][sg];
+            const unsigned rnd = 0x00800080u, msk = 0x00FF00FFu;
+            const unsigned v0 = ((a0.x + a4.x + 4u * (a1.x + a3.x) + 6u * a2.x + rnd) >> 8) & msk;
+            const unsigned v1 = ((a0.y + a4.y + 4u * (a1.y + a3.y) + 6u * a2.y + rnd) >> 8) & msk;
+            const unsigned v2 = ((a0.z + a4.z + 4u * (a1.z + a3.z) + 6u * a2.z + rnd) >> 8) & msk;
+            const unsigned v3 = ((a0.w + a4.w + 4u * (a1.w + a3.w) + 6u * a2.w + rnd) >> 8) & msk;
+            const unsigned lo = __byte_perm(v0, v1, 0x6420), hi = __byte_perm(v2, v3, 0x6420);
+            uint8_t *q = dst + (size_t)dy * dp + dx0;
+            if (dx0 + 8 <= dw) *reinterpret_cast<uint2 *>(q) = make_uint2(lo, hi);
+            else {
+#pragma unroll
+                for (int k = 0; k < 8; ++k)
+                    if (dx0 + k < dw) q[k] = (uint8_t)(((k < 4 ? lo : hi) >> (8 * (k & 3))) & 0xFFu);
+            }
         }
     }
 }
