@@ -238,6 +238,8 @@ long vrf_debug_read(vrf_handle *h, const char *what, int seq, void *dst, size_t 
 /* Back end (declared in vrf_ba.h, included here for convenience)             */
 /* ------------------------------------------------------------------------- */
 #include "vrf_ba.h"
+/* Neighbouring steps: triangulateWithDepth, movingConsistencyCheck, IMU pre-integration (vrf_fm.h) */
+#include "vrf_fm.h"
 
 #ifdef __cplusplus
 }

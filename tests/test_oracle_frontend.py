@@ -123,7 +123,7 @@ def test_stdsort_restatement_matches_libstdcxx(built_lib):
 def test_abi_exports_every_declared_symbol(built_lib):
     from vrf_b200 import binding
     declared = set()
-    for hdr in ("vrf.h", "vrf_ba.h"):
+    for hdr in ("vrf.h", "vrf_ba.h", "vrf_fm.h"):
         txt = open(os.path.join(ROOT, "include", hdr)).read()
         txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
         declared |= set(re.findall(r"\b(vrf_[a-z0-9_]+)\s*\(", txt))

@@ -195,6 +195,7 @@ extern "C" void vrf_destroy(vrf_handle *h)
     for (int k = 0; k < VRF_COPY_STREAMS; ++k) if (h->copy_stream[k]) cudaStreamSynchronize(h->copy_stream[k]);
     if (h->stream) cudaStreamSynchronize(h->stream);
     ba_destroy(h);
+    fm_destroy(h);
     FrontDev &d = h->fd;
     void *ptrs[] = {d.pyr[0], d.pyr[1], d.cur_pts, d.prev_un, d.ids, d.cnt, d.n_pts, d.n_id, d.pred_pts, d.lk_pts,
                     d.lk_status, d.n_lk, d.t_prev, d.t_forw, d.t_prevun, d.t_ids, d.t_cnt, d.t_n, d.t_keep,

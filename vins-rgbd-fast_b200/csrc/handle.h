@@ -11,15 +11,16 @@
 
 namespace vrf {
 struct BaState;   // ba_host.cu
+struct FmState;   // fm_kernels.cu
 
 // Kernel ids for launch counting and optional per-kernel CUDA-event profiling.
 enum KernelId {
     K_INGEST = 0, K_PYRDOWN, K_LK, K_POST_A, K_RANSAC, K_POST_B, K_FAST, K_FINISH,
-    K_BA_SOLVE, K_BA_MARG, K_COUNT
+    K_BA_SOLVE, K_BA_MARG, K_FM_TRI, K_FM_CHECK, K_IMU_PREINT, K_COUNT
 };
 static const char *const kKernelNames[K_COUNT] = {
     "k_ingest", "k_pyrdown", "k_lk", "k_post_a", "k_ransac", "k_post_b", "k_fast", "k_finish",
-    "k_ba_solve", "k_ba_marg"};
+    "k_ba_solve", "k_ba_marg", "k_fm_triangulate", "k_fm_check", "k_imu_preint"};
 
 struct Prof {
     bool enabled = false;
@@ -95,6 +96,7 @@ struct vrf_handle {
     uint64_t launches = 0;
     vrf::Prof prof;
     vrf::BaState *ba = nullptr;
+    vrf::FmState *fm = nullptr;      // staging of the stateless feature-manager / pre-integration calls (lazily allocated)
 };
 
 namespace vrf {
@@ -111,4 +113,6 @@ int ba_create(vrf_handle *h);
 void ba_destroy(vrf_handle *h);
 int ba_reset_sequence(vrf_handle *h, int seq);
 long ba_debug_prof(vrf_handle *h, int slot, void *dst, size_t bytes);
+// fm_kernels.cu
+void fm_destroy(vrf_handle *h);
 }  // namespace vrf

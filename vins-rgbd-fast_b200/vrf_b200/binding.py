@@ -8,7 +8,7 @@ import os
 import numpy as np
 
 _PKG = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-LIB_PATH = os.path.join(_PKG, "libvrf.so")
+LIB_PATH = os.environ.get("VRF_LIB_PATH") or os.path.join(_PKG, "libvrf.so")      # override: A/B builds of the same CUDA library
 
 TRACK_CAP = 1024
 NUM_FRAMES = 11
@@ -99,7 +99,52 @@ class VrfBaResult(C.Structure):
     ]
 
 
-# every symbol include/vrf.h + include/vrf_ba.h declare
+class VrfFmProblem(C.Structure):
+    """include/vrf_fm.h"""
+    _fields_ = [
+        ("Ps", (C.c_double * 3) * NUM_FRAMES), ("Rs", (C.c_double * 9) * NUM_FRAMES),
+        ("tic", C.c_double * 3), ("ric", C.c_double * 9),
+        ("n_landmarks", C.c_int32), ("n_obs", C.c_int32),
+        ("lm_start_frame", C.c_void_p), ("lm_obs_ptr", C.c_void_p), ("obs_pts", C.c_void_p), ("obs_depth", C.c_void_p),
+        ("estimated_depth", C.c_void_p), ("estimate_flag", C.c_void_p), ("is_dynamic", C.c_void_p), ("remove", C.c_void_p),
+    ]
+
+
+class VrfImuSegment(C.Structure):
+    _fields_ = [
+        ("acc_0", C.c_double * 3), ("gyr_0", C.c_double * 3), ("linearized_ba", C.c_double * 3), ("linearized_bg", C.c_double * 3),
+        ("n_samples", C.c_int32), ("reserved", C.c_int32),
+        ("dt", C.c_void_p), ("acc", C.c_void_p), ("gyr", C.c_void_p),
+    ]
+
+
+class FmProblem:
+    """Owns the numpy buffers a VrfFmProblem points to (one sequence's f_manager.feature list + window states)."""
+
+    def __init__(self, Ps, Rs, tic, ric, start, obs_ptr, obs_pts, obs_depth, est_depth, est_flag=None, is_dynamic=None):
+        self.start = np.ascontiguousarray(start, np.int32)
+        self.obs_ptr = np.ascontiguousarray(obs_ptr, np.int32)
+        self.obs_pts = np.ascontiguousarray(obs_pts, np.float64).reshape(-1, 2)
+        self.obs_depth = np.ascontiguousarray(obs_depth, np.float64)
+        M = len(self.start)
+        self.est_depth = np.ascontiguousarray(est_depth, np.float64).copy()
+        self.est_flag = np.zeros(M, np.int32) if est_flag is None else np.ascontiguousarray(est_flag, np.int32).copy()
+        self.is_dynamic = np.zeros(M, np.uint8) if is_dynamic is None else np.ascontiguousarray(is_dynamic, np.uint8).copy()
+        self.remove = np.zeros(M, np.uint8)
+        self.Ps = np.ascontiguousarray(Ps, np.float64).reshape(NUM_FRAMES, 3)
+        self.Rs = np.ascontiguousarray(Rs, np.float64).reshape(NUM_FRAMES, 3, 3)
+        self.tic = np.ascontiguousarray(tic, np.float64); self.ric = np.ascontiguousarray(ric, np.float64).reshape(3, 3)
+        c = self.c = VrfFmProblem()
+        C.memmove(c.Ps, self.Ps.ctypes.data, 8 * 3 * NUM_FRAMES); C.memmove(c.Rs, self.Rs.ctypes.data, 8 * 9 * NUM_FRAMES)
+        C.memmove(c.tic, self.tic.ctypes.data, 24); C.memmove(c.ric, self.ric.ctypes.data, 72)
+        c.n_landmarks, c.n_obs = M, len(self.obs_depth)
+        c.lm_start_frame, c.lm_obs_ptr = self.start.ctypes.data, self.obs_ptr.ctypes.data
+        c.obs_pts, c.obs_depth = self.obs_pts.ctypes.data, self.obs_depth.ctypes.data
+        c.estimated_depth, c.estimate_flag = self.est_depth.ctypes.data, self.est_flag.ctypes.data
+        c.is_dynamic, c.remove = self.is_dynamic.ctypes.data, self.remove.ctypes.data
+
+
+# every symbol include/vrf.h + include/vrf_ba.h + include/vrf_fm.h declare
 EXPORTS = [
     "vrf_config_default", "vrf_create", "vrf_destroy", "vrf_strerror", "vrf_last_cuda_error",
     "vrf_launch_count", "vrf_reset_sequence", "vrf_tracker_read_image", "vrf_tracker_read_image_batch",
@@ -107,6 +152,7 @@ EXPORTS = [
     "vrf_tracker_enqueue_batch_dev", "vrf_tracker_fetch_batch", "vrf_synchronize", "vrf_stream",
     "vrf_profile_enable", "vrf_profile_read", "vrf_debug_sort_desc", "vrf_debug_read", "vrf_ba_solve", "vrf_ba_solve_batch", "vrf_ba_upload_batch",
     "vrf_ba_enqueue_batch", "vrf_ba_download_batch", "vrf_ba_submit_batch", "vrf_ba_collect_batch",
+    "vrf_fm_triangulate_with_depth_batch", "vrf_fm_moving_consistency_check_batch", "vrf_imu_preintegrate_batch",
 ]
 
 _lib = None
@@ -161,6 +207,9 @@ def load():
     lib.vrf_ba_upload_batch.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.POINTER(VrfBaProblem)]
     lib.vrf_ba_enqueue_batch.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
     lib.vrf_ba_download_batch.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.POINTER(VrfBaResult)]
+    lib.vrf_fm_triangulate_with_depth_batch.argtypes = [C.c_void_p, C.c_int, C.POINTER(VrfFmProblem)]
+    lib.vrf_fm_moving_consistency_check_batch.argtypes = [C.c_void_p, C.c_int, C.POINTER(VrfFmProblem)]
+    lib.vrf_imu_preintegrate_batch.argtypes = [C.c_void_p, C.c_int, C.POINTER(VrfImuSegment), C.POINTER(VrfImuPreint)]
     _lib = lib
     return lib
 
@@ -399,6 +448,38 @@ class Handle:
     def ba_download(self, seqs):
         seq_a = np.asarray(seqs, np.int32)
         check(self.lib.vrf_ba_download_batch(self.h, len(seqs), seq_a.ctypes.data, None), self.h)
+
+    # ---- steps either side of optimization() (include/vrf_fm.h) ----
+    def _fm_call(self, fn, problems):
+        arr = (VrfFmProblem * len(problems))()
+        for i, pb in enumerate(problems):
+            C.memmove(C.byref(arr[i]), C.byref(pb.c), C.sizeof(VrfFmProblem))
+        check(fn(self.h, len(problems), arr), self.h, allow_soft=False)
+
+    def fm_triangulate_with_depth(self, problems):
+        """FeatureManager::triangulateWithDepth on a list of FmProblem (results land in .est_depth / .est_flag)."""
+        self._fm_call(self.lib.vrf_fm_triangulate_with_depth_batch, problems)
+
+    def fm_moving_consistency_check(self, problems):
+        """Estimator::movingConsistencyCheck (results in .is_dynamic / .remove)."""
+        self._fm_call(self.lib.vrf_fm_moving_consistency_check_batch, problems)
+
+    def imu_preintegrate(self, segments):
+        """segments: list of (acc0, gyr0, ba, bg, dt[n], acc[n,3], gyr[n,3]).  Returns a ctypes array of VrfImuPreint."""
+        n = len(segments)
+        segs = (VrfImuSegment * n)()
+        keep = []
+        for i, (a0, g0, ba, bg, dt, acc, gyr) in enumerate(segments):
+            dt = np.ascontiguousarray(dt, np.float64); acc = np.ascontiguousarray(acc, np.float64).reshape(-1, 3)
+            gyr = np.ascontiguousarray(gyr, np.float64).reshape(-1, 3)
+            keep += [dt, acc, gyr]
+            for k in range(3):
+                segs[i].acc_0[k], segs[i].gyr_0[k], segs[i].linearized_ba[k], segs[i].linearized_bg[k] = a0[k], g0[k], ba[k], bg[k]
+            segs[i].n_samples = len(dt)
+            segs[i].dt, segs[i].acc, segs[i].gyr = dt.ctypes.data, acc.ctypes.data, gyr.ctypes.data
+        out = (VrfImuPreint * n)()
+        check(self.lib.vrf_imu_preintegrate_batch(self.h, n, segs, out), self.h, allow_soft=False)
+        return out
 
     # ---- preallocated batch calls (no per-call python allocations; used by bench.py's e2e arm) ----
     def make_track_batch(self, n, debug=False):
