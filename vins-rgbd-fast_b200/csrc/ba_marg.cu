@@ -150,6 +150,10 @@ __device__ __forceinline__ double2 jac_angle(const double *A, int ld, int2 pq)
 }
 
 #define JAC_ANGLE_THREADS 64       /* warps 0-1 compute the next round's angles while the others rotate V */
+// (Also measured and rejected: 256 threads per window with a < 113 KB frame, i.e. two windows or a window plus a
+// front-end CTA per SM.  The Jacobi phase took the same 2.5 M cycles with half the threads -- it is bound by dependent
+// shared-memory latency -- but the whole step got 7 % slower: SMs shared with front-end CTAs never drain, which starves
+// the solve kernel that needs a whole SM.)
 // (A table of the round-robin pairs in shared memory was tried and measured 7 % SLOWER: a round is bound by the
 // latency of its dependent shared-memory accesses, not by instruction issue, and the lookup lengthens that chain.)
 __device__ __noinline__ void jacobi_eig_smem(double *A, double *VT, int n, MargShared &sh)

@@ -7,7 +7,7 @@
 #define VRF_CALL_SLOTS 32
 #define VRF_COPY_CHUNKS 8
 #define VRF_PIPE_DEPTH 2        // host-frame batches in flight (submit / collect)
-#define VRF_COPY_STREAMS 2      // H2D copies alternate over two streams to keep the copy engines busy
+#define VRF_COPY_STREAMS 4      // H2D copies rotate over four streams (measured on B200, 444 frames/step: 31.8k -> 36.6k frames/s e2e vs two)
 
 namespace vrf {
 struct BaState;   // ba_host.cu
