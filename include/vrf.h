@@ -72,7 +72,8 @@ typedef struct VrfConfig {
     int32_t min_dist;                 /* MIN_DIST */
     int32_t num_grid_rows, num_grid_cols;
     int32_t use_imu;                  /* USE_IMU: IMU-predicted LK, maxLevel 1 (else maxLevel 3) */
-    int32_t equalize;                 /* EQUALIZE: must be 0 (CLAHE not on the benchmark path) */
+    int32_t equalize;                 /* EQUALIZE: cv::createCLAHE(3.0, Size(8,8)) on every incoming frame (feature_tracker.cpp:269-275);
+                                         needs ROW and COL to be multiples of 8, else VRF_ERR_UNSUPPORTED */
     int32_t fisheye;                  /* FISHEYE: must be 0 */
     int32_t lk_max_level;             /* -1 = reference default; else explicit maxLevel (0..3) */
     int32_t use_ransac;               /* 1 = rejectWithF enabled (reference behaviour) */

@@ -96,6 +96,7 @@ class FrontendConfig:
     p2: float = 1e-3
     lk_max_level: int = -1          # -1 => reference default (1 with IMU, 3 without)
     use_ransac: int = 1             # 0 skips rejectWithF (kernel bring-up only)
+    equalize: int = 0               # EQUALIZE: CLAHE on every incoming frame (feature_tracker.cpp:269-275)
 
 
 class PinholeCamera:
@@ -346,6 +347,8 @@ class FeatureTrackerRef:
             relative_R = np.eye(3)
         self.cur_time = cur_time
         img = np.ascontiguousarray(img)
+        if c.equalize:                                      # feature_tracker.cpp:269-275 (the real cv::CLAHE)
+            img = cv2.createCLAHE(3.0, (8, 8)).apply(img)
         if self.forw_img is None:
             self.cur_img = self.forw_img = img
         else:

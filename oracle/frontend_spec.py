@@ -317,3 +317,46 @@ def fast_detect(roi, threshold=10, mask=None):
 def circle_covers(cx, cy, r, x, y):
     """True iff cv::circle(mask,(cx,cy),r,0,-1) zeroes pixel (x,y)."""
     return (x - cx) * (x - cx) + (y - cy) * (y - cy) <= r * r
+
+
+def clahe(img, clip=3.0, tiles=8):
+    """cv::createCLAHE(clip, Size(tiles, tiles))->apply(img) for frame sizes that are multiples of the tile grid
+    (OpenCV imgproc/clahe.cpp: CLAHE_CalcLut_Body + CLAHE_Interpolation_Body; call site feature_tracker.cpp:269-275).
+    Pinned bit-exactly against cv2 4.13 in tests/test_oracle_frontend.py."""
+    h, w = img.shape
+    assert h % tiles == 0 and w % tiles == 0
+    th, tw = h // tiles, w // tiles
+    tot = th * tw
+    lut_scale = np.float32(255.0) / np.float32(tot)
+    cl = max(int(clip * tot / 256), 1)
+    luts = np.zeros((tiles, tiles, 256), np.uint8)
+    for ty in range(tiles):
+        for tx in range(tiles):
+            hist = np.bincount(img[ty * th:(ty + 1) * th, tx * tw:(tx + 1) * tw].ravel(), minlength=256).astype(np.int64)
+            clipped = int(np.maximum(hist - cl, 0).sum())
+            hist = np.minimum(hist, cl)
+            batch = clipped // 256
+            resid = clipped - batch * 256
+            hist += batch
+            if resid != 0:
+                step = max(256 // resid, 1)
+                i = 0
+                while i < 256 and resid > 0:
+                    hist[i] += 1; i += step; resid -= 1
+            s = np.cumsum(hist).astype(np.float32) * lut_scale
+            luts[ty, tx] = np.clip(np.rint(s), 0, 255).astype(np.uint8)
+    one, half = np.float32(1), np.float32(0.5)
+    inv_tw, inv_th = one / np.float32(tw), one / np.float32(th)
+    txf = np.arange(w, dtype=np.float32) * inv_tw - half
+    tyf = np.arange(h, dtype=np.float32) * inv_th - half
+    tx1 = np.floor(txf).astype(np.int32); ty1 = np.floor(tyf).astype(np.int32)
+    xa = (txf - tx1.astype(np.float32)).astype(np.float32); ya = (tyf - ty1.astype(np.float32)).astype(np.float32)
+    xa1, ya1 = one - xa, one - ya
+    tx2 = np.minimum(tx1 + 1, tiles - 1); tx1 = np.maximum(tx1, 0)
+    ty2 = np.minimum(ty1 + 1, tiles - 1); ty1 = np.maximum(ty1, 0)
+    v = img.astype(np.int64)
+    Y1, Y2, X1, X2 = ty1[:, None], ty2[:, None], tx1[None, :], tx2[None, :]
+    a = luts[Y1, X1, v].astype(np.float32); b = luts[Y1, X2, v].astype(np.float32)
+    c = luts[Y2, X1, v].astype(np.float32); d = luts[Y2, X2, v].astype(np.float32)
+    res = (a * xa1[None, :] + b * xa[None, :]) * ya1[:, None] + (c * xa1[None, :] + d * xa[None, :]) * ya[:, None]
+    return np.clip(np.rint(res), 0, 255).astype(np.uint8)

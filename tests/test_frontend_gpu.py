@@ -100,6 +100,24 @@ def test_sequence_parity_no_imu_four_levels():
         check_frame(k, out, ref)
 
 
+def test_sequence_parity_with_clahe():
+    """EQUALIZE = 1: cv::createCLAHE(3.0, Size(8, 8)) on every frame before tracking/detection; a dim, low-contrast
+    sequence (the case the option exists for), IDs / occupancy bit-exact, tracks within 1e-3 px."""
+    cam = synth.CamModel()
+    seq = synth.Sequence(2718, cam)
+    cfg = binding.default_config(use_ransac=1, equalize=1)
+    h = binding.Handle(cfg, 1, 0)
+    ref = FeatureTrackerRef(FrontendConfig(use_ransac=1, equalize=1))
+    for k in range(9):
+        gray = (seq.frame(k)[1].astype(np.float32) * 0.35 + 15).astype(np.uint8)
+        R = seq.relative_R(k)
+        out = h.read_image(0, gray, seq.time(k), R, pub=(k % 3 == 0))
+        ref.read_image(gray, seq.time(k), R, pub_this_frame=(k % 3 == 0))
+        check_frame(k, out, ref)
+    assert out.n > 60
+    h.close()
+
+
 def test_rgb_ingest_equals_gray_path():
     """RGB8 payload: device-side cvtColor(RGB2GRAY) then the same pipeline."""
     for k, out, ref in run_pair({}, 5, 31, rgb=True):

@@ -60,6 +60,18 @@ def test_fast_bit_exact(rect):
         assert got == S.fast_detect(roi, mask=m)
 
 
+@pytest.mark.parametrize("shape,seed", [((480, 640), 1), ((240, 320), 2), ((720, 1280), 3), ((480, 640), 4), ((64, 64), 5)])
+def test_clahe_bit_exact(shape, seed):
+    """EQUALIZE: the numpy spec of cv::createCLAHE(3.0, Size(8, 8)) equals the real OpenCV, incl. a dark low-contrast frame
+    (heavy clipping + residual redistribution) and a frame of constant blocks."""
+    img = tex(*shape, seed=seed)
+    if seed == 4:
+        img = (img.astype(np.float32) * 0.3 + 20).astype(np.uint8)
+    if seed == 5:
+        img = np.kron(np.random.default_rng(5).integers(0, 256, (8, 8)), np.ones((8, 8))).astype(np.uint8)
+    assert np.array_equal(S.clahe(img), cv2.createCLAHE(3.0, (8, 8)).apply(img))
+
+
 def test_fast_flat_and_tiny():
     assert S.fast_detect(np.full((40, 40), 128, np.uint8)) == []
     assert S.fast_detect(np.zeros((6, 6), np.uint8)) == []

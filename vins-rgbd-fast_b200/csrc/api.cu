@@ -79,7 +79,9 @@ static int build_front_cfg(const VrfConfig &cfg, FrontCfg &fc)
 {
     memset(&fc, 0, sizeof(fc));
     if (cfg.row < 64 || cfg.col < 64 || (cfg.col & 15)) return VRF_ERR_ARG;   // uint4 row access
-    if (cfg.equalize || cfg.fisheye) return VRF_ERR_UNSUPPORTED;
+    if (cfg.fisheye) return VRF_ERR_UNSUPPORTED;
+    // CLAHE: OpenCV pads frames whose size is not a multiple of the 8x8 tile grid; that variant is not built
+    if (cfg.equalize && ((cfg.row & 7) || (cfg.col & 7))) return VRF_ERR_UNSUPPORTED;
     if (cfg.max_cnt <= 0 || cfg.max_cnt > VRF_CAP / 2 || cfg.min_dist < 1) return VRF_ERR_ARG;
     fc.rows = cfg.row; fc.cols = cfg.col;
     int maxLevel = cfg.lk_max_level < 0 ? (cfg.use_imu ? 1 : 3) : cfg.lk_max_level;
@@ -116,6 +118,7 @@ static int build_front_cfg(const VrfConfig &cfg, FrontCfg &fc)
     fc.nodist = (cfg.k1 == 0.0 && cfg.k2 == 0.0 && cfg.p1 == 0.0 && cfg.p2 == 0.0);
     fc.focal = cfg.focal_length; fc.f_thr = cfg.f_threshold;
     fc.depth_min_dist = cfg.depth_min_dist;
+    fc.equalize = cfg.equalize ? 1 : 0;
     return VRF_OK;
 }
 
@@ -166,6 +169,7 @@ extern "C" int vrf_create(const VrfConfig *cfg, int n_seq, int device, vrf_handl
     A(d.o_pts, SW); A(d.o_un, SW); A(d.o_vel, SW); A(d.o_ids, SW); A(d.o_cnt, SW); A(d.out_hdr, S * 8);
     A(d.o_depth, SW); A(d.o_dkeep, SW);
     A(d.work_prefix, VRF_MAX_BATCH + 1);
+    if (fc.equalize) { A(d.clahe_lut, S * 64 * 256); }
     for (int k = 0; k < VRF_CALL_SLOTS; ++k) { A(h->d_calls_ring[k], S); }
     h->frame_bytes_max = (size_t)cfg->row * cfg->col * 3;
 #undef A
@@ -201,7 +205,7 @@ extern "C" void vrf_destroy(vrf_handle *h)
                     d.lk_status, d.n_lk, d.t_prev, d.t_forw, d.t_prevun, d.t_ids, d.t_cnt, d.t_n, d.t_keep,
                     d.unstable, d.n_unstable, d.maskpts, d.n_maskpts, d.grid_cnt, d.tex_status, d.cell_k, d.cand,
                     d.ncand, d.o_pts, d.o_un, d.o_vel, d.o_ids, d.o_cnt, d.out_hdr, d.work_prefix,
-                    d.o_depth, d.o_dkeep, h->d_stage[0], h->d_stage[1], h->d_stage_depth[0], h->d_stage_depth[1]};
+                    d.o_depth, d.o_dkeep, d.clahe_lut, h->d_stage[0], h->d_stage[1], h->d_stage_depth[0], h->d_stage_depth[1]};
     static_assert(VRF_PIPE_DEPTH == 2, "staging slots listed explicitly above");
     for (void *p : ptrs) if (p) cudaFree(p);
     for (int k = 0; k < VRF_CALL_SLOTS; ++k) {

@@ -31,6 +31,7 @@ struct FrontCfg {
     double focal, f_thr;
     double depth_min_dist;
     int nodist;
+    int equalize;               // EQUALIZE: cv::createCLAHE(3.0, Size(8, 8)) on the incoming frame (feature_tracker.cpp:269-275)
 };
 
 // One batch item of a tracker call.
@@ -77,6 +78,7 @@ struct FrontDev {
     uint8_t *o_dkeep;           // 0: erased by the DEPTH_MIN_DIST test of addFeatureCheckParallax
     int *out_hdr;               // [batch][8]: n, n_id, n_predict, n_unstable, status
     int *work_prefix;           // [MAX_BATCH+1] prefix of LK work items for the current call
+    uint8_t *clahe_lut;         // [S][64][256] per-tile CLAHE look-up tables (EQUALIZE only)
 };
 
 __device__ __forceinline__ int reflect101(int i, int n)

@@ -92,6 +92,119 @@ k_ingest(FrontCfg c, const SeqCall *calls, int ncalls, FrontDev d, const uint8_t
 }
 
 // ---------------------------------------------------------------------------
+// EQUALIZE: cv::createCLAHE(3.0, Size(8, 8))->apply(img) (feature_tracker.cpp:269-275; OpenCV imgproc/clahe.cpp,
+// restated bit-exactly in oracle/frontend_spec.py::clahe and pinned against cv2 there).  Frame sizes are
+// multiples of the 8x8 tile grid (enforced at create), so no border padding is involved.
+//   k_clahe_lut   one CTA per (tile, frame): 256-bin histogram in shared memory, clip at
+//                 int(3.0 * tile_pixels / 256), uniform redistribution + the strided residual, prefix sum,
+//                 lut[i] = cvRound(float(sum_i) * (255.f / tile_pixels)).
+//   k_clahe_apply per pixel: bilinear blend of the four neighbouring tiles' LUT entries in OpenCV's float32
+//                 operation order, in place on pyramid level 0 (reads and writes the same byte only).
+// Both are pure image scans: WH bytes read (+ WH written by the second) per frame.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_clahe_lut(FrontCfg c, const SeqCall *calls, FrontDev d)
+{
+    __shared__ int s_hist[256];
+    __shared__ int s_scan[256];
+    __shared__ int s_warp[8];
+    const int t = threadIdx.x;
+    const SeqCall call = calls[blockIdx.y];
+    const uint8_t *img = d.pyr[call.buf_cur] + (size_t)call.seq * c.pyr_bytes;
+    const int th = c.rows >> 3, tw = c.cols >> 3, pitch = c.lp[0];
+    const int ty = blockIdx.x >> 3, tx = blockIdx.x & 7;
+    const uint8_t *tile = img + (size_t)(ty * th) * pitch + tx * tw;
+    s_hist[t] = 0;
+    __syncthreads();
+    if ((tw & 3) == 0) {
+        const int wpr = tw >> 2;
+        for (int i = t; i < th * wpr; i += 256) {
+            const int y = i / wpr, xw = i - y * wpr;
+            const unsigned v = __ldg(reinterpret_cast<const unsigned *>(tile + (size_t)y * pitch) + xw);
+            atomicAdd(&s_hist[v & 255u], 1); atomicAdd(&s_hist[(v >> 8) & 255u], 1);
+            atomicAdd(&s_hist[(v >> 16) & 255u], 1); atomicAdd(&s_hist[v >> 24], 1);
+        }
+    } else {
+        for (int i = t; i < th * tw; i += 256) {
+            const int y = i / tw, x = i - y * tw;
+            atomicAdd(&s_hist[__ldg(tile + (size_t)y * pitch + x)], 1);
+        }
+    }
+    __syncthreads();
+    const int total = th * tw;
+    int clip = (int)(3.0 * total / 256);
+    if (clip < 1) clip = 1;
+    int v = s_hist[t];
+    int excess = v > clip ? v - clip : 0;
+    v = v > clip ? clip : v;
+    // clipped = sum of the excess over the 256 bins
+    for (int o = 16; o > 0; o >>= 1) excess += __shfl_xor_sync(0xffffffffu, excess, o);
+    if ((t & 31) == 0) s_warp[t >> 5] = excess;
+    __syncthreads();
+    int clipped = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) clipped += s_warp[i];
+    const int batch = clipped / 256, resid = clipped - batch * 256;
+    v += batch;
+    if (resid != 0) {
+        const int step = 256 / resid > 1 ? 256 / resid : 1;
+        if (t % step == 0 && t / step < resid) ++v;
+    }
+    // inclusive prefix sum over the bins
+    s_scan[t] = v;
+    __syncthreads();
+    for (int o = 1; o < 256; o <<= 1) {
+        const int add = t >= o ? s_scan[t - o] : 0;
+        __syncthreads();
+        s_scan[t] += add;
+        __syncthreads();
+    }
+    const float lut_scale = 255.0f / (float)total;
+    int q = __float2int_rn((float)s_scan[t] * lut_scale);
+    q = q < 0 ? 0 : (q > 255 ? 255 : q);
+    d.clahe_lut[((size_t)call.seq * 64 + blockIdx.x) * 256 + t] = (uint8_t)q;
+}
+
+__global__ void __launch_bounds__(256)
+k_clahe_apply(FrontCfg c, const SeqCall *calls, FrontDev d)
+{
+    const SeqCall call = calls[blockIdx.y];
+    uint8_t *img = d.pyr[call.buf_cur] + (size_t)call.seq * c.pyr_bytes;
+    const uint8_t *lut = d.clahe_lut + (size_t)call.seq * 64 * 256;
+    const int th = c.rows >> 3, tw = c.cols >> 3, pitch = c.lp[0];
+    const float inv_tw = 1.0f / (float)tw, inv_th = 1.0f / (float)th;
+    const int wpr = c.cols >> 2;                            // 4 pixels per thread
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < c.rows * wpr; i += gridDim.x * blockDim.x) {
+        const int y = i / wpr, x0 = (i - y * wpr) << 2;
+        const float tyf = (float)y * inv_th - 0.5f;
+        int ty1 = (int)floorf(tyf);
+        const float ya = tyf - (float)ty1, ya1 = 1.0f - ya;
+        int ty2 = ty1 + 1;
+        ty1 = ty1 < 0 ? 0 : ty1; ty2 = ty2 > 7 ? 7 : ty2;
+        const uint8_t *l1 = lut + ty1 * 8 * 256, *l2 = lut + ty2 * 8 * 256;
+        unsigned *p = reinterpret_cast<unsigned *>(img + (size_t)y * pitch + x0);
+        const unsigned w = *p;
+        unsigned out = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int sv = (w >> (8 * k)) & 255u;
+            const float txf = (float)(x0 + k) * inv_tw - 0.5f;
+            int tx1 = (int)floorf(txf);
+            const float xa = txf - (float)tx1, xa1 = 1.0f - xa;
+            int tx2 = tx1 + 1;
+            tx1 = tx1 < 0 ? 0 : tx1; tx2 = tx2 > 7 ? 7 : tx2;
+            const float a = (float)l1[tx1 * 256 + sv], b = (float)l1[tx2 * 256 + sv];
+            const float cc = (float)l2[tx1 * 256 + sv], dd = (float)l2[tx2 * 256 + sv];
+            const float res = (a * xa1 + b * xa) * ya1 + (cc * xa1 + dd * xa) * ya;
+            int q = __float2int_rn(res);
+            q = q < 0 ? 0 : (q > 255 ? 255 : q);
+            out |= (unsigned)q << (8 * k);
+        }
+        *p = out;
+    }
+}
+
+// ---------------------------------------------------------------------------
 // k_pyrdown: cv::pyrDown (5x5 separable [1 4 6 4 1], (sum+128)>>8, REFLECT_101).
 // CTA tile = 64 x 32 outputs.  A thread owns 8 adjacent outputs of a row: the
 // horizontal pass reads their 20 source bytes as one 16-byte word plus two
@@ -1116,6 +1229,16 @@ int front_launch(const FrontCfg &c, const SeqCall *d_calls, int ncalls, const Fr
     lc.begin(K_INGEST);
     k_ingest<<<gi, 256, 0, st>>>(c, d_calls, ncalls, d, d_frames, frame_bytes, fmt);
     lc.end();
+    if (c.equalize) {
+        lc.begin(K_CLAHE_LUT);
+        k_clahe_lut<<<dim3(64, ncalls), 256, 0, st>>>(c, d_calls, d);
+        lc.end();
+        dim3 ga((c.rows * (c.cols >> 2) + 255) / 256, ncalls);
+        if (ga.x > 64) ga.x = 64;
+        lc.begin(K_CLAHE_APPLY);
+        k_clahe_apply<<<ga, 256, 0, st>>>(c, d_calls, d);
+        lc.end();
+    }
     for (int l = 0; l + 1 < c.levels; ++l) {
         dim3 g((c.lw[l + 1] + PD_TW - 1) / PD_TW, (c.lh[l + 1] + PD_TH - 1) / PD_TH, ncalls);
         lc.begin(K_PYRDOWN);
