@@ -93,6 +93,35 @@ def test_device_resident_prior_chain():
     h.close()
 
 
+def test_information_form_prior_chain_without_decomposition():
+    """Throughput path: new_prior = NULL, so the marginalization kernel leaves the prior on the device in information
+    form (A', b', c0) and no eigen-decomposition runs.  The chain must track the oracle chain (which uses the
+    reference's factor form sqrt(S) V^T) like the factor-form chain does, and the first window -- identical inputs --
+    must agree to solver precision incl. the cost constant."""
+    cfg = make_cfg()
+    h = B.Handle(cfg, 1, 0)
+    sim_o = BP.WindowSimulator(9, cfg, n_landmarks=120)
+    sim_g = BP.WindowSimulator(9, cfg, n_landmarks=120)
+    for a in range(5):
+        pbo = sim_o.window(a)
+        so = ba_ref.solve(cfg, pbo)
+        sim_o.commit(a, so)
+        pbg = sim_g.window(a)
+        if a > 0:
+            pbg.c.prior = C.cast(C.c_void_p(1), C.POINTER(B.VrfPrior))      # VRF_PRIOR_DEVICE
+        l0 = h.launches
+        sg = h.ba_solve(0, pbg, want_prior=False)
+        assert h.launches - l0 == 2                                         # solve + marginalization, no factor kernel
+        sim_g.commit(a, sg)
+        assert sg.c.has_new_prior == 1
+        assert (sg.c.iterations, sg.c.successful_steps) == (so.c.iterations, so.c.successful_steps) or a > 1
+        assert np.abs(sg.Ps - so.Ps).max() <= (1e-7 if a == 0 else 1e-5)
+        assert abs(sg.c.final_cost - so.c.final_cost) <= (1e-7 if a == 0 else 1e-4) * so.c.final_cost
+        if a == 1:      # same prior content as the oracle's (to rounding): the cost constant c0 must match 1/2 r0^T r0
+            assert abs(sg.c.initial_cost - so.c.initial_cost) <= 1e-6 * so.c.initial_cost
+    h.close()
+
+
 def test_margin_second_new_and_batch():
     """Batch of 3 sequences; the third marginalises the second-newest frame (prior only)."""
     cfg = make_cfg()

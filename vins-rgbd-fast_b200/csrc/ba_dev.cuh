@@ -30,10 +30,16 @@ struct BaMeta {
 };
 
 // prior as stored on device (MarginalizationInfo: marginalization_factor.h:62-74); produced by
-// k_ba_marg or uploaded from a host VrfPrior.  J0 has leading dimension n.
+// k_ba_marg or uploaded from a host VrfPrior.  Two forms of the same quadratic 1/2 |r0 + J0 dx|^2:
+//   form 0 (factor, what the reference stores): J0 = linearized_jacobians (n x n), r0 = linearized_residuals
+//   form 1 (information):                       J0 := J0^T J0 (symmetric), r0 := J0^T r0, c0 = 1/2 r0^T r0
+// The kernels evaluate the prior in information form (cost = c0 + dx.(g + H dx / 2), gradient = g + H dx): k_ba_marg
+// writes form 1 directly (no eigen-decomposition on the throughput path), k_ba_solve converts an uploaded form-0 prior
+// in place, and k_ba_prior_factor produces the reference's factor form on demand (host copy-out of new_prior).
 struct BaPriorStore {
-    int n, n_blocks, valid, pad;
+    int n, n_blocks, valid, form;
     int kind[VRF_PRIOR_MAX_BLOCKS], index[VRF_PRIOR_MAX_BLOCKS], size[VRF_PRIOR_MAX_BLOCKS], idx[VRF_PRIOR_MAX_BLOCKS];
+    double c0;
     double x0[VRF_PRIOR_MAX_BLOCKS * 9];
     double r0[VRF_PRIOR_MAX_DIM];
     double J0[VRF_PRIOR_MAX_DIM * VRF_PRIOR_MAX_DIM];
@@ -89,5 +95,7 @@ struct BaMargDev {
 size_t ba_solve_smem_bytes();
 int ba_solve_launch(const BaMeta *d_meta, const BaProbDev *d_prob, BaOutDev *d_out, int n, LaunchCtx &lc);
 int ba_marg_launch(const BaMeta *d_meta, const BaProbDev *d_prob, BaOutDev *d_out, BaMargDev *d_marg, int n, LaunchCtx &lc);
+// factor form (J0, r0) of an information-form prior, on demand; scratch: 2 * VRF_PRIOR_MAX_DIM^2 doubles
+int ba_prior_factor_launch(const BaPriorStore *src, BaPriorStore *dst, double *scratch, LaunchCtx &lc);
 
 }  // namespace vrf

@@ -50,6 +50,8 @@ struct BaState {
     unsigned n_submit = 0, n_collect = 0;
     BaPriorStore *d_prior[2] = {nullptr, nullptr};   // [n_seq] each; cur index per sequence below
     BaPriorStore *h_prior_dl = nullptr;              // pinned download staging [1]
+    BaPriorStore *d_prior_factor = nullptr;          // [1] factor form produced on demand for the host copy-out
+    double *d_factor_scratch = nullptr;              // [2 * VRF_PRIOR_MAX_DIM^2]
     std::vector<int> prior_cur;                      // which store is "last_marginalization_info"
     std::vector<uint8_t> prior_valid;
     // per-sequence scratch
@@ -105,6 +107,8 @@ int ba_create(vrf_handle *h)
         BCK(cudaMemset(b->d_prior[k], 0, S * sizeof(BaPriorStore)));
     }
     BCK(cudaMallocHost((void **)&b->h_prior_dl, sizeof(BaPriorStore)));
+    BCK(cudaMalloc((void **)&b->d_prior_factor, sizeof(BaPriorStore)));
+    BCK(cudaMalloc((void **)&b->d_factor_scratch, 2 * (size_t)VRF_PRIOR_MAX_DIM * VRF_PRIOR_MAX_DIM * sizeof(double)));
     BCK(cudaMalloc((void **)&b->d_lam, S * BA_MAX_LM * sizeof(double)));
     BCK(cudaMalloc((void **)&b->d_clam, S * BA_MAX_LM * sizeof(double)));
     BCK(cudaMalloc((void **)&b->d_W, S * BA_MAX_LM * BA_WS * sizeof(double)));
@@ -124,7 +128,7 @@ void ba_destroy(vrf_handle *h)
 {
     BaState *b = h->ba;
     if (!b) return;
-    void *dev[] = {b->d_prior[0], b->d_prior[1], b->d_lam, b->d_clam,
+    void *dev[] = {b->d_prior[0], b->d_prior[1], b->d_prior_factor, b->d_factor_scratch, b->d_lam, b->d_clam,
                    b->d_W, b->d_vecs, b->d_imuS, b->d_HP, b->d_colmap, b->d_margbuf, b->d_lmcol};
     for (void *p : dev) if (p) cudaFree(p);
     if (b->h_prior_dl) cudaFreeHost(b->h_prior_dl);
@@ -210,7 +214,7 @@ static int pack_problem(vrf_handle *h, BaSlot &sl, int slot, int seq, const VrfB
         const VrfPrior *P = pb->prior;
         if (P->n < 0 || P->n > VRF_PRIOR_MAX_DIM || P->n_blocks > VRF_PRIOR_MAX_BLOCKS) return VRF_ERR_ARG;
         BaPriorStore *hp = sl.h_prior + slot;          // per-problem pinned staging (the slot is idle while it is packed)
-        hp->n = P->n; hp->n_blocks = P->n_blocks; hp->valid = 1; hp->pad = 0;
+        hp->n = P->n; hp->n_blocks = P->n_blocks; hp->valid = 1; hp->form = 0; hp->c0 = 0.0;
         for (int q = 0; q < P->n_blocks; ++q) {
             hp->kind[q] = P->blocks[q].kind; hp->index[q] = P->blocks[q].index; hp->size[q] = P->blocks[q].size; hp->idx[q] = P->blocks[q].idx;
             memcpy(hp->x0 + 9 * q, P->blocks[q].x0, sizeof(double) * 9);
@@ -333,8 +337,15 @@ static int finish_download(vrf_handle *h, BaSlot &sl, int n, const int32_t *seqs
             memcpy(r.para_Feature, sl.h_lam + (size_t)i * BA_MAX_LM, sizeof(double) * b->last_M[seq]);
         if (o.has_new_prior && r.new_prior) {
             // (the store just produced is only read, never written, by the one later batch that may be in flight)
+            // the stored prior is in information form; the reference's (linearized_jacobians, linearized_residuals)
+            // are produced here, on demand, by the eigen-decomposition kernel
             BaPriorStore *hp = b->h_prior_dl;
-            const BaPriorStore *src = b->d_prior[b->prior_cur[seq]] + seq;
+            {
+                LaunchCtx lc{h->stream, &h->launches, &h->prof};
+                if (ba_prior_factor_launch(b->d_prior[b->prior_cur[seq]] + seq, b->d_prior_factor, b->d_factor_scratch, lc) != 0) return VRF_ERR_CUDA;
+                BCK(cudaStreamSynchronize(h->stream));
+            }
+            const BaPriorStore *src = b->d_prior_factor;
             BCK(cudaMemcpy(hp, src, offsetof(BaPriorStore, J0), cudaMemcpyDeviceToHost));
             const int nn = hp->n;
             BCK(cudaMemcpy(hp->J0, src->J0, sizeof(double) * (size_t)nn * nn, cudaMemcpyDeviceToHost));

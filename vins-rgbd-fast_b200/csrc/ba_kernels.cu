@@ -44,6 +44,7 @@ struct BaShared {
     double px0[VRF_PRIOR_MAX_BLOCKS * 9], pr0[VRF_PRIOR_MAX_DIM];
     int pkind[VRF_PRIOR_MAX_BLOCKS], pindex[VRF_PRIOR_MAX_BLOCKS], psize[VRF_PRIOR_MAX_BLOCKS], pidx[VRF_PRIOR_MAX_BLOCKS];
     int pcol[VRF_PRIOR_MAX_DIM], pnb;
+    double pc0;                                       // constant term of the prior (1/2 r0^T r0)
     double imuJ[BA_NF - 1][15 * 30];                 // whitened IMU Jacobians of the current linearisation
     double imur[BA_NF - 1][16];
     double red[BA_THREADS / 32];
@@ -333,13 +334,15 @@ __device__ __noinline__ double ba_evaluate_t(const BaMeta &m, const BaProbDev &p
     __syncthreads();
     EPROF(3);
     EPROF(2);
-    // ---- prior ----
+    // ---- prior (MarginalizationFactor::Evaluate, marginalization_factor.cpp:353-415), in information form:
+    //      1/2 |r0 + J0 dx|^2 = c0 + dx.(gp + HP dx / 2),  J0^T (r0 + J0 dx) = gp + HP dx,  HP = J0^T J0, gp = J0^T r0 ----
     const BaPriorStore *P = p.prior;
     const int np_ = (P && P->valid) ? P->n : 0;
     if (np_ > 0) {
         const int n = np_;
-        // r = r0 + J0 dx: one warp per row, lanes along the row (coalesced).  For the usual sizes (n <= 96) a warp's
-        // row fragments are requested before dx exists, so that the L2 latency overlaps prior_dx.
+        const double *HPm = P->J0;              // information form (see the kernel's set-up)
+        // w = HP dx: one warp per row, lanes along the row (coalesced).  For the usual sizes (n <= 96) a warp's row
+        // fragments are requested before dx exists, so that the L2 latency overlaps prior_dx.
         const bool small = n <= 96;
         double jv[6][3];
         if (small) {
@@ -348,11 +351,12 @@ __device__ __noinline__ double ba_evaluate_t(const BaMeta &m, const BaProbDev &p
 #pragma unroll
                 for (int kk = 0; kk < 3; ++kk) {
                     const int rI = warp + nwarp * q, k = lane + 32 * kk;
-                    jv[q][kk] = (rI < n && k < n) ? __ldg(&P->J0[(size_t)rI * n + k]) : 0.0;
+                    jv[q][kk] = (rI < n && k < n) ? __ldg(&HPm[(size_t)rI * n + k]) : 0.0;
                 }
         }
         prior_dx_smem(sh, pose, sb, ex, td);
         __syncthreads();
+        if (tid == 0) cost += sh.pc0;
         if (small) {
             double dxv[3], a[6];
 #pragma unroll
@@ -366,30 +370,23 @@ __device__ __noinline__ double ba_evaluate_t(const BaMeta &m, const BaProbDev &p
 #pragma unroll
             for (int q = 0; q < 6; ++q) {
                 const int rI = warp + nwarp * q;
-                if (lane == 0 && rI < n) { const double v = a[q] + sh.pr0[rI]; sh.pr[rI] = v; cost += 0.5 * v * v; }
+                if (lane == 0 && rI < n) { sh.pr[rI] = a[q]; cost += sh.dx[rI] * (sh.pr0[rI] + 0.5 * a[q]); }
             }
         } else {
             for (int rI = warp; rI < n; rI += nwarp) {
-                const double *row = P->J0 + (size_t)rI * n;
+                const double *row = HPm + (size_t)rI * n;
                 double a = 0;
                 for (int k = lane; k < n; k += 32) a += row[k] * sh.dx[k];
                 a = warp_sum_d(a);
-                if (lane == 0) { a += sh.pr0[rI]; sh.pr[rI] = a; cost += 0.5 * a * a; }
+                if (lane == 0) { sh.pr[rI] = a; cost += sh.dx[rI] * (sh.pr0[rI] + 0.5 * a); }
             }
         }
         __syncthreads();
         if (lin) {
-            // g += J0^T r (column sums split over thread groups) ; H += J0^T J0 (precomputed HP), both through the column map
-            const int npad = (n + 31) & ~31, ngrp = BA_THREADS / npad;
-            const int a = tid % npad, grp = tid / npad;
-            if (grp < ngrp && a < n) {
+            // g += gp + HP dx ; H += HP, both through the column map (constant blocks drop out)
+            for (int a = tid; a < n; a += BA_THREADS) {
                 const int ca = sh.pcol[a];
-                if (ca >= 0) {
-                    double gsum = 0;
-#pragma unroll 5
-                    for (int rI = grp; rI < n; rI += ngrp) gsum += __ldg(&P->J0[(size_t)rI * n + a]) * sh.pr[rI];
-                    atomicAdd(&sh.g[ca], gsum);
-                }
+                if (ca >= 0) atomicAdd(&sh.g[ca], sh.pr0[a] + sh.pr[a]);
             }
 #pragma unroll 4
             for (int e = tid; e < n * n; e += BA_THREADS) {
@@ -397,7 +394,7 @@ __device__ __noinline__ double ba_evaluate_t(const BaMeta &m, const BaProbDev &p
                 if (b > a2) continue;
                 int ca = sh.pcol[a2], cb = sh.pcol[b];
                 if (ca < 0 || cb < 0) continue;
-                sh.H[pk(ca, cb)] += p.HP[(size_t)a2 * n + b];
+                sh.H[pk(ca, cb)] += __ldg(&HPm[(size_t)a2 * n + b]);
             }
         }
     }
@@ -524,13 +521,32 @@ k_ba_solve(const BaMeta *metas, const BaProbDev *probs, BaOutDev *outs)
         for (int f = warp + nwarp; f < m.nimu; f += nwarp) imu_sqrt_info_warp(p.imu[m.imu_j[f] - 1].covariance, p.imuS + (size_t)(m.imu_j[f] - 1) * 225, scr);
         const BaPriorStore *P = p.prior;
         const int n = (P && P->valid) ? P->n : 0;
-        for (int e = tid; e < n * n; e += BA_THREADS) {
-            int a = e / n, b = e - a * n;
-            if (b > a) continue;
-            double h = 0;
-            for (int rI = 0; rI < n; ++rI) h += P->J0[(size_t)rI * n + a] * P->J0[(size_t)rI * n + b];
-            p.HP[(size_t)a * n + b] = h;
+        if (n > 0 && P->form == 0) {
+            // an uploaded (linearized_jacobians, linearized_residuals) prior: J0 <- J0^T J0, r0 <- J0^T r0, c0 = r0^T r0 / 2,
+            // in place (through the HP scratch); from here on every kernel sees the information form
+            BaPriorStore *Pw = const_cast<BaPriorStore *>(P);
+            for (int e = tid; e < n * n; e += BA_THREADS) {
+                int a = e / n, b = e - a * n;
+                if (b > a) continue;
+                double h = 0;
+                for (int rI = 0; rI < n; ++rI) h += P->J0[(size_t)rI * n + a] * P->J0[(size_t)rI * n + b];
+                p.HP[(size_t)a * n + b] = h; p.HP[(size_t)b * n + a] = h;
+            }
+            double cc = 0;
+            for (int a = tid; a < n; a += BA_THREADS) {
+                double gsum = 0;
+                for (int rI = 0; rI < n; ++rI) gsum += P->J0[(size_t)rI * n + a] * P->r0[rI];
+                sh.pr[a] = gsum;
+                cc += 0.5 * P->r0[a] * P->r0[a];
+            }
+            cc = block_sum(cc, sh.red);              // (barriers inside: every read of J0 / r0 above is complete)
+            for (int e = tid; e < n * n; e += BA_THREADS) Pw->J0[e] = p.HP[e];
+            for (int a = tid; a < n; a += BA_THREADS) Pw->r0[a] = sh.pr[a];
+            if (tid == 0) { Pw->c0 = cc; Pw->form = 1; }
+            __threadfence();
+            __syncthreads();
         }
+        if (tid == 0) sh.pc0 = n > 0 ? P->c0 : 0.0;
         // prior column -> tangent column (constant blocks drop out); block table, x0 and r0 staged in shared memory
         if (tid == 0) sh.pnb = n > 0 ? P->n_blocks : 0;
         if (n > 0) {

@@ -424,18 +424,18 @@ k_ba_marg(const BaMeta *metas, const BaProbDev *probs, BaOutDev *outs, const BaM
     __syncthreads();
 
     MPROF(0);
-    // ---- 2a. prior factor ----
+    // ---- 2a. prior factor, information form (the solve kernel has normalised the store): A += HP, b += gp + HP dx ----
     if (P) {
         const int np = P->n;
-        // residual at the current (gauge-fixed) states
-        prior_dx(P, pose, sb, ex, out.mtd, sh.dx);
+        const double *HPm = P->J0, *gp = P->r0;
+        prior_dx(P, pose, sb, ex, out.mtd, sh.dx);          // at the current (gauge-fixed) states
         __syncthreads();
         for (int rI = warp; rI < np; rI += nwarp) {       // one warp per row, lanes along the row (coalesced)
-            const double *row = P->J0 + (size_t)rI * np;
+            const double *row = HPm + (size_t)rI * np;
             double a = 0;
             for (int k = lane; k < np; k += 32) a += row[k] * sh.dx[k];
             a = warp_sum_d(a);
-            if (lane == 0) sh.pr[rI] = a + P->r0[rI];
+            if (lane == 0) sh.pr[rI] = a + gp[rI];
         }
         // prior column -> A column (reuse p.colmap scratch)
         for (int b = tid; b < P->n_blocks; b += BA_THREADS) {
@@ -444,21 +444,12 @@ k_ba_marg(const BaMeta *metas, const BaProbDev *probs, BaOutDev *outs, const BaM
             for (int c = 0; c < ls; ++c) p.colmap[P->idx[b] + c] = (i >= 0) ? sh.idx[i] + c : -1;
         }
         __syncthreads();
-        {
-            const int npad = (np + 31) & ~31, ngrp = BA_THREADS / npad;
-            const int a = tid % npad, grp = tid / npad;
-            if (grp < ngrp && a < np && p.colmap[a] >= 0) {
-                double gsum = 0;
-                for (int rI = grp; rI < np; rI += ngrp) gsum += P->J0[(size_t)rI * np + a] * sh.pr[rI];
-                atomicAdd(&bv[p.colmap[a]], gsum);
-            }
-        }
+        for (int a = tid; a < np; a += BA_THREADS) if (p.colmap[a] >= 0) bv[p.colmap[a]] += sh.pr[a];
         for (int e = tid; e < np * np; e += BA_THREADS) {
             int a = e / np, c = e - a * np;
             int ca = p.colmap[a], cc = p.colmap[c];
             if (ca < 0 || cc < 0) continue;
-            double h = (c <= a) ? p.HP[(size_t)a * np + c] : p.HP[(size_t)c * np + a];     // J0^T J0 from the solve kernel
-            A[(size_t)ca * pos + cc] += h;
+            A[(size_t)ca * pos + cc] += HPm[e];
         }
         __syncthreads();
     }
@@ -792,35 +783,65 @@ k_ba_marg(const BaMeta *metas, const BaProbDev *probs, BaOutDev *outs, const BaM
         __syncthreads();
     }
     MPROF(4);
-    // second decomposition: A' = V2 diag(S) V2^T (in shared memory when it fits)
-    if (nn <= MARG_SMEM_N) {
-        const int ne2 = MARG_NE(nn), ld2 = MARG_LDA(nn);
-        double *As = big, *Vs = big + MARG_A_ELEMS(nn);
-        for (int e = tid; e < ne2 * ld2; e += BA_THREADS) {
-            const int i = e / ld2, j = e - i * ld2;
-            As[e] = (i < nn && j < nn && j >= i) ? Ar[(size_t)i * nn + j] : 0.0;      // upper triangle
-        }
-        __syncthreads();
-        jacobi_eig_smem(As, Vs, nn, sh);
+    // ---- 5. the new prior in information form: HP = A' (symmetric, from its upper triangle -- what
+    // SelfAdjointEigenSolver would read), gp = b'.  The reference factors A' = V S V^T, zeroes eigenvalues <= 1e-8 and
+    // stores J0 = sqrt(S) V^T, r0 = S^-1/2 V^T b' (marginalization_factor.cpp:298-308); J0^T J0 and J0^T r0 equal A' and
+    // b' up to the truncated part (|lambda| <= 1e-8 against ||A'|| ~ 1e7: below FP64 resolution of the products), so the
+    // decomposition is only run when the factor form itself is asked for (k_ba_prior_factor).  The constant
+    // c0 = 1/2 r0^T r0 = 1/2 b'^T A'^+ b' comes from a diagonally pivoted Cholesky that stops at pivots <= 1e-8. ----
+    double c0acc = 0.0;
+    {
+        const int cap = MARG_A_ELEMS(MARG_SMEM_N) + MARG_V_ELEMS(MARG_SMEM_N);
+        const bool insm = nn * nn + 3 * nn + 8 <= cap;
+        double *Mw = insm ? big : V2;
+        double *yv = insm ? big + nn * nn : Tm;
+        double *colb = yv + nn;
+        int *done = reinterpret_cast<int *>(colb + nn);
         for (int e = tid; e < nn * nn; e += BA_THREADS) {
             const int i = e / nn, j = e - i * nn;
-            V2[e] = Vs[j * ne2 + i];                 // VT[col][row]
-            if (i == j) Ar[e] = As[i * ld2 + i];
+            const double v = (j >= i) ? Ar[(size_t)i * nn + j] : Ar[(size_t)j * nn + i];
+            Q->J0[e] = v; Mw[e] = v;
+        }
+        for (int i = tid; i < nn; i += BA_THREADS) { const double v = br[i]; Q->r0[i] = v; yv[i] = v; done[i] = 0; }
+        __syncthreads();
+        for (int k = 0; k < nn; ++k) {
+            // pivot = largest remaining diagonal entry
+            double v = -1.0;
+            int bi = tid;
+            for (int i = tid; i < nn; i += BA_THREADS) { const double d_ = done[i] ? -1.0 : Mw[(size_t)i * nn + i]; if (d_ > v) { v = d_; bi = i; } }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const double ov = __shfl_xor_sync(0xffffffffu, v, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                if (ov > v || (ov == v && oi < bi)) { v = ov; bi = oi; }
+            }
+            if (lane == 0) { sh.red[warp] = v; sh.chunk[warp] = bi; }
+            __syncthreads();
+            double dmax = -1.0;
+            int pv = 0;
+            for (int w = 0; w < nwarp; ++w) { const double ov = sh.red[w]; const int oi = sh.chunk[w]; if (ov > dmax || (ov == dmax && oi < pv)) { dmax = ov; pv = oi; } }
+            if (!(dmax > 1e-8)) break;                         // uniform: every thread sees the same (dmax, pv)
+            const double l_ = sqrt(dmax), yk = yv[pv] / l_;
+            c0acc += yk * yk;
+            __syncthreads();
+            for (int i = tid; i < nn; i += BA_THREADS) {
+                double cb = 0.0;
+                if (!done[i] && i != pv) { cb = Mw[(size_t)i * nn + pv] / l_; yv[i] -= cb * yk; }
+                colb[i] = cb;
+            }
+            if (tid == 0) done[pv] = 1;
+            __syncthreads();
+            for (int i = warp; i < nn; i += nwarp) {          // one warp per remaining row, lanes along the row
+                const double ci = colb[i];
+                if (ci == 0.0) continue;
+                double *row = Mw + (size_t)i * nn;
+                for (int j = lane; j < nn; j += 32) row[j] -= ci * colb[j];
+            }
+            __syncthreads();
         }
         __syncthreads();
-    } else {
-        jacobi_eig(Ar, V2, nn, sh);
     }
     MPROF(5);
-    // ---- 5. linearized_jacobians / residuals + kept blocks into the next prior store ----
-    for (int k = tid; k < nn; k += BA_THREADS) {
-        const double w = Ar[(size_t)k * nn + k];
-        const double S = w > 1e-8 ? w : 0.0, Sinv = w > 1e-8 ? 1.0 / w : 0.0;
-        const double ss = sqrt(S), sis = sqrt(Sinv);
-        double vb = 0;
-        for (int j = 0; j < nn; ++j) { Q->J0[(size_t)k * nn + j] = ss * V2[(size_t)j * nn + k]; vb += V2[(size_t)j * nn + k] * br[j]; }
-        Q->r0[k] = sis * vb;
-    }
     if (tid == 0) {
         int nk = 0;
         for (int i = sh.first_kept; i < sh.nb; ++i) {
@@ -834,7 +855,7 @@ k_ba_marg(const BaMeta *metas, const BaProbDev *probs, BaOutDev *outs, const BaM
             else Q->index[nk] = (sh.index[i] == VRF_WINDOW_SIZE) ? VRF_WINDOW_SIZE - 1 : sh.index[i];
             ++nk;
         }
-        Q->n = nn; Q->n_blocks = nk; Q->valid = 1;
+        Q->n = nn; Q->n_blocks = nk; Q->valid = 1; Q->form = 1; Q->c0 = 0.5 * c0acc;
         out.has_new_prior = 1;
         MPROF(6);
         for (int k = 0; k < 7; ++k) out.prof2[k] = tp[k];
@@ -845,8 +866,72 @@ k_ba_marg(const BaMeta *metas, const BaProbDev *probs, BaOutDev *outs, const BaM
 // 164 KB carve-out (minus the 1 KB reserve): leaves 92 KB of L1 for the global scratch of the elimination phases
 static_assert(((sizeof(MargShared) + 15) & ~(size_t)15) + sizeof(double) * (MARG_A_ELEMS(MARG_SMEM_N) + MARG_V_ELEMS(MARG_SMEM_N)) <= 164 * 1024 - 1024,
               "marginalization frame must fit the 164 KB carve-out");
+// ---------------------------------------------------------------------------
+// k_ba_prior_factor: the reference's factor form of a stored (information-form) prior, on demand:
+// A' = V S V^T (cyclic Jacobi, as Eigen::SelfAdjointEigenSolver in marginalization_factor.cpp:298),
+// S = lambda > 1e-8 ? lambda : 0, linearized_jacobians = sqrt(S) V^T, linearized_residuals = S^-1/2 V^T b' (:299-308).
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(BA_THREADS, 1)
+k_ba_prior_factor(const BaPriorStore *src, BaPriorStore *dst, double *scratch)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    MargShared &sh = *reinterpret_cast<MargShared *>(smem_raw);
+    double *big = reinterpret_cast<double *>(smem_raw + ((sizeof(MargShared) + 15) & ~(size_t)15));
+    const int tid = threadIdx.x;
+    const int nn = src->n;
+    if (tid == 0) { sh.jdbg = 0; dst->n = nn; dst->n_blocks = src->n_blocks; dst->valid = 1; dst->form = 0; dst->c0 = src->c0; }
+    for (int b = tid; b < src->n_blocks; b += BA_THREADS) { dst->kind[b] = src->kind[b]; dst->index[b] = src->index[b]; dst->size[b] = src->size[b]; dst->idx[b] = src->idx[b]; }
+    for (int i = tid; i < src->n_blocks * 9; i += BA_THREADS) dst->x0[i] = src->x0[i];
+    __syncthreads();
+    const double *HPm = src->J0, *gp = src->r0;
+    if (nn <= MARG_SMEM_N) {
+        const int ne2 = MARG_NE(nn), ld2 = MARG_LDA(nn);
+        double *As = big, *Vs = big + MARG_A_ELEMS(nn);
+        for (int e = tid; e < ne2 * ld2; e += BA_THREADS) {
+            const int i = e / ld2, j = e - i * ld2;
+            As[e] = (i < nn && j < nn && j >= i) ? HPm[(size_t)i * nn + j] : 0.0;      // upper triangle
+        }
+        __syncthreads();
+        jacobi_eig_smem(As, Vs, nn, sh);
+        for (int k = tid; k < nn; k += BA_THREADS) {
+            const double w = As[k * ld2 + k];
+            const double S = w > 1e-8 ? w : 0.0, Sinv = w > 1e-8 ? 1.0 / w : 0.0;
+            const double ss = sqrt(S), sis = sqrt(Sinv);
+            double vb = 0;
+            for (int j = 0; j < nn; ++j) { const double vjk = Vs[k * ne2 + j]; dst->J0[(size_t)k * nn + j] = ss * vjk; vb += vjk * gp[j]; }   // VT[col k][row j]
+            dst->r0[k] = sis * vb;
+        }
+    } else {
+        double *Ag = scratch, *Vg = scratch + (size_t)VRF_PRIOR_MAX_DIM * VRF_PRIOR_MAX_DIM;
+        for (int e = tid; e < nn * nn; e += BA_THREADS) Ag[e] = HPm[e];
+        __syncthreads();
+        jacobi_eig(Ag, Vg, nn, sh);
+        for (int k = tid; k < nn; k += BA_THREADS) {
+            const double w = Ag[(size_t)k * nn + k];
+            const double S = w > 1e-8 ? w : 0.0, Sinv = w > 1e-8 ? 1.0 / w : 0.0;
+            const double ss = sqrt(S), sis = sqrt(Sinv);
+            double vb = 0;
+            for (int j = 0; j < nn; ++j) { const double vjk = Vg[(size_t)j * nn + k]; dst->J0[(size_t)k * nn + j] = ss * vjk; vb += vjk * gp[j]; }
+            dst->r0[k] = sis * vb;
+        }
+    }
+}
+
 static size_t marg_smem() { return ((sizeof(MargShared) + 15) & ~(size_t)15) + sizeof(double) * (MARG_A_ELEMS(MARG_SMEM_N) + MARG_V_ELEMS(MARG_SMEM_N)); }
 size_t ba_marg_smem_bytes() { return marg_smem(); }
+
+int ba_prior_factor_launch(const BaPriorStore *src, BaPriorStore *dst, double *scratch, LaunchCtx &lc)
+{
+    static bool configured = false;
+    if (!configured) {
+        if (cudaFuncSetAttribute(k_ba_prior_factor, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)marg_smem()) != cudaSuccess) return -1;
+        configured = true;
+    }
+    lc.begin(K_BA_PRIOR_FACTOR);
+    k_ba_prior_factor<<<1, BA_THREADS, marg_smem(), lc.st>>>(src, dst, scratch);
+    lc.end();
+    return 0;
+}
 
 int ba_marg_launch(const BaMeta *d_meta, const BaProbDev *d_prob, BaOutDev *d_out, BaMargDev *d_marg, int n, LaunchCtx &lc)
 {

@@ -412,8 +412,10 @@ class Handle:
         return [r.finish() for r in results]
 
     # ---- back end ----
-    def ba_solve_batch(self, seqs, problems):
-        """problems: list of vrf_b200.ba_problem.BaProblem (finalized). Returns list of BaSolution."""
+    def ba_solve_batch(self, seqs, problems, want_prior=True):
+        """problems: list of vrf_b200.ba_problem.BaProblem (finalized). Returns list of BaSolution.
+        want_prior=False passes new_prior = NULL: the new prior stays on the device in information form and the
+        eigen-decomposition that produces (linearized_jacobians, linearized_residuals) is not run."""
         from .ba_problem import BaSolution
         n = len(seqs)
         seq_a = np.asarray(seqs, np.int32)
@@ -422,6 +424,8 @@ class Handle:
         res = (VrfBaResult * n)()
         for i, pb in enumerate(problems):
             C.memmove(C.byref(probs[i]), C.byref(pb.c), C.sizeof(VrfBaProblem))
+            if not want_prior:
+                sols[i].c.new_prior = None
             C.memmove(C.byref(res[i]), C.byref(sols[i].c), C.sizeof(VrfBaResult))
         rc = self.lib.vrf_ba_solve_batch(self.h, n, seq_a.ctypes.data, probs, res)
         check(rc, self.h)
@@ -430,8 +434,8 @@ class Handle:
             s.rc = res[i].status
         return sols
 
-    def ba_solve(self, seq, problem):
-        return self.ba_solve_batch([seq], [problem])[0]
+    def ba_solve(self, seq, problem, want_prior=True):
+        return self.ba_solve_batch([seq], [problem], want_prior)[0]
 
     def ba_upload(self, seqs, problems):
         n = len(seqs)
