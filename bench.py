@@ -552,26 +552,30 @@ def main():
     part = os.environ.get("VRF_E2E_PART", "both")          # diagnosis only: "front" / "ba"
 
     def run_host_steps(k0, k1):
-        """Steps k0..k1-1 through the host-buffer C ABI.  Two host threads like the reference's trackThread /
-        processThread: the back end's host-buffer call runs on its own handle (ctypes releases the GIL) while the
-        front end keeps two batches in flight (submit k+1, collect k) so that the next batch's frames cross PCIe
-        while this batch's kernels run.  Every frame's H2D and every result's D2H happens inside [k0, k1)."""
+        """Steps k0..k1-1 through the host-buffer C ABI.  Two free-running host threads like the reference's trackThread /
+        processThread (estimator_nodelet.cpp:61-62): the back end's host-buffer calls run on their own handle (ctypes
+        releases the GIL) and are only joined at the end; the front end keeps two batches in flight (submit k+1,
+        collect k) so that the next batch's frames cross PCIe while this batch's kernels run.  Every frame's H2D and
+        every result's D2H happens inside [k0, k1); the interval ends when BOTH threads have finished all their steps."""
         n_out = 0
+
+        def ba_loop():
+            hnd2_ba.ba_submit_into(ba_grp[k0 % 2], ba_probs_c)
+            for k in range(k0, k1):
+                run_host_ba(k, k + 1 < k1)
+
+        th = threading.Thread(target=ba_loop if part != "front" else (lambda: None))
+        th.start()
         if part != "ba":
             submit_front(k0)
-        if part != "front":
-            hnd2_ba.ba_submit_into(ba_grp[k0 % 2], ba_probs_c)
-        for k in range(k0, k1):
-            th = threading.Thread(target=(lambda: run_host_ba(k, k + 1 < k1)) if part != "front" else (lambda: None))
-            th.start()
-            if part != "ba":
+            for k in range(k0, k1):
                 t_ = time.perf_counter()
                 if k + 1 < k1:
                     submit_front(k + 1)
                 hnd2.collect_batch_into(seq_np, tr_outs)
                 t_host["front"] += time.perf_counter() - t_
                 n_out = sum(tr_outs[i_].n for i_ in range(S))
-            th.join()
+        th.join()
         return n_out
 
     if e2e_steps:

@@ -141,7 +141,12 @@ extern "C" int vrf_create(const VrfConfig *cfg, int n_seq, int device, vrf_handl
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return fail(VRF_ERR_CUDA);
     h->sm_count = prop.multiProcessorCount;
-    if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) return fail(VRF_ERR_CUDA);
+    {   // the handle's main stream (kernels, small packed uploads, result copies) outranks the bulk frame copies of any
+        // handle's copy streams: a BA batch's 30 MB upload must not queue behind 500 MB of frames on the copy engines
+        int prio_lo = 0, prio_hi = 0;
+        cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+        if (cudaStreamCreateWithPriority(&h->stream, cudaStreamNonBlocking, prio_hi) != cudaSuccess) return fail(VRF_ERR_CUDA);
+    }
     for (int k = 0; k < VRF_COPY_STREAMS; ++k)
         if (cudaStreamCreateWithFlags(&h->copy_stream[k], cudaStreamNonBlocking) != cudaSuccess) return fail(VRF_ERR_CUDA);
     for (int p = 0; p < VRF_PIPE_DEPTH; ++p) {
