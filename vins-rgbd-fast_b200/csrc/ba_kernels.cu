@@ -16,14 +16,16 @@
 //                            UNPINNED against real Ceres)
 //
 // Data layout (HBM, per problem, SoA over landmarks so that lanes of a warp read
-// consecutive words): lam[M], start[M], flag[M], obs_ptr[M+1], obs[O][2]; W[M][66]
-// (landmark-to-pose coupling rows), hll/gl/diag/gd/gn/step per landmark.
-// On chip: the 171x171 camera system lives in shared memory as a packed lower
-// triangle (117 KB) and is Schur-reduced and Cholesky-factorised in place; the
-// tangent layout is [pose f: 6f | speed-bias f: 66+9f | ex-pose: 165].
+// consecutive words): lam[M], start[M], flag[M], obs_ptr[M+1], obs[O][2]; W[M][73]
+// (landmark-to-pose / ex-pose / td coupling rows), hll/gl/diag/gd/gn/step per landmark.
+// On chip: the 172x172 camera system lives in shared memory as a packed lower
+// triangle (119 KB) and is Schur-reduced and Cholesky-factorised in place; the
+// tangent layout is [pose f: 6f | speed-bias f: 66+9f | ex-pose: 165 | td: 171].
+// The marginalization prior is consumed in information form (ba_dev.cuh, BaPriorStore).
 //
-// Roofline: ~100-160 KB touched and ~5 MFLOP FP64 per iteration per problem => compute /
-// latency bound; the only dense contraction is the 171^3/3 Cholesky.
+// Roofline: ~100-160 KB touched and ~5 MFLOP FP64 per iteration per problem => FP64 dependency
+// chains and shared-memory bandwidth bound; the only
+// dense contraction is the 172^3/3 Cholesky.
 #include "ba_math.cuh"
 
 namespace vrf {
@@ -107,8 +109,6 @@ __device__ __noinline__ void accumulate_g(double *H, double *g, int i, int j, in
 }
 
 #define BA_NPAIR (BA_NF * (BA_NF - 1) / 2)
-
-__device__ __forceinline__ int pair_index(int i, int j) { return i * (2 * BA_NF - i - 1) / 2 + (j - i - 1); }
 
 // entry e of the 12x12 normal-equation block of one projection factor (host Jacobian Ji, observer Jacobian Jj,
 // 2x6 row-major each): 0..35 Jj^T Ji, 36..56 lower triangle of Jj^T Jj, 57..77 of Ji^T Ji, 78..83 Jj^T r, 84..89 Ji^T r.
