@@ -74,7 +74,8 @@ typedef struct VrfConfig {
     int32_t use_imu;                  /* USE_IMU: IMU-predicted LK, maxLevel 1 (else maxLevel 3) */
     int32_t equalize;                 /* EQUALIZE: cv::createCLAHE(3.0, Size(8,8)) on every incoming frame (feature_tracker.cpp:269-275);
                                          needs ROW and COL to be multiples of 8, else VRF_ERR_UNSUPPORTED */
-    int32_t fisheye;                  /* FISHEYE: must be 0 */
+    int32_t fisheye;                  /* FISHEYE: setMask starts from fisheye_mask (feature_tracker.cpp:175-178); the mask image is handed
+                                         over with vrf_set_fisheye_mask before the first frame */
     int32_t lk_max_level;             /* -1 = reference default; else explicit maxLevel (0..3) */
     int32_t use_ransac;               /* 1 = rejectWithF enabled (reference behaviour) */
     int32_t reserved0;
@@ -111,6 +112,12 @@ uint64_t vrf_launch_count(const vrf_handle *h);
 /* Replaces: Estimator::clearState() + setParameter() for one sequence
  * (estimator_nodelet.cpp:255-258; failureDetection reboot estimator.cpp:345-353). */
 int  vrf_reset_sequence(vrf_handle *h, int seq);
+
+/* FISHEYE: the reference loads fisheye_mask = cv::imread(FISHEYE_MASK, 0) in Estimator::setParameter (estimator.cpp:31)
+ * and uses it as the initial mask of setMask() (feature_tracker.cpp:175-178): tracked points and new corners are kept
+ * only where the mask is 255, FAST only detects where it is non-zero.  mask: ROW x COL, 8-bit, `stride` bytes per row
+ * (0 = COL).  Requires VrfConfig::fisheye = 1; tracker calls fail with VRF_ERR_ARG until the mask is set. */
+int  vrf_set_fisheye_mask(vrf_handle *h, const uint8_t *mask, size_t stride);
 
 /* ------------------------------------------------------------------------- */
 /* Front end                                                                  */

@@ -97,6 +97,7 @@ class FrontendConfig:
     lk_max_level: int = -1          # -1 => reference default (1 with IMU, 3 without)
     use_ransac: int = 1             # 0 skips rejectWithF (kernel bring-up only)
     equalize: int = 0               # EQUALIZE: CLAHE on every incoming frame (feature_tracker.cpp:269-275)
+    fisheye: int = 0                # FISHEYE: setMask starts from fisheye_mask (feature_tracker.cpp:175-178)
 
 
 class PinholeCamera:
@@ -167,6 +168,7 @@ class FeatureTrackerRef:
         self.cur_time = 0.0
         self.prev_time = 0.0
         self.mask = None
+        self.fisheye_mask = None         # set by the caller when cfg.fisheye (Estimator::setParameter, estimator.cpp:31)
         self.last_status = None
         self.last_ransac_status = None
         self.last_new_keypoints = []
@@ -251,7 +253,10 @@ class FeatureTrackerRef:
     # feature_tracker.cpp:173-208
     def set_mask(self):
         c = self.cfg
-        self.mask = np.full((c.row, c.col), 255, np.uint8)
+        if c.fisheye:                                       # feature_tracker.cpp:175-178
+            self.mask = self.fisheye_mask.copy()
+        else:
+            self.mask = np.full((c.row, c.col), 255, np.uint8)
         perm = stdsort_desc_perm(self.track_cnt)
         pts, ids, cnt = [], [], []
         for k in perm:

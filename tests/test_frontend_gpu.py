@@ -118,6 +118,34 @@ def test_sequence_parity_with_clahe():
     h.close()
 
 
+def test_sequence_parity_with_fisheye_mask():
+    """FISHEYE = 1: setMask starts from fisheye_mask (255 inside a disc, a grey ring where FAST may detect but nothing is
+    kept, 0 outside): tracked points and new corners only survive where the mask is 255."""
+    cam = synth.CamModel()
+    seq = synth.Sequence(1618, cam)
+    yy, xx = np.mgrid[0:cam.height, 0:cam.width]
+    rr = np.hypot(xx - cam.width / 2 + 0.5, yy - cam.height / 2 + 0.5)
+    fm = np.where(rr < 230, 255, np.where(rr < 260, 128, 0)).astype(np.uint8)
+    cfg = binding.default_config(use_ransac=1, fisheye=1)
+    h = binding.Handle(cfg, 1, 0)
+    with pytest.raises(RuntimeError):                       # no mask yet: refused, not ignored
+        h.read_image(0, seq.frame(0)[1], seq.time(0), np.eye(3), pub=True)
+    h.set_fisheye_mask(fm)
+    ref = FeatureTrackerRef(FrontendConfig(use_ransac=1, fisheye=1))
+    ref.fisheye_mask = fm
+    for k in range(9):
+        gray = seq.frame(k)[1]
+        R = seq.relative_R(k)
+        out = h.read_image(0, gray, seq.time(k), R, pub=(k % 3 == 0))
+        ref.read_image(gray, seq.time(k), R, pub_this_frame=(k % 3 == 0))
+        check_frame(k, out, ref)
+        if k % 3 == 0:
+            p = np.rint(out.cur_pts).astype(int)
+            assert np.all(fm[p[:, 1], p[:, 0]] == 255)
+    assert 40 < out.n < 150
+    h.close()
+
+
 def test_rgb_ingest_equals_gray_path():
     """RGB8 payload: device-side cvtColor(RGB2GRAY) then the same pipeline."""
     for k, out, ref in run_pair({}, 5, 31, rgb=True):

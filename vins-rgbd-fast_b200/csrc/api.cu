@@ -79,7 +79,6 @@ static int build_front_cfg(const VrfConfig &cfg, FrontCfg &fc)
 {
     memset(&fc, 0, sizeof(fc));
     if (cfg.row < 64 || cfg.col < 64 || (cfg.col & 15)) return VRF_ERR_ARG;   // uint4 row access
-    if (cfg.fisheye) return VRF_ERR_UNSUPPORTED;
     // CLAHE: OpenCV pads frames whose size is not a multiple of the 8x8 tile grid; that variant is not built
     if (cfg.equalize && ((cfg.row & 7) || (cfg.col & 7))) return VRF_ERR_UNSUPPORTED;
     if (cfg.max_cnt <= 0 || cfg.max_cnt > VRF_CAP / 2 || cfg.min_dist < 1) return VRF_ERR_ARG;
@@ -210,7 +209,7 @@ extern "C" void vrf_destroy(vrf_handle *h)
                     d.lk_status, d.n_lk, d.t_prev, d.t_forw, d.t_prevun, d.t_ids, d.t_cnt, d.t_n, d.t_keep,
                     d.unstable, d.n_unstable, d.maskpts, d.n_maskpts, d.grid_cnt, d.tex_status, d.cell_k, d.cand,
                     d.ncand, d.o_pts, d.o_un, d.o_vel, d.o_ids, d.o_cnt, d.out_hdr, d.work_prefix,
-                    d.o_depth, d.o_dkeep, d.clahe_lut, h->d_stage[0], h->d_stage[1], h->d_stage_depth[0], h->d_stage_depth[1]};
+                    d.o_depth, d.o_dkeep, d.clahe_lut, const_cast<uint8_t *>(d.fisheye), h->d_stage[0], h->d_stage[1], h->d_stage_depth[0], h->d_stage_depth[1]};
     static_assert(VRF_PIPE_DEPTH == 2, "staging slots listed explicitly above");
     for (void *p : ptrs) if (p) cudaFree(p);
     for (int k = 0; k < VRF_CALL_SLOTS; ++k) {
@@ -236,6 +235,23 @@ extern "C" int vrf_synchronize(vrf_handle *h)
 {
     if (!h) return VRF_ERR_ARG;
     CK(cudaStreamSynchronize(h->stream));
+    return VRF_OK;
+}
+
+extern "C" int vrf_set_fisheye_mask(vrf_handle *h, const uint8_t *mask, size_t stride)
+{
+    if (!h || !mask || !h->cfg.fisheye) return VRF_ERR_ARG;
+    if (stride == 0) stride = (size_t)h->cfg.col;
+    if (stride < (size_t)h->cfg.col) return VRF_ERR_ARG;
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->stream));
+    FrontDev &d = h->fd;
+    if (!d.fisheye) {
+        uint8_t *p = nullptr;
+        CK(cudaMalloc((void **)&p, (size_t)h->cfg.row * h->cfg.col));
+        d.fisheye = p;
+    }
+    CK(cudaMemcpy2D(const_cast<uint8_t *>(d.fisheye), h->cfg.col, mask, stride, h->cfg.col, h->cfg.row, cudaMemcpyHostToDevice));
     return VRF_OK;
 }
 
@@ -265,6 +281,7 @@ static int enqueue_front(vrf_handle *h, int n, const int32_t *seqs, const uint8_
 {
     if (n < 1 || out_base < 0 || out_base + n > h->n_seq || !seqs || !times) return VRF_ERR_ARG;
     if (fmt != VRF_FMT_GRAY8 && fmt != VRF_FMT_RGB8) return VRF_ERR_ARG;
+    if (h->cfg.fisheye && !h->fd.fisheye) return VRF_ERR_ARG;        // FISHEYE without vrf_set_fisheye_mask: no silent fallback
     std::vector<uint8_t> seen(h->n_seq, 0);
     int any_pub = 0;
     const unsigned slot = h->call_ctr++ % VRF_CALL_SLOTS;

@@ -79,6 +79,7 @@ struct FrontDev {
     int *out_hdr;               // [batch][8]: n, n_id, n_predict, n_unstable, status
     int *work_prefix;           // [MAX_BATCH+1] prefix of LK work items for the current call
     uint8_t *clahe_lut;         // [S][64][256] per-tile CLAHE look-up tables (EQUALIZE only)
+    const uint8_t *fisheye;     // [rows][cols] fisheye_mask (FISHEYE only, shared by all sequences), else NULL
 };
 
 __device__ __forceinline__ int reflect101(int i, int n)

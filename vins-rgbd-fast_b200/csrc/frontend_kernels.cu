@@ -821,7 +821,8 @@ k_post_b(FrontCfg c, const SeqCall *calls, FrontDev d)
                 int src = s_sort[k].val;
                 float2 p = s_forw[src];
                 int px = __float2int_rn(p.x), py = __float2int_rn(p.y);
-                bool hit = false;
+                // FISHEYE: the mask starts as fisheye_mask.clone() (feature_tracker.cpp:175-178); the test is == 255
+                bool hit = d.fisheye && d.fisheye[(size_t)py * c.cols + px] != 255;
                 for (int l = lane; l < nacc; l += 32) {
                     int dx = s_acc[l].x - px, dy = s_acc[l].y - py;
                     hit |= (dx * dx + dy * dy <= r2);
@@ -1017,6 +1018,7 @@ k_fast(FrontCfg c, const SeqCall *calls, FrontDev d)
                 sc > q[rw - 1] && sc > q[rw] && sc > q[rw + 1]) {
                 flag = 1;
                 int gx = rx + x, gy = ry + y;
+                if (d.fisheye && d.fisheye[(size_t)gy * c.cols + gx] == 0) flag = 0;      // detect(img, kps, mask): mask != 0
                 for (int m = 0; m < nmask; ++m) {
                     int dx = s_m[m].x - gx, dy = s_m[m].y - gy;
                     if (dx * dx + dy * dy <= r2) { flag = 0; break; }
@@ -1114,7 +1116,7 @@ k_finish(FrontCfg c, const SeqCall *calls, FrontDev d, const uint8_t *depth, siz
             for (int j = 0; j < nc; ++j) {
                 float px = cand[3 * j], py = cand[3 * j + 1];
                 int ix = __float2int_rn(px), iy = __float2int_rn(py);
-                bool hit = false;
+                bool hit = d.fisheye && d.fisheye[(size_t)iy * c.cols + ix] != 255;
                 for (int l = lane; l < nm; l += 32) {
                     int dx = mp[l].x - ix, dy = mp[l].y - iy;
                     hit |= (dx * dx + dy * dy <= r2);

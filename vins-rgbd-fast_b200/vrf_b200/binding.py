@@ -147,7 +147,7 @@ class FmProblem:
 # every symbol include/vrf.h + include/vrf_ba.h + include/vrf_fm.h declare
 EXPORTS = [
     "vrf_config_default", "vrf_create", "vrf_destroy", "vrf_strerror", "vrf_last_cuda_error",
-    "vrf_launch_count", "vrf_reset_sequence", "vrf_tracker_read_image", "vrf_tracker_read_image_batch",
+    "vrf_launch_count", "vrf_reset_sequence", "vrf_set_fisheye_mask", "vrf_tracker_read_image", "vrf_tracker_read_image_batch",
     "vrf_tracker_read_rgbd_batch", "vrf_tracker_submit_rgbd_batch", "vrf_tracker_collect_batch",
     "vrf_tracker_enqueue_batch_dev", "vrf_tracker_fetch_batch", "vrf_synchronize", "vrf_stream",
     "vrf_profile_enable", "vrf_profile_read", "vrf_debug_sort_desc", "vrf_debug_read", "vrf_ba_solve", "vrf_ba_solve_batch", "vrf_ba_upload_batch",
@@ -170,6 +170,7 @@ def load():
     lib.vrf_config_default.restype = None
     lib.vrf_create.argtypes = [C.POINTER(VrfConfig), C.c_int, C.c_int, C.POINTER(C.c_void_p)]
     lib.vrf_destroy.argtypes = [C.c_void_p]
+    lib.vrf_set_fisheye_mask.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
     lib.vrf_destroy.restype = None
     lib.vrf_strerror.argtypes = [C.c_int]
     lib.vrf_strerror.restype = C.c_char_p
@@ -452,6 +453,10 @@ class Handle:
     def ba_download(self, seqs):
         seq_a = np.asarray(seqs, np.int32)
         check(self.lib.vrf_ba_download_batch(self.h, len(seqs), seq_a.ctypes.data, None), self.h)
+
+    def set_fisheye_mask(self, mask):
+        m = np.ascontiguousarray(mask, np.uint8)
+        check(self.lib.vrf_set_fisheye_mask(self.h, m.ctypes.data, m.shape[1]), self.h, allow_soft=False)
 
     # ---- steps either side of optimization() (include/vrf_fm.h) ----
     def _fm_call(self, fn, problems):
