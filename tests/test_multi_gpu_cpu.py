@@ -55,3 +55,18 @@ def test_pingpong_plan_is_continuous():
     R = np.stack([np.eye(3)] + [np.array([[0, -1, 0], [1, 0, 0], [0, 0, 1.0]])] * (T - 1))
     assert np.allclose(bench.rel_rotation(R, 3, 2), R[3])
     assert np.allclose(bench.rel_rotation(R, 2, 3), R[3].T)
+
+
+def test_gpu_arm_never_touches_the_oracle():
+    """oracle/ is test infrastructure: bench.py's GPU arm (main) must not import it -- only the CPU legs
+    (run_reference / _ref_prepare / _ref_step, executed in child processes) may -- and the product package may only
+    reach it through the generator's explicit default (tests, CPU arm)."""
+    import inspect
+    import bench
+    import re
+    src = inspect.getsource(bench.main)
+    assert not re.search(r"(from|import)\s+oracle", src)
+    for fn in (bench.run_reference, bench._ref_prepare, bench._ref_step):
+        assert fn.__module__ == "bench"
+    import vrf_b200.binding as binding
+    assert not re.search(r"(from|import)\s+oracle", inspect.getsource(binding))

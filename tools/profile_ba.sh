@@ -3,7 +3,7 @@
 mkdir -p gpurun_out
 CMD="python bench.py --steps 3 --warmup 3 --seqs 96 --quick"
 for k in ${KERNELS:-k_ba_marg k_ba_solve k_lk}; do
-  timeout 400 ncu --set full --clock-control none --import-source on -k regex:$k -s 2 -c 1 -f -o gpurun_out/prof_$k $CMD > gpurun_out/prof_$k.log 2>&1
+  timeout 400 ncu --set full --clock-control none --import-source on -k regex:$k -s ${SKIP:-12} -c 1 -f -o gpurun_out/prof_$k $CMD > gpurun_out/prof_$k.log 2>&1
 done
 ls -la gpurun_out
 # afterwards, here:  for k in ...; do ncu -i gpurun_out/prof_$k.ncu-rep --page source --csv --print-source cuda,sass > /tmp/$k.csv;

@@ -134,8 +134,12 @@ class WindowSimulator:
     (what FeatureManager / processIMU would hand to optimization())."""
 
     def __init__(self, seed, cfg, n_landmarks=150, kf_dt=0.1, imu_rate=200.0, flag2_frac=0.1,
-                 pix_noise=0.5, ric=None, tic=None, td_true=0.0, ex_constant=1, td_constant=1, ex_perturb=0.0):
+                 pix_noise=0.5, ric=None, tic=None, td_true=0.0, ex_constant=1, td_constant=1, ex_perturb=0.0, preintegrate=None):
         self.cfg = cfg
+        # IntegrationBase for the generated IMU samples: preintegrate(samples, acc0, gyr0, ba, bg, cfg) -> VrfImuPreint.
+        # None = the C oracle (tests, CPU arm); bench.py's GPU arm passes the library's own vrf_imu_preintegrate_batch so
+        # that nothing under oracle/ is touched outside the checker legs.
+        self._preintegrate = preintegrate
         self.rng = np.random.default_rng(seed)
         self.traj = synth.Trajectory(seed, fps=1.0 / kf_dt, trans_per_frame=0.06, rot_deg_per_frame=1.5)
         self.kf_dt = kf_dt
@@ -207,7 +211,10 @@ class WindowSimulator:
 
     def _preint(self, k0, k1, ba, bg):
         """IMU between absolute frames k0 -> k1 (processIMU: first sample initialises acc_0/gyr_0)."""
-        from oracle import ba_ref    # only used by tests / bench cpu legs (generator needs IntegrationBase)
+        pre_fn = self._preintegrate
+        if pre_fn is None:
+            from oracle import ba_ref    # tests / CPU arm only
+            pre_fn = ba_ref.preintegrate
         t0, t1 = self.t(k0), self.t(k1)
         n = max(2, int(round((t1 - t0) * self.imu_rate)))
         ts = np.linspace(t0, t1, n + 1)
@@ -218,7 +225,7 @@ class WindowSimulator:
             a = self.traj.acc_body(tt) + self.ba_true + rng.normal(0, self.cfg.acc_n, 3)
             meas.append((a, g))
         samples = [(ts[i] - ts[i - 1], meas[i][0], meas[i][1]) for i in range(1, n + 1)]
-        return ba_ref.preintegrate(samples, meas[0][0], meas[0][1], ba, bg, self.cfg)
+        return pre_fn(samples, meas[0][0], meas[0][1], ba, bg, self.cfg)
 
     def window(self, a, marg_flag=B.MARGIN_OLD, perturb=True):
         """Problem for absolute frames a..a+10."""
