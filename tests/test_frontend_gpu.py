@@ -146,6 +146,17 @@ def test_sequence_parity_with_fisheye_mask():
     h.close()
 
 
+def test_odd_frame_size_three_levels():
+    """336x250 (width a multiple of 16 only, odd pyramid sizes 168x125 and 84x63): the vectorised pyrDown's partial
+    segments and reflected borders, LK and FAST on cells that do not tile the frame evenly."""
+    cam = synth.CamModel(fx=320.0, fy=320.0, cx=168.0, cy=125.0, width=336, height=250)
+    n = 0
+    for k, out, ref in run_pair({"lk_max_level": 2, "max_cnt": 120, "min_dist": 15}, 7, 4711, cam=cam, ransac=1):
+        check_frame(k, out, ref)
+        n += 1
+    assert n == 7 and out.n > 60
+
+
 def test_rgb_ingest_equals_gray_path():
     """RGB8 payload: device-side cvtColor(RGB2GRAY) then the same pipeline."""
     for k, out, ref in run_pair({}, 5, 31, rgb=True):
