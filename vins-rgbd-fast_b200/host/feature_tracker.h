@@ -86,7 +86,8 @@ public:
     void readIntrinsicParameter(const std::string &) {}   // intrinsics travel in VrfConfig
     void initGridsDetector() {}                            // grid table is built in vrf_create (feature_tracker.cpp:33-94)
 
-    cv::Mat fisheye_mask, grids_detector_img;              // visualisation only; FISHEYE must be 0
+    cv::Mat fisheye_mask, grids_detector_img;              // FISHEYE: hand fisheye_mask to the library once with setFisheyeMask()
+    void setFisheyeMask() { if (!fisheye_mask.empty()) vrf_set_fisheye_mask(h_, fisheye_mask.data, fisheye_mask.step); }
     std::vector<cv::Point2f> cur_pts, predict_pts, cur_un_pts, pts_velocity;
     std::vector<int> ids, track_cnt, grids_track_num;
     std::vector<uint16_t> depth_mm;                        // depth_img.at<ushort>((int)v, (int)u) per feature (publish frames)
