@@ -312,7 +312,8 @@ def main():
     # CPU baseline first, in a child process, before this process creates a CUDA context
     # (the oracle fans out over all host cores with multiprocessing)
     cpu_base = None
-    if rank == 0 and not args.no_cpu_baseline and not args.quick:
+    # (rank 0 at N = 1 only: at N > 1 the other ranks' set-up would compete for the host cores)
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and not args.quick:
         try:
             out = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "3",
                                   "--warmup", "1", "--ref-frames", "24"], capture_output=True, text=True, timeout=600)
