@@ -321,3 +321,50 @@ def test_td_and_extrinsic_estimation_recover_truth():
         # (the extrinsic translation is barely observable under this gentle rotation; the rotation is)
         assert np.linalg.norm(synth.so3_log(sim.ric.T @ sim.ex_est[1])) < 0.75 * ang0
     assert abs((est[0.03] - est[-0.03]) - 0.06) < 0.2 * 0.06
+
+
+def _pivoted_cholesky_c0(A, b, eps=1e-8):
+    """numpy restatement of the c0 computation in k_ba_marg: diagonally pivoted Cholesky of the (semi-definite) prior
+    information matrix that stops at pivots <= eps, forward substitution folded in; returns 1/2 b^T A^+ b."""
+    M = A.copy(); y = b.copy()
+    done = np.zeros(len(b), bool)
+    c = 0.0
+    for _ in range(len(b)):
+        d = np.where(done, -1.0, np.diag(M))
+        p = int(np.argmax(d))
+        if not d[p] > eps:
+            break
+        l = np.sqrt(d[p]); yk = y[p] / l
+        c += yk * yk
+        col = np.where(done, 0.0, M[:, p] / l); col[p] = 0.0
+        y -= col * yk
+        done[p] = True
+        M -= np.outer(col, col)
+    return 0.5 * c
+
+
+def test_information_form_of_the_prior_is_equivalent():
+    """The GPU keeps the prior as (HP, gp, c0) = (J0^T J0, J0^T r0, r0^T r0 / 2) and evaluates
+    c0 + dx.(gp + HP dx / 2) instead of 1/2 |r0 + J0 dx|^2.  On the oracle's priors (factor form,
+    eigenvalues <= 1e-8 truncated like the reference): (i) the two cost expressions agree for random dx, (ii) the
+    pivoted-Cholesky constant equals r0^T r0 / 2 although the matrix is rank deficient."""
+    cfg = make_cfg()
+    sim = BP.WindowSimulator(12, cfg, n_landmarks=120)
+    rng = np.random.default_rng(0)
+    for a in range(3):
+        pb = sim.window(a)
+        sol = ba_ref.solve(cfg, pb)
+        sim.commit(a, sol)
+        P = sol.new_prior
+        n = P.n
+        J = np.ctypeslib.as_array(P.linearized_jacobians)[: n * n].reshape(n, n).copy()
+        r0 = np.ctypeslib.as_array(P.linearized_residuals)[:n].copy()
+        HP, gp, c0 = J.T @ J, J.T @ r0, 0.5 * r0 @ r0
+        for _ in range(5):
+            dx = rng.normal(0, 1e-2, n)
+            lhs = 0.5 * np.sum((r0 + J @ dx) ** 2)
+            rhs = c0 + dx @ (gp + 0.5 * (HP @ dx))
+            assert abs(lhs - rhs) <= 1e-9 * max(1.0, lhs)
+        assert np.linalg.matrix_rank(J) < n or a > 0          # the first prior has truncated (zero) rows
+        c_piv = _pivoted_cholesky_c0(HP, gp)
+        assert abs(c_piv - c0) <= 1e-6 * max(c0, 1e-12), (a, c_piv, c0)
