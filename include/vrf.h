@@ -72,8 +72,7 @@ typedef struct VrfConfig {
     int32_t min_dist;                 /* MIN_DIST */
     int32_t num_grid_rows, num_grid_cols;
     int32_t use_imu;                  /* USE_IMU: IMU-predicted LK, maxLevel 1 (else maxLevel 3) */
-    int32_t equalize;                 /* EQUALIZE: cv::createCLAHE(3.0, Size(8,8)) on every incoming frame (feature_tracker.cpp:269-275);
-                                         needs ROW and COL to be multiples of 8, else VRF_ERR_UNSUPPORTED */
+    int32_t equalize;                 /* EQUALIZE: cv::createCLAHE(3.0, Size(8,8)) on every incoming frame (feature_tracker.cpp:269-275) */
     int32_t fisheye;                  /* FISHEYE: setMask starts from fisheye_mask (feature_tracker.cpp:175-178); the mask image is handed
                                          over with vrf_set_fisheye_mask before the first frame */
     int32_t lk_max_level;             /* -1 = reference default; else explicit maxLevel (0..3) */

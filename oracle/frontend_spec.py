@@ -320,19 +320,27 @@ def circle_covers(cx, cy, r, x, y):
 
 
 def clahe(img, clip=3.0, tiles=8):
-    """cv::createCLAHE(clip, Size(tiles, tiles))->apply(img) for frame sizes that are multiples of the tile grid
-    (OpenCV imgproc/clahe.cpp: CLAHE_CalcLut_Body + CLAHE_Interpolation_Body; call site feature_tracker.cpp:269-275).
-    Pinned bit-exactly against cv2 4.13 in tests/test_oracle_frontend.py."""
+    """cv::createCLAHE(clip, Size(tiles, tiles))->apply(img) (OpenCV imgproc/clahe.cpp: CLAHE_CalcLut_Body +
+    CLAHE_Interpolation_Body; call site feature_tracker.cpp:269-275), incl. the border extension for frame sizes that are
+    not multiples of the tile grid: copyMakeBorder(src, ext, 0, tiles - h % tiles, 0, tiles - w % tiles, REFLECT_101) --
+    a dimension that already divides still receives `tiles` extra pixels.  Pinned bit-exactly against cv2 4.13 in
+    tests/test_oracle_frontend.py."""
     h, w = img.shape
-    assert h % tiles == 0 and w % tiles == 0
-    th, tw = h // tiles, w // tiles
+    if h % tiles == 0 and w % tiles == 0:
+        ext = img
+    else:
+        eh, ew = h + (tiles - h % tiles), w + (tiles - w % tiles)
+        ry, rx = np.arange(eh), np.arange(ew)
+        ry = np.where(ry >= h, 2 * h - 2 - ry, ry); rx = np.where(rx >= w, 2 * w - 2 - rx, rx)      # REFLECT_101
+        ext = img[ry][:, rx]
+    th, tw = ext.shape[0] // tiles, ext.shape[1] // tiles
     tot = th * tw
     lut_scale = np.float32(255.0) / np.float32(tot)
     cl = max(int(clip * tot / 256), 1)
     luts = np.zeros((tiles, tiles, 256), np.uint8)
     for ty in range(tiles):
         for tx in range(tiles):
-            hist = np.bincount(img[ty * th:(ty + 1) * th, tx * tw:(tx + 1) * tw].ravel(), minlength=256).astype(np.int64)
+            hist = np.bincount(ext[ty * th:(ty + 1) * th, tx * tw:(tx + 1) * tw].ravel(), minlength=256).astype(np.int64)
             clipped = int(np.maximum(hist - cl, 0).sum())
             hist = np.minimum(hist, cl)
             batch = clipped // 256

@@ -157,6 +157,26 @@ def test_odd_frame_size_three_levels():
     assert n == 7 and out.n > 60
 
 
+def test_clahe_on_a_frame_size_that_needs_padding():
+    """EQUALIZE at 336x250: rows are not a multiple of the 8x8 tile grid, so OpenCV extends the frame (REFLECT_101,
+    8 extra columns and 6 extra rows) before cutting tiles; the device path must follow bit-exactly."""
+    cam = synth.CamModel(fx=320.0, fy=320.0, cx=168.0, cy=125.0, width=336, height=250)
+    seq = synth.Sequence(31, cam)
+    cfg = binding.default_config(row=250, col=336, fx=320.0, fy=320.0, cx=168.0, cy=125.0, use_ransac=0, equalize=1,
+                                 lk_max_level=2, max_cnt=120, min_dist=15)
+    h = binding.Handle(cfg, 1, 0)
+    ref = FeatureTrackerRef(FrontendConfig(row=250, col=336, fx=320.0, fy=320.0, cx=168.0, cy=125.0, use_ransac=0, equalize=1,
+                                           lk_max_level=2, max_cnt=120, min_dist=15))
+    for k in range(5):
+        gray = (seq.frame(k)[1].astype(np.float32) * 0.4 + 10).astype(np.uint8)
+        R = seq.relative_R(k)
+        out = h.read_image(0, gray, seq.time(k), R, pub=(k % 3 == 0))
+        ref.read_image(gray, seq.time(k), R, pub_this_frame=(k % 3 == 0))
+        check_frame(k, out, ref)
+    assert out.n > 50
+    h.close()
+
+
 def test_rgb_ingest_equals_gray_path():
     """RGB8 payload: device-side cvtColor(RGB2GRAY) then the same pipeline."""
     for k, out, ref in run_pair({}, 5, 31, rgb=True):

@@ -60,10 +60,12 @@ def test_fast_bit_exact(rect):
         assert got == S.fast_detect(roi, mask=m)
 
 
-@pytest.mark.parametrize("shape,seed", [((480, 640), 1), ((240, 320), 2), ((720, 1280), 3), ((480, 640), 4), ((64, 64), 5)])
+@pytest.mark.parametrize("shape,seed", [((480, 640), 1), ((240, 320), 2), ((720, 1280), 3), ((480, 640), 4), ((64, 64), 5),
+                                        ((250, 336), 6), ((483, 640), 7), ((480, 644), 8), ((77, 85), 9)])
 def test_clahe_bit_exact(shape, seed):
     """EQUALIZE: the numpy spec of cv::createCLAHE(3.0, Size(8, 8)) equals the real OpenCV, incl. a dark low-contrast frame
-    (heavy clipping + residual redistribution) and a frame of constant blocks."""
+    (heavy clipping + residual redistribution), a frame of constant blocks, and sizes that are not multiples of the 8x8 tile
+    grid (OpenCV's REFLECT_101 extension, which adds a full tile row/column to a dimension that already divides)."""
     img = tex(*shape, seed=seed)
     if seed == 4:
         img = (img.astype(np.float32) * 0.3 + 20).astype(np.uint8)

@@ -79,8 +79,6 @@ static int build_front_cfg(const VrfConfig &cfg, FrontCfg &fc)
 {
     memset(&fc, 0, sizeof(fc));
     if (cfg.row < 64 || cfg.col < 64 || (cfg.col & 15)) return VRF_ERR_ARG;   // uint4 row access
-    // CLAHE: OpenCV pads frames whose size is not a multiple of the 8x8 tile grid; that variant is not built
-    if (cfg.equalize && ((cfg.row & 7) || (cfg.col & 7))) return VRF_ERR_UNSUPPORTED;
     if (cfg.max_cnt <= 0 || cfg.max_cnt > VRF_CAP / 2 || cfg.min_dist < 1) return VRF_ERR_ARG;
     fc.rows = cfg.row; fc.cols = cfg.col;
     int maxLevel = cfg.lk_max_level < 0 ? (cfg.use_imu ? 1 : 3) : cfg.lk_max_level;

@@ -93,8 +93,8 @@ k_ingest(FrontCfg c, const SeqCall *calls, int ncalls, FrontDev d, const uint8_t
 
 // ---------------------------------------------------------------------------
 // EQUALIZE: cv::createCLAHE(3.0, Size(8, 8))->apply(img) (feature_tracker.cpp:269-275; OpenCV imgproc/clahe.cpp,
-// restated bit-exactly in oracle/frontend_spec.py::clahe and pinned against cv2 there).  Frame sizes are
-// multiples of the 8x8 tile grid (enforced at create), so no border padding is involved.
+// restated bit-exactly in oracle/frontend_spec.py::clahe and pinned against cv2 there), incl. OpenCV's border
+// extension for frame sizes that are not multiples of the 8x8 tile grid.
 //   k_clahe_lut   one CTA per (tile, frame): 256-bin histogram in shared memory, clip at
 //                 int(3.0 * tile_pixels / 256), uniform redistribution + the strided residual, prefix sum,
 //                 lut[i] = cvRound(float(sum_i) * (255.f / tile_pixels)).
@@ -102,6 +102,16 @@ k_ingest(FrontCfg c, const SeqCall *calls, int ncalls, FrontDev d, const uint8_t
 //                 operation order, in place on pyramid level 0 (reads and writes the same byte only).
 // Both are pure image scans: WH bytes read (+ WH written by the second) per frame.
 // ---------------------------------------------------------------------------
+// tile size of the 8x8 grid.  Frames whose size is not a multiple of 8 are extended like OpenCV does:
+// copyMakeBorder(src, ext, 0, 8 - rows % 8, 0, 8 - cols % 8, BORDER_REFLECT_101) -- note the full 8 extra columns (rows)
+// when only the other dimension needs padding -- and the tiles are cut from the extended frame.
+__device__ __forceinline__ void clahe_tiles(const FrontCfg &c, int &th, int &tw, bool &padded)
+{
+    padded = (c.rows & 7) || (c.cols & 7);
+    const int eh = padded ? c.rows + (8 - (c.rows & 7)) : c.rows, ew = padded ? c.cols + (8 - (c.cols & 7)) : c.cols;
+    th = eh >> 3; tw = ew >> 3;
+}
+
 __global__ void __launch_bounds__(256)
 k_clahe_lut(FrontCfg c, const SeqCall *calls, FrontDev d)
 {
@@ -111,12 +121,21 @@ k_clahe_lut(FrontCfg c, const SeqCall *calls, FrontDev d)
     const int t = threadIdx.x;
     const SeqCall call = calls[blockIdx.y];
     const uint8_t *img = d.pyr[call.buf_cur] + (size_t)call.seq * c.pyr_bytes;
-    const int th = c.rows >> 3, tw = c.cols >> 3, pitch = c.lp[0];
+    int th, tw;
+    bool padded;
+    clahe_tiles(c, th, tw, padded);
+    const int pitch = c.lp[0];
     const int ty = blockIdx.x >> 3, tx = blockIdx.x & 7;
     const uint8_t *tile = img + (size_t)(ty * th) * pitch + tx * tw;
     s_hist[t] = 0;
     __syncthreads();
-    if ((tw & 3) == 0) {
+    if (padded) {
+        for (int i = t; i < th * tw; i += 256) {
+            const int y = i / tw, x = i - y * tw;
+            const int sy = reflect101(ty * th + y, c.rows), sx = reflect101(tx * tw + x, c.cols);
+            atomicAdd(&s_hist[__ldg(img + (size_t)sy * pitch + sx)], 1);
+        }
+    } else if ((tw & 3) == 0) {
         const int wpr = tw >> 2;
         for (int i = t; i < th * wpr; i += 256) {
             const int y = i / wpr, xw = i - y * wpr;
@@ -171,7 +190,10 @@ k_clahe_apply(FrontCfg c, const SeqCall *calls, FrontDev d)
     const SeqCall call = calls[blockIdx.y];
     uint8_t *img = d.pyr[call.buf_cur] + (size_t)call.seq * c.pyr_bytes;
     const uint8_t *lut = d.clahe_lut + (size_t)call.seq * 64 * 256;
-    const int th = c.rows >> 3, tw = c.cols >> 3, pitch = c.lp[0];
+    int th, tw;
+    bool padded;
+    clahe_tiles(c, th, tw, padded);
+    const int pitch = c.lp[0];
     const float inv_tw = 1.0f / (float)tw, inv_th = 1.0f / (float)th;
     const int wpr = c.cols >> 2;                            // 4 pixels per thread
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < c.rows * wpr; i += gridDim.x * blockDim.x) {
