@@ -35,11 +35,43 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "vins-rgbd-fast_b200"))
 
-W, H = 640, 480
-A_FRAME = 5 * W * H           # RGB8 + depth16 read once per frame (SURVEY.md section 8d)
 PUB_EVERY = 3                 # freq 10 Hz / 30 Hz input
 N_DISTINCT = 8                # distinct rendered base sequences (replicated with phase offsets)
 T_FRAMES = 12                 # frames per base sequence, played ping-pong
+
+# Workloads = the BASELINE.json configs that run on a GPU.  `c3` (configs[1]+[2]) is the one the
+# metric is quoted on and the default; `c4` / `c5` are configs[3] / configs[4] with their per-GPU share of sequences.
+CONFIGS = {
+    "c3": dict(W=640, H=480, fx=600.0, max_cnt=150, min_dist=25, lk_max_level=2, seqs=444, ba_landmarks=150,
+               label="BASELINE configs[1]+[2]: 640x480 RGB-D streams (RGB8 + 16UC1 depth), 150 feats, 3-level pyramid LK"),
+    "c4": dict(W=1280, H=720, fx=900.0, max_cnt=500, min_dist=30, lk_max_level=3, seqs=16, ba_landmarks=500,
+               label="BASELINE configs[3]: 1280x720 RGB-D streams (RGB8 + 16UC1 depth), 500 feats, 4-level pyramid LK, "
+                     "64 sequences over 4 GPUs = 16 per GPU"),
+    "c5": dict(W=640, H=480, fx=600.0, max_cnt=300, min_dist=25, lk_max_level=1, seqs=32, ba_landmarks=300,
+               label="BASELINE configs[4]: 640x480 RGB-D streams (RGB8 + 16UC1 depth), 300 feats, reference-default 2-level LK, "
+                     "full VIO incl. marginalization, 256 sequences over 8 GPUs = 32 per GPU"),
+}
+CFG = dict(CONFIGS["c3"], name="c3")
+METRIC = "RGB-D VIO frames/sec (640x480, 10-KF BA)"
+W, H = CFG["W"], CFG["H"]
+A_FRAME = 5 * W * H           # RGB8 + depth16 read once per frame (SURVEY.md section 8d)
+BA_LANDMARKS = CFG["ba_landmarks"]
+
+
+def select_config(name):
+    """Bind the module-level workload parameters to one of CONFIGS (before anything is rendered)."""
+    global CFG, W, H, A_FRAME, BA_LANDMARKS, WORKLOAD, METRIC
+    CFG = dict(CONFIGS[name]); CFG["name"] = name
+    W, H = CFG["W"], CFG["H"]
+    A_FRAME = 5 * W * H
+    BA_LANDMARKS = CFG["ba_landmarks"]
+    WORKLOAD = workload_text()
+    METRIC = "RGB-D VIO frames/sec (%dx%d, 10-KF BA)" % (W, H)
+
+
+def cam_model():
+    from vrf_b200 import synth
+    return synth.CamModel(fx=CFG["fx"], fy=CFG["fx"], cx=W / 2.0, cy=H / 2.0, width=W, height=H)
 
 
 def load_peaks():
@@ -105,7 +137,7 @@ def render_inputs(n_distinct, t_frames):
     from vrf_b200 import synth
     base = []
     for i in range(n_distinct):
-        s = synth.Sequence(1234 + i)
+        s = synth.Sequence(1234 + i, cam_model())
         rgb = np.zeros((t_frames, H, W, 3), np.uint8)
         dep = np.zeros((t_frames, H, W), np.uint16)
         gray = np.zeros((t_frames, H, W), np.uint8)
@@ -161,95 +193,110 @@ def aggregate_timing(ms_local, frames_local, dist_mod, device=None):
 
 
 def run_reference(args):
-    """CPU arm: the cv2-backed front-end oracle + the C back-end oracle on all host cores: one independent
-    sequence per worker process (cv2 threads = 1 each; BA single-threaded like Ceres in the reference,
-    estimator.cpp:1351).  Workers are persistent; a step = every worker tracks `ref_frames` frames of its
-    sequence from a fresh tracker (bounded sample of the workload) and solves one BA window per publish frame."""
+    """CPU arm: the cv2-backed front-end oracle + the C back-end oracle on all host cores.  One independent sequence
+    per persistent worker process (cv2 threads = 1 each; BA single-threaded like Ceres in the reference,
+    estimator.cpp:1351).  The trackers stay alive across steps exactly like the GPU arm's sequences (steady state:
+    ping-pong playback of the same rendered frames, same publish phase rule), a step = every worker advances its sequence by
+    `ref_frames` frames (bounded sample of the workload) and solves one BA window (+ marginalization) per publish frame."""
     import multiprocessing as mp
     cores = os.cpu_count() or 1
-    frames_per_worker = max(3, min(T_FRAMES * 2, args.ref_frames))
+    frames_per_worker = max(3, args.ref_frames)
     steps = max(1, args.steps)
     ctx = mp.get_context("fork")
-    t_all = []
-    with ctx.Pool(cores, initializer=_ref_init) as pool:
-        pool.map(_ref_prepare, [1234 + (i % N_DISTINCT) for i in range(cores)], chunksize=1)
-        for it in range(args.warmup + steps):
-            res = pool.map(_ref_step, [frames_per_worker] * cores, chunksize=1)
-            if it >= args.warmup:
-                t_all.append(max(r[1] for r in res))       # workers run concurrently; the slowest bounds the step
+    workers = []
+    for i in range(cores):
+        parent, child = ctx.Pipe()
+        pr = ctx.Process(target=_ref_worker, args=(child, 1234 + (i % N_DISTINCT), i, CFG["name"]), daemon=True)
+        pr.start()
+        workers.append((pr, parent))
+    for _, c_ in workers:
+        assert c_.recv() == "ready"
+    t_all, t_front, t_ba, n_ba = [], 0.0, 0.0, 0
+    for it in range(args.warmup + steps):
+        for _, c_ in workers:
+            c_.send(frames_per_worker)
+        res = [c_.recv() for _, c_ in workers]
+        if it >= args.warmup:
+            t_all.append(max(r[0] for r in res))       # workers run concurrently; the slowest bounds the step
+            t_front += sum(r[1] for r in res); t_ba += sum(r[2] for r in res); n_ba += sum(r[3] for r in res)
+    for pr, c_ in workers:
+        c_.send(None)
+        pr.join(timeout=5)
     frames = cores * frames_per_worker
     sec = float(np.mean(t_all))
     fps = frames / sec
+    nfr = frames * steps
+    sample = (f"{cores} persistent workers x {frames_per_worker} frames/step (steady state, trackers kept alive): cv2 4.13 (real OpenCV) "
+              f"RGB2GRAY+FAST+PyrLK+RANSAC with vectorised numpy glue, depth lookup, C restatement of the Ceres problem for the BA "
+              f"(1 thread per solve); front end {t_front / nfr * 1e3:.2f} ms/frame, BA+marginalization {t_ba / max(n_ba, 1) * 1e3:.1f} ms/window "
+              f"({n_ba / nfr:.2f} windows/frame)")
     line = {
-        "impl": "reference", "metric": "RGB-D VIO frames/sec (640x480, 10-KF BA)", "value": fps,
+        "impl": "reference", "metric": METRIC, "value": fps,
         "unit": "frames/s", "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup,
         "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u8/f32 (cv2), f64 (BA)", "data": "synthetic",
         "config": {"workload": WORKLOAD, "sample": f"{cores} sequences x {frames_per_worker} frames per step"},
-        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
-                         "sample": f"{cores} workers x {frames_per_worker} frames/step: cv2 4.13 (real OpenCV) RGB2GRAY+FAST+PyrLK+RANSAC with python glue, depth lookup, "
-                                   f"C restatement of the Ceres problem for the BA (1 thread per solve)"},
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample,
+                         "front_ms_per_frame": t_front / nfr * 1e3, "ba_ms_per_window": t_ba / max(n_ba, 1) * 1e3},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     emit(line)
 
 
-_REF = {}
-
-
-def _ref_init():
+def _ref_worker(conn, seed, widx, cfg_name):
+    """One persistent CPU worker = one sequence: renders its frames and builds its BA window once (not timed), then
+    serves `n`-frame steps."""
     import cv2
     cv2.setNumThreads(1)
-
-
-def _ref_prepare(seed):
-    """Render this worker's frames and build its BA window once (not timed)."""
+    select_config(cfg_name)
     from oracle import ba_ref
+    from oracle.frontend_ref import FeatureTrackerRef, FrontendConfig, decode_depth, depth_lookup
     from vrf_b200 import ba_problem as BP, synth
-    s = synth.Sequence(seed)
+    s = synth.Sequence(seed, cam_model())
     frames = [s.frame(k) for k in range(T_FRAMES)]          # (rgb, gray, depth16) as the two camera topics deliver them
     Rf = np.stack([s.relative_R(k) for k in range(T_FRAMES)])
     cfg = ba_config()
     sim = BP.WindowSimulator(seed, cfg, n_landmarks=BA_LANDMARKS)
     sol = ba_ref.solve(cfg, sim.window(0)); sim.commit(0, sol)
-    _REF.update(frames=frames, Rf=Rf, cfg=cfg, pb=sim.window(1))
-    return True
-
-
-def _ref_step(n):
-    import cv2
-    from oracle import ba_ref
-    from oracle.frontend_ref import FeatureTrackerRef, FrontendConfig, decode_depth, depth_lookup
-    if "frames" not in _REF:
-        _ref_prepare(1234 + os.getpid() % N_DISTINCT)
-    frames, Rf, cfg, pb = _REF["frames"], _REF["Rf"], _REF["cfg"], _REF["pb"]
-    ft = FeatureTrackerRef(FrontendConfig(lk_max_level=2, use_ransac=int(os.environ.get("VRF_BENCH_RANSAC", "1"))))
-    t0 = time.perf_counter()
-    for step in range(n):
-        idx, pidx = frame_plan(step, len(frames))
-        R = np.eye(3) if step == 0 else rel_rotation(Rf, idx, pidx)
-        pub = (step % PUB_EVERY == 0)
-        rgb, _, dep = frames[idx]
-        gray = cv2.cvtColor(rgb, cv2.COLOR_RGB2GRAY)        # cv_bridge::toCvCopy(MONO8), estimator_nodelet.cpp:292-307
-        ft.read_image(gray, 1.0 + step / 30.0, R, pub_this_frame=pub)
-        if pub:
-            depth_lookup(decode_depth(dep, H, W), ft.cur_pts, cfg.depth_min_dist)   # :512-534, feature_manager.cpp:71-80
-            ba_ref.solve(cfg, pb)          # Estimator::optimization: solve + marginalization, 1 thread (Ceres num_threads = 1)
-    return len(ft.ids), time.perf_counter() - t0
-
-
-BA_LANDMARKS = 150
+    pb = sim.window(1)
+    ft = FeatureTrackerRef(FrontendConfig(row=H, col=W, max_cnt=CFG["max_cnt"], min_dist=CFG["min_dist"], lk_max_level=CFG["lk_max_level"],
+                                          fx=CFG["fx"], fy=CFG["fx"], cx=W / 2.0, cy=H / 2.0,
+                                          use_ransac=int(os.environ.get("VRF_BENCH_RANSAC", "1"))))
+    step = 0
+    phase = widx % PUB_EVERY
+    conn.send("ready")
+    while True:
+        n = conn.recv()
+        if n is None:
+            return
+        t0 = time.perf_counter()
+        t_ba, n_ba = 0.0, 0
+        for _ in range(n):
+            idx, pidx = frame_plan(step + phase, len(frames))
+            R = np.eye(3) if step == 0 else rel_rotation(Rf, idx, pidx)
+            pub = ((step + phase) % PUB_EVERY == 0)
+            rgb, _, dep = frames[idx]
+            gray = cv2.cvtColor(rgb, cv2.COLOR_RGB2GRAY)        # cv_bridge::toCvCopy(MONO8), estimator_nodelet.cpp:292-307
+            ft.read_image(gray, 1.0 + step / 30.0, R, pub_this_frame=pub)
+            if pub:
+                depth_lookup(decode_depth(dep, H, W), ft.cur_pts, cfg.depth_min_dist)   # :512-534, feature_manager.cpp:71-80
+                tb = time.perf_counter()
+                ba_ref.solve(cfg, pb)          # Estimator::optimization: solve + marginalization, 1 thread (Ceres num_threads = 1)
+                t_ba += time.perf_counter() - tb; n_ba += 1
+            step += 1
+        tot = time.perf_counter() - t0
+        conn.send((tot, tot - t_ba, t_ba, n_ba))
 
 
 def ba_config():
     """VrfConfig without touching CUDA (the reference arm must not create a context)."""
     from vrf_b200 import binding as B
     cfg = B.VrfConfig()
-    cfg.row, cfg.col, cfg.max_cnt, cfg.min_dist = H, W, 150, 25
-    cfg.num_grid_rows, cfg.num_grid_cols, cfg.use_imu, cfg.lk_max_level = 7, 8, 1, 2
+    cfg.row, cfg.col, cfg.max_cnt, cfg.min_dist = H, W, CFG["max_cnt"], CFG["min_dist"]
+    cfg.num_grid_rows, cfg.num_grid_cols, cfg.use_imu, cfg.lk_max_level = 7, 8, 1, CFG["lk_max_level"]
     cfg.use_ransac = int(os.environ.get("VRF_BENCH_RANSAC", "1"))
     cfg.f_threshold, cfg.focal_length = 1.0, 460.0
-    cfg.fx = cfg.fy = 600.0; cfg.cx, cfg.cy = 320.0, 240.0
+    cfg.fx = cfg.fy = CFG["fx"]; cfg.cx, cfg.cy = W / 2.0, H / 2.0
     cfg.k1, cfg.k2, cfg.p1, cfg.p2 = 0.1, -0.2, 1e-3, 1e-3
     cfg.num_iterations, cfg.fix_depth, cfg.depth_max_dist, cfg.g_norm = 8, 0, 10.0, 9.81
     cfg.acc_n, cfg.acc_w, cfg.gyr_n, cfg.gyr_w = 0.1, 0.001, 0.01, 0.0001
@@ -257,9 +304,13 @@ def ba_config():
     return cfg
 
 
-WORKLOAD = ("BASELINE configs[1]+[2]: 640x480 RGB-D streams (RGB8 + 16UC1 depth), 150 feats, 3-level pyramid LK, 7x8 grid FAST + RANSAC, "
-            "publish every 3rd frame (freq 10 Hz @ 30 Hz) with per-feature depth lookup; every publish frame runs one 10-keyframe sliding-window BA "
-            "(150 landmarks, ~1000 projection factors, 10 IMU factors, prior n=75, 8 dogleg iterations) + marginalization")
+def workload_text():
+    return (CFG["label"] + ", 7x8 grid FAST + RANSAC, publish every 3rd frame (freq 10 Hz @ 30 Hz) with per-feature depth lookup; "
+            "every publish frame runs one 10-keyframe sliding-window BA (%d landmarks, 10 IMU factors, prior n=75, "
+            "<= 8 dogleg iterations) + marginalization" % CFG["ba_landmarks"])
+
+
+WORKLOAD = workload_text()
 
 
 _REAL_STDOUT = None
@@ -290,7 +341,9 @@ def main():
     ap.add_argument("--steps", type=int, default=60)
     ap.add_argument("--warmup", type=int, default=6)
     ap.add_argument("--impl", default="ours")
-    ap.add_argument("--seqs", type=int, default=444, help="sequences per GPU (444 => 148 concurrent BA windows = one CTA per SM)")
+    ap.add_argument("--config", default="c3", choices=sorted(CONFIGS), help="workload: c3 = BASELINE configs[1]+[2] (default, the metric's config), "
+                    "c4 = configs[3] (1280x720, 500 feats, 4 levels, 16 seqs/GPU), c5 = configs[4] (300 feats, full VIO, 32 seqs/GPU)")
+    ap.add_argument("--seqs", type=int, default=0, help="sequences per GPU (default: the config's; c3: 444 => 148 concurrent BA windows = one CTA per SM)")
     ap.add_argument("--ref-frames", type=int, default=12, help="frames per worker per step of the reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--quick", action="store_true", help="profiling runs: skip the e2e arm and the CPU baseline")
@@ -298,6 +351,9 @@ def main():
     args = ap.parse_args()
     if args.impl != "reference":
         args.warmup = max(args.warmup, 3)
+    select_config(args.config)
+    if args.seqs <= 0:
+        args.seqs = CFG["seqs"]
 
     quiet_stdout()
     rank = int(os.environ.get("RANK", "0"))
@@ -316,7 +372,8 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu_baseline and not args.quick:
         try:
             out = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "3",
-                                  "--warmup", "1", "--ref-frames", "24"], capture_output=True, text=True, timeout=600)
+                                  "--warmup", "1", "--ref-frames", "24" if W * H <= 640 * 480 else "9", "--config", args.config],
+                                 capture_output=True, text=True, timeout=900)
             cpu_base = json.loads(out.stdout.strip().splitlines()[-1])["cpu_baseline"]
         except Exception as e:           # reported, never silently replaced
             cpu_base = {"value": None, "unit": "frames/s", "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {e}"}
@@ -617,7 +674,7 @@ def main():
 
     if rank == 0:
         line = {
-            "metric": "RGB-D VIO frames/sec (640x480, 10-KF BA)", "value": value, "unit": "frames/s",
+            "metric": METRIC, "value": value, "unit": "frames/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total_max / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/i32/f32 (LK), f64 (camera model)",
             "data": f"synthetic: {nb} rendered base sequences x {T_FRAMES} frames (ping-pong), replicated to {S} sequences/GPU with phase offsets",

@@ -145,6 +145,16 @@ class PinholeCamera:
             y = y + dy
         return self.fx * x + self.cx, self.fy * y + self.cy
 
+    # The three functions above are written with elementwise float64 arithmetic only, so they accept numpy
+    # arrays as well as Python floats and give bit-identical results either way (IEEE double, no contraction);
+    # the tracker below calls them on whole point arrays so that the timed CPU baseline is OpenCV + arithmetic,
+    # not interpreter loops.  tests/test_oracle_frontend.py pins array == per-point evaluation.
+    def lift_projective_pts(self, pts):
+        """liftProjective of an (n, 2) float32 point array -> (x, y) float64 arrays (z == 1)."""
+        p = np.asarray(pts, np.float32).reshape(-1, 2).astype(np.float64)
+        x, y, _ = self.lift_projective(p[:, 0], p[:, 1])
+        return x, y
+
 
 class FeatureTrackerRef:
     def __init__(self, cfg: FrontendConfig):
@@ -163,8 +173,8 @@ class FeatureTrackerRef:
         self.pts_velocity = np.zeros((0, 2), np.float32)
         self.ids = []
         self.track_cnt = []
-        self.cur_un_pts_map = {}
-        self.prev_un_pts_map = {}
+        self.cur_un_pts_map = None       # (sorted ids, points): the std::map<int, Point2f> of the reference
+        self.prev_un_pts_map = None
         self.cur_time = 0.0
         self.prev_time = 0.0
         self.mask = None
@@ -214,14 +224,18 @@ class FeatureTrackerRef:
 
     # feature_tracker.cpp:595-608
     def predict_pts_in_next_frame(self, R):
-        out = np.zeros((len(self.cur_pts), 2), np.float32)
-        for i, p in enumerate(self.cur_pts):
-            x, y, z = self.cam.lift_projective(float(p[0]), float(p[1]))
-            P = R @ np.array([x, y, z], np.float64)
-            u, v = self.cam.space_to_plane(P[0], P[1], P[2])
-            out[i, 0] = u
-            out[i, 1] = v
-        self.predict_pts = out
+        x, y = self.cam.lift_projective_pts(self.cur_pts)
+        xyz = np.stack([x, y, np.ones_like(x)], 1)
+        # batched (3,3)@(3,1): the same product kernel as the per-point `R @ [x, y, z]` (pinned in the tests)
+        P = np.matmul(np.asarray(R, np.float64)[None], xyz[:, :, None])[:, :, 0] if len(x) else np.zeros((0, 3))
+        u, v = self.cam.space_to_plane(P[:, 0], P[:, 1], P[:, 2])
+        self.predict_pts = np.stack([u, v], 1).astype(np.float32)
+
+    def in_border_pts(self, pts):
+        """inBorder for an (n, 2) array (cvRound = rint, half to even)."""
+        x = np.rint(pts[:, 0]).astype(np.int64)
+        y = np.rint(pts[:, 1]).astype(np.int64)
+        return (1 <= x) & (x < self.cfg.col - 1) & (1 <= y) & (y < self.cfg.row - 1)
 
     # feature_tracker.cpp:105-171 (deterministic mask-snapshot semantics)
     def grid_detect(self, grid_id, mask_snapshot):
@@ -301,13 +315,10 @@ class FeatureTrackerRef:
         self.last_ransac_status = None
         if len(self.forw_pts) >= 8 and c.use_ransac:
             n = len(self.cur_pts)
-            un_cur = np.zeros((n, 2), np.float32)
-            un_forw = np.zeros((n, 2), np.float32)
-            for i in range(n):
-                x, y, z = self.cam.lift_projective(float(self.cur_pts[i, 0]), float(self.cur_pts[i, 1]))
-                un_cur[i] = (c.focal_length * x / z + c.col / 2.0, c.focal_length * y / z + c.row / 2.0)
-                x, y, z = self.cam.lift_projective(float(self.forw_pts[i, 0]), float(self.forw_pts[i, 1]))
-                un_forw[i] = (c.focal_length * x / z + c.col / 2.0, c.focal_length * y / z + c.row / 2.0)
+            x, y = self.cam.lift_projective_pts(self.cur_pts)
+            un_cur = np.stack([c.focal_length * x / 1.0 + c.col / 2.0, c.focal_length * y / 1.0 + c.row / 2.0], 1).astype(np.float32)
+            x, y = self.cam.lift_projective_pts(self.forw_pts)
+            un_forw = np.stack([c.focal_length * x / 1.0 + c.col / 2.0, c.focal_length * y / 1.0 + c.row / 2.0], 1).astype(np.float32)
             self.last_un_cur, self.last_un_forw = un_cur, un_forw
             _, status = cv2.findFundamentalMat(un_cur, un_forw, cv2.FM_RANSAC, c.f_threshold, 0.99)
             if status is None:
@@ -319,24 +330,23 @@ class FeatureTrackerRef:
     # feature_tracker.cpp:542-593
     def undistorted_points(self):
         n = len(self.cur_pts)
-        self.cur_un_pts = np.zeros((n, 2), np.float32)
-        self.cur_un_pts_map = {}
-        for i in range(n):
-            x, y, z = self.cam.lift_projective(float(self.cur_pts[i, 0]), float(self.cur_pts[i, 1]))
-            v = (np.float32(x / z), np.float32(y / z))
-            self.cur_un_pts[i] = v
-            if self.ids[i] not in self.cur_un_pts_map:     # std::map::insert keeps the first
-                self.cur_un_pts_map[self.ids[i]] = v
+        x, y = self.cam.lift_projective_pts(self.cur_pts)
+        self.cur_un_pts = np.stack([x / 1.0, y / 1.0], 1).astype(np.float32)      # (x / z, y / z) with z == 1
+        ids = np.asarray(self.ids, np.int64).reshape(-1)
+        # cur_un_pts_map: std::map::insert keeps the first entry of an id (only -1 can repeat)
+        uniq, first = np.unique(ids, return_index=True) if n else (np.zeros(0, np.int64), np.zeros(0, np.int64))
         vel = np.zeros((n, 2), np.float32)
-        if self.prev_un_pts_map:
+        if self.prev_un_pts_map is not None and len(self.prev_un_pts_map[0]):
             dt = self.cur_time - self.prev_time
-            for i in range(n):
-                if self.ids[i] != -1 and self.ids[i] in self.prev_un_pts_map:
-                    pv = self.prev_un_pts_map[self.ids[i]]
-                    vel[i, 0] = np.float32(np.float64(np.float32(self.cur_un_pts[i, 0] - pv[0])) / dt)
-                    vel[i, 1] = np.float32(np.float64(np.float32(self.cur_un_pts[i, 1] - pv[1])) / dt)
+            pids, ppts = self.prev_un_pts_map
+            pos = np.searchsorted(pids, ids)
+            pos_c = np.minimum(pos, len(pids) - 1)
+            hit = (ids != -1) & (pids[pos_c] == ids)
+            d = (self.cur_un_pts[hit] - ppts[pos_c[hit]]).astype(np.float32)
+            vel[hit] = (d.astype(np.float64) / dt).astype(np.float32)
         self.pts_velocity = vel
-        self.prev_un_pts_map = dict(self.cur_un_pts_map)
+        self.cur_un_pts_map = (uniq, self.cur_un_pts[first])                      # sorted ids -> point
+        self.prev_un_pts_map = self.cur_un_pts_map
 
     # feature_tracker.cpp:485-495 + estimator_nodelet.cpp:324-330
     def update_ids(self):
@@ -378,14 +388,10 @@ class FeatureTrackerRef:
             status = status.ravel().copy()
             self.last_lk_pts = self.forw_pts.copy()
             self.last_lk_status = status.copy()
-            unstable = []
-            for i in range(len(self.forw_pts)):
-                ib = self.in_border(self.forw_pts[i])
-                if not status[i] and ib:
-                    unstable.append(self.forw_pts[i])
-                elif status[i] and not ib:
-                    status[i] = 0
-            self.unstable_pts = np.array(unstable, np.float32).reshape(-1, 2)
+            ib = self.in_border_pts(self.forw_pts)
+            ok = status.astype(bool)
+            self.unstable_pts = self.forw_pts[~ok & ib].astype(np.float32).reshape(-1, 2)
+            status[ok & ~ib] = 0
             self.last_status = status.copy()
             self._reduce(status)
         self.track_cnt = [n + 1 for n in self.track_cnt]
@@ -397,15 +403,12 @@ class FeatureTrackerRef:
             n_max_cnt = c.max_cnt - len(self.forw_pts)
             if n_max_cnt > 0:
                 R, C = c.num_grid_rows, c.num_grid_cols
-                self.grids_track_num = [0] * (R * C)
-                for p in self.forw_pts:
-                    col_id = int(p[0]) // self.grid_width
-                    row_id = int(p[1]) // self.grid_height
-                    if col_id == C:
-                        col_id -= 1
-                    if row_id == R:
-                        row_id -= 1
-                    self.grids_track_num[col_id + C * row_id] += 1
+                fp = self.forw_pts.reshape(-1, 2)
+                col_id = fp[:, 0].astype(np.int64) // self.grid_width        # (int)p.x truncates; coordinates are > 0 here
+                row_id = fp[:, 1].astype(np.int64) // self.grid_height
+                col_id[col_id == C] -= 1
+                row_id[row_id == R] -= 1
+                self.grids_track_num = np.bincount(col_id + C * row_id, minlength=R * C).astype(int).tolist()
                 grids_id = []
                 for i in range(R * C):
                     if self.grids_track_num[i] < self.grids_threshold and self.grids_texture_status[i]:
@@ -472,13 +475,8 @@ def depth_lookup(depth_img, cur_pts, depth_min_dist):
         pt_depth_mm = depth_img.at<unsigned short>((int)v, (int)u);  pt_depth_m = pt_depth_mm / 1000.0
         erase the feature iff 0 < pt_depth_m < DEPTH_MIN_DIST
     Returns (depth_mm u16 [n], keep u8 [n])."""
-    n = len(cur_pts)
-    mm = np.zeros(n, np.uint16)
-    keep = np.ones(n, np.uint8)
-    for j in range(n):
-        u, v = float(cur_pts[j][0]), float(cur_pts[j][1])
-        mm[j] = depth_img[int(v), int(u)]
-        d_m = float(mm[j]) / 1000.0
-        if 0 < d_m < depth_min_dist:
-            keep[j] = 0
+    p = np.asarray(cur_pts, np.float32).reshape(-1, 2)
+    mm = depth_img[p[:, 1].astype(np.int64), p[:, 0].astype(np.int64)].astype(np.uint16)
+    d_m = mm.astype(np.float64) / 1000.0
+    keep = np.where((0 < d_m) & (d_m < depth_min_dist), 0, 1).astype(np.uint8)
     return mm, keep

@@ -196,3 +196,33 @@ def test_depth_lookup_truncates_and_culls():
     mm, keep = depth_lookup(dep, pts, 0.3)
     assert mm.tolist() == [299, 300, 0, 4000]
     assert keep.tolist() == [0, 1, 1, 1]
+
+
+def test_vectorised_glue_equals_per_point_evaluation():
+    """The tracker restatement evaluates liftProjective / spaceToPlane / R*p / inBorder on whole point arrays (so that the
+    timed CPU baseline is not interpreter time); the array forms must be bit-identical to the per-point statements of
+    PinholeCamera.cc:450-543 and feature_tracker.cpp:96-103,595-608."""
+    from oracle.frontend_ref import FeatureTrackerRef, FrontendConfig, PinholeCamera, cv_round
+    cfg = FrontendConfig()
+    cam = PinholeCamera(cfg)
+    r = np.random.default_rng(5)
+    pts = np.stack([r.uniform(-5, 645, 400), r.uniform(-5, 485, 400)], 1).astype(np.float32)
+    pts[:8] = [[0.5, 0.5], [1.5, 2.5], [638.5, 478.5], [637.5, 477.5], [639.49, 10], [10, 479.49], [0.49, 3], [3, 0.51]]
+    x, y = cam.lift_projective_pts(pts)
+    for i in range(len(pts)):
+        xs, ys, _ = cam.lift_projective(float(pts[i, 0]), float(pts[i, 1]))
+        assert xs == x[i] and ys == y[i]
+    # R * [x, y, 1] and the re-projection
+    th = 0.01
+    R = np.array([[np.cos(th), -np.sin(th), 0.001], [np.sin(th), np.cos(th), -0.002], [-0.001, 0.002, 1.0]])
+    ft = FeatureTrackerRef(cfg)
+    ft.cur_pts = pts
+    ft.predict_pts_in_next_frame(R)
+    for i in range(len(pts)):
+        xs, ys, zs = cam.lift_projective(float(pts[i, 0]), float(pts[i, 1]))
+        P = R @ np.array([xs, ys, zs], np.float64)
+        u, v = cam.space_to_plane(P[0], P[1], P[2])
+        assert np.float32(u) == ft.predict_pts[i, 0] and np.float32(v) == ft.predict_pts[i, 1]
+    ib = ft.in_border_pts(pts)
+    for i in range(len(pts)):
+        assert bool(ib[i]) == ft.in_border(pts[i])

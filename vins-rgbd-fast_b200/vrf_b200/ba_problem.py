@@ -181,8 +181,11 @@ class WindowSimulator:
         """new landmarks first seen at absolute frame k"""
         pc, Rc = self._cam(k)
         out = []
-        for _ in range(1000):
-            if len(out) >= 40:
+        # 40 new landmarks per keyframe fill windows of up to ~320 landmarks (the reference's 150-feature configs); larger
+        # windows (BASELINE configs[3]: 500 feats) spawn proportionally more
+        per_frame = 40 if self.n_landmarks <= 300 else -(-self.n_landmarks * 40 // 280)
+        for _ in range(25 * per_frame):
+            if len(out) >= per_frame:
                 break
             d = self.rng.uniform(1.5, 6.0)
             xy = self.rng.uniform([-0.5, -0.38], [0.5, 0.38])
