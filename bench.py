@@ -256,7 +256,7 @@ def _ref_worker(conn, seed, widx, cfg_name):
     frames = [s.frame(k) for k in range(T_FRAMES)]          # (rgb, gray, depth16) as the two camera topics deliver them
     Rf = np.stack([s.relative_R(k) for k in range(T_FRAMES)])
     cfg = ba_config()
-    sim = BP.WindowSimulator(seed, cfg, n_landmarks=BA_LANDMARKS)
+    sim = BP.WindowSimulator(seed, cfg, n_landmarks=BA_LANDMARKS, preintegrate=ba_ref.preintegrate)
     sol = ba_ref.solve(cfg, sim.window(0)); sim.commit(0, sol)
     pb = sim.window(1)
     ft = FeatureTrackerRef(FrontendConfig(row=H, col=W, max_cnt=CFG["max_cnt"], min_dist=CFG["min_dist"], lk_max_level=CFG["lk_max_level"],

@@ -10,6 +10,10 @@ sys.path.insert(0, os.path.join(ROOT, "vins-rgbd-fast_b200"))
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    # the seeded window simulator of the product package takes its IntegrationBase from the checker in the tests
+    from oracle import ba_ref
+    from vrf_b200 import ba_problem
+    ba_problem.DEFAULT_PREINTEGRATE = ba_ref.preintegrate
 
 
 def _has_gpu():

@@ -9,7 +9,8 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 from test_ba_gpu import make_cfg
 cfg = make_cfg()
 h = B.Handle(cfg, 1, 0)
-sim = BP.WindowSimulator(5, cfg, n_landmarks=150)
+from oracle import ba_ref as _br
+sim = BP.WindowSimulator(5, cfg, n_landmarks=150, preintegrate=_br.preintegrate)
 import ctypes as C
 for a in range(2):
     pb = sim.window(a)

@@ -255,3 +255,22 @@ def test_projection_td_factor_matches_oracle(td_constant, ex_constant, tr):
         assert (B.BLK_TD, 1) in kinds
         sim.commit(a, so)
     h.close()
+
+
+@pytest.mark.parametrize("n_landmarks", [300, 500])
+def test_window_chain_at_config_sizes(n_landmarks):
+    """BASELINE configs[4] / configs[3]: windows of 300 / 500 landmarks (1800 / 3000 projection factors), two consecutive
+    windows incl. the marginalization prior (estimator.cpp:1243-1302, :1376-1502)."""
+    cfg = make_cfg(max_cnt=n_landmarks)
+    h = B.Handle(cfg, 1, 0)
+    sim = BP.WindowSimulator(21 + n_landmarks, cfg, n_landmarks=n_landmarks)
+    for a in range(2):
+        pb = sim.window(a)
+        assert pb.M == n_landmarks
+        so = ba_ref.solve(cfg, pb)
+        sg = h.ba_solve(0, pb)
+        compare(sg, so, pb)
+        assert sg.c.has_new_prior == so.c.has_new_prior == 1
+        compare_prior(sg.new_prior, so.new_prior)
+        sim.commit(a, so)
+    h.close()

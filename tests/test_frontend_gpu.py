@@ -190,6 +190,27 @@ def test_1280x720_500_features():
         check_frame(k, out, ref)
 
 
+def test_1280x720_500_features_with_ransac():
+    """BASELINE configs[3] incl. rejectWithF on the publish frames (feature_tracker.cpp:441-473): 1280x720, 500 feats,
+    4 levels, min_dist 30; IDs / occupancy bit-exact over 7 frames (3 publish frames)."""
+    cam = synth.CamModel(fx=900.0, fy=900.0, cx=640.0, cy=360.0, width=1280, height=720)
+    n = 0
+    for k, out, ref in run_pair({"max_cnt": 500, "min_dist": 30, "lk_max_level": 3}, 7, 17, cam=cam, ransac=1):
+        check_frame(k, out, ref)
+        n += ref.last_ransac_status is not None
+    assert n >= 2 and out.n > 250
+
+
+def test_300_features_full_front_end():
+    """BASELINE configs[4]: 640x480, max_cnt 300 (grid threshold 5), reference-default 2-level LK with IMU prediction,
+    RANSAC on; 10 frames."""
+    n = 0
+    for k, out, ref in run_pair({"max_cnt": 300}, 10, 303, ransac=1):
+        check_frame(k, out, ref)
+        n += ref.last_ransac_status is not None
+    assert n >= 3 and out.n > 150
+
+
 def test_batch_equals_single():
     """Batched call over 3 independent sequences == three single-sequence calls."""
     cam = synth.CamModel()

@@ -59,14 +59,17 @@ def test_pingpong_plan_is_continuous():
 
 def test_gpu_arm_never_touches_the_oracle():
     """oracle/ is test infrastructure: bench.py's GPU arm (main) must not import it -- only the CPU legs
-    (run_reference / _ref_prepare / _ref_step, executed in child processes) may -- and the product package may only
-    reach it through the generator's explicit default (tests, CPU arm)."""
+    (run_reference / _ref_worker, executed in child processes) may -- and the product package never imports it."""
     import inspect
     import bench
     import re
     src = inspect.getsource(bench.main)
     assert not re.search(r"(from|import)\s+oracle", src)
-    for fn in (bench.run_reference, bench._ref_prepare, bench._ref_step):
+    for fn in (bench.run_reference, bench._ref_worker):
         assert fn.__module__ == "bench"
     import vrf_b200.binding as binding
     assert not re.search(r"(from|import)\s+oracle", inspect.getsource(binding))
+    import vrf_b200.ba_problem as ba_problem
+    import vrf_b200.synth as synth_mod
+    for mod in (ba_problem, synth_mod):
+        assert not re.search(r"(from|import)\s+oracle", inspect.getsource(mod))

@@ -129,6 +129,12 @@ def R_to_quat(R):
     return q
 
 
+# IntegrationBase implementation used when a WindowSimulator is built without an explicit `preintegrate` callback.  The
+# package itself never imports the checker: tests/conftest.py, the CPU arm of bench.py and __graft_entry__.smoke() install
+# the C oracle's here; the GPU arm passes the library's own vrf_imu_preintegrate_batch.
+DEFAULT_PREINTEGRATE = None
+
+
 class WindowSimulator:
     """Ground-truth trajectory + landmark pool -> a chain of 11-frame windows
     (what FeatureManager / processIMU would hand to optimization())."""
@@ -137,8 +143,8 @@ class WindowSimulator:
                  pix_noise=0.5, ric=None, tic=None, td_true=0.0, ex_constant=1, td_constant=1, ex_perturb=0.0, preintegrate=None):
         self.cfg = cfg
         # IntegrationBase for the generated IMU samples: preintegrate(samples, acc0, gyr0, ba, bg, cfg) -> VrfImuPreint.
-        # None = the C oracle (tests, CPU arm); bench.py's GPU arm passes the library's own vrf_imu_preintegrate_batch so
-        # that nothing under oracle/ is touched outside the checker legs.
+        # None = ba_problem.DEFAULT_PREINTEGRATE (installed by the checker legs); bench.py's GPU arm passes the library's
+        # own vrf_imu_preintegrate_batch so that nothing under oracle/ is touched outside the checker legs.
         self._preintegrate = preintegrate
         self.rng = np.random.default_rng(seed)
         self.traj = synth.Trajectory(seed, fps=1.0 / kf_dt, trans_per_frame=0.06, rot_deg_per_frame=1.5)
@@ -214,10 +220,10 @@ class WindowSimulator:
 
     def _preint(self, k0, k1, ba, bg):
         """IMU between absolute frames k0 -> k1 (processIMU: first sample initialises acc_0/gyr_0)."""
-        pre_fn = self._preintegrate
+        pre_fn = self._preintegrate or DEFAULT_PREINTEGRATE
         if pre_fn is None:
-            from oracle import ba_ref    # tests / CPU arm only
-            pre_fn = ba_ref.preintegrate
+            raise RuntimeError("WindowSimulator needs a preintegrate callback (the library's vrf_imu_preintegrate_batch, or the "
+                               "checker's, installed by tests/conftest.py through ba_problem.DEFAULT_PREINTEGRATE)")
         t0, t1 = self.t(k0), self.t(k1)
         n = max(2, int(round((t1 - t0) * self.imu_rate)))
         ts = np.linspace(t0, t1, n + 1)
