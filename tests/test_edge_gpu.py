@@ -49,7 +49,7 @@ def test_ba_window_without_landmarks():
 def big_window(seed, cfg, copies=4):
     """A window at the landmark capacity: the simulator's landmarks replicated with perturbed inverse depths
     (landmarks hosted at frame 0 only once, the marginalization drops at most BA_MAX_M0 = 384 of them)."""
-    sim = BP.WindowSimulator(seed, cfg, n_landmarks=3300)
+    sim = BP.WindowSimulator(seed, cfg, n_landmarks=3300, spawn_per_frame=40)
     pb = sim.window(0)
     rng = np.random.default_rng(seed)
     lam, start, flag, ptr, obs = [pb.lam], [pb.start], [pb.flag], list(pb.obs_ptr), [pb.obs_pts]

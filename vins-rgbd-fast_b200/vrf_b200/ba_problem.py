@@ -140,7 +140,8 @@ class WindowSimulator:
     (what FeatureManager / processIMU would hand to optimization())."""
 
     def __init__(self, seed, cfg, n_landmarks=150, kf_dt=0.1, imu_rate=200.0, flag2_frac=0.1,
-                 pix_noise=0.5, ric=None, tic=None, td_true=0.0, ex_constant=1, td_constant=1, ex_perturb=0.0, preintegrate=None):
+                 pix_noise=0.5, ric=None, tic=None, td_true=0.0, ex_constant=1, td_constant=1, ex_perturb=0.0, preintegrate=None,
+                 spawn_per_frame=None):
         self.cfg = cfg
         # IntegrationBase for the generated IMU samples: preintegrate(samples, acc0, gyr0, ba, bg, cfg) -> VrfImuPreint.
         # None = ba_problem.DEFAULT_PREINTEGRATE (installed by the checker legs); bench.py's GPU arm passes the library's
@@ -156,6 +157,7 @@ class WindowSimulator:
         self.ba_true = self.rng.uniform(-0.02, 0.02, 3)
         self.bg_true = self.rng.uniform(-0.005, 0.005, 3)
         self.n_landmarks = n_landmarks
+        self.spawn_per_frame = spawn_per_frame
         self.flag2_frac = flag2_frac
         self.pool = []          # dicts: P (world), first, last (absolute frame idx), eps, flag
         self.est = {}           # absolute frame -> (P, R, V, Ba, Bg) current estimate
@@ -189,7 +191,7 @@ class WindowSimulator:
         out = []
         # 40 new landmarks per keyframe fill windows of up to ~320 landmarks (the reference's 150-feature configs); larger
         # windows (BASELINE configs[3]: 500 feats) spawn proportionally more
-        per_frame = 40 if self.n_landmarks <= 300 else -(-self.n_landmarks * 40 // 280)
+        per_frame = self.spawn_per_frame or (40 if self.n_landmarks <= 300 else -(-self.n_landmarks * 40 // 280))
         for _ in range(25 * per_frame):
             if len(out) >= per_frame:
                 break
