@@ -187,6 +187,7 @@ extern "C" int vrf_create(const VrfConfig *cfg, int n_seq, int device, vrf_handl
     h->has_img.assign(n_seq, 0);
     h->prev_time.assign(n_seq, 0.0);
     if (front_configure_kernels(fc) != 0) { snprintf(h->errbuf, sizeof(h->errbuf), "kernel attribute setup failed"); return fail(VRF_ERR_CUDA); }
+    if (int lrc = lk_configure(fc, d, n_seq, &h->lk_maps)) { snprintf(h->errbuf, sizeof(h->errbuf), "k_lk setup (attributes / cuTensorMapEncodeTiled) failed: %d", lrc); return fail(VRF_ERR_CUDA); }
     rc = ba_create(h);
     if (rc != VRF_OK) return fail(rc);
     if (cudaDeviceSynchronize() != cudaSuccess) return fail(VRF_ERR_CUDA);
@@ -310,7 +311,7 @@ static int enqueue_front(vrf_handle *h, int n, const int32_t *seqs, const uint8_
     const size_t ob = (size_t)out_base * fd.out_pitch;
     fd.o_pts += ob; fd.o_un += ob; fd.o_vel += ob; fd.o_ids += ob; fd.o_cnt += ob; fd.o_depth += ob; fd.o_dkeep += ob;
     fd.out_hdr += (size_t)out_base * 8;
-    front_launch(h->fc, h->d_calls, n, fd, d_frames, frame_bytes, fmt, any_pub, h->sm_count, lc);
+    front_launch(h->fc, h->d_calls, n, fd, h->lk_maps, d_frames, frame_bytes, fmt, any_pub, h->sm_count, lc);
     if (h->fc.use_ransac && any_pub) ransac_launch(h->fc, h->d_calls, n, fd, lc);
     front_launch_tail(h->fc, h->d_calls, n, fd, any_pub, d_depth, depth_frame_bytes, depth_fmt, lc);
     CK(cudaGetLastError());

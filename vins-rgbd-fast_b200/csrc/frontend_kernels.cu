@@ -8,7 +8,7 @@
 //   k_ingest        frame (GRAY8 | RGB8) -> pyramid level 0 of the "forw" buffer
 //                   (+ work-list prefix for k_lk)                 [HBM-bound]
 //   k_pyrdown xL    cv::pyrDown level l -> l+1                    [HBM/L2-bound]
-//   k_lk            predictPtsInNextFrame + cv::calcOpticalFlowPyrLK, one warp / feature
+//   k_lk            predictPtsInNextFrame + cv::calcOpticalFlowPyrLK, one warp / feature   (lk_kernels.cu)
 //   k_post_a        status fix-up, inBorder, reduceVector x5, track_cnt++
 //   k_ransac        rejectWithF (cv::findFundamentalMat RANSAC)   (ransac_kernels.cu)
 //   k_post_b        reduceVector by inliers, setMask (std::sort + greedy circles),
@@ -312,370 +312,6 @@ k_pyrdown(FrontCfg c, const SeqCall *calls, FrontDev d, int level)
                 for (int k = 0; k < 8; ++k)
                     if (dx0 + k < dw) q[k] = (uint8_t)(((k < 4 ? lo : hi) >> (8 * (k & 3))) & 0xFFu);
             }
-        }
-    }
-}
-
-// ---------------------------------------------------------------------------
-// k_lk: predictPtsInNextFrame (feature_tracker.cpp:595-608) + the per-point body of
-// cv::calcOpticalFlowPyrLK (LKTrackerInvoker; semantics pinned in
-// oracle/frontend_spec.py::lk_track).  One warp per feature, all pyramid levels.
-//   - 24x24 patch of the previous level staged in shared memory (REFLECT_101
-//     addressing = the padded pyramid of buildOpticalFlowPyramid),
-//   - Scharr derivatives computed on the fly (REFLECT_101 at the image border,
-//     0 outside the image = BORDER_CONSTANT of the derivative pyramid),
-//   - integer bilinear interpolation (14-bit weights), all 32 lanes in parallel,
-//   - the 2x2 normal equations / mismatch vector are accumulated in float32 in
-//     *exactly OpenCV's SIMD lane order* (ordered add chains, one lane per chain),
-//     so tracks are bit-identical to cv2.calcOpticalFlowPyrLK -- no drift between
-//     the two pipelines over long sequences.
-// ---------------------------------------------------------------------------
-#define LK_WPB 8
-#define LK_NPX 14   // ceil(441/32)
-#define LK_R1_BYTES 3584    // region 1: 24x24 u8 patch of I, later the float addend arrays of the b-sum chains (792 floats)
-#define LK_R2_BYTES 1936    // region 2: 22x22 short2 Scharr, later 441(+7) short2 (Ix,Iy) of the window
-
-// OpenCV's float accumulation order (lkpyramid.cpp SSE path; pinned bit-exactly against
-// cv2 4.13 in oracle/frontend_spec.py::_sum_a_opencv/_sum_b_opencv):
-//   per window row, pixels 0..15 feed 4 SIMD-lane accumulators, pixels 16..20 a scalar one;
-//   total = scalar + ((l0 + l2) + (l1 + l3)).
-// A-sums: lane j adds float(prod[x]) for x = j, j+4, j+8, j+12 (in that order) per row.
-// b-sums: lane k adds float(prod[x0+k] + prod[x0+k+4]) for x0 = 0, 8 per row (v_dotprod).
-// Each accumulator is an ordered chain of float adds => one warp lane per chain:
-//   lane = 5*q + r, q = which sum, r = 0..3 SIMD lane, r = 4 scalar tail.
-__device__ __forceinline__ float lk_combine(float acc, int q)
-{
-    float l0 = __shfl_sync(0xffffffffu, acc, 5 * q + 0);
-    float l1 = __shfl_sync(0xffffffffu, acc, 5 * q + 1);
-    float l2 = __shfl_sync(0xffffffffu, acc, 5 * q + 2);
-    float l3 = __shfl_sync(0xffffffffu, acc, 5 * q + 3);
-    float tl = __shfl_sync(0xffffffffu, acc, 5 * q + 4);
-    return tl + ((l0 + l2) + (l1 + l3));
-}
-
-// b-sum chains live on lanes 4q + r (SIMD accumulators) and 8 + q (scalar tail)
-__device__ __forceinline__ float lk_combine_b(float acc, int q)
-{
-    float l0 = __shfl_sync(0xffffffffu, acc, 4 * q + 0);
-    float l1 = __shfl_sync(0xffffffffu, acc, 4 * q + 1);
-    float l2 = __shfl_sync(0xffffffffu, acc, 4 * q + 2);
-    float l3 = __shfl_sync(0xffffffffu, acc, 4 * q + 3);
-    float tl = __shfl_sync(0xffffffffu, acc, 8 + q);
-    return tl + ((l0 + l2) + (l1 + l3));
-}
-
-// LK_UNITS: the 441 window pixels as 168 SIMD units (row y, half hq, SIMD lane r: pixels x = 8 hq + r and x + 4,
-// chain step s = 2 y + hq) followed by 105 tail units (row y, x = 16..20, chain step t = 5 y + x - 16).
-// Unit u = lane + 32 m; m = 0..4 are SIMD units on every lane, m = 5 is SIMD on lanes 0..7 and tail on the rest,
-// m = 6..8 are tail units.  Addend arrays (float, region 1): SIMD chain (q, r) at (4 q + r) * LK_FS_STRIDE + s,
-// tail chain q at LK_FT_BASE + q * LK_FT_STRIDE + t.
-#define LK_NUNIT 9
-#define LK_FS_STRIDE 72          // >= 44, = 8 mod 32: the four SIMD lanes of a step hit different banks
-#define LK_FT_BASE (8 * LK_FS_STRIDE)
-#define LK_FT_STRIDE 108
-__device__ __forceinline__ void lk_unit(int m, int lane, int &pa, int &pb, int &dst)
-{
-    const int u = lane + 32 * m;
-    if (m < 5 || (m == 5 && lane < 8)) {
-        const int sidx = u >> 2, r = u & 3;
-        pa = (sidx >> 1) * 21 + 8 * (sidx & 1) + r; pb = pa + 4;
-        dst = r * LK_FS_STRIDE + sidx;
-    } else {
-        const int t = u - 168;
-        if (t < 105) { const int y = t / 5; pa = y * 21 + 16 + (t - 5 * y); pb = -1; dst = LK_FT_BASE + t; }
-        else { pa = -1; pb = -1; dst = 0; }
-    }
-}
-
-// I (5 fractional bits), Ix, Iy of window pixel p by integer bilinear interpolation of the staged patch / Scharr tile
-__device__ __forceinline__ void lk_interp_I(const uint8_t *s_I, const short2 *s_D, int p, int iw00, int iw01, int iw10, int iw11,
-                                            int &iv, int &ixv, int &iyv)
-{
-    const int wy = p / 21, wx = p - wy * 21;
-    const uint8_t *q = &s_I[(wy + 1) * 24 + wx + 1];
-    iv = ((int)q[0] * iw00 + (int)q[1] * iw01 + (int)q[24] * iw10 + (int)q[25] * iw11 + (1 << 8)) >> 9;
-    const short2 *dq = &s_D[wy * 22 + wx];
-    const short2 d00 = dq[0], d01 = dq[1], d10 = dq[22], d11 = dq[23];
-    ixv = (d00.x * iw00 + d01.x * iw01 + d10.x * iw10 + d11.x * iw11 + (1 << 13)) >> 14;
-    iyv = (d00.y * iw00 + d01.y * iw01 + d10.y * iw10 + d11.y * iw11 + (1 << 13)) >> 14;
-}
-
-__global__ void __launch_bounds__(LK_WPB * 32, 2)
-k_lk(FrontCfg c, const SeqCall *calls, int ncalls, FrontDev d)
-{
-    __shared__ __align__(16) unsigned char s_r1[LK_WPB][LK_R1_BYTES];
-    __shared__ __align__(16) unsigned char s_r2[LK_WPB][LK_R2_BYTES];
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    uint8_t *s_I = s_r1[wib];
-    float *s_F = reinterpret_cast<float *>(s_r1[wib]);     // addend arrays of the b-sum chains (see LK_UNITS)
-    const unsigned *s_dIw = reinterpret_cast<const unsigned *>(s_r2[wib]);   // packed (Ix | Iy<<16) per window pixel
-    short2 *s_D = reinterpret_cast<short2 *>(s_r2[wib]);
-    const short *s_dI = reinterpret_cast<const short *>(s_r2[wib]);   // interleaved (Ix, Iy) per window pixel
-    const int total = d.work_prefix[ncalls];
-    const int maxLevel = c.levels - 1;
-    const int cq = lane / 5, cr = lane - 5 * cq;      // accumulation chain owned by this lane
-
-    for (int g = blockIdx.x * LK_WPB + wib; g < total; g += gridDim.x * LK_WPB) {
-        // locate the batch item: largest ci with prefix[ci] <= g
-        int lo = 0, hi = ncalls;
-        while (hi - lo > 1) {
-            int mid = (lo + hi) >> 1;
-            if (d.work_prefix[mid] <= g) lo = mid; else hi = mid;
-        }
-        const int ci = lo;
-        const int idx = g - d.work_prefix[ci];
-        const SeqCall call = calls[ci];
-        const size_t base = (size_t)call.seq * VRF_CAP + idx;
-        const uint8_t *pyrI = d.pyr[call.buf_prev] + (size_t)call.seq * c.pyr_bytes;
-        const uint8_t *pyrJ = d.pyr[call.buf_cur] + (size_t)call.seq * c.pyr_bytes;
-
-        const float2 prev = d.cur_pts[base];
-        float2 init = prev;
-        if (c.use_imu) {
-            double mx, my;
-            cam_lift(c, (double)prev.x, (double)prev.y, mx, my);
-            const double *R = call.R;
-            double X = R[0] * mx + R[1] * my + R[2];
-            double Y = R[3] * mx + R[4] * my + R[5];
-            double Z = R[6] * mx + R[7] * my + R[8];
-            double u, v;
-            cam_project(c, X, Y, Z, u, v);
-            init.x = (float)u; init.y = (float)v;
-        }
-        if (lane == 0) d.pred_pts[base] = init;
-
-        int st = 1;
-        float2 nextStored = init;
-        for (int level = maxLevel; level >= 0; --level) {
-            const int cols = c.lw[level], rows = c.lh[level], pitch = c.lp[level];
-            const uint8_t *I = pyrI + c.loff[level];
-            const uint8_t *J = pyrJ + c.loff[level];
-            const float scale = 1.0f / (float)(1 << level);
-            float2 prevPt = make_float2(prev.x * scale, prev.y * scale);
-            float2 nextPt;
-            if (level == maxLevel) {
-                if (c.use_imu) nextPt = make_float2(init.x * scale, init.y * scale);
-                else nextPt = prevPt;
-            } else
-                nextPt = make_float2(nextStored.x * 2.f, nextStored.y * 2.f);
-            nextStored = nextPt;
-            prevPt.x -= VRF_LK_HALF; prevPt.y -= VRF_LK_HALF;
-            const int ix = (int)floorf(prevPt.x), iy = (int)floorf(prevPt.y);
-            if (ix < -VRF_LK_WIN || ix >= cols || iy < -VRF_LK_WIN || iy >= rows) {
-                if (level == 0) st = 0;
-                continue;
-            }
-            float a = prevPt.x - (float)ix, b = prevPt.y - (float)iy;
-            int iw00 = __float2int_rn((1.f - a) * (1.f - b) * 16384.f);
-            int iw01 = __float2int_rn(a * (1.f - b) * 16384.f);
-            int iw10 = __float2int_rn((1.f - a) * b * 16384.f);
-            int iw11 = 16384 - iw00 - iw01 - iw10;
-
-            __syncwarp();
-            // stage 24x24 of I (origin ix-1, iy-1), REFLECT_101 = the padded pyramid level
-            for (int t = lane; t < 576; t += 32) {
-                int sy = t / 24, sx = t - sy * 24;
-                int gx = reflect101(ix - 1 + sx, cols), gy = reflect101(iy - 1 + sy, rows);
-                s_I[t] = __ldg(I + (size_t)gy * pitch + gx);
-            }
-            __syncwarp();
-            // Scharr at the 22x22 positions (ix+dx, iy+dy); 0 outside the image (BORDER_CONSTANT)
-            for (int t = lane; t < 484; t += 32) {
-                int dy_ = t / 22, dx_ = t - dy_ * 22;
-                int gx = ix + dx_, gy = iy + dy_;
-                short2 dv = make_short2(0, 0);
-                if (gx >= 0 && gx < cols && gy >= 0 && gy < rows) {
-                    const uint8_t *p = &s_I[(dy_ + 1) * 24 + dx_ + 1];
-                    int p00 = p[-25], p01 = p[-24], p02 = p[-23];
-                    int p10 = p[-1], p12 = p[1];
-                    int p20 = p[23], p21 = p[24], p22 = p[25];
-                    int t0l = 3 * (p00 + p20) + 10 * p10;     // smoothing along y at x-1
-                    int t0r = 3 * (p02 + p22) + 10 * p12;     // at x+1
-                    int t1l = p20 - p00, t1c = p21 - p01, t1r = p22 - p02;
-                    dv.x = (short)(t0r - t0l);
-                    dv.y = (short)(3 * (t1l + t1r) + 10 * t1c);
-                }
-                s_D[t] = dv;
-            }
-            __syncwarp();
-            // integer bilinear interpolation of the window: I (5 fractional bits), Ix, Iy.
-            // Work is dealt in "units" that match OpenCV's accumulation (see LK_UNITS above): a SIMD unit is the
-            // pixel pair (x, x+4) whose products are summed in int32 before the float conversion, a tail unit
-            // is one pixel of columns 16..20.  Unit u = lane + 32 m.
-            unsigned IwU[LK_NUNIT];               // I of the unit's pixel(s): lo 16 bits pixel a, hi 16 bits pixel b
-            unsigned dpa[LK_NUNIT], dpb[LK_NUNIT];   // packed (Ix, Iy) as two int16
-#pragma unroll
-            for (int mm = 0; mm < LK_NUNIT; ++mm) {
-                int pa, pb, dst;
-                lk_unit(mm, lane, pa, pb, dst);
-                unsigned iw = 0, da_ = 0, db_ = 0;
-                if (pa >= 0) {
-                    int iv, ixv, iyv;
-                    lk_interp_I(s_I, s_D, pa, iw00, iw01, iw10, iw11, iv, ixv, iyv);
-                    iw = (unsigned)iv;
-                    da_ = ((unsigned)ixv & 0xFFFFu) | ((unsigned)iyv << 16);
-                    if (pb >= 0) {
-                        lk_interp_I(s_I, s_D, pb, iw00, iw01, iw10, iw11, iv, ixv, iyv);
-                        iw |= (unsigned)iv << 16;
-                        db_ = ((unsigned)ixv & 0xFFFFu) | ((unsigned)iyv << 16);
-                    }
-                }
-                IwU[mm] = iw; dpa[mm] = da_; dpb[mm] = db_;
-            }
-            __syncwarp();
-            // regions are free now: region 2 <- (Ix,Iy) per window pixel; region 1 <- zero padding of the addend arrays
-#pragma unroll
-            for (int mm = 0; mm < LK_NUNIT; ++mm) {
-                int pa, pb, dst;
-                lk_unit(mm, lane, pa, pb, dst);
-                if (pa >= 0) {
-                    reinterpret_cast<unsigned *>(s_r2[wib])[pa] = dpa[mm];
-                    if (pb >= 0) reinterpret_cast<unsigned *>(s_r2[wib])[pb] = dpb[mm];
-                }
-            }
-            if (lane < 7) reinterpret_cast<unsigned *>(s_r2[wib])[441 + lane] = 0u;
-            if (lane < 16) s_F[(lane >> 1) * LK_FS_STRIDE + 42 + (lane & 1)] = 0.f;            // SIMD chains: steps 42, 43
-            else if (lane < 22) s_F[LK_FT_BASE + ((lane - 16) / 3) * LK_FT_STRIDE + 105 + (lane - 16) % 3] = 0.f;   // tails: 105..107
-            __syncwarp();
-            // A11, A12, A22: 15 ordered float chains (lanes 0..14).  (Measured and rejected: writing the 3 x 441 products as
-            // float addend arrays first -- like the b-sums -- and summing with 16-byte loads: 13 % fewer instructions and
-            // still bit-exact, but 58 KB of shared memory per CTA takes 32 KB from L1 and the kernel got 9 % slower.)
-            float A11, A12, A22;
-            {
-                float acc = 0.f;
-                if (lane < 15) {
-                    const int sa = (cq == 2) ? 1 : 0, sb = (cq == 0) ? 0 : 1;   // (Ix,Ix) (Ix,Iy) (Iy,Iy)
-#pragma unroll 1
-                    for (int y = 0; y < VRF_LK_WIN; ++y) {
-                        const short *row = s_dI + 2 * (y * 21);
-                        if (cr < 4) {
-#pragma unroll
-                            for (int gq = 0; gq < 4; ++gq) {
-                                const short *e = row + 2 * (4 * gq + cr);
-                                acc += (float)((int)e[sa] * (int)e[sb]);
-                            }
-                        } else {
-#pragma unroll
-                            for (int x = 16; x < 21; ++x) {
-                                const short *e = row + 2 * x;
-                                acc += (float)((int)e[sa] * (int)e[sb]);
-                            }
-                        }
-                    }
-                }
-                A11 = lk_combine(acc, 0);
-                A12 = lk_combine(acc, 1);
-                A22 = lk_combine(acc, 2);
-            }
-            const float FLT_SCALE = 1.f / (float)(1 << 20);
-            A11 *= FLT_SCALE; A12 *= FLT_SCALE; A22 *= FLT_SCALE;
-            float D = A11 * A22 - A12 * A12;
-            float minEig = (A22 + A11 - sqrtf((A11 - A22) * (A11 - A22) + 4.f * A12 * A12)) / 882.f;
-            if (minEig < 1e-4f || D < 1.1920929e-07f) {
-                if (level == 0) st = 0;
-                continue;
-            }
-            D = 1.f / D;
-            nextPt.x -= VRF_LK_HALF; nextPt.y -= VRF_LK_HALF;
-            float2 prevDelta = make_float2(0.f, 0.f);
-            for (int j = 0; j < 30; ++j) {
-                const int jx = (int)floorf(nextPt.x), jy = (int)floorf(nextPt.y);
-                if (jx < -VRF_LK_WIN || jx >= cols || jy < -VRF_LK_WIN || jy >= rows) {
-                    if (level == 0) st = 0;
-                    break;
-                }
-                a = nextPt.x - (float)jx; b = nextPt.y - (float)jy;
-                const int w00 = __float2int_rn((1.f - a) * (1.f - b) * 16384.f);
-                const int w01 = __float2int_rn(a * (1.f - b) * 16384.f);
-                const int w10 = __float2int_rn((1.f - a) * b * 16384.f);
-                const int w11 = 16384 - w00 - w01 - w10;
-                const bool inside = (jx >= 0) && (jy >= 0) && (jx + 22 <= cols) && (jy + 22 <= rows);
-                __syncwarp();
-                if (inside) {
-                    const uint8_t *Jb = J + (size_t)jy * pitch + jx;
-#pragma unroll
-                    for (int mm = 0; mm < LK_NUNIT; ++mm) {
-                        int pa, pb, dst;
-                        lk_unit(mm, lane, pa, pb, dst);
-                        if (pa < 0) continue;
-                        const int wy = pa / 21, wx = pa - wy * 21;
-                        const uint8_t *q = Jb + wy * pitch + wx;
-                        int jv = ((int)__ldg(q) * w00 + (int)__ldg(q + 1) * w01 + (int)__ldg(q + pitch) * w10 +
-                                  (int)__ldg(q + pitch + 1) * w11 + (1 << 8)) >> 9;
-                        int diff = jv - (int)(IwU[mm] & 0xFFFFu);
-                        unsigned dw = s_dIw[pa];
-                        int d1 = diff * (int)(short)(dw & 0xFFFFu), d2 = diff * ((int)dw >> 16);
-                        if (pb >= 0) {
-                            q += 4;
-                            jv = ((int)__ldg(q) * w00 + (int)__ldg(q + 1) * w01 + (int)__ldg(q + pitch) * w10 +
-                                  (int)__ldg(q + pitch + 1) * w11 + (1 << 8)) >> 9;
-                            diff = jv - (int)(IwU[mm] >> 16);
-                            dw = s_dIw[pb];
-                            d1 += diff * (int)(short)(dw & 0xFFFFu); d2 += diff * ((int)dw >> 16);     // v_dotprod pair sum, exact in int32
-                        }
-                        s_F[dst] = (float)d1;
-                        s_F[dst + (pb >= 0 ? 4 * LK_FS_STRIDE : LK_FT_STRIDE)] = (float)d2;
-                    }
-                } else {
-#pragma unroll
-                    for (int mm = 0; mm < LK_NUNIT; ++mm) {
-                        int pa, pb, dst;
-                        lk_unit(mm, lane, pa, pb, dst);
-                        if (pa < 0) continue;
-                        int d1 = 0, d2 = 0;
-#pragma unroll
-                        for (int hh = 0; hh < 2; ++hh) {
-                            const int pp = hh ? pb : pa;
-                            if (pp < 0) continue;
-                            const int wy = pp / 21, wx = pp - wy * 21;
-                            const int x0 = reflect101(jx + wx, cols), x1 = reflect101(jx + wx + 1, cols);
-                            const int y0 = reflect101(jy + wy, rows), y1 = reflect101(jy + wy + 1, rows);
-                            const uint8_t *r0 = J + (size_t)y0 * pitch, *r1 = J + (size_t)y1 * pitch;
-                            const int jv = ((int)__ldg(r0 + x0) * w00 + (int)__ldg(r0 + x1) * w01 + (int)__ldg(r1 + x0) * w10 +
-                                            (int)__ldg(r1 + x1) * w11 + (1 << 8)) >> 9;
-                            const int diff = jv - (int)(hh ? (IwU[mm] >> 16) : (IwU[mm] & 0xFFFFu));
-                            const unsigned dw = s_dIw[pp];
-                            d1 += diff * (int)(short)(dw & 0xFFFFu); d2 += diff * ((int)dw >> 16);
-                        }
-                        s_F[dst] = (float)d1;
-                        s_F[dst + (pb >= 0 ? 4 * LK_FS_STRIDE : LK_FT_STRIDE)] = (float)d2;
-                    }
-                }
-                __syncwarp();
-                // b1, b2: 10 ordered float chains (lanes 0..3 / 4..7: SIMD accumulators of b1 / b2, lanes 8, 9: scalar tails);
-                // every chain is a contiguous, zero-padded array (x + 0.0f is exact), read 4 addends at a time
-                float acc = 0.f;
-                if (lane < 10) {
-                    const float4 *src = reinterpret_cast<const float4 *>(s_F + (lane < 8 ? lane * LK_FS_STRIDE : LK_FT_BASE + (lane - 8) * LK_FT_STRIDE));
-                    const int nq = lane < 8 ? 11 : 27;
-#pragma unroll 3
-                    for (int qd = 0; qd < nq; ++qd) {
-                        const float4 f4 = src[qd];
-                        acc += f4.x; acc += f4.y; acc += f4.z; acc += f4.w;
-                    }
-                }
-                float fb1 = lk_combine_b(acc, 0) * FLT_SCALE;
-                float fb2 = lk_combine_b(acc, 1) * FLT_SCALE;
-                float2 delta = make_float2((A12 * fb2 - A22 * fb1) * D, (A12 * fb1 - A11 * fb2) * D);
-                nextPt.x += delta.x; nextPt.y += delta.y;
-                nextStored = make_float2(nextPt.x + VRF_LK_HALF, nextPt.y + VRF_LK_HALF);
-                if ((double)delta.x * (double)delta.x + (double)delta.y * (double)delta.y <= 0.01 * 0.01) break;
-                if (j > 0 && (double)fabsf(delta.x + prevDelta.x) < 0.01 && (double)fabsf(delta.y + prevDelta.y) < 0.01) {
-                    nextStored.x -= delta.x * 0.5f; nextStored.y -= delta.y * 0.5f;
-                    break;
-                }
-                prevDelta = delta;
-            }
-            if (st && level == 0) {
-                // `err` is requested by the reference => final bounds check (lkpyramid.cpp)
-                float qx = nextStored.x - VRF_LK_HALF, qy = nextStored.y - VRF_LK_HALF;
-                int kx = (int)floorf(qx), ky = (int)floorf(qy);
-                if (kx < -VRF_LK_WIN || kx >= cols || ky < -VRF_LK_WIN || ky >= rows) st = 0;
-            }
-        }
-        if (lane == 0) {
-            d.lk_pts[base] = nextStored;
-            d.lk_status[base] = (uint8_t)st;
         }
     }
 }
@@ -1246,7 +882,7 @@ int front_configure_kernels(const FrontCfg &c)
     return (int)e;
 }
 
-int front_launch(const FrontCfg &c, const SeqCall *d_calls, int ncalls, const FrontDev &d,
+int front_launch(const FrontCfg &c, const SeqCall *d_calls, int ncalls, const FrontDev &d, const LkMaps &maps,
                  const uint8_t *d_frames, size_t frame_bytes, int fmt, int any_pub, int sm_count, LaunchCtx &lc)
 {
     cudaStream_t st = lc.st;
@@ -1271,15 +907,7 @@ int front_launch(const FrontCfg &c, const SeqCall *d_calls, int ncalls, const Fr
         k_pyrdown<<<g, 256, 0, st>>>(c, d_calls, d, l);
         lc.end();
     }
-    {
-        long long maxwork = (long long)ncalls * VRF_CAP;
-        long long want = ((long long)ncalls * (c.max_cnt + 2 * c.ncells) + LK_WPB - 1) / LK_WPB;
-        long long cap = (long long)sm_count * 8;
-        int grid = (int)max(1LL, min(min(want, cap), maxwork));
-        lc.begin(K_LK);
-        k_lk<<<grid, LK_WPB * 32, 0, st>>>(c, d_calls, ncalls, d);
-        lc.end();
-    }
+    lk_launch(c, d_calls, ncalls, d, maps, sm_count, lc);
     lc.begin(K_POST_A);
     k_post_a<<<ncalls, 256, 0, st>>>(c, d_calls, d);
     lc.end();

@@ -3,13 +3,18 @@
 #include <vector>
 
 #include "common.cuh"
+#include "tma.cuh"
 
 #define VRF_CALL_SLOTS 32
 #define VRF_COPY_CHUNKS 8
 #define VRF_PIPE_DEPTH 2        // host-frame batches in flight (submit / collect)
 #define VRF_COPY_STREAMS 4      // H2D copies rotate over four streams (measured on B200, 444 frames/step: 31.8k -> 36.6k frames/s e2e vs two)
 
+#define LK_WPB 8                // k_lk: warps (= features in flight) per CTA
+
 namespace vrf {
+// TMA tensor maps of the two pyramid buffers, one per level: u8 [n_seq][rows][cols] (strides pyr_bytes, pitch), box 48 x 32 x 1
+struct LkMaps { CUtensorMap m[2][VRF_MAX_LEVELS]; };
 struct BaState;   // ba_host.cu
 struct FmState;   // fm_kernels.cu
 
@@ -67,6 +72,7 @@ struct vrf_handle {
     cudaStream_t copy_stream[VRF_COPY_STREAMS] = {};
     cudaEvent_t copy_ev[VRF_PIPE_DEPTH][VRF_COPY_CHUNKS][VRF_COPY_STREAMS] = {};
     vrf::FrontDev fd = {};
+    vrf::LkMaps lk_maps;                    // built once in vrf_create (the pyramid buffers never move)
     // per-call descriptor ring (host pinned + device) so that enqueue calls can be pipelined
     vrf::SeqCall *h_calls_ring[VRF_CALL_SLOTS] = {};
     vrf::SeqCall *d_calls_ring[VRF_CALL_SLOTS] = {};
@@ -102,8 +108,11 @@ struct vrf_handle {
 namespace vrf {
 // frontend_kernels.cu
 int front_configure_kernels(const FrontCfg &c);
-int front_launch(const FrontCfg &c, const SeqCall *d_calls, int ncalls, const FrontDev &d, const uint8_t *d_frames,
+int front_launch(const FrontCfg &c, const SeqCall *d_calls, int ncalls, const FrontDev &d, const LkMaps &maps, const uint8_t *d_frames,
                  size_t frame_bytes, int fmt, int any_pub, int sm_count, LaunchCtx &lc);
+// lk_kernels.cu
+int lk_configure(const FrontCfg &c, const FrontDev &d, int n_seq, LkMaps *maps);
+int lk_launch(const FrontCfg &c, const SeqCall *d_calls, int ncalls, const FrontDev &d, const LkMaps &maps, int sm_count, LaunchCtx &lc);
 int front_launch_tail(const FrontCfg &c, const SeqCall *d_calls, int ncalls, const FrontDev &d, int any_pub,
                       const uint8_t *d_depth, size_t depth_frame_bytes, int depth_fmt, LaunchCtx &lc);
 // ransac_kernels.cu

@@ -39,9 +39,11 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, unsigned parity)
     return ok != 0;
 }
 
+// Bounded wait: a TMA that never completes (bad tensor map) traps instead of hanging the device.
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity)
 {
-    while (!mbar_try_wait(bar, parity)) {}
+    for (unsigned spin = 0; !mbar_try_wait(bar, parity); ++spin)
+        if (spin > (1u << 22)) __trap();
 }
 
 // TMA tiled load of one box of a 3-D u8 tensor (x = column, y = row, z = sequence) into shared memory; out-of-bounds
