@@ -175,6 +175,26 @@ def rel_rotation(base_R, idx, pidx):
     return base_R[pidx].T        # going backwards: inverse of cam(idx)->cam(pidx)
 
 
+def pin_to_gpu_numa_node(gpu_index):
+    """Bind this rank (and every pinned host buffer it allocates afterwards: first touch) to the CPU cores / NUMA node
+    nearest its GPU -- torchrun does not.  At N = 8 the host-buffer arm is bound by host-memory / PCIe-root traffic; frames
+    that cross the inter-socket link cost twice.  Returns a short description for the JSON line."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        n_words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, n_words)
+        cpus = [64 * w + b for w, word in enumerate(mask) for b in range(64) if (word >> b) & 1]
+        cpus = [c for c in cpus if c in os.sched_getaffinity(0)]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return "cpus %d-%d (%d) nearest GPU %d" % (min(cpus), max(cpus), len(cpus), gpu_index)
+    except Exception as e:           # reported, not fatal
+        return "unpinned (%s)" % type(e).__name__
+    return "unpinned"
+
+
 def shard_sequences(seqs_per_gpu, rank, world):
     """Global ids of the sequences owned by `rank` (weak scaling: every rank owns `seqs_per_gpu`
     independent sequences; sequence g lives on GPU g // seqs_per_gpu; frames never cross GPUs)."""
@@ -338,7 +358,7 @@ def emit(line):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=60)
+    ap.add_argument("--steps", type=int, default=250)
     ap.add_argument("--warmup", type=int, default=6)
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--config", default="c3", choices=sorted(CONFIGS), help="workload: c3 = BASELINE configs[1]+[2] (default, the metric's config), "
@@ -378,6 +398,8 @@ def main():
         except Exception as e:           # reported, never silently replaced
             cpu_base = {"value": None, "unit": "frames/s", "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {e}"}
 
+    numa = pin_to_gpu_numa_node(local_rank)
+
     import torch
     import torch.distributed as dist
     from vrf_b200 import binding
@@ -398,6 +420,7 @@ def main():
     d_dep = [torch.from_numpy(b[1].view(np.int16)).to(dev) for b in base]
     # pinned host mirrors for the e2e arm
     h_rgb = [torch.from_numpy(b[0]).pin_memory() for b in base]
+    h_gray = [torch.from_numpy(b[2]).pin_memory() for b in base]      # MONO8 frames: what FeatureTracker::readImage receives
     h_dep = [torch.from_numpy(b[1].view(np.int16)).pin_memory() for b in base]
 
     cfg = ba_config()
@@ -406,10 +429,14 @@ def main():
     # (prior from a first solved window), uploaded to HBM before timing ----
     from vrf_b200 import ba_problem as BP
     NBA = max(1, S // PUB_EVERY)
-    ba_probs = []
-    n_ba_distinct = min(NBA, 8)
+    # Distinct windows: up to 37 independent simulators (replicated over the NBA slots), and for each of them N_WIN consecutive
+    # windows of its chain (window a+1 starts from the solution and the marginalization prior of window a): the timed steps
+    # cycle through the N_WIN groups, so that consecutive steps solve different problems with a realistic mix of
+    # 3..8 accepted dogleg steps per window.
+    n_ba_distinct = min(NBA, 37)
+    N_WIN = 3
     # Input generation uses the library itself, never oracle/: IMU pre-integration through vrf_imu_preintegrate_batch,
-    # the first window's solve + marginalization (which yields the prior of the benchmarked window) through vrf_ba_solve.
+    # the chain's solves + marginalizations (which yield the priors of the benchmarked windows) through vrf_ba_solve.
     gen = binding.Handle(cfg, 1, local_rank)
 
     def gpu_preintegrate(samples, acc0, gyr0, ba, bg, _cfg):
@@ -417,19 +444,29 @@ def main():
         out = gen.imu_preintegrate([(acc0, gyr0, ba, bg, dt, acc, gyr)])
         return binding.VrfImuPreint.from_buffer_copy(out[0])
 
+    ba_chain = []
     for i in range(n_ba_distinct):
         sim = BP.WindowSimulator(1234 + i, cfg, n_landmarks=BA_LANDMARKS, preintegrate=gpu_preintegrate)
-        sol0 = gen.ba_solve(0, sim.window(0)); sim.commit(0, sol0)
-        ba_probs.append(sim.window(1))
+        sol = gen.ba_solve(0, sim.window(0)); sim.commit(0, sol)
+        wins = []
+        for a in range(1, 1 + N_WIN):
+            pb = sim.window(a)
+            wins.append(pb)
+            if a < N_WIN:
+                sol = gen.ba_solve(0, pb); sim.commit(a, sol)
+        ba_chain.append(wins)
     gen.close()
-    ba_batch = [ba_probs[i % n_ba_distinct] for i in range(NBA)]
+    ba_groups = [[ba_chain[i % n_ba_distinct][w] for i in range(NBA)] for w in range(N_WIN)]
+    ba_batch = ba_groups[0]
     ba_seqs = list(range(NBA))
+    ba_group_seqs = [list(range(w * NBA, (w + 1) * NBA)) for w in range(N_WIN)]
     ba_bytes = sum(56 * len(pb.obs_pts) + 8 * (75 * 75 + 75) + 10 * 3800 + 1500 for pb in ba_batch)
     # the back end runs on its own handle/stream so that it overlaps the front end, as the
     # reference's processThread overlaps its trackThread (estimator_nodelet.cpp:61-62)
-    hnd_ba = binding.Handle(cfg, NBA, local_rank)
+    hnd_ba = binding.Handle(cfg, NBA * N_WIN, local_rank)
     ext_stream_ba = torch.cuda.ExternalStream(hnd_ba.stream(), device=dev)
-    hnd_ba.ba_upload(ba_seqs, ba_batch)
+    for w in range(N_WIN):
+        hnd_ba.ba_upload(ba_group_seqs[w], ba_groups[w])
     hnd_ba.synchronize()
     ext_stream = torch.cuda.ExternalStream(hnd.stream(), device=dev)
     seqs = list(range(S))          # local slots; global ids: shard_sequences(S, rank, world)
@@ -465,7 +502,7 @@ def main():
         idxs, Rs, pubs, times = plans[k]
         hnd.enqueue_dev(seqs, d_steps[k % PERIOD].data_ptr(), binding.FMT_RGB8, times, Rs, pubs,
                         d_depth=d_steps_dep[k % PERIOD].data_ptr(), depth_fmt=binding.DEPTH_16UC1)
-        hnd_ba.ba_enqueue(ba_seqs)           # S/3 windows: solve + gauge fix + marginalization
+        hnd_ba.ba_enqueue(ba_group_seqs[k % N_WIN])           # S/3 windows: solve + gauge fix + marginalization
 
     # ---- warm-up ----
     sampler = ClockSampler(local_rank)
@@ -510,7 +547,7 @@ def main():
     hnd.profile(False)
     hnd_ba.profile(True); hnd_ba.profile_read(reset=True)
     for k in range(nprof):
-        hnd_ba.ba_enqueue(ba_seqs)
+        hnd_ba.ba_enqueue(ba_group_seqs[k % N_WIN])
     for kname, v in hnd_ba.profile_read(reset=True).items():
         prof[kname] = (prof.get(kname, (0.0, 0))[0] + v[0], prof.get(kname, (0, 0))[1] + v[1])
     hnd_ba.profile(False)
@@ -523,24 +560,27 @@ def main():
                       "| marg phases", v[8:15].tolist(), "| it/succ/term/status", v[16:20].tolist(), file=sys.stderr)
     except Exception:
         ba_phase = None
+    peaks, peak_kind = load_peaks()
     tot_ms = sum(v[0] for v in prof.values()) or 1.0
     kern = {k: {"ms_per_step": v[0] / nprof, "launches_per_step": v[1] / nprof, "share": v[0] / tot_ms}
             for k, v in prof.items() if v[1] > 0}
-    peaks, peak_kind = load_peaks()
-    dom = max(kern.items(), key=lambda kv: kv[1]["ms_per_step"])[0] if kern else None
+    # Roofline of the two kernels that carry the path (reported every time, so that the line does not flip between them);
+    # "kernel" = the one with the larger device time.  Algorithmic bytes per launch: k_lk is charged the
+    # frames it tracks (S x A_frame), the BA kernels the problem bytes of SURVEY 8(d).
     roof = None
+    alg_of = {"k_lk": S * A_FRAME, "k_ba_solve": ba_bytes, "k_ba_marg": ba_bytes, "k_ingest": S * (3 * W * H + W * H)}
+    per_kernel = {}
+    for kname in ("k_lk", "k_ba_solve"):
+        if kname in kern:
+            ms_l = kern[kname]["ms_per_step"] / max(kern[kname]["launches_per_step"], 1e-9)
+            ach_ = alg_of[kname] / (ms_l * 1e-3) / 1e9
+            per_kernel[kname] = {"alg_bytes_per_launch": alg_of[kname], "launch_ms": ms_l, "achieved": ach_, "frac": ach_ / peaks["hbm_gbs"]}
+    dom = max(per_kernel, key=lambda kn: per_kernel[kn]["launch_ms"]) if per_kernel else None
     if dom:
-        # algorithmic bytes per launch of the dominant kernel (DESIGN.md section "roofline")
-        # algorithmic bytes per launch (DESIGN.md "Roofline"): image kernels = frame bytes they must move;
-        # k_ba_solve = the BA problem bytes of SURVEY 8(d); other kernels are charged the per-frame A_frame.
-        alg = {"k_ingest": S * (3 * W * H + W * H),                 # RGB8 read + gray write
-               "k_ba_solve": ba_bytes, "k_ba_marg": ba_bytes}.get(dom)
-        per_launch_ms = kern[dom]["ms_per_step"] / max(kern[dom]["launches_per_step"], 1e-9)
-        alg_bytes = alg if alg else S * A_FRAME / max(kern[dom]["launches_per_step"], 1)
-        ach = alg_bytes / (per_launch_ms * 1e-3) / 1e9
-        roof = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                "frac": ach / peaks["hbm_gbs"], "traffic": None, "peak_source": peak_kind,
-                "alg_bytes_per_launch": alg_bytes, "launch_ms": per_launch_ms, "kernels": kern,
+        roof = {"kernel": dom, "bound": "hbm", "achieved": per_kernel[dom]["achieved"], "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                "frac": per_kernel[dom]["frac"], "traffic": None, "peak_source": peak_kind,
+                "alg_bytes_per_launch": per_kernel[dom]["alg_bytes_per_launch"], "launch_ms": per_kernel[dom]["launch_ms"],
+                "per_kernel": per_kernel, "kernels": kern,
                 "ba_solve_phase_cycles": dict(zip(["linearise", "scale_grad", "cauchy", "schur", "cholesky", "solve_tail", "dogleg", "candidate"], ba_phase)) if ba_phase else None}
 
     if roof is not None:
@@ -588,6 +628,8 @@ def main():
         r_.new_prior = None          # the new prior stays in HBM (last_marginalization_info lives in the handle)
     import ctypes as C_
     host_ptr = [[h_rgb[b_][f_].data_ptr() for f_ in range(T_FRAMES)] for b_ in range(nb)]
+    host_gptr = [[h_gray[b_][f_].data_ptr() for f_ in range(T_FRAMES)] for b_ in range(nb)]
+    e2e_fmt = {"fmt": binding.FMT_RGB8, "ptr": host_ptr}
     host_dptr = [[h_dep[b_][f_].data_ptr() for f_ in range(T_FRAMES)] for b_ in range(nb)]
     ptr_arr = (C_.c_void_p * S)()
     dptr_arr = (C_.c_void_p * S)()
@@ -611,9 +653,9 @@ def main():
     def submit_front(k):
         idxs = plans[k][0]
         for s_ in seqs:
-            ptr_arr[s_] = host_ptr[s_ % nb][idxs[s_]]
+            ptr_arr[s_] = e2e_fmt["ptr"][s_ % nb][idxs[s_]]
             dptr_arr[s_] = host_dptr[s_ % nb][idxs[s_]]
-        hnd2.submit_batch_into(seq_np, ptr_arr, binding.FMT_RGB8, time_np[k], R_flat[k], pub_np[k],
+        hnd2.submit_batch_into(seq_np, ptr_arr, e2e_fmt["fmt"], time_np[k], R_flat[k], pub_np[k],
                                dptrs=dptr_arr, dfmt=binding.DEPTH_16UC1)
 
     part = os.environ.get("VRF_E2E_PART", "both")          # diagnosis only: "front" / "ba"
@@ -670,18 +712,42 @@ def main():
         dist.barrier()
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_val = (S * e2e_steps * world / float(t.item())) if e2e_steps else None
+    # ---- the same arm fed with MONO8 frames (W*H bytes): the class-surface entry, FeatureTracker::readImage(const cv::Mat &) gets
+    # the cv_bridge MONO8 image (estimator_nodelet.cpp:292-313); RGB8 above = the raw camera topic payload ----
+    e2e_gray_val = None
+    if e2e_steps:
+        for s_ in seqs:
+            hnd2.reset(s_)
+        e2e_fmt["fmt"], e2e_fmt["ptr"] = binding.FMT_GRAY8, host_gptr
+        run_host_steps(0, 3)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        run_host_steps(3, 3 + e2e_steps)
+        torch.cuda.synchronize()
+        tg = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.barrier()
+            dist.all_reduce(tg, op=dist.ReduceOp.MAX)
+        e2e_gray_val = S * e2e_steps * world / float(tg.item())
     hnd2.close(); hnd2_ba.close()
 
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": "frames/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total_max / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/i32/f32 (LK), f64 (camera model)",
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/i32/f32 (front end: integer image arithmetic, f32 LK normal equations), f64 (camera model, BA)",
             "data": f"synthetic: {nb} rendered base sequences x {T_FRAMES} frames (ping-pong), replicated to {S} sequences/GPU with phase offsets",
-            "config": {"workload": WORKLOAD, "seqs_per_gpu": S, "ba_solves_per_step": NBA, "l2": "inputs cycle through %d MB of distinct frames (> L2)" % (nb * T_FRAMES * 3 * W * H // 2**20),
-                       "parallelism": f"sequences sharded over {world} GPU(s), no data-path collective"},
+            "config": {"workload": WORKLOAD, "seqs_per_gpu": S, "ba_solves_per_step": NBA,
+                       "ba_inputs": "%d independent window chains x %d consecutive windows, cycled over the steps" % (n_ba_distinct, N_WIN),
+                       "l2": "every step reads a different one of the %d HBM-resident frame batches (%d MB each incl. depth; the ring is %d MB >> the 126 MB L2)" % (
+                           PERIOD, S * 5 * W * H // 2**20, PERIOD * S * 5 * W * H // 2**20),
+                       "parallelism": f"sequences sharded over {world} GPU(s), no data-path collective", "host_affinity": numa},
             "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": e2e_val, "unit": "frames/s", "h2d_bytes_per_step": S * 3 * W * H + (S // PUB_EVERY) * 2 * W * H + NBA * (195600 + 8 * (75 * 75 + 75 + 40 * 13)), "d2h_bytes_per_step": int(d2h)},
+            "e2e_gray8": {"value": e2e_gray_val, "unit": "frames/s", "note": "same arm fed with MONO8 host frames (the FeatureTracker::readImage class-surface input)",
+                          "h2d_bytes_per_step": S * W * H + (S // PUB_EVERY) * 2 * W * H + NBA * (195600 + 8 * (75 * 75 + 75 + 40 * 13)), "d2h_bytes_per_step": int(d2h)},
             "roofline": roof, "cpu_baseline": cpu_base,
         }
         emit(line)

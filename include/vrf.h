@@ -240,6 +240,10 @@ void vrf_debug_sort_desc(const int32_t *cnt, int32_t n, int32_t *perm_out);
  *       "cell_k" (cells int32), "maskpts" (2*n int32), "ba_prof" (8 int64 SM clock counts per
  *       phase of the last k_ba_solve in batch slot `seq`) -- returns bytes written or <0. */
 long vrf_debug_read(vrf_handle *h, const char *what, int seq, void *dst, size_t dst_bytes);
+/* Test entry: FeatureTracker::rejectWithF (feature_tracker.cpp:441-473: cv::findFundamentalMat(FM_RANSAC, F_THRESHOLD,
+ * 0.99) on the lifted points) alone, on n caller-supplied pixel pairs (x, y interleaved); status_out[n] receives the
+ * inlier mask.  Clobbers the per-call working arrays of `seq`; not part of the tracking API. */
+int vrf_debug_reject_with_f(vrf_handle *h, int seq, int n, const float *cur_xy, const float *forw_xy, uint8_t *status_out);
 
 /* ------------------------------------------------------------------------- */
 /* Back end (declared in vrf_ba.h, included here for convenience)             */

@@ -944,6 +944,11 @@ static int solve(const VrfBaProblem *pb, const VrfConfig *cfg, Lin *L, State *x,
     State cand;
     int rc = VRF_OK;
 
+    /* TrustRegionMinimizer::Init of a bound-constrained problem: the start point is projected onto the bounds
+     * (x = Plus(x, 0)) before the first evaluation.  Only the estimate_flag == 2 landmarks carry a bound
+     * (estimator.cpp:1293-1298); constant blocks are not part of the program. */
+    for (int l = 0; l < M; l++)
+        if (!L->lm_const[l] && x->lam[l] > L->lm_ub[l]) x->lam[l] = L->lm_ub[l];
     double x_cost = evaluate(pb, cfg, L, x, 1);
     sum->initial_cost = x_cost; sum->iterations = 0; sum->successful = 0; sum->termination = 0;
     /* Jacobi scaling, computed once at iteration 0 */

@@ -10,9 +10,11 @@ cv::RNG, cv::solveCubic) and is pinned against the real cv2.findFundamentalMat i
 tests/test_oracle_ransac.py (identical inlier masks for n >= 15).  It is the
 inspectable spec of csrc/ransac_kernels.cu.
 
-Note: for 8 <= n < 15 OpenCV switches to LMedS; with <= 14 points the median
-residual of every minimal-sample model is rounding noise (7 residuals are exact
-zeros), so the winner depends on the SVD's last bits and cannot be pinned.
+Note: for 8 <= n < 15 OpenCV switches to LMedS (lmeds_F below).  At n = 14 the median (index 7 of the sorted residuals) is
+the best residual outside the minimal sample: pinned against cv2 (identical masks).  For n <= 13 the median index falls
+inside the 7 residuals of the minimal sample itself, i.e. on rounding noise (~1e-25) of OpenCV's LAPACK SVD: cv2 returns a
+different mask when one input coordinate moves by 1 ulp (tests/test_oracle_ransac.py), so only the semantics (LMedS runs,
+the survivors are the points within 0.001 px of one minimal-sample model) can be restated there, not the bits.
 """
 import numpy as np, cv2, math
 M32 = 0xFFFFFFFF
@@ -162,18 +164,22 @@ def ransac_F(m1, m2, thr=1.0, conf=0.99, max_iters=1000, normalize=False, method
     return None, None
 
 def lmeds_F(m1, m2, conf=0.99, max_iters=1000, normalize=False, method='svd'):
+    """LMeDSPointSetRegistrator::run (ptsetreg.cpp), the path cv::findFundamentalMat(FM_RANSAC) takes for npoints < 15:
+    RANSACUpdateNumIters(conf, 0.45, 7, maxIters) (>= 3) iterations, getSubset with the default 1000 attempts, median =
+    std::nth_element at count / 2 of the float residuals, strict minimum in iteration order,
+    sigma = max(2.5 * 1.4826 * (1 + 5 / (count - 7)) * sqrt(median), 0.001), mask = err <= (float)(sigma^2)."""
     count = len(m1)
     rng = CvRNG()
-    niters = update_niters(conf, 0.45, 7, max_iters)
+    niters = max(update_niters(conf, 0.45, 7, max_iters), 3)
     min_median = 1.7976931348623157e308; best_F = None
     for it in range(niters):
-        idx = get_subset(m1, m2, rng, 7, 300)
+        idx = get_subset(m1, m2, rng, 7, 1000)
         if idx is None:
             if it == 0: return None, None
             break
         for F in run7point(m1[idx], m2[idx], normalize, method):
             err = np.sort(compute_error(m1, m2, F))
-            med = float(err[count//2]) if count % 2 else (float(err[count//2-1]) + float(err[count//2]))*0.5
+            med = float(err[count//2])
             if med < min_median: min_median = med; best_F = F
     if min_median < 1.7976931348623157e308:
         sigma = 2.5*1.4826*(1 + 5./(count - 7))*math.sqrt(min_median)

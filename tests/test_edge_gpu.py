@@ -125,3 +125,42 @@ def test_invalid_and_empty_inputs_fail_loudly():
         h.fm_triangulate_with_depth([p])
     assert len(h.imu_preintegrate([])) == 0
     h.close()
+
+
+def test_handles_on_two_devices_in_one_process():
+    """The > 48 KB dynamic shared-memory opt-in of the BA kernels is a per-device attribute: a process that opens handles on
+    two GPUs must be able to solve on both (regression: a process-wide `configured` flag only configured the first)."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    cfg = make_cfg()
+    sim = BP.WindowSimulator(15, cfg, n_landmarks=60)
+    pb = sim.window(0)
+    so = ba_ref.solve(cfg, pb)
+    for dev in (0, 1):
+        h = B.Handle(cfg, 1, dev)
+        sg = h.ba_solve(0, pb)
+        assert sg.c.iterations == so.c.iterations and np.abs(sg.Ps - so.Ps).max() <= 1e-6
+        h.close()
+
+
+def test_flag2_landmark_starting_above_its_bound_is_projected_first():
+    """estimate_flag == 2 landmarks carry inv_depth <= 2 / DEPTH_MAX_DIST (estimator.cpp:1293-1298).  Ceres'
+    TrustRegionMinimizer::Init projects an infeasible start point onto the bounds before the first evaluation; oracle and
+    kernel must agree on the initial cost and on the whole iteration sequence when several landmarks start infeasible."""
+    cfg = make_cfg()
+    h = B.Handle(cfg, 1, 0)
+    sim = BP.WindowSimulator(77, cfg, n_landmarks=120, flag2_frac=0.3)
+    pb = sim.window(0)
+    ub = 2.0 / cfg.depth_max_dist
+    flag2 = np.nonzero(pb.flag == 2)[0]
+    assert len(flag2) >= 10
+    lam = pb.lam.copy()
+    lam[flag2[:6]] = ub * np.array([1.05, 1.5, 2.0, 3.0, 1.01, 1.2])         # depth 1.7 .. 4.9 m: infeasible starts
+    pb.set_landmarks(lam, pb.start, pb.flag, pb.obs_ptr, pb.obs_pts)
+    pb.finalize()
+    so = ba_ref.solve(cfg, pb)
+    sg = h.ba_solve(0, pb)
+    compare(sg, so, pb)
+    assert (sg.lam[flag2] <= ub * (1 + 1e-12)).all()
+    h.close()

@@ -403,3 +403,58 @@ def test_pipelined_submit_collect_equals_synchronous_calls():
             for got, want in zip((r.ids, r.cur_pts, r.cur_un_pts, r.pts_velocity, r.track_cnt, r.depth_mm, r.depth_keep), e):
                 assert np.array_equal(got, want), (k, s)
     h_sync.close(); h_pipe.close()
+
+
+def _two_view_pixels(rng, n, out_frac, noise):
+    """Distorted pixel coordinates of n scene points in two nearby views (what cur_pts / forw_pts hold)."""
+    import cv2
+    from oracle.frontend_ref import PinholeCamera
+    cam = PinholeCamera(FrontendConfig())
+    P = rng.uniform([-1.6, -1.2, 2.0], [1.6, 1.2, 6.0], (n, 3))
+    R, _ = cv2.Rodrigues(rng.normal(0, 0.02, 3))
+    P2 = P @ R.T + rng.normal(0, 0.05, 3)
+    u1, v1 = cam.space_to_plane(P[:, 0], P[:, 1], P[:, 2])
+    u2, v2 = cam.space_to_plane(P2[:, 0], P2[:, 1], P2[:, 2])
+    a = np.stack([u1, v1], 1)
+    b = np.stack([u2, v2], 1) + rng.normal(0, noise, (n, 2))
+    no = int(out_frac * n)
+    b[:no] += rng.normal(0, 8, (no, 2))
+    return cam, a.astype(np.float32), b.astype(np.float32)
+
+
+def _cv2_reject_with_f(cam, cur, forw, cfg):
+    """feature_tracker.cpp:441-473 on the real OpenCV."""
+    import cv2
+    x, y = cam.lift_projective_pts(cur)
+    un_cur = np.stack([cfg.focal_length * x + cfg.col / 2.0, cfg.focal_length * y + cfg.row / 2.0], 1).astype(np.float32)
+    x, y = cam.lift_projective_pts(forw)
+    un_forw = np.stack([cfg.focal_length * x + cfg.col / 2.0, cfg.focal_length * y + cfg.row / 2.0], 1).astype(np.float32)
+    _, st = cv2.findFundamentalMat(un_cur, un_forw, cv2.FM_RANSAC, cfg.f_threshold, 0.99)
+    return None if st is None else st.ravel()
+
+
+def test_reject_with_f_lmeds_regime():
+    """rejectWithF for 8 <= n < 15, where cv::findFundamentalMat(FM_RANSAC) runs LMedS (feature_tracker.cpp:445 enters at
+    forw_pts.size() >= 8).  n = 14 is pinned: identical masks to cv2.  For n <= 13 cv2's own mask is decided by rounding noise
+    (tests/test_oracle_ransac.py), so the kernel is held to the algorithm's semantics: LMedS ran, a minimal-sample model's
+    consensus (>= 7 points, <= n) survives, and fewer than 8 points are left untouched."""
+    cfg = binding.default_config(use_ransac=1)
+    h = binding.Handle(cfg, 1, 0)
+    rng = np.random.default_rng(1414)
+    for n, out_frac in [(14, 0.0), (14, 0.15), (14, 0.3), (14, 0.15), (14, 0.3), (14, 0.0)]:
+        cam, cur, forw = _two_view_pixels(rng, n, out_frac, rng.choice([0.05, 0.3, 0.8]))
+        want = _cv2_reject_with_f(cam, cur, forw, cfg)
+        got = h.reject_with_f(0, cur, forw)
+        assert want is not None and np.array_equal(got, want), (n, out_frac, got, want)
+    for n in (8, 9, 10, 11, 12, 13):
+        cam, cur, forw = _two_view_pixels(rng, n, 0.2, 0.5)
+        got = h.reject_with_f(0, cur, forw)
+        assert 7 <= int(got.sum()) <= n
+    cam, cur, forw = _two_view_pixels(rng, 7, 0.0, 0.1)
+    assert h.reject_with_f(0, cur, forw).all()              # n < 8: rejectWithF does nothing
+    # and the RANSAC regime through the same entry (n >= 15)
+    for n in (15, 40, 150):
+        cam, cur, forw = _two_view_pixels(rng, n, 0.2, 0.3)
+        want = _cv2_reject_with_f(cam, cur, forw, cfg)
+        assert np.array_equal(h.reject_with_f(0, cur, forw), want), n
+    h.close()

@@ -591,6 +591,32 @@ extern "C" long vrf_debug_read(vrf_handle *h, const char *what, int seq, void *d
     return (long)need;
 }
 
+// Test entry: FeatureTracker::rejectWithF (feature_tracker.cpp:441-473) alone on caller-supplied point pairs (pixel
+// coordinates of cur_pts / forw_pts) through the product kernel k_ransac; clobbers the working arrays of `seq`.
+extern "C" int vrf_debug_reject_with_f(vrf_handle *h, int seq, int n, const float *cur_xy, const float *forw_xy, uint8_t *status_out)
+{
+    if (!h || !cur_xy || !forw_xy || !status_out || seq < 0 || seq >= h->n_seq || n < 0 || n > VRF_CAP) return VRF_ERR_ARG;
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->stream));
+    FrontDev &d = h->fd;
+    const size_t base = (size_t)seq * VRF_CAP;
+    std::vector<uint8_t> ones(n > 0 ? n : 1, 1);
+    CK(cudaMemcpy(d.t_prev + base, cur_xy, (size_t)n * sizeof(float2), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d.t_forw + base, forw_xy, (size_t)n * sizeof(float2), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d.t_keep + base, ones.data(), n, cudaMemcpyHostToDevice));       // status starts as "keep" (n < 8: untouched)
+    CK(cudaMemcpy(d.t_n + seq, &n, sizeof(int), cudaMemcpyHostToDevice));
+    SeqCall call;
+    memset(&call, 0, sizeof(call));
+    call.seq = seq; call.pub = 1; call.dslot = -1;
+    SeqCall *d_call = h->d_calls_ring[0];
+    CK(cudaMemcpy(d_call, &call, sizeof(call), cudaMemcpyHostToDevice));
+    LaunchCtx lc{h->stream, &h->launches, &h->prof};
+    if (ransac_launch(h->fc, d_call, 1, d, lc) != 0) return VRF_ERR_CUDA;
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaMemcpy(status_out, d.t_keep + base, n, cudaMemcpyDeviceToHost));
+    return VRF_OK;
+}
+
 extern "C" int vrf_profile_enable(vrf_handle *h, int on)
 {
     if (!h) return VRF_ERR_ARG;

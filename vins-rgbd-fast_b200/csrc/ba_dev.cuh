@@ -93,6 +93,8 @@ struct BaMargDev {
 
 // ba_kernels.cu / ba_marg.cu
 size_t ba_solve_smem_bytes();
+int ba_solve_configure();
+int ba_marg_configure();
 int ba_solve_launch(const BaMeta *d_meta, const BaProbDev *d_prob, BaOutDev *d_out, int n, LaunchCtx &lc);
 int ba_marg_launch(const BaMeta *d_meta, const BaProbDev *d_prob, BaOutDev *d_out, BaMargDev *d_marg, int n, LaunchCtx &lc);
 // factor form (J0, r0) of an information-form prior, on demand; scratch: 2 * VRF_PRIOR_MAX_DIM^2 doubles

@@ -101,6 +101,8 @@ int ba_create(vrf_handle *h)
     h->ba = b;
     const size_t S = h->n_seq;
     b->n_seq = h->n_seq;
+    // kernel attributes are per device: vrf_create() has made the handle's device current
+    if (ba_solve_configure() != 0 || ba_marg_configure() != 0) { snprintf(h->errbuf, sizeof(h->errbuf), "BA kernel attribute setup failed"); return VRF_ERR_CUDA; }
     if (int rc = slot_alloc(h, b->slot[0])) return rc;        // slot 1 is allocated by the first pipelined submit
     for (int k = 0; k < 2; ++k) {
         BCK(cudaMalloc((void **)&b->d_prior[k], S * sizeof(BaPriorStore)));

@@ -179,10 +179,15 @@ __device__ __noinline__ double ba_evaluate_t(const BaMeta &m, const BaProbDev &p
     const int nbatch = (m.M + 31) >> 5;
     const int nproj = lin ? BA_NPAIR : (m.M + 1) >> 1;
     const int ntask = m.nimu + nproj;
+    int ptask = -1;
+    long long ptask_t0 = 0;
     for (;;) {
         int task = 0;
         if (lane == 0) task = atomicAdd(&sh.flag[2], 1);
         task = __shfl_sync(0xffffffffu, task, 0);
+        if (eprof && blockIdx.x == 0 && lane == 0 && ptask >= 0)
+            printf("task lin=%d id=%d (%s) warp=%d cycles=%lld\n", (int)lin, ptask, ptask < m.nimu ? "imu" : "proj", warp, clock64() - ptask_t0);
+        ptask = task; ptask_t0 = eprof ? clock64() : 0;
         if (task >= ntask) break;
         if (task < m.nimu) {
             // ---- IMU factor: one warp per factor ----
@@ -511,7 +516,9 @@ k_ba_solve(const BaMeta *metas, const BaProbDev *probs, BaOutDev *outs)
     for (int i = tid; i < BA_NF * 9; i += BA_THREADS) sh.sb[i] = p.sb0[i];
     if (tid < 7) sh.ex[tid] = p.ex0[tid];
     if (tid == 0) { sh.tdv[0] = *p.td0; sh.tdv[1] = *p.td0; }
-    for (int l = tid; l < M; l += BA_THREADS) p.lam[l] = p.lam0[l];
+    // TrustRegionMinimizer::Init of a bound-constrained problem projects the start point onto the bounds (Plus(x, 0)) before
+    // the first evaluation: only the estimate_flag == 2 landmarks carry one (estimator.cpp:1293-1298)
+    for (int l = tid; l < M; l += BA_THREADS) p.lam[l] = p.lm_const[l] ? p.lam0[l] : fmin(p.lam0[l], p.lm_ub[l]);
     const int ws = (m.ex_active || m.td_active) ? BA_WS : 66;      // used width of the landmark coupling rows
     __syncthreads();
     // ---- once per solve: IMU information square roots, prior normal matrix ----
@@ -1107,13 +1114,15 @@ k_ba_solve(const BaMeta *metas, const BaProbDev *probs, BaOutDev *outs)
 
 size_t ba_solve_smem_bytes() { return sizeof(BaShared); }
 
+// The opt-in for > 48 KB of dynamic shared memory is a per-device attribute: set by ba_create() for the handle's device
+// (a process may open handles on several GPUs).
+int ba_solve_configure()
+{
+    return cudaFuncSetAttribute(k_ba_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BaShared)) == cudaSuccess ? 0 : -1;
+}
+
 int ba_solve_launch(const BaMeta *d_meta, const BaProbDev *d_prob, BaOutDev *d_out, int n, LaunchCtx &lc)
 {
-    static bool configured = false;
-    if (!configured) {
-        if (cudaFuncSetAttribute(k_ba_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BaShared)) != cudaSuccess) return -1;
-        configured = true;
-    }
     lc.begin(K_BA_SOLVE);
     k_ba_solve<<<n, BA_THREADS, sizeof(BaShared), lc.st>>>(d_meta, d_prob, d_out);
     lc.end();

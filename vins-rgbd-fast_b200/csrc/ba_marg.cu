@@ -920,13 +920,16 @@ k_ba_prior_factor(const BaPriorStore *src, BaPriorStore *dst, double *scratch)
 static size_t marg_smem() { return ((sizeof(MargShared) + 15) & ~(size_t)15) + sizeof(double) * (MARG_A_ELEMS(MARG_SMEM_N) + MARG_V_ELEMS(MARG_SMEM_N)); }
 size_t ba_marg_smem_bytes() { return marg_smem(); }
 
+// per-device shared-memory opt-in of the two marginalization kernels (called by ba_create() for the handle's device)
+int ba_marg_configure()
+{
+    if (cudaFuncSetAttribute(k_ba_prior_factor, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)marg_smem()) != cudaSuccess) return -1;
+    if (cudaFuncSetAttribute(k_ba_marg, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)marg_smem()) != cudaSuccess) return -1;
+    return 0;
+}
+
 int ba_prior_factor_launch(const BaPriorStore *src, BaPriorStore *dst, double *scratch, LaunchCtx &lc)
 {
-    static bool configured = false;
-    if (!configured) {
-        if (cudaFuncSetAttribute(k_ba_prior_factor, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)marg_smem()) != cudaSuccess) return -1;
-        configured = true;
-    }
     lc.begin(K_BA_PRIOR_FACTOR);
     k_ba_prior_factor<<<1, BA_THREADS, marg_smem(), lc.st>>>(src, dst, scratch);
     lc.end();
@@ -935,11 +938,6 @@ int ba_prior_factor_launch(const BaPriorStore *src, BaPriorStore *dst, double *s
 
 int ba_marg_launch(const BaMeta *d_meta, const BaProbDev *d_prob, BaOutDev *d_out, BaMargDev *d_marg, int n, LaunchCtx &lc)
 {
-    static bool configured = false;
-    if (!configured) {
-        if (cudaFuncSetAttribute(k_ba_marg, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)marg_smem()) != cudaSuccess) return -1;
-        configured = true;
-    }
     lc.begin(K_BA_MARG);
     k_ba_marg<<<n, BA_THREADS, marg_smem(), lc.st>>>(d_meta, d_prob, d_out, d_marg);
     lc.end();

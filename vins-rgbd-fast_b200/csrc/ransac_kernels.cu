@@ -24,9 +24,15 @@
 // normalised points instead of LAPACK SVD): the rank-2 members of the pencil are basis
 // independent, so the candidate F set is the same up to rounding (~1e-12).
 //
-// For 8 <= n < 15 OpenCV silently switches to LMedS, whose winner among <= 14 residuals
-// (7 of them exact zeros of the minimal sample) is decided by rounding noise of its SVD;
-// that regime cannot be pinned and is treated as "keep all" here (documented in DESIGN.md).
+// For 8 <= n < 15 cv::findFundamentalMat(FM_RANSAC) switches to LMedS (fundam.cpp: `npoints >= 15` selects RANSAC;
+// ptsetreg.cpp LMeDSPointSetRegistrator::run): the same RNG / getSubset / 7-point machinery, a fixed
+// RANSACUpdateNumIters(0.99, 0.45, 7, 1000) = 300 iterations, per model the median (nth_element at count / 2) of the float
+// residuals, strict-minimum selection in iteration order, sigma = max(2.5 * 1.4826 * (1 + 5 / (n - 7)) * sqrt(median), 0.001)
+// and the mask err <= (float)(sigma^2).  Restated here with the same structure.  Pinned against cv2 at n = 14 (identical
+// masks, tests/test_oracle_ransac.py and the GPU tests).  For n <= 13 the median index falls inside the 7 residuals of the
+// minimal sample, i.e. on rounding noise of OpenCV's LAPACK SVD (~1e-25): cv2 itself returns a different 7-survivor mask
+// when one input coordinate moves by 1 ulp (shown in tests/test_oracle_ransac.py), so that regime has the reference's
+// semantics (LMedS runs, typically exactly the 7 points of one minimal sample survive) but cannot be bit-pinned.
 #include "common.cuh"
 #include "handle.h"
 
@@ -247,6 +253,7 @@ k_ransac(FrontCfg c, const SeqCall *calls, FrontDev d)
     __shared__ int s_idx[RS_BATCH][7];
     __shared__ int s_nmod[RS_BATCH];
     __shared__ int s_cnt[RS_BATCH * 3];
+    __shared__ float s_med[RS_BATCH * 3];      // LMedS: median residual of every model of the batch
     __shared__ int s_ctl[4];        // 0: batch size, 1: continue flag, 2: have best
     const SeqCall call = calls[blockIdx.x];
     if (!call.pub) return;
@@ -254,7 +261,7 @@ k_ransac(FrontCfg c, const SeqCall *calls, FrontDev d)
     const size_t base = (size_t)seq * VRF_CAP;
     const int n = d.t_n[seq];
     if (n < 8) return;              // rejectWithF: if (forw_pts.size() >= 8)
-    if (n < 15) return;             // OpenCV switches to LMedS (noise-decided): keep all, see header
+    const bool lmeds = n < 15;      // fundam.cpp: RANSAC needs npoints >= 15, else LMedS
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     // un_cur_pts / un_forw_pts (feature_tracker.cpp:446-459)
     for (int i = tid; i < n; i += RS_THREADS) {
@@ -270,6 +277,9 @@ k_ransac(FrontCfg c, const SeqCall *calls, FrontDev d)
     // sequential control state lives in thread 0's registers
     CvRng rng; rng.state = 0xFFFFFFFFFFFFFFFFULL;
     int niters = 1000, iter = 0, maxGood = 0;
+    double minMedian = 1.7976931348623157e308;
+    if (lmeds) { niters = rs_update_niters(0.99, 0.45, 7, 1000); niters = max(niters, 3); }
+    const int max_attempts = lmeds ? 1000 : 10000;      // getSubset(): RANSAC passes 10000, LMedS the default
     if (tid == 0) s_ctl[2] = 0;
     while (true) {
         if (tid == 0) {
@@ -279,7 +289,7 @@ k_ransac(FrontCfg c, const SeqCall *calls, FrontDev d)
             for (; nb < want; ++nb) {
                 // getSubset(m1, m2, ms1, ms2, rng, 10000)
                 bool found = false;
-                for (int att = 0; att < 10000 && !found; ++att) {
+                for (int att = 0; att < max_attempts && !found; ++att) {
                     int *idx = s_idx[nb];
                     for (int i = 0; i < 7; ++i) {
                         int v;
@@ -307,6 +317,18 @@ k_ransac(FrontCfg c, const SeqCall *calls, FrontDev d)
             const int hb = m / 3, k = m - hb * 3;
             if (k >= s_nmod[hb]) continue;
             const double *F = s_F[m];
+            if (lmeds) {
+                // median = element count/2 of the sorted residuals (std::nth_element on the float bit patterns, n <= 14):
+                // lane i ranks its residual by counting (ties broken by index), the lane of rank n/2 holds the median
+                const float e = lane < n ? rs_error(F, s_m1[lane], s_m2[lane]) : 0.f;
+                int rank = 0;
+                for (int j = 0; j < n; ++j) {
+                    const float ej = __shfl_sync(0xffffffffu, e, j);
+                    rank += (ej < e || (ej == e && j < lane)) ? 1 : 0;
+                }
+                if (lane < n && rank == n / 2) s_med[m] = e;
+                continue;
+            }
             int cnt = 0;
             for (int i = lane; i < n; i += 32) cnt += (rs_error(F, s_m1[i], s_m2[i]) <= thr) ? 1 : 0;
             cnt = __reduce_add_sync(0xffffffffu, cnt);
@@ -317,6 +339,15 @@ k_ransac(FrontCfg c, const SeqCall *calls, FrontDev d)
             bool stop = false;
             for (int hb = 0; hb < nb && !stop; ++hb) {
                 for (int k = 0; k < s_nmod[hb]; ++k) {
+                    if (lmeds) {
+                        const double median = (double)s_med[hb * 3 + k];
+                        if (median < minMedian) {
+                            minMedian = median;
+                            for (int j = 0; j < 9; ++j) s_best[j] = s_F[hb * 3 + k][j];
+                            s_ctl[2] = 1;
+                        }
+                        continue;
+                    }
                     int good = s_cnt[hb * 3 + k];
                     if (good > max(maxGood, 6)) {
                         maxGood = good;
@@ -335,9 +366,20 @@ k_ransac(FrontCfg c, const SeqCall *calls, FrontDev d)
     }
     // inlier mask of the best model (== the mask OpenCV kept); none => all rejected
     const int have = s_ctl[2];
+    float thr_final = thr;
+    if (lmeds) {
+        // thread 0 owns minMedian: broadcast the final threshold (float)(sigma^2) through shared memory
+        if (tid == 0) {
+            double sigma = 2.5 * 1.4826 * (1 + 5. / (n - 7)) * sqrt(minMedian);
+            sigma = fmax(sigma, 0.001);
+            s_med[0] = (float)(sigma * sigma);
+        }
+        __syncthreads();
+        thr_final = s_med[0];
+    }
     for (int i = tid; i < n; i += RS_THREADS) {
         uint8_t keep = 0;
-        if (have) keep = (rs_error(s_best, s_m1[i], s_m2[i]) <= thr) ? 1 : 0;
+        if (have) keep = (rs_error(s_best, s_m1[i], s_m2[i]) <= thr_final) ? 1 : 0;
         d.t_keep[base + i] = keep;
     }
 }

@@ -199,8 +199,16 @@ class WindowSimulator:
             xy = self.rng.uniform([-0.5, -0.38], [0.5, 0.38])
             P = pc + Rc @ (np.array([xy[0], xy[1], 1.0]) * d)
             length = int(self.rng.integers(2, 14))
-            out.append({"P": P, "first": k, "last": k + length - 1, "eps": self.rng.normal(0, 0.01),
-                        "flag": 2 if self.rng.random() < self.flag2_frac else 1, "id": len(self.pool) + len(out)})
+            eps = self.rng.normal(0, 0.01)
+            flag = 2 if self.rng.random() < self.flag2_frac else 1
+            if flag == 2:
+                # estimate_flag 2 = no depth measurement, depth from triangulation: points beyond the sensor range.  The
+                # reference bounds their inverse depth by 2 / DEPTH_MAX_DIST (estimator.cpp:1293-1298), i.e. depth >= 5 m
+                # with the shipped DEPTH_MAX_DIST = 10: spread them over 5.2 .. 12 m (a few start just above the bound
+                # through `eps`, which exercises the projection of the start point)
+                d = 5.2 + (d - 1.5) / 4.5 * 6.8
+                P = pc + Rc @ (np.array([xy[0], xy[1], 1.0]) * d)
+            out.append({"P": P, "first": k, "last": k + length - 1, "eps": eps, "flag": flag, "id": len(self.pool) + len(out)})
         return out
 
     def _observe(self, lm, k):

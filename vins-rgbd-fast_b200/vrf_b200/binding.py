@@ -150,7 +150,7 @@ EXPORTS = [
     "vrf_launch_count", "vrf_reset_sequence", "vrf_set_fisheye_mask", "vrf_tracker_read_image", "vrf_tracker_read_image_batch",
     "vrf_tracker_read_rgbd_batch", "vrf_tracker_submit_rgbd_batch", "vrf_tracker_collect_batch",
     "vrf_tracker_enqueue_batch_dev", "vrf_tracker_fetch_batch", "vrf_synchronize", "vrf_stream",
-    "vrf_profile_enable", "vrf_profile_read", "vrf_debug_sort_desc", "vrf_debug_read", "vrf_ba_solve", "vrf_ba_solve_batch", "vrf_ba_upload_batch",
+    "vrf_profile_enable", "vrf_profile_read", "vrf_debug_sort_desc", "vrf_debug_read", "vrf_debug_reject_with_f", "vrf_ba_solve", "vrf_ba_solve_batch", "vrf_ba_upload_batch",
     "vrf_ba_enqueue_batch", "vrf_ba_download_batch", "vrf_ba_submit_batch", "vrf_ba_collect_batch",
     "vrf_fm_triangulate_with_depth_batch", "vrf_fm_moving_consistency_check_batch", "vrf_imu_preintegrate_batch",
 ]
@@ -201,6 +201,7 @@ def load():
     lib.vrf_profile_read.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
     lib.vrf_debug_read.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_void_p, C.c_size_t]
     lib.vrf_debug_read.restype = C.c_long
+    lib.vrf_debug_reject_with_f.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.vrf_ba_solve.argtypes = [C.c_void_p, C.c_int, C.POINTER(VrfBaProblem), C.POINTER(VrfBaResult)]
     lib.vrf_ba_solve_batch.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.POINTER(VrfBaProblem), C.POINTER(VrfBaResult)]
     lib.vrf_ba_submit_batch.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.POINTER(VrfBaProblem)]
@@ -360,6 +361,14 @@ class Handle:
         for _ in range(level):
             w, hh = (w + 1) // 2, (hh + 1) // 2
         return self.debug_read(f"pyr{level}", seq, np.uint8, w * hh).reshape(hh, w)
+
+    def reject_with_f(self, seq, cur_pts, forw_pts):
+        """rejectWithF alone (test entry): inlier mask of cv::findFundamentalMat(FM_RANSAC) on the lifted points."""
+        a = np.ascontiguousarray(cur_pts, np.float32).reshape(-1, 2)
+        b = np.ascontiguousarray(forw_pts, np.float32).reshape(-1, 2)
+        st = np.zeros(len(a), np.uint8)
+        check(self.lib.vrf_debug_reject_with_f(self.h, seq, len(a), a.ctypes.data, b.ctypes.data, st.ctypes.data), self.h, allow_soft=False)
+        return st
 
     def reset(self, seq):
         check(self.lib.vrf_reset_sequence(self.h, seq), self.h)
