@@ -37,7 +37,7 @@ struct IntegrationBase {
     std::vector<double> dt_buf; std::vector<V3> acc_buf, gyr_buf;
 };
 struct Estimator {
-    int frame_count = 10, marginalization_flag = 0; bool openExEstimation = false;
+    int frame_count = 10, marginalization_flag = 0; bool openExEstimation = false, relocalization_info = false;
     double para_Pose[11][7] = {}, para_SpeedBias[11][9] = {}, para_Feature[1000][1] = {}, para_Ex_Pose[1][7] = {}, para_Td[1][1] = {};
     V3 Ps[11], Vs[11], Bas[11], Bgs[11], tic[1]; M3 Rs[11], ric[1]; double td = 0;
     FeatureManager f_manager; IntegrationBase *pre_integrations[11] = {};
@@ -51,6 +51,7 @@ int main()
     int (*f2)(Estimator &, vrf_handle *) = &vrf_host::triangulateWithDepth<Estimator>;
     int (*f3)(Estimator &, vrf_handle *, std::set<int> &) = &vrf_host::movingConsistencyCheck<Estimator>;
     int (*f4)(IntegrationBase &, vrf_handle *) = &vrf_host::preintegrate<IntegrationBase>;
+    { FeatureTracker unattached; (void)unattached; }      // default-constructible
     std::printf("shims instantiated: %d\n", (f1 != nullptr) + (f2 != nullptr) + (f3 != nullptr) + (f4 != nullptr));
     VrfConfig cfg;
     vrf_config_default(&cfg);
@@ -59,10 +60,13 @@ int main()
     std::printf("vrf_create rc %d\n", rc);
     if (rc == VRF_OK) {
         // the class surface of the reference: construct, feed one texture-less frame, read the public members
-        FeatureTracker ft(h, 0, cfg);
+        // (default construction + attach(), as a by-value member of the reference's Estimator needs, estimator.h:117)
+        FeatureTracker ft;
+        ft.attach(h, 0, cfg);
         std::vector<unsigned char> img((size_t)cfg.row * cfg.col, 128);
         cv::Mat m; m.rows = cfg.row; m.cols = cfg.col; m.step = cfg.col; m.data = img.data();
-        ft.readImage(m, 0.0);
+        PUB_THIS_FRAME = true;
+        ft.readImage(m, 0.0);                     // the reference's 3-argument signature
         std::printf("readImage: %zu features, updateID(0) %d\n", ft.cur_pts.size(), (int)ft.updateID(0));
         vrf_destroy(h);
     }

@@ -80,6 +80,10 @@ static int build_front_cfg(const VrfConfig &cfg, FrontCfg &fc)
     memset(&fc, 0, sizeof(fc));
     if (cfg.row < 64 || cfg.col < 64 || (cfg.col & 15)) return VRF_ERR_ARG;   // uint4 row access
     if (cfg.max_cnt <= 0 || cfg.max_cnt > VRF_CAP / 2 || cfg.min_dist < 1) return VRF_ERR_ARG;
+    // FOCAL_LENGTH is a compile-time constant of the reference (parameters.h:11) that enters rejectWithF, ProjectionFactor's
+    // sqrt_info (= 460 / 1.5, estimator.cpp:23) and movingConsistencyCheck alike: the BA kernels fix it too, so a handle
+    // whose front end would use another value is refused rather than silently inconsistent.
+    if (cfg.focal_length != 460.0) return VRF_ERR_ARG;
     fc.rows = cfg.row; fc.cols = cfg.col;
     int maxLevel = cfg.lk_max_level < 0 ? (cfg.use_imu ? 1 : 3) : cfg.lk_max_level;
     if (maxLevel > VRF_MAX_LEVELS - 1) return VRF_ERR_ARG;

@@ -156,7 +156,9 @@ int ba_reset_sequence(vrf_handle *h, int seq)
 static int pack_problem(vrf_handle *h, BaSlot &sl, int slot, int seq, const VrfBaProblem *pb)
 {
     BaState *b = h->ba;
-    if (!pb || pb->n_landmarks < 0 || pb->n_landmarks > BA_MAX_LM || pb->n_obs > BA_MAX_OBS) return VRF_ERR_CAPACITY;
+    if (!pb || pb->n_landmarks < 0 || pb->n_obs < 0) return VRF_ERR_ARG;
+    if (pb->n_landmarks > BA_MAX_LM || pb->n_obs > BA_MAX_OBS) return VRF_ERR_CAPACITY;
+    if (pb->n_landmarks > 0 && pb->lm_obs_ptr && pb->lm_obs_ptr[0] != 0) return VRF_ERR_ARG;      // CSR offsets start at 0
     if (pb->frame_count < 1 || pb->frame_count > VRF_WINDOW_SIZE) return VRF_ERR_ARG;
     const int td_factor = h->cfg.estimate_td != 0;
     if (td_factor && pb->n_landmarks > 0 && (!pb->obs_velocity || !pb->obs_cur_td || !pb->obs_row)) return VRF_ERR_ARG;

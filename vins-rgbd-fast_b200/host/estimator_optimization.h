@@ -65,7 +65,8 @@ int optimization(EstimatorT &e, vrf_handle *h, int seq, bool first_call_after_re
     pb.lm_obs_ptr = ptr.data(); pb.obs_pts = obs.data();
     if (estimate_td) { pb.obs_velocity = vel.data(); pb.obs_cur_td = ctd.data(); pb.obs_row = row.data(); }
     std::vector<VrfImuPreint> imu(VRF_WINDOW_SIZE);
-    for (int j = 1; j <= e.frame_count; ++j) {
+    // without IMU the reference never allocates pre_integrations[] (processIMU is not called): nothing to gather
+    for (int j = 1; use_imu && j <= e.frame_count; ++j) {
         const auto &p = *e.pre_integrations[j];
         VrfImuPreint &o = imu[j - 1];
         o.sum_dt = p.sum_dt;
@@ -73,7 +74,10 @@ int optimization(EstimatorT &e, vrf_handle *h, int seq, bool first_call_after_re
         o.delta_q[0] = p.delta_q.x(); o.delta_q[1] = p.delta_q.y(); o.delta_q[2] = p.delta_q.z(); o.delta_q[3] = p.delta_q.w();
         for (int r = 0; r < 15; ++r) for (int c = 0; c < 15; ++c) { o.jacobian[r * 15 + c] = p.jacobian(r, c); o.covariance[r * 15 + c] = p.covariance(r, c); }
     }
-    pb.imu = imu.data();
+    pb.imu = use_imu ? imu.data() : nullptr;
+    // Relocalisation residuals (estimator.cpp:1307-1346) are not part of the device problem: refuse instead of solving
+    // a different problem (loop_closure is 0 in every shipped configuration of this path)
+    if (e.relocalization_info) return VRF_ERR_UNSUPPORTED;
     pb.prior = first_call_after_reset ? nullptr : VRF_PRIOR_DEVICE;       // last_marginalization_info stays in HBM
     VrfBaResult res{};
     std::vector<double> lam_out(lam.size());
@@ -89,9 +93,9 @@ int optimization(EstimatorT &e, vrf_handle *h, int seq, bool first_call_after_re
     }
     for (size_t l = 0; l < lam_out.size(); ++l) e.para_Feature[l][0] = lam_out[l];
     // double2vector: tic/ric <- para_Ex_Pose, td <- para_Td (estimator.cpp:1033-1060)
-    for (int k = 0; k < 7; ++k) e.para_Ex_Pose[0][k] = res.para_Ex_Pose[k];
-    e.para_Td[0][0] = res.para_Td;
     if (use_imu) {
+        for (int k = 0; k < 7; ++k) e.para_Ex_Pose[0][k] = res.para_Ex_Pose[k];
+        e.para_Td[0][0] = res.para_Td;
         for (int k = 0; k < 3; ++k) e.tic[0](k) = res.para_Ex_Pose[k];
         // ric = Quaterniond(w, x, y, z).normalized().toRotationMatrix()
         double q[4] = {res.para_Ex_Pose[3], res.para_Ex_Pose[4], res.para_Ex_Pose[5], res.para_Ex_Pose[6]};

@@ -28,17 +28,39 @@ namespace Eigen { struct Matrix3d { double m[9]; static Matrix3d Identity() { Ma
 #include <opencv2/opencv.hpp>
 #endif
 
+// The reference publishes on a frame iff the unsynchronised global PUB_THIS_FRAME is set (utility/parameters.h; written by
+// the nodelet, estimator_nodelet.cpp:274-286, read inside readImage).  Inside the reference's tree the shim reads that very
+// global; stand-alone it owns one.
+#ifdef VRF_SHIM_STANDALONE
+inline bool PUB_THIS_FRAME = false;
+#else
+extern bool PUB_THIS_FRAME;
+#endif
+
 class FeatureTracker
 {
 public:
-    // `cfg` replaces the extern globals of utility/parameters.h; `handle`/`seq` select the
-    // sequence slot inside a (possibly shared, batched) vrf_handle.
-    FeatureTracker(vrf_handle *handle, int seq, const VrfConfig &cfg) : h_(handle), seq_(seq), cfg_(cfg), n_id(0)
+    // Default-constructible like the reference's (`FeatureTracker featureTracker;` is a by-value member of Estimator,
+    // estimator.h:117): the sequence slot inside a (possibly shared, batched) vrf_handle is bound later with attach(),
+    // e.g. from Estimator::setParameter() where the reference loads the intrinsics (estimator.cpp:25-35).
+    FeatureTracker() : n_id(0), h_(nullptr), seq_(-1), cfg_() {}
+    // `cfg` replaces the extern globals of utility/parameters.h
+    FeatureTracker(vrf_handle *handle, int seq, const VrfConfig &cfg) : n_id(0), h_(nullptr), seq_(-1), cfg_() { attach(handle, seq, cfg); }
+
+    void attach(vrf_handle *handle, int seq, const VrfConfig &cfg)
     {
+        h_ = handle; seq_ = seq; cfg_ = cfg;
         const size_t cap = VRF_TRACK_CAP;
         b_pts_.resize(2 * cap); b_un_.resize(2 * cap); b_vel_.resize(2 * cap); b_pred_.resize(2 * cap);
         b_ids_.resize(cap); b_cnt_.resize(cap); b_dmm_.resize(cap); b_dkeep_.resize(cap);
         grids_track_num.assign(cfg.num_grid_rows * cfg.num_grid_cols, 0);
+    }
+
+    // The reference's own signature (feature_tracker.h:36-37, call site estimator_nodelet.cpp:313): publish decision from the
+    // global PUB_THIS_FRAME.
+    void readImage(const cv::Mat &_img, double _cur_time, const Eigen::Matrix3d &_relative_R = Eigen::Matrix3d::Identity())
+    {
+        readImage(_img, _cur_time, _relative_R, PUB_THIS_FRAME);
     }
 
     // feature_tracker.cpp:263-439 (+ the nodelet's updateID loop, estimator_nodelet.cpp:324-330).
@@ -46,9 +68,10 @@ public:
     // `depth` (optional): the depth frame the nodelet pairs with this image (estimator_nodelet.cpp:206-225); its decode
     // (:512-533) and the per-feature lookup + DEPTH_MIN_DIST test of FeatureManager::addFeatureCheckParallax
     // (feature_manager.cpp:71-80) then run on the device: results in depth_mm / depth_keep.
-    void readImage(const cv::Mat &_img, double _cur_time, const Eigen::Matrix3d &_relative_R = Eigen::Matrix3d::Identity(),
-                   bool pub_this_frame = true, const void *depth = nullptr, size_t depth_step = 0, int depth_fmt = VRF_DEPTH_NONE)
+    void readImage(const cv::Mat &_img, double _cur_time, const Eigen::Matrix3d &_relative_R, bool pub_this_frame,
+                   const void *depth = nullptr, size_t depth_step = 0, int depth_fmt = VRF_DEPTH_NONE)
     {
+        if (!h_) throw std::runtime_error("FeatureTracker::readImage before attach()");
         double R[9];
         for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) R[r * 3 + c] = _relative_R(r, c);
         VrfTrackOut o{};
