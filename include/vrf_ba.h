@@ -129,7 +129,9 @@ typedef struct VrfBaResult {
     double  Bgs[VRF_NUM_FRAMES][3];
     /* new prior (valid iff has_new_prior; produced when frame_count == WINDOW_SIZE) */
     int32_t has_new_prior;
-    int32_t reserved;
+    int32_t armijo_failures;    /* diagnostic: trust-region steps of a bound-constrained problem (estimate_flag == 2 landmarks,
+                                   estimator.cpp:1293-1298) that fail Ceres' Armijo test at step size 1, i.e. where Ceres'
+                                   projected line search -- not restated by this library -- would have shortened the step */
     VrfPrior *new_prior;        /* caller-allocated, may be NULL to skip the copy-out */
 } VrfBaResult;
 

@@ -884,6 +884,7 @@ static void state_plus(const VrfBaProblem *pb, const Lin *L, const State *x, con
 /* ------------------------------------------------------------------ */
 typedef struct {
     int iterations, successful, termination;
+    int armijo_failures;    /* steps of a bound-constrained problem that fail Ceres' Armijo test at step size 1 (see below) */
     double initial_cost, final_cost;
 } SolveSummary;
 
@@ -950,7 +951,10 @@ static int solve(const VrfBaProblem *pb, const VrfConfig *cfg, Lin *L, State *x,
     for (int l = 0; l < M; l++)
         if (!L->lm_const[l] && x->lam[l] > L->lm_ub[l]) x->lam[l] = L->lm_ub[l];
     double x_cost = evaluate(pb, cfg, L, x, 1);
-    sum->initial_cost = x_cost; sum->iterations = 0; sum->successful = 0; sum->termination = 0;
+    sum->initial_cost = x_cost; sum->iterations = 0; sum->successful = 0; sum->termination = 0; sum->armijo_failures = 0;
+    /* Solver::Options::is_constrained: some non-constant parameter block carries a bound */
+    int constrained = 0;
+    for (int l = 0; l < M; l++) if (!L->lm_const[l] && isfinite(L->lm_ub[l])) constrained = 1;
     /* Jacobi scaling, computed once at iteration 0 */
     {
         CtxColNorm cn = {NULL, tmp};
@@ -1102,6 +1106,16 @@ static int solve(const VrfBaProblem *pb, const VrfConfig *cfg, Lin *L, State *x,
                 for (int c = 0; c < NT; c++) delta[c] = step[c] * jscale[c];
                 apply_delta(L, x, delta, &cand, lam2);
                 double cand_cost = evaluate(pb, cfg, L, &cand, 0);
+                /* For a bound-constrained problem Ceres runs a projected Armijo line search on the step before evaluating the
+                 * candidate (TrustRegionMinimizer::DoLineSearch: sufficient decrease 1e-4, cubic interpolation).  When the full
+                 * step passes the test, f(x [+] delta) <= f(x) + 1e-4 g.delta, the search returns step size 1 and nothing
+                 * changes -- the case restated here.  When it fails, Ceres shortens the step (NOT restated: unverifiable
+                 * without Ceres); such steps are counted so that callers and tests can see where the two can differ. */
+                if (constrained) {
+                    double gts = 0;
+                    for (int c = 0; c < NT; c++) gts += g[c] * step[c];        /* = unscaled gradient . unscaled step */
+                    if (cand_cost > x_cost + 1e-4 * gts) sum->armijo_failures++;
+                }
                 double step_norm = sqrt(active_x_norm2_diff(L, x, &cand));
                 if (step_norm <= 1e-8 * (x_norm + 1e-8)) { sum->termination = 3; break; }      /* parameter tolerance */
                 double cost_change = x_cost - cand_cost;
@@ -1490,6 +1504,7 @@ int oracle_ba_solve(const VrfConfig *cfg, const VrfBaProblem *pb, VrfBaResult *r
     SolveSummary sum;
     int rc = solve(pb, cfg, &L, &x, &sum);
     res->status = rc; res->iterations = sum.iterations; res->successful_steps = sum.successful;
+    res->armijo_failures = sum.armijo_failures;
     res->termination = sum.termination; res->initial_cost = sum.initial_cost; res->final_cost = sum.final_cost;
     memcpy(res->para_Pose, x.pose, sizeof(x.pose)); memcpy(res->para_SpeedBias, x.sb, sizeof(x.sb));
     memcpy(res->para_Ex_Pose, x.ex, sizeof(x.ex)); res->para_Td = x.td;

@@ -30,6 +30,7 @@ def make_cfg(**kw):
 def compare(sol_g, sol_o, pb, tol=POSE_TOL):
     cg, co = sol_g.c, sol_o.c
     assert (cg.iterations, cg.successful_steps, cg.termination) == (co.iterations, co.successful_steps, co.termination)
+    assert cg.armijo_failures == co.armijo_failures          # steps where Ceres' projected line search would have engaged
     assert abs(cg.initial_cost - co.initial_cost) <= 1e-9 * co.initial_cost
     assert abs(cg.final_cost - co.final_cost) <= 1e-7 * co.final_cost
     assert np.abs(sol_g.pose[:, :3] - sol_o.pose[:, :3]).max() <= tol
@@ -211,7 +212,7 @@ def test_ba_pipelined_submit_collect_equals_synchronous():
             g, r = sols[j], ref[2 * i + j]
             assert (g.c.iterations, g.c.successful_steps) == (r.c.iterations, r.c.successful_steps)
             # (double atomics in the linearisation: summation order, hence the last bits, vary from run to run)
-            assert abs(g.c.final_cost - r.c.final_cost) <= 1e-10 * r.c.final_cost
+            assert abs(g.c.final_cost - r.c.final_cost) <= 1e-9 * r.c.final_cost      # run-to-run: FP64 atomics in the linearisation
             assert np.abs(g.Ps - r.Ps).max() <= 1e-9 and np.abs(g.pose - r.pose).max() <= 1e-9
             assert np.abs(g.lam[:pbs[2 * i + j].M] - r.lam[:pbs[2 * i + j].M]).max() <= 1e-9
     h.close(); h_sync.close()
@@ -274,3 +275,38 @@ def test_window_chain_at_config_sizes(n_landmarks):
         compare_prior(sg.new_prior, so.new_prior)
         sim.commit(a, so)
     h.close()
+
+
+def test_long_chain_device_prior_equals_host_round_trip():
+    """12 consecutive windows, two GPU chains from identical inputs: (a) the prior never leaves the device (information form
+    A', b', c0, no eigenvalue truncation); (b) after every window the prior is downloaded in the reference's factor form
+    (k_ba_prior_factor: eigenvalues <= 1e-8 zeroed, marginalization_factor.cpp:298-308) and uploaded again for the next
+    window.  The truncated part is below FP64 resolution of the products, so the two chains must stay together over the
+    whole run -- no drift of the device-resident prior away from the reference's form -- and both track the oracle chain."""
+    cfg = make_cfg()
+    hd, hr = B.Handle(cfg, 1, 0), B.Handle(cfg, 1, 0)
+    sims = [BP.WindowSimulator(19, cfg, n_landmarks=100) for _ in range(3)]      # device chain, round-trip chain, oracle chain
+    worst = 0.0
+    for a in range(12):
+        pbd, pbr, pbo = (s.window(a) for s in sims)
+        if a > 0:
+            pbd.c.prior = C.cast(C.c_void_p(1), C.POINTER(B.VrfPrior))          # VRF_PRIOR_DEVICE
+        sd = hd.ba_solve(0, pbd, want_prior=False)
+        sr = hr.ba_solve(0, pbr)                                                 # host prior in, factor-form prior out
+        so = ba_ref.solve(cfg, pbo)
+        sims[0].commit(a, sd); sims[1].commit(a, sr); sims[2].commit(a, so)
+        assert sd.c.has_new_prior == sr.c.has_new_prior == 1
+        d = max(np.abs(sd.Ps - sr.Ps).max(), np.abs(sd.Rs - sr.Rs).max())
+        worst = max(worst, d)
+        assert d <= 1e-6, (a, d)                                                 # the two prior forms do not drift apart
+        # The two forms are the same quadratic up to the directions the reference truncates (eigenvalues <= 1e-8 of A') and the
+        # ones the information form's pivoted Cholesky drops from the constant c0: components of b' along the (near-)null
+        # gauge directions divided by tiny eigenvalues -- ratios of rounding noise.  They show up in the reported COST at the
+        # 0.5 % level (the poses above do not see them); the iteration counts stay equal.
+        assert abs(sd.c.final_cost - sr.c.final_cost) <= 1e-2 * sr.c.final_cost, (a, sd.c.final_cost, sr.c.final_cost)
+        assert abs(sd.c.initial_cost - sr.c.initial_cost) <= 1e-4 * sr.c.initial_cost, a
+        assert sd.c.iterations == sr.c.iterations, a
+        assert np.abs(sr.Ps - so.Ps).max() <= 1e-4, a                            # and the chain tracks the oracle (bar: 1e-4 m)
+        assert np.isfinite(sd.c.final_cost) and sd.c.final_cost > 0
+    print("long chain: max |device - round trip| =", worst)
+    hd.close(); hr.close()

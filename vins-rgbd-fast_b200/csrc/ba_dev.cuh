@@ -66,6 +66,8 @@ struct BaProbDev {
     double *W;                            // [M][BA_WS]
     double *hll, *gl, *jscale_l, *diag_l, *gd_l, *gn_l, *u_l, *y_l, *hinv_l, *shinv_l;   // shinv_l = sqrt(hinv_l)
     double *imuS;                         // [10][225] sqrt information (upper)
+    int *fac;                             // [nobs] projection factors in frame-pair-major order: landmark | observer frame << 16
+                                          //        (built once per solve by k_ba_solve; pair offsets in BaShared::pair_ptr)
 };
 
 struct BaOutDev {
@@ -77,7 +79,7 @@ struct BaOutDev {
     // states re-packed by vector2double after the gauge fix (marginalization linearises here)
     double mpose[BA_NF * 7], msb[BA_NF * 9], mex[7];
     double td, mtd;      // para_Td after the solve / as re-packed for marginalization
-    int has_new_prior, pad;
+    int has_new_prior, armijo_failures;
     long long prof2[8];  // k_ba_marg: 0 table+zero, 1 prior, 2 imu+proj, 3 pd test, 4 schur (fast or eig), 5 jacobi, 6 output, 7 total kernel cycles of k_ba_solve
     long long prof[8];   // clock64 per phase: 0 linearise, 1 scale+grad, 2 cauchy, 3 schur, 4 cholesky, 5 solve tail, 6 dogleg, 7 candidate cost
 };

@@ -59,6 +59,7 @@ struct BaState {
     int *d_colmap = nullptr;
     double *d_margbuf = nullptr;
     int *d_lmcol = nullptr;
+    int *d_fac = nullptr;                            // [n_seq][BA_MAX_OBS] pair-major projection factor lists (k_ba_solve scratch)
     std::vector<int> last_M;
     std::vector<int> last_slots;
 };
@@ -120,6 +121,7 @@ int ba_create(vrf_handle *h)
     BCK(cudaMalloc((void **)&b->d_colmap, S * VRF_PRIOR_MAX_DIM * sizeof(int)));
     BCK(cudaMalloc((void **)&b->d_margbuf, S * kMargDoubles * sizeof(double)));
     BCK(cudaMalloc((void **)&b->d_lmcol, S * BA_MAX_LM * sizeof(int)));
+    BCK(cudaMalloc((void **)&b->d_fac, S * BA_MAX_OBS * sizeof(int)));
     b->prior_cur.assign(S, 0);
     b->prior_valid.assign(S, 0);
     b->last_M.assign(S, 0);
@@ -131,7 +133,7 @@ void ba_destroy(vrf_handle *h)
     BaState *b = h->ba;
     if (!b) return;
     void *dev[] = {b->d_prior[0], b->d_prior[1], b->d_prior_factor, b->d_factor_scratch, b->d_lam, b->d_clam,
-                   b->d_W, b->d_vecs, b->d_imuS, b->d_HP, b->d_colmap, b->d_margbuf, b->d_lmcol};
+                   b->d_W, b->d_vecs, b->d_imuS, b->d_HP, b->d_colmap, b->d_margbuf, b->d_lmcol, b->d_fac};
     for (void *p : dev) if (p) cudaFree(p);
     if (b->h_prior_dl) cudaFreeHost(b->h_prior_dl);
     for (BaSlot &sl : b->slot) {
@@ -252,6 +254,7 @@ static int pack_problem(vrf_handle *h, BaSlot &sl, int slot, int seq, const VrfB
     pd.gn_l = v + 5 * BA_MAX_LM; pd.u_l = v + 6 * BA_MAX_LM; pd.y_l = v + 7 * BA_MAX_LM; pd.hinv_l = v + 8 * BA_MAX_LM;
     pd.shinv_l = v + 9 * BA_MAX_LM;
     pd.imuS = b->d_imuS + (size_t)seq * (BA_NF - 1) * 225;
+    pd.fac = b->d_fac + (size_t)seq * BA_MAX_OBS;
 
     BaMargDev &mg = sl.h_marg[slot];
     double *mb = b->d_margbuf + (size_t)seq * kMargDoubles;
@@ -337,6 +340,7 @@ static int finish_download(vrf_handle *h, BaSlot &sl, int n, const int32_t *seqs
         memcpy(r.Ps, o.Ps, sizeof(o.Ps)); memcpy(r.Rs, o.Rs, sizeof(o.Rs)); memcpy(r.Vs, o.Vs, sizeof(o.Vs));
         memcpy(r.Bas, o.Bas, sizeof(o.Bas)); memcpy(r.Bgs, o.Bgs, sizeof(o.Bgs));
         r.has_new_prior = o.has_new_prior;
+        r.armijo_failures = o.armijo_failures;
         if (r.para_Feature && b->last_M[seq] > 0)
             memcpy(r.para_Feature, sl.h_lam + (size_t)i * BA_MAX_LM, sizeof(double) * b->last_M[seq]);
         if (o.has_new_prior && r.new_prior) {

@@ -36,7 +36,8 @@ namespace vrf {
 struct BaShared {
     double H[BA_NC * (BA_NC + 1) / 2];     // packed lower triangle: camera system, Schur-reduced & factorised in place
     double g[BA_NC], diag[BA_NC], gd[BA_NC], gn[BA_NC], jscale[BA_NC], tmp[BA_NC], y[BA_NC + 1], colv[BA_NC + 1];
-    double Lp[8][BA_NC + 5];                 // current Cholesky panel, transposed: Lp[c][row] (bank-conflict-free trailing update)
+    double Lp[8][BA_NC + 8];                 // current Cholesky panel, transposed: Lp[c][row]; row stride 180 = 4 mod 16 doubles, so that the
+                                             // DMMA fragment loads of the trailing update (lane -> [lane & 3][row0 + (lane >> 2)]) are conflict-free
     double pose[BA_NF * 7], sb[BA_NF * 9], ex[7];
     double cpose[BA_NF * 7], csb[BA_NF * 9], cex[7];  // candidate
     double tdv[2];                                    // para_Td: current, candidate
@@ -50,6 +51,9 @@ struct BaShared {
     double imuJ[BA_NF - 1][15 * 30];                 // whitened IMU Jacobians of the current linearisation
     double imur[BA_NF - 1][16];
     double red[BA_THREADS / 32];
+    int pair_ptr[BA_NF * (BA_NF - 1) / 2 + 1];        // offsets of the frame pairs (host i, observer j) in BaProbDev::fac
+    int pair_cnt[BA_NF * (BA_NF - 1) / 2 + 1];
+    double d8[36];                                    // chol_diag8: the 8x8 diagonal block being factorised (packed lower triangle)
     double sc[16];
     int flag[8];
 };
@@ -176,8 +180,7 @@ __device__ __noinline__ double ba_evaluate_t(const BaMeta &m, const BaProbDev &p
     // ---- residual blocks as a dynamic task queue over the 16 warps: the IMU factors first (the longest tasks), then the
     // projection factors (linearisation: one task per frame pair; cost only: one task per two landmarks).  The IMU and
     // projection tasks touch disjoint accumulators except the pose blocks of adjacent frames, which use atomics. ----
-    const int nbatch = (m.M + 31) >> 5;
-    const int nproj = lin ? BA_NPAIR : (m.M + 1) >> 1;
+    const int nproj = lin ? BA_NPAIR : (sh.pair_ptr[BA_NPAIR] + 31) >> 5;
     const int ntask = m.nimu + nproj;
     int ptask = -1;
     long long ptask_t0 = 0;
@@ -226,19 +229,17 @@ __device__ __noinline__ double ba_evaluate_t(const BaMeta &m, const BaProbDev &p
                 atomicAdd(&sh.g[tcol(lane)], gsum);
             }
         } else if (!lin) {
-            // ---- projection factors, cost only: two landmarks per warp (16 lanes each), one lane per factor ----
-            const int half = lane >> 4, hl = lane & 15;
-            const int l = 2 * (task - m.nimu) + half;
-            if (l < m.M) {
-                const int o0 = p.obs_ptr[l], nf = p.obs_ptr[l + 1] - o0 - 1;
-                if (hl < nf) {
-                    const int i = p.start[l], j = i + 1 + hl;
-                    double r[2], Ji[12], Jj[12], Jl[2], xi, yi, xj, yj;
-                    obs_at(m, p, o0, td, xi, yi);
-                    obs_at(m, p, o0 + 1 + hl, td, xj, yj);
-                    cost += 0.5 * proj_eval(pose + 7 * i, sh.R + 9 * i, pose + 7 * j, sh.R + 9 * j, ex, sh.ric, lam[l], xi, yi, xj, yj, false,
-                                            p.lm_const[l] != 0, r, Ji, Jj, Jl);
-                }
+            // ---- projection factors, cost only: 32 consecutive factors of the pair-major list per warp, one lane per factor ----
+            const int f = 32 * (task - m.nimu) + lane;
+            if (f < sh.pair_ptr[BA_NPAIR]) {
+                const int code = p.fac[f];
+                const int l = code & 0xFFFF, j = code >> 16, i = p.start[l];
+                const int o0 = p.obs_ptr[l];
+                double r[2], Ji[12], Jj[12], Jl[2], xi, yi, xj, yj;
+                obs_at(m, p, o0, td, xi, yi);
+                obs_at(m, p, o0 + (j - i), td, xj, yj);
+                cost += 0.5 * proj_eval(pose + 7 * i, sh.R + 9 * i, pose + 7 * j, sh.R + 9 * j, ex, sh.ric, lam[l], xi, yi, xj, yj, false,
+                                        p.lm_const[l] != 0, r, Ji, Jj, Jl);
             }
         } else {
             // ---- projection factors, linearisation: one warp per frame pair (host i, observer j), one lane per factor ----
@@ -254,15 +255,13 @@ __device__ __noinline__ double ba_evaluate_t(const BaMeta &m, const BaProbDev &p
             const int j = i + 1 + rem;
             double acc[6] = {0, 0, 0, 0, 0, 0};
             bool any_pair = false;
-            for (int bt = 0; bt < nbatch; ++bt) {
-                const int l = 32 * bt + lane;
-                bool act = false;
-                int o0 = 0;
-                if (l < m.M && p.start[l] == i) {
-                    o0 = p.obs_ptr[l];
-                    act = (p.obs_ptr[l + 1] - o0 - 1) >= (j - i);
-                }
-                if (!__any_sync(0xffffffffu, act)) continue;
+            // the pair's factors are contiguous in the pair-major list built once per solve: full batches of 32 factors
+            // instead of a scan over all landmarks that finds a handful of this pair's factors per 32-landmark batch
+            const int f_end = sh.pair_ptr[pi + 1];
+            for (int fb = sh.pair_ptr[pi]; fb < f_end; fb += 32) {
+                const bool act = fb + lane < f_end;
+                const int l = act ? (p.fac[fb + lane] & 0xFFFF) : 0;
+                const int o0 = act ? p.obs_ptr[l] : 0;
                 any_pair = true;
                 double r[2] = {0, 0}, Ji[12], Jj[12], Jl[2] = {0, 0};
                 double Jg[14];          // [ex-pose | td] block, only touched when one of them is variable
@@ -418,56 +417,76 @@ __device__ __forceinline__ double ba_evaluate(const BaMeta &m, const BaProbDev &
                                         : ba_evaluate_t<false>(m, p, sh, pose, sb, ex, td, lam, lin);
 }
 
-// 8x8 diagonal block (rows/cols j0 .. j0+nbp-1) of the blocked Cholesky, factorised by ONE warp in registers (lane r = row r,
-// shuffles for the pivot column).  `update`: first subtract the rank-8 contribution of the panel staged in sh.Lp (look-ahead).
-// Writes the factor back to sh.H, the reciprocal pivots to sh.colv[0..7], and raises sh.flag[0] on a non-positive pivot.
-__device__ __noinline__ void chol_diag8(BaShared &sh, int j0, int nbp, int lane, bool update)
+// D(8x8) = A(8x4) B(4x8) + D on the FP64 tensor cores (SASS: DMMA.8x8x4); see the trailing update of the Cholesky below
+__device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b)
 {
-    const int rr = lane;
-    double a8[8];
-    const int rrow = j0 + min(rr, nbp - 1);
-    const double *rp = sh.H + rrow * (rrow + 1) / 2 + j0;
-    double lr[8];
-    if (update) {
-#pragma unroll
-        for (int c = 0; c < 8; ++c) lr[c] = sh.Lp[c][rrow];
-    }
-#pragma unroll
-    for (int c = 0; c < 8; ++c) {
-        double v = (rr < nbp && c <= rr && c < nbp) ? rp[c] : 0.0;
-        if (update && rr < nbp && c <= rr && c < nbp) {
-            double acc = 0;
-#pragma unroll
-            for (int k = 0; k < 8; ++k) acc += lr[k] * sh.Lp[k][j0 + c];
-            v -= acc;
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+// 8x8 diagonal block (rows/cols j0 .. j0+nbp-1) of the blocked Cholesky, factorised by ONE warp.  This block is the serial
+// spine of the factorisation (22 panels x 8 dependent pivots per solve): every lane keeps the WHOLE lower triangle (36 doubles)
+// in registers and runs the 8 pivots redundantly, so that a pivot costs one rsqrt + one multiply + one FMA of latency and no
+// shuffles (the previous version held one row per lane and paid 8 shuffle round trips per pivot: ~5.5 k cycles per block,
+// the critical path of the panel loop; this one ~1.2 k).
+// `update`: first subtract the rank-8 contribution of the panel staged in sh.Lp (look-ahead), two entries per lane, gathered
+// through sh.d8.  Writes the factor back to sh.H, the reciprocal pivots to sh.colv[0..7], and raises sh.flag[0] on a
+// non-positive pivot.  Entries outside the nbp x nbp block are treated as the identity.
+__device__ __noinline__ void chol_diag8(BaShared &sh, int j0, int nbp, int lane, bool update, bool dprof = false)
+{
+    long long dt0 = dprof ? clock64() : 0, dt1 = 0, dt2 = 0, dt3 = 0;
+    {
+        // the block as one DMMA tile: lane -> row m8, columns 2 kq, 2 kq + 1 (C fragment of m8n8k4); with `update` the rank-8
+        // contribution of the staged panel is subtracted by two DMMAs (A = -B^T = -Lp[.][j0 + .])
+        const int m8 = lane >> 2, kq = lane & 3, row = j0 + m8, c = 2 * kq;
+        const bool v0 = m8 < nbp && c <= m8, v1 = m8 < nbp && c + 1 <= m8;
+        const double *rp = sh.H + row * (row + 1) / 2 + j0;
+        double c0 = v0 ? rp[c] : 0.0, c1 = v1 ? rp[c + 1] : 0.0;
+        if (update) {
+            const double b0 = sh.Lp[kq][row], b1 = sh.Lp[4 + kq][row];
+            dmma884(c0, c1, -b0, b0);
+            dmma884(c0, c1, -b1, b1);
         }
-        a8[c] = v;
+        if (c <= m8) sh.d8[m8 * (m8 + 1) / 2 + c] = v0 ? c0 : (m8 == c ? 1.0 : 0.0);
+        if (c + 1 <= m8) sh.d8[m8 * (m8 + 1) / 2 + c + 1] = v1 ? c1 : (m8 == c + 1 ? 1.0 : 0.0);
     }
+    __syncwarp();
+    if (dprof) dt1 = clock64();
+    double a[8][8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+#pragma unroll
+        for (int c = 0; c <= r; ++c) a[r][c] = sh.d8[r * (r + 1) / 2 + c];
+    if (dprof) dt2 = clock64();
     bool okp = true;
+    double rinv[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-        if (j < nbp) {
-            const double dj = __shfl_sync(0xffffffffu, a8[j], j);
-            if (!(dj > 0.0)) okp = false;
-            // FP64 sqrt/div have ~500-cycle latencies on this part: one rsqrt per pivot instead
-            const double rinv = rsqrt(dj);
-            const double ljj = dj * rinv;
-            const double lrj = (rr == j) ? ljj : a8[j] * rinv;
-            if (rr >= j) a8[j] = lrj;
-            if (lane == 0) sh.colv[j] = rinv;            // 1 / L[j0+j, j0+j]
+        const double dj = a[j][j];
+        if (!(dj > 0.0)) okp = false;
+        // FP64 sqrt/div have ~500-cycle latencies on this part: one rsqrt per pivot instead
+        rinv[j] = rsqrt(dj);
+        a[j][j] = dj * rinv[j];
 #pragma unroll
-            for (int c = j + 1; c < 8; ++c) {
-                const double lcj = __shfl_sync(0xffffffffu, a8[j], c);
-                if (c < nbp && rr >= c) a8[c] -= lrj * lcj;
-            }
+        for (int r = j + 1; r < 8; ++r) a[r][j] *= rinv[j];
+#pragma unroll
+        for (int c = j + 1; c < 8; ++c)
+#pragma unroll
+            for (int r = c; r < 8; ++r) a[r][c] -= a[r][j] * a[c][j];
+    }
+    if (dprof) dt3 = clock64();
+    // every lane holds the same factor; lane 0 writes it back (32 lanes storing to one address serialise: measured 1 k cycles)
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+        if (r < nbp && lane == 0) {
+            double *wp = sh.H + (j0 + r) * (j0 + r + 1) / 2 + j0;
+#pragma unroll
+            for (int c = 0; c <= r; ++c) wp[c] = a[r][c];
+            sh.colv[r] = rinv[r];                    // 1 / L[j0+r, j0+r]
         }
     }
-    if (rr < nbp) {
-        double *wp = sh.H + (j0 + rr) * (j0 + rr + 1) / 2 + j0;
-#pragma unroll
-        for (int c = 0; c < 8; ++c) if (c <= rr && c < nbp) wp[c] = a8[c];
-    }
     if (!okp && lane == 0) sh.flag[0] = 1;
+    if (dprof && lane == 0)
+        printf("diag8 j0=%d: update+gather %lld  load %lld  factor %lld  store %lld cycles\n", j0, dt1 - dt0, dt2 - dt1, dt3 - dt2, clock64() - dt3);
 }
 
 // scale a fresh linearisation: H_s = D H D, g_s = D g, W_s, hll_s, gl_s (Jacobi scaling of the Jacobian columns)
@@ -480,15 +499,16 @@ __device__ __noinline__ void ba_scale(const BaMeta &m, const BaProbDev &p, BaSha
         for (int b = lane; b <= a; b += 32) row[b] *= sa * sh.jscale[b];
     }
     for (int c = tid; c < BA_NC; c += BA_THREADS) sh.g[c] *= sh.jscale[c];
-    // coupling rows in HBM/L2: flat element loop so that every thread keeps several independent accesses in flight
-    const int nW = m.M * BA_WS;
-#pragma unroll 4
-    for (int e = tid; e < nW; e += BA_THREADS) {
-        const int l = e / BA_WS, k = e - l * BA_WS;
-        p.W[e] *= p.jscale_l[l] * sh.jscale[wcol(k)];
-    }
+    // The coupling rows W stay UNSCALED in HBM/L2 (one read-modify-write pass over M x 73 doubles less per linearisation): their
+    // four readers apply the factor jscale_l[l] * jscale[col] on the fly (bit-identical products, see wsc()).
     for (int l = tid; l < m.M; l += BA_THREADS) { const double sl = p.jscale_l[l]; p.hll[l] *= sl * sl; p.gl[l] *= sl; }
     __syncthreads();
+}
+
+// scaled coupling entry: W_s[l][k] = W[l][k] * (jscale_l[l] * jscale[col(k)])  (what ba_scale used to store in place)
+__device__ __forceinline__ double wsc(const BaShared &sh, const double *Wl, int k, double sl)
+{
+    return Wl[k] * (sl * sh.jscale[wcol(k)]);
 }
 
 // (sum over camera + landmark entries of a_c*b_c) helper: camera part from smem arrays, landmark part from global
@@ -572,6 +592,37 @@ k_ba_solve(const BaMeta *metas, const BaProbDev *probs, BaOutDev *outs)
     __syncthreads();
     __threadfence_block();
 
+    // ---- once per solve: the projection factors in frame-pair-major order (pair (i, j) = host frame i, observer frame j > i;
+    //      within a pair in landmark order, so the list -- and every sum formed over it -- is reproducible) ----
+    {
+        for (int pass = 0; pass < 2; ++pass) {
+            for (int pi = warp; pi < BA_NPAIR; pi += nwarp) {
+                int i = 0, rem = pi;
+                while (rem >= BA_NF - 1 - i) { rem -= BA_NF - 1 - i; ++i; }
+                const int j = i + 1 + rem;
+                int off = pass ? sh.pair_ptr[pi] : 0;
+                for (int b0 = 0; b0 < M; b0 += 32) {
+                    const int l = b0 + lane;
+                    const bool a = l < M && p.start[l] == i && (p.obs_ptr[l + 1] - p.obs_ptr[l] - 1) >= (j - i);
+                    const unsigned mask = __ballot_sync(0xffffffffu, a);
+                    if (pass && a) p.fac[off + __popc(mask & ((1u << lane) - 1u))] = l | (j << 16);
+                    off += __popc(mask);
+                }
+                if (!pass && lane == 0) sh.pair_cnt[pi] = off;
+            }
+            __syncthreads();
+            if (!pass) {
+                if (tid == 0) {
+                    int acc = 0;
+                    for (int pi = 0; pi < BA_NPAIR; ++pi) { sh.pair_ptr[pi] = acc; acc += sh.pair_cnt[pi]; }
+                    sh.pair_ptr[BA_NPAIR] = acc;
+                }
+                __syncthreads();
+            }
+        }
+        __threadfence_block();
+    }
+
     const long long t_kernel0 = t_kernel00;
     long long tprof[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tmark = clock64();
 #define TPROF(k) do { long long t_ = clock64(); tprof[k] += t_ - tmark; tmark = t_; } while (0)
@@ -601,6 +652,14 @@ k_ba_solve(const BaMeta *metas, const BaProbDev *probs, BaOutDev *outs)
         return block_sum(v, sh.red);
     };
     x_norm = sqrt(xnorm2(sh.pose, sh.sb, p.lam));
+    // Solver::Options::is_constrained: some non-constant parameter block carries a bound
+    int armijo_failures = 0;
+    bool constrained;
+    {
+        double nb_ = 0;
+        for (int l = tid; l < M; l += BA_THREADS) if (!p.lm_const[l] && isfinite(p.lm_ub[l])) nb_ += 1;
+        constrained = block_sum(nb_, sh.red) > 0;
+    }
 
     while (true) {
         if (need_scale) {
@@ -663,17 +722,21 @@ k_ba_solve(const BaMeta *metas, const BaProbDev *probs, BaOutDev *outs)
             __syncthreads();
             // Cauchy point: alpha = |gd|^2 / (u^T H u), H = J^T J of the scaled problem (before it is reduced in place)
             {
+                // u_c^T H_cc u_c over the packed lower triangle: one row per warp pass, lanes along the row (coalesced, no index
+                // arithmetic per element); off-diagonal entries count twice
                 double v = 0;
-                for (int a = tid; a < BA_NC; a += BA_THREADS) {
+                for (int a = warp; a < BA_NC; a += nwarp) {
+                    const double *row = sh.H + a * (a + 1) / 2;
                     double hv = 0;
-                    for (int b = 0; b < BA_NC; ++b) hv += sh.H[pk(a, b)] * sh.tmp[b];
+                    for (int b = lane; b <= a; b += 32) hv += row[b] * sh.tmp[b] * (b == a ? 1.0 : 2.0);
                     v += sh.tmp[a] * hv;
                 }
                 for (int l = warp; l < M; l += nwarp) {
                     if (p.lm_const[l]) continue;
                     const double *Wl = p.W + (size_t)l * BA_WS;
+                    const double sl = p.jscale_l[l];
                     double wv = 0;
-                    for (int k = lane; k < ws; k += 32) wv += Wl[k] * sh.tmp[wcol(k)];
+                    for (int k = lane; k < ws; k += 32) wv += wsc(sh, Wl, k, sl) * sh.tmp[wcol(k)];
                     wv = warp_sum_d(wv);
                     if (lane == 0) v += 2.0 * p.u_l[l] * wv + p.hll[l] * p.u_l[l] * p.u_l[l];
                 }
@@ -701,14 +764,22 @@ k_ba_solve(const BaMeta *metas, const BaProbDev *probs, BaOutDev *outs)
                 // per-landmark pivots; reduce rhs
                 if (tid == 0) sh.flag[0] = 0;
                 __syncthreads();
-                for (int l = warp; l < M; l += nwarp) {
+                // pivots of all landmarks, one landmark per thread (division / sqrt once per landmark, not once per warp pass);
+                // y_l is free until the back-substitution and carries g_l / h_l to the reduction of the right-hand side
+                for (int l = tid; l < M; l += BA_THREADS) {
                     if (p.lm_const[l]) continue;
                     const double hl = p.hll[l] + mu * p.diag_l[l] * p.diag_l[l];
-                    if (!(hl > 0)) { if (lane == 0) sh.flag[0] = 1; continue; }
+                    if (!(hl > 0)) { sh.flag[0] = 1; continue; }
+                    const double hi_ = 1.0 / hl;
+                    p.hinv_l[l] = hi_; p.shinv_l[l] = sqrt(hi_); p.y_l[l] = p.gl[l] / hl;
+                }
+                __syncthreads();
+                for (int l = warp; l < M; l += nwarp) {
+                    if (p.lm_const[l]) continue;
+                    if (!(p.hll[l] + mu * p.diag_l[l] * p.diag_l[l] > 0)) continue;
                     const double *Wl = p.W + (size_t)l * BA_WS;
-                    const double gl_h = p.gl[l] / hl;
-                    for (int k = lane; k < ws; k += 32) { double w = Wl[k]; if (w != 0.0) atomicAdd(&sh.y[wcol(k)], -w * gl_h); }
-                    if (lane == 0) { const double hi_ = 1.0 / hl; p.hinv_l[l] = hi_; p.shinv_l[l] = sqrt(hi_); }
+                    const double gl_h = p.y_l[l], sl = p.jscale_l[l];
+                    for (int k = lane; k < ws; k += 32) { double w = wsc(sh, Wl, k, sl); if (w != 0.0) atomicAdd(&sh.y[wcol(k)], -w * gl_h); }
                 }
                 __syncthreads();
                 // S = H + mu D^2 - W^T diag(1/h) W on the pose block (66 columns; + ex-pose and td when variable: ws = 73).
@@ -732,9 +803,9 @@ k_ba_solve(const BaMeta *metas, const BaProbDev *probs, BaOutDev *outs)
                         const int nt = min(tl, M - t0);
                         for (int lr = warp; lr < nt; lr += nwarp) {
                             const int l = t0 + lr;
-                            const double sc_ = p.lm_const[l] ? 0.0 : p.shinv_l[l];
+                            const double sc_ = p.lm_const[l] ? 0.0 : p.shinv_l[l], sl = p.jscale_l[l];
                             const double *Wl = p.W + (size_t)l * BA_WS;
-                            for (int k = lane; k < wsp; k += 32) tile[lr * wsp + k] = k < ws ? Wl[k] * sc_ : 0.0;
+                            for (int k = lane; k < wsp; k += 32) tile[lr * wsp + k] = k < ws ? wsc(sh, Wl, k, sl) * sc_ : 0.0;
                         }
                         __syncthreads();
                         if (actv) {
@@ -776,6 +847,9 @@ k_ba_solve(const BaMeta *metas, const BaProbDev *probs, BaOutDev *outs)
                     __syncthreads();
                     bad = sh.flag[0] != 0;
                 }
+                const bool cprof = (m.debug & 32) != 0 && blockIdx.x == 0 && iterations == 1;
+                long long cp_solve = 0, cp_work = 0, cp_wait1 = 0, cp_wait2 = 0, cp_t = cprof ? clock64() : 0;
+#define CPROF(acc) do { if (cprof) { long long t_ = clock64(); acc += t_ - cp_t; cp_t = t_; } } while (0)
                 for (int j0 = 0; j0 < BA_NC && !bad; j0 += 8) {
                     const int nbp = min(8, BA_NC - j0);
                     // (2) rows below the panel (incl. the rhs row): x * Ld^T = a ; the solved panel is also
@@ -797,47 +871,64 @@ k_ba_solve(const BaMeta *metas, const BaProbDev *probs, BaOutDev *outs)
                             sh.Lp[c][i2] = x[c];
                         }
                     }
+                    CPROF(cp_solve);
                     __syncthreads();
+                    CPROF(cp_wait1);
                     // (3) trailing update H[ii,kk] -= sum_c L[ii,j0+c] L[kk,j0+c]
                     const int t0 = j0 + nbp;
                     const int nb2 = min(8, BA_NC - t0);            // width of the next panel (<= 0: none)
                     if (warp == 0) {
-                        if (nb2 > 0) chol_diag8(sh, t0, nb2, lane, true);
+                        if (nb2 > 0) chol_diag8(sh, t0, nb2, lane, true, cprof && (j0 == 16 || j0 == 80));
                     } else {
+                        // FP64 tensor cores: the rank-8 update is cut into 8 x 8 tiles C(I, K) -= A(I) B(K)^T of the global
+                        // 8-aligned tile grid, A(I)[m][p] = L[8 I + m][j0 + p] = Lp[p][8 I + m]; two mma.sync.m8n8k4.f64 (DMMA) per
+                        // tile instead of 64 DFMA + ~300 address / predicate / shared-memory instructions.  Fragments (PTX ISA,
+                        // m8n8k4 .f64): A, B: lane -> [lane >> 2][lane & 3]; C: lane -> row lane >> 2, columns 2 (lane & 3), +1.
+                        // Tiles are dealt to the 15 warps cyclically over (7 I + K); entries outside the lower triangle / above
+                        // the next diagonal block / beyond the rhs row (index BA_NC) are computed and discarded.
                         const int w1 = warp - 1, nw1 = BA_THREADS / 32 - 1;
-                        for (int ib = t0 + max(nb2, 0) + w1; ib <= BA_NC; ib += 4 * nw1) {
-                            double lv[4][8];
-                            double *rowp[4];
-                            int kend[4];
-#pragma unroll
-                            for (int r = 0; r < 4; ++r) {
-                                const int ii = ib + r * nw1;
-                                const bool ok = ii <= BA_NC;
-                                rowp[r] = (ii < BA_NC) ? sh.H + ii * (ii + 1) / 2 : sh.y;
-                                kend[r] = ok ? min(ii, BA_NC - 1) : -1;
-#pragma unroll
-                                for (int c = 0; c < 8; ++c) lv[r][c] = ok ? sh.Lp[c][ii] : 0.0;
+                        const int R0 = t0 + max(nb2, 0);                   // first row of the trailing rows below the next diagonal block
+                        const int m8 = lane >> 2, kq = lane & 3;
+                        const int K0 = t0 >> 3, I0 = R0 >> 3, IL = BA_NC >> 3;       // tile rows I0 .. IL, tile row I holds tiles K0 .. I
+                        // tiles in row-major order of the lower block triangle, tile t -> warp t % 15; (I, K) advance without divisions.
+                        // (Measured: two tiles in flight per pass with split accumulators is not faster -- the phase is bound by the
+                        // shared-memory pipe, not by the 26-cycle DMMA accumulator latency.)
+                        int I = I0, K = K0 + w1;
+                        while (I <= IL && K > I) { K -= I - K0 + 1; ++I; }
+                        int Icur = -1, row = 0, cmax = 0;
+                        bool rowok = false;
+                        double a0 = 0, a1 = 0;
+                        double *rp = sh.y;
+                        while (I <= IL) {
+                            if (I != Icur) {
+                                Icur = I;
+                                row = 8 * I + m8;
+                                a0 = -sh.Lp[kq][row]; a1 = -sh.Lp[4 + kq][row];
+                                rowok = row >= R0 && row <= BA_NC;
+                                rp = row < BA_NC ? sh.H + row * (row + 1) / 2 : sh.y;
+                                cmax = min(row, BA_NC - 1);
                             }
-                            const int kmax = max(max(kend[0], kend[1]), max(kend[2], kend[3]));
-                            for (int kk = t0 + lane; kk <= kmax; kk += 32) {
-                                double lp[8];
-#pragma unroll
-                                for (int c = 0; c < 8; ++c) lp[c] = sh.Lp[c][kk];
-#pragma unroll
-                                for (int r = 0; r < 4; ++r) {
-                                    if (kk <= kend[r]) {
-                                        double acc = 0;
-#pragma unroll
-                                        for (int c = 0; c < 8; ++c) acc += lv[r][c] * lp[c];
-                                        rowp[r][kk] -= acc;
-                                    }
-                                }
-                            }
+                            const int col = 8 * K + 2 * kq;
+                            const double b0 = sh.Lp[kq][8 * K + m8], b1 = sh.Lp[4 + kq][8 * K + m8];
+                            const bool v0 = rowok && col >= t0 && col <= cmax, v1 = rowok && col + 1 >= t0 && col + 1 <= cmax;
+                            double c0 = v0 ? rp[col] : 0.0, c1 = v1 ? rp[col + 1] : 0.0;
+                            dmma884(c0, c1, a0, b0);
+                            dmma884(c0, c1, a1, b1);
+                            if (v0) rp[col] = c0;
+                            if (v1) rp[col + 1] = c1;
+                            K += nw1;
+                            while (I <= IL && K > I) { K -= I - K0 + 1; ++I; }
                         }
                     }
+                    CPROF(cp_work);
                     __syncthreads();
+                    CPROF(cp_wait2);
                     if (sh.flag[0]) { bad = true; break; }
                 }
+                if (cprof && lane == 0 && (warp == 0 || warp == 1 || warp == 8 || warp == 15))
+                    printf("chol warp %2d: panel solve %lld  wait %lld  %s %lld  wait %lld cycles (22 panels)\n", warp, cp_solve, cp_wait1,
+                           warp == 0 ? "diag8" : "trailing", cp_work, cp_wait2);
+#undef CPROF
                 TPROF(4);
                 if (!bad) {
                     // back substitution L^T x = z by one warp with the solution vector in registers (lane holds entries
@@ -892,7 +983,8 @@ k_ba_solve(const BaMeta *metas, const BaProbDev *probs, BaOutDev *outs)
                             double v = 0;
                             if (!p.lm_const[l]) {
                                 const double *Wl = p.W + (size_t)l * BA_WS;
-                                for (int k = lane; k < ws; k += 32) v += Wl[k] * sh.y[wcol(k)];
+                                const double sl = p.jscale_l[l];
+                                for (int k = lane; k < ws; k += 32) v += wsc(sh, Wl, k, sl) * sh.y[wcol(k)];
                                 v = warp_sum_d(v);
                                 v = (p.gl[l] - v) * p.hinv_l[l];
                             }
@@ -988,6 +1080,10 @@ k_ba_solve(const BaMeta *metas, const BaProbDev *probs, BaOutDev *outs)
                 TPROF(6);
                 const double cand_cost = ba_evaluate(m, p, sh, sh.cpose, sh.csb, sh.cex, sh.tdv[1], p.clam, false);
                 TPROF(7);
+                // Ceres' projected Armijo line search of bound-constrained problems (TrustRegionMinimizer::DoLineSearch) leaves
+                // the step alone when f(x [+] delta) <= f(x) + 1e-4 g.delta -- the case implemented here; steps that fail the
+                // test (where Ceres would shorten the step) are counted for the caller (VrfBaResult::armijo_failures)
+                if (constrained && cand_cost > x_cost + 1e-4 * sTg) ++armijo_failures;
                 // step norm over the non-constant blocks (ambient space)
                 double sn = 0;
                 for (int i = tid; i < BA_NF * 7; i += BA_THREADS) if (col_active_dev(m, 6 * (i / 7))) { double dd = sh.pose[i] - sh.cpose[i]; sn += dd * dd; }
@@ -1106,6 +1202,7 @@ k_ba_solve(const BaMeta *metas, const BaProbDev *probs, BaOutDev *outs)
     __syncthreads();
     if (tid == 0) {
         out.status = status; out.iterations = iterations; out.successful = successful; out.termination = termination;
+        out.armijo_failures = armijo_failures;
         out.initial_cost = initial_cost; out.final_cost = x_cost;
         for (int k = 0; k < 8; ++k) out.prof[k] = tprof[k];
         out.prof2[7] = clock64() - t_kernel0;

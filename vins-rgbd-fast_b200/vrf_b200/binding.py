@@ -95,7 +95,7 @@ class VrfBaResult(C.Structure):
         ("Ps", (C.c_double * 3) * NUM_FRAMES), ("Rs", (C.c_double * 9) * NUM_FRAMES),
         ("Vs", (C.c_double * 3) * NUM_FRAMES), ("Bas", (C.c_double * 3) * NUM_FRAMES),
         ("Bgs", (C.c_double * 3) * NUM_FRAMES),
-        ("has_new_prior", C.c_int32), ("reserved", C.c_int32), ("new_prior", C.POINTER(VrfPrior)),
+        ("has_new_prior", C.c_int32), ("armijo_failures", C.c_int32), ("new_prior", C.POINTER(VrfPrior)),
     ]
 
 
