@@ -192,8 +192,8 @@ int vrf_tracker_read_rgbd_batch(vrf_handle *h, int n, const int32_t *seqs,
 /* Pipelined form of vrf_tracker_read_rgbd_batch for throughput over many sequences: submit() enqueues the H2D
  * copies (pinned host memory recommended), every front-end kernel and the D2H copy of the results, and returns
  * without waiting; collect() blocks until the OLDEST submitted batch has finished and fills `outs` (same n / seqs
- * as its submit).  Up to two batches may be in flight (submit k+1, then collect k): the next batch's frames cross
- * PCIe while the current batch's kernels run.  submit() returns VRF_ERR_CAPACITY when two batches are already
+ * as its submit).  Up to three batches may be in flight (submit k+2, then collect k): the next batches' frames cross
+ * PCIe while the current batch's kernels run.  submit() returns VRF_ERR_CAPACITY when three batches are already
  * pending.  The host frame buffers must stay valid until the batch has been collected.  The optional
  * parity/debug members of VrfTrackOut (predict_pts, lk_*, grids_*) reflect the latest submitted batch.
  * (Reference analogue: the img_buf / feature_buf queues between the ROS callbacks, trackThread and

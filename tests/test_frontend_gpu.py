@@ -385,13 +385,19 @@ def test_pipelined_submit_collect_equals_synchronous_calls():
         expect.append([(r.finish().ids.copy(), r.cur_pts.copy(), r.cur_un_pts.copy(), r.pts_velocity.copy(),
                         r.track_cnt.copy(), r.depth_mm.copy(), r.depth_keep.copy()) for r in res])
     keep_alive = []
-    a0 = args(0); keep_alive.append(a0)
-    h_pipe.submit_batch_into(seq_a, a0[0], binding.FMT_RGB8, a0[2], a0[3], a0[4], dptrs=a0[1], dfmt=binding.DEPTH_16UC1)
+    DEPTH = 3                                   # batches in flight (VRF_PIPE_DEPTH): submit k+2, then collect k
+
+    def submit(k):
+        a = args(k); keep_alive.append(a)
+        h_pipe.submit_batch_into(seq_a, a[0], binding.FMT_RGB8, a[2], a[3], a[4], dptrs=a[1], dfmt=binding.DEPTH_16UC1)
+        return a
+
+    for k in range(min(DEPTH - 1, T)):
+        submit(k)
     for k in range(T):
-        if k + 1 < T:
-            a = args(k + 1); keep_alive.append(a)
-            h_pipe.submit_batch_into(seq_a, a[0], binding.FMT_RGB8, a[2], a[3], a[4], dptrs=a[1], dfmt=binding.DEPTH_16UC1)
-            if k == 0:      # two batches pending: a third submit must be refused, not queued
+        if k + DEPTH - 1 < T:
+            a = submit(k + DEPTH - 1)
+            if k == 0:      # three batches pending: a fourth submit must be refused, not queued
                 rc = h_pipe.lib.vrf_tracker_submit_rgbd_batch(h_pipe.h, S, seq_a.ctypes.data, C.cast(a[0], C.c_void_p), 0,
                                                               binding.FMT_RGB8, None, 0, 0, a[2].ctypes.data, a[3].ctypes.data, a[4].ctypes.data)
                 assert rc == -4

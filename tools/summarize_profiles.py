@@ -32,7 +32,7 @@ for k, ns in rows:
 ours = {k: v for k, v in agg.items() if k.startswith("k_")}
 tot = sum(v[1] for v in ours.values()) or 1.0
 with open(os.path.join(OUT, f"{tag}_launches.csv"), "w") as f:
-    f.write("# ncu --metrics gpu__time_duration.sum --clock-control none   python bench.py --steps 4 --warmup 3 --quick\n")
+    f.write("# ncu --metrics gpu__time_duration.sum --clock-control none --nvtx --nvtx-include vrf_timed/   VRF_NVTX=1 python bench.py --steps 4 --warmup 3 --quick\n")
     f.write("# (per-launch times under ncu are cold-cache and serialised: compare SHARES with bench.py's roofline.kernels, not absolutes)\n")
     f.write("kernel,launches,total_us,avg_us,share\n")
     for k, (n, ns) in sorted(ours.items(), key=lambda kv: -kv[1][1]):

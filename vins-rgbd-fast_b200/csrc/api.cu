@@ -212,9 +212,12 @@ extern "C" void vrf_destroy(vrf_handle *h)
                     d.lk_status, d.n_lk, d.t_prev, d.t_forw, d.t_prevun, d.t_ids, d.t_cnt, d.t_n, d.t_keep,
                     d.unstable, d.n_unstable, d.maskpts, d.n_maskpts, d.grid_cnt, d.tex_status, d.cell_k, d.cand,
                     d.ncand, d.o_pts, d.o_un, d.o_vel, d.o_ids, d.o_cnt, d.out_hdr, d.work_prefix,
-                    d.o_depth, d.o_dkeep, d.clahe_lut, const_cast<uint8_t *>(d.fisheye), h->d_stage[0], h->d_stage[1], h->d_stage_depth[0], h->d_stage_depth[1]};
-    static_assert(VRF_PIPE_DEPTH == 2, "staging slots listed explicitly above");
+                    d.o_depth, d.o_dkeep, d.clahe_lut, const_cast<uint8_t *>(d.fisheye)};
     for (void *p : ptrs) if (p) cudaFree(p);
+    for (int p = 0; p < VRF_PIPE_DEPTH; ++p) {
+        if (h->d_stage[p]) cudaFree(h->d_stage[p]);
+        if (h->d_stage_depth[p]) cudaFree(h->d_stage_depth[p]);
+    }
     for (int k = 0; k < VRF_CALL_SLOTS; ++k) {
         if (h->d_calls_ring[k]) cudaFree(h->d_calls_ring[k]);
         if (h->h_calls_ring[k]) cudaFreeHost(h->h_calls_ring[k]);
@@ -447,7 +450,8 @@ extern "C" int vrf_tracker_submit_rgbd_batch(vrf_handle *h, int n, const int32_t
     // frames already cross PCIe while this batch's kernels run, and the batch is enqueued in one piece (measured on
     // B200: cutting it up only multiplies the latency-bound small kernels, 3.5 -> 6.1 ms per 444 frames).  A lone
     // batch is cut into a few chunks so that chunk c+1's frames are copied while chunk c's kernels run.
-    const bool other_in_flight = h->pipe_busy[(slot + 1) % VRF_PIPE_DEPTH];
+    bool other_in_flight = false;
+    for (int q = 0; q < VRF_PIPE_DEPTH; ++q) other_in_flight |= (q != slot && h->pipe_busy[q]);
     int nchunk = other_in_flight ? 1 : n / 96;
     nchunk = nchunk < 1 ? 1 : (nchunk > 4 ? 4 : nchunk);
     if (getenv("VRF_DEBUG_CHUNKS")) nchunk = atoi(getenv("VRF_DEBUG_CHUNKS"));

@@ -13,14 +13,25 @@
 namespace vrf {
 
 // pinned host staging of one packed problem
+// Fixed part, then a variable part packed back to back for the problem's own M landmarks / O observations:
+//   double lam[M], lm_ub[M], obs[2 O] | int start[M], obs_ptr[M + 1] | uint8 lm_const[M]
+// so that the upload of a batch is ONE strided copy of only the used prefix of every slot (a 150-landmark window is 60 KB,
+// the full-capacity pack 196 KB: the difference was 5 % of the PCIe traffic of the host-buffer path).
 struct BaHostPack {
     double pose[BA_NF * 7], sb[BA_NF * 9], ex[7], td;
     VrfImuPreint imu[BA_NF - 1];
-    double lam[BA_MAX_LM], lm_ub[BA_MAX_LM];
-    int start[BA_MAX_LM], obs_ptr[BA_MAX_LM + 1];
-    uint8_t lm_const[BA_MAX_LM];
-    double obs[BA_MAX_OBS * 2];
+    double var[2 * BA_MAX_LM + 2 * BA_MAX_OBS + (2 * BA_MAX_LM + 2) / 2 + BA_MAX_LM / 8 + 2];
 };
+struct BaPackView { double *lam, *lm_ub, *obs; int *start, *obs_ptr; uint8_t *lm_const; size_t used_bytes; };
+static inline BaPackView pack_view(BaHostPack *k, int M, int O)
+{
+    BaPackView v;
+    v.lam = k->var; v.lm_ub = v.lam + M; v.obs = v.lm_ub + M;
+    v.start = reinterpret_cast<int *>(v.obs + 2 * (size_t)O); v.obs_ptr = v.start + M;
+    v.lm_const = reinterpret_cast<uint8_t *>(v.obs_ptr + M + 1);
+    v.used_bytes = (size_t)(v.lm_const + M - reinterpret_cast<uint8_t *>(k));
+    return v;
+}
 // ProjectionTdFactor inputs (only staged / uploaded when VrfConfig::estimate_td)
 struct BaHostPackTd {
     double vel[BA_MAX_OBS * 2], ctd[BA_MAX_OBS], row[BA_MAX_OBS];
@@ -40,6 +51,7 @@ struct BaSlot {
     BaPriorStore *h_prior = nullptr;                       // pinned upload staging [n_seq]
     double *h_lam = nullptr, *d_lam_out = nullptr;         // optimised inverse depths by batch position [n_seq][BA_MAX_LM]
     cudaEvent_t done = nullptr;
+    size_t used_bytes = 0;                                 // widest used prefix of a BaHostPack in the batch being packed
     bool busy = false;
     std::vector<int> seqs;                                 // sequences of the batch this slot holds
 };
@@ -167,6 +179,8 @@ static int pack_problem(vrf_handle *h, BaSlot &sl, int slot, int seq, const VrfB
     if (pb->n_landmarks > 0 && (!pb->para_Feature || !pb->lm_start_frame || !pb->lm_estimate_flag || !pb->lm_obs_ptr || !pb->obs_pts)) return VRF_ERR_ARG;
     if (pb->use_imu && !pb->imu) return VRF_ERR_ARG;
     BaHostPack &k = sl.h_pack[slot];
+    const BaPackView kv = pack_view(&k, pb->n_landmarks, pb->n_obs);
+    sl.used_bytes = std::max(sl.used_bytes, kv.used_bytes);
     memcpy(k.pose, pb->para_Pose, sizeof(k.pose));
     memcpy(k.sb, pb->para_SpeedBias, sizeof(k.sb));
     memcpy(k.ex, pb->para_Ex_Pose, sizeof(k.ex));
@@ -174,18 +188,18 @@ static int pack_problem(vrf_handle *h, BaSlot &sl, int slot, int seq, const VrfB
     if (pb->use_imu) memcpy(k.imu, pb->imu, sizeof(VrfImuPreint) * pb->frame_count);
     const int M = pb->n_landmarks;
     for (int l = 0; l < M; ++l) {
-        k.lam[l] = pb->para_Feature[l];
-        k.start[l] = pb->lm_start_frame[l];
-        k.obs_ptr[l] = pb->lm_obs_ptr[l];
+        kv.lam[l] = pb->para_Feature[l];
+        kv.start[l] = pb->lm_start_frame[l];
+        kv.obs_ptr[l] = pb->lm_obs_ptr[l];
         const int nobs = pb->lm_obs_ptr[l + 1] - pb->lm_obs_ptr[l];
         if (nobs < 1 || pb->lm_start_frame[l] < 0 || pb->lm_start_frame[l] + nobs - 1 > pb->frame_count) return VRF_ERR_ARG;
         // estimator.cpp:1291-1298: constant if (flag==1 && FIX_DEPTH); upper bound if flag==2
-        k.lm_const[l] = (pb->lm_estimate_flag[l] == 1 && h->cfg.fix_depth) ? 1 : 0;
-        k.lm_ub[l] = (pb->lm_estimate_flag[l] == 2) ? 2.0 / h->cfg.depth_max_dist : INFINITY;
+        kv.lm_const[l] = (pb->lm_estimate_flag[l] == 1 && h->cfg.fix_depth) ? 1 : 0;
+        kv.lm_ub[l] = (pb->lm_estimate_flag[l] == 2) ? 2.0 / h->cfg.depth_max_dist : INFINITY;
     }
-    k.obs_ptr[M] = M ? pb->lm_obs_ptr[M] : 0;
-    if (k.obs_ptr[M] != pb->n_obs) return VRF_ERR_ARG;
-    memcpy(k.obs, pb->obs_pts, sizeof(double) * 2 * pb->n_obs);
+    kv.obs_ptr[M] = M ? pb->lm_obs_ptr[M] : 0;
+    if (kv.obs_ptr[M] != pb->n_obs) return VRF_ERR_ARG;
+    memcpy(kv.obs, pb->obs_pts, sizeof(double) * 2 * pb->n_obs);
     if (td_factor && pb->n_obs > 0) {
         BaHostPackTd &kt = sl.h_packtd[slot];
         memcpy(kt.vel, pb->obs_velocity, sizeof(double) * 2 * pb->n_obs);
@@ -237,10 +251,11 @@ static int pack_problem(vrf_handle *h, BaSlot &sl, int slot, int seq, const VrfB
 
     BaProbDev &pd = sl.h_prob[slot];
     BaHostPack *dp = sl.d_pack + slot;
-    pd.pose0 = dp->pose; pd.sb0 = dp->sb; pd.ex0 = dp->ex; pd.lam0 = dp->lam; pd.td0 = &dp->td;
+    const BaPackView dv = pack_view(dp, pb->n_landmarks, pb->n_obs);           // same layout, device addresses
+    pd.pose0 = dp->pose; pd.sb0 = dp->sb; pd.ex0 = dp->ex; pd.lam0 = dv.lam; pd.td0 = &dp->td;
     if (td_factor) { BaHostPackTd *dt = sl.d_packtd + slot; pd.obs_vel = dt->vel; pd.obs_td = dt->ctd; pd.obs_row = dt->row; }
     else { pd.obs_vel = nullptr; pd.obs_td = nullptr; pd.obs_row = nullptr; }
-    pd.start = dp->start; pd.obs_ptr = dp->obs_ptr; pd.lm_const = dp->lm_const; pd.lm_ub = dp->lm_ub; pd.obs = dp->obs; pd.imu = dp->imu;
+    pd.start = dv.start; pd.obs_ptr = dv.obs_ptr; pd.lm_const = dv.lm_const; pd.lm_ub = dv.lm_ub; pd.obs = dv.obs; pd.imu = dp->imu;
     pd.prior = have_prior ? b->d_prior[b->prior_cur[seq]] + seq : nullptr;
     pd.prior_next = b->d_prior[1 - b->prior_cur[seq]] + seq;
     pd.HP = b->d_HP + (size_t)seq * VRF_PRIOR_MAX_DIM * VRF_PRIOR_MAX_DIM;
@@ -288,12 +303,14 @@ static int upload(vrf_handle *h, BaSlot &sl, int n, const int32_t *seqs, const V
     for (BaSlot &o : b->slot)
         if (&o != &sl && o.busy)
             for (int q : o.seqs) if (seen[q]) return VRF_ERR_ARG;
+    sl.used_bytes = 0;
     for (int i = 0; i < n; ++i) {
         int rc = pack_problem(h, sl, i, seqs[i], &probs[i]);
         if (rc != VRF_OK) return rc;
     }
-    // one contiguous copy of the n packed problems (pinned staging -> HBM); far cheaper than per-array copies
-    BCK(cudaMemcpyAsync(sl.d_pack, sl.h_pack, (size_t)n * sizeof(BaHostPack), cudaMemcpyHostToDevice, h->stream));
+    // one strided copy of the used prefix of the n packed problems (pinned staging -> HBM)
+    const size_t width = std::min(sizeof(BaHostPack), (sl.used_bytes + 15) & ~(size_t)15);
+    BCK(cudaMemcpy2DAsync(sl.d_pack, sizeof(BaHostPack), sl.h_pack, sizeof(BaHostPack), width, (size_t)n, cudaMemcpyHostToDevice, h->stream));
     if (h->cfg.estimate_td)
         BCK(cudaMemcpyAsync(sl.d_packtd, sl.h_packtd, (size_t)n * sizeof(BaHostPackTd), cudaMemcpyHostToDevice, h->stream));
     BCK(cudaMemcpyAsync(sl.d_meta, sl.h_meta, n * sizeof(BaMeta), cudaMemcpyHostToDevice, h->stream));

@@ -51,6 +51,8 @@ struct BaShared {
     double imuJ[BA_NF - 1][15 * 30];                 // whitened IMU Jacobians of the current linearisation
     double imur[BA_NF - 1][16];
     double red[BA_THREADS / 32];
+    BaMeta meta;                                      // this CTA's problem descriptors (see k_ba_solve)
+    BaProbDev prob;
     int pair_ptr[BA_NF * (BA_NF - 1) / 2 + 1];        // offsets of the frame pairs (host i, observer j) in BaProbDev::fac
     int pair_cnt[BA_NF * (BA_NF - 1) / 2 + 1];
     double d8[36];                                    // chol_diag8: the 8x8 diagonal block being factorised (packed lower triangle)
@@ -525,8 +527,15 @@ k_ba_solve(const BaMeta *metas, const BaProbDev *probs, BaOutDev *outs)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     BaShared &sh = *reinterpret_cast<BaShared *>(smem_raw);
-    const BaMeta m = metas[blockIdx.x];
-    const BaProbDev p = probs[blockIdx.x];
+    // The problem descriptors live in SHARED memory, one copy per CTA.  As per-thread copies they were forced into local
+    // memory (they are passed by reference to the __noinline__ phases): 512 threads x 2.8 KB of stack = 1.4 MB per CTA behind
+    // a 36 KB L1, so every `p.field` pointer load on the way to a global access missed to L2 (and 148 CTAs x 1.4 MB spilled
+    // out of L2: 1.1 GB of DRAM traffic per launch, profiles/r02_kernels.md).
+    if (threadIdx.x < (int)(sizeof(BaMeta) / sizeof(int))) reinterpret_cast<int *>(&sh.meta)[threadIdx.x] = reinterpret_cast<const int *>(metas + blockIdx.x)[threadIdx.x];
+    if (threadIdx.x < (int)(sizeof(BaProbDev) / sizeof(int))) reinterpret_cast<int *>(&sh.prob)[threadIdx.x] = reinterpret_cast<const int *>(probs + blockIdx.x)[threadIdx.x];
+    __syncthreads();
+    const BaMeta &m = sh.meta;
+    const BaProbDev &p = sh.prob;
     BaOutDev &out = outs[blockIdx.x];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = BA_THREADS / 32;
     const int M = m.M;

@@ -19,6 +19,9 @@
 namespace vrf {
 
 struct MargShared {
+    BaMeta meta;                // this CTA's problem descriptors
+    BaProbDev prob;
+    BaMargDev mdev;
     int kind[64], index[64], lsize[64], gsize[64], idx[64], present[64], drop[64];
     int nb, m, n, pos, first_kept, go;
     int chunk[BA_MAX_LM / 32], maxobs, lm0, jdbg;
@@ -302,10 +305,15 @@ k_ba_marg(const BaMeta *metas, const BaProbDev *probs, BaOutDev *outs, const BaM
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     MargShared &sh = *reinterpret_cast<MargShared *>(smem_raw);
-    const BaMeta m = metas[blockIdx.x];
-    const BaProbDev p = probs[blockIdx.x];
+    // problem descriptors in shared memory, one copy per CTA (per-thread copies end up in local memory: see k_ba_solve)
+    if (threadIdx.x < (int)(sizeof(BaMeta) / sizeof(int))) reinterpret_cast<int *>(&sh.meta)[threadIdx.x] = reinterpret_cast<const int *>(metas + blockIdx.x)[threadIdx.x];
+    if (threadIdx.x < (int)(sizeof(BaProbDev) / sizeof(int))) reinterpret_cast<int *>(&sh.prob)[threadIdx.x] = reinterpret_cast<const int *>(probs + blockIdx.x)[threadIdx.x];
+    if (threadIdx.x < (int)(sizeof(BaMargDev) / sizeof(int))) reinterpret_cast<int *>(&sh.mdev)[threadIdx.x] = reinterpret_cast<const int *>(margs + blockIdx.x)[threadIdx.x];
+    __syncthreads();
+    const BaMeta &m = sh.meta;
+    const BaProbDev &p = sh.prob;
     BaOutDev &out = outs[blockIdx.x];
-    const BaMargDev mg = margs[blockIdx.x];
+    const BaMargDev &mg = sh.mdev;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = BA_THREADS / 32;
     const int M = m.M;
     const BaPriorStore *P = (p.prior && p.prior->valid) ? p.prior : nullptr;

@@ -7,7 +7,8 @@
 
 #define VRF_CALL_SLOTS 32
 #define VRF_COPY_CHUNKS 8
-#define VRF_PIPE_DEPTH 2        // host-frame batches in flight (submit / collect)
+#define VRF_PIPE_DEPTH 3        // host-frame batches in flight (submit / collect): two ahead of the one being collected, so that the
+                                // PCIe stream never waits for a collect() that is itself waiting for kernels held up by the BA stream
 #define VRF_COPY_STREAMS 4      // H2D copies rotate over four streams (measured on B200, 444 frames/step: 31.8k -> 36.6k frames/s e2e vs two)
 
 #define LK_WPB 8                // k_lk: warps (= features in flight) per CTA

@@ -83,7 +83,7 @@ __device__ __forceinline__ void lk_stage_reflect(uint8_t *tile, const uint8_t *i
                                                  int c0, int nrows, int lane)
 {
     const int gx = reflect101(x0 + c0 + lane, cols);
-#pragma unroll 4
+#pragma unroll 8
     for (int rr = 0; rr < nrows; ++rr) {
         const int gy = reflect101(y0 + rr, rows);
         tile[rr * LK_TW + c0 + lane] = __ldg(img + (size_t)gy * pitch + gx);
@@ -197,14 +197,10 @@ k_lk(FrontCfg c, const SeqCall *calls, int ncalls, FrontDev d, const __grid_cons
                     if (tmaI) tma_load_3d(tileI, &maps.m[call.buf_prev][level], bar, ial, iy - 1, call.seq);
                     if (tmaJ) tma_load_3d(tileJ, &maps.m[call.buf_cur][level], bar, jal, tyo, call.seq);
                 }
-                if (!tmaI) {
-                    lk_stage_reflect(tileI, I, pitch, cols, rows, ial, iy - 1, 0, 24, lane);
-                    if (lane < LK_TW - 32) lk_stage_reflect(tileI, I, pitch, cols, rows, ial, iy - 1, 32, 24, lane);
-                }
-                if (jstaged && !tmaJ) {
-                    lk_stage_reflect(tileJ, J, pitch, cols, rows, jal, tyo, 0, 32, lane);
-                    if (lane < LK_TW - 32) lk_stage_reflect(tileJ, J, pitch, cols, rows, jal, tyo, 32, 32, lane);
-                }
+                // (only the 32 columns that can be read are gathered: the 24-wide patch resp. the 32-wide window range, both
+                // starting at the residual offset inside the 16-aligned tile)
+                if (!tmaI) lk_stage_reflect(tileI, I, pitch, cols, rows, ial, iy - 1, ioff, 24, lane);
+                if (jstaged && !tmaJ) lk_stage_reflect(tileJ, J, pitch, cols, rows, jal, tyo, tx0 - jal, 32, lane);
                 if (tmaI || tmaJ) { mbar_wait(bar, ph); ph ^= 1u; }
                 __syncwarp();
             }
@@ -364,10 +360,8 @@ k_lk(FrontCfg c, const SeqCall *calls, int ncalls, FrontDev d, const __grid_cons
                             tma_load_3d(tileJ, &maps.m[call.buf_cur][level], bar, jal, tyo, call.seq);
                         }
                         mbar_wait(bar, ph); ph ^= 1u;
-                    } else {
-                        lk_stage_reflect(tileJ, J, pitch, cols, rows, jal, tyo, 0, 32, lane);
-                        if (lane < LK_TW - 32) lk_stage_reflect(tileJ, J, pitch, cols, rows, jal, tyo, 32, 32, lane);
-                    }
+                    } else
+                        lk_stage_reflect(tileJ, J, pitch, cols, rows, jal, tyo, tx0 - jal, 32, lane);
                     __syncwarp();
                 }
                 offx += tx0 - jal;              // column of the window origin inside the 16-aligned tile

@@ -254,7 +254,9 @@ k_ransac(FrontCfg c, const SeqCall *calls, FrontDev d)
     __shared__ int s_nmod[RS_BATCH];
     __shared__ int s_cnt[RS_BATCH * 3];
     __shared__ float s_med[RS_BATCH * 3];      // LMedS: median residual of every model of the batch
-    __shared__ int s_ctl[4];        // 0: batch size, 1: continue flag, 2: have best
+    __shared__ int s_ctl[4];        // 0: batch size, 1: continue flag, 2: have best, 3: first subset that failed the parallel collinearity test
+    __shared__ int s_want;
+    __shared__ unsigned long long s_rng[RS_BATCH];      // RNG state after the draws of each subset of the batch
     const SeqCall call = calls[blockIdx.x];
     if (!call.pub) return;
     const int seq = call.seq;
@@ -282,28 +284,62 @@ k_ransac(FrontCfg c, const SeqCall *calls, FrontDev d)
     const int max_attempts = lmeds ? 1000 : 10000;      // getSubset(): RANSAC passes 10000, LMedS the default
     if (tid == 0) s_ctl[2] = 0;
     while (true) {
+        // getSubset() for up to 32 hypotheses.  The RNG stream is sequential by definition, but the collinearity test of a
+        // drawn subset (the expensive part: 2 x 15 triple products in double) is not: thread 0 draws all index sets assuming
+        // every subset passes (recording the RNG state after each), 32 lanes test them in parallel, and only if a subset
+        // fails -- rare -- does thread 0 redo the stream from that subset on with the reference's sequential retry rule.
         if (tid == 0) {
-            int nb = 0;
-            int cont = 1;
-            const int want = min(RS_BATCH, niters - iter);
-            for (; nb < want; ++nb) {
-                // getSubset(m1, m2, ms1, ms2, rng, 10000)
-                bool found = false;
-                for (int att = 0; att < max_attempts && !found; ++att) {
-                    int *idx = s_idx[nb];
-                    for (int i = 0; i < 7; ++i) {
-                        int v;
-                        bool dup;
-                        do {
-                            v = rng.uniform(0, n);
-                            dup = false;
-                            for (int k = 0; k < i; ++k) dup |= (idx[k] == v);
-                        } while (dup);
-                        idx[i] = v;
-                    }
-                    found = !rs_collinear(s_m1, idx, 7) && !rs_collinear(s_m2, idx, 7);
+            const int want0 = min(RS_BATCH, niters - iter);        // niters / iter live in thread 0's registers
+            s_want = want0;
+            for (int nb = 0; nb < want0; ++nb) {
+                int *idx = s_idx[nb];
+                for (int i = 0; i < 7; ++i) {
+                    int v;
+                    bool dup;
+                    do {
+                        v = rng.uniform(0, n);
+                        dup = false;
+                        for (int k = 0; k < i; ++k) dup |= (idx[k] == v);
+                    } while (dup);
+                    idx[i] = v;
                 }
-                if (!found) { cont = 0; break; }
+                s_rng[nb] = rng.state;
+            }
+        }
+        __syncthreads();
+        const int want = s_want;
+        if (warp == 0) {
+            const bool bad = lane < want && (rs_collinear(s_m1, s_idx[lane], 7) || rs_collinear(s_m2, s_idx[lane], 7));
+            const unsigned badmask = __ballot_sync(0xffffffffu, bad);
+            if (lane == 0) s_ctl[3] = badmask ? __ffs(badmask) - 1 : want;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            int nb = s_ctl[3];
+            int cont = 1;
+            if (nb < want) {
+                // subset nb failed its first attempt: continue the stream after its draws, sequentially (attempt 2, 3, ...)
+                rng.state = s_rng[nb];
+                int first_att = 1;
+                for (; nb < want; ++nb) {
+                    bool found = false;
+                    for (int att = first_att; att < max_attempts && !found; ++att) {
+                        int *idx = s_idx[nb];
+                        for (int i = 0; i < 7; ++i) {
+                            int v;
+                            bool dup;
+                            do {
+                                v = rng.uniform(0, n);
+                                dup = false;
+                                for (int k = 0; k < i; ++k) dup |= (idx[k] == v);
+                            } while (dup);
+                            idx[i] = v;
+                        }
+                        found = !rs_collinear(s_m1, idx, 7) && !rs_collinear(s_m2, idx, 7);
+                    }
+                    first_att = 0;
+                    if (!found) { cont = 0; break; }
+                }
             }
             s_ctl[0] = nb;
             s_ctl[1] = cont;
