@@ -606,14 +606,17 @@ def main():
         roof["path"] = {"alg_bytes_per_frame": A_FRAME, "achieved_gbs_per_gpu": path_gbs, "frac_of_hbm_peak": path_gbs / peaks["hbm_gbs"],
                         "sm_ms_per_frame": {k: v["ms_per_step"] * 1.0 / S for k, v in kern.items()}}
         img = {}
-        if "k_ingest" in kern:
-            t_ms = kern["k_ingest"]["ms_per_step"]
-            b_ = S * (3 * W * H + W * H)
-            img["k_ingest"] = {"alg_bytes": b_, "ms": t_ms, "achieved_gbs": b_ / (t_ms * 1e-3) / 1e9, "frac": b_ / (t_ms * 1e-3) / 1e9 / peaks["hbm_gbs"]}
-        if "k_pyrdown" in kern:
-            t_ms = kern["k_pyrdown"]["ms_per_step"]
-            b_ = S * (W * H + W * H // 4 + W * H // 4 + W * H // 16)      # level 0 -> 1 -> 2: read + write
-            img["k_pyrdown"] = {"alg_bytes": b_, "ms": t_ms, "achieved_gbs": b_ / (t_ms * 1e-3) / 1e9, "frac": b_ / (t_ms * 1e-3) / 1e9 / peaks["hbm_gbs"]}
+        if "k_pyr" in kern:
+            # the image-scan kernel: launch 1 reads the RGB8 frame once and writes levels 0 and 1 (ingest fused with the first
+            # cv::pyrDown), the deeper launches read level l and write level l + 1 -- all launches of a step together
+            t_ms = kern["k_pyr"]["ms_per_step"]
+            b_ = S * (3 * W * H + W * H + W * H // 4)
+            wl, hl = W // 2, H // 2
+            for _l in range(1, CFG["lk_max_level"]):
+                b_ += S * (wl * hl + (wl // 2) * (hl // 2))
+                wl, hl = wl // 2, hl // 2
+            img["k_pyr"] = {"alg_bytes": b_, "ms": t_ms, "launches": kern["k_pyr"]["launches_per_step"],
+                            "achieved_gbs": b_ / (t_ms * 1e-3) / 1e9, "frac": b_ / (t_ms * 1e-3) / 1e9 / peaks["hbm_gbs"]}
         roof["image_scan_kernels"] = img
         try:    # DRAM traffic of the dominant kernel from the committed ncu capture (profiles/), per launch
             tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))

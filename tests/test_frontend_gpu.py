@@ -464,3 +464,28 @@ def test_reject_with_f_lmeds_regime():
         want = _cv2_reject_with_f(cam, cur, forw, cfg)
         assert np.array_equal(h.reject_with_f(0, cur, forw), want), n
     h.close()
+
+
+@pytest.mark.parametrize("shape,levels", [((480, 640), 3), ((720, 1280), 4), ((250, 336), 3), ((357, 400), 3), ((123, 208), 2)])
+@pytest.mark.parametrize("rgb", [False, True])
+def test_pyramid_levels_bit_exact_vs_cv2(shape, levels, rgb):
+    """k_pyr (ingest fused with the first pyrDown, then the deeper levels): every level of every sequence of a batch is
+    bit-identical to cv2.cvtColor(RGB2GRAY) + cv2.pyrDown -- random frames (every rounding case), odd level sizes
+    (reflected borders, partial 8-output groups), strips that end below the image, two sequences per launch."""
+    import cv2
+    rows, cols = shape
+    rng = np.random.default_rng(rows * 7 + cols + int(rgb))
+    cfg = binding.default_config(row=rows, col=cols, fx=300.0, fy=300.0, cx=cols / 2, cy=rows / 2, use_ransac=0,
+                                 lk_max_level=levels - 1, max_cnt=60, min_dist=12)
+    h = binding.Handle(cfg, 2, 0)
+    for k in range(2):
+        frames = [rng.integers(0, 256, (rows, cols, 3) if rgb else (rows, cols), dtype=np.uint8) for _ in range(2)]
+        h.read_image_batch([0, 1], frames, [0.1 * k, 0.1 * k], pubs=[1, 1])
+        for s in range(2):
+            lvl = cv2.cvtColor(frames[s], cv2.COLOR_RGB2GRAY) if rgb else frames[s]
+            for l in range(levels):
+                got = h.pyramid_level(s, l)
+                assert got.shape == lvl.shape, (s, l)
+                assert np.array_equal(got, lvl), (k, s, l, np.argwhere(got != lvl)[:4])
+                lvl = cv2.pyrDown(lvl)
+    h.close()

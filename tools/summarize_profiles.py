@@ -64,7 +64,7 @@ with open(os.path.join(OUT, f"{tag}_kernels.md"), "w") as md:
             if len(vals) != len(hdr):
                 continue
             name = vals[hdr.index("Kernel Name")].split("(")[0].split("::")[-1]
-            if name in seen and name != "k_pyrdown":
+            if name in seen and name != "k_pyr":
                 continue
             seen.add(name)
             md.write(f"## {name}\n\n| metric | value | unit |\n|---|---|---|\n")

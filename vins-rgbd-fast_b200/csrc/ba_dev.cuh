@@ -14,6 +14,11 @@
 #define BA_MAX_OBS 8192
 #define BA_MAX_M0 384             // landmarks hosted at frame 0 that one marginalization can drop
 #define BA_MAX_POS (15 + BA_MAX_M0 + BA_NC)
+// Deterministic accumulation (no floating-point atomics anywhere in the back end): every sum that several warps contribute
+// to is first written as per-contributor partials and then added by ONE owner thread in a fixed order.
+#define BA_PP_STRIDE 256          // per frame pair: [0..95] the 90 sums of pair_entry() | [96 + 16 q + e] Jg_q^T (Ji | Jj | r) | [208 + e] tri(Jg^T Jg)
+#define BA_FP_STRIDE 16           // per projection factor: [0..5] host-frame part of the landmark's W row | [6] hll | [7] gl | [8..14] ex-pose / td part
+#define BA_MAX_TASKS (BA_NF + BA_MAX_OBS / 32 + 64)
 
 namespace vrf {
 
@@ -68,6 +73,9 @@ struct BaProbDev {
     double *imuS;                         // [10][225] sqrt information (upper)
     int *fac;                             // [nobs] projection factors in frame-pair-major order: landmark | observer frame << 16
                                           //        (built once per solve by k_ba_solve; pair offsets in BaShared::pair_ptr)
+    double *pair_part;                    // [45][BA_PP_STRIDE] per-pair partial sums of one linearisation
+    double *fpart;                        // [nobs][BA_FP_STRIDE] per-factor contributions to the landmark sums
+    double *task_cost;                    // [BA_MAX_TASKS] cost of each task of the dynamic queue (summed in task order)
 };
 
 struct BaOutDev {

@@ -72,6 +72,7 @@ struct BaState {
     double *d_margbuf = nullptr;
     int *d_lmcol = nullptr;
     int *d_fac = nullptr;                            // [n_seq][BA_MAX_OBS] pair-major projection factor lists (k_ba_solve scratch)
+    double *d_pair_part = nullptr, *d_fpart = nullptr, *d_task_cost = nullptr;   // fixed-order accumulation scratch (ba_dev.cuh)
     std::vector<int> last_M;
     std::vector<int> last_slots;
 };
@@ -134,6 +135,9 @@ int ba_create(vrf_handle *h)
     BCK(cudaMalloc((void **)&b->d_margbuf, S * kMargDoubles * sizeof(double)));
     BCK(cudaMalloc((void **)&b->d_lmcol, S * BA_MAX_LM * sizeof(int)));
     BCK(cudaMalloc((void **)&b->d_fac, S * BA_MAX_OBS * sizeof(int)));
+    BCK(cudaMalloc((void **)&b->d_pair_part, S * (BA_NF * (BA_NF - 1) / 2) * BA_PP_STRIDE * sizeof(double)));
+    BCK(cudaMalloc((void **)&b->d_fpart, S * (size_t)BA_MAX_OBS * BA_FP_STRIDE * sizeof(double)));
+    BCK(cudaMalloc((void **)&b->d_task_cost, S * BA_MAX_TASKS * sizeof(double)));
     b->prior_cur.assign(S, 0);
     b->prior_valid.assign(S, 0);
     b->last_M.assign(S, 0);
@@ -145,7 +149,8 @@ void ba_destroy(vrf_handle *h)
     BaState *b = h->ba;
     if (!b) return;
     void *dev[] = {b->d_prior[0], b->d_prior[1], b->d_prior_factor, b->d_factor_scratch, b->d_lam, b->d_clam,
-                   b->d_W, b->d_vecs, b->d_imuS, b->d_HP, b->d_colmap, b->d_margbuf, b->d_lmcol, b->d_fac};
+                   b->d_W, b->d_vecs, b->d_imuS, b->d_HP, b->d_colmap, b->d_margbuf, b->d_lmcol, b->d_fac,
+                   b->d_pair_part, b->d_fpart, b->d_task_cost};
     for (void *p : dev) if (p) cudaFree(p);
     if (b->h_prior_dl) cudaFreeHost(b->h_prior_dl);
     for (BaSlot &sl : b->slot) {
@@ -270,6 +275,9 @@ static int pack_problem(vrf_handle *h, BaSlot &sl, int slot, int seq, const VrfB
     pd.shinv_l = v + 9 * BA_MAX_LM;
     pd.imuS = b->d_imuS + (size_t)seq * (BA_NF - 1) * 225;
     pd.fac = b->d_fac + (size_t)seq * BA_MAX_OBS;
+    pd.pair_part = b->d_pair_part + (size_t)seq * (BA_NF * (BA_NF - 1) / 2) * BA_PP_STRIDE;
+    pd.fpart = b->d_fpart + (size_t)seq * BA_MAX_OBS * BA_FP_STRIDE;
+    pd.task_cost = b->d_task_cost + (size_t)seq * BA_MAX_TASKS;
 
     BaMargDev &mg = sl.h_marg[slot];
     double *mb = b->d_margbuf + (size_t)seq * kMargDoubles;

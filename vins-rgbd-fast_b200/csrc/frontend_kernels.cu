@@ -5,9 +5,10 @@
 //
 // Kernel sequence for one batched readImage call (all sequences of the batch in
 // each launch; no host round trip in between):
-//   k_ingest        frame (GRAY8 | RGB8) -> pyramid level 0 of the "forw" buffer
-//                   (+ work-list prefix for k_lk)                 [HBM-bound]
-//   k_pyrdown xL    cv::pyrDown level l -> l+1                    [HBM/L2-bound]
+//   k_pyr<frame>    frame (GRAY8 | RGB8) -> pyramid levels 0 and 1 of the "forw" buffer: ingest fused with the first
+//                   cv::pyrDown, the frame is read once (+ work-list prefix for k_lk)   [HBM-bound]
+//   k_pyr<level>    cv::pyrDown level l -> l+1 for the deeper levels                    [HBM/L2-bound]
+//                   (EQUALIZE: k_ingest -> k_clahe_lut -> k_clahe_apply -> k_pyr<level> from level 0)
 //   k_lk            predictPtsInNextFrame + cv::calcOpticalFlowPyrLK, one warp / feature   (lk_kernels.cu)
 //   k_post_a        status fix-up, inBorder, reduceVector x5, track_cnt++
 //   k_ransac        rejectWithF (cv::findFundamentalMat RANSAC)   (ransac_kernels.cu)
@@ -15,14 +16,41 @@
 //                   grid occupancy + cell selection
 //   k_fast          gridDetect: FAST-9/16 + NMS + mask + top-K slots, one CTA / cell
 //   k_finish        addPoints, undistortedPoints (+velocity), updateID, outputs
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "handle.h"
 #include "introsort.h"
 
 namespace vrf {
 
+// exclusive prefix of the LK work items (n_pts of every sequence of the batch), by one CTA
+__device__ void lk_work_prefix(const SeqCall *calls, int ncalls, const FrontDev &d, int *s_part)
+{
+    const int t = threadIdx.x;
+    const int per = (ncalls + 255) / 256;
+    const int b = t * per, e = min(ncalls, b + per);
+    int s = 0;
+    for (int i = b; i < e; ++i) s += calls[i].first ? 0 : d.n_pts[calls[i].seq];
+    s_part[t] = s;
+    __syncthreads();
+    if (t == 0) {
+        int acc = 0;
+        for (int i = 0; i < 256; ++i) { int v = s_part[i]; s_part[i] = acc; acc += v; }
+        d.work_prefix[ncalls] = acc;
+    }
+    __syncthreads();
+    int acc = s_part[t];
+    for (int i = b; i < e; ++i) {
+        d.work_prefix[i] = acc;
+        acc += calls[i].first ? 0 : d.n_pts[calls[i].seq];
+    }
+    __syncthreads();
+}
+
 // ---------------------------------------------------------------------------
-// k_ingest: copy / convert the input frame into pyramid level 0.
+// k_ingest: copy / convert the input frame into pyramid level 0 (EQUALIZE path and single-level pyramids only; otherwise
+// the ingest is fused into k_pyr below).
 // GRAY8: 16 px per thread (uint4 load/store).  RGB8: 16 px per thread =
 // 3 x uint4 coalesced loads, fixed-point cv::cvtColor RGB2GRAY
 // ((R*9798 + G*19235 + B*3735 + 16384) >> 15), one uint4 store.
@@ -39,26 +67,8 @@ k_ingest(FrontCfg c, const SeqCall *calls, int ncalls, FrontDev d, const uint8_t
 {
     const int ci = blockIdx.y;
     if (blockIdx.x == 0 && ci == 0) {
-        // exclusive prefix of LK work items (n_pts of every sequence of the batch)
         __shared__ int s_part[256];
-        int t = threadIdx.x;
-        int per = (ncalls + 255) / 256;
-        int b = t * per, e = min(ncalls, b + per);
-        int s = 0;
-        for (int i = b; i < e; ++i) s += calls[i].first ? 0 : d.n_pts[calls[i].seq];
-        s_part[t] = s;
-        __syncthreads();
-        if (t == 0) {
-            int acc = 0;
-            for (int i = 0; i < 256; ++i) { int v = s_part[i]; s_part[i] = acc; acc += v; }
-            d.work_prefix[ncalls] = acc;
-        }
-        __syncthreads();
-        int acc = s_part[t];
-        for (int i = b; i < e; ++i) {
-            d.work_prefix[i] = acc;
-            acc += calls[i].first ? 0 : d.n_pts[calls[i].seq];
-        }
+        lk_work_prefix(calls, ncalls, d, s_part);
     }
     const SeqCall call = calls[ci];
     uint8_t *dst = d.pyr[call.buf_cur] + (size_t)call.seq * c.pyr_bytes;   // level 0 at offset 0
@@ -227,91 +237,142 @@ k_clahe_apply(FrontCfg c, const SeqCall *calls, FrontDev d)
 }
 
 // ---------------------------------------------------------------------------
-// k_pyrdown: cv::pyrDown (5x5 separable [1 4 6 4 1], (sum+128)>>8, REFLECT_101).
-// CTA tile = 64 x 32 outputs.  A thread owns 8 adjacent outputs of a row: the
-// horizontal pass reads their 20 source bytes as one 16-byte word plus two
-// 2-byte halos (rows are 16-byte aligned), forms the five taps as packed
-// u16 pairs with byte permutes (row sums <= 16*255 fit 16 bits) and parks
-// 8 sums = 16 bytes in shared memory; the vertical pass combines five such
-// rows, again on packed pairs (<= 256*255 still fits), and stores 8 bytes.
+// k_pyr: one pyramid step, cv::pyrDown (5x5 separable [1 4 6 4 1], (sum+128)>>8, REFLECT_101), fused with the frame
+// ingest when the source is the incoming frame (cv::buildOpticalFlowPyramid's first level, feature_tracker.cpp:302-310):
+//   SRC_RGB8 / SRC_GRAY8 : frame -> level 0 (stored) and level 1, the frame is read from HBM exactly once
+//   SRC_PYR              : level l -> level l + 1 (the deeper levels; level 0 -> 1 on the EQUALIZE path, where CLAHE
+//                          needs the whole level-0 image first)
+// A CTA owns a full-width strip of R1 destination rows.  Three phases over shared memory:
+//   (1) the 2 R1 + 3 source rows are loaded 16 px per thread (RGB8: 3 x uint4, fixed-point RGB2GRAY with IDP.2A:
+//       two dot-product instructions per pixel on doubled 16-bit weights, the gray value lands in byte 2), written to
+//       the level-0 image (own rows only) and parked in shared memory; the two reflected border columns are patched in;
+//   (2) horizontal pass: 8 outputs per thread from one 16-byte shared-memory word + two halo words, two IDP.4A per
+//       output (the five taps 1 4 6 4 1 split over the 4-byte word boundary), stored as packed u16 pairs.  The
+//       rounding constant rides along: +8 per row sum = +128 after the vertical weights (sum 16);
+//   (3) vertical pass on the packed pairs (<= 16 * (16 * 255 + 8) < 2^16), 8 output bytes per thread.
+// All of it exact integer arithmetic => bit-identical to cv::cvtColor / cv::pyrDown (parity: tests/test_frontend_gpu.py,
+// tests/test_golden.py).  ~7 instructions per source pixel instead of ~30: the kernel is HBM-bound.
 // ---------------------------------------------------------------------------
-#define PD_TW 64
-#define PD_TH 32
-#define PD_SEG (PD_TW / 8)
-__global__ void __launch_bounds__(256)
-k_pyrdown(FrontCfg c, const SeqCall *calls, FrontDev d, int level)
+enum { SRC_RGB8 = 0, SRC_GRAY8 = 1, SRC_PYR = 2 };
+
+__device__ __forceinline__ unsigned dp2a_lo_uu(unsigned a, unsigned b, unsigned c)
 {
-    __shared__ uint4 s_h[2 * PD_TH + 3][PD_SEG];
-    const SeqCall call = calls[blockIdx.z];
-    const uint8_t *src = d.pyr[call.buf_cur] + (size_t)call.seq * c.pyr_bytes + c.loff[level];
-    uint8_t *dst = d.pyr[call.buf_cur] + (size_t)call.seq * c.pyr_bytes + c.loff[level + 1];
+    unsigned d;
+    asm("dp2a.lo.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+__device__ __forceinline__ unsigned dp2a_hi_uu(unsigned a, unsigned b, unsigned c)
+{
+    unsigned d;
+    asm("dp2a.hi.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+
+// 4 RGB pixels (12 bytes, words w0 w1 w2) -> 4 gray bytes.  (R*9798 + G*19235 + B*3735 + 16384) >> 15 evaluated as
+// (R*19596 + G*38470 + B*7470 + 32768) >> 16: same quotient, the doubled weights still fit 16 bits and the result is byte 2.
+__device__ __forceinline__ unsigned rgb4_to_gray(unsigned w0, unsigned w1, unsigned w2)
+{
+    const unsigned WRG = 19596u | (38470u << 16), WB0 = 7470u, W0R = 19596u << 16, WGB = 38470u | (7470u << 16);
+    const unsigned v0 = dp2a_hi_uu(WB0, w0, dp2a_lo_uu(WRG, w0, 32768u));   // R G B = w0.b0 b1 b2
+    const unsigned v1 = dp2a_lo_uu(WGB, w1, dp2a_hi_uu(W0R, w0, 32768u));   // w0.b3 w1.b0 b1
+    const unsigned v2 = dp2a_lo_uu(WB0, w2, dp2a_hi_uu(WRG, w1, 32768u));   // w1.b2 b3 w2.b0
+    const unsigned v3 = dp2a_hi_uu(WGB, w2, dp2a_lo_uu(W0R, w2, 32768u));   // w2.b1 b2 b3
+    return __byte_perm(__byte_perm(v0, v1, 0x0062), __byte_perm(v2, v3, 0x0062), 0x5410);
+}
+
+template <int SRC>
+__global__ void __launch_bounds__(256)
+k_pyr(FrontCfg c, const SeqCall *calls, int ncalls, FrontDev d, const uint8_t *frames, size_t frame_bytes, int level, int R1)
+{
+    extern __shared__ __align__(16) uint8_t s_pyr[];
+    const int tid = threadIdx.x;
+    const int ci = blockIdx.y;
+    if (SRC != SRC_PYR && blockIdx.x == 0 && ci == 0) lk_work_prefix(calls, ncalls, d, reinterpret_cast<int *>(s_pyr));
+    const SeqCall call = calls[ci];
+    uint8_t *pyr = d.pyr[call.buf_cur] + (size_t)call.seq * c.pyr_bytes;
     const int sw = c.lw[level], sh = c.lh[level], sp = c.lp[level];
     const int dw = c.lw[level + 1], dh = c.lh[level + 1], dp = c.lp[level + 1];
-    const int ox = blockIdx.x * PD_TW, oy = blockIdx.y * PD_TH;
-    const int nrow = 2 * PD_TH + 3;
-    for (int it = threadIdx.x; it < nrow * PD_SEG; it += 256) {
-        const int r = it / PD_SEG, sg = it - r * PD_SEG;
-        const int dx0 = ox + 8 * sg;
-        uint4 out = make_uint4(0, 0, 0, 0);
-        if (dx0 < dw) {
-            const int sy = reflect101(2 * oy + r - 2, sh);
-            const uint8_t *row = src + (size_t)sy * sp;
-            const int x0 = 2 * dx0;                       // source column of the first output's centre tap
-            uint4 w;
-            unsigned lft, rgt;                            // bytes (x0-2, x0-1) and (x0+16, x0+17)
-            if (x0 >= 2 && x0 + 18 <= sw) {
-                w = *reinterpret_cast<const uint4 *>(row + x0);
-                lft = *reinterpret_cast<const unsigned short *>(row + x0 - 2);
-                rgt = *reinterpret_cast<const unsigned short *>(row + x0 + 16);
-            } else {
-                unsigned bb[20];
-#pragma unroll
-                for (int k = 0; k < 20; ++k) bb[k] = row[reflect101(x0 - 2 + k, sw)];
-                lft = bb[0] | (bb[1] << 8);
-                w.x = bb[2] | (bb[3] << 8) | (bb[4] << 16) | (bb[5] << 24);
-                w.y = bb[6] | (bb[7] << 8) | (bb[8] << 16) | (bb[9] << 24);
-                w.z = bb[10] | (bb[11] << 8) | (bb[12] << 16) | (bb[13] << 24);
-                w.w = bb[14] | (bb[15] << 8) | (bb[16] << 16) | (bb[17] << 24);
-                rgt = bb[18] | (bb[19] << 8);
-            }
-            // even / odd source bytes as u16 pairs: EP[j] = (b[4j], b[4j+2]), OP[j] = (b[4j+1], b[4j+3])
-            const unsigned wv[4] = {w.x, w.y, w.z, w.w};
-            unsigned EP[6], OP[5];
-            EP[0] = (lft & 0xFFu) << 16;                  // (-, b[-2])
-            OP[0] = (lft >> 8) << 16;                     // (-, b[-1])
-#pragma unroll
-            for (int j = 0; j < 4; ++j) { EP[j + 1] = __byte_perm(wv[j], 0u, 0x4240); OP[j + 1] = __byte_perm(wv[j], 0u, 0x4341); }
-            EP[5] = rgt & 0xFFu;                          // (b[16], -)
-            unsigned o[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const unsigned eprev = __byte_perm(EP[j], EP[j + 1], 0x5432), enext = __byte_perm(EP[j + 1], EP[j + 2], 0x5432);
-                const unsigned oprev = __byte_perm(OP[j], OP[j + 1], 0x5432);
-                o[j] = eprev + enext + 6u * EP[j + 1] + 4u * (oprev + OP[j + 1]);
-            }
-            out = make_uint4(o[0], o[1], o[2], o[3]);
+    const uint8_t *src = SRC == SRC_PYR ? pyr + c.loff[level] : frames + (size_t)ci * frame_bytes;
+    uint8_t *dst0 = pyr + c.loff[level];          // level-l image (written by the ingest variants)
+    uint8_t *dst1 = pyr + c.loff[level + 1];
+    const int gpr = sp >> 4;                      // 16-px groups per source row (pitches are multiples of 16)
+    const int hpr = (dw + 7) >> 3;                // 8-output groups per destination row
+    const int NR = 2 * R1 + 3;
+    const int gpitch = sp + 32;                   // shared gray rows: 16 B margin | row | 16 B margin
+    const int hpitch = hpr * 16;
+    uint8_t *gs = s_pyr;
+    uint8_t *hs = s_pyr + (size_t)NR * gpitch;
+    const int y1_0 = blockIdx.x * R1;
+    const int r0 = 2 * y1_0 - 2;                  // source row of shared row 0
+
+    // ---- (1) load / convert / store level l, park in shared memory ----
+    for (int it = tid; it < NR * gpr; it += 256) {
+        const int r = it / gpr, g = it - r * gpr;
+        const int sy = r0 + r;
+        if (sy > sh + 1) continue;                // rows only destination rows >= dh would use
+        const int syr = reflect101(sy, sh);
+        uint4 out;
+        if (SRC == SRC_RGB8) {
+            const uint4 *p = reinterpret_cast<const uint4 *>(src + (size_t)syr * sw * 3) + g * 3;
+            const uint4 a = __ldg(p), b = __ldg(p + 1), cc = __ldg(p + 2);
+            out = make_uint4(rgb4_to_gray(a.x, a.y, a.z), rgb4_to_gray(a.w, b.x, b.y), rgb4_to_gray(b.z, b.w, cc.x),
+                             rgb4_to_gray(cc.y, cc.z, cc.w));
+        } else if (SRC == SRC_GRAY8) {
+            out = __ldg(reinterpret_cast<const uint4 *>(src + (size_t)syr * sw) + g);
+        } else {
+            out = *(reinterpret_cast<const uint4 *>(src + (size_t)syr * sp) + g);
         }
-        s_h[r][sg] = out;
+        *reinterpret_cast<uint4 *>(gs + (size_t)r * gpitch + 16 + 16 * g) = out;
+        if (SRC != SRC_PYR && r >= 2 && r < 2 + 2 * R1 && sy < sh)
+            *reinterpret_cast<uint4 *>(dst0 + (size_t)sy * sp + 16 * g) = out;
     }
     __syncthreads();
-    {
-        const int y = threadIdx.x / PD_SEG, sg = threadIdx.x - y * PD_SEG;
-        const int dy = oy + y, dx0 = ox + 8 * sg;
-        if (dy < dh && dx0 < dw) {
-            const uint4 a0 = s_h[2 * y][sg], a1 = s_h[2 * y + 1][sg], a2 = s_h[2 * y + 2][sg], a3 = s_h[2 * y + 3][sg], a4 = s_h[2 * y + 4][sg];
-            const unsigned rnd = 0x00800080u, msk = 0x00FF00FFu;
-            const unsigned v0 = ((a0.x + a4.x + 4u * (a1.x + a3.x) + 6u * a2.x + rnd) >> 8) & msk;
-            const unsigned v1 = ((a0.y + a4.y + 4u * (a1.y + a3.y) + 6u * a2.y + rnd) >> 8) & msk;
-            const unsigned v2 = ((a0.z + a4.z + 4u * (a1.z + a3.z) + 6u * a2.z + rnd) >> 8) & msk;
-            const unsigned v3 = ((a0.w + a4.w + 4u * (a1.w + a3.w) + 6u * a2.w + rnd) >> 8) & msk;
-            const unsigned lo = __byte_perm(v0, v1, 0x6420), hi = __byte_perm(v2, v3, 0x6420);
-            uint8_t *q = dst + (size_t)dy * dp + dx0;
-            if (dx0 + 8 <= dw) *reinterpret_cast<uint2 *>(q) = make_uint2(lo, hi);
-            else {
+    for (int r = tid; r < NR; r += 256) {         // REFLECT_101 columns -2, -1, sw, sw + 1
+        uint8_t *row = gs + (size_t)r * gpitch + 16;
+        row[-1] = row[1]; row[-2] = row[2];
+        row[sw] = row[sw - 2]; row[sw + 1] = row[sw - 3];
+    }
+    __syncthreads();
+
+    // ---- (2) horizontal pass: h[x] = p[2x-2] + 4 p[2x-1] + 6 p[2x] + 4 p[2x+1] + p[2x+2] + 8, packed (h[2m], h[2m+1]) ----
+    for (int it = tid; it < NR * hpr; it += 256) {
+        const int r = it / hpr, q = it - r * hpr;
+        const unsigned *rw = reinterpret_cast<const unsigned *>(gs + (size_t)r * gpitch + 16) + 4 * q;
+        const uint4 w = *reinterpret_cast<const uint4 *>(rw);
+        const unsigned wv[6] = {rw[-1], w.x, w.y, w.z, w.w, rw[4]};
+        unsigned o[4];
 #pragma unroll
-                for (int k = 0; k < 8; ++k)
-                    if (dx0 + k < dw) q[k] = (uint8_t)(((k < 4 ? lo : hi) >> (8 * (k & 3))) & 0xFFu);
-            }
+        for (int m = 0; m < 4; ++m) {
+            // outputs 2m (taps: bytes 2,3 of word m-1, bytes 0..2 of word m) and 2m+1 (word m, byte 0 of word m+1)
+            const unsigned lo = __dp4a(wv[m], 0x04010000u, __dp4a(wv[m + 1], 0x00010406u, 8u));
+            const unsigned hi = __dp4a(wv[m + 1], 0x04060401u, __dp4a(wv[m + 2], 0x00000001u, 8u));
+            o[m] = __byte_perm(lo, hi, 0x5410);
+        }
+        *reinterpret_cast<uint4 *>(hs + (size_t)r * hpitch + 16 * q) = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+    __syncthreads();
+
+    // ---- (3) vertical pass ----
+    for (int it = tid; it < R1 * hpr; it += 256) {
+        const int y = it / hpr, q = it - y * hpr;
+        const int dy = y1_0 + y, dx0 = 8 * q;
+        if (dy >= dh) break;
+        const uint8_t *hp = hs + (size_t)(2 * y) * hpitch + 16 * q;
+        const uint4 a0 = *reinterpret_cast<const uint4 *>(hp), a1 = *reinterpret_cast<const uint4 *>(hp + hpitch),
+                    a2 = *reinterpret_cast<const uint4 *>(hp + 2 * hpitch), a3 = *reinterpret_cast<const uint4 *>(hp + 3 * hpitch),
+                    a4 = *reinterpret_cast<const uint4 *>(hp + 4 * hpitch);
+        const unsigned msk = 0x00FF00FFu;
+        const unsigned v0 = ((a0.x + a4.x + 4u * (a1.x + a3.x) + 6u * a2.x) >> 8) & msk;
+        const unsigned v1 = ((a0.y + a4.y + 4u * (a1.y + a3.y) + 6u * a2.y) >> 8) & msk;
+        const unsigned v2 = ((a0.z + a4.z + 4u * (a1.z + a3.z) + 6u * a2.z) >> 8) & msk;
+        const unsigned v3 = ((a0.w + a4.w + 4u * (a1.w + a3.w) + 6u * a2.w) >> 8) & msk;
+        const unsigned lo = __byte_perm(v0, v1, 0x6420), hi = __byte_perm(v2, v3, 0x6420);
+        uint8_t *qd = dst1 + (size_t)dy * dp + dx0;
+        if (dx0 + 8 <= dw) *reinterpret_cast<uint2 *>(qd) = make_uint2(lo, hi);
+        else {
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                if (dx0 + k < dw) qd[k] = (uint8_t)(((k < 4 ? lo : hi) >> (8 * (k & 3))) & 0xFFu);
         }
     }
 }
@@ -874,10 +935,30 @@ size_t fast_smem_bytes(const FrontCfg &c)
     return 2 * a + (npx / 4 + 64) * sizeof(unsigned) + (size_t)2 * VRF_CAP * sizeof(int2);
 }
 
+// k_pyr strip height (destination rows per CTA) and dynamic shared memory: 2 R1 + 3 gray rows + as many packed row-sum rows
+static int pyr_strip_rows(const FrontCfg &c, int level)
+{
+    int r1 = 16;
+    if (const char *e = getenv("VRF_PYR_R1")) { const int v = atoi(e); if (v >= 1 && v <= 64) r1 = v; }
+    while (r1 > 1 && (size_t)(2 * r1 + 3) * (c.lp[level] + 32 + ((c.lw[level + 1] + 7) >> 3) * 16) > 96 * 1024) r1 >>= 1;
+    return r1;
+}
+static size_t pyr_smem_bytes(const FrontCfg &c, int level, int r1)
+{
+    const size_t b = (size_t)(2 * r1 + 3) * (c.lp[level] + 32 + ((c.lw[level + 1] + 7) >> 3) * 16);
+    return b < 1024 ? 1024 : b;        // the LK work-list prefix borrows 1 KB
+}
+
 int front_configure_kernels(const FrontCfg &c)
 {
     cudaError_t e = cudaFuncSetAttribute(k_post_b, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)post_b_smem_bytes());
     if (e != cudaSuccess) return (int)e;
+    if (c.levels > 1) {
+        const int smem0 = (int)pyr_smem_bytes(c, 0, pyr_strip_rows(c, 0));
+        if ((e = cudaFuncSetAttribute(k_pyr<SRC_RGB8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem0)) != cudaSuccess) return (int)e;
+        if ((e = cudaFuncSetAttribute(k_pyr<SRC_GRAY8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem0)) != cudaSuccess) return (int)e;
+        if ((e = cudaFuncSetAttribute(k_pyr<SRC_PYR>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem0)) != cudaSuccess) return (int)e;
+    }
     e = cudaFuncSetAttribute(k_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast_smem_bytes(c));
     return (int)e;
 }
@@ -886,11 +967,24 @@ int front_launch(const FrontCfg &c, const SeqCall *d_calls, int ncalls, const Fr
                  const uint8_t *d_frames, size_t frame_bytes, int fmt, int any_pub, int sm_count, LaunchCtx &lc)
 {
     cudaStream_t st = lc.st;
-    dim3 gi((c.rows * (c.cols >> 4) + 255) / 256, ncalls);
-    if (gi.x > 64) gi.x = 64;
-    lc.begin(K_INGEST);
-    k_ingest<<<gi, 256, 0, st>>>(c, d_calls, ncalls, d, d_frames, frame_bytes, fmt);
-    lc.end();
+    // Level 0 (+ level 1): the frame is read once by the fused ingest + pyrDown kernel.  With EQUALIZE the whole level-0
+    // image has to exist before CLAHE, so the frame is ingested alone and level 1 is built from the equalised image.
+    int l_first = 0;
+    if (c.equalize || c.levels < 2) {
+        dim3 gi((c.rows * (c.cols >> 4) + 255) / 256, ncalls);
+        if (gi.x > 64) gi.x = 64;
+        lc.begin(K_INGEST);
+        k_ingest<<<gi, 256, 0, st>>>(c, d_calls, ncalls, d, d_frames, frame_bytes, fmt);
+        lc.end();
+    } else {
+        const int r1 = pyr_strip_rows(c, 0);
+        dim3 g((c.lh[1] + r1 - 1) / r1, ncalls);
+        lc.begin(K_PYR);
+        if (fmt == VRF_FMT_RGB8) k_pyr<SRC_RGB8><<<g, 256, pyr_smem_bytes(c, 0, r1), st>>>(c, d_calls, ncalls, d, d_frames, frame_bytes, 0, r1);
+        else k_pyr<SRC_GRAY8><<<g, 256, pyr_smem_bytes(c, 0, r1), st>>>(c, d_calls, ncalls, d, d_frames, frame_bytes, 0, r1);
+        lc.end();
+        l_first = 1;
+    }
     if (c.equalize) {
         lc.begin(K_CLAHE_LUT);
         k_clahe_lut<<<dim3(64, ncalls), 256, 0, st>>>(c, d_calls, d);
@@ -901,10 +995,11 @@ int front_launch(const FrontCfg &c, const SeqCall *d_calls, int ncalls, const Fr
         k_clahe_apply<<<ga, 256, 0, st>>>(c, d_calls, d);
         lc.end();
     }
-    for (int l = 0; l + 1 < c.levels; ++l) {
-        dim3 g((c.lw[l + 1] + PD_TW - 1) / PD_TW, (c.lh[l + 1] + PD_TH - 1) / PD_TH, ncalls);
-        lc.begin(K_PYRDOWN);
-        k_pyrdown<<<g, 256, 0, st>>>(c, d_calls, d, l);
+    for (int l = l_first; l + 1 < c.levels; ++l) {
+        const int r1 = pyr_strip_rows(c, l);
+        dim3 g((c.lh[l + 1] + r1 - 1) / r1, ncalls);
+        lc.begin(K_PYR);
+        k_pyr<SRC_PYR><<<g, 256, pyr_smem_bytes(c, l, r1), st>>>(c, d_calls, ncalls, d, d_frames, frame_bytes, l, r1);
         lc.end();
     }
     lk_launch(c, d_calls, ncalls, d, maps, sm_count, lc);

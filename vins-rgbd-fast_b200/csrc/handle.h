@@ -21,11 +21,11 @@ struct FmState;   // fm_kernels.cu
 
 // Kernel ids for launch counting and optional per-kernel CUDA-event profiling.
 enum KernelId {
-    K_INGEST = 0, K_CLAHE_LUT, K_CLAHE_APPLY, K_PYRDOWN, K_LK, K_POST_A, K_RANSAC, K_POST_B, K_FAST, K_FINISH,
+    K_INGEST = 0, K_CLAHE_LUT, K_CLAHE_APPLY, K_PYR, K_LK, K_POST_A, K_RANSAC, K_POST_B, K_FAST, K_FINISH,
     K_BA_SOLVE, K_BA_MARG, K_BA_PRIOR_FACTOR, K_FM_TRI, K_FM_CHECK, K_IMU_PREINT, K_COUNT
 };
 static const char *const kKernelNames[K_COUNT] = {
-    "k_ingest", "k_clahe_lut", "k_clahe_apply", "k_pyrdown", "k_lk", "k_post_a", "k_ransac", "k_post_b", "k_fast", "k_finish",
+    "k_ingest", "k_clahe_lut", "k_clahe_apply", "k_pyr", "k_lk", "k_post_a", "k_ransac", "k_post_b", "k_fast", "k_finish",
     "k_ba_solve", "k_ba_marg", "k_ba_prior_factor", "k_fm_triangulate", "k_fm_check", "k_imu_preint"};
 
 struct Prof {
