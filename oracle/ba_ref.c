@@ -706,8 +706,14 @@ static double evaluate(const VrfBaProblem *pb, const VrfConfig *cfg, Lin *L, con
         if (with_jac) {
             /* local parameterisation: first 6 columns of the 2x7 blocks */
             double li[12], lj[12], le[12], lf[2] = {0, 0};
+            /* a constant parameter block is not part of the Ceres program: its Jacobian columns do not exist (para_Pose[0] in
+             * VO mode, estimator.cpp:1182-1185; para_Ex_Pose / para_Td when held constant) */
+            const int host_const = (i == 0 && L->pose0_const);
             for (int rr = 0; rr < 2; rr++)
-                for (int c = 0; c < 6; c++) { li[rr * 6 + c] = Ji[rr * 7 + c]; lj[rr * 6 + c] = Jj[rr * 7 + c]; le[rr * 6 + c] = L->ex_active ? Jex[rr * 7 + c] : 0.0; }
+                for (int c = 0; c < 6; c++) {
+                    li[rr * 6 + c] = host_const ? 0.0 : Ji[rr * 7 + c]; lj[rr * 6 + c] = Jj[rr * 7 + c];
+                    le[rr * 6 + c] = L->ex_active ? Jex[rr * 7 + c] : 0.0;
+                }
             if (!L->lm_const[l]) { lf[0] = Jf[0]; lf[1] = Jf[1]; }
             double *Jb[5] = {li, lj, le, lf, Jt};
             int ncl[5] = {6, 6, 6, 1, 1};
@@ -824,6 +830,12 @@ static void fn_mul(void *c_, const double *v, const int *cols, int n, double r, 
     for (int k = 0; k < n; k++) a += v[k] * c->scale[cols[k]] * c->x[cols[k]];
     c->y[rid] = a;
 }
+static void fn_grad(void *c_, const double *v, const int *cols, int n, double r, int rid)     /* g += J^T r (unscaled) */
+{
+    double *g = (double *)c_;
+    (void)rid;
+    for (int k = 0; k < n; k++) g[cols[k]] += v[k] * r;
+}
 typedef struct { const double *scale; double *g; double *H; double *hll; double *W; int M; } CtxNormal;
 static void fn_normal(void *c_, const double *v, const int *cols, int n, double r, int rid)
 {
@@ -879,12 +891,182 @@ static void state_plus(const VrfBaProblem *pb, const Lin *L, const State *x, con
     *o = *x;            /* shares lam pointer: caller provides separate storage */
 }
 
+
+/* ------------------------------------------------------------------ */
+/* Ceres' projected Armijo line search of bound-constrained problems     */
+/* (third party, restated from the published algorithm: Ceres Solver      */
+/*  internal/ceres/trust_region_minimizer.cc DoLineSearch,                */
+/*  line_search.cc ArmijoLineSearch::DoSearch +                           */
+/*  InterpolatingPolynomialMinimizingStepSize, polynomial.cc).            */
+/* Solver::Options defaults, which estimator.cpp:1348-1363 leaves alone:  */
+/*   line_search_interpolation_type CUBIC, sufficient decrease 1e-4,      */
+/*   max_line_search_step_contraction 1e-3, min_..._contraction 0.6,      */
+/*   max_num_line_search_step_size_iterations 20, min step size 1e-9.     */
+/* PARITY UNPINNED against Ceres itself (not installed here).             */
+/* ------------------------------------------------------------------ */
+typedef struct { double x, value, gradient; int value_ok, grad_ok; } LsSample;
+
+static double poly_eval(const double *c, int n, double x)      /* n coefficients, highest power first (Horner) */
+{
+    double v = 0;
+    for (int i = 0; i < n; i++) v = v * x + c[i];
+    return v;
+}
+
+/* FindInterpolatingPolynomial: the polynomial of degree (#constraints - 1) through the samples' values and gradients;
+ * Ceres solves the Vandermonde-type system with Eigen's fullPivLu -- Gaussian elimination with full pivoting here. */
+static int poly_interpolate(const LsSample *smp, int ns, double *coef)
+{
+    int nc = 0;
+    for (int i = 0; i < ns; i++) nc += (smp[i].value_ok ? 1 : 0) + (smp[i].grad_ok ? 1 : 0);
+    const int degree = nc - 1;
+    double A[6][7];
+    int row = 0;
+    for (int i = 0; i < ns; i++) {
+        if (smp[i].value_ok) {
+            for (int j = 0; j <= degree; j++) A[row][j] = pow(smp[i].x, degree - j);
+            A[row][nc] = smp[i].value; row++;
+        }
+        if (smp[i].grad_ok) {
+            for (int j = 0; j < degree; j++) A[row][j] = (degree - j) * pow(smp[i].x, degree - j - 1);
+            A[row][degree] = 0.0;
+            A[row][nc] = smp[i].gradient; row++;
+        }
+    }
+    int perm[6];
+    for (int j = 0; j < nc; j++) perm[j] = j;
+    for (int k = 0; k < nc; k++) {
+        int pr = k, pc = k; double best = -1;
+        for (int r = k; r < nc; r++) for (int c = k; c < nc; c++) if (fabs(A[r][c]) > best) { best = fabs(A[r][c]); pr = r; pc = c; }
+        if (best <= 0) { for (int r = k; r < nc; r++) A[r][nc] = 0; break; }     /* rank deficient: remaining unknowns 0 */
+        if (pr != k) for (int c = 0; c <= nc; c++) { double t = A[k][c]; A[k][c] = A[pr][c]; A[pr][c] = t; }
+        if (pc != k) { for (int r = 0; r < nc; r++) { double t = A[r][k]; A[r][k] = A[r][pc]; A[r][pc] = t; } int t = perm[k]; perm[k] = perm[pc]; perm[pc] = t; }
+        for (int r = k + 1; r < nc; r++) {
+            double f = A[r][k] / A[k][k];
+            for (int c = k; c <= nc; c++) A[r][c] -= f * A[k][c];
+        }
+    }
+    double y[6];
+    for (int k = nc - 1; k >= 0; k--) {
+        double v = A[k][nc];
+        for (int c = k + 1; c < nc; c++) v -= A[k][c] * y[c];
+        y[k] = A[k][k] != 0.0 ? v / A[k][k] : 0.0;
+    }
+    for (int k = 0; k < nc; k++) coef[perm[k]] = y[k];
+    return nc;
+}
+
+/* Real parts of all roots of a polynomial (n coefficients, highest first).  Ceres' FindPolynomialRoots: leading zeros
+ * removed; degree 1 and 2 in closed form; higher degrees through the eigenvalues of the balanced companion matrix -- here
+ * the same roots from the Aberth-Ehrlich iteration (converged to machine precision).  MinimizePolynomial tests the real
+ * part of EVERY root, complex ones included ("a bit of an overkill ... simpler to just check these values"). */
+static int poly_root_real_parts(const double *c_in, int n, double *re)
+{
+    while (n > 0 && c_in[0] == 0.0) { c_in++; n--; }
+    const int deg = n - 1;
+    if (deg < 1) return 0;
+    if (deg == 1) { re[0] = -c_in[1] / c_in[0]; return 1; }
+    if (deg == 2) {
+        const double a = c_in[0], b = c_in[1], c = c_in[2];
+        const double D = b * b - 4 * a * c, sD = sqrt(fabs(D));
+        if (D >= 0) {
+            if (b >= 0) { re[0] = (-b - sD) / (2.0 * a); re[1] = (2.0 * c) / (-b - sD); }
+            else { re[0] = (2.0 * c) / (-b + sD); re[1] = (-b + sD) / (2.0 * a); }
+        } else { re[0] = -b / (2.0 * a); re[1] = -b / (2.0 * a); }
+        return 2;
+    }
+    /* monic coefficients */
+    double a[8];
+    for (int i = 0; i <= deg; i++) a[i] = c_in[i] / c_in[0];
+    double rad = 0;
+    for (int i = 1; i <= deg; i++) rad = fmax(rad, fabs(a[i]));
+    rad = 1.0 + rad;                                             /* Cauchy bound */
+    double zr[8], zi[8];
+    for (int k = 0; k < deg; k++) { double ang = 2.0 * 3.14159265358979323846 * k / deg + 0.4; zr[k] = 0.5 * rad * cos(ang); zi[k] = 0.5 * rad * sin(ang); }
+    for (int it = 0; it < 500; it++) {
+        double change = 0;
+        for (int k = 0; k < deg; k++) {
+            /* p(z), p'(z) by Horner in complex arithmetic */
+            double pr = 1.0, pi = 0.0, dr = 0.0, di = 0.0;
+            for (int i = 1; i <= deg; i++) {
+                double ndr = dr * zr[k] - di * zi[k] + pr, ndi = dr * zi[k] + di * zr[k] + pi;
+                dr = ndr; di = ndi;
+                double npr = pr * zr[k] - pi * zi[k] + a[i], npi = pr * zi[k] + pi * zr[k];
+                pr = npr; pi = npi;
+            }
+            const double dd = dr * dr + di * di;
+            if (dd == 0.0) continue;
+            double wr = (pr * dr + pi * di) / dd, wi = (pi * dr - pr * di) / dd;        /* p / p' */
+            double sr = 0, si = 0;
+            for (int j = 0; j < deg; j++) {
+                if (j == k) continue;
+                const double er = zr[k] - zr[j], ei = zi[k] - zi[j], ee = er * er + ei * ei;
+                if (ee == 0.0) continue;
+                sr += er / ee; si -= ei / ee;
+            }
+            /* w / (1 - w s) */
+            const double qr = 1.0 - (wr * sr - wi * si), qi = -(wr * si + wi * sr), qq = qr * qr + qi * qi;
+            if (qq == 0.0) continue;
+            const double ur = (wr * qr + wi * qi) / qq, ui = (wi * qr - wr * qi) / qq;
+            zr[k] -= ur; zi[k] -= ui;
+            change = fmax(change, fabs(ur) + fabs(ui));
+        }
+        if (change <= 1e-15 * rad) break;
+    }
+    for (int k = 0; k < deg; k++) re[k] = zr[k];
+    return deg;
+}
+
+/* MinimizePolynomial on [x_min, x_max] */
+static double poly_minimize(const double *c, int n, double x_min, double x_max)
+{
+    double best_x = (x_min + x_max) / 2.0, best = poly_eval(c, n, best_x);
+    double v = poly_eval(c, n, x_min);
+    if (v < best) { best = v; best_x = x_min; }
+    v = poly_eval(c, n, x_max);
+    if (v < best) { best = v; best_x = x_max; }
+    if (n <= 2) return best_x;
+    double d[8], re[8];
+    for (int i = 0; i < n - 1; i++) d[i] = (n - 1 - i) * c[i];
+    const int nr = poly_root_real_parts(d, n - 1, re);
+    for (int i = 0; i < nr; i++) {
+        if (re[i] < x_min || re[i] > x_max) continue;
+        v = poly_eval(c, n, re[i]);
+        if (v < best) { best = v; best_x = re[i]; }
+    }
+    return best_x;
+}
+
+/* LineSearch::InterpolatingPolynomialMinimizingStepSize for CUBIC interpolation */
+static double ls_interpolating_step(const LsSample *lower, const LsSample *prev, const LsSample *cur, double min_step, double max_step)
+{
+    if (!cur->value_ok) return fmin(fmax(cur->x * 0.5, min_step), max_step);
+    LsSample smp[3];
+    int ns = 0;
+    smp[ns++] = *lower;
+    smp[ns++] = *cur;
+    if (prev->value_ok) smp[ns++] = *prev;
+    double coef[6];
+    const int nc = poly_interpolate(smp, ns, coef);
+    return poly_minimize(coef, nc, min_step, max_step);
+}
+
+/* test hook: minimiser of the interpolating polynomial through up to three (x, value, gradient) samples */
+double oracle_ls_interpolating_step(const double *xs, const double *vals, const double *grads, int ns, double min_step, double max_step)
+{
+    const int cur_ok = isfinite(vals[1]) && isfinite(grads[1]);
+    LsSample lower = {xs[0], vals[0], grads[0], 1, 1}, cur = {xs[1], vals[1], grads[1], cur_ok, cur_ok}, prev = {0, 0, 0, 0, 0};
+    if (ns > 2) { prev.x = xs[2]; prev.value = vals[2]; prev.gradient = grads[2]; prev.value_ok = 1; prev.grad_ok = 1; }
+    return ls_interpolating_step(&lower, &prev, &cur, min_step, max_step);
+}
+
 /* ------------------------------------------------------------------ */
 /* the solver (Ceres trust-region / traditional dogleg / dense Schur)   */
 /* ------------------------------------------------------------------ */
 typedef struct {
     int iterations, successful, termination;
-    int armijo_failures;    /* steps of a bound-constrained problem that fail Ceres' Armijo test at step size 1 (see below) */
+    int armijo_failures;    /* steps of a bound-constrained problem that fail Ceres' Armijo test at step size 1: the line search ran */
+    int line_search_steps;  /* ... and returned a shortened step */
     double initial_cost, final_cost;
 } SolveSummary;
 
@@ -951,7 +1133,7 @@ static int solve(const VrfBaProblem *pb, const VrfConfig *cfg, Lin *L, State *x,
     for (int l = 0; l < M; l++)
         if (!L->lm_const[l] && x->lam[l] > L->lm_ub[l]) x->lam[l] = L->lm_ub[l];
     double x_cost = evaluate(pb, cfg, L, x, 1);
-    sum->initial_cost = x_cost; sum->iterations = 0; sum->successful = 0; sum->termination = 0; sum->armijo_failures = 0;
+    sum->initial_cost = x_cost; sum->iterations = 0; sum->successful = 0; sum->termination = 0; sum->armijo_failures = 0; sum->line_search_steps = 0;
     /* Solver::Options::is_constrained: some non-constant parameter block carries a bound */
     int constrained = 0;
     for (int l = 0; l < M; l++) if (!L->lm_const[l] && isfinite(L->lm_ub[l])) constrained = 1;
@@ -1107,14 +1289,50 @@ static int solve(const VrfBaProblem *pb, const VrfConfig *cfg, Lin *L, State *x,
                 apply_delta(L, x, delta, &cand, lam2);
                 double cand_cost = evaluate(pb, cfg, L, &cand, 0);
                 /* For a bound-constrained problem Ceres runs a projected Armijo line search on the step before evaluating the
-                 * candidate (TrustRegionMinimizer::DoLineSearch: sufficient decrease 1e-4, cubic interpolation).  When the full
-                 * step passes the test, f(x [+] delta) <= f(x) + 1e-4 g.delta, the search returns step size 1 and nothing
-                 * changes -- the case restated here.  When it fails, Ceres shortens the step (NOT restated: unverifiable
-                 * without Ceres); such steps are counted so that callers and tests can see where the two can differ. */
+                 * candidate (TrustRegionMinimizer::DoLineSearch).  phi(t) = f(x [+] t delta) with the bounds projection inside
+                 * Plus, phi'(t) = delta . gradient(x [+] t delta).  When the full step passes the sufficient-decrease test the
+                 * search returns t = 1 and nothing changes; otherwise the step is contracted to the minimiser of the cubic /
+                 * quintic through (0, current, previous) inside [1e-3 t, 0.6 t] until the test holds (<= 20 iterations), and
+                 * delta is scaled by the accepted t.  A failed search leaves delta alone.  The trust-region bookkeeping
+                 * (model cost change, dogleg step norm) keeps referring to the unshortened step, as in Ceres. */
                 if (constrained) {
-                    double gts = 0;
-                    for (int c = 0; c < NT; c++) gts += g[c] * step[c];        /* = unscaled gradient . unscaled step */
-                    if (cand_cost > x_cost + 1e-4 * gts) sum->armijo_failures++;
+                    double gts = 0, dmax = 0;
+                    for (int c = 0; c < NT; c++) { gts += g[c] * step[c]; dmax = fmax(dmax, fabs(delta[c])); }   /* unscaled gradient . delta */
+                    if (!(isfinite(cand_cost)) || cand_cost > x_cost + 1e-4 * gts) {
+                        sum->armijo_failures++;
+                        LsSample lower = {0.0, x_cost, gts, 1, 1}, prev = {0, 0, 0, 0, 0}, cur = {1.0, cand_cost, 0, 0, 1};
+                        State trial;
+                        int ok = 0;
+                        /* value and gradient at t = 1 */
+                        for (int it = 0;; it++) {
+                            if (it > 0) {
+                                if (it >= 20) break;                                  /* max_num_line_search_step_size_iterations */
+                                const double t = ls_interpolating_step(&lower, &prev, &cur, 1e-3 * cur.x, 0.6 * cur.x);
+                                if (t * dmax < 1e-9) break;                           /* min_line_search_step_size */
+                                prev = cur;
+                                cur.x = t;
+                            }
+                            for (int c = 0; c < NT; c++) tmp[c] = cur.x * delta[c];
+                            apply_delta(L, x, tmp, &trial, lam3);
+                            cur.value = evaluate(pb, cfg, L, &trial, 1);
+                            memset(tmp, 0, sizeof(double) * NT);
+                            for_each_row(pb, L, fn_grad, tmp);
+                            cur.gradient = 0;
+                            for (int c = 0; c < NT; c++) cur.gradient += tmp[c] * delta[c];
+                            cur.value_ok = isfinite(cur.value) && isfinite(cur.gradient);
+                            cur.grad_ok = cur.value_ok;
+                            if (getenv("ORACLE_BA_DEBUG"))
+                                fprintf(stderr, "   ls it %d t %.6g value %.9f dphi %.6g (phi0 %.9f dphi0 %.6g dmax %.3g)\n", it, cur.x, cur.value, cur.gradient, x_cost, gts, dmax);
+                            if (cur.value_ok && cur.value <= x_cost + 1e-4 * gts * cur.x) { ok = (it > 0); break; }
+                        }
+                        if (ok) {
+                            for (int c = 0; c < NT; c++) delta[c] *= cur.x;
+                            apply_delta(L, x, delta, &cand, lam2);
+                            cand_cost = cur.value;
+                            sum->line_search_steps++;
+                        }
+                        evaluate(pb, cfg, L, x, 1);       /* the linearisation at x again (the rows are re-used by a rejected step) */
+                    }
                 }
                 double step_norm = sqrt(active_x_norm2_diff(L, x, &cand));
                 if (step_norm <= 1e-8 * (x_norm + 1e-8)) { sum->termination = 3; break; }      /* parameter tolerance */

@@ -33,7 +33,15 @@ def lib():
         _lib.oracle_preint_propagate.restype = None
         _lib.oracle_prior_residual.argtypes = [C.POINTER(B.VrfPrior)] + [C.c_void_p] * 3 + [C.c_double, C.c_void_p]
         _lib.oracle_prior_residual.restype = None
+        _lib.oracle_ls_interpolating_step.argtypes = [C.c_void_p] * 3 + [C.c_int, C.c_double, C.c_double]
+        _lib.oracle_ls_interpolating_step.restype = C.c_double
     return _lib
+
+
+def ls_interpolating_step(xs, vals, grads, min_step, max_step):
+    """Ceres' InterpolatingPolynomialMinimizingStepSize (CUBIC) on samples [lower bound, current(, previous)]."""
+    a = [np.ascontiguousarray(v, np.float64) for v in (xs, vals, grads)]
+    return float(lib().oracle_ls_interpolating_step(_p(a[0]), _p(a[1]), _p(a[2]), len(a[0]), float(min_step), float(max_step)))
 
 
 def _p(a):

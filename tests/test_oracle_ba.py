@@ -368,3 +368,46 @@ def test_information_form_of_the_prior_is_equivalent():
         assert np.linalg.matrix_rank(J) < n or a > 0          # the first prior has truncated (zero) rows
         c_piv = _pivoted_cholesky_c0(HP, gp)
         assert abs(c_piv - c0) <= 1e-6 * max(c0, 1e-12), (a, c_piv, c0)
+
+
+def _ceres_interpolating_step(xs, vals, grads, lo, hi):
+    """Ceres' FindInterpolatingPolynomial + MinimizePolynomial written with numpy's own tools: np.linalg.solve for the
+    Vandermonde-type system and np.roots -- the eigenvalues of the companion matrix, which is how Ceres' FindPolynomialRoots
+    obtains the roots -- taking the real part of every root like MinimizePolynomial does."""
+    n = 2 * len(xs)
+    deg = n - 1
+    A, b = [], []
+    for x, v, g in zip(xs, vals, grads):
+        A.append([x ** (deg - j) for j in range(n)]); b.append(v)
+        A.append([(deg - j) * x ** (deg - j - 1) if j < deg else 0.0 for j in range(n)]); b.append(g)
+    c = np.linalg.solve(np.array(A), np.array(b))
+    cand = [(lo + hi) / 2.0, lo, hi]
+    cand += [r.real for r in np.roots(np.polyder(c)) if lo <= r.real <= hi]
+    vals_ = [np.polyval(c, t) for t in cand]
+    return cand[int(np.argmin(vals_))], c
+
+
+def test_line_search_step_matches_companion_matrix_minimiser():
+    """The step-size rule of the projected Armijo line search (oracle/ba_ref.c::ls_interpolating_step, Aberth-Ehrlich roots)
+    against an independent statement with numpy's companion-matrix roots: cubic (two samples) and quintic (three samples)
+    interpolants, contraction interval [1e-3 t, 0.6 t] as ArmijoLineSearch::DoSearch passes it."""
+    rng = np.random.default_rng(5)
+    n_checked = 0
+    for trial in range(400):
+        ns = 2 + trial % 2
+        t_cur = float(rng.uniform(0.05, 1.0))
+        xs = [0.0, t_cur] + ([float(rng.uniform(t_cur * 1.5, t_cur * 5.0))] if ns == 3 else [])
+        f0 = float(rng.uniform(10, 100))
+        g0 = -float(rng.uniform(0.1, 5.0))
+        vals = [f0] + [f0 + float(rng.uniform(-0.2, 2.0)) * x for x in xs[1:]]
+        grads = [g0] + [float(rng.uniform(-3.0, 6.0)) for _ in xs[1:]]
+        lo, hi = 1e-3 * t_cur, 0.6 * t_cur
+        want, c = _ceres_interpolating_step(xs, vals, grads, lo, hi)
+        got = ba_ref.ls_interpolating_step(xs, vals, grads, lo, hi)
+        # equal minimisers, or -- when two candidates tie to rounding -- equal polynomial values
+        if abs(got - want) > 1e-9 * max(1.0, abs(want)):
+            assert abs(np.polyval(c, got) - np.polyval(c, want)) <= 1e-9 * max(1.0, abs(np.polyval(c, want))), (trial, got, want)
+        n_checked += 1
+    assert n_checked == 400
+    # a sample that could not be evaluated: bisection inside the interval
+    assert ba_ref.ls_interpolating_step([0.0, 0.8], [1.0, np.nan], [-1.0, np.nan], 1e-3 * 0.8, 0.6 * 0.8) == 0.4

@@ -27,6 +27,7 @@
 // chains and shared-memory bandwidth bound; the only
 // dense contraction is the 172^3/3 Cholesky.
 #include "ba_math.cuh"
+#include "ba_linesearch.cuh"
 
 namespace vrf {
 
@@ -56,6 +57,7 @@ struct BaShared {
     int pair_ptr[BA_NF * (BA_NF - 1) / 2 + 1];        // offsets of the frame pairs (host i, observer j) in BaProbDev::fac
     int pair_cnt[BA_NF * (BA_NF - 1) / 2 + 1];
     double d8[36];                                    // chol_diag8: the 8x8 diagonal block being factorised (packed lower triangle)
+    int imu_ord[BA_NF], imu_neven;                    // IMU factors ordered [even j ... | odd j ...] for the two assembly passes
     double sc[16];
     int flag[8];
 };
@@ -71,12 +73,12 @@ __device__ __forceinline__ bool col_active_dev(const BaMeta &m, int col)
     return col == BA_COL_TD ? m.td_active != 0 : m.ex_active != 0;
 }
 
-// Contributions of one batch of projection factors of the pair (host i, observer j) to the rows of the "global"
-// block g = [ex-pose (6) | td (1)] (tangent columns 165..171), only when one of them is variable:
-// Jg^T Ji, Jg^T Jj, Jg^T r and the lower triangle of Jg^T Jg, each summed over the warp's lanes with the
-// reduce-scatter butterfly and added to the shared system.  Jg: 2 x 7 row-major.
-__device__ __noinline__ void accumulate_g(double *H, double *g, int i, int j, int lane, const double *Ji, const double *Jj,
-                                          const double *Jg, const double *r)
+// Contributions of one batch of projection factors of a frame pair to the rows of the "global" block
+// g = [ex-pose (6) | td (1)] (tangent columns 165..171), only when one of them is variable: Jg^T Ji, Jg^T Jj, Jg^T r
+// (13 sums per row q) and the lower triangle of Jg^T Jg (28 sums), each summed over the warp's lanes with the
+// reduce-scatter butterfly and accumulated over the pair's batches in accg[0..6] / accg[7..8] (lane 2e holds entry e).
+// Jg: 2 x 7 row-major.
+__device__ __noinline__ void accumulate_g(double *accg, int lane, const double *Ji, const double *Jj, const double *Jg, const double *r)
 {
 #pragma unroll 1
     for (int q = 0; q < 7; ++q) {
@@ -85,13 +87,7 @@ __device__ __noinline__ void accumulate_g(double *H, double *g, int i, int j, in
 #pragma unroll
         for (int c = 0; c < 6; ++c) { v[c] = g0 * Ji[c] + g1 * Ji[6 + c]; v[6 + c] = g0 * Jj[c] + g1 * Jj[6 + c]; }
         v[12] = g0 * r[0] + g1 * r[1]; v[13] = 0; v[14] = 0; v[15] = 0;
-        const double s_ = reduce_scatter16(v, lane);
-        if (!(lane & 1) && s_ != 0.0) {
-            const int e = lane >> 1;
-            if (e < 6) atomicAdd(&H[pk(BA_COL_EX + q, 6 * i + e)], s_);
-            else if (e < 12) atomicAdd(&H[pk(BA_COL_EX + q, 6 * j + e - 6)], s_);
-            else if (e == 12) atomicAdd(&g[BA_COL_EX + q], s_);
-        }
+        accg[q] += reduce_scatter16(v, lane);
     }
 #pragma unroll 1
     for (int rd = 0; rd < 2; ++rd) {
@@ -104,13 +100,7 @@ __device__ __noinline__ void accumulate_g(double *H, double *g, int i, int j, in
             const int b = e - a * (a + 1) / 2;
             v[t] = (e < 28) ? Jg[a] * Jg[b] + Jg[7 + a] * Jg[7 + b] : 0.0;
         }
-        const double s_ = reduce_scatter16(v, lane);
-        const int e = rd * 16 + (lane >> 1);
-        if (!(lane & 1) && e < 28 && s_ != 0.0) {
-            int a = 0;
-            while ((a + 1) * (a + 2) / 2 <= e) ++a;
-            atomicAdd(&H[pk(BA_COL_EX + a, BA_COL_EX + e - a * (a + 1) / 2)], s_);
-        }
+        accg[7 + rd] += reduce_scatter16(v, lane);
     }
 }
 
@@ -155,20 +145,30 @@ __device__ __forceinline__ void prior_dx_smem(BaShared &sh, const double *pose, 
     }
 }
 
+// index of the frame pair (host i, observer j > i) in the pair-major order
+__device__ __forceinline__ int pair_index(int i, int j) { return i * (2 * BA_NF - i - 1) / 2 + (j - i - 1); }
+
 // cost of all residual blocks at (pose, sb, lam); optionally the full linearisation into sh.H / sh.g / landmark arrays.
 // __noinline__: the solve loop calls this from five sites; inlining produced a 51k-instruction kernel (800 KB of SASS)
 // that thrashed the instruction cache (one resident CTA per SM, 16 warps in different code regions).
 // GACT: ex-pose and/or td variable (two instantiations so that the common constant-extrinsic path keeps its registers).
+//
+// Bit-reproducible: the residual blocks are dealt to the warps by a dynamic queue, but no sum depends on which warp ran
+// which task or when -- a task only produces partials that it alone owns (whitened IMU Jacobians in shared memory,
+// per-pair and per-factor sums in the L2-resident scratch of ba_dev.cuh, its own cost), and the assembly pass adds them
+// with one owner thread per destination in a fixed order.  No floating-point atomics.
 template <bool GACT>
 __device__ __noinline__ double ba_evaluate_t(const BaMeta &m, const BaProbDev &p, BaShared &sh, const double *pose, const double *sb,
-                                const double *ex, const double td, const double *lam, bool lin)
+                                const double *ex, const double td, const double *lam, const int mode)
 {
+    // mode 0: cost only; 1: cost + full linearisation (H, g, W, hll, gl); 2: cost + gradient only (g, gl), for the trial
+    // points of the projected line search -- H, W and hll are left alone
+    const bool lin = mode != 0, full = mode == 1;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = BA_THREADS / 32;
     if (lin) {
-        for (int i = tid; i < BA_NC * (BA_NC + 1) / 2; i += BA_THREADS) sh.H[i] = 0.0;
+        if (full) for (int i = tid; i < BA_NC * (BA_NC + 1) / 2; i += BA_THREADS) sh.H[i] = 0.0;
         for (int i = tid; i < BA_NC; i += BA_THREADS) sh.g[i] = 0.0;
-        for (int i = tid; i < m.M * BA_WS; i += BA_THREADS) p.W[i] = 0.0;
-        for (int l = tid; l < m.M; l += BA_THREADS) { p.hll[l] = 0.0; p.gl[l] = 0.0; }
+        // (the coupling rows W are zeroed once per solve: a linearisation rewrites the same entries every time)
     }
     for (int f = tid; f < BA_NF; f += BA_THREADS) d_q2R(pose + 7 * f + 3, sh.R + 9 * f);
     if (tid == 0) { d_q2R(ex + 3, sh.ric); sh.flag[2] = 0; }
@@ -178,24 +178,19 @@ __device__ __noinline__ double ba_evaluate_t(const BaMeta &m, const BaProbDev &p
 #define EPROF(k) do { if (eprof) { long long t_ = clock64(); et[k] += t_ - ec; ec = t_; } } while (0)
     __syncthreads();
     EPROF(0);
-    double cost = 0.0;
     // ---- residual blocks as a dynamic task queue over the 16 warps: the IMU factors first (the longest tasks), then the
-    // projection factors (linearisation: one task per frame pair; cost only: one task per two landmarks).  The IMU and
-    // projection tasks touch disjoint accumulators except the pose blocks of adjacent frames, which use atomics. ----
+    // projection factors (linearisation: one task per frame pair; cost only: one task per 32 factors) ----
     const int nproj = lin ? BA_NPAIR : (sh.pair_ptr[BA_NPAIR] + 31) >> 5;
     const int ntask = m.nimu + nproj;
-    int ptask = -1;
-    long long ptask_t0 = 0;
     for (;;) {
         int task = 0;
         if (lane == 0) task = atomicAdd(&sh.flag[2], 1);
         task = __shfl_sync(0xffffffffu, task, 0);
-        if (eprof && blockIdx.x == 0 && lane == 0 && ptask >= 0)
-            printf("task lin=%d id=%d (%s) warp=%d cycles=%lld\n", (int)lin, ptask, ptask < m.nimu ? "imu" : "proj", warp, clock64() - ptask_t0);
-        ptask = task; ptask_t0 = eprof ? clock64() : 0;
         if (task >= ntask) break;
+        double tcost = 0.0;
         if (task < m.nimu) {
-            // ---- IMU factor: one warp per factor ----
+            // ---- IMU factor: one warp per factor; whitened residual and Jacobian go to shared memory, J^T J is formed by
+            //      the assembly pass below ----
             const int f = task;
             const int j = m.imu_j[f], i = j - 1;
             const VrfImuPreint *pre = p.imu + (j - 1);
@@ -205,30 +200,14 @@ __device__ __noinline__ double ba_evaluate_t(const BaMeta &m, const BaProbDev &p
             imu_residual_raw(pre, pose + 7 * i, sb + 9 * i, pose + 7 * j, sb + 9 * j, m.g_norm, rr, &cx);
             // whitened residual row `lane`
             double rw = 0;
-            if (lane < 15) { for (int k = lane; k < 15; ++k) rw += S[lane * 15 + k] * rr[k]; cost += 0.5 * rw * rw; }
-            if (!lin) continue;
-            if (lane < 15) sh.imur[f][lane] = rw;
-            if (lane < 30) {
-                double col[15];
-                imu_jac_col(pre, pose + 7 * i, sb + 9 * i, pose + 7 * j, sb + 9 * j, m.g_norm, &cx, lane, col);
-                for (int rI = 0; rI < 15; ++rI) { double a = 0; for (int k = rI; k < 15; ++k) a += S[rI * 15 + k] * col[k]; sh.imuJ[f][rI * 30 + lane] = a; }
-            }
-            __syncwarp();
-            // accumulate J^T J and J^T r ; tangent column of local column c
-            auto tcol = [&](int c) { return c < 6 ? 6 * i + c : c < 15 ? 66 + 9 * i + (c - 6) : c < 21 ? 6 * j + (c - 15) : 66 + 9 * j + (c - 21); };
-            for (int a = 0; a < 30; ++a) {
-                // row a of the 30x30 lower triangle: lanes over b <= a
-                if (lane <= a) {
-                    double h = 0;
-#pragma unroll
-                    for (int k = 0; k < 15; ++k) h += sh.imuJ[f][k * 30 + a] * sh.imuJ[f][k * 30 + lane];
-                    atomicAdd(&sh.H[pk(tcol(a), tcol(lane))], h);
+            if (lane < 15) { for (int k = lane; k < 15; ++k) rw += S[lane * 15 + k] * rr[k]; tcost = 0.5 * rw * rw; }
+            if (lin) {
+                if (lane < 15) sh.imur[f][lane] = rw;
+                if (lane < 30) {
+                    double col[15];
+                    imu_jac_col(pre, pose + 7 * i, sb + 9 * i, pose + 7 * j, sb + 9 * j, m.g_norm, &cx, lane, col);
+                    for (int rI = 0; rI < 15; ++rI) { double a = 0; for (int k = rI; k < 15; ++k) a += S[rI * 15 + k] * col[k]; sh.imuJ[f][rI * 30 + lane] = a; }
                 }
-            }
-            if (lane < 30) {
-                double gsum = 0;
-                for (int k = 0; k < 15; ++k) gsum += sh.imuJ[f][k * 30 + lane] * sh.imur[f][k];
-                atomicAdd(&sh.g[tcol(lane)], gsum);
             }
         } else if (!lin) {
             // ---- projection factors, cost only: 32 consecutive factors of the pair-major list per warp, one lane per factor ----
@@ -240,31 +219,29 @@ __device__ __noinline__ double ba_evaluate_t(const BaMeta &m, const BaProbDev &p
                 double r[2], Ji[12], Jj[12], Jl[2], xi, yi, xj, yj;
                 obs_at(m, p, o0, td, xi, yi);
                 obs_at(m, p, o0 + (j - i), td, xj, yj);
-                cost += 0.5 * proj_eval(pose + 7 * i, sh.R + 9 * i, pose + 7 * j, sh.R + 9 * j, ex, sh.ric, lam[l], xi, yi, xj, yj, false,
+                tcost = 0.5 * proj_eval(pose + 7 * i, sh.R + 9 * i, pose + 7 * j, sh.R + 9 * j, ex, sh.ric, lam[l], xi, yi, xj, yj, false,
                                         p.lm_const[l] != 0, r, Ji, Jj, Jl);
             }
         } else {
             // ---- projection factors, linearisation: one warp per frame pair (host i, observer j), one lane per factor ----
             // Every factor of the pair adds to the same 12x12 block of J^T J.  The 90 distinct sums (off-diagonal 6x6,
             // two diagonal lower triangles, two gradient 6-vectors) are reduced over the warp's lanes with a
-            // reduce-scatter butterfly (one shuffle per value instead of five) and accumulated in registers over the
-            // pair's batches: no shared-memory atomics.  The off-diagonal block has a single projection owner (adjacent
-            // frames also receive the IMU factor's block, hence the atomic there); the diagonal parts go to per-pair
-            // partials that are summed per frame afterwards.
+            // reduce-scatter butterfly (one shuffle per value instead of five), accumulated in registers over the
+            // pair's batches and written to the pair's slot of p.pair_part.  The landmark sums (host-frame part of the W
+            // row, hll, gl) of a factor go to the factor's slot of p.fpart; the observer part of the W row has this factor
+            // as its only contributor and is stored directly.
             const int pi = task - m.nimu;
             int i = 0, rem = pi;
             while (rem >= BA_NF - 1 - i) { rem -= BA_NF - 1 - i; ++i; }
             const int j = i + 1 + rem;
             double acc[6] = {0, 0, 0, 0, 0, 0};
-            bool any_pair = false;
+            double accg[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
             // the pair's factors are contiguous in the pair-major list built once per solve: full batches of 32 factors
-            // instead of a scan over all landmarks that finds a handful of this pair's factors per 32-landmark batch
             const int f_end = sh.pair_ptr[pi + 1];
             for (int fb = sh.pair_ptr[pi]; fb < f_end; fb += 32) {
                 const bool act = fb + lane < f_end;
                 const int l = act ? (p.fac[fb + lane] & 0xFFFF) : 0;
                 const int o0 = act ? p.obs_ptr[l] : 0;
-                any_pair = true;
                 double r[2] = {0, 0}, Ji[12], Jj[12], Jl[2] = {0, 0};
                 double Jg[14];          // [ex-pose | td] block, only touched when one of them is variable
 #pragma unroll
@@ -279,6 +256,7 @@ __device__ __noinline__ double ba_evaluate_t(const BaMeta &m, const BaProbDev &p
                     obs_at(m, p, o0, td, xi, yi);
                     obs_at(m, p, oj, td, xj, yj);
                     double *Wl = p.W + (size_t)l * BA_WS;
+                    double *fp = p.fpart + (size_t)oj * BA_FP_STRIDE;
                     if (!gact)
                         rho0 = proj_eval(pose + 7 * i, sh.R + 9 * i, pose + 7 * j, sh.R + 9 * j, ex, sh.ric, lam[l], xi, yi, xj, yj, true,
                                          p.lm_const[l] != 0, r, Ji, Jj, Jl);
@@ -290,54 +268,206 @@ __device__ __noinline__ double ba_evaluate_t(const BaMeta &m, const BaProbDev &p
 #pragma unroll
                         for (int c = 0; c < 6; ++c) { Jg[c] = m.ex_active ? Je[c] : 0.0; Jg[7 + c] = m.ex_active ? Je[6 + c] : 0.0; }
                         Jg[6] = Jt[0]; Jg[13] = Jt[1];
+                        if (full) {
 #pragma unroll
-                        for (int q = 0; q < 7; ++q) atomicAdd(&Wl[66 + q], Jg[q] * Jl[0] + Jg[7 + q] * Jl[1]);
+                            for (int q = 0; q < 7; ++q) fp[8 + q] = Jg[q] * Jl[0] + Jg[7 + q] * Jl[1];
+                        }
                     }
-                    cost += 0.5 * rho0;
-                    // landmark rows: the observer part has one contributor, the rest sums over the landmark's factors
+                    tcost += 0.5 * rho0;
+                    // a constant parameter block is not part of the Ceres program: no Jacobian columns (para_Pose[0] in VO mode,
+                    // estimator.cpp:1182-1185)
+                    if (i == 0 && !m.use_imu) {
 #pragma unroll
-                    for (int a = 0; a < 6; ++a) {
-                        Wl[6 * j + a] = Jj[a] * Jl[0] + Jj[6 + a] * Jl[1];
-                        atomicAdd(&Wl[6 * i + a], Ji[a] * Jl[0] + Ji[6 + a] * Jl[1]);
+                        for (int k = 0; k < 12; ++k) Ji[k] = 0.0;
                     }
-                    atomicAdd(&p.hll[l], Jl[0] * Jl[0] + Jl[1] * Jl[1]);
-                    atomicAdd(&p.gl[l], Jl[0] * r[0] + Jl[1] * r[1]);
+                    if (full) {
+#pragma unroll
+                        for (int a = 0; a < 6; ++a) {
+                            Wl[6 * j + a] = Jj[a] * Jl[0] + Jj[6 + a] * Jl[1];
+                            fp[a] = Ji[a] * Jl[0] + Ji[6 + a] * Jl[1];
+                        }
+                        fp[6] = Jl[0] * Jl[0] + Jl[1] * Jl[1];
+                    }
+                    fp[7] = Jl[0] * r[0] + Jl[1] * r[1];
                 }
-                if (gact) accumulate_g(sh.H, sh.g, i, j, lane, Ji, Jj, Jg, r);
+                if (gact) {
+                    if (full) accumulate_g(accg, lane, Ji, Jj, Jg, r);
+                    else {
+                        // gradient only: Jg_q^T r, q = 0..6, into the slot the full pass uses (lane 2 * 12 of row q)
+                        double v[16];
+#pragma unroll
+                        for (int t = 0; t < 16; ++t) v[t] = t < 7 ? Jg[t] * r[0] + Jg[7 + t] * r[1] : 0.0;
+                        accg[0] += reduce_scatter16(v, lane);
+                    }
+                }
 #pragma unroll
                 for (int ps = 0; ps < 6; ++ps) {
+                    if (!full && ps < 4) continue;          // the gradient entries 78..89 live in rounds 4 and 5
                     double v[16];
 #pragma unroll
                     for (int t = 0; t < 16; ++t) v[t] = pair_entry(ps * 16 + t, Ji, Jj, r);
                     acc[ps] += reduce_scatter16(v, lane);
                 }
             }
-            if (any_pair && !(lane & 1)) {
-                // off-diagonal 6x6 block: this pair is its only projection owner (adjacent frames also receive the IMU
-                // factor's block, hence the atomic there); diagonal blocks / gradients are shared with the other pairs of
-                // frames i and j and with the IMU factors: atomics (2970 per linearisation, spread over the 16 warps)
-                const bool adjacent = (j == i + 1);
+            if (!(lane & 1)) {
+                double *pp = p.pair_part + (size_t)pi * BA_PP_STRIDE + (lane >> 1);
 #pragma unroll
-                for (int ps = 0; ps < 6; ++ps) {
-                    const int e = ps * 16 + (lane >> 1);
-                    if (e < 36) {
-                        double *dst = &sh.H[pk(6 * j + e / 6, 6 * i + e % 6)];
-                        if (adjacent) atomicAdd(dst, acc[ps]); else *dst = acc[ps];
-                    } else if (e < 78) {
-                        const int f = e < 57 ? j : i, t = e < 57 ? e - 36 : e - 57;
-                        int a = 0;
-                        while ((a + 1) * (a + 2) / 2 <= t) ++a;
-                        atomicAdd(&sh.H[pk(6 * f + a, 6 * f + (t - a * (a + 1) / 2))], acc[ps]);
-                    } else if (e < 90) {
-                        const int f = e < 84 ? j : i, a = e < 84 ? e - 78 : e - 84;
-                        atomicAdd(&sh.g[6 * f + a], acc[ps]);
-                    }
+                for (int ps = 0; ps < 6; ++ps) pp[16 * ps] = acc[ps];
+                if (gact && full) {
+#pragma unroll
+                    for (int q = 0; q < 9; ++q) pp[96 + 16 * q] = accg[q];
                 }
+                // gradient only: lane 2 q holds Jg_q^T r -> slot 96 + 16 q + 12
+                if (gact && !full && (lane >> 1) < 7) p.pair_part[(size_t)pi * BA_PP_STRIDE + 96 + 16 * (lane >> 1) + 12] = accg[0];
             }
         }
+        tcost = warp_sum_d(tcost);
+        if (lane == 0) p.task_cost[task] = tcost;
     }
     EPROF(1);
     __syncthreads();
+    double cost = 0.0;
+    for (int t = tid; t < ntask; t += BA_THREADS) cost += p.task_cost[t];
+    if (mode == 2) {
+        // ---- gradient only: pose gradients from the per-pair sums, ex-pose / td gradient, g_l from the per-factor slots ----
+        const int nC = BA_NF * 6, nE = gact ? 7 : 0;
+        for (int it = tid; it < nC + nE + m.M; it += BA_THREADS) {
+            double sum = 0.0;
+            if (it < nC) {
+                const int f = it / 6, t = it - 6 * f;
+                for (int i = 0; i < f; ++i) sum += p.pair_part[(size_t)pair_index(i, f) * BA_PP_STRIDE + 78 + t];
+                for (int j = f + 1; j < BA_NF; ++j) sum += p.pair_part[(size_t)pair_index(f, j) * BA_PP_STRIDE + 84 + t];
+                sh.g[6 * f + t] = sum;
+            } else if (it < nC + nE) {
+                const int q = it - nC;
+                for (int pi = 0; pi < BA_NPAIR; ++pi) sum += p.pair_part[(size_t)pi * BA_PP_STRIDE + 96 + 16 * q + 12];
+                sh.g[BA_COL_EX + q] = sum;
+            } else {
+                const int l = it - nC - nE;
+                const int o0 = p.obs_ptr[l], o1 = p.obs_ptr[l + 1];
+                for (int o = o0 + 1; o < o1; ++o) sum += p.fpart[(size_t)o * BA_FP_STRIDE + 7];
+                p.gl[l] = sum;
+            }
+        }
+        __syncthreads();
+        for (int pass = 0; pass < 2; ++pass) {
+            const int f_lo = pass ? sh.imu_neven : 0, f_hi = pass ? m.nimu : sh.imu_neven;
+            for (int it = tid + f_lo * 30; it < f_hi * 30; it += BA_THREADS) {
+                const int fo = it / 30, c = it - fo * 30;
+                const int f = sh.imu_ord[fo];
+                const int j = m.imu_j[f], i = j - 1;
+                const double *J = sh.imuJ[f];
+                const int tc = c < 6 ? 6 * i + c : c < 15 ? 66 + 9 * i + (c - 6) : c < 21 ? 6 * j + (c - 15) : 66 + 9 * j + (c - 21);
+                double gsum = 0;
+#pragma unroll
+                for (int k = 0; k < 15; ++k) gsum += J[k * 30 + c] * sh.imur[f][k];
+                sh.g[tc] += gsum;
+            }
+            __syncthreads();
+        }
+    }
+    if (full) {
+        // ---- assembly, one owner thread per destination, contributions added in a fixed order ----
+        // (a) projection factors: pose blocks and gradient from the per-pair sums, landmark sums from the per-factor slots
+        const int nfp = gact ? 15 : 8;
+        const int nA = BA_NPAIR * 36, nB = BA_NF * 21, nC = BA_NF * 6, nD = gact ? 7 * BA_NF * 6 + 7 + 28 : 0, nG = m.M * nfp;
+        for (int it = tid; it < nA + nB + nC + nD + nG; it += BA_THREADS) {
+            int e = it;
+            if (e < nA) {
+                // off-diagonal 6 x 6 block Jj^T Ji of pair (i, j): this pair is its only projection contributor
+                const int pi = e / 36, t = e - pi * 36;
+                int i = 0, rem = pi;
+                while (rem >= BA_NF - 1 - i) { rem -= BA_NF - 1 - i; ++i; }
+                const int j = i + 1 + rem;
+                sh.H[pk(6 * j + t / 6, 6 * i + t % 6)] = p.pair_part[(size_t)pi * BA_PP_STRIDE + t];
+                continue;
+            }
+            e -= nA;
+            if (e < nB + nC) {
+                // diagonal 6 x 6 block (lower triangle, 21 entries) / gradient (6 entries) of frame f: frame f is the observer of
+                // the pairs (i < f, f) and the host of the pairs (f, j > f)
+                const bool grad = e >= nB;
+                if (grad) e -= nB;
+                const int per = grad ? 6 : 21;
+                const int f = e / per, t = e - f * per;
+                const int so = grad ? 78 + t : 36 + t, sh_ = grad ? 84 + t : 57 + t;     // slot as observer / as host
+                double sum = 0.0;
+                for (int i = 0; i < f; ++i) sum += p.pair_part[(size_t)pair_index(i, f) * BA_PP_STRIDE + so];
+                for (int j = f + 1; j < BA_NF; ++j) sum += p.pair_part[(size_t)pair_index(f, j) * BA_PP_STRIDE + sh_];
+                if (grad) sh.g[6 * f + t] = sum;
+                else {
+                    int a = 0;
+                    while ((a + 1) * (a + 2) / 2 <= t) ++a;
+                    sh.H[pk(6 * f + a, 6 * f + (t - a * (a + 1) / 2))] = sum;
+                }
+                continue;
+            }
+            e -= nB + nC;
+            if (e < nD) {
+                double sum = 0.0;
+                if (e < 7 * BA_NF * 6) {
+                    // H[ex/td row q, pose column 6 f + c]
+                    const int q = e / (BA_NF * 6), fc = e - q * (BA_NF * 6), f = fc / 6, c = fc - 6 * f;
+                    for (int i = 0; i < f; ++i) sum += p.pair_part[(size_t)pair_index(i, f) * BA_PP_STRIDE + 96 + 16 * q + 6 + c];
+                    for (int j = f + 1; j < BA_NF; ++j) sum += p.pair_part[(size_t)pair_index(f, j) * BA_PP_STRIDE + 96 + 16 * q + c];
+                    sh.H[pk(BA_COL_EX + q, 6 * f + c)] = sum;
+                } else if (e < 7 * BA_NF * 6 + 7) {
+                    const int q = e - 7 * BA_NF * 6;
+                    for (int pi = 0; pi < BA_NPAIR; ++pi) sum += p.pair_part[(size_t)pi * BA_PP_STRIDE + 96 + 16 * q + 12];
+                    sh.g[BA_COL_EX + q] = sum;
+                } else {
+                    const int t = e - (7 * BA_NF * 6 + 7);
+                    for (int pi = 0; pi < BA_NPAIR; ++pi) sum += p.pair_part[(size_t)pi * BA_PP_STRIDE + 208 + t];
+                    int a = 0;
+                    while ((a + 1) * (a + 2) / 2 <= t) ++a;
+                    sh.H[pk(BA_COL_EX + a, BA_COL_EX + t - a * (a + 1) / 2)] = sum;
+                }
+                continue;
+            }
+            e -= nD;
+            {
+                // landmark l, value a: sum over the landmark's factors in observation order
+                const int l = e / nfp, a = e - l * nfp;
+                const int o0 = p.obs_ptr[l], o1 = p.obs_ptr[l + 1];
+                double sum = 0.0;
+                for (int o = o0 + 1; o < o1; ++o) sum += p.fpart[(size_t)o * BA_FP_STRIDE + a];
+                if (a < 6) p.W[(size_t)l * BA_WS + 6 * p.start[l] + a] = sum;
+                else if (a == 6) p.hll[l] = sum;
+                else if (a == 7) p.gl[l] = sum;
+                else p.W[(size_t)l * BA_WS + 66 + (a - 8)] = sum;
+            }
+        }
+        __syncthreads();
+        // (b) IMU factors: J^T J (465 entries of the 30 x 30 lower triangle) and J^T r (30) per factor from the whitened
+        //     Jacobians in shared memory.  Factors with equal parity of j touch disjoint frames: two passes, plain adds.
+        for (int pass = 0; pass < 2; ++pass) {
+            const int f_lo = pass ? sh.imu_neven : 0, f_hi = pass ? m.nimu : sh.imu_neven;
+            for (int it = tid + f_lo * 495; it < f_hi * 495; it += BA_THREADS) {
+                const int fo = it / 495, e = it - fo * 495;
+                const int f = sh.imu_ord[fo];
+                const int j = m.imu_j[f], i = j - 1;
+                const double *J = sh.imuJ[f];
+                auto tcol = [&](int c) { return c < 6 ? 6 * i + c : c < 15 ? 66 + 9 * i + (c - 6) : c < 21 ? 6 * j + (c - 15) : 66 + 9 * j + (c - 21); };
+                if (e < 465) {
+                    int a = (int)((sqrtf(8.0f * e + 1.0f) - 1.0f) * 0.5f);
+                    while (a * (a + 1) / 2 > e) --a;
+                    while ((a + 1) * (a + 2) / 2 <= e) ++a;
+                    const int b = e - a * (a + 1) / 2;
+                    double h = 0;
+#pragma unroll
+                    for (int k = 0; k < 15; ++k) h += J[k * 30 + a] * J[k * 30 + b];
+                    sh.H[pk(tcol(a), tcol(b))] += h;
+                } else {
+                    const int c = e - 465;
+                    double gsum = 0;
+#pragma unroll
+                    for (int k = 0; k < 15; ++k) gsum += J[k * 30 + c] * sh.imur[f][k];
+                    sh.g[tcol(c)] += gsum;
+                }
+            }
+            __syncthreads();
+        }
+    }
     EPROF(3);
     EPROF(2);
     // ---- prior (MarginalizationFactor::Evaluate, marginalization_factor.cpp:353-415), in information form:
@@ -389,13 +519,14 @@ __device__ __noinline__ double ba_evaluate_t(const BaMeta &m, const BaProbDev &p
         }
         __syncthreads();
         if (lin) {
-            // g += gp + HP dx ; H += HP, both through the column map (constant blocks drop out)
+            // g += gp + HP dx ; H += HP, both through the column map (constant blocks drop out; distinct prior columns map to
+            // distinct tangent columns, so every destination has one writer)
             for (int a = tid; a < n; a += BA_THREADS) {
                 const int ca = sh.pcol[a];
-                if (ca >= 0) atomicAdd(&sh.g[ca], sh.pr0[a] + sh.pr[a]);
+                if (ca >= 0) sh.g[ca] += sh.pr0[a] + sh.pr[a];
             }
 #pragma unroll 4
-            for (int e = tid; e < n * n; e += BA_THREADS) {
+            for (int e = tid; full && e < n * n; e += BA_THREADS) {
                 int a2 = e / n, b = e - a2 * n;
                 if (b > a2) continue;
                 int ca = sh.pcol[a2], cb = sh.pcol[b];
@@ -407,16 +538,16 @@ __device__ __noinline__ double ba_evaluate_t(const BaMeta &m, const BaProbDev &p
     __syncthreads();
     EPROF(4);
     if (eprof && blockIdx.x == 0 && (tid == 0 || tid == 320 || tid == 500))
-        printf("evaluate lin=%d tid=%d zero=%lld tasks=%lld diag=%lld wait=%lld prior=%lld\n", (int)lin, tid, et[0], et[1], et[2], et[3], et[4]);
+        printf("evaluate mode=%d tid=%d zero=%lld tasks=%lld diag=%lld wait=%lld prior=%lld\n", mode, tid, et[0], et[1], et[2], et[3], et[4]);
 #undef EPROF
     return block_sum(cost, sh.red);
 }
 
 __device__ __forceinline__ double ba_evaluate(const BaMeta &m, const BaProbDev &p, BaShared &sh, const double *pose, const double *sb,
-                                              const double *ex, const double td, const double *lam, bool lin)
+                                              const double *ex, const double td, const double *lam, int mode)
 {
-    return (m.ex_active || m.td_active) ? ba_evaluate_t<true>(m, p, sh, pose, sb, ex, td, lam, lin)
-                                        : ba_evaluate_t<false>(m, p, sh, pose, sb, ex, td, lam, lin);
+    return (m.ex_active || m.td_active) ? ba_evaluate_t<true>(m, p, sh, pose, sb, ex, td, lam, mode)
+                                        : ba_evaluate_t<false>(m, p, sh, pose, sb, ex, td, lam, mode);
 }
 
 // D(8x8) = A(8x4) B(4x8) + D on the FP64 tensor cores (SASS: DMMA.8x8x4); see the trailing update of the Cholesky below
@@ -548,6 +679,14 @@ k_ba_solve(const BaMeta *metas, const BaProbDev *probs, BaOutDev *outs)
     // TrustRegionMinimizer::Init of a bound-constrained problem projects the start point onto the bounds (Plus(x, 0)) before
     // the first evaluation: only the estimate_flag == 2 landmarks carry one (estimator.cpp:1293-1298)
     for (int l = tid; l < M; l += BA_THREADS) p.lam[l] = p.lm_const[l] ? p.lam0[l] : fmin(p.lam0[l], p.lm_ub[l]);
+    // coupling rows: zeroed once, every linearisation then rewrites the same entries (host frame, observer frames, ex-pose / td)
+    for (int i = tid; i < M * BA_WS; i += BA_THREADS) p.W[i] = 0.0;
+    if (tid == 0) {
+        int k = 0;
+        for (int f = 0; f < m.nimu; ++f) if (!(m.imu_j[f] & 1)) sh.imu_ord[k++] = f;
+        sh.imu_neven = k;
+        for (int f = 0; f < m.nimu; ++f) if (m.imu_j[f] & 1) sh.imu_ord[k++] = f;
+    }
     const int ws = (m.ex_active || m.td_active) ? BA_WS : 66;      // used width of the landmark coupling rows
     __syncthreads();
     // ---- once per solve: IMU information square roots, prior normal matrix ----
@@ -635,7 +774,7 @@ k_ba_solve(const BaMeta *metas, const BaProbDev *probs, BaOutDev *outs)
     const long long t_kernel0 = t_kernel00;
     long long tprof[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tmark = clock64();
 #define TPROF(k) do { long long t_ = clock64(); tprof[k] += t_ - tmark; tmark = t_; } while (0)
-    double x_cost = ba_evaluate(m, p, sh, sh.pose, sh.sb, sh.ex, sh.tdv[0], p.lam, true);
+    double x_cost = ba_evaluate(m, p, sh, sh.pose, sh.sb, sh.ex, sh.tdv[0], p.lam, 1);
     TPROF(0);
     const double initial_cost = x_cost;
     // Jacobi scaling (once): 1 / (1 + ||column||)
@@ -783,12 +922,28 @@ k_ba_solve(const BaMeta *metas, const BaProbDev *probs, BaOutDev *outs)
                     p.hinv_l[l] = hi_; p.shinv_l[l] = sqrt(hi_); p.y_l[l] = p.gl[l] / hl;
                 }
                 __syncthreads();
-                for (int l = warp; l < M; l += nwarp) {
-                    if (p.lm_const[l]) continue;
-                    if (!(p.hll[l] + mu * p.diag_l[l] * p.diag_l[l] > 0)) continue;
-                    const double *Wl = p.W + (size_t)l * BA_WS;
-                    const double gl_h = p.y_l[l], sl = p.jscale_l[l];
-                    for (int k = lane; k < ws; k += 32) { double w = wsc(sh, Wl, k, sl); if (w != 0.0) atomicAdd(&sh.y[wcol(k)], -w * gl_h); }
+                {
+                    // y_c -= sum_l w_l (g_l / h_l): per-warp partial rows in registers (lane <-> columns lane, lane + 32, lane + 64),
+                    // parked in the (idle) tile buffer and added by one thread per column in warp order
+                    double *part = reinterpret_cast<double *>(sh.imuJ);      // [nwarp][96]
+                    double a0 = 0, a1 = 0, a2 = 0;
+                    for (int l = warp; l < M; l += nwarp) {
+                        if (p.lm_const[l]) continue;
+                        if (!(p.hll[l] + mu * p.diag_l[l] * p.diag_l[l] > 0)) continue;
+                        const double *Wl = p.W + (size_t)l * BA_WS;
+                        const double gl_h = p.y_l[l], sl = p.jscale_l[l];
+                        a0 += wsc(sh, Wl, lane, sl) * gl_h;
+                        a1 += wsc(sh, Wl, lane + 32, sl) * gl_h;
+                        if (lane + 64 < ws) a2 += wsc(sh, Wl, lane + 64, sl) * gl_h;
+                    }
+                    part[warp * 96 + lane] = a0; part[warp * 96 + 32 + lane] = a1; part[warp * 96 + 64 + lane] = a2;
+                    __syncthreads();
+                    if (tid < ws) {
+                        double t = 0;
+#pragma unroll
+                        for (int w = 0; w < BA_THREADS / 32; ++w) t += part[w * 96 + tid];
+                        sh.y[wcol(tid)] -= t;
+                    }
                 }
                 __syncthreads();
                 // S = H + mu D^2 - W^T diag(1/h) W on the pose block (66 columns; + ex-pose and td when variable: ws = 73).
@@ -830,13 +985,22 @@ k_ba_solve(const BaMeta *metas, const BaProbDev *probs, BaOutDev *outs)
                         }
                         __syncthreads();
                     }
-                    if (actv) {
+                    // the second landmark subset hands its block to the first through the (now idle) tile: one writer per entry
+                    if (actv && grp == 1) {
+#pragma unroll
+                        for (int i = 0; i < 3; ++i)
+#pragma unroll
+                            for (int j = 0; j < 3; ++j) tile[blk * 9 + 3 * i + j] = acc[i][j];
+                    }
+                    __syncthreads();
+                    if (actv && grp == 0) {
 #pragma unroll
                         for (int i = 0; i < 3; ++i)
 #pragma unroll
                             for (int j = 0; j < 3; ++j) {
                                 const int r = 3 * bi + i, c = 3 * bj + j;
-                                if (r < ws && c <= r && acc[i][j] != 0.0) atomicAdd(&sh.H[pk(wcol(r), wcol(c))], -acc[i][j]);
+                                const double a = ngrp == 2 ? acc[i][j] + tile[blk * 9 + 3 * i + j] : acc[i][j];
+                                if (r < ws && c <= r) sh.H[pk(wcol(r), wcol(c))] -= a;
                             }
                     }
                 }
@@ -1006,7 +1170,7 @@ k_ba_solve(const BaMeta *metas, const BaProbDev *probs, BaOutDev *outs)
                 if (solved) break;
                 // failed: the in-place factorisation destroyed H => re-linearise and retry with a larger mu
                 mu *= mu_inc;
-                ba_evaluate(m, p, sh, sh.pose, sh.sb, sh.ex, sh.tdv[0], p.lam, true);
+                ba_evaluate(m, p, sh, sh.pose, sh.sb, sh.ex, sh.tdv[0], p.lam, 1);
                 ba_scale(m, p, sh);
             }
             TPROF(5);
@@ -1056,43 +1220,85 @@ k_ba_solve(const BaMeta *metas, const BaProbDev *probs, BaOutDev *outs)
             if (!(mcc > 0.0)) step_ok = false;
             else {
                 invalid = 0;
-                // candidate = x (+) (step * jscale)
-                for (int f = tid; f < BA_NF; f += BA_THREADS) {
-                    if (col_active_dev(m, 6 * f)) {
-                        double dl[6];
-                        for (int k = 0; k < 6; ++k) { int c = 6 * f + k; dl[k] = (c1 * sh.gd[c] + c2 * sh.gn[c]) / sh.diag[c] * sh.jscale[c]; }
-                        d_pose_plus(sh.pose + 7 * f, dl, sh.cpose + 7 * f);
-                    } else for (int k = 0; k < 7; ++k) sh.cpose[7 * f + k] = sh.pose[7 * f + k];
-                    for (int k = 0; k < 9; ++k) {
-                        int c = 66 + 9 * f + k;
-                        sh.csb[9 * f + k] = sh.sb[9 * f + k] + (col_active_dev(m, c) ? (c1 * sh.gd[c] + c2 * sh.gn[c]) / sh.diag[c] * sh.jscale[c] : 0.0);
+                // candidate = x (+) t (step * jscale); t = 1 except for the trial points of the line search below
+                auto dcol = [&](int c) { return (c1 * sh.gd[c] + c2 * sh.gn[c]) / sh.diag[c] * sh.jscale[c]; };       // delta, camera columns
+                auto dlm = [&](int l) { return (c1 * p.gd_l[l] + c2 * p.gn_l[l]) / p.diag_l[l] * p.jscale_l[l]; };    // delta, landmark l
+                auto make_candidate = [&](const double t) {
+                    for (int f = tid; f < BA_NF; f += BA_THREADS) {
+                        if (col_active_dev(m, 6 * f)) {
+                            double dl[6];
+                            for (int k = 0; k < 6; ++k) dl[k] = dcol(6 * f + k) * t;
+                            d_pose_plus(sh.pose + 7 * f, dl, sh.cpose + 7 * f);
+                        } else for (int k = 0; k < 7; ++k) sh.cpose[7 * f + k] = sh.pose[7 * f + k];
+                        for (int k = 0; k < 9; ++k) {
+                            const int c = 66 + 9 * f + k;
+                            sh.csb[9 * f + k] = sh.sb[9 * f + k] + (col_active_dev(m, c) ? dcol(c) * t : 0.0);
+                        }
                     }
-                }
-                if (tid == 64) {
-                    if (m.ex_active) {
-                        double dl[6];
-                        for (int k = 0; k < 6; ++k) { int c = BA_COL_EX + k; dl[k] = (c1 * sh.gd[c] + c2 * sh.gn[c]) / sh.diag[c] * sh.jscale[c]; }
-                        d_pose_plus(sh.ex, dl, sh.cex);
-                    } else for (int k = 0; k < 7; ++k) sh.cex[k] = sh.ex[k];
-                    const int c = BA_COL_TD;
-                    sh.tdv[1] = sh.tdv[0] + (m.td_active ? (c1 * sh.gd[c] + c2 * sh.gn[c]) / sh.diag[c] * sh.jscale[c] : 0.0);
-                }
-                for (int l = tid; l < M; l += BA_THREADS) {
-                    double v = p.lam[l];
-                    if (!p.lm_const[l]) {
-                        v += (c1 * p.gd_l[l] + c2 * p.gn_l[l]) / p.diag_l[l] * p.jscale_l[l];
-                        v = fmin(v, p.lm_ub[l]);           // ParameterBlock::Plus projects onto the bounds
+                    if (tid == 64) {
+                        if (m.ex_active) {
+                            double dl[6];
+                            for (int k = 0; k < 6; ++k) dl[k] = dcol(BA_COL_EX + k) * t;
+                            d_pose_plus(sh.ex, dl, sh.cex);
+                        } else for (int k = 0; k < 7; ++k) sh.cex[k] = sh.ex[k];
+                        sh.tdv[1] = sh.tdv[0] + (m.td_active ? dcol(BA_COL_TD) * t : 0.0);
                     }
-                    p.clam[l] = v;
-                }
-                __syncthreads();
+                    for (int l = tid; l < M; l += BA_THREADS) {
+                        double v = p.lam[l];
+                        if (!p.lm_const[l]) {
+                            v += dlm(l) * t;
+                            v = fmin(v, p.lm_ub[l]);           // ParameterBlock::Plus projects onto the bounds
+                        }
+                        p.clam[l] = v;
+                    }
+                    __syncthreads();
+                };
+                make_candidate(1.0);
                 TPROF(6);
-                const double cand_cost = ba_evaluate(m, p, sh, sh.cpose, sh.csb, sh.cex, sh.tdv[1], p.clam, false);
+                double cand_cost = ba_evaluate(m, p, sh, sh.cpose, sh.csb, sh.cex, sh.tdv[1], p.clam, 0);
                 TPROF(7);
-                // Ceres' projected Armijo line search of bound-constrained problems (TrustRegionMinimizer::DoLineSearch) leaves
-                // the step alone when f(x [+] delta) <= f(x) + 1e-4 g.delta -- the case implemented here; steps that fail the
-                // test (where Ceres would shorten the step) are counted for the caller (VrfBaResult::armijo_failures)
-                if (constrained && cand_cost > x_cost + 1e-4 * sTg) ++armijo_failures;
+                // ---- Ceres' projected Armijo line search of bound-constrained problems (TrustRegionMinimizer::DoLineSearch;
+                // statement and defaults: ba_linesearch.cuh, oracle/ba_ref.c).  phi(t) = f(x [+] t delta), phi'(t) = delta . gradient
+                // at the trial point.  The full step passing f(x [+] delta) <= f(x) + 1e-4 g.delta is the common case and costs
+                // nothing; otherwise the step is contracted by polynomial interpolation until the test holds.  The trial
+                // evaluations overwrite the gradient of the linearisation at x (sh.g, p.gl): whatever happens to the step
+                // afterwards either re-linearises (accepted / invalid) or only needs the stored dogleg vectors (rejected). ----
+                if (constrained && (!isfinite(cand_cost) || cand_cost > x_cost + 1e-4 * sTg)) {
+                    ++armijo_failures;
+                    double dmax = 0;
+                    for (int c = tid; c < BA_NC; c += BA_THREADS) dmax = fmax(dmax, fabs(dcol(c)));
+                    for (int l = tid; l < M; l += BA_THREADS) if (!p.lm_const[l]) dmax = fmax(dmax, fabs(dlm(l)));
+                    for (int o = 16; o > 0; o >>= 1) dmax = fmax(dmax, __shfl_xor_sync(0xffffffffu, dmax, o));
+                    __syncthreads();
+                    if (lane == 0) sh.red[warp] = dmax;
+                    __syncthreads();
+                    dmax = 0;
+                    for (int i = 0; i < nwarp; ++i) dmax = fmax(dmax, sh.red[i]);
+                    __syncthreads();
+                    const LsSample lower = {0.0, x_cost, sTg, true, true};
+                    LsSample prev = {0.0, 0.0, 0.0, false, false}, cur = {1.0, cand_cost, 0.0, false, true};
+                    bool ok = false;
+                    for (int it = 0;; ++it) {
+                        if (it > 0) {
+                            if (it >= 20) break;                                   // max_num_line_search_step_size_iterations
+                            const double t = ls_interpolating_step(lower, prev, cur, 1e-3 * cur.x, 0.6 * cur.x);
+                            if (t * dmax < 1e-9) break;                            // min_line_search_step_size
+                            prev = cur;
+                            cur.x = t;
+                            make_candidate(t);
+                        }
+                        cur.value = ba_evaluate(m, p, sh, sh.cpose, sh.csb, sh.cex, sh.tdv[1], p.clam, 2);
+                        double dg = 0;
+                        for (int c = tid; c < BA_NC; c += BA_THREADS) dg += sh.g[c] * dcol(c);
+                        for (int l = tid; l < M; l += BA_THREADS) if (!p.lm_const[l]) dg += p.gl[l] * dlm(l);
+                        cur.gradient = block_sum(dg, sh.red);
+                        cur.value_ok = isfinite(cur.value) && isfinite(cur.gradient);
+                        cur.grad_ok = cur.value_ok;
+                        if (cur.value_ok && cur.value <= x_cost + 1e-4 * sTg * cur.x) { ok = it > 0; break; }
+                    }
+                    if (ok) cand_cost = cur.value;         // the candidate arrays already hold x [+] t delta
+                    else make_candidate(1.0);              // failed search: the step stays as it was
+                }
                 // step norm over the non-constant blocks (ambient space)
                 double sn = 0;
                 for (int i = tid; i < BA_NF * 7; i += BA_THREADS) if (col_active_dev(m, 6 * (i / 7))) { double dd = sh.pose[i] - sh.cpose[i]; sn += dd * dd; }
@@ -1118,7 +1324,7 @@ k_ba_solve(const BaMeta *metas, const BaProbDev *probs, BaOutDev *outs)
                     x_cost = cand_cost;
                     x_norm = sqrt(xnorm2(sh.pose, sh.sb, p.lam));
                     TPROF(6);
-                    ba_evaluate(m, p, sh, sh.pose, sh.sb, sh.ex, sh.tdv[0], p.lam, true);
+                    ba_evaluate(m, p, sh, sh.pose, sh.sb, sh.ex, sh.tdv[0], p.lam, 1);
                     TPROF(0);
                     need_scale = 1;
                     ++successful;
@@ -1138,7 +1344,7 @@ k_ba_solve(const BaMeta *metas, const BaProbDev *probs, BaOutDev *outs)
         reuse = 0;
         if (status == VRF_SOFT_NOT_SPD && mu >= max_mu) { termination = 5; break; }
         // H was consumed by the failed factorisation attempts: rebuild it
-        ba_evaluate(m, p, sh, sh.pose, sh.sb, sh.ex, sh.tdv[0], p.lam, true);
+        ba_evaluate(m, p, sh, sh.pose, sh.sb, sh.ex, sh.tdv[0], p.lam, 1);
         need_scale = 1;
     }
     __syncthreads();

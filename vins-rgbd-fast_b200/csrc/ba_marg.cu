@@ -34,6 +34,7 @@ struct MargShared {
     double dx[VRF_PRIOR_MAX_DIM], pr[VRF_PRIOR_MAX_DIM];
     double R[BA_NF * 9], ric[9];
     int flag;
+    int pair_off[BA_NF], pair_cnt[BA_NF];       // factor lists of the pairs (host 0, observer j), phase 2c
 };
 
 // parallel-order cyclic Jacobi: A (n x n, row-major, global) -> eigenvalues on the diagonal, V eigenvectors (columns)
@@ -482,9 +483,9 @@ k_ba_marg(const BaMeta *metas, const BaProbDev *probs, BaOutDev *outs, const BaM
             int a = e / 30, c = e - a * 30;
             double h = 0;
             for (int k = 0; k < 15; ++k) h += sh.J[k * 30 + a] * sh.J[k * 30 + c];
-            atomicAdd(&A[(size_t)acol(a) * pos + acol(c)], h);
+            A[(size_t)acol(a) * pos + acol(c)] += h;            // distinct (a, c) -> distinct entries, this warp is the only writer
         }
-        if (lane < 30) { double gsum = 0; for (int k = 0; k < 15; ++k) gsum += sh.J[k * 30 + lane] * sh.r[k]; atomicAdd(&bv[acol(lane)], gsum); }
+        if (lane < 30) { double gsum = 0; for (int k = 0; k < 15; ++k) gsum += sh.J[k * 30 + lane] * sh.r[k]; bv[acol(lane)] += gsum; }
     }
     __syncthreads();
     // ---- 2c. projection factors hosted at frame 0 (all four parameter blocks, Cauchy corrector) ----
@@ -499,43 +500,79 @@ k_ba_marg(const BaMeta *metas, const BaProbDev *probs, BaOutDev *outs, const BaM
     for (int i = 0; i < sh.first_kept; ++i) if (sh.present[i]) lm0c += sh.lsize[i];
     const int nl0c = mm - lm0c;
     if (flag == VRF_MARGIN_OLD && nl0c > 0) {
+        // Bit-reproducible accumulation without floating-point atomics, frame-pair major like the linearisation of k_ba_solve:
+        // warp j - 1 owns the pair (host 0, observer j) and walks its factors (dropped landmarks seen in frame j, in landmark
+        // order) in batches of 32, one lane per factor.  Per batch the sums over the lanes are formed with the reduce-scatter
+        // butterfly and kept in registers over the batches:
+        //   (b) the observer's own rows (gradient 6, diagonal 6 x 6 triangle 21, coupling with pose 0 / ex-pose / td 6 x 13):
+        //       this pair is their only contributor -> stored straight into the shared system;
+        //   (a) the 13 columns all factors share (pose 0, ex-pose, td: triangle 91 + gradient 13): per-pair partials in the
+        //       L2 scratch, added over the pairs in order afterwards;
+        //   landmark sums (coupling with the 13 shared columns, h, g): one slot per factor, added per landmark afterwards.
         for (int e = tid; e < MG_LP + MG_L; e += BA_THREADS) big0[e] = 0.0;
         for (int e = tid; e < nl0c * MG_L; e += BA_THREADS) Wm[e] = 0.0;
-        __syncthreads();
-        auto pk72 = [](int a_, int b_) { return a_ >= b_ ? a_ * (a_ + 1) / 2 + b_ : b_ * (b_ + 1) / 2 + a_; };
-        for (int l = warp; l < M; l += nwarp) {
-            const int cl = mg.lmcol[l];
-            if (cl < 0) continue;
-            const int li = cl - lm0c;       // ordinal among the dropped landmarks
-            const int o0 = p.obs_ptr[l], nf = p.obs_ptr[l + 1] - o0 - 1;
-            const bool act = lane < nf;
-            const int j = 1 + lane;
-            double r[2] = {0, 0}, Ji[12], Jj[12], Jl[2] = {0, 0}, Je[12], Jt[2] = {0, 0};
-#pragma unroll
-            for (int k = 0; k < 12; ++k) { Ji[k] = 0; Jj[k] = 0; Je[k] = 0; }
-            if (act) {
-                double xi, yi, xj, yj;
-                obs_at(m, p, o0, out.mtd, xi, yi);
-                obs_at(m, p, o0 + j, out.mtd, xj, yj);
-                proj_eval(pose, sh.R, pose + 7 * j, sh.R + 9 * j, ex, sh.ric, lam[l], xi, yi, xj, yj, true, false, r, Ji, Jj, Jl, Je,
-                          m.td_factor ? p.obs_vel + 2 * o0 : nullptr, m.td_factor ? p.obs_vel + 2 * (o0 + j) : nullptr,
-                          m.td_factor ? Jt : nullptr);
+        int *flist = p.fac;                          // k_ba_solve's factor list is dead by now: [pair offsets] lists of landmarks
+        for (int pass = 0; pass < 2; ++pass) {
+            if (warp < BA_NF - 1) {
+                const int j = warp + 1;
+                int off = pass ? sh.pair_off[warp] : 0;
+                for (int b0 = 0; b0 < M; b0 += 32) {
+                    const int l = b0 + lane;
+                    const bool a_ = l < M && mg.lmcol[l] >= 0 && (p.obs_ptr[l + 1] - p.obs_ptr[l] - 1) >= j;
+                    const unsigned mask = __ballot_sync(0xffffffffu, a_);
+                    if (pass && a_) flist[off + __popc(mask & ((1u << lane) - 1u))] = l;
+                    off += __popc(mask);
+                }
+                if (!pass && lane == 0) sh.pair_cnt[warp] = off;
             }
-            const double hsum = warp_sum_d(Jl[0] * Jl[0] + Jl[1] * Jl[1]);
-            const double gsum = warp_sum_d(Jl[0] * r[0] + Jl[1] * r[1]);
-            if (lane == 0) { hm[li] = hsum; hm[nl0c + li] = gsum; }
-            double *wr = Wm + (size_t)li * MG_L;
-            // (a) the 13 columns every factor of this landmark shares -- pose0 (Ji), ex-pose (Je), td (Jt): their 91
-            // normal-matrix entries, 13 gradient entries and 13 landmark-coupling entries are summed over the lanes
-            // with the reduce-scatter butterfly; one lane per value then adds the warp total (no intra-warp contention).
-            {
+            __syncthreads();
+            if (!pass) {
+                if (tid == 0) {
+                    int acc = 0;
+                    for (int q = 0; q < BA_NF - 1; ++q) { sh.pair_off[q] = acc; acc += sh.pair_cnt[q]; }
+                    sh.pair_off[BA_NF - 1] = acc;
+                }
+                __syncthreads();
+            }
+        }
+        __threadfence_block();
+        auto pk72 = [](int a_, int b_) { return a_ >= b_ ? a_ * (a_ + 1) / 2 + b_ : b_ * (b_ + 1) / 2 + a_; };
+        auto scol = [](int a_) { return a_ < 6 ? a_ : a_ < 12 ? 66 + (a_ - 6) : 72; };
+        if (warp < BA_NF - 1) {
+            const int j = warp + 1;
+            double acca[7] = {0, 0, 0, 0, 0, 0, 0}, accb[7] = {0, 0, 0, 0, 0, 0, 0};
+            const int f_end = sh.pair_off[warp + 1];
+            for (int fb = sh.pair_off[warp]; fb < f_end; fb += 32) {
+                const bool act = fb + lane < f_end;
+                const int l = act ? flist[fb + lane] : 0;
+                const int o0 = act ? p.obs_ptr[l] : 0;
+                double r[2] = {0, 0}, Ji[12], Jj[12], Jl[2] = {0, 0}, Je[12], Jt[2] = {0, 0};
+#pragma unroll
+                for (int k = 0; k < 12; ++k) { Ji[k] = 0; Jj[k] = 0; Je[k] = 0; }
+                if (act) {
+                    double xi, yi, xj, yj;
+                    obs_at(m, p, o0, out.mtd, xi, yi);
+                    obs_at(m, p, o0 + j, out.mtd, xj, yj);
+                    proj_eval(pose, sh.R, pose + 7 * j, sh.R + 9 * j, ex, sh.ric, lam[l], xi, yi, xj, yj, true, false, r, Ji, Jj, Jl, Je,
+                              m.td_factor ? p.obs_vel + 2 * o0 : nullptr, m.td_factor ? p.obs_vel + 2 * (o0 + j) : nullptr,
+                              m.td_factor ? Jt : nullptr);
+                }
                 double s0[13], s1[13];
 #pragma unroll
                 for (int c = 0; c < 6; ++c) { s0[c] = Ji[c]; s1[c] = Ji[6 + c]; s0[6 + c] = Je[c]; s1[6 + c] = Je[6 + c]; }
                 s0[12] = Jt[0]; s1[12] = Jt[1];
-                auto scol = [](int a_) { return a_ < 6 ? a_ : a_ < 12 ? 66 + (a_ - 6) : 72; };
+                if (act) {
+                    double *fp = p.fpart + (size_t)(o0 + j) * BA_FP_STRIDE;
 #pragma unroll
-                for (int rd = 0; rd < 8; ++rd) {
+                    for (int c = 0; c < 13; ++c) fp[c] = s0[c] * Jl[0] + s1[c] * Jl[1];
+                    fp[13] = Jl[0] * Jl[0] + Jl[1] * Jl[1];
+                    fp[14] = Jl[0] * r[0] + Jl[1] * r[1];
+                    double *wr = Wm + (size_t)(mg.lmcol[l] - lm0c) * MG_L;
+#pragma unroll
+                    for (int a_ = 0; a_ < 6; ++a_) wr[6 * j + a_] = Jj[a_] * Jl[0] + Jj[6 + a_] * Jl[1];
+                }
+#pragma unroll
+                for (int rd = 0; rd < 7; ++rd) {
                     double v[16];
 #pragma unroll
                     for (int t = 0; t < 16; ++t) {
@@ -546,38 +583,68 @@ k_ba_marg(const BaMeta *metas, const BaProbDev *probs, BaOutDev *outs, const BaM
                             const int b_ = e - a_ * (a_ + 1) / 2;
                             v[t] = s0[a_] * s0[b_] + s1[a_] * s1[b_];
                         } else if (e < 104) v[t] = s0[e - 91] * r[0] + s1[e - 91] * r[1];
-                        else if (e < 117) v[t] = s0[e - 104] * Jl[0] + s1[e - 104] * Jl[1];
                         else v[t] = 0.0;
                     }
-                    const double tot = reduce_scatter16(v, lane);
-                    const int e = rd * 16 + (lane >> 1);
-                    if (!(lane & 1) && e < 117 && tot != 0.0) {
-                        if (e < 91) {
+                    acca[rd] += reduce_scatter16(v, lane);
+                }
+#pragma unroll
+                for (int rd = 0; rd < 7; ++rd) {
+                    double v[16];
+#pragma unroll
+                    for (int t = 0; t < 16; ++t) {
+                        const int e = rd * 16 + t;
+                        if (e < 6) v[t] = Jj[e] * r[0] + Jj[6 + e] * r[1];
+                        else if (e < 27) {
                             int a_ = 0;
-                            while ((a_ + 1) * (a_ + 2) / 2 <= e) ++a_;
-                            atomicAdd(&H72[pk72(scol(a_), scol(e - a_ * (a_ + 1) / 2))], tot);
-                        } else if (e < 104) atomicAdd(&g72[scol(e - 91)], tot);
-                        else wr[scol(e - 104)] = tot;                 // this warp owns the landmark's row
+                            while ((a_ + 1) * (a_ + 2) / 2 <= e - 6) ++a_;
+                            const int b_ = e - 6 - a_ * (a_ + 1) / 2;
+                            v[t] = Jj[a_] * Jj[b_] + Jj[6 + a_] * Jj[6 + b_];
+                        } else if (e < 105) {
+                            const int a_ = (e - 27) / 13, c_ = (e - 27) % 13;
+                            v[t] = Jj[a_] * s0[c_] + Jj[6 + a_] * s1[c_];
+                        } else v[t] = 0.0;
                     }
+                    accb[rd] += reduce_scatter16(v, lane);
                 }
             }
-            if (!act) continue;
-            // (b) the observer's own pose block (columns 6j..6j+5): lane-private within the warp
+            if (!(lane & 1)) {
+                double *pp = p.pair_part + (size_t)warp * BA_PP_STRIDE + (lane >> 1);
 #pragma unroll
-            for (int a_ = 0; a_ < 6; ++a_) {
-                const double j0a = Jj[a_], j1a = Jj[6 + a_];
-                const int ca = 6 * j + a_;
-                atomicAdd(&g72[ca], j0a * r[0] + j1a * r[1]);
-                wr[ca] = j0a * Jl[0] + j1a * Jl[1];
-#pragma unroll
-                for (int c = 0; c <= a_; ++c) atomicAdd(&H72[pk72(ca, 6 * j + c)], j0a * Jj[c] + j1a * Jj[6 + c]);
-#pragma unroll
-                for (int c = 0; c < 6; ++c) {
-                    atomicAdd(&H72[pk72(ca, c)], j0a * Ji[c] + j1a * Ji[6 + c]);
-                    atomicAdd(&H72[pk72(66 + c, ca)], j0a * Je[c] + j1a * Je[6 + c]);
+                for (int rd = 0; rd < 7; ++rd) {
+                    pp[16 * rd] = acca[rd];
+                    const int e = rd * 16 + (lane >> 1);
+                    if (e < 6) g72[6 * j + e] = accb[rd];
+                    else if (e < 27) {
+                        int a_ = 0;
+                        while ((a_ + 1) * (a_ + 2) / 2 <= e - 6) ++a_;
+                        H72[pk72(6 * j + a_, 6 * j + (e - 6 - a_ * (a_ + 1) / 2))] = accb[rd];
+                    } else if (e < 105) H72[pk72(6 * j + (e - 27) / 13, scol((e - 27) % 13))] = accb[rd];
                 }
-                if (m.td_factor) atomicAdd(&H72[pk72(72, ca)], j0a * Jt[0] + j1a * Jt[1]);
             }
+        }
+        __syncthreads();
+        // shared 13 x 13 block and gradient: sum of the per-pair partials in pair order; landmark rows: sum over the landmark's
+        // factors in observation order
+        for (int it = tid; it < 104 + M * 15; it += BA_THREADS) {
+            if (it < 104) {
+                double t = 0;
+                for (int q = 0; q < BA_NF - 1; ++q) t += p.pair_part[(size_t)q * BA_PP_STRIDE + it];
+                if (it < 91) {
+                    int a_ = 0;
+                    while ((a_ + 1) * (a_ + 2) / 2 <= it) ++a_;
+                    H72[pk72(scol(a_), scol(it - a_ * (a_ + 1) / 2))] = t;
+                } else g72[scol(it - 91)] = t;
+                continue;
+            }
+            const int l = (it - 104) / 15, a_ = (it - 104) - 15 * l;
+            const int cl = mg.lmcol[l];
+            if (cl < 0) continue;
+            const int li = cl - lm0c;
+            const int o0 = p.obs_ptr[l], o1 = p.obs_ptr[l + 1];
+            double t = 0;
+            for (int o = o0 + 1; o < o1 && o - o0 <= BA_NF - 1; ++o) t += p.fpart[(size_t)o * BA_FP_STRIDE + a_];
+            if (a_ < 13) Wm[(size_t)li * MG_L + scol(a_)] = t;
+            else hm[(a_ == 13 ? 0 : nl0c) + li] = t;
         }
         __syncthreads();
         __threadfence();

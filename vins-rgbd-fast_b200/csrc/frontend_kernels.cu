@@ -305,26 +305,47 @@ k_pyr(FrontCfg c, const SeqCall *calls, int ncalls, FrontDev d, const uint8_t *f
     const int y1_0 = blockIdx.x * R1;
     const int r0 = 2 * y1_0 - 2;                  // source row of shared row 0
 
-    // ---- (1) load / convert / store level l, park in shared memory ----
-    for (int it = tid; it < NR * gpr; it += 256) {
-        const int r = it / gpr, g = it - r * gpr;
+    // ---- (1) load / convert / store level l, park in shared memory; two items per thread in flight ----
+    constexpr int NLD = SRC == SRC_RGB8 ? 3 : 1;
+    // items (row r, 16-px group g) are walked without divisions: 256 items further = dq rows and dm groups further
+    const int dq1 = 256 / gpr, dm1 = 256 - dq1 * gpr;
+    auto item_row = [&](int it, int r) -> int {               // source row of item `it` (>= -2), or -1000 when nothing needs it
         const int sy = r0 + r;
-        if (sy > sh + 1) continue;                // rows only destination rows >= dh would use
+        return (it < NR * gpr && sy <= sh + 1) ? sy : -1000;  // rows beyond sh + 1: only destination rows >= dh would use them
+    };
+    auto item_load = [&](int sy, int g, uint4 (&v)[NLD]) {
         const int syr = reflect101(sy, sh);
-        uint4 out;
         if (SRC == SRC_RGB8) {
             const uint4 *p = reinterpret_cast<const uint4 *>(src + (size_t)syr * sw * 3) + g * 3;
-            const uint4 a = __ldg(p), b = __ldg(p + 1), cc = __ldg(p + 2);
+            v[0] = __ldg(p); v[NLD > 1 ? 1 : 0] = __ldg(p + 1); v[NLD > 2 ? 2 : 0] = __ldg(p + 2);
+        } else if (SRC == SRC_GRAY8) v[0] = __ldg(reinterpret_cast<const uint4 *>(src + (size_t)syr * sw) + g);
+        else v[0] = *(reinterpret_cast<const uint4 *>(src + (size_t)syr * sp) + g);
+    };
+    auto item_store = [&](int sy, int r, int g, const uint4 (&v)[NLD]) {
+        uint4 out = v[0];
+        if (SRC == SRC_RGB8) {
+            const uint4 a = v[0], b = v[NLD > 1 ? 1 : 0], cc = v[NLD > 2 ? 2 : 0];
             out = make_uint4(rgb4_to_gray(a.x, a.y, a.z), rgb4_to_gray(a.w, b.x, b.y), rgb4_to_gray(b.z, b.w, cc.x),
                              rgb4_to_gray(cc.y, cc.z, cc.w));
-        } else if (SRC == SRC_GRAY8) {
-            out = __ldg(reinterpret_cast<const uint4 *>(src + (size_t)syr * sw) + g);
-        } else {
-            out = *(reinterpret_cast<const uint4 *>(src + (size_t)syr * sp) + g);
         }
         *reinterpret_cast<uint4 *>(gs + (size_t)r * gpitch + 16 + 16 * g) = out;
         if (SRC != SRC_PYR && r >= 2 && r < 2 + 2 * R1 && sy < sh)
             *reinterpret_cast<uint4 *>(dst0 + (size_t)sy * sp + 16 * g) = out;
+    };
+    {
+        int rA = tid / gpr, gA = tid - rA * gpr;
+        for (int it = tid; it < NR * gpr; it += 512) {
+            int rB = rA + dq1, gB = gA + dm1;
+            if (gB >= gpr) { gB -= gpr; ++rB; }
+            const int syA = item_row(it, rA), syB = item_row(it + 256, rB);
+            uint4 vA[NLD], vB[NLD];
+            if (syA >= -2) item_load(syA, gA, vA);
+            if (syB >= -2) item_load(syB, gB, vB);
+            if (syA >= -2) item_store(syA, rA, gA, vA);
+            if (syB >= -2) item_store(syB, rB, gB, vB);
+            rA = rB + dq1; gA = gB + dm1;
+            if (gA >= gpr) { gA -= gpr; ++rA; }
+        }
     }
     __syncthreads();
     for (int r = tid; r < NR; r += 256) {         // REFLECT_101 columns -2, -1, sw, sw + 1
@@ -335,8 +356,9 @@ k_pyr(FrontCfg c, const SeqCall *calls, int ncalls, FrontDev d, const uint8_t *f
     __syncthreads();
 
     // ---- (2) horizontal pass: h[x] = p[2x-2] + 4 p[2x-1] + 6 p[2x] + 4 p[2x+1] + p[2x+2] + 8, packed (h[2m], h[2m+1]) ----
+    const int dq2 = 256 / hpr, dm2 = 256 - dq2 * hpr;
+    int r = tid / hpr, q = tid - r * hpr;
     for (int it = tid; it < NR * hpr; it += 256) {
-        const int r = it / hpr, q = it - r * hpr;
         const unsigned *rw = reinterpret_cast<const unsigned *>(gs + (size_t)r * gpitch + 16) + 4 * q;
         const uint4 w = *reinterpret_cast<const uint4 *>(rw);
         const unsigned wv[6] = {rw[-1], w.x, w.y, w.z, w.w, rw[4]};
@@ -349,12 +371,16 @@ k_pyr(FrontCfg c, const SeqCall *calls, int ncalls, FrontDev d, const uint8_t *f
             o[m] = __byte_perm(lo, hi, 0x5410);
         }
         *reinterpret_cast<uint4 *>(hs + (size_t)r * hpitch + 16 * q) = make_uint4(o[0], o[1], o[2], o[3]);
+        r += dq2; q += dm2;
+        if (q >= hpr) { q -= hpr; ++r; }
     }
     __syncthreads();
 
     // ---- (3) vertical pass ----
-    for (int it = tid; it < R1 * hpr; it += 256) {
-        const int y = it / hpr, q = it - y * hpr;
+    int y = tid / hpr;
+    q = tid - y * hpr;
+    for (int it = tid; it < R1 * hpr; it += 256, y += dq2, q += dm2) {
+        if (q >= hpr) { q -= hpr; ++y; }
         const int dy = y1_0 + y, dx0 = 8 * q;
         if (dy >= dh) break;
         const uint8_t *hp = hs + (size_t)(2 * y) * hpitch + 16 * q;
