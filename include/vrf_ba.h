@@ -130,8 +130,8 @@ typedef struct VrfBaResult {
     /* new prior (valid iff has_new_prior; produced when frame_count == WINDOW_SIZE) */
     int32_t has_new_prior;
     int32_t armijo_failures;    /* diagnostic: trust-region steps of a bound-constrained problem (estimate_flag == 2 landmarks,
-                                   estimator.cpp:1293-1298) that fail Ceres' Armijo test at step size 1, i.e. where Ceres'
-                                   projected line search -- not restated by this library -- would have shortened the step */
+                                   estimator.cpp:1293-1298) whose full step failed Ceres' sufficient-decrease test, i.e. for which
+                                   the projected Armijo line search (TrustRegionMinimizer::DoLineSearch) had to contract the step */
     VrfPrior *new_prior;        /* caller-allocated, may be NULL to skip the copy-out */
 } VrfBaResult;
 

@@ -34,6 +34,7 @@
 #include <float.h>
 #include <stdio.h>
 #include <math.h>
+#include <stdbool.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -906,149 +907,162 @@ static void state_plus(const VrfBaProblem *pb, const Lin *L, const State *x, con
 /* ------------------------------------------------------------------ */
 typedef struct { double x, value, gradient; int value_ok, grad_ok; } LsSample;
 
-static double poly_eval(const double *c, int n, double x)      /* n coefficients, highest power first (Horner) */
+static double lsq_poly_eval(const double *c, int n, double x)      /* n coefficients, highest power first (Horner) */
 {
     double v = 0;
     for (int i = 0; i < n; i++) v = v * x + c[i];
     return v;
 }
 
-/* FindInterpolatingPolynomial: the polynomial of degree (#constraints - 1) through the samples' values and gradients;
- * Ceres solves the Vandermonde-type system with Eigen's fullPivLu -- Gaussian elimination with full pivoting here. */
-static int poly_interpolate(const LsSample *smp, int ns, double *coef)
+/* value and derivative of a polynomial (n coefficients, highest power first) */
+static void lsq_poly_eval2(const double *c, int n, double x, double *f, double *df)
 {
-    int nc = 0;
-    for (int i = 0; i < ns; i++) nc += (smp[i].value_ok ? 1 : 0) + (smp[i].grad_ok ? 1 : 0);
-    const int degree = nc - 1;
-    double A[6][7];
-    int row = 0;
-    for (int i = 0; i < ns; i++) {
-        if (smp[i].value_ok) {
-            for (int j = 0; j <= degree; j++) A[row][j] = pow(smp[i].x, degree - j);
-            A[row][nc] = smp[i].value; row++;
-        }
-        if (smp[i].grad_ok) {
-            for (int j = 0; j < degree; j++) A[row][j] = (degree - j) * pow(smp[i].x, degree - j - 1);
-            A[row][degree] = 0.0;
-            A[row][nc] = smp[i].gradient; row++;
-        }
-    }
-    int perm[6];
-    for (int j = 0; j < nc; j++) perm[j] = j;
-    for (int k = 0; k < nc; k++) {
-        int pr = k, pc = k; double best = -1;
-        for (int r = k; r < nc; r++) for (int c = k; c < nc; c++) if (fabs(A[r][c]) > best) { best = fabs(A[r][c]); pr = r; pc = c; }
-        if (best <= 0) { for (int r = k; r < nc; r++) A[r][nc] = 0; break; }     /* rank deficient: remaining unknowns 0 */
-        if (pr != k) for (int c = 0; c <= nc; c++) { double t = A[k][c]; A[k][c] = A[pr][c]; A[pr][c] = t; }
-        if (pc != k) { for (int r = 0; r < nc; r++) { double t = A[r][k]; A[r][k] = A[r][pc]; A[r][pc] = t; } int t = perm[k]; perm[k] = perm[pc]; perm[pc] = t; }
-        for (int r = k + 1; r < nc; r++) {
-            double f = A[r][k] / A[k][k];
-            for (int c = k; c <= nc; c++) A[r][c] -= f * A[k][c];
-        }
-    }
-    double y[6];
-    for (int k = nc - 1; k >= 0; k--) {
-        double v = A[k][nc];
-        for (int c = k + 1; c < nc; c++) v -= A[k][c] * y[c];
-        y[k] = A[k][k] != 0.0 ? v / A[k][k] : 0.0;
-    }
-    for (int k = 0; k < nc; k++) coef[perm[k]] = y[k];
-    return nc;
+    double v = c[0], d = 0.0;
+    for (int i = 1; i < n; ++i) { d = d * x + v; v = v * x + c[i]; }
+    *f = v; *df = d;
 }
 
-/* Real parts of all roots of a polynomial (n coefficients, highest first).  Ceres' FindPolynomialRoots: leading zeros
- * removed; degree 1 and 2 in closed form; higher degrees through the eigenvalues of the balanced companion matrix -- here
- * the same roots from the Aberth-Ehrlich iteration (converged to machine precision).  MinimizePolynomial tests the real
- * part of EVERY root, complex ones included ("a bit of an overkill ... simpler to just check these values"). */
-static int poly_root_real_parts(const double *c_in, int n, double *re)
+/* root of c inside the bracket [u, v] (sign change, fu = c(u)): Newton steps, bisection whenever Newton leaves the bracket or */
+/* stops halving the step (Numerical Recipes' rtsafe), down to a few ulp */
+static double lsq_root_bracketed(const double *c, int n, double u, double v, double fu)
 {
-    while (n > 0 && c_in[0] == 0.0) { c_in++; n--; }
+    double xl = fu < 0 ? u : v, xh = fu < 0 ? v : u;          /* c(xl) < 0 < c(xh) */
+    double x = 0.5 * (u + v), dxold = fabs(v - u), dx = dxold, f, df;
+    lsq_poly_eval2(c, n, x, &f, &df);
+    for (int it = 0; it < 200; ++it) {
+        if (((x - xh) * df - f) * ((x - xl) * df - f) > 0.0 || fabs(2.0 * f) > fabs(dxold * df)) {
+            dxold = dx; dx = 0.5 * (xh - xl);
+            const double xn = xl + dx;
+            if (xn == xl) return xn;
+            x = xn;
+        } else {
+            dxold = dx; dx = f / df;
+            const double xn = x - dx;
+            if (xn == x) return x;
+            x = xn;
+        }
+        if (fabs(dx) <= 4.4e-16 * fabs(x)) return x;
+        lsq_poly_eval2(c, n, x, &f, &df);
+        if (f == 0.0) return x;
+        if (f < 0) xl = x; else xh = x;
+    }
+    return x;
+}
+
+/* real roots of c (degree <= 2 after stripping leading zeros) inside [a, b], ascending */
+static int lsq_roots_low(const double *c, int n, double a, double b, double *roots)
+{
+    while (n > 0 && c[0] == 0.0) { ++c; --n; }
     const int deg = n - 1;
+    int nr = 0;
     if (deg < 1) return 0;
-    if (deg == 1) { re[0] = -c_in[1] / c_in[0]; return 1; }
-    if (deg == 2) {
-        const double a = c_in[0], b = c_in[1], c = c_in[2];
-        const double D = b * b - 4 * a * c, sD = sqrt(fabs(D));
-        if (D >= 0) {
-            if (b >= 0) { re[0] = (-b - sD) / (2.0 * a); re[1] = (2.0 * c) / (-b - sD); }
-            else { re[0] = (2.0 * c) / (-b + sD); re[1] = (-b + sD) / (2.0 * a); }
-        } else { re[0] = -b / (2.0 * a); re[1] = -b / (2.0 * a); }
-        return 2;
-    }
-    /* monic coefficients */
-    double a[8];
-    for (int i = 0; i <= deg; i++) a[i] = c_in[i] / c_in[0];
-    double rad = 0;
-    for (int i = 1; i <= deg; i++) rad = fmax(rad, fabs(a[i]));
-    rad = 1.0 + rad;                                             /* Cauchy bound */
-    double zr[8], zi[8];
-    for (int k = 0; k < deg; k++) { double ang = 2.0 * 3.14159265358979323846 * k / deg + 0.4; zr[k] = 0.5 * rad * cos(ang); zi[k] = 0.5 * rad * sin(ang); }
-    for (int it = 0; it < 500; it++) {
-        double change = 0;
-        for (int k = 0; k < deg; k++) {
-            /* p(z), p'(z) by Horner in complex arithmetic */
-            double pr = 1.0, pi = 0.0, dr = 0.0, di = 0.0;
-            for (int i = 1; i <= deg; i++) {
-                double ndr = dr * zr[k] - di * zi[k] + pr, ndi = dr * zi[k] + di * zr[k] + pi;
-                dr = ndr; di = ndi;
-                double npr = pr * zr[k] - pi * zi[k] + a[i], npi = pr * zi[k] + pi * zr[k];
-                pr = npr; pi = npi;
-            }
-            const double dd = dr * dr + di * di;
-            if (dd == 0.0) continue;
-            double wr = (pr * dr + pi * di) / dd, wi = (pi * dr - pr * di) / dd;        /* p / p' */
-            double sr = 0, si = 0;
-            for (int j = 0; j < deg; j++) {
-                if (j == k) continue;
-                const double er = zr[k] - zr[j], ei = zi[k] - zi[j], ee = er * er + ei * ei;
-                if (ee == 0.0) continue;
-                sr += er / ee; si -= ei / ee;
-            }
-            /* w / (1 - w s) */
-            const double qr = 1.0 - (wr * sr - wi * si), qi = -(wr * si + wi * sr), qq = qr * qr + qi * qi;
-            if (qq == 0.0) continue;
-            const double ur = (wr * qr + wi * qi) / qq, ui = (wi * qr - wr * qi) / qq;
-            zr[k] -= ur; zi[k] -= ui;
-            change = fmax(change, fabs(ur) + fabs(ui));
-        }
-        if (change <= 1e-15 * rad) break;
-    }
-    for (int k = 0; k < deg; k++) re[k] = zr[k];
-    return deg;
+    if (deg == 1) { const double r = -c[1] / c[0]; if (r >= a && r <= b) roots[nr++] = r; return nr; }
+    const double D_ = c[1] * c[1] - 4 * c[0] * c[2];
+    if (D_ < 0) return 0;
+    const double sD = sqrt(D_);
+    double r0, r1;
+    if (c[1] >= 0) { r0 = (-c[1] - sD) / (2.0 * c[0]); r1 = (2.0 * c[2]) / (-c[1] - sD); }
+    else { r0 = (2.0 * c[2]) / (-c[1] + sD); r1 = (-c[1] + sD) / (2.0 * c[0]); }
+    if (r0 > r1) { const double t = r0; r0 = r1; r1 = t; }
+    if (r0 >= a && r0 <= b) roots[nr++] = r0;
+    if (r1 >= a && r1 <= b && r1 != r0) roots[nr++] = r1;
+    return nr;
 }
 
-/* MinimizePolynomial on [x_min, x_max] */
-static double poly_minimize(const double *c, int n, double x_min, double x_max)
+/* real roots inside [a, b] of c given the real roots `crit` of its derivative: they cut [a, b] into monotone pieces */
+static int lsq_roots_from_crit(const double *c, int n, double a, double b, const double *crit, int ncrit, double *roots)
 {
-    double best_x = (x_min + x_max) / 2.0, best = poly_eval(c, n, best_x);
-    double v = poly_eval(c, n, x_min);
-    if (v < best) { best = v; best_x = x_min; }
-    v = poly_eval(c, n, x_max);
-    if (v < best) { best = v; best_x = x_max; }
-    if (n <= 2) return best_x;
-    double d[8], re[8];
-    for (int i = 0; i < n - 1; i++) d[i] = (n - 1 - i) * c[i];
-    const int nr = poly_root_real_parts(d, n - 1, re);
-    for (int i = 0; i < nr; i++) {
-        if (re[i] < x_min || re[i] > x_max) continue;
-        v = poly_eval(c, n, re[i]);
-        if (v < best) { best = v; best_x = re[i]; }
+    int nr = 0;
+    double u = a, fu = lsq_poly_eval(c, n, a);
+    for (int k = 0; k <= ncrit; ++k) {
+        const double v = k < ncrit ? crit[k] : b;
+        if (!(v > u)) continue;
+        const double fv = lsq_poly_eval(c, n, v);
+        double r = 0;
+        bool have = true;
+        if (fu == 0.0) r = u;
+        else if (fv == 0.0) r = v;
+        else if ((fu < 0) != (fv < 0)) r = lsq_root_bracketed(c, n, u, v, fu);
+        else have = false;
+        if (have && (nr == 0 || r != roots[nr - 1])) roots[nr++] = r;
+        u = v; fu = fv;
     }
-    return best_x;
+    return nr;
 }
 
-/* LineSearch::InterpolatingPolynomialMinimizingStepSize for CUBIC interpolation */
+/* real roots inside [a, b] of a polynomial of degree <= 4, ascending (degree 2 in closed form, 3 and 4 through the derivative) */
+static int lsq_roots_in(const double *c, int n, double a, double b, double *roots)
+{
+    while (n > 0 && c[0] == 0.0) { ++c; --n; }
+    if (n - 1 <= 2) return lsq_roots_low(c, n, a, b, roots);
+    double d1[4], d2[3], crit2[4], crit1[4];
+    for (int i = 0; i < n - 1; ++i) d1[i] = (n - 1 - i) * c[i];
+    int n1;
+    if (n - 1 == 3) n1 = lsq_roots_low(d1, 3, a, b, crit1);
+    else {
+        for (int i = 0; i < 3; ++i) d2[i] = (3 - i) * d1[i];
+        const int n2 = lsq_roots_low(d2, 3, a, b, crit2);
+        n1 = lsq_roots_from_crit(d1, 4, a, b, crit2, n2, crit1);
+    }
+    return lsq_roots_from_crit(c, n, a, b, crit1, n1, roots);
+}
+
+/* LineSearch::InterpolatingPolynomialMinimizingStepSize for CUBIC interpolation: the minimiser over [min_step, max_step] of the
+ * polynomial through value and gradient of (lower bound at 0, current[, previous]).  FindInterpolatingPolynomial solves the
+ * Vandermonde-type system of all (4 or 6) constraints with Eigen's fullPivLu; the same polynomial is obtained here in the
+ * scaled variable u = x / current.x, q(u) = f0 + g0 xc u + b2 u^2 + ... (the two constraints at 0 fix the low coefficients),
+ * from a 2 x 2 / 4 x 4 system with entries of order one.  MinimizePolynomial samples the midpoint, the ends and the real part
+ * of EVERY root of the derivative (companion-matrix eigenvalues, complex ones included, "a bit of an overkill") inside the
+ * interval; the minimum over an interval sits at an end or at a real critical point, so only the real roots inside the
+ * interval can win, and those are found exactly (bracketed through the derivative's roots, polished by safeguarded Newton). */
 static double ls_interpolating_step(const LsSample *lower, const LsSample *prev, const LsSample *cur, double min_step, double max_step)
 {
     if (!cur->value_ok) return fmin(fmax(cur->x * 0.5, min_step), max_step);
-    LsSample smp[3];
-    int ns = 0;
-    smp[ns++] = *lower;
-    smp[ns++] = *cur;
-    if (prev->value_ok) smp[ns++] = *prev;
-    double coef[6];
-    const int nc = poly_interpolate(smp, ns, coef);
-    return poly_minimize(coef, nc, min_step, max_step);
+    const double xc = cur->x, f0 = lower->value, g0 = lower->gradient * xc;
+    double q[6];
+    int nq;
+    const double rv = cur->value - f0 - g0, rg = cur->gradient * xc - g0;
+    if (!prev->value_ok) {
+        /* cubic: b3 + b2 = rv, 3 b3 + 2 b2 = rg */
+        const double b3 = rg - 2.0 * rv, b2 = 3.0 * rv - rg;
+        q[0] = b3; q[1] = b2; q[2] = g0; q[3] = f0; nq = 4;
+    } else {
+        const double u = prev->x / xc, u2 = u * u, u3 = u2 * u, u4 = u3 * u, u5 = u4 * u;
+        double A[4][5] = {{1, 1, 1, 1, rv}, {5, 4, 3, 2, rg},
+                          {u5, u4, u3, u2, prev->value - f0 - g0 * u}, {5 * u4, 4 * u3, 3 * u2, 2 * u, prev->gradient * xc - g0}};
+        for (int k = 0; k < 4; k++) {                      /* Gaussian elimination, partial pivoting */
+            int pr = k;
+            for (int r = k + 1; r < 4; r++) if (fabs(A[r][k]) > fabs(A[pr][k])) pr = r;
+            if (pr != k) for (int c = 0; c < 5; c++) { const double t = A[k][c]; A[k][c] = A[pr][c]; A[pr][c] = t; }
+            if (A[k][k] == 0.0) continue;
+            for (int r = k + 1; r < 4; r++) {
+                const double f = A[r][k] / A[k][k];
+                for (int c = k; c < 5; c++) A[r][c] -= f * A[k][c];
+            }
+        }
+        double b[4];
+        for (int k = 3; k >= 0; k--) {
+            double v = A[k][4];
+            for (int c = k + 1; c < 4; c++) v -= A[k][c] * b[c];
+            b[k] = A[k][k] != 0.0 ? v / A[k][k] : 0.0;
+        }
+        q[0] = b[0]; q[1] = b[1]; q[2] = b[2]; q[3] = b[3]; q[4] = g0; q[5] = f0; nq = 6;
+    }
+    /* MinimizePolynomial over [min_step, max_step] in u */
+    const double ua = min_step / xc, ub = max_step / xc;
+    double best_x = (min_step + max_step) / 2.0, best = lsq_poly_eval(q, nq, (ua + ub) / 2.0);
+    double v = lsq_poly_eval(q, nq, ua);
+    if (v < best) { best = v; best_x = min_step; }
+    v = lsq_poly_eval(q, nq, ub);
+    if (v < best) { best = v; best_x = max_step; }
+    double d[5], roots[4];
+    for (int i = 0; i < nq - 1; i++) d[i] = (nq - 1 - i) * q[i];
+    const int nr = lsq_roots_in(d, nq - 1, ua, ub, roots);
+    for (int i = 0; i < nr; i++) {
+        v = lsq_poly_eval(q, nq, roots[i]);
+        if (v < best) { best = v; best_x = roots[i] * xc; }
+    }
+    return best_x;
 }
 
 /* test hook: minimiser of the interpolating polynomial through up to three (x, value, gradient) samples */

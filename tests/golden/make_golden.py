@@ -144,6 +144,7 @@ def back_end():
     from oracle import ba_ref
     from vrf_b200 import ba_problem as BP
     cfg = golden_cfg()
+    BP.WindowSimulator.FLAG2_DEPTH = (0.52, 1.2)        # bounded landmarks next to their bound, like tests/conftest.py
     sim = BP.WindowSimulator(11, cfg, n_landmarks=80, preintegrate=ba_ref.preintegrate)
     out = {}
     for a in range(3):              # window 0: no prior; 1, 2: with the prior of the previous window

@@ -388,7 +388,8 @@ def _ceres_interpolating_step(xs, vals, grads, lo, hi):
 
 
 def test_line_search_step_matches_companion_matrix_minimiser():
-    """The step-size rule of the projected Armijo line search (oracle/ba_ref.c::ls_interpolating_step, Aberth-Ehrlich roots)
+    """The step-size rule of the projected Armijo line search (oracle/ba_ref.c::ls_interpolating_step: only the real
+    critical points inside the interval, bracketed through the derivative's roots and bisected)
     against an independent statement with numpy's companion-matrix roots: cubic (two samples) and quintic (three samples)
     interpolants, contraction interval [1e-3 t, 0.6 t] as ArmijoLineSearch::DoSearch passes it."""
     rng = np.random.default_rng(5)

@@ -75,7 +75,7 @@ struct BaProbDev {
                                           //        (built once per solve by k_ba_solve; pair offsets in BaShared::pair_ptr)
     double *pair_part;                    // [45][BA_PP_STRIDE] per-pair partial sums of one linearisation
     double *fpart;                        // [nobs][BA_FP_STRIDE] per-factor contributions to the landmark sums
-    double *task_cost;                    // [BA_MAX_TASKS] cost of each task of the dynamic queue (summed in task order)
+    double *task_cost;                    // [2][BA_MAX_TASKS] cost (and directional derivative) of each task of the dynamic queue, summed in task order
 };
 
 struct BaOutDev {

@@ -137,7 +137,7 @@ int ba_create(vrf_handle *h)
     BCK(cudaMalloc((void **)&b->d_fac, S * BA_MAX_OBS * sizeof(int)));
     BCK(cudaMalloc((void **)&b->d_pair_part, S * (BA_NF * (BA_NF - 1) / 2) * BA_PP_STRIDE * sizeof(double)));
     BCK(cudaMalloc((void **)&b->d_fpart, S * (size_t)BA_MAX_OBS * BA_FP_STRIDE * sizeof(double)));
-    BCK(cudaMalloc((void **)&b->d_task_cost, S * BA_MAX_TASKS * sizeof(double)));
+    BCK(cudaMalloc((void **)&b->d_task_cost, S * 2 * BA_MAX_TASKS * sizeof(double)));
     b->prior_cur.assign(S, 0);
     b->prior_valid.assign(S, 0);
     b->last_M.assign(S, 0);
@@ -277,7 +277,7 @@ static int pack_problem(vrf_handle *h, BaSlot &sl, int slot, int seq, const VrfB
     pd.fac = b->d_fac + (size_t)seq * BA_MAX_OBS;
     pd.pair_part = b->d_pair_part + (size_t)seq * (BA_NF * (BA_NF - 1) / 2) * BA_PP_STRIDE;
     pd.fpart = b->d_fpart + (size_t)seq * BA_MAX_OBS * BA_FP_STRIDE;
-    pd.task_cost = b->d_task_cost + (size_t)seq * BA_MAX_TASKS;
+    pd.task_cost = b->d_task_cost + (size_t)seq * 2 * BA_MAX_TASKS;
 
     BaMargDev &mg = sl.h_marg[slot];
     double *mb = b->d_margbuf + (size_t)seq * kMargDoubles;

@@ -157,16 +157,19 @@ __device__ __forceinline__ int pair_index(int i, int j) { return i * (2 * BA_NF 
 // which task or when -- a task only produces partials that it alone owns (whitened IMU Jacobians in shared memory,
 // per-pair and per-factor sums in the L2-resident scratch of ba_dev.cuh, its own cost), and the assembly pass adds them
 // with one owner thread per destination in a fixed order.  No floating-point atomics.
-template <bool GACT>
+template <bool GACT, bool DIRDER>
 __device__ __noinline__ double ba_evaluate_t(const BaMeta &m, const BaProbDev &p, BaShared &sh, const double *pose, const double *sb,
-                                const double *ex, const double td, const double *lam, const int mode)
+                                const double *ex, const double td, const double *lam, const int mode, double *dphi_out = nullptr)
 {
-    // mode 0: cost only; 1: cost + full linearisation (H, g, W, hll, gl); 2: cost + gradient only (g, gl), for the trial
-    // points of the projected line search -- H, W and hll are left alone
-    const bool lin = mode != 0, full = mode == 1;
+    // mode 0: cost only; 1: cost + full linearisation (H, g, W, hll, gl); 2: cost + directional derivative delta . gradient
+    // for the trial points of the projected line search -- delta in sh.colv (camera columns) and p.y_l (landmarks), every
+    // factor contributes r^T (J delta): no assembly, the linearisation at x is left alone
+    // (DIRDER is a separate instantiation: the trial-point code stays out of the registers of the iteration's hot path)
+    const bool lin = !DIRDER && mode == 1;
+    constexpr bool dirder = DIRDER;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = BA_THREADS / 32;
     if (lin) {
-        if (full) for (int i = tid; i < BA_NC * (BA_NC + 1) / 2; i += BA_THREADS) sh.H[i] = 0.0;
+        for (int i = tid; i < BA_NC * (BA_NC + 1) / 2; i += BA_THREADS) sh.H[i] = 0.0;
         for (int i = tid; i < BA_NC; i += BA_THREADS) sh.g[i] = 0.0;
         // (the coupling rows W are zeroed once per solve: a linearisation rewrites the same entries every time)
     }
@@ -187,7 +190,7 @@ __device__ __noinline__ double ba_evaluate_t(const BaMeta &m, const BaProbDev &p
         if (lane == 0) task = atomicAdd(&sh.flag[2], 1);
         task = __shfl_sync(0xffffffffu, task, 0);
         if (task >= ntask) break;
-        double tcost = 0.0;
+        double tcost = 0.0, tdphi = 0.0;
         if (task < m.nimu) {
             // ---- IMU factor: one warp per factor; whitened residual and Jacobian go to shared memory, J^T J is formed by
             //      the assembly pass below ----
@@ -208,6 +211,21 @@ __device__ __noinline__ double ba_evaluate_t(const BaMeta &m, const BaProbDev &p
                     imu_jac_col(pre, pose + 7 * i, sb + 9 * i, pose + 7 * j, sb + 9 * j, m.g_norm, &cx, lane, col);
                     for (int rI = 0; rI < 15; ++rI) { double a = 0; for (int k = rI; k < 15; ++k) a += S[rI * 15 + k] * col[k]; sh.imuJ[f][rI * 30 + lane] = a; }
                 }
+            } else if (dirder) {
+                // delta . J^T r: lane c holds column c of the whitened Jacobian, the whitened residual rows come by shuffle
+                double col[15];
+#pragma unroll
+                for (int k = 0; k < 15; ++k) col[k] = 0.0;
+                if (lane < 30) imu_jac_col(pre, pose + 7 * i, sb + 9 * i, pose + 7 * j, sb + 9 * j, m.g_norm, &cx, lane, col);
+                double gcol = 0;
+                for (int rI = 0; rI < 15; ++rI) {
+                    double a = 0;
+                    for (int k = rI; k < 15; ++k) a += S[rI * 15 + k] * col[k];
+                    gcol += a * __shfl_sync(0xffffffffu, rw, rI);
+                }
+                const int c = lane;
+                const int tc = c < 6 ? 6 * i + c : c < 15 ? 66 + 9 * i + (c - 6) : c < 21 ? 6 * j + (c - 15) : 66 + 9 * j + (c - 21);
+                if (lane < 30) tdphi = gcol * sh.colv[tc];
             }
         } else if (!lin) {
             // ---- projection factors, cost only: 32 consecutive factors of the pair-major list per warp, one lane per factor ----
@@ -219,8 +237,38 @@ __device__ __noinline__ double ba_evaluate_t(const BaMeta &m, const BaProbDev &p
                 double r[2], Ji[12], Jj[12], Jl[2], xi, yi, xj, yj;
                 obs_at(m, p, o0, td, xi, yi);
                 obs_at(m, p, o0 + (j - i), td, xj, yj);
-                tcost = 0.5 * proj_eval(pose + 7 * i, sh.R + 9 * i, pose + 7 * j, sh.R + 9 * j, ex, sh.ric, lam[l], xi, yi, xj, yj, false,
-                                        p.lm_const[l] != 0, r, Ji, Jj, Jl);
+                if (!dirder)
+                    tcost = 0.5 * proj_eval(pose + 7 * i, sh.R + 9 * i, pose + 7 * j, sh.R + 9 * j, ex, sh.ric, lam[l], xi, yi, xj, yj, false,
+                                            p.lm_const[l] != 0, r, Ji, Jj, Jl);
+                else {
+                    // r^T (J delta) of this factor (corrected residual and Jacobians, like the linearisation)
+                    double j0, j1;
+                    if (!gact) {
+                        tcost = 0.5 * proj_eval(pose + 7 * i, sh.R + 9 * i, pose + 7 * j, sh.R + 9 * j, ex, sh.ric, lam[l], xi, yi, xj, yj, true,
+                                                p.lm_const[l] != 0, r, Ji, Jj, Jl);
+                        j0 = 0; j1 = 0;
+                    } else {
+                        const int oj = o0 + (j - i);
+                        double Je[12], Jt[2] = {0, 0};
+                        tcost = 0.5 * proj_eval(pose + 7 * i, sh.R + 9 * i, pose + 7 * j, sh.R + 9 * j, ex, sh.ric, lam[l], xi, yi, xj, yj, true,
+                                                p.lm_const[l] != 0, r, Ji, Jj, Jl, Je, m.td_active ? p.obs_vel + 2 * o0 : nullptr,
+                                                m.td_active ? p.obs_vel + 2 * oj : nullptr, m.td_active ? Jt : nullptr);
+                        j0 = Jt[0] * sh.colv[BA_COL_TD]; j1 = Jt[1] * sh.colv[BA_COL_TD];
+                        if (m.ex_active) {
+#pragma unroll
+                            for (int c = 0; c < 6; ++c) { j0 += Je[c] * sh.colv[BA_COL_EX + c]; j1 += Je[6 + c] * sh.colv[BA_COL_EX + c]; }
+                        }
+                    }
+                    const bool host_const = (i == 0 && !m.use_imu);
+                    const double dl = p.y_l[l];
+                    j0 += Jl[0] * dl; j1 += Jl[1] * dl;
+#pragma unroll
+                    for (int a = 0; a < 6; ++a) {
+                        const double di = host_const ? 0.0 : sh.colv[6 * i + a], dj = sh.colv[6 * j + a];
+                        j0 += Ji[a] * di + Jj[a] * dj; j1 += Ji[6 + a] * di + Jj[6 + a] * dj;
+                    }
+                    tdphi = j0 * r[0] + j1 * r[1];
+                }
             }
         } else {
             // ---- projection factors, linearisation: one warp per frame pair (host i, observer j), one lane per factor ----
@@ -268,10 +316,8 @@ __device__ __noinline__ double ba_evaluate_t(const BaMeta &m, const BaProbDev &p
 #pragma unroll
                         for (int c = 0; c < 6; ++c) { Jg[c] = m.ex_active ? Je[c] : 0.0; Jg[7 + c] = m.ex_active ? Je[6 + c] : 0.0; }
                         Jg[6] = Jt[0]; Jg[13] = Jt[1];
-                        if (full) {
 #pragma unroll
-                            for (int q = 0; q < 7; ++q) fp[8 + q] = Jg[q] * Jl[0] + Jg[7 + q] * Jl[1];
-                        }
+                        for (int q = 0; q < 7; ++q) fp[8 + q] = Jg[q] * Jl[0] + Jg[7 + q] * Jl[1];
                     }
                     tcost += 0.5 * rho0;
                     // a constant parameter block is not part of the Ceres program: no Jacobian columns (para_Pose[0] in VO mode,
@@ -280,29 +326,17 @@ __device__ __noinline__ double ba_evaluate_t(const BaMeta &m, const BaProbDev &p
 #pragma unroll
                         for (int k = 0; k < 12; ++k) Ji[k] = 0.0;
                     }
-                    if (full) {
 #pragma unroll
-                        for (int a = 0; a < 6; ++a) {
-                            Wl[6 * j + a] = Jj[a] * Jl[0] + Jj[6 + a] * Jl[1];
-                            fp[a] = Ji[a] * Jl[0] + Ji[6 + a] * Jl[1];
-                        }
-                        fp[6] = Jl[0] * Jl[0] + Jl[1] * Jl[1];
+                    for (int a = 0; a < 6; ++a) {
+                        Wl[6 * j + a] = Jj[a] * Jl[0] + Jj[6 + a] * Jl[1];
+                        fp[a] = Ji[a] * Jl[0] + Ji[6 + a] * Jl[1];
                     }
+                    fp[6] = Jl[0] * Jl[0] + Jl[1] * Jl[1];
                     fp[7] = Jl[0] * r[0] + Jl[1] * r[1];
                 }
-                if (gact) {
-                    if (full) accumulate_g(accg, lane, Ji, Jj, Jg, r);
-                    else {
-                        // gradient only: Jg_q^T r, q = 0..6, into the slot the full pass uses (lane 2 * 12 of row q)
-                        double v[16];
-#pragma unroll
-                        for (int t = 0; t < 16; ++t) v[t] = t < 7 ? Jg[t] * r[0] + Jg[7 + t] * r[1] : 0.0;
-                        accg[0] += reduce_scatter16(v, lane);
-                    }
-                }
+                if (gact) accumulate_g(accg, lane, Ji, Jj, Jg, r);
 #pragma unroll
                 for (int ps = 0; ps < 6; ++ps) {
-                    if (!full && ps < 4) continue;          // the gradient entries 78..89 live in rounds 4 and 5
                     double v[16];
 #pragma unroll
                     for (int t = 0; t < 16; ++t) v[t] = pair_entry(ps * 16 + t, Ji, Jj, r);
@@ -313,60 +347,21 @@ __device__ __noinline__ double ba_evaluate_t(const BaMeta &m, const BaProbDev &p
                 double *pp = p.pair_part + (size_t)pi * BA_PP_STRIDE + (lane >> 1);
 #pragma unroll
                 for (int ps = 0; ps < 6; ++ps) pp[16 * ps] = acc[ps];
-                if (gact && full) {
+                if (gact) {
 #pragma unroll
                     for (int q = 0; q < 9; ++q) pp[96 + 16 * q] = accg[q];
                 }
-                // gradient only: lane 2 q holds Jg_q^T r -> slot 96 + 16 q + 12
-                if (gact && !full && (lane >> 1) < 7) p.pair_part[(size_t)pi * BA_PP_STRIDE + 96 + 16 * (lane >> 1) + 12] = accg[0];
             }
         }
         tcost = warp_sum_d(tcost);
-        if (lane == 0) p.task_cost[task] = tcost;
+        if (dirder) tdphi = warp_sum_d(tdphi);
+        if (lane == 0) { p.task_cost[task] = tcost; if (dirder) p.task_cost[BA_MAX_TASKS + task] = tdphi; }
     }
     EPROF(1);
     __syncthreads();
-    double cost = 0.0;
-    for (int t = tid; t < ntask; t += BA_THREADS) cost += p.task_cost[t];
-    if (mode == 2) {
-        // ---- gradient only: pose gradients from the per-pair sums, ex-pose / td gradient, g_l from the per-factor slots ----
-        const int nC = BA_NF * 6, nE = gact ? 7 : 0;
-        for (int it = tid; it < nC + nE + m.M; it += BA_THREADS) {
-            double sum = 0.0;
-            if (it < nC) {
-                const int f = it / 6, t = it - 6 * f;
-                for (int i = 0; i < f; ++i) sum += p.pair_part[(size_t)pair_index(i, f) * BA_PP_STRIDE + 78 + t];
-                for (int j = f + 1; j < BA_NF; ++j) sum += p.pair_part[(size_t)pair_index(f, j) * BA_PP_STRIDE + 84 + t];
-                sh.g[6 * f + t] = sum;
-            } else if (it < nC + nE) {
-                const int q = it - nC;
-                for (int pi = 0; pi < BA_NPAIR; ++pi) sum += p.pair_part[(size_t)pi * BA_PP_STRIDE + 96 + 16 * q + 12];
-                sh.g[BA_COL_EX + q] = sum;
-            } else {
-                const int l = it - nC - nE;
-                const int o0 = p.obs_ptr[l], o1 = p.obs_ptr[l + 1];
-                for (int o = o0 + 1; o < o1; ++o) sum += p.fpart[(size_t)o * BA_FP_STRIDE + 7];
-                p.gl[l] = sum;
-            }
-        }
-        __syncthreads();
-        for (int pass = 0; pass < 2; ++pass) {
-            const int f_lo = pass ? sh.imu_neven : 0, f_hi = pass ? m.nimu : sh.imu_neven;
-            for (int it = tid + f_lo * 30; it < f_hi * 30; it += BA_THREADS) {
-                const int fo = it / 30, c = it - fo * 30;
-                const int f = sh.imu_ord[fo];
-                const int j = m.imu_j[f], i = j - 1;
-                const double *J = sh.imuJ[f];
-                const int tc = c < 6 ? 6 * i + c : c < 15 ? 66 + 9 * i + (c - 6) : c < 21 ? 6 * j + (c - 15) : 66 + 9 * j + (c - 21);
-                double gsum = 0;
-#pragma unroll
-                for (int k = 0; k < 15; ++k) gsum += J[k * 30 + c] * sh.imur[f][k];
-                sh.g[tc] += gsum;
-            }
-            __syncthreads();
-        }
-    }
-    if (full) {
+    double cost = 0.0, dphi = 0.0;
+    for (int t = tid; t < ntask; t += BA_THREADS) { cost += p.task_cost[t]; if (dirder) dphi += p.task_cost[BA_MAX_TASKS + t]; }
+    if (lin) {
         // ---- assembly, one owner thread per destination, contributions added in a fixed order ----
         // (a) projection factors: pose blocks and gradient from the per-pair sums, landmark sums from the per-factor slots
         const int nfp = gact ? 15 : 8;
@@ -518,6 +513,12 @@ __device__ __noinline__ double ba_evaluate_t(const BaMeta &m, const BaProbDev &p
             }
         }
         __syncthreads();
+        if (dirder) {
+            for (int a = tid; a < n; a += BA_THREADS) {
+                const int ca = sh.pcol[a];
+                if (ca >= 0) dphi += (sh.pr0[a] + sh.pr[a]) * sh.colv[ca];
+            }
+        }
         if (lin) {
             // g += gp + HP dx ; H += HP, both through the column map (constant blocks drop out; distinct prior columns map to
             // distinct tangent columns, so every destination has one writer)
@@ -526,7 +527,7 @@ __device__ __noinline__ double ba_evaluate_t(const BaMeta &m, const BaProbDev &p
                 if (ca >= 0) sh.g[ca] += sh.pr0[a] + sh.pr[a];
             }
 #pragma unroll 4
-            for (int e = tid; full && e < n * n; e += BA_THREADS) {
+            for (int e = tid; e < n * n; e += BA_THREADS) {
                 int a2 = e / n, b = e - a2 * n;
                 if (b > a2) continue;
                 int ca = sh.pcol[a2], cb = sh.pcol[b];
@@ -540,14 +541,18 @@ __device__ __noinline__ double ba_evaluate_t(const BaMeta &m, const BaProbDev &p
     if (eprof && blockIdx.x == 0 && (tid == 0 || tid == 320 || tid == 500))
         printf("evaluate mode=%d tid=%d zero=%lld tasks=%lld diag=%lld wait=%lld prior=%lld\n", mode, tid, et[0], et[1], et[2], et[3], et[4]);
 #undef EPROF
+    if (dirder) { const double d_ = block_sum(dphi, sh.red); __syncthreads(); *dphi_out = d_; }
     return block_sum(cost, sh.red);
 }
 
 __device__ __forceinline__ double ba_evaluate(const BaMeta &m, const BaProbDev &p, BaShared &sh, const double *pose, const double *sb,
-                                              const double *ex, const double td, const double *lam, int mode)
+                                              const double *ex, const double td, const double *lam, int mode, double *dphi_out = nullptr)
 {
-    return (m.ex_active || m.td_active) ? ba_evaluate_t<true>(m, p, sh, pose, sb, ex, td, lam, mode)
-                                        : ba_evaluate_t<false>(m, p, sh, pose, sb, ex, td, lam, mode);
+    if (mode == 2)
+        return (m.ex_active || m.td_active) ? ba_evaluate_t<true, true>(m, p, sh, pose, sb, ex, td, lam, mode, dphi_out)
+                                            : ba_evaluate_t<false, true>(m, p, sh, pose, sb, ex, td, lam, mode, dphi_out);
+    return (m.ex_active || m.td_active) ? ba_evaluate_t<true, false>(m, p, sh, pose, sb, ex, td, lam, mode, dphi_out)
+                                        : ba_evaluate_t<false, false>(m, p, sh, pose, sb, ex, td, lam, mode, dphi_out);
 }
 
 // D(8x8) = A(8x4) B(4x8) + D on the FP64 tensor cores (SASS: DMMA.8x8x4); see the trailing update of the Cholesky below
@@ -652,6 +657,101 @@ __device__ double dot_full(const BaMeta &m, const double *ac, const double *bc, 
     for (int l = threadIdx.x; l < m.M; l += BA_THREADS) v += al[l] * bl[l];
     return block_sum(v, s_red);
 }
+
+// the trust-region step in the parameters' tangent space: delta = (c1 gd + c2 gn) / diag * jscale (dogleg coefficients c1, c2)
+__device__ __forceinline__ double ba_dcol(const BaShared &sh, double c1, double c2, int c)
+{
+    return (c1 * sh.gd[c] + c2 * sh.gn[c]) / sh.diag[c] * sh.jscale[c];
+}
+__device__ __forceinline__ double ba_dlm(const BaProbDev &p, double c1, double c2, int l)
+{
+    return (c1 * p.gd_l[l] + c2 * p.gn_l[l]) / p.diag_l[l] * p.jscale_l[l];
+}
+
+// candidate = x (+) t delta into sh.cpose / sh.csb / sh.cex / sh.tdv[1] / p.clam; t = 1 except for the trial points of the line search
+__device__ __noinline__ void ba_make_candidate(const BaMeta &m, const BaProbDev &p, BaShared &sh, double c1, double c2, const double t)
+{
+    const int tid = threadIdx.x;
+    for (int f = tid; f < BA_NF; f += BA_THREADS) {
+        if (col_active_dev(m, 6 * f)) {
+            double dl[6];
+            for (int k = 0; k < 6; ++k) dl[k] = ba_dcol(sh, c1, c2, 6 * f + k) * t;
+            d_pose_plus(sh.pose + 7 * f, dl, sh.cpose + 7 * f);
+        } else for (int k = 0; k < 7; ++k) sh.cpose[7 * f + k] = sh.pose[7 * f + k];
+        for (int k = 0; k < 9; ++k) {
+            const int c = 66 + 9 * f + k;
+            sh.csb[9 * f + k] = sh.sb[9 * f + k] + (col_active_dev(m, c) ? ba_dcol(sh, c1, c2, c) * t : 0.0);
+        }
+    }
+    if (tid == 64) {
+        if (m.ex_active) {
+            double dl[6];
+            for (int k = 0; k < 6; ++k) dl[k] = ba_dcol(sh, c1, c2, BA_COL_EX + k) * t;
+            d_pose_plus(sh.ex, dl, sh.cex);
+        } else for (int k = 0; k < 7; ++k) sh.cex[k] = sh.ex[k];
+        sh.tdv[1] = sh.tdv[0] + (m.td_active ? ba_dcol(sh, c1, c2, BA_COL_TD) * t : 0.0);
+    }
+    for (int l = tid; l < m.M; l += BA_THREADS) {
+        double v = p.lam[l];
+        if (!p.lm_const[l]) {
+            v += ba_dlm(p, c1, c2, l) * t;
+            v = fmin(v, p.lm_ub[l]);           // ParameterBlock::Plus projects onto the bounds
+        }
+        p.clam[l] = v;
+    }
+    __syncthreads();
+}
+
+// Ceres' projected Armijo line search of bound-constrained problems (TrustRegionMinimizer::DoLineSearch; statement and
+// defaults: ba_linesearch.cuh, oracle/ba_ref.c), entered when the full step fails f(x [+] delta) <= f(x) + 1e-4 g.delta.
+// phi(t) = f(x [+] t delta) with the bounds projection inside Plus, phi'(t) = delta . gradient at the trial point.  The step
+// is contracted by polynomial interpolation until the test holds (<= 20 iterations, step size >= 1e-9 / |delta|_inf).  A trial
+// point costs one evaluation of all factors with Jacobians, each contributing r^T (J delta): the linearisation at x stays
+// untouched.  On success the candidate arrays hold x [+] t delta and *cand_cost its cost; a failed search leaves the full step.
+__device__ __noinline__ bool ba_line_search(const BaMeta &m, const BaProbDev &p, BaShared &sh, double c1, double c2, double x_cost,
+                                            double sTg, double *cand_cost)
+{
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = BA_THREADS / 32;
+    const int M = m.M;
+    double dmax = 0;
+    // the direction for the trial evaluations (both arrays are idle between two factorisations)
+    for (int c = tid; c < BA_NC; c += BA_THREADS) { const double d = ba_dcol(sh, c1, c2, c); sh.colv[c] = d; dmax = fmax(dmax, fabs(d)); }
+    for (int l = tid; l < M; l += BA_THREADS) { const double d = p.lm_const[l] ? 0.0 : ba_dlm(p, c1, c2, l); p.y_l[l] = d; dmax = fmax(dmax, fabs(d)); }
+    for (int o = 16; o > 0; o >>= 1) dmax = fmax(dmax, __shfl_xor_sync(0xffffffffu, dmax, o));
+    __syncthreads();
+    if (lane == 0) sh.red[warp] = dmax;
+    __syncthreads();
+    dmax = 0;
+    for (int i = 0; i < nwarp; ++i) dmax = fmax(dmax, sh.red[i]);
+    __syncthreads();
+    const LsSample lower = {0.0, x_cost, sTg, true, true};
+    LsSample prev = {0.0, 0.0, 0.0, false, false}, cur = {1.0, *cand_cost, 0.0, false, true};
+    bool ok = false;
+    for (int it = 0;; ++it) {
+        if (it > 0) {
+            if (it >= 20) break;                                   // max_num_line_search_step_size_iterations
+            // (one warp evaluates the polynomial step, the others wait: the samples are identical in every thread)
+            if (warp == 0) { const double t_ = ls_interpolating_step(lower, prev, cur, 1e-3 * cur.x, 0.6 * cur.x); if (lane == 0) sh.sc[0] = t_; }
+            __syncthreads();
+            const double t = sh.sc[0];
+            __syncthreads();
+            if (t * dmax < 1e-9) break;                            // min_line_search_step_size
+            prev = cur;
+            cur.x = t;
+            ba_make_candidate(m, p, sh, c1, c2, t);
+        }
+        double dg = 0;
+        cur.value = ba_evaluate(m, p, sh, sh.cpose, sh.csb, sh.cex, sh.tdv[1], p.clam, 2, &dg);
+        cur.gradient = dg;
+        cur.value_ok = isfinite(cur.value) && isfinite(cur.gradient);
+        cur.grad_ok = cur.value_ok;
+        if (cur.value_ok && cur.value <= x_cost + 1e-4 * sTg * cur.x) { ok = it > 0; break; }
+    }
+    if (ok) *cand_cost = cur.value;                    // the candidate arrays already hold x [+] t delta
+    else ba_make_candidate(m, p, sh, c1, c2, 1.0);    // failed search: the step stays as it was
+    return ok;
+}
+
 
 __global__ void __launch_bounds__(BA_THREADS, 1)
 k_ba_solve(const BaMeta *metas, const BaProbDev *probs, BaOutDev *outs)
@@ -1220,84 +1320,16 @@ k_ba_solve(const BaMeta *metas, const BaProbDev *probs, BaOutDev *outs)
             if (!(mcc > 0.0)) step_ok = false;
             else {
                 invalid = 0;
-                // candidate = x (+) t (step * jscale); t = 1 except for the trial points of the line search below
-                auto dcol = [&](int c) { return (c1 * sh.gd[c] + c2 * sh.gn[c]) / sh.diag[c] * sh.jscale[c]; };       // delta, camera columns
-                auto dlm = [&](int l) { return (c1 * p.gd_l[l] + c2 * p.gn_l[l]) / p.diag_l[l] * p.jscale_l[l]; };    // delta, landmark l
-                auto make_candidate = [&](const double t) {
-                    for (int f = tid; f < BA_NF; f += BA_THREADS) {
-                        if (col_active_dev(m, 6 * f)) {
-                            double dl[6];
-                            for (int k = 0; k < 6; ++k) dl[k] = dcol(6 * f + k) * t;
-                            d_pose_plus(sh.pose + 7 * f, dl, sh.cpose + 7 * f);
-                        } else for (int k = 0; k < 7; ++k) sh.cpose[7 * f + k] = sh.pose[7 * f + k];
-                        for (int k = 0; k < 9; ++k) {
-                            const int c = 66 + 9 * f + k;
-                            sh.csb[9 * f + k] = sh.sb[9 * f + k] + (col_active_dev(m, c) ? dcol(c) * t : 0.0);
-                        }
-                    }
-                    if (tid == 64) {
-                        if (m.ex_active) {
-                            double dl[6];
-                            for (int k = 0; k < 6; ++k) dl[k] = dcol(BA_COL_EX + k) * t;
-                            d_pose_plus(sh.ex, dl, sh.cex);
-                        } else for (int k = 0; k < 7; ++k) sh.cex[k] = sh.ex[k];
-                        sh.tdv[1] = sh.tdv[0] + (m.td_active ? dcol(BA_COL_TD) * t : 0.0);
-                    }
-                    for (int l = tid; l < M; l += BA_THREADS) {
-                        double v = p.lam[l];
-                        if (!p.lm_const[l]) {
-                            v += dlm(l) * t;
-                            v = fmin(v, p.lm_ub[l]);           // ParameterBlock::Plus projects onto the bounds
-                        }
-                        p.clam[l] = v;
-                    }
-                    __syncthreads();
-                };
-                make_candidate(1.0);
+                // candidate = x (+) (step * jscale)
+                ba_make_candidate(m, p, sh, c1, c2, 1.0);
                 TPROF(6);
                 double cand_cost = ba_evaluate(m, p, sh, sh.cpose, sh.csb, sh.cex, sh.tdv[1], p.clam, 0);
                 TPROF(7);
-                // ---- Ceres' projected Armijo line search of bound-constrained problems (TrustRegionMinimizer::DoLineSearch;
-                // statement and defaults: ba_linesearch.cuh, oracle/ba_ref.c).  phi(t) = f(x [+] t delta), phi'(t) = delta . gradient
-                // at the trial point.  The full step passing f(x [+] delta) <= f(x) + 1e-4 g.delta is the common case and costs
-                // nothing; otherwise the step is contracted by polynomial interpolation until the test holds.  The trial
-                // evaluations overwrite the gradient of the linearisation at x (sh.g, p.gl): whatever happens to the step
-                // afterwards either re-linearises (accepted / invalid) or only needs the stored dogleg vectors (rejected). ----
+                // Ceres' projected Armijo line search of bound-constrained problems: the full step passing
+                // f(x [+] delta) <= f(x) + 1e-4 g.delta is the common case and costs nothing (ba_line_search above)
                 if (constrained && (!isfinite(cand_cost) || cand_cost > x_cost + 1e-4 * sTg)) {
                     ++armijo_failures;
-                    double dmax = 0;
-                    for (int c = tid; c < BA_NC; c += BA_THREADS) dmax = fmax(dmax, fabs(dcol(c)));
-                    for (int l = tid; l < M; l += BA_THREADS) if (!p.lm_const[l]) dmax = fmax(dmax, fabs(dlm(l)));
-                    for (int o = 16; o > 0; o >>= 1) dmax = fmax(dmax, __shfl_xor_sync(0xffffffffu, dmax, o));
-                    __syncthreads();
-                    if (lane == 0) sh.red[warp] = dmax;
-                    __syncthreads();
-                    dmax = 0;
-                    for (int i = 0; i < nwarp; ++i) dmax = fmax(dmax, sh.red[i]);
-                    __syncthreads();
-                    const LsSample lower = {0.0, x_cost, sTg, true, true};
-                    LsSample prev = {0.0, 0.0, 0.0, false, false}, cur = {1.0, cand_cost, 0.0, false, true};
-                    bool ok = false;
-                    for (int it = 0;; ++it) {
-                        if (it > 0) {
-                            if (it >= 20) break;                                   // max_num_line_search_step_size_iterations
-                            const double t = ls_interpolating_step(lower, prev, cur, 1e-3 * cur.x, 0.6 * cur.x);
-                            if (t * dmax < 1e-9) break;                            // min_line_search_step_size
-                            prev = cur;
-                            cur.x = t;
-                            make_candidate(t);
-                        }
-                        cur.value = ba_evaluate(m, p, sh, sh.cpose, sh.csb, sh.cex, sh.tdv[1], p.clam, 2);
-                        double dg = 0;
-                        for (int c = tid; c < BA_NC; c += BA_THREADS) dg += sh.g[c] * dcol(c);
-                        for (int l = tid; l < M; l += BA_THREADS) if (!p.lm_const[l]) dg += p.gl[l] * dlm(l);
-                        cur.gradient = block_sum(dg, sh.red);
-                        cur.value_ok = isfinite(cur.value) && isfinite(cur.gradient);
-                        cur.grad_ok = cur.value_ok;
-                        if (cur.value_ok && cur.value <= x_cost + 1e-4 * sTg * cur.x) { ok = it > 0; break; }
-                    }
-                    if (ok) cand_cost = cur.value;         // the candidate arrays already hold x [+] t delta
-                    else make_candidate(1.0);              // failed search: the step stays as it was
+                    ba_line_search(m, p, sh, c1, c2, x_cost, sTg, &cand_cost);
                 }
                 // step norm over the non-constant blocks (ambient space)
                 double sn = 0;

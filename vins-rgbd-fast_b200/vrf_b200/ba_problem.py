@@ -139,6 +139,8 @@ class WindowSimulator:
     """Ground-truth trajectory + landmark pool -> a chain of 11-frame windows
     (what FeatureManager / processIMU would hand to optimization())."""
 
+    FLAG2_DEPTH = (1.02, 2.2)      # depth range of the estimate_flag == 2 landmarks in units of DEPTH_MAX_DIST (see _spawn)
+
     def __init__(self, seed, cfg, n_landmarks=150, kf_dt=0.1, imu_rate=200.0, flag2_frac=0.1,
                  pix_noise=0.5, ric=None, tic=None, td_true=0.0, ex_constant=1, td_constant=1, ex_perturb=0.0, preintegrate=None,
                  spawn_per_frame=None):
@@ -202,11 +204,14 @@ class WindowSimulator:
             eps = self.rng.normal(0, 0.01)
             flag = 2 if self.rng.random() < self.flag2_frac else 1
             if flag == 2:
-                # estimate_flag 2 = no depth measurement, depth from triangulation: points beyond the sensor range.  The
-                # reference bounds their inverse depth by 2 / DEPTH_MAX_DIST (estimator.cpp:1293-1298), i.e. depth >= 5 m
-                # with the shipped DEPTH_MAX_DIST = 10: spread them over 5.2 .. 12 m (a few start just above the bound
-                # through `eps`, which exercises the projection of the start point)
-                d = 5.2 + (d - 1.5) / 4.5 * 6.8
+                # estimate_flag 2 = no depth measurement, depth from triangulation: points beyond the sensor range
+                # (DEPTH_MAX_DIST, 10 m as shipped).  The reference bounds their inverse depth by 2 / DEPTH_MAX_DIST
+                # (estimator.cpp:1293-1298), i.e. depth >= DEPTH_MAX_DIST / 2.  FLAG2_DEPTH = (lo, hi) in units of DEPTH_MAX_DIST:
+                # the default spreads them over 1.02 .. 2.2 x the range; the parity tests use (0.52, 1.2) = 5.2 .. 12 m, next to
+                # the bound (a few start just above it through `eps`), so that the projection of the start point, the projection
+                # inside Plus() and Ceres' projected line search are exercised by every window chain.
+                lo, hi = (v * float(self.cfg.depth_max_dist) for v in self.FLAG2_DEPTH)
+                d = lo + (d - 1.5) / 4.5 * (hi - lo)
                 P = pc + Rc @ (np.array([xy[0], xy[1], 1.0]) * d)
             out.append({"P": P, "first": k, "last": k + length - 1, "eps": eps, "flag": flag, "id": len(self.pool) + len(out)})
         return out
