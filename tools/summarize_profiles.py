@@ -16,6 +16,14 @@ tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
 S_FRAMES, N_BA = 444, 148          # units per launch of the profiled command (bench.py defaults)
 os.makedirs(OUT, exist_ok=True)
 
+
+
+def kname(full):
+    """'void vrf::k_pyr<0>(FrontCfg, ...)' -> 'k_pyr<0>'"""
+    n = full.split("(")[0].split("::")[-1].strip()
+    return n[5:] if n.startswith("void ") else n
+
+
 rows = []
 with open(os.path.join(GO, "launches.csv")) as f:
     lines = [l for l in f if l.startswith('"')]
@@ -24,7 +32,7 @@ for r in csv.DictReader(lines):
         v = float(r["Metric Value"].replace(",", ""))
         unit = r.get("Metric Unit", "ns")
         v *= {"ns": 1.0, "us": 1e3, "ms": 1e6, "s": 1e9}.get(unit, 1.0)
-        rows.append((r["Kernel Name"].split("(")[0].split("::")[-1], v))
+        rows.append((kname(r["Kernel Name"]), v))
 agg = collections.OrderedDict()
 for k, ns in rows:
     a = agg.setdefault(k, [0, 0.0])
@@ -63,8 +71,8 @@ with open(os.path.join(OUT, f"{tag}_kernels.md"), "w") as md:
         for vals in rr[2:]:
             if len(vals) != len(hdr):
                 continue
-            name = vals[hdr.index("Kernel Name")].split("(")[0].split("::")[-1]
-            if name in seen and name != "k_pyr":
+            name = kname(vals[hdr.index("Kernel Name")])
+            if name in seen:
                 continue
             seen.add(name)
             md.write(f"## {name}\n\n| metric | value | unit |\n|---|---|---|\n")
