@@ -231,7 +231,9 @@ __device__ __noinline__ void jacobi_eig_smem(double *A, double *VT, int n, MargS
                     // diagonal block (k1 == k2): entries (p,p) (p,q) (p,q) (q,q)
                     e11[uu] = min(i1.x, i2.x) * ld + max(i1.x, i2.x); e12[uu] = min(i1.x, i2.y) * ld + max(i1.x, i2.y);
                     e21[uu] = min(i1.y, i2.x) * ld + max(i1.y, i2.x); e22[uu] = min(i1.y, i2.y) * ld + max(i1.y, i2.y);
-                    a11[uu] = A[e11[uu]]; a12[uu] = A[e12[uu]]; a21[uu] = A[e21[uu]]; a22[uu] = A[e22[uu]];
+                    // (idle slots must not touch A: their stand-in block (0, 0) belongs to another thread, which rewrites it in this phase)
+                    if (live[uu]) { a11[uu] = A[e11[uu]]; a12[uu] = A[e12[uu]]; a21[uu] = A[e21[uu]]; a22[uu] = A[e22[uu]]; }
+                    else { a11[uu] = 0.0; a12[uu] = 0.0; a21[uu] = 0.0; a22[uu] = 0.0; }
                 }
 #pragma unroll
                 for (int uu = 0; uu < 2; ++uu) {
