@@ -271,7 +271,8 @@ __device__ __noinline__ void jacobi_eig_smem(double *A, double *VT, int n, MargS
                         const int2 ip = pair_at(r, k);
                         colp[uu] = reinterpret_cast<double2 *>(VT + ip.x * ldv) + vi[u0 + uu];
                         colq[uu] = reinterpret_cast<double2 *>(VT + ip.y * ldv) + vi[u0 + uu];
-                        va[uu] = *colp[uu]; vb[uu] = *colq[uu];
+                        if (vk[u0 + uu] >= 0) { va[uu] = *colp[uu]; vb[uu] = *colq[uu]; }
+                        else { va[uu] = make_double2(0.0, 0.0); vb[uu] = va[uu]; }
                     }
 #pragma unroll
                     for (int uu = 0; uu < 4; ++uu) {
