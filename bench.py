@@ -363,6 +363,7 @@ def main():
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--config", default="c3", choices=sorted(CONFIGS), help="workload: c3 = BASELINE configs[1]+[2] (default, the metric's config), "
                     "c4 = configs[3] (1280x720, 500 feats, 4 levels, 16 seqs/GPU), c5 = configs[4] (300 feats, full VIO, 32 seqs/GPU)")
+    ap.add_argument("--ba-streams", type=int, default=0, help="back-end handles / streams for the publish-phase groups of sequences (0 = auto: one per group for small batches, one in all when a batch fills the GPU)")
     ap.add_argument("--seqs", type=int, default=0, help="sequences per GPU (default: the config's; c3: 444 => 148 concurrent BA windows = one CTA per SM)")
     ap.add_argument("--ref-frames", type=int, default=12, help="frames per worker per step of the reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -468,11 +469,26 @@ def main():
                         for pb in ba_batch) + 1024
     # the back end runs on its own handle/stream so that it overlaps the front end, as the
     # reference's processThread overlaps its trackThread (estimator_nodelet.cpp:61-62)
-    hnd_ba = binding.Handle(cfg, NBA * N_WIN, local_rank)
-    ext_stream_ba = torch.cuda.ExternalStream(hnd_ba.stream(), device=dev)
+    # Sequences publish every PUB_EVERY-th frame with staggered phases: N_WIN groups of sequences, group w's estimators run their
+    # optimisation on the steps k = w (mod N_WIN).  The groups are independent estimator instances (a processThread each in the
+    # reference), so each group gets its own handle / stream (--ba-streams, default one per group): a group's batch may still be
+    # running when the next group's batch is enqueued, and the GPU interleaves their CTAs.
+    # Default: one stream per group when a batch leaves most of the GPU idle (NBA <= half the SMs: the small-batch workloads c4 / c5,
+    # whose step would otherwise last as long as one window), a single stream when one batch already fills the GPU (c3: measured
+    # +0.8 % device-timed with three streams, and -11 % in the PCIe-bound host-buffer arm, where three batches of 148 CTAs in flight
+    # delay the front-end kernels the frame pipeline waits for).
+    sm_count = torch.cuda.get_device_properties(dev).multi_processor_count
+    NBS = max(1, min(N_WIN, args.ba_streams)) if args.ba_streams > 0 else (N_WIN if 2 * NBA <= sm_count else 1)
+    hnd_bas = [binding.Handle(cfg, NBA * N_WIN // NBS if N_WIN % NBS == 0 else NBA * N_WIN, local_rank) for _ in range(NBS)]
+    ext_stream_bas = [torch.cuda.ExternalStream(hb.stream(), device=dev) for hb in hnd_bas]
+    # group w lives on handle w % NBS, in the slot range of its ordinal among that handle's groups
+    ba_group_handle = [hnd_bas[w % NBS] for w in range(N_WIN)]
+    ba_group_seqs = [list(range((w // NBS) * NBA, (w // NBS + 1) * NBA)) for w in range(N_WIN)]
     for w in range(N_WIN):
-        hnd_ba.ba_upload(ba_group_seqs[w], ba_groups[w])
-    hnd_ba.synchronize()
+        ba_group_handle[w].ba_upload(ba_group_seqs[w], ba_groups[w])
+    for hb in hnd_bas:
+        hb.synchronize()
+    hnd_ba = hnd_bas[0]
     ext_stream = torch.cuda.ExternalStream(hnd.stream(), device=dev)
     seqs = list(range(S))          # local slots; global ids: shard_sequences(S, rank, world)
     # sequence s plays base s % nb with phase offset (s // nb) so that publish frames are staggered
@@ -507,23 +523,24 @@ def main():
         idxs, Rs, pubs, times = plans[k]
         hnd.enqueue_dev(seqs, d_steps[k % PERIOD].data_ptr(), binding.FMT_RGB8, times, Rs, pubs,
                         d_depth=d_steps_dep[k % PERIOD].data_ptr(), depth_fmt=binding.DEPTH_16UC1)
-        hnd_ba.ba_enqueue(ba_group_seqs[k % N_WIN])           # S/3 windows: solve + gauge fix + marginalization
+        ba_group_handle[k % N_WIN].ba_enqueue(ba_group_seqs[k % N_WIN])           # S/3 windows: solve + gauge fix + marginalization
 
     # ---- warm-up ----
     sampler = ClockSampler(local_rank)
     sampler.start()
     for k in range(args.warmup):
         run_dev_step(k)
-    hnd.synchronize(); hnd_ba.synchronize()
+    hnd.synchronize(); [hb.synchronize() for hb in hnd_bas]
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    l0 = hnd.launches + hnd_ba.launches
+    l0 = hnd.launches + sum(hb.launches for hb in hnd_bas)
     ev0 = torch.cuda.Event(enable_timing=True)
     ev1 = torch.cuda.Event(enable_timing=True)
     ev1b = torch.cuda.Event(enable_timing=True)
     ev0.record(ext_stream)
-    ext_stream_ba.wait_event(ev0)            # common start for both streams
+    for es in ext_stream_bas:
+        es.wait_event(ev0)                   # common start for all streams
     # NVTX ranges for the profiling recipe (tools/profile.sh): "vrf_timed" = the timed region, "vrf_profile_step" = one step of it
     nvtx = torch.cuda.nvtx if os.environ.get("VRF_NVTX") else None
     if nvtx:
@@ -537,12 +554,14 @@ def main():
     if nvtx:
         nvtx.range_pop()
     ev1.record(ext_stream)
-    ev1b.record(ext_stream_ba)
-    hnd.synchronize(); hnd_ba.synchronize()
+    ev1bs = [torch.cuda.Event(enable_timing=True) for _ in ext_stream_bas]
+    for e_, es in zip(ev1bs, ext_stream_bas):
+        e_.record(es)
+    hnd.synchronize(); [hb.synchronize() for hb in hnd_bas]
     torch.cuda.synchronize()
     clocks = sampler.stop()
-    launches = hnd.launches + hnd_ba.launches - l0
-    ms_total = max(ev0.elapsed_time(ev1), ev0.elapsed_time(ev1b))
+    launches = hnd.launches + sum(hb.launches for hb in hnd_bas) - l0
+    ms_total = max([ev0.elapsed_time(ev1)] + [ev0.elapsed_time(e_) for e_ in ev1bs])
     if world > 1:
         dist.barrier()
     ms_total_max, frames_total = aggregate_timing(ms_total, S * args.steps, dist if world > 1 else None, dev)
@@ -552,7 +571,7 @@ def main():
     # per-kernel CUDA events; the two streams are profiled one after the other so that a kernel's
     # duration is not inflated by waiting for SMs held by the other stream
     nprof = min(12, args.steps)
-    hnd.synchronize(); hnd_ba.synchronize()
+    hnd.synchronize(); [hb.synchronize() for hb in hnd_bas]
     hnd.profile(True); hnd.profile_read(reset=True)
     for k in range(args.warmup, args.warmup + nprof):
         idxs, Rs, pubs, times = plans[k]
@@ -560,12 +579,15 @@ def main():
                         d_depth=d_steps_dep[k % PERIOD].data_ptr(), depth_fmt=binding.DEPTH_16UC1)
     prof = hnd.profile_read(reset=True)
     hnd.profile(False)
-    hnd_ba.profile(True); hnd_ba.profile_read(reset=True)
-    for k in range(nprof):
-        hnd_ba.ba_enqueue(ba_group_seqs[k % N_WIN])
-    for kname, v in hnd_ba.profile_read(reset=True).items():
-        prof[kname] = (prof.get(kname, (0.0, 0))[0] + v[0], prof.get(kname, (0, 0))[1] + v[1])
-    hnd_ba.profile(False)
+    for hb in hnd_bas:
+        hb.profile(True); hb.profile_read(reset=True)
+    for k in range(nprof):                      # one batch at a time: a kernel's duration must not include waiting for SMs
+        ba_group_handle[k % N_WIN].ba_enqueue(ba_group_seqs[k % N_WIN])
+        ba_group_handle[k % N_WIN].synchronize()
+    for hb in hnd_bas:
+        for kname, v in hb.profile_read(reset=True).items():
+            prof[kname] = (prof.get(kname, (0.0, 0))[0] + v[0], prof.get(kname, (0, 0))[1] + v[1])
+        hb.profile(False)
     try:
         ba_all = [hnd_ba.debug_read("ba_prof", i, np.int64, 20) for i in range(min(NBA, 8))]
         ba_phase = ba_all[0][:8].tolist()
@@ -632,10 +654,18 @@ def main():
     # ---- e2e arm: host buffers through the C ABI (H2D + kernels + D2H per step) ----
     e2e_steps = 0 if (args.quick and not args.with_e2e) else max(3, min(args.steps, 20))
     hnd2 = binding.Handle(cfg, S, local_rank)
-    # processThread's handle (estimator_nodelet.cpp:61-62).  Different sequences publish on different frames, so
-    # consecutive BA batches belong to different sequences: two groups of NBA sequences alternate.
-    hnd2_ba = binding.Handle(cfg, 2 * NBA, local_rank)
-    ba_grp = [np.arange(NBA, dtype=np.int32), np.arange(NBA, 2 * NBA, dtype=np.int32)]
+    # processThread's handles (estimator_nodelet.cpp:61-62).  Different sequences publish on different frames, so
+    # consecutive BA batches belong to different groups of sequences: one handle / stream per group (like the device-timed
+    # arm above), batch k goes to handle k mod NBS2 and up to NBS2 batches are in flight.
+    # NBS == 1: one handle, two groups of NBA sequences alternate in its two pipeline slots (two batches in flight on one stream).
+    if NBS == 1:
+        hnd2_bas = [binding.Handle(cfg, 2 * NBA, local_rank)]
+        ba_slots = [(hnd2_bas[0], np.arange(NBA, dtype=np.int32)), (hnd2_bas[0], np.arange(NBA, 2 * NBA, dtype=np.int32))]
+    else:
+        hnd2_bas = [binding.Handle(cfg, NBA, local_rank) for _ in range(NBS)]
+        ba_slots = [(hb, np.arange(NBA, dtype=np.int32)) for hb in hnd2_bas]
+    NBS2 = len(ba_slots)
+    hnd2_ba = hnd2_bas[0]
 
     # everything the harness allocates is created once; the timed loop only moves data and calls the C ABI
     seq_np = np.asarray(seqs, np.int32)
@@ -656,12 +686,13 @@ def main():
 
     import threading
 
-    def run_host_ba(k, more):
-        # host problems in, optimised states out; two batches in flight (submit k+1, collect k)
+    def run_host_ba(k, k_last):
+        # host problems in, optimised states out; NBS2 batches in flight (submit k + NBS2 - 1, collect k)
         t_ = time.perf_counter()
-        if more:
-            hnd2_ba.ba_submit_into(ba_grp[(k + 1) % 2], ba_probs_c)
-        hnd2_ba.ba_collect_into(ba_grp[k % 2], ba_res_c)
+        kn = k + NBS2 - 1
+        if kn < k_last:
+            ba_slots[kn % NBS2][0].ba_submit_into(ba_slots[kn % NBS2][1], ba_probs_c)
+        ba_slots[k % NBS2][0].ba_collect_into(ba_slots[k % NBS2][1], ba_res_c)
         t_host["ba"] += time.perf_counter() - t_
 
     R_flat = [np.ascontiguousarray(pl[1].reshape(S, 9)) for pl in plans]
@@ -687,9 +718,10 @@ def main():
         n_out = 0
 
         def ba_loop():
-            hnd2_ba.ba_submit_into(ba_grp[k0 % 2], ba_probs_c)
+            for q in range(k0, min(k1, k0 + NBS2 - 1)):
+                ba_slots[q % NBS2][0].ba_submit_into(ba_slots[q % NBS2][1], ba_probs_c)
             for k in range(k0, k1):
-                run_host_ba(k, k + 1 < k1)
+                run_host_ba(k, k1)
 
         th = threading.Thread(target=ba_loop if part != "front" else (lambda: None))
         th.start()
@@ -751,7 +783,7 @@ def main():
             dist.barrier()
             dist.all_reduce(tg, op=dist.ReduceOp.MAX)
         e2e_gray_val = S * e2e_steps * world / float(tg.item())
-    hnd2.close(); hnd2_ba.close()
+    hnd2.close(); [hb.close() for hb in hnd2_bas]
 
     if rank == 0:
         line = {
@@ -763,7 +795,8 @@ def main():
                        "ba_inputs": "%d independent window chains x %d consecutive windows, cycled over the steps" % (n_ba_distinct, N_WIN),
                        "l2": "every step reads a different one of the %d HBM-resident frame batches (%d MB each incl. depth; the ring is %d MB >> the 126 MB L2)" % (
                            PERIOD, S * 5 * W * H // 2**20, PERIOD * S * 5 * W * H // 2**20),
-                       "parallelism": f"sequences sharded over {world} GPU(s), no data-path collective", "host_affinity": numa},
+                       "parallelism": f"sequences sharded over {world} GPU(s), no data-path collective", "host_affinity": numa,
+                       "ba_streams": f"{NBS} back-end handle(s) / stream(s) for the {N_WIN} publish-phase groups of sequences (independent estimators)"},
             "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": e2e_val, "unit": "frames/s", "h2d_bytes_per_step": S * 3 * W * H + (S // PUB_EVERY) * 2 * W * H + NBA * (ba_pack_bytes + 8 * (75 * 75 + 75 + 40 * 13)), "d2h_bytes_per_step": int(d2h)},
             "e2e_gray8": {"value": e2e_gray_val, "unit": "frames/s", "note": "same arm fed with MONO8 host frames (the FeatureTracker::readImage class-surface input)",
@@ -771,7 +804,7 @@ def main():
             "roofline": roof, "cpu_baseline": cpu_base,
         }
         emit(line)
-    hnd.close(); hnd_ba.close()
+    hnd.close(); [hb.close() for hb in hnd_bas]
     if world > 1:
         dist.destroy_process_group()
 
