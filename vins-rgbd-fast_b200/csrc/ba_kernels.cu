@@ -979,14 +979,29 @@ k_ba_solve(const BaMeta *metas, const BaProbDev *probs, BaOutDev *outs)
                     for (int b = lane; b <= a; b += 32) hv += row[b] * sh.tmp[b] * (b == a ? 1.0 : 2.0);
                     v += sh.tmp[a] * hv;
                 }
-                for (int l = warp; l < M; l += nwarp) {
-                    if (p.lm_const[l]) continue;
-                    const double *Wl = p.W + (size_t)l * BA_WS;
-                    const double sl = p.jscale_l[l];
-                    double wv = 0;
-                    for (int k = lane; k < ws; k += 32) wv += wsc(sh, Wl, k, sl) * sh.tmp[wcol(k)];
-                    wv = warp_sum_d(wv);
-                    if (lane == 0) v += 2.0 * p.u_l[l] * wv + p.hll[l] * p.u_l[l] * p.u_l[l];
+                // (four landmarks per pass: their coupling rows live in L2, ~700 cycles away -- the loads of a pass are issued together
+                // and the four shuffle reductions interleave; the sums are added in landmark order as before)
+                for (int l0 = warp; l0 < M; l0 += 4 * nwarp) {
+                    double wv[4];
+                    bool on[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int l = l0 + u * nwarp;
+                        on[u] = l < M && !p.lm_const[l];
+                        wv[u] = 0;
+                        if (on[u]) {
+                            const double *Wl = p.W + (size_t)l * BA_WS;
+                            const double sl = p.jscale_l[l];
+                            for (int k = lane; k < ws; k += 32) wv[u] += wsc(sh, Wl, k, sl) * sh.tmp[wcol(k)];
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) wv[u] = warp_sum_d(wv[u]);
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int l = l0 + u * nwarp;
+                        if (on[u] && lane == 0) v += 2.0 * p.u_l[l] * wv[u] + p.hll[l] * p.u_l[l] * p.u_l[l];
+                    }
                 }
                 Quu = block_sum(v, sh.red);
                 double gsq = 0;
@@ -1027,14 +1042,22 @@ k_ba_solve(const BaMeta *metas, const BaProbDev *probs, BaOutDev *outs)
                     // parked in the (idle) tile buffer and added by one thread per column in warp order
                     double *part = reinterpret_cast<double *>(sh.imuJ);      // [nwarp][96]
                     double a0 = 0, a1 = 0, a2 = 0;
-                    for (int l = warp; l < M; l += nwarp) {
-                        if (p.lm_const[l]) continue;
-                        if (!(p.hll[l] + mu * p.diag_l[l] * p.diag_l[l] > 0)) continue;
-                        const double *Wl = p.W + (size_t)l * BA_WS;
-                        const double gl_h = p.y_l[l], sl = p.jscale_l[l];
-                        a0 += wsc(sh, Wl, lane, sl) * gl_h;
-                        a1 += wsc(sh, Wl, lane + 32, sl) * gl_h;
-                        if (lane + 64 < ws) a2 += wsc(sh, Wl, lane + 64, sl) * gl_h;
+                    for (int l0 = warp; l0 < M; l0 += 4 * nwarp) {
+                        double w0[4], w1[4], w2[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {                  // the four rows' loads in flight together
+                            const int l = l0 + u * nwarp;
+                            w0[u] = 0; w1[u] = 0; w2[u] = 0;
+                            if (l < M && !p.lm_const[l] && (p.hll[l] + mu * p.diag_l[l] * p.diag_l[l] > 0)) {
+                                const double *Wl = p.W + (size_t)l * BA_WS;
+                                const double gl_h = p.y_l[l], sl = p.jscale_l[l];
+                                w0[u] = wsc(sh, Wl, lane, sl) * gl_h;
+                                w1[u] = wsc(sh, Wl, lane + 32, sl) * gl_h;
+                                if (lane + 64 < ws) w2[u] = wsc(sh, Wl, lane + 64, sl) * gl_h;
+                            }
+                        }
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) { a0 += w0[u]; a1 += w1[u]; a2 += w2[u]; }
                     }
                     part[warp * 96 + lane] = a0; part[warp * 96 + 32 + lane] = a1; part[warp * 96 + 64 + lane] = a2;
                     __syncthreads();
@@ -1065,11 +1088,29 @@ k_ba_solve(const BaMeta *metas, const BaProbDev *probs, BaOutDev *outs)
                     double acc[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
                     for (int t0 = 0; t0 < M; t0 += tl) {
                         const int nt = min(tl, M - t0);
-                        for (int lr = warp; lr < nt; lr += nwarp) {
-                            const int l = t0 + lr;
-                            const double sc_ = p.lm_const[l] ? 0.0 : p.shinv_l[l], sl = p.jscale_l[l];
-                            const double *Wl = p.W + (size_t)l * BA_WS;
-                            for (int k = lane; k < wsp; k += 32) tile[lr * wsp + k] = k < ws ? wsc(sh, Wl, k, sl) * sc_ : 0.0;
+                        for (int lr0 = warp; lr0 < nt; lr0 += 4 * nwarp) {
+                            double wq[4][3];
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) {              // four rows' loads in flight together (wsp <= 75: three entries per lane)
+                                const int lr = lr0 + u * nwarp;
+#pragma unroll
+                                for (int q = 0; q < 3; ++q) wq[u][q] = 0.0;
+                                if (lr < nt) {
+                                    const int l = t0 + lr;
+                                    const double sc_ = p.lm_const[l] ? 0.0 : p.shinv_l[l], sl = p.jscale_l[l];
+                                    const double *Wl = p.W + (size_t)l * BA_WS;
+#pragma unroll
+                                    for (int q = 0; q < 3; ++q) { const int k = lane + 32 * q; if (k < ws) wq[u][q] = wsc(sh, Wl, k, sl) * sc_; }
+                                }
+                            }
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) {
+                                const int lr = lr0 + u * nwarp;
+                                if (lr < nt) {
+#pragma unroll
+                                    for (int q = 0; q < 3; ++q) { const int k = lane + 32 * q; if (k < wsp) tile[lr * wsp + k] = wq[u][q]; }
+                                }
+                            }
                         }
                         __syncthreads();
                         if (actv) {
@@ -1252,16 +1293,25 @@ k_ba_solve(const BaMeta *metas, const BaProbDev *probs, BaOutDev *outs)
                     fin = block_sum(fin, sh.red);
                     if (fin == 0) {
                         // back-substitute the landmarks: y_l = (g_l - w_l . y_c) / h_l
-                        for (int l = warp; l < M; l += nwarp) {
-                            double v = 0;
-                            if (!p.lm_const[l]) {
-                                const double *Wl = p.W + (size_t)l * BA_WS;
-                                const double sl = p.jscale_l[l];
-                                for (int k = lane; k < ws; k += 32) v += wsc(sh, Wl, k, sl) * sh.y[wcol(k)];
-                                v = warp_sum_d(v);
-                                v = (p.gl[l] - v) * p.hinv_l[l];
+                        for (int l0 = warp; l0 < M; l0 += 4 * nwarp) {
+                            double v[4];
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) {              // the four rows' loads in flight together
+                                const int l = l0 + u * nwarp;
+                                v[u] = 0;
+                                if (l < M && !p.lm_const[l]) {
+                                    const double *Wl = p.W + (size_t)l * BA_WS;
+                                    const double sl = p.jscale_l[l];
+                                    for (int k = lane; k < ws; k += 32) v[u] += wsc(sh, Wl, k, sl) * sh.y[wcol(k)];
+                                }
                             }
-                            if (lane == 0) p.y_l[l] = v;
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) v[u] = warp_sum_d(v[u]);
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) {
+                                const int l = l0 + u * nwarp;
+                                if (l < M && lane == 0) p.y_l[l] = p.lm_const[l] ? 0.0 : (p.gl[l] - v[u]) * p.hinv_l[l];
+                            }
                         }
                         solved = true;
                     }
