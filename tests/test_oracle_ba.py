@@ -420,8 +420,14 @@ class DenseCeresRestatement:
     packed storage, its own line search -- used to cross-check oracle/ba_ref.c::solve.  Only the single-factor evaluations
     (projection / IMU / prior residuals and Jacobians, pinned by the finite-difference tests above) are shared with the C oracle."""
 
-    def __init__(self, cfg, pb):
+    def __init__(self, cfg, pb, use_imu=True):
         self.cfg, self.pb, self.M = cfg, pb, pb.M
+        # VO mode (USE_IMU = 0): no IMU factors, no speed-bias blocks, para_Pose[0] constant (estimator.cpp:1174-1185): constant blocks
+        # are not part of the Ceres program -- their columns do not exist
+        self.use_imu = use_imu
+        self.active = np.ones(165 + pb.M, bool)
+        if not use_imu:
+            self.active[0:6] = False; self.active[66:165] = False
         self.ub = np.where(pb.flag == 2, 2.0 / cfg.depth_max_dist, np.inf)
         self.NT = 165 + self.M
         P = pb.prior
@@ -434,10 +440,12 @@ class DenseCeresRestatement:
                 ls = 6 if b.size == 7 else b.size
                 if b.kind == B.BLK_POSE: cols[b.idx:b.idx + ls] = 6 * b.index + np.arange(ls)
                 elif b.kind == B.BLK_SPEEDBIAS: cols[b.idx:b.idx + ls] = 66 + 9 * b.index + np.arange(ls)
-            self.pcols = cols                      # the ex-pose block is constant: its columns drop out
+            cols[cols >= 0] = np.where(self.active[cols[cols >= 0]], cols[cols >= 0], -1)
+            self.pcols = cols                      # constant blocks (ex-pose; pose 0 / speed-bias in VO mode): their columns drop out
 
     def plus(self, x, d):
         pose, sb, lam = x
+        d = np.where(self.active, d, 0.0)
         pose2 = np.array([pose_plus(pose[f], d[6 * f:6 * f + 6]) for f in range(11)])
         sb2 = sb + d[66:165].reshape(11, 9)
         lam2 = np.minimum(lam + d[165:], self.ub)                       # ParameterBlock::Plus projects onto the bounds
@@ -458,7 +466,7 @@ class DenseCeresRestatement:
                     J = np.zeros((2, self.NT))
                     J[:, 6 * i:6 * i + 6] = w * Ji[:, :6]; J[:, 6 * (i + k):6 * (i + k) + 6] = w * Jj[:, :6]; J[:, 165 + l] = w * Jf
                     rows_J.append(J); rows_r.append(w * r)
-        for j in range(1, 11):
+        for j in range(1, 11 if self.use_imu else 0):
             r, Jpi, Jsi, Jpj, Jsj = ba_ref.imu_eval(pb.imu[j - 1], pose[j - 1], sb[j - 1], pose[j], sb[j], jac=jac)
             cost += 0.5 * r @ r
             if jac:
@@ -476,11 +484,14 @@ class DenseCeresRestatement:
                 rows_J.append(J); rows_r.append(r)
         if not jac:
             return cost
-        return cost, np.vstack(rows_J), np.concatenate(rows_r)
+        J = np.vstack(rows_J)
+        J[:, ~self.active] = 0.0
+        return cost, J, np.concatenate(rows_r)
 
-    @staticmethod
-    def ambient(x):
-        return np.concatenate([x[0].ravel(), x[1].ravel(), x[2]])
+    def ambient(self, x):
+        """the non-constant parameter blocks in the ambient parameterisation (what Ceres' step / parameter norms run over)"""
+        pose = x[0] if self.use_imu else x[0][1:]
+        return np.concatenate([pose.ravel(), x[1].ravel() if self.use_imu else np.zeros(0), x[2]])
 
     def line_search(self, x, delta, x_cost, gts, cand_cost):
         """TrustRegionMinimizer::DoLineSearch / ArmijoLineSearch::DoSearch with CUBIC interpolation (numpy polynomial tools)."""
@@ -612,3 +623,23 @@ def test_oracle_solver_matches_an_independent_dense_restatement(seed, nlm, min_l
         n_ls += dn["line_searches"]; n_short += dn["shortened"]
         sim.commit(a, so)
     assert n_ls >= min_ls and n_short >= min_short, (n_ls, n_short)
+
+
+def test_oracle_solver_matches_the_dense_restatement_in_vo_mode():
+    """USE_IMU = 0: projection factors + prior only, para_Pose[0] constant (estimator.cpp:1182-1185) -- its Jacobian columns must
+    not exist in the normal equations (r1 kept them and only ignored the update, which changes the step of every other block)."""
+    cfg = make_cfg()
+    cfg.use_imu = 0
+    sim = BP.WindowSimulator(15, cfg, n_landmarks=30, flag2_frac=0.2)
+    for a in range(3):
+        pb = sim.window(a)
+        pb.c.use_imu = 0
+        so = ba_ref.solve(cfg, pb)
+        if a > 0:
+            dn = DenseCeresRestatement(cfg, pb, use_imu=False).solve(max_iter=8)
+            assert (so.c.iterations, so.c.successful_steps, so.c.termination) == (dn["iterations"], dn["successful"], dn["termination"]), (a, dn["trace"])
+            assert so.c.armijo_failures == dn["line_searches"], a
+            assert abs(so.c.final_cost - dn["cost"]) <= 1e-7 * dn["cost"], (a, so.c.final_cost, dn["cost"])
+            assert np.abs(so.pose - dn["x"][0]).max() <= 1e-6 and np.abs(so.lam[:pb.M] - dn["x"][2]).max() <= 1e-6, a
+            assert np.array_equal(so.pose[0], pb.pose[0])
+        sim.commit(a, so)
