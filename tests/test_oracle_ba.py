@@ -418,18 +418,24 @@ class DenseCeresRestatement:
     """A second, structurally independent statement of the solver the reference configures (ceres::Solve with DENSE_SCHUR + DOGLEG,
     Ceres defaults otherwise, estimator.cpp:1348-1363) -- dense numpy linear algebra on the full Jacobian, no Schur complement, no
     packed storage, its own line search -- used to cross-check oracle/ba_ref.c::solve.  Only the single-factor evaluations
-    (projection / IMU / prior residuals and Jacobians, pinned by the finite-difference tests above) are shared with the C oracle."""
+    (projection / IMU / prior residuals and Jacobians, pinned by the finite-difference tests above) are shared with the C oracle.
+    Tangent layout: pose f -> 6 f, speed-bias f -> 66 + 9 f, ex-pose -> 165, td -> 171, landmark l -> 172 + l; x = (pose, sb, lam, ex, td)."""
+
+    NC = 172
 
     def __init__(self, cfg, pb, use_imu=True):
         self.cfg, self.pb, self.M = cfg, pb, pb.M
-        # VO mode (USE_IMU = 0): no IMU factors, no speed-bias blocks, para_Pose[0] constant (estimator.cpp:1174-1185): constant blocks
-        # are not part of the Ceres program -- their columns do not exist
+        self.ub = np.where(pb.flag == 2, 2.0 / cfg.depth_max_dist, np.inf)
+        self.NT = self.NC + self.M
+        self.td_factor = bool(cfg.estimate_td)
+        # Constant blocks are not part of the Ceres program -- their columns do not exist: the ex-pose / td unless they are estimated
+        # (estimator.cpp:1186-1212); in VO mode (USE_IMU = 0: no IMU factors) the speed-bias blocks and para_Pose[0] (:1174-1185)
         self.use_imu = use_imu
-        self.active = np.ones(165 + pb.M, bool)
+        self.active = np.ones(self.NT, bool)
+        self.active[165:171] = not pb.c.ex_constant
+        self.active[171] = self.td_factor and not (use_imu and pb.c.td_constant)
         if not use_imu:
             self.active[0:6] = False; self.active[66:165] = False
-        self.ub = np.where(pb.flag == 2, 2.0 / cfg.depth_max_dist, np.inf)
-        self.NT = 165 + self.M
         P = pb.prior
         self.pcols = None
         if P is not None:
@@ -438,33 +444,44 @@ class DenseCeresRestatement:
             cols = np.full(n, -1)
             for b in P.blocks[: P.n_blocks]:
                 ls = 6 if b.size == 7 else b.size
-                if b.kind == B.BLK_POSE: cols[b.idx:b.idx + ls] = 6 * b.index + np.arange(ls)
-                elif b.kind == B.BLK_SPEEDBIAS: cols[b.idx:b.idx + ls] = 66 + 9 * b.index + np.arange(ls)
+                base = {B.BLK_POSE: 6 * b.index, B.BLK_SPEEDBIAS: 66 + 9 * b.index, B.BLK_EXPOSE: 165, B.BLK_TD: 171}[b.kind]
+                cols[b.idx:b.idx + ls] = base + np.arange(ls)
             cols[cols >= 0] = np.where(self.active[cols[cols >= 0]], cols[cols >= 0], -1)
-            self.pcols = cols                      # constant blocks (ex-pose; pose 0 / speed-bias in VO mode): their columns drop out
+            self.pcols = cols
+
+    def start(self):
+        pb = self.pb
+        return (pb.pose.copy(), pb.sb.copy(), np.minimum(pb.lam.copy(), self.ub), np.array(pb.ex, float), float(pb.td))
 
     def plus(self, x, d):
-        pose, sb, lam = x
+        pose, sb, lam, ex, td = x
         d = np.where(self.active, d, 0.0)
         pose2 = np.array([pose_plus(pose[f], d[6 * f:6 * f + 6]) for f in range(11)])
         sb2 = sb + d[66:165].reshape(11, 9)
-        lam2 = np.minimum(lam + d[165:], self.ub)                       # ParameterBlock::Plus projects onto the bounds
-        return pose2, sb2, lam2
+        lam2 = np.minimum(lam + d[172:], self.ub)                       # ParameterBlock::Plus projects onto the bounds
+        return pose2, sb2, lam2, pose_plus(ex, d[165:171]), td + d[171]
 
     def evaluate(self, x, jac=True):
-        pose, sb, lam = x
+        pose, sb, lam, ex, td = x
         pb, M = self.pb, self.M
         rows_r, rows_J, cost = [], [], 0.0
         for l in range(M):
             o0, i = pb.obs_ptr[l], pb.start[l]
             for k in range(1, pb.obs_ptr[l + 1] - o0):
-                r, Ji, Jj, Je, Jf = ba_ref.projection_eval(pose[i], pose[i + k], pb.ex, lam[l], pb.obs_pts[o0], pb.obs_pts[o0 + k], jac=jac)
+                Jt = np.zeros(2)
+                if self.td_factor:
+                    r, Ji, Jj, Je, Jf, Jt = ba_ref.projection_td_eval(
+                        pose[i], pose[i + k], ex, lam[l], td, pb.obs_pts[o0], pb.obs_pts[o0 + k], pb.obs_vel[o0], pb.obs_vel[o0 + k],
+                        pb.obs_cur_td[o0], pb.obs_cur_td[o0 + k], pb.obs_row[o0], pb.obs_row[o0 + k], self.cfg.tr / self.cfg.row, jac=jac)
+                else:
+                    r, Ji, Jj, Je, Jf = ba_ref.projection_eval(pose[i], pose[i + k], ex, lam[l], pb.obs_pts[o0], pb.obs_pts[o0 + k], jac=jac)
                 s = r @ r
                 cost += 0.5 * np.log1p(s)
                 if jac:
                     w = np.sqrt(1.0 / (1.0 + s))          # CauchyLoss: rho'' < 0 => the Corrector is the plain sqrt(rho') scaling
                     J = np.zeros((2, self.NT))
-                    J[:, 6 * i:6 * i + 6] = w * Ji[:, :6]; J[:, 6 * (i + k):6 * (i + k) + 6] = w * Jj[:, :6]; J[:, 165 + l] = w * Jf
+                    J[:, 6 * i:6 * i + 6] = w * Ji[:, :6]; J[:, 6 * (i + k):6 * (i + k) + 6] = w * Jj[:, :6]; J[:, 172 + l] = w * Jf
+                    J[:, 165:171] = w * Je[:, :6]; J[:, 171] = w * Jt
                     rows_J.append(J); rows_r.append(w * r)
         for j in range(1, 11 if self.use_imu else 0):
             r, Jpi, Jsi, Jpj, Jsj = ba_ref.imu_eval(pb.imu[j - 1], pose[j - 1], sb[j - 1], pose[j], sb[j], jac=jac)
@@ -475,7 +492,7 @@ class DenseCeresRestatement:
                 J[:, 6 * j:6 * j + 6] = Jpj[:, :6]; J[:, 66 + 9 * j:66 + 9 * j + 9] = Jsj
                 rows_J.append(J); rows_r.append(r)
         if self.pcols is not None:
-            r = ba_ref.prior_residual(pb.prior, pose, sb, pb.ex)
+            r = ba_ref.prior_residual(pb.prior, pose, sb, ex, td)
             cost += 0.5 * r @ r
             if jac:
                 J = np.zeros((len(r), self.NT))
@@ -491,13 +508,16 @@ class DenseCeresRestatement:
     def ambient(self, x):
         """the non-constant parameter blocks in the ambient parameterisation (what Ceres' step / parameter norms run over)"""
         pose = x[0] if self.use_imu else x[0][1:]
-        return np.concatenate([pose.ravel(), x[1].ravel() if self.use_imu else np.zeros(0), x[2]])
+        parts = [pose.ravel(), x[1].ravel() if self.use_imu else np.zeros(0), x[2]]
+        if self.active[165]: parts.append(x[3])
+        if self.active[171]: parts.append(np.array([x[4]]))
+        return np.concatenate(parts)
 
     def line_search(self, x, delta, x_cost, gts, cand_cost):
         """TrustRegionMinimizer::DoLineSearch / ArmijoLineSearch::DoSearch with CUBIC interpolation (numpy polynomial tools)."""
         dmax = np.abs(delta).max()
         samples = [(0.0, x_cost, gts)]
-        cur = None
+        cur = prev = None
         t = 1.0
         for it in range(20):
             if it > 0:
@@ -513,8 +533,7 @@ class DenseCeresRestatement:
         return None
 
     def solve(self, max_iter=8):
-        pb = self.pb
-        x = (pb.pose.copy(), pb.sb.copy(), np.minimum(pb.lam.copy(), self.ub))      # TrustRegionMinimizer::Init projects the start point
+        x = self.start()                                  # TrustRegionMinimizer::Init projects the start point onto the bounds
         x_cost, J, r = self.evaluate(x)
         jscale = 1.0 / (1.0 + np.sqrt((J * J).sum(0)))
         constrained = bool(np.isfinite(self.ub).any())
@@ -642,4 +661,27 @@ def test_oracle_solver_matches_the_dense_restatement_in_vo_mode():
             assert abs(so.c.final_cost - dn["cost"]) <= 1e-7 * dn["cost"], (a, so.c.final_cost, dn["cost"])
             assert np.abs(so.pose - dn["x"][0]).max() <= 1e-6 and np.abs(so.lam[:pb.M] - dn["x"][2]).max() <= 1e-6, a
             assert np.array_equal(so.pose[0], pb.pose[0])
+        sim.commit(a, so)
+
+
+@pytest.mark.parametrize("ex_constant,td_constant", [(0, 0), (1, 0), (0, 1)])
+def test_oracle_solver_matches_the_dense_restatement_with_td_and_extrinsic(ex_constant, td_constant):
+    """ESTIMATE_TD (ProjectionTdFactor) with para_Td and / or para_Ex_Pose variable: the extra tangent columns (165..171), their
+    prior blocks and the constant-block handling of the C solver against the dense statement."""
+    cfg = make_cfg()
+    cfg.estimate_td = 1; cfg.tr = 0.02; cfg.row = 480
+    sim = BP.WindowSimulator(33, cfg, n_landmarks=30, td_true=0.02, td_constant=td_constant, ex_constant=ex_constant,
+                             ex_perturb=0.0 if ex_constant else 0.02, tic=np.array([0.05, -0.03, 0.02]), flag2_frac=0.2)
+    sol0 = ba_ref.solve(cfg, sim.window(0)); sim.commit(0, sol0)
+    for a in (1, 2):
+        pb = sim.window(a)
+        so = ba_ref.solve(cfg, pb)
+        dn = DenseCeresRestatement(cfg, pb).solve(max_iter=8)
+        assert (so.c.iterations, so.c.successful_steps, so.c.termination) == (dn["iterations"], dn["successful"], dn["termination"]), (a, dn["trace"])
+        assert so.c.armijo_failures == dn["line_searches"], a
+        assert abs(so.c.final_cost - dn["cost"]) <= 1e-7 * dn["cost"], (a, so.c.final_cost, dn["cost"])
+        assert np.abs(so.pose - dn["x"][0]).max() <= 1e-6 and np.abs(so.lam[:pb.M] - dn["x"][2]).max() <= 1e-6, a
+        assert np.abs(so.ex - dn["x"][3]).max() <= 1e-6 and abs(so.td - dn["x"][4]) <= 1e-7, a
+        if not ex_constant: assert np.abs(so.ex - pb.ex).max() > 1e-6
+        if not td_constant: assert abs(so.td - pb.td) > 1e-7
         sim.commit(a, so)
