@@ -685,3 +685,44 @@ def test_oracle_solver_matches_the_dense_restatement_with_td_and_extrinsic(ex_co
         if not ex_constant: assert np.abs(so.ex - pb.ex).max() > 1e-6
         if not td_constant: assert abs(so.td - pb.td) > 1e-7
         sim.commit(a, so)
+
+
+def test_margin_second_new_matches_independent_numpy_schur():
+    """MARGIN_SECOND_NEW (estimator.cpp:1504-1575): the new prior is the old prior with para_Pose[WINDOW_SIZE - 1] marginalised out
+    -- only the MarginalizationFactor enters, linearised at the states after the gauge fix.  Independent numpy statement: A = J0^T J0,
+    b = J0^T r(x), pseudo-inverse Schur complement of the dropped 6 columns (marginalization_factor.cpp:273-296)."""
+    cfg = make_cfg()
+    sim = BP.WindowSimulator(23, cfg, n_landmarks=60)
+    sol = ba_ref.solve(cfg, sim.window(0)); sim.commit(0, sol)
+    pb = sim.window(1, marg_flag=B.MARGIN_SECOND_NEW)
+    P = pb.prior
+    assert any(b.kind == B.BLK_POSE and b.index == 9 for b in P.blocks[: P.n_blocks])
+    sol = ba_ref.solve(cfg, pb)
+    assert sol.c.has_new_prior == 1
+    x_pose = np.zeros((11, 7)); x_sb = np.zeros((11, 9))
+    for i in range(11):
+        x_pose[i, :3] = sol.Ps[i]; x_pose[i, 3:] = BP.R_to_quat(sol.Rs[i])
+        x_sb[i] = np.concatenate([sol.Vs[i], sol.Bas[i], sol.Bgs[i]])
+    n = P.n
+    J0 = np.ctypeslib.as_array(P.linearized_jacobians)[: n * n].reshape(n, n)
+    r = ba_ref.prior_residual(P, x_pose, x_sb, pb.ex)
+    A, bv = J0.T @ J0, J0.T @ r
+    drop = np.zeros(n, bool)
+    old_cols = {}
+    for b in P.blocks[: P.n_blocks]:
+        ls = 6 if b.size == 7 else b.size
+        if b.kind == B.BLK_POSE and b.index == 9: drop[b.idx:b.idx + ls] = True
+        old_cols[(b.kind, b.index)] = np.arange(b.idx, b.idx + ls)
+    # kept columns in the order of the new prior's block table (indices unchanged: only frames >= WINDOW_SIZE - 1 shift, :1546-1560)
+    keep = np.concatenate([old_cols[(k, i)] for (k, i, s_, ix, x0) in BP.prior_blocks(sol.new_prior)])
+    assert sorted(keep.tolist()) == np.nonzero(~drop)[0].tolist()
+    Amm = 0.5 * (A[np.ix_(drop, drop)] + A[np.ix_(drop, drop)].T)
+    w, V = np.linalg.eigh(Amm)
+    Ainv = (V * np.where(w > 1e-8, 1.0 / np.where(w > 1e-8, w, 1.0), 0.0)) @ V.T
+    Arm = A[np.ix_(keep, np.nonzero(drop)[0])]
+    Ar = A[np.ix_(keep, keep)] - Arm @ Ainv @ Arm.T
+    br = bv[keep] - Arm @ Ainv @ bv[drop]
+    JtJ, Jtr = BP.prior_normal_equations(sol.new_prior)
+    assert JtJ.shape == Ar.shape
+    assert np.abs(JtJ - Ar).max() <= 1e-7 * np.abs(Ar).max()
+    assert np.abs(Jtr - br).max() <= 1e-7 * max(1.0, np.abs(br).max())
