@@ -755,3 +755,72 @@ def test_preintegration_bias_jacobians_match_repropagation():
         dq2 = np.array(pre2.delta_q)
         assert min(np.abs(dq2 - dq_pred).max(), np.abs(dq2 + dq_pred).max()) <= 2e-9, k
         assert np.abs(np.array(pre2.delta_p) - dp0).max() > 1e-8 or k >= 3       # the perturbation really moved the result
+
+
+def test_preintegration_covariance_matches_numerical_error_propagation():
+    """IntegrationBase::midPointIntegration propagates the 15 x 15 error-state covariance with analytic F and V
+    (integration_base.h:96-162): P' = F P F^T + V N V^T, N = diag(ACC_N^2, GYR_N^2, ACC_N^2, GYR_N^2, ACC_W^2, GYR_W^2).
+    Independent check: an own numpy midpoint integrator, F and V of every step by central differences on the error state
+    [d_alpha, d_theta (right-multiplied), d_beta, d_ba, d_bg] and on the four measurement noises, same recursion."""
+    cfg = make_cfg()
+    rng = np.random.default_rng(12)
+    n, dt = 20, 0.005
+    acc = [np.array([0.3, -0.2, 9.7]) + rng.normal(0, 0.5, 3) for _ in range(n + 1)]
+    gyr = [np.array([0.1, 0.3, -0.2]) + rng.normal(0, 0.2, 3) for _ in range(n + 1)]
+    ba, bg = np.array([0.02, -0.01, 0.015]), np.array([0.003, -0.002, 0.001])
+    pre = ba_ref.preintegrate([(dt, acc[i], gyr[i]) for i in range(1, n + 1)], acc[0], gyr[0], ba, bg, cfg)
+
+    def qmul(a, b):
+        return np.concatenate([a[3] * b[:3] + b[3] * a[:3] + np.cross(a[:3], b[:3]), [a[3] * b[3] - a[:3] @ b[:3]]])
+
+    def qrot(q, v):
+        return v + 2.0 * np.cross(q[:3], np.cross(q[:3], v) + q[3] * v)
+
+    def step(state, a0, w0, a1, w1):
+        al, q, be, ba_, bg_ = state
+        ua0 = qrot(q, a0 - ba_)
+        ug = 0.5 * (w0 + w1) - bg_
+        q2 = qmul(q, np.concatenate([ug * dt / 2.0, [1.0]]))
+        ua = 0.5 * (ua0 + qrot(q2, a1 - ba_))          # (the reference rotates with the not yet normalised product, :74-76,190)
+        return (al + be * dt + 0.5 * ua * dt * dt, q2 / np.linalg.norm(q2), be + ua * dt, ba_, bg_)
+
+    def perturb(state, e):          # error state -> state
+        al, q, be, ba_, bg_ = state
+        q2 = qmul(q, np.concatenate([0.5 * e[3:6], [1.0]])); q2 /= np.linalg.norm(q2)
+        return (al + e[0:3], q2, be + e[6:9], ba_ + e[9:12], bg_ + e[12:15])
+
+    def err(nom, st):               # state -> error state around nom
+        qi = np.concatenate([-nom[1][:3], [nom[1][3]]])
+        dq = qmul(qi, st[1])
+        return np.concatenate([st[0] - nom[0], 2.0 * dq[:3] * np.sign(dq[3]), st[2] - nom[2], st[3] - nom[3], st[4] - nom[4]])
+
+    N = np.diag(np.repeat([cfg.acc_n ** 2, cfg.gyr_n ** 2, cfg.acc_n ** 2, cfg.gyr_n ** 2, cfg.acc_w ** 2, cfg.gyr_w ** 2], 3))
+    state = (np.zeros(3), np.array([0, 0, 0, 1.0]), np.zeros(3), ba, bg)
+    Pc = np.zeros((15, 15))
+    h = 1e-6
+    for k in range(1, n + 1):
+        a0, w0, a1, w1 = acc[k - 1], gyr[k - 1], acc[k], gyr[k]
+        nxt = step(state, a0, w0, a1, w1)
+        F = np.zeros((15, 15)); V = np.zeros((15, 18))
+        for c in range(15):
+            e = np.zeros(15); e[c] = h
+            F[:, c] = (err(nxt, step(perturb(state, e), a0, w0, a1, w1)) - err(nxt, step(perturb(state, -e), a0, w0, a1, w1))) / (2 * h)
+        for c in range(12):
+            d = np.zeros(12); d[c] = h
+            V[:, c] = (err(nxt, step(state, a0 + d[0:3], w0 + d[3:6], a1 + d[6:9], w1 + d[9:12])) -
+                       err(nxt, step(state, a0 - d[0:3], w0 - d[3:6], a1 - d[6:9], w1 - d[9:12]))) / (2 * h)
+        V[9:12, 12:15] = np.eye(3) * dt; V[12:15, 15:18] = np.eye(3) * dt          # bias random walks
+        Pc = F @ Pc @ F.T + V @ N @ V.T
+        state = nxt
+    # the integrators agree ...
+    assert np.abs(np.array(pre.delta_p) - state[0]).max() <= 1e-12 and np.abs(np.array(pre.delta_v) - state[2]).max() <= 1e-12
+    dq = np.array(pre.delta_q)
+    assert min(np.abs(dq - state[1]).max(), np.abs(dq + state[1]).max()) <= 1e-12
+    # ... and so do the covariances.  The reference's F is first order in dt in its rotation blocks (I - [w]x dt for exp(-[w]x dt),
+    # integration_base.h:104-127), the central differences are exact derivatives of the discrete step: they differ at
+    # O((|w| dt)^2) per step, a few 1e-5 of sqrt(P_ii P_jj) after 20 steps; a wrong block or sign would show at O(1).
+    cov = np.array(pre.covariance).reshape(15, 15)
+    scale = np.sqrt(np.outer(np.diag(cov), np.diag(cov)))
+    assert np.abs(cov - Pc).max() <= 1e-6 * np.abs(cov).max()
+    assert np.abs((cov - Pc) / scale).max() <= 2e-4
+    assert np.abs(np.diag(cov) / np.diag(Pc) - 1.0).max() <= 1e-4
